@@ -1,0 +1,208 @@
+"""ctypes mirror of include/lvio2d.h (the C ABI of the B200 front-end solver).
+
+Pure declarations: the structs are shared by the product host code (solver.py) and by the test-side
+oracle wrapper (tests/oracle_lib.py) so both sides receive byte-identical inputs.
+"""
+import ctypes as C
+
+import numpy as np
+
+ABI_VERSION = 1
+STATE_DIM = 15
+IMU_BLOB = 466
+WHEEL_BLOB = 15
+LASER_BLOCK = 28
+
+OK = 0
+ERR_INVALID_ARG, ERR_NO_DEVICE, ERR_CUDA, ERR_NO_WINDOW, ERR_DOMAIN, ERR_ALLOC = -1, -2, -3, -4, -5, -6
+
+CONST_P, CONST_Q, CONST_V, CONST_BS = 1, 2, 4, 8
+
+TERM_NO_CONVERGENCE = 0
+TERM_CONVERGENCE_FUNCTION = 1
+TERM_CONVERGENCE_PARAMETER = 2
+TERM_CONVERGENCE_GRADIENT = 3
+TERM_CONVERGENCE_RADIUS = 4
+TERM_FAILURE = 5
+
+c_double_p = C.POINTER(C.c_double)
+c_int32_p = C.POINTER(C.c_int32)
+c_int64_p = C.POINTER(C.c_int64)
+c_uint8_p = C.POINTER(C.c_uint8)
+
+
+class Params(C.Structure):
+    """lvio2d_params (include/lvio2d.h)."""
+
+    _fields_ = [
+        ("abi_version", C.c_int32),
+        ("device", C.c_int32),
+        ("T_imu_to_laser", C.c_double * 12),
+        ("T_imu_to_wheel", C.c_double * 12),
+        ("g", C.c_double),
+        ("line_to_line_sigma", C.c_double),
+        ("manifold_p_sigma", C.c_double),
+        ("manifold_q_sigma", C.c_double),
+        ("imu_noise_acc_sigma", C.c_double * 3),
+        ("imu_bias_acc_sigma", C.c_double * 3),
+        ("imu_noise_gyro_sigma", C.c_double * 3),
+        ("imu_bias_gyro_sigma", C.c_double * 3),
+        ("wheel_sigma", C.c_double * 3),
+        ("max_iters", C.c_int32),
+        ("reserved0", C.c_int32),
+        ("huber_delta", C.c_double),
+        ("function_tolerance", C.c_double),
+        ("gradient_tolerance", C.c_double),
+        ("parameter_tolerance", C.c_double),
+        ("initial_trust_region_radius", C.c_double),
+    ]
+
+
+class WindowBatch(C.Structure):
+    """lvio2d_window_batch (include/lvio2d.h)."""
+
+    _fields_ = [
+        ("n_windows", C.c_int32),
+        ("n_frames", C.c_int32),
+        ("states", c_double_p),
+        ("const_mask", c_uint8_p),
+        ("point_offset", c_int64_p),
+        ("points", c_double_p),
+        ("point_line", c_int32_p),
+        ("point_weight", c_double_p),
+        ("line_offset", c_int64_p),
+        ("lines", c_double_p),
+        ("ref_frame", c_int32_p),
+        ("ref_pose", c_double_p),
+        ("imu", c_double_p),
+        ("wheel", c_double_p),
+        ("ground_multiplicity", C.c_int32),
+        ("prior_frame", C.c_int32),
+        ("prior_X0", c_double_p),
+        ("prior_J", c_double_p),
+    ]
+
+
+class Summary(C.Structure):
+    """lvio2d_summary (include/lvio2d.h)."""
+
+    _fields_ = [
+        ("iterations", C.c_int32),
+        ("termination", C.c_int32),
+        ("num_successful_steps", C.c_int32),
+        ("num_unsuccessful_steps", C.c_int32),
+        ("initial_cost", C.c_double),
+        ("final_cost", C.c_double),
+        ("final_radius", C.c_double),
+        ("reserved", C.c_double),
+    ]
+
+
+SUMMARY_DTYPE = np.dtype(
+    [
+        ("iterations", np.int32),
+        ("termination", np.int32),
+        ("num_successful_steps", np.int32),
+        ("num_unsuccessful_steps", np.int32),
+        ("initial_cost", np.float64),
+        ("final_cost", np.float64),
+        ("final_radius", np.float64),
+        ("reserved", np.float64),
+    ]
+)
+assert SUMMARY_DTYPE.itemsize == C.sizeof(Summary)
+
+_PTR_FIELDS = {
+    "states": (np.float64, c_double_p),
+    "const_mask": (np.uint8, c_uint8_p),
+    "point_offset": (np.int64, c_int64_p),
+    "points": (np.float64, c_double_p),
+    "point_line": (np.int32, c_int32_p),
+    "point_weight": (np.float64, c_double_p),
+    "line_offset": (np.int64, c_int64_p),
+    "lines": (np.float64, c_double_p),
+    "ref_frame": (np.int32, c_int32_p),
+    "ref_pose": (np.float64, c_double_p),
+    "imu": (np.float64, c_double_p),
+    "wheel": (np.float64, c_double_p),
+    "prior_X0": (np.float64, c_double_p),
+    "prior_J": (np.float64, c_double_p),
+}
+
+
+def ptr(arr, ctype):
+    return arr.ctypes.data_as(ctype) if arr is not None else ctype()
+
+
+class HostBatch:
+    """A window batch held as contiguous numpy arrays + the ctypes struct that points into them.
+
+    `fields` maps lvio2d_window_batch member names to arrays (or None for NULL pointers).
+    """
+
+    def __init__(self, n_windows, n_frames, ground_multiplicity, prior_frame=-1, **fields):
+        self.n_windows = int(n_windows)
+        self.n_frames = int(n_frames)
+        self.ground_multiplicity = int(ground_multiplicity)
+        self.prior_frame = int(prior_frame)
+        self.arrays = {}
+        for name, (dtype, _) in _PTR_FIELDS.items():
+            a = fields.get(name)
+            self.arrays[name] = None if a is None else np.ascontiguousarray(a, dtype=dtype)
+        unknown = set(fields) - set(_PTR_FIELDS)
+        if unknown:
+            raise TypeError(f"unknown batch fields {sorted(unknown)}")
+        self._check()
+
+    def _check(self):
+        B, n = self.n_windows, self.n_frames
+        a = self.arrays
+        assert a["states"] is not None and a["states"].size == B * n * STATE_DIM
+        if a["const_mask"] is not None:
+            assert a["const_mask"].size == B * n
+        if a["point_offset"] is not None:
+            assert a["point_offset"].size == B * n + 1
+            N = int(a["point_offset"][-1])
+            assert a["points"].size == 2 * N and a["point_line"].size == N
+            assert a["line_offset"].size == B * n + 1
+            assert a["lines"].size == 4 * int(a["line_offset"][-1])
+            if a["point_weight"] is not None:
+                assert a["point_weight"].size == N
+            if a["ref_frame"] is not None:
+                assert a["ref_frame"].size == B * n
+            assert a["ref_pose"] is not None and a["ref_pose"].size == B * n * 6
+        if a["imu"] is not None:
+            assert a["imu"].size == B * (n - 1) * IMU_BLOB
+        if a["wheel"] is not None:
+            assert a["wheel"].size == B * (n - 1) * WHEEL_BLOB
+        if self.prior_frame >= 0:
+            assert a["prior_X0"].size == B * 15 and a["prior_J"].size == B * 225
+
+    def __getitem__(self, name):
+        return self.arrays[name]
+
+    @property
+    def n_points(self):
+        po = self.arrays["point_offset"]
+        return 0 if po is None else int(po[-1])
+
+    def struct(self):
+        s = WindowBatch()
+        s.n_windows, s.n_frames = self.n_windows, self.n_frames
+        s.ground_multiplicity, s.prior_frame = self.ground_multiplicity, self.prior_frame
+        for name, (_, ctype) in _PTR_FIELDS.items():
+            setattr(s, name, ptr(self.arrays[name], ctype))
+        return s
+
+    def replace(self, **fields):
+        merged = dict(self.arrays)
+        merged.update(fields)
+        kw = dict(n_windows=self.n_windows, n_frames=self.n_frames, ground_multiplicity=self.ground_multiplicity,
+                  prior_frame=self.prior_frame)
+        for k in ("n_windows", "n_frames", "ground_multiplicity", "prior_frame"):
+            if k in merged:
+                kw[k] = merged.pop(k)
+        return HostBatch(**kw, **merged)
+
+    def nbytes(self):
+        return sum(a.nbytes for a in self.arrays.values() if a is not None)

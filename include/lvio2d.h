@@ -1,0 +1,238 @@
+/*
+ * lvio2d.h — C ABI of the B200-native front-end sliding-window solver.
+ *
+ * This is the drop-in boundary for ONE hot path of LittleDang/2DLIW-SLAM (lvio_2d):
+ * the front-end optimiser `lvio_2d::solver` (reference src/factor/solver.h:28-80) with its
+ * factors (src/factor/{laser,imu,wheel,ground,marginalization}_factor.h) and the two
+ * preintegrators that produce the factors' constants (src/factor/imu_preintegraption.h,
+ * src/factor/wheel_odom_preintegration.h).  The reference has no FFI of its own; the entry
+ * points below are what a `lvio_2d::solver` shim binds (see INTEGRATION.md and
+ * shim/lvio2d_solver_shim.h).  Every entry point cites the reference code it replaces.
+ *
+ * Conventions
+ *   - plain C, no C++/torch types; all matrices row-major; all reals are IEEE double
+ *     (the reference is double everywhere, src/trajectory/trajectory_type.h:23-26).
+ *   - per-frame state is 15 doubles in the solver's column order [p(3) q(3) v(3) bs(6)]
+ *     (src/factor/solver.cpp:332-342); q is the angle-axis vector of the IMU orientation and must
+ *     satisfy |q| <= pi (what lie::normalize_so3 guarantees, src/utilies/common.h:121-135).
+ *   - preintegration order is [alpha beta gamma ba bw] (src/factor/factor_common.h:16-20).
+ *   - every function returns 0 (LVIO2D_OK) or a negative lvio2d_status; nothing throws across
+ *     the ABI.  The caller owns all host buffers; they are copied during the call.
+ *   - a context is single-threaded and non-reentrant like the reference's solver, which is only
+ *     touched by the dispatch thread (src/trajectory/dispatch.h:104,240).
+ *   - the library is CUDA-only: lvio2d_create fails with LVIO2D_ERR_NO_DEVICE when no sm_100
+ *     device is present.  There is no CPU fallback.
+ */
+#ifndef LVIO2D_H_
+#define LVIO2D_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LVIO2D_ABI_VERSION 1
+#define LVIO2D_STATE_DIM 15
+/* imu_preint_result flattened: X[15] | J[15x15] | sqrt_inverse_P[15x15] | Dt
+ * (src/factor/imu_preintegraption.h:45-52) */
+#define LVIO2D_IMU_BLOB 466
+/* wheel_odom_preint_result flattened: delta_Tij[3x4] | diag(sqrt_inverse_P)[3]
+ * (src/factor/wheel_odom_preintegration.h:25-33; only the diagonal is read, wheel_factor.h:59-69) */
+#define LVIO2D_WHEEL_BLOB 15
+/* per-frame laser normal-equation block: 21 upper-triangular entries of the 6x6 J^T J block over
+ * (p,q), 6 entries of J^T r, 1 sum of squared residuals */
+#define LVIO2D_LASER_BLOCK 28
+
+typedef enum lvio2d_status {
+    LVIO2D_OK = 0,
+    LVIO2D_ERR_INVALID_ARG = -1,
+    LVIO2D_ERR_NO_DEVICE = -2,   /* no CUDA device / not sm_100: the product never falls back to CPU */
+    LVIO2D_ERR_CUDA = -3,
+    LVIO2D_ERR_NO_WINDOW = -4,   /* solve/linearize called before set_windows */
+    LVIO2D_ERR_DOMAIN = -5,      /* |q| > pi, n_frames out of range, too many lines per frame ... */
+    LVIO2D_ERR_ALLOC = -6
+} lvio2d_status;
+
+/* bits of const_mask[frame]: which parameter blocks ceres::Problem::SetParameterBlockConstant was
+ * called on (src/factor/solver.cpp:787-794) */
+#define LVIO2D_CONST_P 1u
+#define LVIO2D_CONST_Q 2u
+#define LVIO2D_CONST_V 4u
+#define LVIO2D_CONST_BS 8u
+
+/* termination codes of lvio2d_summary.termination (Ceres TerminationType semantics) */
+#define LVIO2D_TERM_NO_CONVERGENCE 0  /* max_iters reached */
+#define LVIO2D_TERM_CONVERGENCE_FUNCTION 1
+#define LVIO2D_TERM_CONVERGENCE_PARAMETER 2
+#define LVIO2D_TERM_CONVERGENCE_GRADIENT 3
+#define LVIO2D_TERM_CONVERGENCE_RADIUS 4
+#define LVIO2D_TERM_FAILURE 5         /* >= 5 consecutive invalid steps, or NaN */
+
+/* The values of param::manager the hot path reads (src/utilies/params.h:7, params.cpp:92-175).
+ * T_imu_to_laser / T_imu_to_wheel are the already re-orthonormalised isometries
+ * (lie::normalize_tf, src/utilies/params.cpp:52) as row-major 3x4 [R | t]. */
+typedef struct lvio2d_params {
+    int32_t abi_version;          /* LVIO2D_ABI_VERSION */
+    int32_t device;               /* CUDA device ordinal */
+    double T_imu_to_laser[12];
+    double T_imu_to_wheel[12];
+    double g;                     /* PARAM(g), imu_factor.h:41 */
+    double line_to_line_sigma;    /* laser_factor.h:21 */
+    double manifold_p_sigma;      /* ground_factor.h:20 */
+    double manifold_q_sigma;      /* ground_factor.h:21 */
+    double imu_noise_acc_sigma[3];   /* imu_preintegraption.h:26-42 */
+    double imu_bias_acc_sigma[3];
+    double imu_noise_gyro_sigma[3];
+    double imu_bias_gyro_sigma[3];
+    double wheel_sigma[3];        /* wheel_odom_preintegration.h:19-22 */
+    int32_t max_iters;            /* ceres max_num_iterations: 50 default, 10 in fast_mode (solver.cpp:800-801) */
+    int32_t reserved0;
+    double huber_delta;           /* <= 0 or inf: no robust loss = the reference (solver.cpp:635) */
+    /* ceres::Solver::Options defaults the reference never changes; <= 0 selects the default */
+    double function_tolerance;    /* 1e-6 */
+    double gradient_tolerance;    /* 1e-10 */
+    double parameter_tolerance;   /* 1e-8 */
+    double initial_trust_region_radius; /* 1e4 */
+} lvio2d_params;
+
+/* A batch of B independent sliding windows with the same number of frames.  One window is what
+ * solver::solve / solver::init_solve receive as `std::deque<frame_info::ptr>` (solver.h:72-76),
+ * flattened to SoA.  Laser terms are "points against lines": residual w*dis_from_line(C, A1, A2)
+ * (src/utilies/common.h:86-95) with C the point moved by the frame's pose and (A1,A2) the line moved
+ * by its reference pose — the reference's laser_factor (laser_factor.h:45-89) is the special case
+ * of 2 points (the segment end points) per matched line pair with the pair weight
+ * (laser_factor.h:38-42); "beam mode" feeds every scan point.
+ *
+ * Index f = window*n_frames + frame.  All pointers are host pointers for lvio2d_set_windows and
+ * device pointers for lvio2d_bind_windows. */
+typedef struct lvio2d_window_batch {
+    int32_t n_windows;            /* B >= 1 */
+    int32_t n_frames;             /* n >= 1, frames per window */
+    const double* states;         /* [B*n][15]  p q v bs, read at set time, solution via lvio2d_get_states */
+    const uint8_t* const_mask;    /* [B*n]  LVIO2D_CONST_* bits */
+    /* laser */
+    const int64_t* point_offset;  /* [B*n+1] prefix offsets into points / point_line / point_weight */
+    const double* points;         /* [N][2]  x,y in the frame's own laser frame (z = 0, common.cpp:22-24) */
+    const int32_t* point_line;    /* [N]  index into the frame's line list, < 0 = no correspondence */
+    const double* point_weight;   /* [N] or NULL: per-point weight multiplying 1/line_to_line_sigma
+                                     (laser_factor::sum, laser_factor.h:40-42); NULL = 1 */
+    const int64_t* line_offset;   /* [B*n+1] prefix offsets into lines */
+    const double* lines;          /* [L][4]  p1.x p1.y p2.x p2.y in the REFERENCE laser frame */
+    const int32_t* ref_frame;     /* [B*n]  -1: lines live under the external pose ref_pose[f], constant
+                                     (tracking, solver.cpp:685-691);  k>=0: under frame k of this window,
+                                     a free block (initialisation, solver.cpp:93-106) */
+    const double* ref_pose;       /* [B*n][6]  p1,q1 of laser_match (laser_type.h:83), used when ref_frame<0 */
+    /* imu / wheel factors between frame i-1 and i, i = 1..n-1 */
+    const double* imu;            /* [B*(n-1)][LVIO2D_IMU_BLOB] */
+    const double* wheel;          /* [B*(n-1)][LVIO2D_WHEEL_BLOB] */
+    /* ground factors: the reference adds both factors `n` times per frame (solver.cpp:727-743) */
+    int32_t ground_multiplicity;  /* reference behaviour: n_frames */
+    /* marginalisation prior r = J (X - X0) on frame prior_frame (solver.cpp:744-785,
+     * marginalization_factor.h:22-53).  prior_frame < 0: no prior */
+    int32_t prior_frame;          /* reference: n_frames - 2 */
+    const double* prior_X0;       /* [B][15] */
+    const double* prior_J;        /* [B][15x15] */
+} lvio2d_window_batch;
+
+typedef struct lvio2d_summary {
+    int32_t iterations;           /* LM iterations executed (Ceres iteration counter, excludes iteration 0) */
+    int32_t termination;          /* LVIO2D_TERM_* */
+    int32_t num_successful_steps;
+    int32_t num_unsuccessful_steps;
+    double initial_cost;          /* 1/2 sum r^2 over active residual blocks */
+    double final_cost;
+    double final_radius;
+    double reserved;
+} lvio2d_summary;
+
+typedef struct lvio2d_ctx lvio2d_ctx;
+
+/* ---- lifetime: replaces solver::solver() (src/factor/solver.cpp:43-48) and the PARAM()/noise
+ * singletons the functors read on every call (laser_factor.h:12-24, ground_factor.h:11-22) ---- */
+int lvio2d_create(lvio2d_ctx** out, const lvio2d_params* params);
+void lvio2d_destroy(lvio2d_ctx* ctx);
+const char* lvio2d_strerror(int status);
+/* last CUDA error string recorded by the context (empty if none) */
+const char* lvio2d_last_error(const lvio2d_ctx* ctx);
+/* the CUDA stream (cudaStream_t) all work of this context is enqueued on */
+void* lvio2d_stream(lvio2d_ctx* ctx);
+
+/* ---- problem upload: replaces ceres::Problem assembly, solver.cpp:636-794 / :50-159 ---- */
+int lvio2d_set_windows(lvio2d_ctx* ctx, const lvio2d_window_batch* host_batch);
+/* zero-copy variant: every pointer of the batch is a device pointer that stays valid until the next
+ * set/bind; states are copied into context-owned buffers (they are mutated by solve) */
+int lvio2d_bind_windows(lvio2d_ctx* ctx, const lvio2d_window_batch* device_batch);
+/* overwrite the states only (same shapes): re-arm a bound batch for another solve */
+int lvio2d_reset_states(lvio2d_ctx* ctx, const double* host_states);
+
+/* ---- solver::solve / solver::do_init_solve: ceres::Solve with the reference's options
+ * (solver.cpp:795-802, :161-168): trust-region Levenberg–Marquardt, Jacobi scaling, exact step ---- */
+int lvio2d_solve(lvio2d_ctx* ctx, lvio2d_summary* summaries /* [B] host, may be NULL */);
+/* same, but only enqueues on lvio2d_stream(); summaries and states are read later */
+int lvio2d_solve_async(lvio2d_ctx* ctx);
+int lvio2d_sync(lvio2d_ctx* ctx);
+int lvio2d_get_summaries(lvio2d_ctx* ctx, lvio2d_summary* summaries /* [B] host */);
+/* frame_infos[i]->{p,q,v,bs} after the solve (written in place by Ceres, solver.cpp:685-707) */
+int lvio2d_get_states(lvio2d_ctx* ctx, double* host_states /* [B*n][15] */);
+
+/* ---- split-phase solve for point-sharded multi-GPU runs (one allreduce per LM iteration).
+ * Each rank owns points [rank*N_f/world, (rank+1)*N_f/world) of every frame.  Loop:
+ *   lvio2d_solve_begin; repeat { lvio2d_eval_laser; allreduce(sum) of the reduce buffer;
+ *   lvio2d_lm_step(&active) } until active == 0. ---- */
+int lvio2d_set_point_shard(lvio2d_ctx* ctx, int32_t rank, int32_t world);
+int lvio2d_solve_begin(lvio2d_ctx* ctx);
+int lvio2d_eval_laser(lvio2d_ctx* ctx);
+/* device pointer + element count (doubles) of the per-frame laser blocks to be summed over ranks;
+ * the caller may instead hand in its own device buffer (e.g. a torch tensor) with set_reduce_buffer */
+int lvio2d_reduce_buffer(lvio2d_ctx* ctx, void** device_ptr, int64_t* count);
+int lvio2d_set_reduce_buffer(lvio2d_ctx* ctx, void* device_ptr, int64_t count);
+int lvio2d_lm_step(lvio2d_ctx* ctx, int32_t* n_active /* host out, may be NULL (no sync) */);
+
+/* ---- one-shot linearisation (test hook + what solver::marginalization builds, solver.cpp:367-380).
+ * mode 0: the solver's reduced program (constant blocks have zero rows/cols, inactive residual
+ *         blocks dropped); mode 1: the marginalisation program of solver.cpp:257-380 (no constant
+ *         blocks, laser Jacobian w.r.t. the frame's own pose only).
+ * H is dense [B][15n][15n], g = J^T r [B][15n], cost = 1/2 sum r^2 [B]; host buffers. ---- */
+int lvio2d_linearize(lvio2d_ctx* ctx, int32_t mode, double* H, double* g, double* cost);
+
+/* ---- solver::marginalization (solver.cpp:257-442 with marginalization_matrix :4-40): Schur
+ * complement onto the last frame, eigen-decomposition, sqrt-information prior.
+ * X0 [B][15], J_lin [B][15x15], r_lin [B][15], host buffers. ---- */
+int lvio2d_marginalize(lvio2d_ctx* ctx, double* X0, double* J_lin, double* r_lin);
+
+/* ---- preintegration (the factors' constants) ----
+ * imu_preintegraption::{reset_imu_measure, update, get_preintegraption_result}
+ * (imu_preintegraption.h:113-124, :170-208, :147-152), one interval per work item.
+ * samples: [M][7] = dt, acc(3), gyro(3): the step `update(dt)` integrates with the PREVIOUS
+ * sample's acc/gyro (last_info, :179-180), so row k holds (dt_k, acc_{k-1}, gyro_{k-1}).
+ * bias0: [n_intervals][6] (ba,bw) at reset.  out: [n_intervals][LVIO2D_IMU_BLOB]. */
+int lvio2d_imu_preintegrate(lvio2d_ctx* ctx, int32_t n_intervals, const int64_t* sample_offset,
+                            const double* samples, const double* bias0, double* out_blobs);
+/* wheel_odom_preintegration::{update_by_v, get_preintegraption_result}
+ * (wheel_odom_preintegration.h:141-152, :111-125).  steps: [M][7] = dt, v(3), omega(3).
+ * out: [n_intervals][LVIO2D_WHEEL_BLOB]. */
+int lvio2d_wheel_preintegrate(lvio2d_ctx* ctx, int32_t n_intervals, const int64_t* step_offset,
+                              const double* steps, double* out_blobs);
+
+/* ---- per-factor evaluation on the device = auto_diff::compute_res_and_jacobi
+ * (src/utilies/common.h:201-217): residual + row-major Jacobian per parameter block, concatenated
+ * column-wise in the functor's parameter order.  Host buffers. ---- */
+/* laser_factor(l1_p1,l1_p2,l2_p1,l2_p2)(p_i,q_i,p_j,q_j): res[2], jac[2][12] (laser_factor.h:31-89);
+ * each l*_p* is 3 doubles */
+int lvio2d_eval_laser_factor(lvio2d_ctx* ctx, const double* l1_p1, const double* l1_p2,
+                             const double* l2_p1, const double* l2_p2, const double* pose_i,
+                             const double* pose_j, double* res, double* jac);
+/* imu_factor(blob)(p_i,q_i,v_i,bs_i,p_j,q_j,v_j,bs_j): res[15], jac[15][30] (imu_factor.h:13-89) */
+int lvio2d_eval_imu_factor(lvio2d_ctx* ctx, const double* imu_blob, const double* state_i,
+                           const double* state_j, double* res, double* jac);
+/* wheel_odom_factor(blob)(p_i,q_i,p_j,q_j): res[3], jac[3][12] (wheel_factor.h:12-73) */
+int lvio2d_eval_wheel_factor(lvio2d_ctx* ctx, const double* wheel_blob, const double* pose_i,
+                             const double* pose_j, double* res, double* jac);
+/* ground_factor_p / ground_factor_q (p,q): res[2] = (res_p, res_q), jac[2][6] (ground_factor.h:27-82) */
+int lvio2d_eval_ground_factors(lvio2d_ctx* ctx, const double* pose, double* res, double* jac);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LVIO2D_H_ */

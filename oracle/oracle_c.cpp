@@ -1,0 +1,190 @@
+// ORACLE — TEST INFRASTRUCTURE ONLY (see jet.hpp header).  PARITY UNPINNED.
+//
+// oracle_c.cpp — extern "C" surface of the CPU restatement, loaded with ctypes by tests/,
+// __graft_entry__.smoke() and bench.py (cpu_baseline / --impl reference).  Mirrors include/lvio2d.h
+// entry point by entry point so a parity test feeds the same structs to both sides.
+#include <cstdio>
+#include <cstring>
+#include <vector>
+#include <atomic>
+#include <thread>
+
+#include "solver.hpp"
+
+using namespace oracle;
+
+extern "C" {
+
+int oracle_abi_version() { return LVIO2D_ABI_VERSION; }
+
+// ---- primitives (src/utilies/common.h:86-95, :121-163)
+void oracle_exp_so3(const double* so3, double* R9) {
+    Mat3<double> R = lie::exp_so3<double>(Vec3<double>(so3[0], so3[1], so3[2]));
+    for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) R9[i * 3 + j] = R.m[i][j];
+}
+void oracle_log_SO3(const double* R9, double* so3) {
+    Mat3<double> R;
+    for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) R.m[i][j] = R9[i * 3 + j];
+    Vec3<double> v = lie::log_SO3<double>(R);
+    so3[0] = v.x; so3[1] = v.y; so3[2] = v.z;
+}
+void oracle_normalize_so3(double* so3) {
+    Vec3<double> v(so3[0], so3[1], so3[2]);
+    lie::normalize_so3(v);
+    so3[0] = v.x; so3[1] = v.y; so3[2] = v.z;
+}
+double oracle_dis_from_line(const double* p, const double* p1, const double* p2) {
+    return e_laser::dis_from_line<double>(Vec3<double>(p[0], p[1], p[2]), Vec3<double>(p1[0], p1[1], p1[2]),
+                                          Vec3<double>(p2[0], p2[1], p2[2]));
+}
+void oracle_so3_plus(const double* theta, const double* delta, double* out) { so3_plus(theta, delta, out); }
+
+// ---- per-factor residual + Jacobian = auto_diff::compute_res_and_jacobi (common.h:201-217)
+int oracle_eval_laser_factor(const lvio2d_params* p, const double* l1_p1, const double* l1_p2, const double* l2_p1,
+                             const double* l2_p2, const double* pose_i, const double* pose_j, double* res, double* jac) {
+    Params P(*p);
+    laser_factor fac(&P, Vec3<double>(l1_p1[0], l1_p1[1], l1_p1[2]), Vec3<double>(l1_p2[0], l1_p2[1], l1_p2[2]),
+                     Vec3<double>(l2_p1[0], l2_p1[1], l2_p1[2]), Vec3<double>(l2_p2[0], l2_p2[1], l2_p2[2]));
+    autodiff<2, 12>(fac, {pose_i, pose_i + 3, pose_j, pose_j + 3}, {3, 3, 3, 3}, res, jac,
+                    [](const laser_factor& f, const Jet<12>* const* a, Jet<12>* r) { f(a[0], a[1], a[2], a[3], r); });
+    return 0;
+}
+int oracle_eval_laser_point(const lvio2d_params* p, const double* a1, const double* a2, const double* c, double weight,
+                            const double* pose_i, const double* pose_j, double* res, double* jac) {
+    Params P(*p);
+    laser_point_factor fac(&P, Vec3<double>(a1[0], a1[1], 0.0), Vec3<double>(a2[0], a2[1], 0.0), Vec3<double>(c[0], c[1], 0.0), weight);
+    autodiff<1, 12>(fac, {pose_i, pose_i + 3, pose_j, pose_j + 3}, {3, 3, 3, 3}, res, jac,
+                    [](const laser_point_factor& f, const Jet<12>* const* a, Jet<12>* r) { f(a[0], a[1], a[2], a[3], r); });
+    return 0;
+}
+int oracle_eval_imu_factor(const lvio2d_params* p, const double* blob, const double* si, const double* sj, double* res, double* jac) {
+    Params P(*p);
+    imu_factor fac(&P, blob);
+    autodiff<15, 30>(fac, {si, si + 3, si + 6, si + 9, sj, sj + 3, sj + 6, sj + 9}, {3, 3, 3, 6, 3, 3, 3, 6}, res, jac,
+                     [](const imu_factor& f, const Jet<30>* const* a, Jet<30>* r) { f(a[0], a[1], a[2], a[3], a[4], a[5], a[6], a[7], r); });
+    return 0;
+}
+int oracle_eval_wheel_factor(const lvio2d_params* p, const double* blob, const double* pose_i, const double* pose_j, double* res, double* jac) {
+    Params P(*p);
+    wheel_odom_factor fac(&P, blob);
+    autodiff<3, 12>(fac, {pose_i, pose_i + 3, pose_j, pose_j + 3}, {3, 3, 3, 3}, res, jac,
+                    [](const wheel_odom_factor& f, const Jet<12>* const* a, Jet<12>* r) { f(a[0], a[1], a[2], a[3], r); });
+    return 0;
+}
+int oracle_eval_ground_factors(const lvio2d_params* p, const double* pose, double* res, double* jac) {
+    Params P(*p);
+    ground_factor_p fp(&P);
+    ground_factor_q fq(&P);
+    autodiff<1, 6>(fp, {pose, pose + 3}, {3, 3}, res, jac,
+                   [](const ground_factor_p& f, const Jet<6>* const* a, Jet<6>* r) { f(a[0], a[1], r); });
+    autodiff<1, 6>(fq, {pose, pose + 3}, {3, 3}, res + 1, jac ? jac + 6 : nullptr,
+                   [](const ground_factor_q& f, const Jet<6>* const* a, Jet<6>* r) { f(a[0], a[1], r); });
+    return 0;
+}
+int oracle_eval_prior_factor(const double* X0, const double* J, const double* state, double* res, double* jac) {
+    marginalization_factor fac(X0, J);
+    autodiff<15, 15>(fac, {state, state + 3, state + 6, state + 9}, {3, 3, 3, 6}, res, jac,
+                     [](const marginalization_factor& f, const Jet<15>* const* a, Jet<15>* r) { f(a[0], a[1], a[2], a[3], r); });
+    return 0;
+}
+
+// ---- preintegration
+int oracle_imu_preintegrate(const lvio2d_params* p, int32_t n_intervals, const int64_t* sample_offset, const double* samples,
+                            const double* bias0, double* out_blobs) {
+    Params P(*p);
+    int bad = 0;
+    for (int i = 0; i < n_intervals; ++i) {
+        imu_preintegraption pre(&P);
+        pre.reset(bias0 + 6 * i, bias0 + 6 * i + 3);
+        for (int64_t s = sample_offset[i]; s < sample_offset[i + 1]; ++s) pre.update(samples[7 * s], samples + 7 * s + 1, samples + 7 * s + 4);
+        if (!pre.result(out_blobs + (size_t)i * LVIO2D_IMU_BLOB)) ++bad;
+    }
+    return bad ? -1 : 0;
+}
+int oracle_wheel_preintegrate(const lvio2d_params* p, int32_t n_intervals, const int64_t* step_offset, const double* steps, double* out_blobs) {
+    Params P(*p);
+    for (int i = 0; i < n_intervals; ++i) {
+        wheel_odom_preintegration pre(&P);
+        for (int64_t s = step_offset[i]; s < step_offset[i + 1]; ++s) pre.update_by_v(steps[7 * s], steps + 7 * s + 1, steps + 7 * s + 4);
+        pre.result(out_blobs + (size_t)i * LVIO2D_WHEEL_BLOB);
+    }
+    return 0;
+}
+
+// ---- window level
+// states == NULL: use batch->states
+int oracle_linearize(const lvio2d_params* p, const lvio2d_window_batch* batch, const double* states, int32_t mode, double* H,
+                     double* g, double* cost) {
+    Params P(*p);
+    const int n = batch->n_frames, dim = 15 * n;
+    const double* X = states ? states : batch->states;
+    for (int w = 0; w < batch->n_windows; ++w) {
+        Window W(batch, w);
+        Evaluator ev(P, W, mode);
+        Linearization lin;
+        ev.evaluate(X + (size_t)w * dim, &lin);
+        if (H) std::memcpy(H + (size_t)w * dim * dim, lin.H.data(), sizeof(double) * dim * dim);
+        if (g) std::memcpy(g + (size_t)w * dim, lin.g.data(), sizeof(double) * dim);
+        if (cost) cost[w] = lin.cost;
+    }
+    return 0;
+}
+int oracle_cost(const lvio2d_params* p, const lvio2d_window_batch* batch, const double* states, double* cost) {
+    Params P(*p);
+    const int dim = 15 * batch->n_frames;
+    const double* X = states ? states : batch->states;
+    for (int w = 0; w < batch->n_windows; ++w) {
+        Window W(batch, w);
+        Evaluator ev(P, W, 0);
+        cost[w] = ev.evaluate(X + (size_t)w * dim, nullptr);
+    }
+    return 0;
+}
+// solver::solve / do_init_solve.  n_threads > 1 parallelises over windows (std::thread) for the all-cores
+// baseline; the reference itself is single threaded (solver.cpp:798).
+int oracle_solve(const lvio2d_params* p, const lvio2d_window_batch* batch, double* states_out, lvio2d_summary* summaries, int32_t n_threads) {
+    Params P(*p);
+    LMOptions opt = lm_options_from(*p);
+    const int dim = 15 * batch->n_frames;
+    std::memcpy(states_out, batch->states, sizeof(double) * (size_t)dim * batch->n_windows);
+    if (n_threads < 1) n_threads = 1;
+    if (n_threads > batch->n_windows) n_threads = batch->n_windows;
+    std::atomic<int> next(0);
+    auto worker = [&]() {
+        for (;;) {
+            const int w = next.fetch_add(1);
+            if (w >= batch->n_windows) break;
+            Window W(batch, w);
+            lvio2d_summary S = lm_solve(P, W, opt, states_out + (size_t)w * dim);
+            if (summaries) summaries[w] = S;
+        }
+    };
+    if (n_threads == 1) {
+        worker();
+    } else {
+        std::vector<std::thread> pool;
+        for (int t = 0; t < n_threads; ++t) pool.emplace_back(worker);
+        for (auto& th : pool) th.join();
+    }
+    return 0;
+}
+int oracle_marginalize(const lvio2d_params* p, const lvio2d_window_batch* batch, const double* states, double* X0, double* J_lin,
+                       double* r_lin, double* Delta_H, double* Delta_g) {
+    Params P(*p);
+    const int dim = 15 * batch->n_frames;
+    const double* X = states ? states : batch->states;
+    int bad = 0;
+    for (int w = 0; w < batch->n_windows; ++w) {
+        Window W(batch, w);
+        if (!marginalize(P, W, X + (size_t)w * dim, X0 + 15 * w, J_lin + 225 * w, r_lin + 15 * w, Delta_H ? Delta_H + 225 * w : nullptr,
+                         Delta_g ? Delta_g + 15 * w : nullptr))
+            ++bad;
+    }
+    return bad ? -1 : 0;
+}
+int oracle_max_threads() {
+    const unsigned h = std::thread::hardware_concurrency();
+    return h ? (int)h : 1;
+}
+
+}  // extern "C"

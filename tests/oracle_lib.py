@@ -1,0 +1,190 @@
+"""ctypes wrapper of oracle/liboracle.so — TEST INFRASTRUCTURE (the CPU restatement of the reference path).
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs import this.
+The library is built by `make -C oracle` (also done by __graft_entry__.build()).
+"""
+import ctypes as C
+import os
+import subprocess
+import sys
+
+import numpy as np
+
+_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if _ROOT not in sys.path:
+    sys.path.insert(0, _ROOT)
+
+from lvio2d_b200 import abi  # noqa: E402
+
+_LIB_PATH = os.path.join(_ROOT, "oracle", "liboracle.so")
+_lib = None
+
+dp = abi.c_double_p
+
+
+def _d(a):
+    return a.ctypes.data_as(dp)
+
+
+def build(force=False):
+    srcs = ["oracle_c.cpp", "solver.hpp", "factors.hpp", "preint.hpp", "lie.hpp", "jet.hpp"]
+    newest = max(os.path.getmtime(os.path.join(_ROOT, "oracle", s)) for s in srcs)
+    if force or not os.path.exists(_LIB_PATH) or os.path.getmtime(_LIB_PATH) < newest:
+        subprocess.check_call(["make", "-C", os.path.join(_ROOT, "oracle"), "-s"])
+    return _LIB_PATH
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_LIB_PATH):
+            build()
+        _lib = C.CDLL(_LIB_PATH)
+        _lib.oracle_dis_from_line.restype = C.c_double
+        _lib.oracle_dis_from_line.argtypes = [dp, dp, dp]
+        _lib.oracle_eval_laser_point.argtypes = [C.POINTER(abi.Params), dp, dp, dp, C.c_double, dp, dp, dp, dp]
+    return _lib
+
+
+def _arr(x):
+    return np.ascontiguousarray(x, dtype=np.float64)
+
+
+# ---- primitives
+def exp_so3(v):
+    R = np.zeros(9)
+    lib().oracle_exp_so3(_d(_arr(v)), _d(R))
+    return R.reshape(3, 3)
+
+
+def log_SO3(R):
+    v = np.zeros(3)
+    lib().oracle_log_SO3(_d(_arr(R).ravel()), _d(v))
+    return v
+
+
+def normalize_so3(v):
+    v = _arr(v).copy()
+    lib().oracle_normalize_so3(_d(v))
+    return v
+
+
+def so3_plus(theta, delta):
+    out = np.zeros(3)
+    lib().oracle_so3_plus(_d(_arr(theta)), _d(_arr(delta)), _d(out))
+    return out
+
+
+def dis_from_line(p, p1, p2):
+    return lib().oracle_dis_from_line(_d(_arr(p)), _d(_arr(p1)), _d(_arr(p2)))
+
+
+# ---- factors
+def eval_laser_factor(params, l1_p1, l1_p2, l2_p1, l2_p2, pose_i, pose_j):
+    res, jac = np.zeros(2), np.zeros((2, 12))
+    lib().oracle_eval_laser_factor(C.byref(params), _d(_arr(l1_p1)), _d(_arr(l1_p2)), _d(_arr(l2_p1)), _d(_arr(l2_p2)),
+                                   _d(_arr(pose_i)), _d(_arr(pose_j)), _d(res), _d(jac))
+    return res, jac
+
+
+def eval_laser_point(params, a1, a2, c, weight, pose_i, pose_j):
+    res, jac = np.zeros(1), np.zeros((1, 12))
+    lib().oracle_eval_laser_point(C.byref(params), _d(_arr(a1)), _d(_arr(a2)), _d(_arr(c)), float(weight),
+                                  _d(_arr(pose_i)), _d(_arr(pose_j)), _d(res), _d(jac))
+    return res, jac
+
+
+def eval_imu_factor(params, blob, state_i, state_j):
+    res, jac = np.zeros(15), np.zeros((15, 30))
+    lib().oracle_eval_imu_factor(C.byref(params), _d(_arr(blob)), _d(_arr(state_i)), _d(_arr(state_j)), _d(res), _d(jac))
+    return res, jac
+
+
+def eval_wheel_factor(params, blob, pose_i, pose_j):
+    res, jac = np.zeros(3), np.zeros((3, 12))
+    lib().oracle_eval_wheel_factor(C.byref(params), _d(_arr(blob)), _d(_arr(pose_i)), _d(_arr(pose_j)), _d(res), _d(jac))
+    return res, jac
+
+
+def eval_ground_factors(params, pose):
+    res, jac = np.zeros(2), np.zeros((2, 6))
+    lib().oracle_eval_ground_factors(C.byref(params), _d(_arr(pose)), _d(res), _d(jac))
+    return res, jac
+
+
+def eval_prior_factor(X0, J, state):
+    res, jac = np.zeros(15), np.zeros((15, 15))
+    lib().oracle_eval_prior_factor(_d(_arr(X0)), _d(_arr(J).ravel()), _d(_arr(state)), _d(res), _d(jac))
+    return res, jac
+
+
+# ---- preintegration
+def imu_preintegrate(params, sample_offset, samples, bias0):
+    off = np.ascontiguousarray(sample_offset, dtype=np.int64)
+    n = off.size - 1
+    out = np.zeros((n, abi.IMU_BLOB))
+    rc = lib().oracle_imu_preintegrate(C.byref(params), n, off.ctypes.data_as(abi.c_int64_p), _d(_arr(samples)), _d(_arr(bias0)), _d(out))
+    assert rc == 0
+    return out
+
+
+def wheel_preintegrate(params, step_offset, steps):
+    off = np.ascontiguousarray(step_offset, dtype=np.int64)
+    n = off.size - 1
+    out = np.zeros((n, abi.WHEEL_BLOB))
+    rc = lib().oracle_wheel_preintegrate(C.byref(params), n, off.ctypes.data_as(abi.c_int64_p), _d(_arr(steps)), _d(out))
+    assert rc == 0
+    return out
+
+
+def preintegrate_batch(params, sb):
+    """SensorBatch -> HostBatch through the ORACLE preintegrators (CPU tests only)."""
+    if sb.n_frames > 1:
+        imu = imu_preintegrate(params, sb.imu_offset, sb.imu_samples, sb.bias0)
+        wheel = wheel_preintegrate(params, sb.wheel_offset, sb.wheel_steps)
+    else:
+        imu = wheel = None
+    return sb.host_batch(imu, wheel)
+
+
+# ---- window level
+def linearize(params, hb, states=None, mode=0):
+    B, dim = hb.n_windows, 15 * hb.n_frames
+    H, g, cost = np.zeros((B, dim, dim)), np.zeros((B, dim)), np.zeros(B)
+    s = hb.struct()
+    st = None if states is None else _arr(states)
+    rc = lib().oracle_linearize(C.byref(params), C.byref(s), _d(st) if st is not None else dp(), int(mode), _d(H), _d(g), _d(cost))
+    assert rc == 0
+    return H, g, cost
+
+
+def cost(params, hb, states=None):
+    out = np.zeros(hb.n_windows)
+    s = hb.struct()
+    st = None if states is None else _arr(states)
+    lib().oracle_cost(C.byref(params), C.byref(s), _d(st) if st is not None else dp(), _d(out))
+    return out
+
+
+def solve(params, hb, n_threads=1):
+    B, n = hb.n_windows, hb.n_frames
+    states = np.zeros((B * n, 15))
+    summ = np.zeros(B, dtype=abi.SUMMARY_DTYPE)
+    s = hb.struct()
+    rc = lib().oracle_solve(C.byref(params), C.byref(s), _d(states), summ.ctypes.data_as(C.c_void_p), int(n_threads))
+    assert rc == 0
+    return states, summ
+
+
+def marginalize(params, hb, states=None):
+    B = hb.n_windows
+    X0, J, r, dH, dg = np.zeros((B, 15)), np.zeros((B, 15, 15)), np.zeros((B, 15)), np.zeros((B, 15, 15)), np.zeros((B, 15))
+    s = hb.struct()
+    st = None if states is None else _arr(states)
+    rc = lib().oracle_marginalize(C.byref(params), C.byref(s), _d(st) if st is not None else dp(), _d(X0), _d(J), _d(r), _d(dH), _d(dg))
+    assert rc == 0
+    return X0, J, r, dH, dg
+
+
+def max_threads():
+    return int(lib().oracle_max_threads())
