@@ -1,0 +1,431 @@
+// lv_math.cuh — scalar/dual-number rotation math and the small factors of the front-end solver,
+// written once for device code and (for CPU unit tests of the formulas only) host code.
+//
+// What it restates (reference file:line):
+//   lie::exp_so3 / log_SO3 / normalize_so3          src/utilies/common.h:121-163
+//   so3_parameterization (Plus = wrap(theta+delta)) src/factor/factor_common.h:40-53
+//   imu_factor residual                             src/factor/imu_factor.h:52-86
+//   wheel_odom_factor residual                      src/factor/wheel_factor.h:20-71
+//   ground_factor_p / ground_factor_q               src/factor/ground_factor.h:27-48, :59-82
+// The reference differentiates these with ceres::Jet<double,N>.  Here the derivative is carried by a
+// single-direction dual number (`Dual`): one lane of a warp evaluates one column of the Jacobian, and
+// only the non-linear pieces (rotations) are pushed through duals — the linear blocks of each
+// Jacobian are filled in closed form (see imu_jacobian_column).
+#pragma once
+#include <math.h>
+
+#if defined(__CUDACC__)
+#define LV_HD __host__ __device__ __forceinline__
+#else
+#define LV_HD inline
+#endif
+
+namespace lv {
+
+constexpr double kPi = 3.14159265358979323846;
+
+// ------------------------------------------------------------------ dual number a + d*eps
+struct Dual {
+    double a, d;
+    LV_HD Dual() : a(0.0), d(0.0) {}
+    LV_HD Dual(double a_) : a(a_), d(0.0) {}
+    LV_HD Dual(double a_, double d_) : a(a_), d(d_) {}
+};
+LV_HD Dual operator+(Dual x, Dual y) { return Dual(x.a + y.a, x.d + y.d); }
+LV_HD Dual operator-(Dual x, Dual y) { return Dual(x.a - y.a, x.d - y.d); }
+LV_HD Dual operator-(Dual x) { return Dual(-x.a, -x.d); }
+LV_HD Dual operator*(Dual x, Dual y) { return Dual(x.a * y.a, x.a * y.d + x.d * y.a); }
+LV_HD Dual operator/(Dual x, Dual y) {
+    const double yi = 1.0 / y.a, q = x.a * yi;
+    return Dual(q, (x.d - q * y.d) * yi);
+}
+LV_HD Dual operator+(Dual x, double s) { return Dual(x.a + s, x.d); }
+LV_HD Dual operator+(double s, Dual x) { return Dual(x.a + s, x.d); }
+LV_HD Dual operator-(Dual x, double s) { return Dual(x.a - s, x.d); }
+LV_HD Dual operator-(double s, Dual x) { return Dual(s - x.a, -x.d); }
+LV_HD Dual operator*(Dual x, double s) { return Dual(x.a * s, x.d * s); }
+LV_HD Dual operator*(double s, Dual x) { return Dual(x.a * s, x.d * s); }
+LV_HD Dual operator/(double s, Dual y) { const double yi = 1.0 / y.a, q = s * yi; return Dual(q, -q * y.d * yi); }
+LV_HD Dual operator/(Dual x, double s) { const double si = 1.0 / s; return Dual(x.a * si, x.d * si); }
+
+LV_HD double val(double x) { return x; }
+LV_HD double val(Dual x) { return x.a; }
+LV_HD double lv_sqrt(double x) { return sqrt(x); }
+LV_HD Dual lv_sqrt(Dual x) { const double t = sqrt(x.a); return Dual(t, x.d / (2.0 * t)); }
+LV_HD void lv_sincos(double x, double* s, double* c) {
+#if defined(__CUDA_ARCH__)
+    sincos(x, s, c);
+#else
+    *s = sin(x); *c = cos(x);
+#endif
+}
+LV_HD void lv_sincos(Dual x, Dual* s, Dual* c) {
+    double sv, cv;
+    lv_sincos(x.a, &sv, &cv);
+    *s = Dual(sv, cv * x.d);
+    *c = Dual(cv, -sv * x.d);
+}
+LV_HD double lv_asin(double x) { return asin(x); }
+LV_HD Dual lv_asin(Dual x) { return Dual(asin(x.a), x.d / sqrt(1.0 - x.a * x.a)); }
+LV_HD double lv_atan2(double y, double x) { return atan2(y, x); }
+LV_HD Dual lv_atan2(Dual y, Dual x) {
+    const double t = 1.0 / (x.a * x.a + y.a * y.a);
+    return Dual(atan2(y.a, x.a), t * (x.a * y.d - y.a * x.d));
+}
+
+// ------------------------------------------------------------------ 3-vectors / 3x3 (row-major)
+template <class T> struct V3 { T x, y, z; };
+template <class T> struct M3 { T m[9]; };
+
+template <class T> LV_HD V3<T> v3(T x, T y, T z) { V3<T> r; r.x = x; r.y = y; r.z = z; return r; }
+template <class T> LV_HD V3<T> operator+(const V3<T>& a, const V3<T>& b) { return v3<T>(a.x + b.x, a.y + b.y, a.z + b.z); }
+template <class T> LV_HD V3<T> operator-(const V3<T>& a, const V3<T>& b) { return v3<T>(a.x - b.x, a.y - b.y, a.z - b.z); }
+template <class T> LV_HD V3<T> neg(const V3<T>& a) { return v3<T>(-a.x, -a.y, -a.z); }
+template <class T> LV_HD V3<T> scale(const V3<T>& a, T s) { return v3<T>(a.x * s, a.y * s, a.z * s); }
+template <class T> LV_HD T dot(const V3<T>& a, const V3<T>& b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+template <class T> LV_HD V3<T> cross(const V3<T>& a, const V3<T>& b) {
+    return v3<T>(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x);
+}
+template <class T> LV_HD T norm(const V3<T>& a) { return lv_sqrt(dot(a, a)); }
+template <class T> LV_HD V3<T> mul(const M3<T>& A, const V3<T>& v) {
+    return v3<T>(A.m[0] * v.x + A.m[1] * v.y + A.m[2] * v.z, A.m[3] * v.x + A.m[4] * v.y + A.m[5] * v.z,
+                 A.m[6] * v.x + A.m[7] * v.y + A.m[8] * v.z);
+}
+template <class T> LV_HD V3<T> mul_t(const M3<T>& A, const V3<T>& v) {  // A^T v
+    return v3<T>(A.m[0] * v.x + A.m[3] * v.y + A.m[6] * v.z, A.m[1] * v.x + A.m[4] * v.y + A.m[7] * v.z,
+                 A.m[2] * v.x + A.m[5] * v.y + A.m[8] * v.z);
+}
+template <class T> LV_HD M3<T> mul(const M3<T>& A, const M3<T>& B) {
+    M3<T> C;
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) C.m[i * 3 + j] = A.m[i * 3] * B.m[j] + A.m[i * 3 + 1] * B.m[3 + j] + A.m[i * 3 + 2] * B.m[6 + j];
+    return C;
+}
+template <class T> LV_HD M3<T> mul_tn(const M3<T>& A, const M3<T>& B) {  // A^T B
+    M3<T> C;
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) C.m[i * 3 + j] = A.m[i] * B.m[j] + A.m[3 + i] * B.m[3 + j] + A.m[6 + i] * B.m[6 + j];
+    return C;
+}
+template <class T> LV_HD M3<T> lift(const M3<double>& A) {
+    M3<T> C;
+#pragma unroll
+    for (int i = 0; i < 9; ++i) C.m[i] = T(A.m[i]);
+    return C;
+}
+template <class T> LV_HD V3<T> lift(const V3<double>& a) { return v3<T>(T(a.x), T(a.y), T(a.z)); }
+LV_HD V3<double> load3(const double* p) { return v3<double>(p[0], p[1], p[2]); }
+
+// rigid transform [R | t] from a row-major 3x4 array
+struct Iso { M3<double> R; V3<double> t; };
+LV_HD Iso load_iso(const double* m) {
+    Iso T;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+#pragma unroll
+        for (int j = 0; j < 3; ++j) T.R.m[i * 3 + j] = m[i * 4 + j];
+    }
+    T.t = v3<double>(m[3], m[7], m[11]);
+    return T;
+}
+
+// ------------------------------------------------------------------ SO(3)
+// angle-axis -> unit quaternion -> rotation matrix (common.h:137-146 through ceres::AngleAxisToQuaternion
+// and Eigen::Quaternion::toRotationMatrix)
+template <class T> LV_HD M3<T> exp_so3(const V3<T>& w) {
+    const T th2 = w.x * w.x + w.y * w.y + w.z * w.z;
+    T qw, k;
+    if (val(th2) > 0.0) {
+        const T th = lv_sqrt(th2);
+        T s, c;
+        lv_sincos(th * 0.5, &s, &c);
+        k = s / th;
+        qw = c;
+    } else {
+        k = T(0.5);
+        qw = T(1.0);
+    }
+    const T qx = w.x * k, qy = w.y * k, qz = w.z * k;
+    const T tx = 2.0 * qx, ty = 2.0 * qy, tz = 2.0 * qz;
+    const T twx = tx * qw, twy = ty * qw, twz = tz * qw;
+    const T txx = tx * qx, txy = ty * qx, txz = tz * qx;
+    const T tyy = ty * qy, tyz = tz * qy, tzz = tz * qz;
+    M3<T> R;
+    R.m[0] = 1.0 - (tyy + tzz); R.m[1] = txy - twz;         R.m[2] = txz + twy;
+    R.m[3] = txy + twz;         R.m[4] = 1.0 - (txx + tzz); R.m[5] = tyz - twx;
+    R.m[6] = txz - twy;         R.m[7] = tyz + twx;         R.m[8] = 1.0 - (txx + tyy);
+    return R;
+}
+
+// common.h:121-135: scale an angle-axis vector whose norm exceeds pi back into (-pi, pi]
+template <class T> LV_HD V3<T> normalize_so3(const V3<T>& w) {
+    const T angle = norm(w);
+    if (!(val(angle) > kPi)) return w;
+    const double turns = floor((val(angle) + kPi) / (2.0 * kPi));  // floor: zero derivative
+    const T wrapped = angle - (2.0 * kPi) * turns;
+    return scale(scale(w, T(1.0) / angle), wrapped);
+}
+
+// rotation matrix -> quaternion (Eigen::Quaternion(Matrix3) branches) -> normalised -> angle-axis
+// (ceres::QuaternionToAngleAxis) -> wrapped (common.h:148-163)
+template <class T> LV_HD V3<T> log_so3(const M3<T>& R) {
+    T q[4];  // w x y z
+    T t = R.m[0] + R.m[4] + R.m[8];
+    if (val(t) > 0.0) {
+        t = lv_sqrt(t + 1.0);
+        q[0] = 0.5 * t;
+        t = 0.5 / t;
+        q[1] = (R.m[7] - R.m[5]) * t;
+        q[2] = (R.m[2] - R.m[6]) * t;
+        q[3] = (R.m[3] - R.m[1]) * t;
+    } else {
+        int i = 0;
+        if (val(R.m[4]) > val(R.m[0])) i = 1;
+        if (val(R.m[8]) > val(R.m[i * 4])) i = 2;
+        const int j = (i + 1) % 3, k = (j + 1) % 3;
+        t = lv_sqrt(R.m[i * 4] - R.m[j * 4] - R.m[k * 4] + 1.0);
+        q[1 + i] = 0.5 * t;
+        t = 0.5 / t;
+        q[0] = (R.m[k * 3 + j] - R.m[j * 3 + k]) * t;
+        q[1 + j] = (R.m[j * 3 + i] + R.m[i * 3 + j]) * t;
+        q[1 + k] = (R.m[k * 3 + i] + R.m[i * 3 + k]) * t;
+    }
+    const T qn = lv_sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+    const T qi = T(1.0) / qn;
+    const T w = q[0] * qi, x = q[1] * qi, y = q[2] * qi, z = q[3] * qi;
+    const T s2 = x * x + y * y + z * z;
+    T k;
+    if (val(s2) > 0.0) {
+        const T s = lv_sqrt(s2);
+        const T two_theta = 2.0 * ((val(w) < 0.0) ? lv_atan2(-s, -w) : lv_atan2(s, w));
+        k = two_theta / s;
+    } else {
+        k = T(2.0);
+    }
+    return normalize_so3(v3<T>(x * k, y * k, z * k));
+}
+
+// so3_parameterization::operator() (factor_common.h:40-53)
+LV_HD void so3_plus(const double* theta, const double* delta, double* out) {
+    V3<double> w = normalize_so3(v3<double>(theta[0] + delta[0], theta[1] + delta[1], theta[2] + delta[2]));
+    out[0] = w.x; out[1] = w.y; out[2] = w.z;
+}
+
+// ------------------------------------------------------------------ solver constants (PARAM() values)
+struct Consts {
+    double T_il[12];  // T_imu_to_laser, row-major 3x4
+    double T_io[12];  // T_imu_to_wheel
+    double g;
+    double laser_sqrt_info;       // 1/line_to_line_sigma      laser_factor.h:21
+    double ground_p_sqrt_info;    // 1/manifold_p_sigma        ground_factor.h:20
+    double ground_q_sqrt_info;    // 1/manifold_q_sigma        ground_factor.h:21
+    double Q[12];                 // diag(imu_noise::Q)        imu_preintegraption.h:30-42
+    double wheel_cov[3];          // diag(wheel_noise::cov)    wheel_odom_preintegration.h:19-22
+    double huber_delta;           // <= 0: none
+};
+
+// ------------------------------------------------------------------ ground factors (ground_factor.h)
+// both residuals of one pose; T = double gives values, T = Dual with the pose seeded along one of the
+// 6 directions gives one Jacobian column.
+template <class T> LV_HD void ground_residuals(const Consts& C, const V3<T>& p, const V3<T>& th, T* res_p, T* res_q) {
+    const Iso Tio = load_iso(C.T_io);
+    const M3<T> R = exp_so3(th);
+    // tf_w_o = make_tf(p, th) * T_io: height of the wheel frame and its z axis in the world
+    const T height = R.m[6] * Tio.t.x + R.m[7] * Tio.t.y + R.m[8] * Tio.t.z + p.z;
+    const V3<T> zax = v3<T>(R.m[0] * Tio.R.m[2] + R.m[1] * Tio.R.m[5] + R.m[2] * Tio.R.m[8],
+                            R.m[3] * Tio.R.m[2] + R.m[4] * Tio.R.m[5] + R.m[5] * Tio.R.m[8],
+                            R.m[6] * Tio.R.m[2] + R.m[7] * Tio.R.m[5] + R.m[8] * Tio.R.m[8]);
+    const V3<T> ez = v3<T>(T(0.0), T(0.0), T(1.0));
+    const T sinn = norm(cross(zax, ez));
+    *res_p = C.ground_p_sqrt_info * height;
+    *res_q = C.ground_q_sqrt_info * lv_asin(sinn);
+}
+
+// ------------------------------------------------------------------ wheel factor (wheel_factor.h:20-71)
+// blob = delta_Tij[3x4] | sqrt_info diag[3]
+template <class T>
+LV_HD void wheel_residuals(const Consts& C, const double* blob, const V3<T>& pi, const V3<T>& thi, const V3<T>& pj,
+                           const V3<T>& thj, T* res) {
+    const Iso Tio = load_iso(C.T_io);
+    const Iso dT = load_iso(blob);
+    const M3<T> Ri = exp_so3(thi), Rj = exp_so3(thj);
+    const M3<T> Rio = lift<T>(Tio.R);
+    const V3<T> tio = lift<T>(Tio.t);
+    // tf_i = make_tf(pi, thi) * T_io ; tf_j likewise ; w_tf_ij = tf_i^-1 * tf_j
+    const M3<T> Roi = mul(Ri, Rio), Roj = mul(Rj, Rio);
+    const V3<T> toi = mul(Ri, tio) + pi, toj = mul(Rj, tio) + pj;
+    const V3<T> p = mul_t(Roi, toj - toi);
+    const V3<T> q = log_so3(mul_tn(Roi, Roj));
+    const V3<double> op = dT.t;
+    const V3<double> oq = log_so3(dT.R);
+    const double o_len = sqrt(op.x * op.x + op.y * op.y);
+    const T len = lv_sqrt(p.x * p.x + p.y * p.y);
+    T angle;
+    if (o_len > 0.0001 && val(len) > 0.0001) {
+        // |o_dir x dir| of the two unit xy-directions
+        const T cz = (op.x / o_len) * (p.y / len) - (op.y / o_len) * (p.x / len);
+        const T sinn = lv_sqrt(cz * cz);
+        angle = lv_asin(sinn);
+    } else {
+        angle = len;
+    }
+    if (val(len) < 0.0001 || o_len < 0.0001)
+        res[0] = blob[12] * len;
+    else
+        res[0] = blob[12] * (o_len - len);
+    res[1] = blob[13] * angle;
+    const T qn = norm(q);
+    const double oqn = norm(oq);
+    if (val(qn) < 0.001 || oqn < 0.001)
+        res[2] = blob[14] * qn;
+    else
+        res[2] = blob[14] * (oqn - qn);
+}
+
+// ------------------------------------------------------------------ imu factor (imu_factor.h:52-86)
+// blob = X[15] | J[15x15] | sqrt_inverse_P[15x15] | Dt.  States are [p q v ba bw].
+// Un-whitened residual (before res_all = sqrt_info * res_all, imu_factor.h:85-86).
+template <class T>
+LV_HD void imu_rotation_residual(const double* blob, const V3<T>& thi, const V3<T>& bwi, const V3<T>& thj, V3<T>* r_gamma) {
+    const double* X = blob;
+    const double* J = blob + 15;
+    const V3<T> dbw = v3<T>(bwi.x - X[12], bwi.y - X[13], bwi.z - X[14]);
+    // gamma_hat = gamma + J_gamma_bw (bw_i - bw_lin)
+    const V3<T> gam = v3<T>(X[6] + (J[6 * 15 + 12] * dbw.x + J[6 * 15 + 13] * dbw.y + J[6 * 15 + 14] * dbw.z),
+                            X[7] + (J[7 * 15 + 12] * dbw.x + J[7 * 15 + 13] * dbw.y + J[7 * 15 + 14] * dbw.z),
+                            X[8] + (J[8 * 15 + 12] * dbw.x + J[8 * 15 + 13] * dbw.y + J[8 * 15 + 14] * dbw.z));
+    const M3<T> E = exp_so3(neg(gam));
+    const M3<T> RiT = exp_so3(neg(thi));
+    const M3<T> Rj = exp_so3(thj);
+    *r_gamma = log_so3(mul(E, mul(RiT, Rj)));
+}
+
+LV_HD void imu_raw_residual(const Consts& C, const double* blob, const double* si, const double* sj, double* r /*[15]*/) {
+    const double* X = blob;
+    const double* J = blob + 15;
+    const double Dt = blob[465];
+    const V3<double> pi = load3(si), thi = load3(si + 3), vi = load3(si + 6), bai = load3(si + 9), bwi = load3(si + 12);
+    const V3<double> pj = load3(sj), thj = load3(sj + 3), vj = load3(sj + 6), baj = load3(sj + 9), bwj = load3(sj + 12);
+    const V3<double> dba = v3<double>(bai.x - X[9], bai.y - X[10], bai.z - X[11]);
+    const V3<double> dbw = v3<double>(bwi.x - X[12], bwi.y - X[13], bwi.z - X[14]);
+    double ab[6];
+#pragma unroll
+    for (int k = 0; k < 6; ++k)
+        ab[k] = X[k] + (J[k * 15 + 9] * dba.x + J[k * 15 + 10] * dba.y + J[k * 15 + 11] * dba.z) +
+                (J[k * 15 + 12] * dbw.x + J[k * 15 + 13] * dbw.y + J[k * 15 + 14] * dbw.z);
+    const M3<double> RiT = exp_so3(neg(thi));
+    const double gz = C.g;
+    const V3<double> y1 = v3<double>(pj.x - pi.x - vi.x * Dt, pj.y - pi.y - vi.y * Dt, pj.z - pi.z + 0.5 * gz * Dt * Dt - vi.z * Dt);
+    const V3<double> y2 = v3<double>(vj.x - vi.x, vj.y - vi.y, vj.z + gz * Dt - vi.z);
+    const V3<double> a = mul(RiT, y1), b = mul(RiT, y2);
+    r[0] = ab[0] - a.x; r[1] = ab[1] - a.y; r[2] = ab[2] - a.z;
+    r[3] = ab[3] - b.x; r[4] = ab[4] - b.y; r[5] = ab[5] - b.z;
+    V3<double> rg;
+    imu_rotation_residual<double>(blob, thi, bwi, thj, &rg);
+    r[6] = rg.x; r[7] = rg.y; r[8] = rg.z;
+    r[9] = baj.x - bai.x; r[10] = baj.y - bai.y; r[11] = baj.z - bai.z;
+    r[12] = bwj.x - bwi.x; r[13] = bwj.y - bwi.y; r[14] = bwj.z - bwi.z;
+}
+
+// Column `c` (0..29) of the un-whitened 15x30 Jacobian; columns follow the functor's parameter order
+// (p_i q_i v_i bs_i p_j q_j v_j bs_j).  Linear blocks in closed form, rotation blocks through Dual.
+LV_HD void imu_jacobian_column(const Consts& C, const double* blob, const double* si, const double* sj, int c, double* col /*[15]*/) {
+    const double* X = blob;
+    const double* J = blob + 15;
+    const double Dt = blob[465];
+#pragma unroll
+    for (int k = 0; k < 15; ++k) col[k] = 0.0;
+    const V3<double> thi = load3(si + 3), bwi = load3(si + 12), thj = load3(sj + 3);
+    const int blk = c / 3, k = c % 3;  // 0 p_i 1 q_i 2 v_i 3 ba_i 4 bw_i 5 p_j 6 q_j 7 v_j 8 ba_j 9 bw_j
+    if (blk == 1) {
+        // theta_i: rows 0-5 = -(d R_i^T / d theta_k) y, rows 6-8 through the rotation residual
+        V3<Dual> th = lift<Dual>(thi);
+        (k == 0 ? th.x : (k == 1 ? th.y : th.z)).d = 1.0;
+        const M3<Dual> RiT = exp_so3(neg(th));
+        const V3<double> pi = load3(si), vi = load3(si + 6), pj = load3(sj), vj = load3(sj + 6);
+        const double gz = C.g;
+        const V3<double> y1 = v3<double>(pj.x - pi.x - vi.x * Dt, pj.y - pi.y - vi.y * Dt, pj.z - pi.z + 0.5 * gz * Dt * Dt - vi.z * Dt);
+        const V3<double> y2 = v3<double>(vj.x - vi.x, vj.y - vi.y, vj.z + gz * Dt - vi.z);
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+            col[r] = -(RiT.m[r * 3].d * y1.x + RiT.m[r * 3 + 1].d * y1.y + RiT.m[r * 3 + 2].d * y1.z);
+            col[3 + r] = -(RiT.m[r * 3].d * y2.x + RiT.m[r * 3 + 1].d * y2.y + RiT.m[r * 3 + 2].d * y2.z);
+        }
+        V3<Dual> rg;
+        imu_rotation_residual<Dual>(blob, th, lift<Dual>(bwi), lift<Dual>(thj), &rg);
+        col[6] = rg.x.d; col[7] = rg.y.d; col[8] = rg.z.d;
+        return;
+    }
+    if (blk == 4) {
+        // bw_i: first-order bias correction columns + rotation residual + (-I) on r_bw
+#pragma unroll
+        for (int r = 0; r < 6; ++r) col[r] = J[r * 15 + 12 + k];
+        V3<Dual> bw = lift<Dual>(bwi);
+        (k == 0 ? bw.x : (k == 1 ? bw.y : bw.z)).d = 1.0;
+        V3<Dual> rg;
+        imu_rotation_residual<Dual>(blob, lift<Dual>(thi), bw, lift<Dual>(thj), &rg);
+        col[6] = rg.x.d; col[7] = rg.y.d; col[8] = rg.z.d;
+        col[12 + k] = -1.0;
+        return;
+    }
+    if (blk == 6) {
+        V3<Dual> th = lift<Dual>(thj);
+        (k == 0 ? th.x : (k == 1 ? th.y : th.z)).d = 1.0;
+        V3<Dual> rg;
+        imu_rotation_residual<Dual>(blob, lift<Dual>(thi), lift<Dual>(bwi), th, &rg);
+        col[6] = rg.x.d; col[7] = rg.y.d; col[8] = rg.z.d;
+        return;
+    }
+    if (blk == 3) {  // ba_i
+#pragma unroll
+        for (int r = 0; r < 6; ++r) col[r] = J[r * 15 + 9 + k];
+        col[9 + k] = -1.0;
+        return;
+    }
+    if (blk == 8) { col[9 + k] = 1.0; return; }    // ba_j
+    if (blk == 9) { col[12 + k] = 1.0; return; }   // bw_j
+    // p_i, v_i, p_j, v_j: +-R_i^T columns
+    const M3<double> RiT = exp_so3(neg(thi));
+    const double c0 = RiT.m[k], c1 = RiT.m[3 + k], c2 = RiT.m[6 + k];
+    if (blk == 0) { col[0] = c0; col[1] = c1; col[2] = c2; }                       // d r_alpha / d p_i = +R_i^T
+    if (blk == 5) { col[0] = -c0; col[1] = -c1; col[2] = -c2; }                    // d r_alpha / d p_j = -R_i^T
+    if (blk == 2) { col[0] = c0 * Dt; col[1] = c1 * Dt; col[2] = c2 * Dt; col[3] = c0; col[4] = c1; col[5] = c2; }  // v_i
+    if (blk == 7) { col[3] = -c0; col[4] = -c1; col[5] = -c2; }                    // v_j
+}
+
+// ------------------------------------------------------------------ laser frame table
+// C = P (R(theta_j) (R_il c + t_il) + p_j) restricted to xy is the affine map  C = M c + t  on the 2-D
+// scan point; d C / d theta_k = B_k c + b_k (SURVEY.md verification note).  Layout (24 doubles):
+//   [M00 M01 M10 M11 t0 t1 | B0(4) b0(2) | B1(4) b1(2) | B2(4) b2(2)]
+constexpr int kFrameTab = 24;
+LV_HD void laser_frame_table(const Consts& C, const double* pose /*p q*/, double* tab) {
+    const Iso Til = load_iso(C.T_il);
+    const V3<double> th = load3(pose + 3);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        V3<Dual> thd = lift<Dual>(th);
+        (k == 0 ? thd.x : (k == 1 ? thd.y : thd.z)).d = 1.0;
+        const M3<Dual> R = exp_so3(thd);
+        // rows 0,1 of R * R_il (columns 0,1) and of R * t_il
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            Dual m0 = R.m[r * 3] * Til.R.m[0] + R.m[r * 3 + 1] * Til.R.m[3] + R.m[r * 3 + 2] * Til.R.m[6];
+            Dual m1 = R.m[r * 3] * Til.R.m[1] + R.m[r * 3 + 1] * Til.R.m[4] + R.m[r * 3 + 2] * Til.R.m[7];
+            Dual tt = R.m[r * 3] * Til.t.x + R.m[r * 3 + 1] * Til.t.y + R.m[r * 3 + 2] * Til.t.z;
+            tab[6 + 6 * k + 2 * r] = m0.d;
+            tab[6 + 6 * k + 2 * r + 1] = m1.d;
+            tab[6 + 6 * k + 4 + r] = tt.d;
+            if (k == 0) {
+                tab[2 * r] = m0.a;
+                tab[2 * r + 1] = m1.a;
+                tab[4 + r] = tt.a + pose[r];
+            }
+        }
+    }
+}
+
+}  // namespace lv

@@ -1,0 +1,656 @@
+// lvio2d_api.cu — host side of the C ABI (include/lvio2d.h): context, device buffers, kernel launches.
+// Everything runs on one CUDA stream owned by the context; there is no CPU compute path.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "../../include/lvio2d.h"
+#include "aux_kernels.cuh"
+
+using namespace lv;
+
+namespace {
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    bool ensure(size_t bytes) {
+        if (bytes <= cap) return true;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        if (cudaMalloc(&p, bytes) != cudaSuccess) return false;
+        cap = bytes;
+        return true;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    template <class T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+}  // namespace
+
+struct lvio2d_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    lvio2d_params params;
+    Consts C;
+    LMOptions opt;
+    char err[512] = {0};
+    int sm_count = 148;
+
+    // problem
+    bool have = false, bound = false;
+    int B = 0, n = 0, ground_mult = 0, prior_frame = -1;
+    bool arrow = false, has_weight = false, has_imu = false, has_wheel = false;
+    int64_t N = 0, L = 0;
+    int tiles = 1, line_cap = 1, npad = kPadTrack;
+    int shard_rank = 0, shard_world = 1;
+    // inputs (owned copies, or borrowed device pointers when bound)
+    DevBuf b_points, b_pline, b_pweight, b_poff, b_loff, b_lines, b_ref, b_refpose, b_imu, b_wheel, b_pX0, b_pJ, b_cmask;
+    const double2* points = nullptr; const int32_t* point_line = nullptr; const double* point_weight = nullptr;
+    const int64_t* point_offset = nullptr; const int64_t* line_offset = nullptr; const double4* lines = nullptr;
+    const int32_t* ref_frame = nullptr; const double* ref_pose = nullptr; const double* imu = nullptr; const double* wheel = nullptr;
+    const double* prior_X0 = nullptr; const double* prior_J = nullptr; const uint8_t* const_mask = nullptr;
+    // work buffers
+    DevBuf b_x0, b_x, b_xc, b_scale, b_ftab, b_reftab, b_wlines, b_part, b_lb, b_pair, b_fac, b_state, b_status, b_active, b_active1, b_reduce;
+    DevBuf b_tmp[8];
+    double* ext_reduce = nullptr; int64_t ext_reduce_count = 0;
+    int step_calls = 0;
+    bool have_solution = false;
+};
+
+namespace {
+
+int fail(lvio2d_ctx* c, int code, const char* what, cudaError_t e = cudaSuccess) {
+    if (c) snprintf(c->err, sizeof(c->err), "%s%s%s", what, e != cudaSuccess ? ": " : "", e != cudaSuccess ? cudaGetErrorString(e) : "");
+    return code;
+}
+#define CK(call)                                                              \
+    do {                                                                      \
+        cudaError_t e_ = (call);                                              \
+        if (e_ != cudaSuccess) return fail(ctx, LVIO2D_ERR_CUDA, #call, e_); \
+    } while (0)
+
+Consts make_consts(const lvio2d_params& p) {
+    Consts C;
+    std::memcpy(C.T_il, p.T_imu_to_laser, sizeof(C.T_il));
+    std::memcpy(C.T_io, p.T_imu_to_wheel, sizeof(C.T_io));
+    C.g = p.g;
+    C.laser_sqrt_info = 1.0 / p.line_to_line_sigma;
+    C.ground_p_sqrt_info = 1.0 / p.manifold_p_sigma;
+    C.ground_q_sqrt_info = 1.0 / p.manifold_q_sigma;
+    for (int i = 0; i < 3; ++i) {
+        C.Q[i] = p.imu_noise_acc_sigma[i] * p.imu_noise_acc_sigma[i];
+        C.Q[3 + i] = p.imu_noise_gyro_sigma[i] * p.imu_noise_gyro_sigma[i];
+        C.Q[6 + i] = p.imu_bias_acc_sigma[i] * p.imu_bias_acc_sigma[i];
+        C.Q[9 + i] = p.imu_bias_gyro_sigma[i] * p.imu_bias_gyro_sigma[i];
+        C.wheel_cov[i] = p.wheel_sigma[i] * p.wheel_sigma[i];
+    }
+    C.huber_delta = p.huber_delta;
+    return C;
+}
+LMOptions make_opts(const lvio2d_params& p) {
+    LMOptions o;
+    o.max_iters = p.max_iters > 0 ? p.max_iters : 50;
+    o.function_tolerance = p.function_tolerance > 0 ? p.function_tolerance : 1e-6;
+    o.gradient_tolerance = p.gradient_tolerance > 0 ? p.gradient_tolerance : 1e-10;
+    o.parameter_tolerance = p.parameter_tolerance > 0 ? p.parameter_tolerance : 1e-8;
+    o.initial_radius = p.initial_trust_region_radius > 0 ? p.initial_trust_region_radius : 1e4;
+    o.max_radius = 1e16; o.min_radius = 1e-32; o.min_relative_decrease = 1e-3;
+    o.min_lm_diagonal = 1e-6; o.max_lm_diagonal = 1e32; o.max_consecutive_invalid = 5;
+    return o;
+}
+
+// copy (host->device) or alias (device pointer) one input array
+template <class T>
+int take(lvio2d_ctx* ctx, bool bind, DevBuf& buf, const T*& dst, const void* src, size_t count) {
+    if (!src || count == 0) { dst = nullptr; return LVIO2D_OK; }
+    if (bind) { dst = reinterpret_cast<const T*>(src); return LVIO2D_OK; }
+    if (!buf.ensure(count * sizeof(T))) return fail(ctx, LVIO2D_ERR_ALLOC, "cudaMalloc(input)");
+    CK(cudaMemcpyAsync(buf.p, src, count * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
+    dst = buf.as<T>();
+    return LVIO2D_OK;
+}
+
+size_t window_smem_bytes(const lvio2d_ctx* c) { return WarpSmem::doubles(c->n, c->npad) * sizeof(double); }
+
+int launch_scan_match(lvio2d_ctx* ctx, int mode = 0) {
+    ScanMatchArgs a;
+    a.points = ctx->points; a.point_line = ctx->point_line; a.point_weight = ctx->point_weight;
+    a.point_offset = ctx->point_offset; a.line_offset = ctx->line_offset;
+    a.wlines = ctx->b_wlines.as<double4>(); a.lines = ctx->lines; a.ref_frame = ctx->ref_frame;
+    a.frame_tab = ctx->b_ftab.as<double>(); a.frame_active = (mode == 1 ? ctx->b_active1 : ctx->b_active).as<uint8_t>();
+    a.win_status = ctx->b_status.as<int32_t>(); a.partial = ctx->b_part.as<double>();
+    a.n_frames = ctx->n; a.tiles = ctx->tiles; a.n_items = ctx->B * ctx->n * ctx->tiles;
+    a.line_cap = ctx->line_cap; a.shard_rank = ctx->shard_rank; a.shard_world = ctx->shard_world;
+    if (ctx->N == 0) return LVIO2D_OK;
+    const int wpc = 8;
+    const int grid = (a.n_items + wpc - 1) / wpc;
+    const size_t smem = (size_t)wpc * ctx->line_cap * (ctx->arrow ? kRowFree : kRowTrack) * sizeof(double);
+#define LAUNCH_SM(RF, HW)                                                                                                \
+    do {                                                                                                                 \
+        CK(cudaFuncSetAttribute(scan_match_kernel<RF, HW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));     \
+        scan_match_kernel<RF, HW><<<grid, wpc * 32, smem, ctx->stream>>>(a);                                             \
+    } while (0)
+    if (ctx->arrow) { if (ctx->has_weight) LAUNCH_SM(true, true); else LAUNCH_SM(true, false); }
+    else { if (ctx->has_weight) LAUNCH_SM(false, true); else LAUNCH_SM(false, false); }
+#undef LAUNCH_SM
+    CK(cudaGetLastError());
+    return LVIO2D_OK;
+}
+
+WindowArgs window_args(lvio2d_ctx* ctx, int mode) {
+    WindowArgs a;
+    std::memset(&a, 0, sizeof(a));
+    a.C = ctx->C; a.opt = ctx->opt;
+    a.n_windows = ctx->B; a.n_frames = ctx->n; a.tiles = ctx->tiles; a.arrow = ctx->arrow; a.mode = mode;
+    a.ground_multiplicity = ctx->ground_mult; a.prior_frame = ctx->prior_frame;
+    a.has_imu = ctx->has_imu; a.has_wheel = ctx->has_wheel;
+    a.const_mask = ctx->const_mask; a.frame_active = (mode == 1 ? ctx->b_active1 : ctx->b_active).as<uint8_t>(); a.ref_frame = ctx->ref_frame;
+    a.imu = ctx->imu; a.wheel = ctx->wheel; a.prior_X0 = ctx->prior_X0; a.prior_J = ctx->prior_J;
+    a.partial = ctx->b_part.as<double>();
+    a.x = ctx->b_x.as<double>(); a.xc = ctx->b_xc.as<double>(); a.scale = ctx->b_scale.as<double>();
+    a.laser_blocks = ctx->b_lb.as<double>(); a.frame_tab = ctx->b_ftab.as<double>();
+    a.pair = ctx->b_pair.as<double>(); a.fac = ctx->b_fac.as<double>();
+    a.state = ctx->b_state.as<LMState>(); a.win_status = ctx->b_status.as<int32_t>();
+    return a;
+}
+
+int launch_window(lvio2d_ctx* ctx, const WindowArgs& a) {
+    const int per_warp = (int)WarpSmem::doubles(ctx->n, ctx->npad);
+    const int wpc = std::max(1, std::min<int>(4, (int)((200 * 1024) / (per_warp * sizeof(double)))));
+    const size_t smem = (size_t)wpc * per_warp * sizeof(double);
+    const int grid = (ctx->B + wpc - 1) / wpc;
+    if (ctx->arrow) {
+        CK(cudaFuncSetAttribute(window_step_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        window_step_kernel<true><<<grid, wpc * 32, smem, ctx->stream>>>(a, per_warp);
+    } else {
+        CK(cudaFuncSetAttribute(window_step_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        window_step_kernel<false><<<grid, wpc * 32, smem, ctx->stream>>>(a, per_warp);
+    }
+    CK(cudaGetLastError());
+    return LVIO2D_OK;
+}
+
+// (re)initialise the minimiser at the initial states (b_x0) or, for linearize/marginalize after a solve, at the solution (b_x)
+int begin_solve(lvio2d_ctx* ctx, bool from_solution = false) {
+    const size_t ns = (size_t)ctx->B * ctx->n * 15;
+    const void* src = from_solution ? ctx->b_x.p : ctx->b_x0.p;
+    CK(cudaMemcpyAsync(ctx->b_xc.p, src, ns * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+    if (!from_solution) CK(cudaMemcpyAsync(ctx->b_x.p, src, ns * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+    std::vector<LMState> st(ctx->B);
+    for (auto& s : st) {
+        std::memset(&s, 0, sizeof(s));
+        s.radius = ctx->opt.initial_radius;
+        s.decrease_factor = 2.0;
+    }
+    CK(cudaMemcpyAsync(ctx->b_state.p, st.data(), sizeof(LMState) * ctx->B, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));  // st is a stack vector
+    CK(cudaMemsetAsync(ctx->b_status.p, 0, sizeof(int32_t) * ctx->B, ctx->stream));
+    const int F = ctx->B * ctx->n;
+    frame_table_kernel<<<(F + 127) / 128, 128, 0, ctx->stream>>>(ctx->C, ctx->b_xc.as<double>(), 15, ctx->b_ftab.as<double>(), F);
+    CK(cudaGetLastError());
+    ctx->step_calls = 0;
+    return LVIO2D_OK;
+}
+
+int setup_batch(lvio2d_ctx* ctx, const lvio2d_window_batch* b, bool bind) {
+    if (!ctx || !b) return LVIO2D_ERR_INVALID_ARG;
+    if (b->n_windows < 1 || b->n_frames < 1 || !b->states) return fail(ctx, LVIO2D_ERR_INVALID_ARG, "n_windows/n_frames/states");
+    if (b->n_frames > 64) return fail(ctx, LVIO2D_ERR_DOMAIN, "n_frames > 64");
+    CK(cudaSetDevice(ctx->device));
+    ctx->have = false;
+    const int B = b->n_windows, n = b->n_frames, F = B * n;
+    ctx->B = B; ctx->n = n; ctx->bound = bind;
+    ctx->ground_mult = b->ground_multiplicity;
+    ctx->prior_frame = (b->prior_frame >= 0 && b->prior_X0 && b->prior_J) ? b->prior_frame : -1;
+    if (ctx->prior_frame >= n) return fail(ctx, LVIO2D_ERR_INVALID_ARG, "prior_frame >= n_frames");
+    ctx->has_imu = b->imu != nullptr && n > 1;
+    ctx->has_wheel = b->wheel != nullptr && n > 1;
+    ctx->has_weight = b->point_weight != nullptr;
+
+    // host-side views of the small index arrays (offsets, masks, ref frames) to derive the launch shape
+    std::vector<int64_t> poff(F + 1, 0), loff(F + 1, 0);
+    std::vector<int32_t> rf(F, -1);
+    std::vector<uint8_t> cm(F, 0);
+    const bool has_laser = b->point_offset && b->points && b->point_line && b->line_offset && b->lines;
+    if (bind) {
+        if (has_laser) {
+            CK(cudaMemcpy(poff.data(), b->point_offset, sizeof(int64_t) * (F + 1), cudaMemcpyDeviceToHost));
+            CK(cudaMemcpy(loff.data(), b->line_offset, sizeof(int64_t) * (F + 1), cudaMemcpyDeviceToHost));
+            if (b->ref_frame) CK(cudaMemcpy(rf.data(), b->ref_frame, sizeof(int32_t) * F, cudaMemcpyDeviceToHost));
+        }
+        if (b->const_mask) CK(cudaMemcpy(cm.data(), b->const_mask, F, cudaMemcpyDeviceToHost));
+    } else {
+        if (has_laser) {
+            std::memcpy(poff.data(), b->point_offset, sizeof(int64_t) * (F + 1));
+            std::memcpy(loff.data(), b->line_offset, sizeof(int64_t) * (F + 1));
+            if (b->ref_frame) std::memcpy(rf.data(), b->ref_frame, sizeof(int32_t) * F);
+        }
+        if (b->const_mask) std::memcpy(cm.data(), b->const_mask, F);
+    }
+    ctx->N = has_laser ? poff[F] : 0;
+    ctx->L = has_laser ? loff[F] : 0;
+    bool arrow = false;
+    int line_cap = 1;
+    std::vector<uint8_t> active(F, 0), active1(F, 0);
+    for (int f = 0; f < F; ++f) {
+        if (!has_laser) break;
+        const int64_t np = poff[f + 1] - poff[f], nl = loff[f + 1] - loff[f];
+        if (np < 0 || nl < 0) return fail(ctx, LVIO2D_ERR_INVALID_ARG, "offsets must be non-decreasing");
+        if (np == 0) continue;
+        active1[f] = 1;
+        line_cap = std::max<int>(line_cap, (int)nl);
+        const int w0 = (f / n) * n;
+        bool act = (cm[f] & 3) != 3;
+        if (rf[f] >= 0) {
+            // the arrow solver keeps fill-in bounded only when every in-window reference frame is frame 0
+            if (rf[f] != 0 || f == w0) return fail(ctx, LVIO2D_ERR_DOMAIN, "ref_frame must be -1 or 0 (and not the frame itself)");
+            arrow = true;
+            act = act || (cm[w0] & 3) != 3;
+        }
+        active[f] = act ? 1 : 0;
+    }
+    if (line_cap > 512) return fail(ctx, LVIO2D_ERR_DOMAIN, "more than 512 lines in one local map");
+    ctx->arrow = arrow;
+    ctx->line_cap = line_cap;
+    ctx->npad = arrow ? kPadFree : kPadTrack;
+    // tiles: enough warps to fill the machine a few times over, at least ~64 points per tile
+    {
+        const int64_t target = (int64_t)ctx->sm_count * 32;
+        int tiles = (int)std::min<int64_t>(16, std::max<int64_t>(1, (target + F - 1) / F));
+        const int64_t avg = F > 0 ? ctx->N / F : 0;
+        tiles = (int)std::max<int64_t>(1, std::min<int64_t>(tiles, avg / 64));
+        ctx->tiles = tiles;
+    }
+    const size_t smem_scan = (size_t)8 * line_cap * (arrow ? kRowFree : kRowTrack) * sizeof(double);
+    if (smem_scan > 200 * 1024) return fail(ctx, LVIO2D_ERR_DOMAIN, "local map too large for shared memory");
+    if (window_smem_bytes(ctx) > 200 * 1024) return fail(ctx, LVIO2D_ERR_DOMAIN, "n_frames too large for shared memory");
+
+    int rc;
+    if ((rc = take<double2>(ctx, bind, ctx->b_points, ctx->points, has_laser ? b->points : nullptr, (size_t)ctx->N))) return rc;
+    if ((rc = take<int32_t>(ctx, bind, ctx->b_pline, ctx->point_line, has_laser ? b->point_line : nullptr, (size_t)ctx->N))) return rc;
+    if ((rc = take<double>(ctx, bind, ctx->b_pweight, ctx->point_weight, has_laser ? b->point_weight : nullptr, (size_t)ctx->N))) return rc;
+    if ((rc = take<int64_t>(ctx, false, ctx->b_poff, ctx->point_offset, poff.data(), (size_t)F + 1))) return rc;
+    if ((rc = take<int64_t>(ctx, false, ctx->b_loff, ctx->line_offset, loff.data(), (size_t)F + 1))) return rc;
+    if ((rc = take<double4>(ctx, bind, ctx->b_lines, ctx->lines, has_laser ? b->lines : nullptr, (size_t)ctx->L))) return rc;
+    if ((rc = take<int32_t>(ctx, false, ctx->b_ref, ctx->ref_frame, rf.data(), (size_t)F))) return rc;
+    if ((rc = take<uint8_t>(ctx, false, ctx->b_cmask, ctx->const_mask, cm.data(), (size_t)F))) return rc;
+    if ((rc = take<double>(ctx, bind, ctx->b_refpose, ctx->ref_pose, has_laser ? b->ref_pose : nullptr, (size_t)F * 6))) return rc;
+    if ((rc = take<double>(ctx, bind, ctx->b_imu, ctx->imu, ctx->has_imu ? b->imu : nullptr, (size_t)B * (n - 1) * LVIO2D_IMU_BLOB))) return rc;
+    if ((rc = take<double>(ctx, bind, ctx->b_wheel, ctx->wheel, ctx->has_wheel ? b->wheel : nullptr, (size_t)B * (n - 1) * LVIO2D_WHEEL_BLOB))) return rc;
+    if ((rc = take<double>(ctx, bind, ctx->b_pX0, ctx->prior_X0, ctx->prior_frame >= 0 ? b->prior_X0 : nullptr, (size_t)B * 15))) return rc;
+    if ((rc = take<double>(ctx, bind, ctx->b_pJ, ctx->prior_J, ctx->prior_frame >= 0 ? b->prior_J : nullptr, (size_t)B * 225))) return rc;
+
+    const size_t ns = (size_t)F * 15 * sizeof(double);
+    bool ok = ctx->b_x0.ensure(ns) && ctx->b_x.ensure(ns) && ctx->b_xc.ensure(ns) && ctx->b_scale.ensure(ns) &&
+              ctx->b_ftab.ensure((size_t)F * kFrameTab * sizeof(double)) && ctx->b_reftab.ensure((size_t)F * kFrameTab * sizeof(double)) &&
+              ctx->b_wlines.ensure(std::max<size_t>(1, (size_t)ctx->L) * sizeof(double4)) &&
+              ctx->b_part.ensure((size_t)F * ctx->tiles * ctx->npad * sizeof(double)) && ctx->b_lb.ensure((size_t)F * ctx->npad * sizeof(double)) &&
+              ctx->b_pair.ensure(std::max<size_t>(1, (size_t)B * (n - 1)) * 3 * kBlk * sizeof(double)) &&
+              ctx->b_fac.ensure((size_t)F * 3 * kBlk * sizeof(double)) && ctx->b_state.ensure(sizeof(LMState) * B) &&
+              ctx->b_status.ensure(sizeof(int32_t) * B) && ctx->b_active.ensure(F) && ctx->b_active1.ensure(F) && ctx->b_reduce.ensure((size_t)F * ctx->npad * sizeof(double));
+    if (!ok) return fail(ctx, LVIO2D_ERR_ALLOC, "cudaMalloc(work buffers)");
+    CK(cudaMemcpyAsync(ctx->b_x0.p, b->states, ns, bind ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->b_active.p, active.data(), F, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->b_active1.p, active1.data(), F, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemsetAsync(ctx->b_part.p, 0, (size_t)F * ctx->tiles * ctx->npad * sizeof(double), ctx->stream));
+    CK(cudaMemsetAsync(ctx->b_pair.p, 0, std::max<size_t>(1, (size_t)B * (n - 1)) * 3 * kBlk * sizeof(double), ctx->stream));
+    if (has_laser && ctx->L > 0) {
+        // world lines of every local map that hangs under an external constant pose
+        frame_table_kernel<<<(F + 127) / 128, 128, 0, ctx->stream>>>(ctx->C, ctx->ref_pose, 6, ctx->b_reftab.as<double>(), F);
+        world_lines_kernel<<<F, 128, 0, ctx->stream>>>(ctx->lines, ctx->line_offset, ctx->ref_frame,
+                                                       ctx->b_reftab.as<double>(), ctx->b_wlines.as<double4>(), F);
+        CK(cudaGetLastError());
+    }
+    CK(cudaStreamSynchronize(ctx->stream));  // host vectors above go out of scope
+    ctx->ext_reduce = nullptr;
+    ctx->have = true;
+    ctx->have_solution = false;
+    return LVIO2D_OK;
+}
+
+int run_linearize(lvio2d_ctx* ctx, int mode, WindowArgs& a) {
+    int rc = begin_solve(ctx, ctx->have_solution);
+    if (rc) return rc;
+    if ((rc = launch_scan_match(ctx, mode))) return rc;
+    a.x = ctx->b_x.as<double>();
+    return launch_window(ctx, a);
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* lvio2d_strerror(int status) {
+    switch (status) {
+        case LVIO2D_OK: return "ok";
+        case LVIO2D_ERR_INVALID_ARG: return "invalid argument";
+        case LVIO2D_ERR_NO_DEVICE: return "no CUDA sm_100 device (the library has no CPU path)";
+        case LVIO2D_ERR_CUDA: return "CUDA error";
+        case LVIO2D_ERR_NO_WINDOW: return "no window batch set";
+        case LVIO2D_ERR_DOMAIN: return "input outside the supported domain";
+        case LVIO2D_ERR_ALLOC: return "device allocation failed";
+        default: return "unknown status";
+    }
+}
+
+const char* lvio2d_last_error(const lvio2d_ctx* ctx) { return ctx ? ctx->err : ""; }
+
+int lvio2d_create(lvio2d_ctx** out, const lvio2d_params* params) {
+    if (!out || !params) return LVIO2D_ERR_INVALID_ARG;
+    *out = nullptr;
+    if (params->abi_version != LVIO2D_ABI_VERSION) return LVIO2D_ERR_INVALID_ARG;
+    if (!(params->line_to_line_sigma > 0) || !(params->manifold_p_sigma > 0) || !(params->manifold_q_sigma > 0)) return LVIO2D_ERR_INVALID_ARG;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count <= params->device || params->device < 0) return LVIO2D_ERR_NO_DEVICE;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, params->device) != cudaSuccess) return LVIO2D_ERR_NO_DEVICE;
+    if (prop.major != 10) return LVIO2D_ERR_NO_DEVICE;  // kernels are built for sm_100a only
+    lvio2d_ctx* ctx = new (std::nothrow) lvio2d_ctx();
+    if (!ctx) return LVIO2D_ERR_ALLOC;
+    ctx->device = params->device;
+    ctx->params = *params;
+    ctx->C = make_consts(*params);
+    ctx->opt = make_opts(*params);
+    ctx->sm_count = prop.multiProcessorCount;
+    if (cudaSetDevice(ctx->device) != cudaSuccess || cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
+        delete ctx;
+        return LVIO2D_ERR_CUDA;
+    }
+    *out = ctx;
+    return LVIO2D_OK;
+}
+
+void lvio2d_destroy(lvio2d_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    DevBuf* all[] = {&ctx->b_points, &ctx->b_pline, &ctx->b_pweight, &ctx->b_poff, &ctx->b_loff, &ctx->b_lines, &ctx->b_ref, &ctx->b_refpose,
+                     &ctx->b_imu, &ctx->b_wheel, &ctx->b_pX0, &ctx->b_pJ, &ctx->b_cmask, &ctx->b_x0, &ctx->b_x, &ctx->b_xc, &ctx->b_scale,
+                     &ctx->b_ftab, &ctx->b_reftab, &ctx->b_wlines, &ctx->b_part, &ctx->b_lb, &ctx->b_pair, &ctx->b_fac, &ctx->b_state,
+                     &ctx->b_status, &ctx->b_active, &ctx->b_active1, &ctx->b_reduce};
+    for (DevBuf* b : all) b->release();
+    for (auto& b : ctx->b_tmp) b.release();
+    cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+void* lvio2d_stream(lvio2d_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+
+int lvio2d_set_windows(lvio2d_ctx* ctx, const lvio2d_window_batch* host_batch) { return setup_batch(ctx, host_batch, false); }
+int lvio2d_bind_windows(lvio2d_ctx* ctx, const lvio2d_window_batch* device_batch) { return setup_batch(ctx, device_batch, true); }
+
+int lvio2d_reset_states(lvio2d_ctx* ctx, const double* host_states) {
+    if (!ctx || !host_states) return LVIO2D_ERR_INVALID_ARG;
+    if (!ctx->have) return fail(ctx, LVIO2D_ERR_NO_WINDOW, "reset_states");
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaMemcpyAsync(ctx->b_x0.p, host_states, (size_t)ctx->B * ctx->n * 15 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    ctx->have_solution = false;
+    return LVIO2D_OK;
+}
+
+int lvio2d_set_point_shard(lvio2d_ctx* ctx, int32_t rank, int32_t world) {
+    if (!ctx || world < 1 || rank < 0 || rank >= world) return LVIO2D_ERR_INVALID_ARG;
+    ctx->shard_rank = rank; ctx->shard_world = world;
+    return LVIO2D_OK;
+}
+
+int lvio2d_solve_begin(lvio2d_ctx* ctx) {
+    if (!ctx) return LVIO2D_ERR_INVALID_ARG;
+    if (!ctx->have) return fail(ctx, LVIO2D_ERR_NO_WINDOW, "solve_begin");
+    CK(cudaSetDevice(ctx->device));
+    return begin_solve(ctx);
+}
+
+int lvio2d_eval_laser(lvio2d_ctx* ctx) {
+    if (!ctx) return LVIO2D_ERR_INVALID_ARG;
+    if (!ctx->have) return fail(ctx, LVIO2D_ERR_NO_WINDOW, "eval_laser");
+    CK(cudaSetDevice(ctx->device));
+    int rc = launch_scan_match(ctx);
+    if (rc) return rc;
+    const int F = ctx->B * ctx->n;
+    double* out = ctx->ext_reduce ? ctx->ext_reduce : ctx->b_reduce.as<double>();
+    const int total = F * ctx->npad;
+    reduce_tiles_kernel<<<(total + 255) / 256, 256, 0, ctx->stream>>>(ctx->b_part.as<double>(), ctx->b_active.as<uint8_t>(), out, F, ctx->tiles, ctx->npad);
+    CK(cudaGetLastError());
+    return LVIO2D_OK;
+}
+
+int lvio2d_reduce_buffer(lvio2d_ctx* ctx, void** device_ptr, int64_t* count) {
+    if (!ctx || !device_ptr || !count) return LVIO2D_ERR_INVALID_ARG;
+    if (!ctx->have) return fail(ctx, LVIO2D_ERR_NO_WINDOW, "reduce_buffer");
+    *device_ptr = ctx->ext_reduce ? (void*)ctx->ext_reduce : ctx->b_reduce.p;
+    *count = (int64_t)ctx->B * ctx->n * ctx->npad;
+    return LVIO2D_OK;
+}
+
+int lvio2d_set_reduce_buffer(lvio2d_ctx* ctx, void* device_ptr, int64_t count) {
+    if (!ctx) return LVIO2D_ERR_INVALID_ARG;
+    if (!ctx->have) return fail(ctx, LVIO2D_ERR_NO_WINDOW, "set_reduce_buffer");
+    if (device_ptr && count < (int64_t)ctx->B * ctx->n * ctx->npad) return fail(ctx, LVIO2D_ERR_INVALID_ARG, "reduce buffer too small");
+    ctx->ext_reduce = reinterpret_cast<double*>(device_ptr);
+    ctx->ext_reduce_count = count;
+    return LVIO2D_OK;
+}
+
+int lvio2d_lm_step(lvio2d_ctx* ctx, int32_t* n_active) {
+    if (!ctx) return LVIO2D_ERR_INVALID_ARG;
+    if (!ctx->have) return fail(ctx, LVIO2D_ERR_NO_WINDOW, "lm_step");
+    CK(cudaSetDevice(ctx->device));
+    WindowArgs a = window_args(ctx, 0);
+    // the (all-reduced) per-frame blocks stand in for the tile partials
+    a.partial = ctx->ext_reduce ? ctx->ext_reduce : ctx->b_reduce.as<double>();
+    a.tiles = 1;
+    int rc = launch_window(ctx, a);
+    if (rc) return rc;
+    ++ctx->step_calls;
+    ctx->have_solution = true;
+    if (n_active) {
+        std::vector<int32_t> st(ctx->B);
+        CK(cudaMemcpyAsync(st.data(), ctx->b_status.p, sizeof(int32_t) * ctx->B, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        int32_t act = 0;
+        for (int32_t s : st) act += (s == 0);
+        *n_active = act;
+    }
+    return LVIO2D_OK;
+}
+
+int lvio2d_solve_async(lvio2d_ctx* ctx) {
+    if (!ctx) return LVIO2D_ERR_INVALID_ARG;
+    if (!ctx->have) return fail(ctx, LVIO2D_ERR_NO_WINDOW, "solve");
+    CK(cudaSetDevice(ctx->device));
+    int rc = begin_solve(ctx);
+    if (rc) return rc;
+    WindowArgs a = window_args(ctx, 0);
+    // trip 0 linearises the initial point; trips 1..max_iters each judge one candidate
+    for (int it = 0; it <= ctx->opt.max_iters; ++it) {
+        if ((rc = launch_scan_match(ctx))) return rc;
+        if ((rc = launch_window(ctx, a))) return rc;
+    }
+    ctx->have_solution = true;
+    return LVIO2D_OK;
+}
+
+int lvio2d_sync(lvio2d_ctx* ctx) {
+    if (!ctx) return LVIO2D_ERR_INVALID_ARG;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return LVIO2D_OK;
+}
+
+int lvio2d_get_summaries(lvio2d_ctx* ctx, lvio2d_summary* out) {
+    if (!ctx || !out) return LVIO2D_ERR_INVALID_ARG;
+    if (!ctx->have) return fail(ctx, LVIO2D_ERR_NO_WINDOW, "get_summaries");
+    CK(cudaSetDevice(ctx->device));
+    std::vector<LMState> st(ctx->B);
+    CK(cudaMemcpyAsync(st.data(), ctx->b_state.p, sizeof(LMState) * ctx->B, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    for (int w = 0; w < ctx->B; ++w) {
+        out[w].iterations = st[w].iteration;
+        out[w].termination = st[w].termination;
+        out[w].num_successful_steps = st[w].n_success;
+        out[w].num_unsuccessful_steps = st[w].n_unsuccess;
+        out[w].initial_cost = st[w].initial_cost;
+        out[w].final_cost = st[w].cost;
+        out[w].final_radius = st[w].radius;
+        out[w].reserved = 0.0;
+    }
+    return LVIO2D_OK;
+}
+
+int lvio2d_solve(lvio2d_ctx* ctx, lvio2d_summary* summaries) {
+    int rc = lvio2d_solve_async(ctx);
+    if (rc) return rc;
+    if (summaries) return lvio2d_get_summaries(ctx, summaries);
+    return lvio2d_sync(ctx);
+}
+
+int lvio2d_get_states(lvio2d_ctx* ctx, double* host_states) {
+    if (!ctx || !host_states) return LVIO2D_ERR_INVALID_ARG;
+    if (!ctx->have) return fail(ctx, LVIO2D_ERR_NO_WINDOW, "get_states");
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaMemcpyAsync(host_states, ctx->b_x.p, (size_t)ctx->B * ctx->n * 15 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return LVIO2D_OK;
+}
+
+int lvio2d_linearize(lvio2d_ctx* ctx, int32_t mode, double* H, double* g, double* cost) {
+    if (!ctx || !H || !g || !cost || (mode != 0 && mode != 1)) return LVIO2D_ERR_INVALID_ARG;
+    if (!ctx->have) return fail(ctx, LVIO2D_ERR_NO_WINDOW, "linearize");
+    CK(cudaSetDevice(ctx->device));
+    const size_t dim = 15 * (size_t)ctx->n;
+    if (!ctx->b_tmp[0].ensure(ctx->B * dim * dim * sizeof(double)) || !ctx->b_tmp[1].ensure(ctx->B * dim * sizeof(double)) ||
+        !ctx->b_tmp[2].ensure(ctx->B * sizeof(double)))
+        return fail(ctx, LVIO2D_ERR_ALLOC, "cudaMalloc(linearize)");
+    WindowArgs a = window_args(ctx, mode);
+    a.dense_H = ctx->b_tmp[0].as<double>(); a.dense_g = ctx->b_tmp[1].as<double>(); a.dense_cost = ctx->b_tmp[2].as<double>();
+    int rc = run_linearize(ctx, mode, a);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(H, a.dense_H, ctx->B * dim * dim * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(g, a.dense_g, ctx->B * dim * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(cost, a.dense_cost, ctx->B * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return LVIO2D_OK;
+}
+
+int lvio2d_marginalize(lvio2d_ctx* ctx, double* X0, double* J_lin, double* r_lin) {
+    if (!ctx || !X0 || !J_lin || !r_lin) return LVIO2D_ERR_INVALID_ARG;
+    if (!ctx->have) return fail(ctx, LVIO2D_ERR_NO_WINDOW, "marginalize");
+    CK(cudaSetDevice(ctx->device));
+    const int B = ctx->B;
+    if (!ctx->b_tmp[3].ensure((size_t)B * 225 * sizeof(double)) || !ctx->b_tmp[4].ensure((size_t)B * 15 * sizeof(double)) ||
+        !ctx->b_tmp[5].ensure((size_t)B * 15 * sizeof(double)) || !ctx->b_tmp[6].ensure((size_t)B * 225 * sizeof(double)) ||
+        !ctx->b_tmp[7].ensure((size_t)B * 15 * sizeof(double)))
+        return fail(ctx, LVIO2D_ERR_ALLOC, "cudaMalloc(marginalize)");
+    WindowArgs a = window_args(ctx, 1);
+    a.marg_H = ctx->b_tmp[3].as<double>(); a.marg_g = ctx->b_tmp[4].as<double>();
+    int rc = run_linearize(ctx, 1, a);
+    if (rc) return rc;
+    marginal_prior_kernel<<<(B + 63) / 64, 64, 0, ctx->stream>>>(B, ctx->n, a.marg_H, a.marg_g, ctx->b_x.as<double>(), ctx->b_tmp[5].as<double>(),
+                                                                ctx->b_tmp[6].as<double>(), ctx->b_tmp[7].as<double>());
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(X0, ctx->b_tmp[5].p, (size_t)B * 15 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(J_lin, ctx->b_tmp[6].p, (size_t)B * 225 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(r_lin, ctx->b_tmp[7].p, (size_t)B * 15 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return LVIO2D_OK;
+}
+
+int lvio2d_imu_preintegrate(lvio2d_ctx* ctx, int32_t n_intervals, const int64_t* sample_offset, const double* samples, const double* bias0,
+                            double* out_blobs) {
+    if (!ctx || n_intervals < 0 || !sample_offset || !bias0 || !out_blobs) return LVIO2D_ERR_INVALID_ARG;
+    if (n_intervals == 0) return LVIO2D_OK;
+    CK(cudaSetDevice(ctx->device));
+    const int64_t M = sample_offset[n_intervals];
+    if (M > 0 && !samples) return LVIO2D_ERR_INVALID_ARG;
+    if (!ctx->b_tmp[0].ensure(sizeof(int64_t) * (n_intervals + 1)) || !ctx->b_tmp[1].ensure(std::max<size_t>(8, sizeof(double) * 7 * M)) ||
+        !ctx->b_tmp[2].ensure(sizeof(double) * 6 * n_intervals) || !ctx->b_tmp[3].ensure(sizeof(double) * 466 * (size_t)n_intervals))
+        return fail(ctx, LVIO2D_ERR_ALLOC, "cudaMalloc(imu_preintegrate)");
+    CK(cudaMemcpyAsync(ctx->b_tmp[0].p, sample_offset, sizeof(int64_t) * (n_intervals + 1), cudaMemcpyHostToDevice, ctx->stream));
+    if (M > 0) CK(cudaMemcpyAsync(ctx->b_tmp[1].p, samples, sizeof(double) * 7 * M, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->b_tmp[2].p, bias0, sizeof(double) * 6 * n_intervals, cudaMemcpyHostToDevice, ctx->stream));
+    const int wpc = 4;
+    const size_t smem = (size_t)wpc * kImuPreSmem * sizeof(double);
+    imu_preintegrate_kernel<<<(n_intervals + wpc - 1) / wpc, wpc * 32, smem, ctx->stream>>>(
+        ctx->C, n_intervals, ctx->b_tmp[0].as<int64_t>(), ctx->b_tmp[1].as<double>(), ctx->b_tmp[2].as<double>(), ctx->b_tmp[3].as<double>());
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(out_blobs, ctx->b_tmp[3].p, sizeof(double) * 466 * (size_t)n_intervals, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return LVIO2D_OK;
+}
+
+int lvio2d_wheel_preintegrate(lvio2d_ctx* ctx, int32_t n_intervals, const int64_t* step_offset, const double* steps, double* out_blobs) {
+    if (!ctx || n_intervals < 0 || !step_offset || !out_blobs) return LVIO2D_ERR_INVALID_ARG;
+    if (n_intervals == 0) return LVIO2D_OK;
+    CK(cudaSetDevice(ctx->device));
+    const int64_t M = step_offset[n_intervals];
+    if (M > 0 && !steps) return LVIO2D_ERR_INVALID_ARG;
+    if (!ctx->b_tmp[0].ensure(sizeof(int64_t) * (n_intervals + 1)) || !ctx->b_tmp[1].ensure(std::max<size_t>(8, sizeof(double) * 7 * M)) ||
+        !ctx->b_tmp[3].ensure(sizeof(double) * 15 * (size_t)n_intervals))
+        return fail(ctx, LVIO2D_ERR_ALLOC, "cudaMalloc(wheel_preintegrate)");
+    CK(cudaMemcpyAsync(ctx->b_tmp[0].p, step_offset, sizeof(int64_t) * (n_intervals + 1), cudaMemcpyHostToDevice, ctx->stream));
+    if (M > 0) CK(cudaMemcpyAsync(ctx->b_tmp[1].p, steps, sizeof(double) * 7 * M, cudaMemcpyHostToDevice, ctx->stream));
+    wheel_preintegrate_kernel<<<(n_intervals + 127) / 128, 128, 0, ctx->stream>>>(ctx->C, n_intervals, ctx->b_tmp[0].as<int64_t>(),
+                                                                                  ctx->b_tmp[1].as<double>(), ctx->b_tmp[3].as<double>());
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(out_blobs, ctx->b_tmp[3].p, sizeof(double) * 15 * (size_t)n_intervals, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return LVIO2D_OK;
+}
+
+// ---- single-factor hooks: inputs staged into one scratch buffer, outputs read back
+static int eval_hook(lvio2d_ctx* ctx, const double* const* in, const int* in_len, int n_in, double* res, int n_res, double* jac, int n_jac, int which) {
+    if (!ctx || !res || !jac) return LVIO2D_ERR_INVALID_ARG;
+    CK(cudaSetDevice(ctx->device));
+    int total = 0;
+    for (int i = 0; i < n_in; ++i) { if (!in[i]) return LVIO2D_ERR_INVALID_ARG; total += in_len[i]; }
+    std::vector<double> stage(total);
+    int off[8], o = 0;
+    for (int i = 0; i < n_in; ++i) { off[i] = o; std::memcpy(stage.data() + o, in[i], sizeof(double) * in_len[i]); o += in_len[i]; }
+    if (!ctx->b_tmp[0].ensure(sizeof(double) * (total + n_res + n_jac))) return fail(ctx, LVIO2D_ERR_ALLOC, "cudaMalloc(eval)");
+    double* d = ctx->b_tmp[0].as<double>();
+    CK(cudaMemcpyAsync(d, stage.data(), sizeof(double) * total, cudaMemcpyHostToDevice, ctx->stream));
+    double* dres = d + total;
+    double* djac = dres + n_res;
+    switch (which) {
+        case 0: eval_laser_factor_kernel<<<1, 32, 0, ctx->stream>>>(ctx->C, d + off[0], d + off[1], d + off[2], d + off[3], d + off[4], d + off[5], dres, djac); break;
+        case 1: eval_imu_factor_kernel<<<1, 32, 0, ctx->stream>>>(ctx->C, d + off[0], d + off[1], d + off[2], dres, djac); break;
+        case 2: eval_wheel_factor_kernel<<<1, 32, 0, ctx->stream>>>(ctx->C, d + off[0], d + off[1], d + off[2], dres, djac); break;
+        default: eval_ground_factors_kernel<<<1, 32, 0, ctx->stream>>>(ctx->C, d + off[0], dres, djac); break;
+    }
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(res, dres, sizeof(double) * n_res, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(jac, djac, sizeof(double) * n_jac, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return LVIO2D_OK;
+}
+
+int lvio2d_eval_laser_factor(lvio2d_ctx* ctx, const double* l1_p1, const double* l1_p2, const double* l2_p1, const double* l2_p2,
+                             const double* pose_i, const double* pose_j, double* res, double* jac) {
+    const double* in[6] = {l1_p1, l1_p2, l2_p1, l2_p2, pose_i, pose_j};
+    const int len[6] = {3, 3, 3, 3, 6, 6};
+    return eval_hook(ctx, in, len, 6, res, 2, jac, 24, 0);
+}
+int lvio2d_eval_imu_factor(lvio2d_ctx* ctx, const double* imu_blob, const double* state_i, const double* state_j, double* res, double* jac) {
+    const double* in[3] = {imu_blob, state_i, state_j};
+    const int len[3] = {466, 15, 15};
+    return eval_hook(ctx, in, len, 3, res, 15, jac, 450, 1);
+}
+int lvio2d_eval_wheel_factor(lvio2d_ctx* ctx, const double* wheel_blob, const double* pose_i, const double* pose_j, double* res, double* jac) {
+    const double* in[3] = {wheel_blob, pose_i, pose_j};
+    const int len[3] = {15, 6, 6};
+    return eval_hook(ctx, in, len, 3, res, 3, jac, 36, 2);
+}
+int lvio2d_eval_ground_factors(lvio2d_ctx* ctx, const double* pose, double* res, double* jac) {
+    const double* in[1] = {pose};
+    const int len[1] = {6};
+    return eval_hook(ctx, in, len, 1, res, 2, jac, 12, 3);
+}
+
+}  // extern "C"

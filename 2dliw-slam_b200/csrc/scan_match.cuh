@@ -1,0 +1,294 @@
+// scan_match.cuh — the hot kernel: for every scan point of every frame of every window, point-to-line
+// residual + 1x6 (or 1x12) Jacobian + accumulation of the per-frame J^T J / J^T r / r^2 blocks.
+//
+// Replaces, for all points at once, what Ceres does per residual block with Jets through
+// laser_factor::operator() (reference src/factor/laser_factor.h:45-89) and
+// e_laser::dis_from_line (src/utilies/common.h:86-95), plus the J^T J accumulation of the normal
+// equations that ceres::Solve builds internally (src/factor/solver.cpp:802, :168).
+//
+// Algebra (verified in tests/test_device_math_host.py): with the frame table
+// (M, t, B_k, b_k) of lv_math.cuh, the flattened world point is C = M c + t and dC/dtheta_k = B_k c + b_k.
+// For a world line with unit normal n and offset c0 = n.A2 the signed distance is
+//     d = n.C - c0 = f0 cx + f1 cy + f2,           f = (n^T M, n.t - c0)
+//     dd/dtheta_j,k = e_k0 cx + e_k1 cy + e_k2,     e_k = (n^T B_k, n.b_k)
+//     dd/dp_j = (nx, ny, 0)
+// The residual is w |d| and its Jacobian w sign(d) (...): sign^2 = 1, so J^T J, J^T r and r^2 never
+// need the sign.  Per line the 12 coefficients (f, e_0, e_1, e_2) + n are staged in shared memory once
+// per (frame, tile); per point the kernel does 8 FMAs for (d, j_theta) and 21 for the accumulation.
+//
+// Work decomposition: one warp per (frame, tile).  Points of a frame are contiguous, so a warp reads
+// 512 B (32 x double2) + 128 B (32 x int32) fully coalesced per step; loads bypass L1 (read once).
+// Reduction: per-lane register accumulators -> recursive-halving warp shuffle (23 exchanges for 21 values
+// instead of 105) -> one 8-byte store per value.  No atomics; results are bit-reproducible.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "lv_math.cuh"
+
+namespace lv {
+
+constexpr int kAccTrack = 21;   // [0..2] aa | [3..8] a x bj | [9..14] bj bj^T (upper) | [15,16] d a | [17..19] d bj | [20] d^2
+constexpr int kAccFree = 45;    // [0..14] as above | [15..20] a x bi | [21..26] bi bi^T (upper) | [27..35] bj x bi | [36,37] d a |
+                                // [38..40] d bj | [41..43] d bi | [44] d^2
+constexpr int kPadTrack = 24;
+constexpr int kPadFree = 48;
+constexpr int kRowTrack = 14;   // f(3) e(9) n(2)
+constexpr int kRowFree = 24;    // + h(3) alpha(3) beta(3) + pad
+
+struct ScanMatchArgs {
+    const double2* points;          // [N] scan points in the frame's laser frame
+    const int32_t* point_line;      // [N] line index inside the frame's local map, < 0: skip
+    const double* point_weight;     // [N] or nullptr
+    const int64_t* point_offset;    // [F+1]
+    const int64_t* line_offset;     // [F+1]
+    const double4* wlines;          // [L] (nx, ny, c0, -) world lines, external constant reference pose
+    const double4* lines;           // [L] raw (a1x a1y a2x a2y) in the reference laser frame
+    const int32_t* ref_frame;       // [F] or nullptr
+    const double* frame_tab;        // [F][24] at the evaluation point
+    const uint8_t* frame_active;    // [F] 1 when the frame's laser residual block is part of the program
+    const int32_t* win_status;      // [B] 0 = window still iterating (nullptr: all)
+    double* partial;                // [F][tiles][pad]
+    int32_t n_frames;               // frames per window
+    int32_t tiles;
+    int32_t n_items;                // F * tiles
+    int32_t line_cap;               // shared-memory rows per warp
+    int32_t shard_rank, shard_world;
+};
+
+__device__ __forceinline__ double2 ld_stream_f64x2(const double2* p) {
+    double2 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ int ld_stream_s32(const int32_t* p) {
+    int v;
+    asm volatile("ld.global.nc.L1::no_allocate.s32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ double ld_stream_f64(const double* p) {
+    double v;
+    asm volatile("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(v) : "l"(p));
+    return v;
+}
+
+// Recursive-halving reduce-scatter over the warp: N values per lane in, ceil(N/32) per lane out.
+// After the call lane holds v[0..len) = full sums of logical indices [base, base+len).
+template <int N, int DIST>
+struct ReduceScatter {
+    static __device__ __forceinline__ void run(double* v, int lane, int& base, int& len) {
+        constexpr int H = (N + 1) / 2;
+        const bool upper = (lane & DIST) != 0;
+#pragma unroll
+        for (int i = 0; i < H; ++i) {
+            const double hi = (i + H < N) ? v[i + H] : 0.0;
+            const double send = upper ? v[i] : hi;
+            const double keep = upper ? hi : v[i];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, DIST);
+        }
+        if (upper) { base += H; len = (len > H) ? len - H : 0; } else { len = (len < H) ? len : H; }
+        ReduceScatter<H, DIST / 2>::run(v, lane, base, len);
+    }
+};
+template <int N>
+struct ReduceScatter<N, 0> {
+    static __device__ __forceinline__ void run(double*, int, int&, int&) {}
+};
+// number of values a lane holds after 5 halvings of N
+__host__ __device__ constexpr int halved5(int n) { for (int i = 0; i < 5; ++i) n = (n + 1) / 2; return n; }
+
+template <bool REF_FREE, bool HAS_WEIGHT>
+__global__ void __launch_bounds__(256) scan_match_kernel(ScanMatchArgs a) {
+    constexpr int NACC = REF_FREE ? kAccFree : kAccTrack;
+    constexpr int NPAD = REF_FREE ? kPadFree : kPadTrack;
+    constexpr int ROW = REF_FREE ? kRowFree : kRowTrack;
+    extern __shared__ __align__(16) double smem[];
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int item = blockIdx.x * (blockDim.x >> 5) + warp;
+    if (item >= a.n_items) return;
+    const int f = item / a.tiles;
+    const int tile = item - f * a.tiles;
+    if (a.win_status && a.win_status[f / a.n_frames] != 0) return;
+    if (!a.frame_active[f]) return;
+    double* tab = smem + (size_t)warp * a.line_cap * ROW;
+
+    // ---- this frame's table (24 doubles, broadcast loads) and the shared-memory line table
+    const double* ft = a.frame_tab + (size_t)f * kFrameTab;
+    const int64_t l0 = a.line_offset[f];
+    const int nl = (int)(a.line_offset[f + 1] - l0);
+    {
+        double T[kFrameTab];
+#pragma unroll
+        for (int i = 0; i < kFrameTab; ++i) T[i] = __ldg(ft + i);
+        if constexpr (!REF_FREE) {
+            for (int l = lane; l < nl; l += 32) {
+                const double4 wl = a.wlines[l0 + l];
+                double* r = tab + l * ROW;
+                r[0] = wl.x * T[0] + wl.y * T[2];
+                r[1] = wl.x * T[1] + wl.y * T[3];
+                r[2] = wl.x * T[4] + wl.y * T[5] - wl.z;
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    const double* Bk = T + 6 + 6 * k;
+                    r[3 + 3 * k] = wl.x * Bk[0] + wl.y * Bk[2];
+                    r[4 + 3 * k] = wl.x * Bk[1] + wl.y * Bk[3];
+                    r[5 + 3 * k] = wl.x * Bk[4] + wl.y * Bk[5];
+                }
+                r[12] = wl.x;
+                r[13] = wl.y;
+            }
+        } else {
+            const int rf = a.ref_frame[f];
+            const double* fi = a.frame_tab + ((size_t)(f - f % a.n_frames) + rf) * kFrameTab;
+            double Ti[kFrameTab];
+#pragma unroll
+            for (int i = 0; i < kFrameTab; ++i) Ti[i] = __ldg(fi + i);
+            for (int l = lane; l < nl; l += 32) {
+                const double4 ln = a.lines[l0 + l];
+                const double A1x = Ti[0] * ln.x + Ti[1] * ln.y + Ti[4], A1y = Ti[2] * ln.x + Ti[3] * ln.y + Ti[5];
+                const double A2x = Ti[0] * ln.z + Ti[1] * ln.w + Ti[4], A2y = Ti[2] * ln.z + Ti[3] * ln.w + Ti[5];
+                const double dx = A2x - A1x, dy = A2y - A1y;
+                const double len = sqrt(dx * dx + dy * dy), inv = 1.0 / len;
+                const double ux = dx * inv, uy = dy * inv, nx = -uy, ny = ux;
+                double* r = tab + l * ROW;
+                r[0] = nx * T[0] + ny * T[2];
+                r[1] = nx * T[1] + ny * T[3];
+                r[2] = nx * T[4] + ny * T[5] - (nx * A2x + ny * A2y);
+                r[14] = ux * T[0] + uy * T[2];
+                r[15] = ux * T[1] + uy * T[3];
+                r[16] = ux * T[4] + uy * T[5] - (ux * A2x + uy * A2y);
+                const double ex = ln.z - ln.x, ey = ln.w - ln.y;
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    const double* Bk = T + 6 + 6 * k;
+                    r[3 + 3 * k] = nx * Bk[0] + ny * Bk[2];
+                    r[4 + 3 * k] = nx * Bk[1] + ny * Bk[3];
+                    r[5 + 3 * k] = nx * Bk[4] + ny * Bk[5];
+                    const double* Ck = Ti + 6 + 6 * k;
+                    // alpha_k = n.(B_ik (a2 - a1)) / L,  beta_k = n.(B_ik a2 + b_ik)
+                    r[17 + k] = (nx * (Ck[0] * ex + Ck[1] * ey) + ny * (Ck[2] * ex + Ck[3] * ey)) * inv;
+                    r[20 + k] = nx * (Ck[0] * ln.z + Ck[1] * ln.w + Ck[4]) + ny * (Ck[2] * ln.z + Ck[3] * ln.w + Ck[5]);
+                }
+                r[12] = nx;
+                r[13] = ny;
+                r[23] = 0.0;
+            }
+        }
+    }
+    __syncwarp();
+
+    // ---- this warp's slice of the frame: rank shard, then tile
+    const int64_t p0 = a.point_offset[f], cnt = a.point_offset[f + 1] - p0;
+    const int64_t s0 = p0 + (cnt * a.shard_rank) / a.shard_world;
+    const int64_t s1 = p0 + (cnt * (a.shard_rank + 1)) / a.shard_world;
+    const int64_t per = (s1 - s0 + a.tiles - 1) / a.tiles;
+    const int64_t pb = s0 + per * tile;
+    const int64_t pe = (pb + per < s1) ? pb + per : s1;
+
+    double acc[NACC];
+#pragma unroll
+    for (int i = 0; i < NACC; ++i) acc[i] = 0.0;
+
+    constexpr int U = 4;
+    for (int64_t base = pb + lane; base < pe; base += 32 * U) {
+        double2 c[U];
+        int li[U];
+        double w[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int64_t p = base + 32 * u;
+            const bool ok = p < pe;
+            li[u] = ok ? ld_stream_s32(a.point_line + p) : -1;
+            c[u] = ok ? ld_stream_f64x2(a.points + p) : make_double2(0.0, 0.0);
+            if constexpr (HAS_WEIGHT) w[u] = ok ? ld_stream_f64(a.point_weight + p) : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            if (li[u] < 0) continue;
+            const double* r = tab + li[u] * ROW;
+            const double2 r01 = *reinterpret_cast<const double2*>(r);
+            const double2 r23 = *reinterpret_cast<const double2*>(r + 2);
+            const double2 r45 = *reinterpret_cast<const double2*>(r + 4);
+            const double2 r67 = *reinterpret_cast<const double2*>(r + 6);
+            const double2 r89 = *reinterpret_cast<const double2*>(r + 8);
+            const double2 rab = *reinterpret_cast<const double2*>(r + 10);
+            const double2 rn = *reinterpret_cast<const double2*>(r + 12);
+            const double cx = c[u].x, cy = c[u].y;
+            double d = fma(r01.x, cx, fma(r01.y, cy, r23.x));
+            double j2 = fma(r23.y, cx, fma(r45.x, cy, r45.y));
+            double j3 = fma(r67.x, cx, fma(r67.y, cy, r89.x));
+            double j4 = fma(r89.y, cx, fma(rab.x, cy, rab.y));
+            double j0 = rn.x, j1 = rn.y;
+            double i2 = 0.0, i3 = 0.0, i4 = 0.0;
+            if constexpr (REF_FREE) {
+                const double2 h01 = *reinterpret_cast<const double2*>(r + 14);
+                const double2 h2a = *reinterpret_cast<const double2*>(r + 16);
+                const double2 a12 = *reinterpret_cast<const double2*>(r + 18);
+                const double2 b01 = *reinterpret_cast<const double2*>(r + 20);
+                const double b2 = r[22];
+                const double tt = fma(h01.x, cx, fma(h01.y, cy, h2a.x));
+                i2 = -fma(tt, h2a.y, b01.x);
+                i3 = -fma(tt, a12.x, b01.y);
+                i4 = -fma(tt, a12.y, b2);
+            }
+            if constexpr (HAS_WEIGHT) {
+                const double ww = w[u];
+                d *= ww; j0 *= ww; j1 *= ww; j2 *= ww; j3 *= ww; j4 *= ww;
+                if constexpr (REF_FREE) { i2 *= ww; i3 *= ww; i4 *= ww; }
+            }
+            acc[0] = fma(j0, j0, acc[0]); acc[1] = fma(j0, j1, acc[1]); acc[2] = fma(j1, j1, acc[2]);
+            acc[3] = fma(j0, j2, acc[3]); acc[4] = fma(j0, j3, acc[4]); acc[5] = fma(j0, j4, acc[5]);
+            acc[6] = fma(j1, j2, acc[6]); acc[7] = fma(j1, j3, acc[7]); acc[8] = fma(j1, j4, acc[8]);
+            acc[9] = fma(j2, j2, acc[9]); acc[10] = fma(j2, j3, acc[10]); acc[11] = fma(j2, j4, acc[11]);
+            acc[12] = fma(j3, j3, acc[12]); acc[13] = fma(j3, j4, acc[13]); acc[14] = fma(j4, j4, acc[14]);
+            if constexpr (!REF_FREE) {
+                acc[15] = fma(d, j0, acc[15]); acc[16] = fma(d, j1, acc[16]);
+                acc[17] = fma(d, j2, acc[17]); acc[18] = fma(d, j3, acc[18]); acc[19] = fma(d, j4, acc[19]);
+                acc[20] = fma(d, d, acc[20]);
+            } else {
+                acc[15] = fma(j0, i2, acc[15]); acc[16] = fma(j0, i3, acc[16]); acc[17] = fma(j0, i4, acc[17]);
+                acc[18] = fma(j1, i2, acc[18]); acc[19] = fma(j1, i3, acc[19]); acc[20] = fma(j1, i4, acc[20]);
+                acc[21] = fma(i2, i2, acc[21]); acc[22] = fma(i2, i3, acc[22]); acc[23] = fma(i2, i4, acc[23]);
+                acc[24] = fma(i3, i3, acc[24]); acc[25] = fma(i3, i4, acc[25]); acc[26] = fma(i4, i4, acc[26]);
+                acc[27] = fma(j2, i2, acc[27]); acc[28] = fma(j2, i3, acc[28]); acc[29] = fma(j2, i4, acc[29]);
+                acc[30] = fma(j3, i2, acc[30]); acc[31] = fma(j3, i3, acc[31]); acc[32] = fma(j3, i4, acc[32]);
+                acc[33] = fma(j4, i2, acc[33]); acc[34] = fma(j4, i3, acc[34]); acc[35] = fma(j4, i4, acc[35]);
+                acc[36] = fma(d, j0, acc[36]); acc[37] = fma(d, j1, acc[37]);
+                acc[38] = fma(d, j2, acc[38]); acc[39] = fma(d, j3, acc[39]); acc[40] = fma(d, j4, acc[40]);
+                acc[41] = fma(d, i2, acc[41]); acc[42] = fma(d, i3, acc[42]); acc[43] = fma(d, i4, acc[43]);
+                acc[44] = fma(d, d, acc[44]);
+            }
+        }
+    }
+
+    int base = 0, len = NACC;
+    ReduceScatter<NACC, 16>::run(acc, lane, base, len);
+    double* out = a.partial + (size_t)item * NPAD;
+    constexpr int OUTN = halved5(NACC);
+#pragma unroll
+    for (int i = 0; i < OUTN; ++i)
+        if (i < len) out[base + i] = acc[i];
+}
+
+// world lines for frames whose local map hangs under an external constant reference pose: computed once per
+// set_windows (the reference pose never changes during a solve, solver.cpp:690-691)
+__global__ void world_lines_kernel(const double4* lines, const int64_t* line_offset, const int32_t* ref_frame,
+                                   const double* ref_tab /*[F][24]*/, double4* wlines, int n_frames_total) {
+    const int f = blockIdx.x;
+    if (f >= n_frames_total) return;
+    if (ref_frame && ref_frame[f] >= 0) return;
+    const double* T = ref_tab + (size_t)f * kFrameTab;
+    const int64_t l0 = line_offset[f], l1 = line_offset[f + 1];
+    for (int64_t l = l0 + threadIdx.x; l < l1; l += blockDim.x) {
+        const double4 ln = lines[l];
+        const double A1x = T[0] * ln.x + T[1] * ln.y + T[4], A1y = T[2] * ln.x + T[3] * ln.y + T[5];
+        const double A2x = T[0] * ln.z + T[1] * ln.w + T[4], A2y = T[2] * ln.z + T[3] * ln.w + T[5];
+        const double dx = A2x - A1x, dy = A2y - A1y;
+        const double inv = 1.0 / sqrt(dx * dx + dy * dy);
+        const double nx = -dy * inv, ny = dx * inv;
+        wlines[l] = make_double4(nx, ny, nx * A2x + ny * A2y, 0.0);
+    }
+}
+
+}  // namespace lv

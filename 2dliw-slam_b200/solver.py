@@ -1,0 +1,412 @@
+"""Host-side mirror of the reference's solver interface, on top of the C ABI (include/lvio2d.h).
+
+Two layers:
+  * `Context` — a thin ctypes binding of liblvio2d.so, one method per C entry point.  This is what a
+    reference maintainer's C++ shim calls (shim/lvio2d_solver_shim.h); Python only plays the role of the
+    host language here because the reference's own host toolchain (ROS/catkin, Eigen) is absent.
+  * `Solver` / `FrameInfo` / `LaserMatch` — the reference's `lvio_2d::solver` surface
+    (reference src/factor/solver.h:71-79: solve, init_solve, marginalization on a deque of frame_info,
+    src/trajectory/trajectory_type.h:9-75) with the same names, argument meaning and in-place write-back.
+
+The compute path is CUDA only.  Importing this module never builds or falls back to anything: if
+csrc/liblvio2d.so is missing or no sm_100 device is present, `Context()` raises.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import abi
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "liblvio2d.so")
+_lib = None
+
+EXPORTS = [
+    "lvio2d_create", "lvio2d_destroy", "lvio2d_strerror", "lvio2d_last_error", "lvio2d_stream", "lvio2d_set_windows",
+    "lvio2d_bind_windows", "lvio2d_reset_states", "lvio2d_solve", "lvio2d_solve_async", "lvio2d_sync", "lvio2d_get_summaries",
+    "lvio2d_get_states", "lvio2d_set_point_shard", "lvio2d_solve_begin", "lvio2d_eval_laser", "lvio2d_reduce_buffer",
+    "lvio2d_set_reduce_buffer", "lvio2d_lm_step", "lvio2d_linearize", "lvio2d_marginalize", "lvio2d_imu_preintegrate",
+    "lvio2d_wheel_preintegrate", "lvio2d_eval_laser_factor", "lvio2d_eval_imu_factor", "lvio2d_eval_wheel_factor",
+    "lvio2d_eval_ground_factors",
+]
+
+
+class Lvio2dError(RuntimeError):
+    def __init__(self, status, what, detail=""):
+        self.status = status
+        super().__init__(f"{what}: status {status}{' (' + detail + ')' if detail else ''}")
+
+
+def load_library(path=LIB_PATH):
+    """dlopen the CUDA library of the C ABI.  No fallback: a missing library is an error."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(path):
+        raise FileNotFoundError(f"{path} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                                "(nvcc, sm_100a). There is no CPU fallback for this path.")
+    lib = C.CDLL(path)
+    vp, dp = C.c_void_p, abi.c_double_p
+    lib.lvio2d_create.argtypes = [C.POINTER(vp), C.POINTER(abi.Params)]
+    lib.lvio2d_destroy.argtypes = [vp]
+    lib.lvio2d_destroy.restype = None
+    lib.lvio2d_strerror.argtypes = [C.c_int]
+    lib.lvio2d_strerror.restype = C.c_char_p
+    lib.lvio2d_last_error.argtypes = [vp]
+    lib.lvio2d_last_error.restype = C.c_char_p
+    lib.lvio2d_stream.argtypes = [vp]
+    lib.lvio2d_stream.restype = vp
+    lib.lvio2d_set_windows.argtypes = [vp, C.POINTER(abi.WindowBatch)]
+    lib.lvio2d_bind_windows.argtypes = [vp, C.POINTER(abi.WindowBatch)]
+    lib.lvio2d_reset_states.argtypes = [vp, vp]
+    lib.lvio2d_solve.argtypes = [vp, vp]
+    lib.lvio2d_solve_async.argtypes = [vp]
+    lib.lvio2d_sync.argtypes = [vp]
+    lib.lvio2d_get_summaries.argtypes = [vp, vp]
+    lib.lvio2d_get_states.argtypes = [vp, vp]
+    lib.lvio2d_set_point_shard.argtypes = [vp, C.c_int32, C.c_int32]
+    lib.lvio2d_solve_begin.argtypes = [vp]
+    lib.lvio2d_eval_laser.argtypes = [vp]
+    lib.lvio2d_reduce_buffer.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_int64)]
+    lib.lvio2d_set_reduce_buffer.argtypes = [vp, vp, C.c_int64]
+    lib.lvio2d_lm_step.argtypes = [vp, C.POINTER(C.c_int32)]
+    lib.lvio2d_linearize.argtypes = [vp, C.c_int32, dp, dp, dp]
+    lib.lvio2d_marginalize.argtypes = [vp, dp, dp, dp]
+    lib.lvio2d_imu_preintegrate.argtypes = [vp, C.c_int32, abi.c_int64_p, dp, dp, dp]
+    lib.lvio2d_wheel_preintegrate.argtypes = [vp, C.c_int32, abi.c_int64_p, dp, dp]
+    lib.lvio2d_eval_laser_factor.argtypes = [vp] + [dp] * 8
+    lib.lvio2d_eval_imu_factor.argtypes = [vp] + [dp] * 5
+    lib.lvio2d_eval_wheel_factor.argtypes = [vp] + [dp] * 5
+    lib.lvio2d_eval_ground_factors.argtypes = [vp] + [dp] * 3
+    _lib = lib
+    return lib
+
+
+def _d(a):
+    return a.ctypes.data_as(abi.c_double_p)
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+class Context:
+    """lvio2d_ctx: one solver instance = one CUDA stream + device buffers (include/lvio2d.h)."""
+
+    def __init__(self, params):
+        self.lib = load_library()
+        self.params = params
+        self._h = C.c_void_p()
+        rc = self.lib.lvio2d_create(C.byref(self._h), C.byref(params))
+        if rc != abi.OK:
+            self._h = C.c_void_p()
+            raise Lvio2dError(rc, "lvio2d_create", self.lib.lvio2d_strerror(rc).decode())
+        self.n_windows = self.n_frames = 0
+        self._keep = None
+
+    def close(self):
+        if self._h:
+            self.lib.lvio2d_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def _check(self, rc, what):
+        if rc != abi.OK:
+            raise Lvio2dError(rc, what, self.lib.lvio2d_last_error(self._h).decode() or self.lib.lvio2d_strerror(rc).decode())
+
+    @property
+    def stream(self):
+        """cudaStream_t (as int) all work of this context is enqueued on."""
+        return int(self.lib.lvio2d_stream(self._h) or 0)
+
+    # ---- problem upload
+    def set_windows(self, host_batch):
+        s = host_batch.struct()
+        self._check(self.lib.lvio2d_set_windows(self._h, C.byref(s)), "lvio2d_set_windows")
+        self.n_windows, self.n_frames = host_batch.n_windows, host_batch.n_frames
+
+    def bind_windows(self, device_struct, keepalive=None):
+        """`device_struct`: abi.WindowBatch whose pointers are device pointers; `keepalive` owns the memory."""
+        self._check(self.lib.lvio2d_bind_windows(self._h, C.byref(device_struct)), "lvio2d_bind_windows")
+        self.n_windows, self.n_frames = device_struct.n_windows, device_struct.n_frames
+        self._keep = keepalive
+
+    def reset_states(self, states):
+        st = _f64(states)
+        assert st.size == self.n_windows * self.n_frames * 15
+        self._check(self.lib.lvio2d_reset_states(self._h, st.ctypes.data), "lvio2d_reset_states")
+
+    # ---- solve
+    def solve(self, want_summary=True):
+        if want_summary:
+            summ = np.zeros(self.n_windows, dtype=abi.SUMMARY_DTYPE)
+            self._check(self.lib.lvio2d_solve(self._h, summ.ctypes.data), "lvio2d_solve")
+            return summ
+        self._check(self.lib.lvio2d_solve(self._h, None), "lvio2d_solve")
+        return None
+
+    def solve_async(self):
+        self._check(self.lib.lvio2d_solve_async(self._h), "lvio2d_solve_async")
+
+    def sync(self):
+        self._check(self.lib.lvio2d_sync(self._h), "lvio2d_sync")
+
+    def get_summaries(self):
+        summ = np.zeros(self.n_windows, dtype=abi.SUMMARY_DTYPE)
+        self._check(self.lib.lvio2d_get_summaries(self._h, summ.ctypes.data), "lvio2d_get_summaries")
+        return summ
+
+    def get_states(self, out=None):
+        if out is None:
+            out = np.zeros((self.n_windows * self.n_frames, 15))
+        self._check(self.lib.lvio2d_get_states(self._h, out.ctypes.data), "lvio2d_get_states")
+        return out
+
+    # ---- split phase (multi-GPU)
+    def set_point_shard(self, rank, world):
+        self._check(self.lib.lvio2d_set_point_shard(self._h, rank, world), "lvio2d_set_point_shard")
+
+    def solve_begin(self):
+        self._check(self.lib.lvio2d_solve_begin(self._h), "lvio2d_solve_begin")
+
+    def eval_laser(self):
+        self._check(self.lib.lvio2d_eval_laser(self._h), "lvio2d_eval_laser")
+
+    def reduce_buffer(self):
+        p, n = C.c_void_p(), C.c_int64()
+        self._check(self.lib.lvio2d_reduce_buffer(self._h, C.byref(p), C.byref(n)), "lvio2d_reduce_buffer")
+        return int(p.value or 0), int(n.value)
+
+    def set_reduce_buffer(self, device_ptr, count):
+        self._check(self.lib.lvio2d_set_reduce_buffer(self._h, device_ptr, count), "lvio2d_set_reduce_buffer")
+
+    def lm_step(self, want_active=False):
+        if want_active:
+            act = C.c_int32()
+            self._check(self.lib.lvio2d_lm_step(self._h, C.byref(act)), "lvio2d_lm_step")
+            return int(act.value)
+        self._check(self.lib.lvio2d_lm_step(self._h, None), "lvio2d_lm_step")
+        return None
+
+    # ---- linearisation / marginalisation
+    def linearize(self, mode=0):
+        B, dim = self.n_windows, 15 * self.n_frames
+        H, g, cost = np.zeros((B, dim, dim)), np.zeros((B, dim)), np.zeros(B)
+        self._check(self.lib.lvio2d_linearize(self._h, mode, _d(H), _d(g), _d(cost)), "lvio2d_linearize")
+        return H, g, cost
+
+    def marginalize(self):
+        B = self.n_windows
+        X0, J, r = np.zeros((B, 15)), np.zeros((B, 15, 15)), np.zeros((B, 15))
+        self._check(self.lib.lvio2d_marginalize(self._h, _d(X0), _d(J), _d(r)), "lvio2d_marginalize")
+        return X0, J, r
+
+    # ---- preintegration
+    def imu_preintegrate(self, sample_offset, samples, bias0):
+        off = np.ascontiguousarray(sample_offset, dtype=np.int64)
+        n = off.size - 1
+        out = np.zeros((n, abi.IMU_BLOB))
+        sm, b0 = _f64(samples), _f64(bias0)
+        self._check(self.lib.lvio2d_imu_preintegrate(self._h, n, off.ctypes.data_as(abi.c_int64_p), _d(sm), _d(b0), _d(out)),
+                    "lvio2d_imu_preintegrate")
+        return out
+
+    def wheel_preintegrate(self, step_offset, steps):
+        off = np.ascontiguousarray(step_offset, dtype=np.int64)
+        n = off.size - 1
+        out = np.zeros((n, abi.WHEEL_BLOB))
+        st = _f64(steps)
+        self._check(self.lib.lvio2d_wheel_preintegrate(self._h, n, off.ctypes.data_as(abi.c_int64_p), _d(st), _d(out)),
+                    "lvio2d_wheel_preintegrate")
+        return out
+
+    def preintegrate_batch(self, sensor_batch):
+        """synth.SensorBatch -> abi.HostBatch through the device preintegrators."""
+        if sensor_batch.n_frames > 1:
+            imu = self.imu_preintegrate(sensor_batch.imu_offset, sensor_batch.imu_samples, sensor_batch.bias0)
+            wheel = self.wheel_preintegrate(sensor_batch.wheel_offset, sensor_batch.wheel_steps)
+        else:
+            imu = wheel = None
+        return sensor_batch.host_batch(imu, wheel)
+
+    # ---- per-factor hooks (auto_diff::compute_res_and_jacobi, reference src/utilies/common.h:201-217)
+    def eval_laser_factor(self, l1_p1, l1_p2, l2_p1, l2_p2, pose_i, pose_j):
+        res, jac = np.zeros(2), np.zeros((2, 12))
+        a = [_f64(x) for x in (l1_p1, l1_p2, l2_p1, l2_p2, pose_i, pose_j)]
+        self._check(self.lib.lvio2d_eval_laser_factor(self._h, *[_d(x) for x in a], _d(res), _d(jac)), "lvio2d_eval_laser_factor")
+        return res, jac
+
+    def eval_imu_factor(self, blob, state_i, state_j):
+        res, jac = np.zeros(15), np.zeros((15, 30))
+        a = [_f64(x) for x in (blob, state_i, state_j)]
+        self._check(self.lib.lvio2d_eval_imu_factor(self._h, *[_d(x) for x in a], _d(res), _d(jac)), "lvio2d_eval_imu_factor")
+        return res, jac
+
+    def eval_wheel_factor(self, blob, pose_i, pose_j):
+        res, jac = np.zeros(3), np.zeros((3, 12))
+        a = [_f64(x) for x in (blob, pose_i, pose_j)]
+        self._check(self.lib.lvio2d_eval_wheel_factor(self._h, *[_d(x) for x in a], _d(res), _d(jac)), "lvio2d_eval_wheel_factor")
+        return res, jac
+
+    def eval_ground_factors(self, pose):
+        res, jac = np.zeros(2), np.zeros((2, 6))
+        p = _f64(pose)
+        self._check(self.lib.lvio2d_eval_ground_factors(self._h, _d(p), _d(res), _d(jac)), "lvio2d_eval_ground_factors")
+        return res, jac
+
+
+# ------------------------------------------------------------------------------------------------------
+# The reference's solver surface
+class Line:
+    """lvio_2d::line (reference src/trajectory/laser_type.h:13-21): end points in a laser frame, z = 0."""
+
+    def __init__(self, p1, p2):
+        self.p1 = np.asarray(p1, dtype=np.float64).reshape(3)
+        self.p2 = np.asarray(p2, dtype=np.float64).reshape(3)
+
+
+class LaserMatch:
+    """lvio_2d::laser_match (laser_type.h:76-85): lines1[j] (reference submap, under pose p1/q1) matched with
+    lines2[j] (this scan, under the frame's pose p2/q2)."""
+
+    def __init__(self, lines1, lines2, p1, q1):
+        assert len(lines1) == len(lines2)
+        self.lines1, self.lines2 = list(lines1), list(lines2)
+        self.p1, self.q1 = np.array(p1, dtype=np.float64), np.array(q1, dtype=np.float64)
+        self.p2, self.q2 = np.zeros(3), np.zeros(3)
+
+
+class FrameInfo:
+    """lvio_2d::frame_info (reference src/trajectory/trajectory_type.h:9-75), laser frames only."""
+
+    def __init__(self, time, p, q, v, bs, imu_observation_result=None, wheel_observation_result=None):
+        self.time = float(time)
+        self.p, self.q = np.array(p, dtype=np.float64), np.array(q, dtype=np.float64)
+        self.v, self.bs = np.array(v, dtype=np.float64), np.array(bs, dtype=np.float64)
+        self.imu_observation_result = imu_observation_result      # [466] blob of interval (i-1, i)
+        self.wheel_observation_result = wheel_observation_result  # [15] blob
+        self.laser_match = None
+        self.is_key_frame = False
+        self.sqrt_H = np.eye(6)
+
+    def add_laser_match(self, match):
+        self.laser_match = match
+
+
+def _pair_weight(l1, l2):
+    # laser_factor::sum (laser_factor.h:38-42)
+    return float(np.sqrt(min(np.linalg.norm(l1.p1 - l1.p2), np.linalg.norm(l2.p1 - l2.p2)) / 2.0 / 0.02))
+
+
+class Solver:
+    """lvio_2d::solver (reference src/factor/solver.h:28-80) backed by the CUDA library.
+
+    solve / init_solve / marginalization take the window as a list of FrameInfo and write the results back in
+    place exactly where the reference does (solver.cpp:685-707 via Ceres, :804-814, :177-190, :401, :409-441).
+    The camera path is not supported (`enable_camera: false` in every shipped config).
+    """
+
+    def __init__(self, params, fast_mode=False):
+        self.params = params
+        self.fast_mode = bool(fast_mode)
+        self.ctx = Context(params)
+        self.has_linearized_block = False
+        self.linearized_X = None
+        self.linearized_jacobians = None
+        self.linearized_residuals = None
+        self.last_summary = None
+
+    def close(self):
+        self.ctx.close()
+
+    # -- flatten a deque of frames into the C ABI batch
+    def _batch(self, frames, topology, with_prior, laser_frames):
+        n = len(frames)
+        states = np.stack([np.concatenate([f.p, f.q, f.v, f.bs]) for f in frames])
+        cmask = np.zeros(n, np.uint8)
+        pts, pl, pw, lines, poff, loff = [], [], [], [], [0], [0]
+        ref_frame = np.full(n, -1, np.int32)
+        ref_pose = np.zeros((n, 6))
+        for i, f in enumerate(frames):
+            m = f.laser_match if i in laser_frames else None
+            if m is not None and len(m.lines1) > 0:
+                for j, (l1, l2) in enumerate(zip(m.lines1, m.lines2)):
+                    w = _pair_weight(l1, l2)
+                    pts += [l2.p1[:2], l2.p2[:2]]
+                    pl += [j, j]
+                    pw += [w, w]
+                    lines.append(np.concatenate([l1.p1[:2], l1.p2[:2]]))
+                if topology == "init":
+                    ref_frame[i] = 0
+                ref_pose[i, 0:3], ref_pose[i, 3:6] = m.p1, m.q1
+            poff.append(len(pts))
+            loff.append(len(lines))
+        if topology == "tracking":
+            # solver.cpp:787-794: every frame but the newest has p, q (and bs in fast_mode) held constant
+            for i in range(n - 1):
+                cmask[i] = abi.CONST_P | abi.CONST_Q | (abi.CONST_BS if self.fast_mode else 0)
+        imu = np.stack([f.imu_observation_result for f in frames[1:]]) if n > 1 else None
+        wheel = np.stack([f.wheel_observation_result for f in frames[1:]]) if n > 1 else None
+        prior = with_prior and self.has_linearized_block and n >= 2
+        return abi.HostBatch(
+            1, n, n, (n - 2) if prior else -1,
+            states=states, const_mask=cmask, point_offset=np.array(poff, np.int64),
+            points=np.array(pts, dtype=np.float64).reshape(-1, 2), point_line=np.array(pl, np.int32),
+            point_weight=np.array(pw, dtype=np.float64), line_offset=np.array(loff, np.int64),
+            lines=np.array(lines, dtype=np.float64).reshape(-1, 4), ref_frame=ref_frame, ref_pose=ref_pose,
+            imu=imu, wheel=wheel,
+            prior_X0=self.linearized_X if prior else None, prior_J=self.linearized_jacobians if prior else None)
+
+    def _write_back(self, frames, states):
+        for f, s in zip(frames, states.reshape(len(frames), 15)):
+            f.p[:], f.q[:], f.v[:], f.bs[:] = s[0:3], s[3:6], s[6:9], s[9:15]
+
+    def solve(self, frame_infos, feature_infos=None):
+        """solver::solve (solver.cpp:631-820): laser factors of the newest frame against the constant reference
+        pose, IMU/wheel chain, ground factors x n, marginalisation prior on frame n-2 unless fast_mode."""
+        n = len(frame_infos)
+        hb = self._batch(frame_infos, "tracking", with_prior=not self.fast_mode, laser_frames={n - 1})
+        self.ctx.set_windows(hb)
+        self.last_summary = self.ctx.solve()
+        self._write_back(frame_infos, self.ctx.get_states())
+        m = frame_infos[-1].laser_match
+        if m is not None:
+            m.p2, m.q2 = frame_infos[-1].p.copy(), frame_infos[-1].q.copy()  # solver.cpp:804-814
+
+    def init_solve(self, frame_infos, feature_infos=None):
+        """solver::init_solve (solver.cpp:171-195): laser factors between frame 0 and every laser frame, nothing
+        constant, then the laser_match poses are refreshed."""
+        n = len(frame_infos)
+        hb = self._batch(frame_infos, "init", with_prior=False, laser_frames=set(range(1, n)))
+        self.ctx.set_windows(hb)
+        self.last_summary = self.ctx.solve()
+        self._write_back(frame_infos, self.ctx.get_states())
+        for f in frame_infos:
+            if f.laser_match is not None:
+                f.laser_match.p1, f.laser_match.q1 = frame_infos[0].p.copy(), frame_infos[0].q.copy()
+                f.laser_match.p2, f.laser_match.q2 = f.p.copy(), f.q.copy()
+
+    def marginalization(self, frame_infos, feature_infos=None):
+        """solver::marginalization (solver.cpp:257-442): early return in fast_mode; otherwise linearise every
+        factor at the current states, Schur-complement onto the newest frame, keep the sqrt-information prior."""
+        if self.fast_mode:
+            return
+        n = len(frame_infos)
+        hb = self._batch(frame_infos, "marg", with_prior=True, laser_frames=set(range(n)))
+        self.ctx.set_windows(hb)
+        X0, J, r = self.ctx.marginalize()
+        self.linearized_X, self.linearized_jacobians, self.linearized_residuals = X0[0], J[0], r[0]
+        frame_infos[-1].sqrt_H = J[0][0:6, 0:6].copy()  # solver.cpp:401
+        self.has_linearized_block = True

@@ -436,22 +436,8 @@ def config_init(n_windows=1, seed=42, n_frames=10, mode="segment"):
 
 
 def config_tracking2(n_windows=1, seed=42):
-    """The steady-state tracking problem of the reference: 2 frames, segment pairs on the newest frame
-    only (solver.cpp:669), frame 0 pose constant, prior on frame n-2 = 0."""
-    sb = make_batch(n_windows, seed, n_frames=2, beams=1081, fov_deg=270.0, topology="tracking", mode="segment")
-    n = 2
-    keep_pts, keep_line, keep_w, off = [], [], [], [0]
-    for f in range(sb.n_windows * n):
-        a, b = int(sb.point_offset[f]), int(sb.point_offset[f + 1])
-        if f % n == n - 1:
-            keep_pts.append(sb.points[a:b])
-            keep_line.append(sb.point_line[a:b])
-            keep_w.append(sb.point_weight[a:b])
-            off.append(off[-1] + (b - a))
-        else:
-            off.append(off[-1])
-    sb.points = np.concatenate(keep_pts).reshape(-1, 2)
-    sb.point_line = np.concatenate(keep_line).astype(np.int32)
-    sb.point_weight = np.concatenate(keep_w)
-    sb.point_offset = np.array(off, dtype=np.int64)
-    return sb
+    """The steady-state tracking problem of the reference: 2 frames, matched segment pairs, frame 0 pose constant,
+    prior on frame n-2 = 0.  solver::solve adds laser factors for the newest frame only (solver.cpp:669): frame 0's
+    pairs hang between two constant poses, so the solver program drops them by itself, while
+    solver::marginalization linearises them too (solver.cpp:448-478)."""
+    return make_batch(n_windows, seed, n_frames=2, beams=1081, fov_deg=270.0, topology="tracking", mode="segment")

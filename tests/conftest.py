@@ -26,3 +26,22 @@ def params():
     import lvio2d_b200 as L
 
     return L.corridor_params()
+
+
+def _stale(target, sources):
+    if not os.path.exists(target):
+        return True
+    t = os.path.getmtime(target)
+    return any(os.path.getmtime(s) > t for s in sources)
+
+
+def pytest_collection_modifyitems(config, items):
+    """GPU tests call the in-tree CUDA library; rebuild it first when a source is newer (nvcc is in the image)."""
+    if not any("gpu" in item.keywords for item in items):
+        return
+    csrc = os.path.join(ROOT, "2dliw-slam_b200", "csrc")
+    srcs = [os.path.join(csrc, f) for f in os.listdir(csrc) if f.endswith((".cu", ".cuh"))] + [os.path.join(ROOT, "include", "lvio2d.h")]
+    if _stale(os.path.join(csrc, "liblvio2d.so"), srcs):
+        import subprocess
+
+        subprocess.check_call(["bash", os.path.join(csrc, "build.sh")])

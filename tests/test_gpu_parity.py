@@ -1,0 +1,252 @@
+"""GPU parity tests: the CUDA path, called through the C ABI (include/lvio2d.h), against the CPU oracle on the same
+seeded inputs.  Tolerances (all float64): factor values/Jacobians 1e-9 relative; normal equations 1e-9 relative to
+the largest entry; solved poses 1e-6 m / rad (the north-star bar is 1e-4 m / 1e-4 rad per keyframe)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import lvio2d_b200 as L
+from lvio2d_b200 import abi
+from lvio2d_b200.params import params_T
+
+pytestmark = pytest.mark.gpu
+
+RNG = np.random.default_rng(11)
+
+
+@pytest.fixture(scope="module")
+def P10():
+    return L.corridor_params(max_iters=10)
+
+
+@pytest.fixture(scope="module")
+def ctx(P10):
+    from lvio2d_b200.solver import Context
+
+    c = Context(P10)
+    yield c
+    c.close()
+
+
+def relclose(a, b, rtol, name=""):
+    scale = max(np.abs(b).max(), 1e-300)
+    err = np.abs(a - b).max() / scale
+    assert err <= rtol, f"{name}: rel err {err:.3e} > {rtol}"
+
+
+def pose_like(sb, f):
+    return sb.states[f, 0:6].copy()
+
+
+def test_library_is_cuda_only(P10):
+    from lvio2d_b200 import solver
+
+    lib = solver.load_library()
+    for name in solver.EXPORTS:
+        assert hasattr(lib, name)
+
+
+def test_factor_hooks_match_oracle(ctx, oracle, P10):
+    sb = L.synth.make_batch(1, 7, n_frames=4, beams=90)
+    hb = oracle.preintegrate_batch(P10, sb)
+    imu, wheel = hb["imu"].reshape(-1, 466), hb["wheel"].reshape(-1, 15)
+    for i in range(1, 4):
+        si, sj = sb.states[i - 1], sb.states[i]
+        r, J = ctx.eval_imu_factor(imu[i - 1], si, sj)
+        orr, oJ = oracle.eval_imu_factor(P10, imu[i - 1], si, sj)
+        relclose(r, orr, 1e-9, "imu res")
+        relclose(J, oJ, 1e-9, "imu jac")
+        r, J = ctx.eval_wheel_factor(wheel[i - 1], si[:6], sj[:6])
+        orr, oJ = oracle.eval_wheel_factor(P10, wheel[i - 1], si[:6], sj[:6])
+        relclose(r, orr, 1e-9, "wheel res")
+        relclose(J, oJ, 1e-8, "wheel jac")
+        r, J = ctx.eval_ground_factors(sj[:6])
+        orr, oJ = oracle.eval_ground_factors(P10, sj[:6])
+        relclose(r, orr, 1e-9, "ground res")
+        relclose(J, oJ, 1e-9, "ground jac")
+    for _ in range(10):
+        pi_, pj_ = sb.states[0, :6], sb.states[2, :6]
+        l1_p1, l1_p2 = np.append(RNG.uniform(-6, 6, 2), 0), np.append(RNG.uniform(-6, 6, 2), 0)
+        l2_p1, l2_p2 = np.append(RNG.uniform(-6, 6, 2), 0), np.append(RNG.uniform(-6, 6, 2), 0)
+        r, J = ctx.eval_laser_factor(l1_p1, l1_p2, l2_p1, l2_p2, pi_, pj_)
+        orr, oJ = oracle.eval_laser_factor(P10, l1_p1, l1_p2, l2_p1, l2_p2, pi_, pj_)
+        relclose(r, orr, 1e-10, "laser res")
+        relclose(J, oJ, 1e-9, "laser jac")
+
+
+def test_preintegration_matches_oracle(ctx, oracle, P10):
+    sb = L.synth.make_batch(2, 3, n_frames=6, beams=32)
+    got = ctx.imu_preintegrate(sb.imu_offset, sb.imu_samples, sb.bias0)
+    want = oracle.imu_preintegrate(P10, sb.imu_offset, sb.imu_samples, sb.bias0)
+    relclose(got[:, :15], want[:, :15], 1e-11, "imu X")
+    relclose(got[:, 15:240], want[:, 15:240], 1e-11, "imu J")
+    relclose(got[:, 240:465], want[:, 240:465], 1e-7, "imu sqrtP")  # cond(P) ~ 1e8 amplifies the inverse's rounding
+    relclose(got[:, 465], want[:, 465], 1e-15, "imu Dt")
+    gw = ctx.wheel_preintegrate(sb.wheel_offset, sb.wheel_steps)
+    ww = oracle.wheel_preintegrate(P10, sb.wheel_offset, sb.wheel_steps)
+    relclose(gw, ww, 1e-12, "wheel blob")
+    # empty interval and ignored steps
+    blob = ctx.wheel_preintegrate([0, 0, 2], np.array([[12.0, 1, 1, 1, 1, 1, 1], [0.05, 0.5, 0, 0, 0, 0, 0.1]]))
+    ob = oracle.wheel_preintegrate(P10, [0, 0, 2], np.array([[12.0, 1, 1, 1, 1, 1, 1], [0.05, 0.5, 0, 0, 0, 0, 0.1]]))
+    relclose(blob, ob, 1e-12, "wheel edge")
+
+
+CASES = {
+    "c1": lambda: L.synth.config_c1(),
+    "c2_small": lambda: L.synth.make_batch(2, 42, n_frames=5, beams=300, fov_deg=270.0),
+    "tracking2": lambda: L.synth.config_tracking2(2),
+    "init": lambda: L.synth.config_init(2, n_frames=6),
+    "init_beam": lambda: L.synth.config_init(1, n_frames=4, mode="beam"),
+    "c2_full": lambda: L.synth.config_c2(1),
+}
+
+
+@pytest.mark.parametrize("case", ["c1", "c2_small", "tracking2", "init", "init_beam"])
+@pytest.mark.parametrize("mode", [0, 1])
+def test_linearize_matches_oracle(ctx, oracle, P10, case, mode):
+    sb = CASES[case]()
+    hb = oracle.preintegrate_batch(P10, sb)
+    ctx.set_windows(hb)
+    H, g, cost = ctx.linearize(mode)
+    oH, og, ocost = oracle.linearize(P10, hb, mode=mode)
+    relclose(cost, ocost, 1e-11, "cost")
+    relclose(g, og, 1e-9, "gradient")
+    relclose(H, oH, 1e-9, "hessian")
+    assert np.allclose(H, np.swapaxes(H, 1, 2), rtol=0, atol=1e-9 * np.abs(H).max())
+
+
+@pytest.mark.parametrize("case,iters", [("c1", 1), ("c2_small", 10), ("tracking2", 20), ("init", 20), ("c2_full", 10),
+                                        ("tracking2", 50), ("init", 50)])
+def test_solve_matches_oracle(oracle, case, iters):
+    """Up to ~20 iterations the two minimisers walk in lock-step (differences ~1e-13).  The reference's default of 50
+    iterations (solver.cpp:161-168, no fast_mode) ends in a slowly converging zig-zag (the ground/wheel residuals are
+    norms) where rounding differences are amplified and an accept/reject decision can flip; there
+    the bar is the north-star's 1e-4 m / 1e-4 rad per keyframe, and costs within 1 %."""
+    from lvio2d_b200.solver import Context
+
+    P = L.corridor_params(max_iters=iters)
+    sb = CASES[case]()
+    hb = oracle.preintegrate_batch(P, sb)
+    with Context(P) as c:
+        c.set_windows(hb)
+        summ = c.solve()
+        got = c.get_states()
+    want, osumm = oracle.solve(P, hb)
+    print(case, "gpu", summ, "oracle", osumm)
+    d = np.abs(got - want)
+    relclose(summ["initial_cost"], osumm["initial_cost"], 1e-11, "initial cost")
+    assert np.all(summ["final_cost"] <= summ["initial_cost"])
+    if iters <= 20:
+        assert np.array_equal(summ["iterations"], osumm["iterations"])
+        assert np.array_equal(summ["termination"], osumm["termination"])
+        assert np.array_equal(summ["num_successful_steps"], osumm["num_successful_steps"])
+        relclose(summ["final_cost"], osumm["final_cost"], 1e-9, "final cost")
+        relclose(summ["final_radius"], osumm["final_radius"], 1e-6, "final radius")
+        assert d[:, 0:6].max() < 1e-9 and d[:, 6:].max() < 1e-9, (d[:, 0:6].max(), d[:, 6:].max())
+    else:
+        relclose(summ["final_cost"], osumm["final_cost"], 1e-2, "final cost")
+        assert d[:, 0:3].max() < 1e-4 and d[:, 3:6].max() < 1e-4, (d[:, 0:3].max(), d[:, 3:6].max())
+
+
+def test_marginalize_matches_oracle(ctx, oracle, P10):
+    for case in ("tracking2", "init"):
+        sb = CASES[case]()
+        hb = oracle.preintegrate_batch(P10, sb)
+        ctx.set_windows(hb)
+        X0, J, r = ctx.marginalize()
+        oX0, oJ, orr, odH, odg = oracle.marginalize(P10, hb)
+        relclose(X0, oX0, 1e-15, "X0")
+        # the prior only enters through J^T J (marginalization_factor.h:50 drops linearized_R); rows are defined
+        # up to sign / rotation inside (near-)degenerate eigenspaces
+        JTJ, oJTJ = np.einsum("bki,bkj->bij", J, J), np.einsum("bki,bkj->bij", oJ, oJ)
+        relclose(JTJ, oJTJ, 1e-7, "J_lin^T J_lin")
+        relclose(np.abs(np.linalg.norm(J, axis=2)), np.abs(np.linalg.norm(oJ, axis=2)), 1e-6, "row norms (sqrt eigenvalues)")
+        relclose(np.einsum("bki,bk->bi", J, r), np.einsum("bki,bk->bi", oJ, orr), 1e-6, "J^T r")
+
+
+def test_solver_class_mirrors_reference_flow(oracle, P10):
+    """lvio_2d::solver surface: solve -> marginalization -> solve with the prior, like trajectory::do_tracking."""
+    from lvio2d_b200.solver import FrameInfo, LaserMatch, Line, Solver
+
+    P = L.corridor_params(max_iters=50)
+    sb = L.synth.config_tracking2(1)
+    hb = oracle.preintegrate_batch(P, sb)
+    imu, wheel = hb["imu"].reshape(-1, 466), hb["wheel"].reshape(-1, 15)
+    frames = []
+    for i in range(2):
+        s = sb.states[i]
+        f = FrameInfo(0.1 * i, s[0:3], s[3:6], s[6:9], s[9:15], imu[i - 1] if i else None, wheel[i - 1] if i else None)
+        a, b = int(sb.point_offset[i]), int(sb.point_offset[i + 1])
+        l0 = int(sb.line_offset[i])
+        lines1, lines2 = [], []
+        for k in range(a, b, 2):
+            li = sb.lines[l0 + sb.point_line[k]]
+            lines1.append(Line([li[0], li[1], 0], [li[2], li[3], 0]))
+            lines2.append(Line([*sb.points[k], 0], [*sb.points[k + 1], 0]))
+        f.add_laser_match(LaserMatch(lines1, lines2, sb.ref_pose[i, 0:3], sb.ref_pose[i, 3:6]))
+        frames.append(f)
+    sol = Solver(P, fast_mode=False)
+    # the oracle solves the very batch the Solver flattens the frames into (no prior yet, frame 0 constant)
+    hb_s = sol._batch(frames, "tracking", with_prior=True, laser_frames={1})
+    assert hb_s.prior_frame == -1 and hb_s["const_mask"][0] == (abi.CONST_P | abi.CONST_Q)
+    P20 = L.corridor_params(max_iters=20)
+    sol.ctx.close()
+    sol = Solver(P20, fast_mode=False)
+    want, _ = oracle.solve(P20, hb_s)
+    sol.solve(frames)
+    got = np.stack([np.concatenate([f.p, f.q, f.v, f.bs]) for f in frames])
+    assert np.abs(got - want).max() < 1e-9
+    assert np.array_equal(frames[-1].laser_match.p2, frames[-1].p)
+    sol.marginalization(frames)
+    assert sol.has_linearized_block and sol.linearized_jacobians.shape == (15, 15)
+    hb_m = sol._batch(frames, "marg", with_prior=False, laser_frames={0, 1})
+    oX0, oJ, _, _, _ = oracle.marginalize(P20, hb_m)
+    relclose(sol.linearized_jacobians.T @ sol.linearized_jacobians, oJ[0].T @ oJ[0], 1e-6, "prior information")
+    assert np.array_equal(sol.linearized_X, got[1])
+    # second solve of the flow: the prior now sits on frame n-2
+    hb2 = sol._batch(frames, "tracking", with_prior=True, laser_frames={1})
+    assert hb2.prior_frame == 0
+    sol.solve(frames)
+    want2, _ = oracle.solve(P20, hb2)
+    got2 = np.stack([np.concatenate([f.p, f.q, f.v, f.bs]) for f in frames])
+    assert np.abs(got2 - want2).max() < 1e-8
+    sol.close()
+
+
+def test_point_sharded_solve_matches_unsharded(oracle, P10):
+    """Two ranks, each owning half of every frame's points, exchanging only the summed per-frame blocks once per
+    iteration (what the NCCL all-reduce does in bench.py --gpus N), reproduce the unsharded solve."""
+    import torch
+    from lvio2d_b200.solver import Context
+
+    sb = L.synth.make_batch(2, 5, n_frames=4, beams=257)
+    hb = oracle.preintegrate_batch(P10, sb)
+    with Context(P10) as ref:
+        ref.set_windows(hb)
+        ref.solve()
+        want = ref.get_states()
+    ranks = []
+    for rank in range(2):
+        c = Context(P10)
+        c.set_windows(hb)
+        c.set_point_shard(rank, 2)
+        _, n = c.reduce_buffer()
+        t = torch.zeros(n, dtype=torch.float64, device="cuda")
+        c.set_reduce_buffer(t.data_ptr(), n)
+        c.solve_begin()
+        ranks.append((c, t))
+    for it in range(P10.max_iters + 1):
+        for c, _ in ranks:
+            c.eval_laser()
+            c.sync()
+        total = ranks[0][1] + ranks[1][1]
+        for _, t in ranks:
+            t.copy_(total)
+        torch.cuda.synchronize()
+        active = [c.lm_step(want_active=True) for c, _ in ranks]
+        assert active[0] == active[1]
+    for c, _ in ranks:
+        got = c.get_states()
+        assert np.abs(got - want).max() < 1e-9
+        c.close()
