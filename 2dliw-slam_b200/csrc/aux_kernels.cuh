@@ -10,6 +10,25 @@
 
 namespace lv {
 
+// in-place lower Cholesky of a 15x15 block in shared memory (lane r owns row r); false when a pivot is not positive
+__device__ __forceinline__ bool chol15(double* A, int lane) {
+    for (int k = 0; k < 15; ++k) {
+        const double d = A[k * 15 + k];
+        if (!(d > 0.0) || !isfinite(d)) return false;
+        const double l = sqrt(d), inv = 1.0 / l;
+        __syncwarp();
+        if (lane == k) A[k * 15 + k] = l;
+        else if (lane > k && lane < 15) A[lane * 15 + k] *= inv;
+        __syncwarp();
+        if (lane > k && lane < 15) {
+            const double lr = A[lane * 15 + k];
+            for (int c = k + 1; c <= lane; ++c) A[lane * 15 + c] -= lr * A[c * 15 + k];
+        }
+        __syncwarp();
+    }
+    return true;
+}
+
 // ------------------------------------------------------------------ IMU preintegration: one warp per interval
 // shared memory per warp: J[225] P[225] F[225] T[225] G[15x12 = 180] X[15] -> 1100 doubles
 constexpr int kImuPreSmem = 1104;

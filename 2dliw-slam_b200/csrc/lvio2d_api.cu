@@ -56,11 +56,17 @@ struct lvio2d_ctx {
     const int32_t* ref_frame = nullptr; const double* ref_pose = nullptr; const double* imu = nullptr; const double* wheel = nullptr;
     const double* prior_X0 = nullptr; const double* prior_J = nullptr; const uint8_t* const_mask = nullptr;
     // work buffers
-    DevBuf b_x0, b_x, b_xc, b_scale, b_ftab, b_reftab, b_wlines, b_part, b_lb, b_pair, b_fac, b_state, b_status, b_active, b_active1, b_reduce;
+    DevBuf b_x0, b_x, b_xc, b_scale, b_ftab, b_reftab, b_wlines, b_part, b_lb, b_items, b_vec, b_fac, b_state, b_status, b_active, b_active1, b_reduce;
     DevBuf b_tmp[8];
     double* ext_reduce = nullptr; int64_t ext_reduce_count = 0;
     int step_calls = 0;
     bool have_solution = false;
+    // measurement
+    bool profiling = false;
+    std::vector<cudaEvent_t> ev_scan, ev_win, ev_fac;   // begin/end pairs
+    size_t ev_scan_used = 0, ev_win_used = 0, ev_fac_used = 0;
+    double launches = 0;
+    double scan_bytes_per_launch = 0;
 };
 
 namespace {
@@ -116,7 +122,12 @@ int take(lvio2d_ctx* ctx, bool bind, DevBuf& buf, const T*& dst, const void* src
     return LVIO2D_OK;
 }
 
-size_t window_smem_bytes(const lvio2d_ctx* c) { return WarpSmem::doubles(c->n, c->npad) * sizeof(double); }
+cudaEvent_t next_event(std::vector<cudaEvent_t>& pool, size_t& used) {
+    if (used == pool.size()) { cudaEvent_t e; cudaEventCreate(&e); pool.push_back(e); }
+    return pool[used++];
+}
+
+size_t window_smem_bytes(const lvio2d_ctx* c) { return window_smem_doubles(c->n, c->arrow) * sizeof(double); }
 
 int launch_scan_match(lvio2d_ctx* ctx, int mode = 0) {
     ScanMatchArgs a;
@@ -131,6 +142,7 @@ int launch_scan_match(lvio2d_ctx* ctx, int mode = 0) {
     const int wpc = 8;
     const int grid = (a.n_items + wpc - 1) / wpc;
     const size_t smem = (size_t)wpc * ctx->line_cap * (ctx->arrow ? kRowFree : kRowTrack) * sizeof(double);
+    if (ctx->profiling) cudaEventRecord(next_event(ctx->ev_scan, ctx->ev_scan_used), ctx->stream);
 #define LAUNCH_SM(RF, HW)                                                                                                \
     do {                                                                                                                 \
         CK(cudaFuncSetAttribute(scan_match_kernel<RF, HW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));     \
@@ -139,6 +151,8 @@ int launch_scan_match(lvio2d_ctx* ctx, int mode = 0) {
     if (ctx->arrow) { if (ctx->has_weight) LAUNCH_SM(true, true); else LAUNCH_SM(true, false); }
     else { if (ctx->has_weight) LAUNCH_SM(false, true); else LAUNCH_SM(false, false); }
 #undef LAUNCH_SM
+    if (ctx->profiling) cudaEventRecord(next_event(ctx->ev_scan, ctx->ev_scan_used), ctx->stream);
+    ctx->launches += 1;
     CK(cudaGetLastError());
     return LVIO2D_OK;
 }
@@ -155,23 +169,38 @@ WindowArgs window_args(lvio2d_ctx* ctx, int mode) {
     a.partial = ctx->b_part.as<double>();
     a.x = ctx->b_x.as<double>(); a.xc = ctx->b_xc.as<double>(); a.scale = ctx->b_scale.as<double>();
     a.laser_blocks = ctx->b_lb.as<double>(); a.frame_tab = ctx->b_ftab.as<double>();
-    a.pair = ctx->b_pair.as<double>(); a.fac = ctx->b_fac.as<double>();
+    a.items = ctx->b_items.as<double>(); a.vec = ctx->b_vec.as<double>(); a.fac = ctx->b_fac.as<double>();
     a.state = ctx->b_state.as<LMState>(); a.win_status = ctx->b_status.as<int32_t>();
     return a;
 }
 
+int launch_factors(lvio2d_ctx* ctx, const WindowArgs& a) {
+    const int wpc = 4;
+    const int items = ctx->B * ctx->n;
+    const size_t smem = (size_t)wpc * kFactorSmem * sizeof(double);
+    if (ctx->profiling) cudaEventRecord(next_event(ctx->ev_fac, ctx->ev_fac_used), ctx->stream);
+    ctx->launches += 1;
+    factor_kernel<<<(items + wpc - 1) / wpc, wpc * 32, smem, ctx->stream>>>(a);
+    if (ctx->profiling) cudaEventRecord(next_event(ctx->ev_fac, ctx->ev_fac_used), ctx->stream);
+    CK(cudaGetLastError());
+    return LVIO2D_OK;
+}
+
 int launch_window(lvio2d_ctx* ctx, const WindowArgs& a) {
-    const int per_warp = (int)WarpSmem::doubles(ctx->n, ctx->npad);
+    const int per_warp = (int)window_smem_doubles(ctx->n, ctx->arrow);
     const int wpc = std::max(1, std::min<int>(4, (int)((200 * 1024) / (per_warp * sizeof(double)))));
     const size_t smem = (size_t)wpc * per_warp * sizeof(double);
     const int grid = (ctx->B + wpc - 1) / wpc;
+    if (ctx->profiling) cudaEventRecord(next_event(ctx->ev_win, ctx->ev_win_used), ctx->stream);
+    ctx->launches += 1;
     if (ctx->arrow) {
-        CK(cudaFuncSetAttribute(window_step_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        window_step_kernel<true><<<grid, wpc * 32, smem, ctx->stream>>>(a, per_warp);
+        CK(cudaFuncSetAttribute(window_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        window_kernel<true><<<grid, wpc * 32, smem, ctx->stream>>>(a, per_warp);
     } else {
-        CK(cudaFuncSetAttribute(window_step_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        window_step_kernel<false><<<grid, wpc * 32, smem, ctx->stream>>>(a, per_warp);
+        CK(cudaFuncSetAttribute(window_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        window_kernel<false><<<grid, wpc * 32, smem, ctx->stream>>>(a, per_warp);
     }
+    if (ctx->profiling) cudaEventRecord(next_event(ctx->ev_win, ctx->ev_win_used), ctx->stream);
     CK(cudaGetLastError());
     return LVIO2D_OK;
 }
@@ -182,18 +211,13 @@ int begin_solve(lvio2d_ctx* ctx, bool from_solution = false) {
     const void* src = from_solution ? ctx->b_x.p : ctx->b_x0.p;
     CK(cudaMemcpyAsync(ctx->b_xc.p, src, ns * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
     if (!from_solution) CK(cudaMemcpyAsync(ctx->b_x.p, src, ns * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
-    std::vector<LMState> st(ctx->B);
-    for (auto& s : st) {
-        std::memset(&s, 0, sizeof(s));
-        s.radius = ctx->opt.initial_radius;
-        s.decrease_factor = 2.0;
-    }
-    CK(cudaMemcpyAsync(ctx->b_state.p, st.data(), sizeof(LMState) * ctx->B, cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));  // st is a stack vector
-    CK(cudaMemsetAsync(ctx->b_status.p, 0, sizeof(int32_t) * ctx->B, ctx->stream));
+    init_state_kernel<<<(ctx->B + 127) / 128, 128, 0, ctx->stream>>>(ctx->b_state.as<LMState>(), ctx->b_status.as<int32_t>(), ctx->B,
+                                                                     ctx->opt.initial_radius);
+    ctx->launches += 1;
     const int F = ctx->B * ctx->n;
     frame_table_kernel<<<(F + 127) / 128, 128, 0, ctx->stream>>>(ctx->C, ctx->b_xc.as<double>(), 15, ctx->b_ftab.as<double>(), F);
     CK(cudaGetLastError());
+    ctx->launches += 1;
     ctx->step_calls = 0;
     return LVIO2D_OK;
 }
@@ -290,8 +314,8 @@ int setup_batch(lvio2d_ctx* ctx, const lvio2d_window_batch* b, bool bind) {
     bool ok = ctx->b_x0.ensure(ns) && ctx->b_x.ensure(ns) && ctx->b_xc.ensure(ns) && ctx->b_scale.ensure(ns) &&
               ctx->b_ftab.ensure((size_t)F * kFrameTab * sizeof(double)) && ctx->b_reftab.ensure((size_t)F * kFrameTab * sizeof(double)) &&
               ctx->b_wlines.ensure(std::max<size_t>(1, (size_t)ctx->L) * sizeof(double4)) &&
-              ctx->b_part.ensure((size_t)F * ctx->tiles * ctx->npad * sizeof(double)) && ctx->b_lb.ensure((size_t)F * ctx->npad * sizeof(double)) &&
-              ctx->b_pair.ensure(std::max<size_t>(1, (size_t)B * (n - 1)) * 3 * kBlk * sizeof(double)) &&
+              ctx->b_part.ensure((size_t)F * ctx->tiles * ctx->npad * sizeof(double)) && ctx->b_lb.ensure((size_t)2 * F * ctx->npad * sizeof(double)) &&
+              ctx->b_items.ensure((size_t)2 * F * kItem * sizeof(double)) && ctx->b_vec.ensure((size_t)B * 2 * n * 15 * sizeof(double)) &&
               ctx->b_fac.ensure((size_t)F * 3 * kBlk * sizeof(double)) && ctx->b_state.ensure(sizeof(LMState) * B) &&
               ctx->b_status.ensure(sizeof(int32_t) * B) && ctx->b_active.ensure(F) && ctx->b_active1.ensure(F) && ctx->b_reduce.ensure((size_t)F * ctx->npad * sizeof(double));
     if (!ok) return fail(ctx, LVIO2D_ERR_ALLOC, "cudaMalloc(work buffers)");
@@ -299,7 +323,6 @@ int setup_batch(lvio2d_ctx* ctx, const lvio2d_window_batch* b, bool bind) {
     CK(cudaMemcpyAsync(ctx->b_active.p, active.data(), F, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(ctx->b_active1.p, active1.data(), F, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemsetAsync(ctx->b_part.p, 0, (size_t)F * ctx->tiles * ctx->npad * sizeof(double), ctx->stream));
-    CK(cudaMemsetAsync(ctx->b_pair.p, 0, std::max<size_t>(1, (size_t)B * (n - 1)) * 3 * kBlk * sizeof(double), ctx->stream));
     if (has_laser && ctx->L > 0) {
         // world lines of every local map that hangs under an external constant pose
         frame_table_kernel<<<(F + 127) / 128, 128, 0, ctx->stream>>>(ctx->C, ctx->ref_pose, 6, ctx->b_reftab.as<double>(), F);
@@ -308,6 +331,14 @@ int setup_batch(lvio2d_ctx* ctx, const lvio2d_window_batch* b, bool bind) {
         CK(cudaGetLastError());
     }
     CK(cudaStreamSynchronize(ctx->stream));  // host vectors above go out of scope
+    {
+        // algorithmic bytes one scan-match launch moves when every active frame is processed
+        double pts = 0, lns = 0, frames = 0;
+        for (int f = 0; f < F; ++f)
+            if (active[f]) { pts += (double)(poff[f + 1] - poff[f]); lns += (double)(loff[f + 1] - loff[f]); frames += 1; }
+        ctx->scan_bytes_per_launch = pts * (16 + 4 + (ctx->has_weight ? 8 : 0)) + lns * 32 +
+                                     frames * (kFrameTab * 8.0 + (double)ctx->tiles * ctx->npad * 8.0);
+    }
     ctx->ext_reduce = nullptr;
     ctx->have = true;
     ctx->have_solution = false;
@@ -319,6 +350,7 @@ int run_linearize(lvio2d_ctx* ctx, int mode, WindowArgs& a) {
     if (rc) return rc;
     if ((rc = launch_scan_match(ctx, mode))) return rc;
     a.x = ctx->b_x.as<double>();
+    if ((rc = launch_factors(ctx, a))) return rc;
     return launch_window(ctx, a);
 }
 
@@ -372,10 +404,13 @@ void lvio2d_destroy(lvio2d_ctx* ctx) {
     cudaStreamSynchronize(ctx->stream);
     DevBuf* all[] = {&ctx->b_points, &ctx->b_pline, &ctx->b_pweight, &ctx->b_poff, &ctx->b_loff, &ctx->b_lines, &ctx->b_ref, &ctx->b_refpose,
                      &ctx->b_imu, &ctx->b_wheel, &ctx->b_pX0, &ctx->b_pJ, &ctx->b_cmask, &ctx->b_x0, &ctx->b_x, &ctx->b_xc, &ctx->b_scale,
-                     &ctx->b_ftab, &ctx->b_reftab, &ctx->b_wlines, &ctx->b_part, &ctx->b_lb, &ctx->b_pair, &ctx->b_fac, &ctx->b_state,
+                     &ctx->b_ftab, &ctx->b_reftab, &ctx->b_wlines, &ctx->b_part, &ctx->b_lb, &ctx->b_items, &ctx->b_vec, &ctx->b_fac, &ctx->b_state,
                      &ctx->b_status, &ctx->b_active, &ctx->b_active1, &ctx->b_reduce};
     for (DevBuf* b : all) b->release();
     for (auto& b : ctx->b_tmp) b.release();
+    for (auto e : ctx->ev_scan) cudaEventDestroy(e);
+    for (auto e : ctx->ev_win) cudaEventDestroy(e);
+    for (auto e : ctx->ev_fac) cudaEventDestroy(e);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -391,6 +426,29 @@ int lvio2d_reset_states(lvio2d_ctx* ctx, const double* host_states) {
     CK(cudaSetDevice(ctx->device));
     CK(cudaMemcpyAsync(ctx->b_x0.p, host_states, (size_t)ctx->B * ctx->n * 15 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
     ctx->have_solution = false;
+    return LVIO2D_OK;
+}
+
+int lvio2d_set_profiling(lvio2d_ctx* ctx, int32_t on) {
+    if (!ctx) return LVIO2D_ERR_INVALID_ARG;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->profiling = on != 0;
+    ctx->ev_scan_used = ctx->ev_win_used = ctx->ev_fac_used = 0;
+    ctx->launches = 0;
+    return LVIO2D_OK;
+}
+
+int lvio2d_get_profile(lvio2d_ctx* ctx, double* out) {
+    if (!ctx || !out) return LVIO2D_ERR_INVALID_ARG;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    for (int i = 0; i < 8; ++i) out[i] = 0.0;
+    for (size_t i = 0; i + 1 < ctx->ev_scan_used; i += 2) { float ms = 0; cudaEventElapsedTime(&ms, ctx->ev_scan[i], ctx->ev_scan[i + 1]); out[0] += ms; out[1] += 1; }
+    for (size_t i = 0; i + 1 < ctx->ev_win_used; i += 2) { float ms = 0; cudaEventElapsedTime(&ms, ctx->ev_win[i], ctx->ev_win[i + 1]); out[2] += ms; out[3] += 1; }
+    for (size_t i = 0; i + 1 < ctx->ev_fac_used; i += 2) { float ms = 0; cudaEventElapsedTime(&ms, ctx->ev_fac[i], ctx->ev_fac[i + 1]); out[6] += ms; out[7] += 1; }
+    out[4] = ctx->launches;
+    out[5] = ctx->scan_bytes_per_launch;
     return LVIO2D_OK;
 }
 
@@ -446,7 +504,9 @@ int lvio2d_lm_step(lvio2d_ctx* ctx, int32_t* n_active) {
     // the (all-reduced) per-frame blocks stand in for the tile partials
     a.partial = ctx->ext_reduce ? ctx->ext_reduce : ctx->b_reduce.as<double>();
     a.tiles = 1;
-    int rc = launch_window(ctx, a);
+    int rc = launch_factors(ctx, a);
+    if (rc) return rc;
+    rc = launch_window(ctx, a);
     if (rc) return rc;
     ++ctx->step_calls;
     ctx->have_solution = true;
@@ -471,6 +531,7 @@ int lvio2d_solve_async(lvio2d_ctx* ctx) {
     // trip 0 linearises the initial point; trips 1..max_iters each judge one candidate
     for (int it = 0; it <= ctx->opt.max_iters; ++it) {
         if ((rc = launch_scan_match(ctx))) return rc;
+        if ((rc = launch_factors(ctx, a))) return rc;
         if ((rc = launch_window(ctx, a))) return rc;
     }
     ctx->have_solution = true;

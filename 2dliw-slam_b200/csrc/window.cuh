@@ -1,24 +1,30 @@
-// window.cuh — one warp per sliding window: everything of an LM iteration that is NOT the scan-point pass.
+// window.cuh — everything of an LM iteration that is NOT the scan-point pass, as two kernels:
 //
-// Replaces ceres::Solve as configured by solver::solve / solver::do_init_solve (reference
-// src/factor/solver.cpp:795-802, :161-168) — Ceres 1.14 TrustRegionMinimizer + LevenbergMarquardtStrategy
-// with Jacobi scaling and an exact Schur/Cholesky step — together with the residual blocks Ceres would
-// evaluate with Jets: imu_factor (imu_factor.h:13-89), wheel_odom_factor (wheel_factor.h:12-73),
-// ground_factor_p/q (ground_factor.h:27-82; added `multiplicity` times, solver.cpp:727-743),
-// marginalization_factor (marginalization_factor.h:22-53) and the constness rules of solver.cpp:787-794.
+//   factor_kernel  one warp per (window, frame i): the residual blocks hanging on frame i — IMU and wheel factor of
+//                  the pair (i-1, i), `multiplicity` ground factors and the marginalisation prior of frame i —
+//                  evaluated AT THE CANDIDATE point: whitened Jacobians, J^T J blocks, J^T r, r^2.
+//   window_kernel  one warp per window: Ceres' minimiser logic + the linear solve.
 //
-// One call of window_step_kernel = one trip through the minimiser loop for every window of the batch:
-//   (1) sum the scan-match partials of the candidate point (scan_match.cuh), add the small factors' cost;
-//   (2) Ceres' parameter-/function-tolerance tests and the step-quality test rho > 1e-3; accept or reject,
-//       update the trust-region radius;
-//   (3) linearise IMU / wheel / ground / prior at the accepted point, assemble the block-tridiagonal
-//       (+ frame-0 arrow in the initialisation topology) normal equations with the laser blocks;
-//   (4) Jacobi scaling, LM damping, block Cholesky in reverse frame order (no fill-in for either topology),
-//       step, model cost change; invalid steps shrink the radius and retry in place;
-//   (5) candidate = Plus(x, step) (so3_parameterization: wrap(theta + delta), factor_common.h:40-53) and
-//       its laser frame tables for the next scan-match pass.
-// The candidate's linearisation is evaluated in the same scan pass as its cost, so an accepted step costs
-// one pass over the points, not two.
+// Together they replace ceres::Solve as configured by solver::solve / solver::do_init_solve (reference
+// src/factor/solver.cpp:795-802, :161-168) — Ceres 1.14 TrustRegionMinimizer + LevenbergMarquardtStrategy with Jacobi
+// scaling and an exact Schur/Cholesky step — and the residual blocks Ceres would evaluate with Jets: imu_factor
+// (imu_factor.h:13-89), wheel_odom_factor (wheel_factor.h:12-73), ground_factor_p/q (ground_factor.h:27-82; added
+// `multiplicity` times, solver.cpp:727-743), marginalization_factor (marginalization_factor.h:22-53) under the
+// constness rules of solver.cpp:787-794.
+//
+// One trip of the minimiser loop = scan_match_kernel + factor_kernel (both at the candidate, independent of each
+// other) followed by window_kernel:
+//   (1) candidate cost = laser tiles + factor items; Ceres' parameter-/function-tolerance tests, then the
+//       step-quality test rho > 1e-3; accept (flip the per-window buffer parity) or reject; trust-region update;
+//   (2) assemble the block-tridiagonal (+ frame-0 arrow in the initialisation topology) normal equations of the
+//       accepted point, Jacobi scaling, LM damping;
+//   (3) block elimination in reverse frame order (no fill-in for either topology) with Gauss-Jordan inverses of
+//       the 15x15 pivots (rows in registers, no serial triangular solves), step, model cost change; invalid steps
+//       shrink the radius and retry in place;
+//   (4) candidate = Plus(x, step) (so3_parameterization: wrap(theta + delta), factor_common.h:40-53) and its laser
+//       frame tables for the next scan-match pass.
+// Because the candidate's linearisation is produced together with its cost, an accepted step costs one pass over
+// the data, not two (Ceres: cost-only evaluation, then a Jacobian evaluation at the same point).
 //
 // Layout of every 15x15 block: packed row-major, 225 doubles (conflict-free for lane-per-row access).
 #pragma once
@@ -33,6 +39,7 @@ namespace lv {
 struct LMState {
     double radius, decrease_factor, cost, model_cost_change, x_norm, initial_cost;
     int32_t iteration, num_invalid, status, termination, n_success, n_unsuccess, last_success, started;
+    int32_t cur, pad0;  // parity of the buffers that hold the linearisation of the accepted point
 };
 
 struct LMOptions {
@@ -41,6 +48,10 @@ struct LMOptions {
     double max_radius, min_radius, min_relative_decrease, min_lm_diagonal, max_lm_diagonal;
     int32_t max_consecutive_invalid;
 };
+
+constexpr int kBlk = 225;
+// factor item record: H_aa | H_ab | H_bb | g_a | g_b | cost | pad
+constexpr int kItemHaa = 0, kItemHab = 225, kItemHbb = 450, kItemGa = 675, kItemGb = 690, kItemCost = 705, kItem = 712;
 
 struct WindowArgs {
     Consts C;
@@ -58,12 +69,13 @@ struct WindowArgs {
     double* x;                      // [B*n][15] accepted point
     double* xc;                     // [B*n][15] candidate
     double* scale;                  // [B*n][15] Jacobi scaling
-    double* laser_blocks;           // [B*n][pad] blocks at the accepted point
+    double* laser_blocks;           // [2][B*n][pad]  parity-buffered laser blocks
+    double* items;                  // [2][B*n][kItem] parity-buffered factor items
     double* frame_tab;              // [B*n][24] tables of the candidate
-    double* pair;                   // [B*(n-1)][3][225]  H_aa | H_ab | H_bb of pair (i-1, i)
-    double* fac;                    // [B*n][3][225]      L_i | E_i | F_i
+    double* fac;                    // [B*n][3][225]  T_i | T'_i | -
+    double* vec;                    // [B][2][n*15]  gradient scratch
     LMState* state;                 // [B]
-    int32_t* win_status;            // [B] mirror of state.status for the scan-match kernel
+    int32_t* win_status;            // [B] mirror of state.status for the other kernels
     // optional dense outputs (lvio2d_linearize): H [B][15n][15n], g [B][15n], cost [B]
     double* dense_H;
     double* dense_g;
@@ -72,8 +84,6 @@ struct WindowArgs {
     double* marg_H;                 // [B][225] Schur complement on the last frame
     double* marg_g;                 // [B][15]
 };
-
-constexpr int kBlk = 225;
 
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
@@ -85,50 +95,246 @@ __device__ __forceinline__ double warp_max(double v) {
     for (int d = 16; d > 0; d >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, d));
     return v;
 }
+__device__ __forceinline__ bool col_const(uint8_t mask, int c) {  // c: column 0..14 of [p q v bs]
+    const int blk = c < 3 ? 0 : (c < 6 ? 1 : (c < 9 ? 2 : 3));
+    return (mask >> blk) & 1;
+}
 
-// ---- warp-cooperative 15x15 kernels on shared memory (lane r owns row r; lanes >= 15 idle)
-// in-place lower Cholesky; returns false (uniformly) when a pivot is not positive
-__device__ __forceinline__ bool chol15(double* A, int lane) {
+// =====================================================================================================
+// factor_kernel: per-warp shared memory = blob 480 | J 15x32 | wheel 3x16 | ground 2x8 | prior r 16; the 30x30 result
+// aliases blob + J once every lane is done reading them
+constexpr int kFactorSmem = 480 + 480 + 48 + 16 + 16;
+__global__ void __launch_bounds__(128) factor_kernel(WindowArgs a) {
+    extern __shared__ __align__(16) double smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int n = a.n_frames;
+    const int item = blockIdx.x * (blockDim.x >> 5) + warp;
+    if (item >= a.n_windows * n) return;
+    const int w = item / n, i = item - w * n;
+    if (a.win_status[w] != 0) return;
+    const int mode = a.mode;
+    const int parity = 1 - a.state[w].cur;
+    double* out = a.items + ((size_t)parity * a.n_windows * n + item) * kItem;
+    double* sblob = smem + (size_t)warp * kFactorSmem;
+    double* sJ = sblob + 480;   // whitened IMU Jacobian [15][32]; column 30 = whitened residual
+    double* sW = sJ + 480;      // wheel [3][16]: cols 0..11 Jacobian, col 12 residual
+    double* sG = sW + 48;       // ground [2][8]: cols 0..5 Jacobian, col 6 residual
+    double* sP = sG + 16;       // prior residual [15]
+    double* sH = sblob;         // [30][30], aliases sblob + sJ after the Jacobian products
+    const double* X = a.xc + (size_t)w * n * 15;
+    const uint8_t* cm = a.const_mask + (size_t)w * n;
+    const uint8_t mb = mode == 1 ? 0 : cm[i];
+    const uint8_t ma = (mode == 1 || i == 0) ? 0 : cm[i - 1];
+    const double* xb = X + 15 * i;
+    const double* xa = X + 15 * (i > 0 ? i - 1 : 0);
+    const bool imu_on = i > 0 && a.has_imu && ((ma & 15) != 15 || (mb & 15) != 15);
+    const bool wheel_on = i > 0 && a.has_wheel && ((ma & 3) != 3 || (mb & 3) != 3);
+    const bool ground_on = a.ground_multiplicity > 0 && (mb & 3) != 3;
+    const bool prior_on = a.prior_frame == i && (mb & 15) != 15;
+    double cost = 0.0;
+    // ---- IMU: lanes 0..29 one Jacobian column each, lane 30 the residual
+    if (imu_on) {
+        const double* blob = a.imu + ((size_t)w * (n - 1) + (i - 1)) * 466;
+        for (int k = lane; k < 466; k += 32) sblob[k] = blob[k];
+        __syncwarp();
+        double col[15];
+        if (lane < 30) imu_jacobian_column(a.C, sblob, xa, xb, lane, col);
+        else if (lane == 30) imu_raw_residual(a.C, sblob, xa, xb, col);
+        if (lane < 31) {
+            const bool dead = lane < 30 && col_const(lane < 15 ? ma : mb, lane % 15);
+            const double* Sq = sblob + 240;  // sqrt_inverse_P = L^T: upper triangular
+#pragma unroll
+            for (int r = 0; r < 15; ++r) {
+                double s = 0.0;
+#pragma unroll
+                for (int k = r; k < 15; ++k) s += Sq[r * 15 + k] * col[k];
+                sJ[r * 32 + lane] = dead ? 0.0 : s;
+                if (lane == 30) cost += s * s;
+            }
+        } else {
+#pragma unroll
+            for (int r = 0; r < 15; ++r) sJ[r * 32 + 31] = 0.0;
+        }
+    } else {
+        for (int k = lane; k < 480; k += 32) sJ[k] = 0.0;
+    }
+    // ---- wheel: lanes 0..11 dual directions, lane 12 value
+    if (wheel_on) {
+        const double* blob = a.wheel + ((size_t)w * (n - 1) + (i - 1)) * 15;
+        if (lane < 13) {
+            V3<Dual> q[4] = {lift<Dual>(load3(xa)), lift<Dual>(load3(xa + 3)), lift<Dual>(load3(xb)), lift<Dual>(load3(xb + 3))};
+            if (lane < 12) {
+                V3<Dual>& t = q[lane / 3];
+                const int k = lane % 3;
+                (k == 0 ? t.x : (k == 1 ? t.y : t.z)).d = 1.0;
+            }
+            Dual r[3];
+            wheel_residuals<Dual>(a.C, blob, q[0], q[1], q[2], q[3], r);
+            const bool dead = lane < 12 && col_const(lane < 6 ? ma : mb, lane % 6);
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                sW[k * 16 + lane] = lane == 12 ? r[k].a : (dead ? 0.0 : r[k].d);
+                if (lane == 12) cost += r[k].a * r[k].a;
+            }
+        }
+    } else {
+        for (int k = lane; k < 48; k += 32) sW[k] = 0.0;
+    }
+    // ---- ground of frame i: lanes 16..21 dual directions, lane 22 value
+    if (ground_on) {
+        if (lane >= 16 && lane < 23) {
+            const int c = lane - 16;
+            V3<Dual> p = lift<Dual>(load3(xb)), th = lift<Dual>(load3(xb + 3));
+            if (c < 6) {
+                V3<Dual>& t = c < 3 ? p : th;
+                (c % 3 == 0 ? t.x : (c % 3 == 1 ? t.y : t.z)).d = 1.0;
+            }
+            Dual dp, dq;
+            ground_residuals<Dual>(a.C, p, th, &dp, &dq);
+            const bool dead = c < 6 && col_const(mb, c);
+            sG[c] = c == 6 ? dp.a : (dead ? 0.0 : dp.d);
+            sG[8 + c] = c == 6 ? dq.a : (dead ? 0.0 : dq.d);
+            if (c == 6) cost += a.ground_multiplicity * (dp.a * dp.a + dq.a * dq.a);
+        }
+    } else {
+        if (lane < 16) sG[lane] = 0.0;
+    }
+    // ---- prior of frame i: r = J (x - X0)
+    const double* PJ = a.prior_J + (size_t)w * kBlk;
+    if (prior_on) {
+        if (lane < 15) {
+            const double* X0 = a.prior_X0 + (size_t)w * 15;
+            double s = 0.0;
+            for (int k = 0; k < 15; ++k) s += PJ[lane * 15 + k] * (xb[k] - X0[k]);
+            sP[lane] = s;
+            cost += s * s;
+        }
+    }
+    __syncwarp();
+    // ---- row `lane` of the 30x30 J^T J of this item + its gradient entry
+    double gsum = 0.0;
+    double hrow[30];
+    if (lane < 30) {
+        double mine[15];
+#pragma unroll
+        for (int r = 0; r < 15; ++r) mine[r] = sJ[r * 32 + lane];
+#pragma unroll
+        for (int r = 0; r < 15; ++r) gsum += mine[r] * sJ[r * 32 + 30];
+#pragma unroll
+        for (int c = 0; c < 30; ++c) {
+            double s = 0.0;
+#pragma unroll
+            for (int r = 0; r < 15; ++r) s += mine[r] * sJ[r * 32 + c];
+            hrow[c] = s;
+        }
+        const int fl = lane % 15;
+        if (fl < 6) {
+            const int wc = (lane < 15 ? 0 : 6) + fl;
+            const double w0 = sW[wc], w1 = sW[16 + wc], w2 = sW[32 + wc];
+            gsum += w0 * sW[12] + w1 * sW[16 + 12] + w2 * sW[32 + 12];
+#pragma unroll
+            for (int c = 0; c < 12; ++c) {
+                const int hc = (c < 6 ? 0 : 15) + (c % 6);
+                hrow[hc] += w0 * sW[c] + w1 * sW[16 + c] + w2 * sW[32 + c];
+            }
+            if (lane >= 15) {
+                const double m = (double)a.ground_multiplicity;
+                const double jp = sG[fl], jq = sG[8 + fl];
+                gsum += m * (jp * sG[6] + jq * sG[8 + 6]);
+#pragma unroll
+                for (int c = 0; c < 6; ++c) hrow[15 + c] += m * (jp * sG[c] + jq * sG[8 + c]);
+            }
+        }
+        if (prior_on && lane >= 15 && !col_const(mb, fl)) {
+            double gs = 0.0;
+            for (int r = 0; r < 15; ++r) gs += PJ[r * 15 + fl] * sP[r];
+            gsum += gs;
+#pragma unroll
+            for (int c = 0; c < 15; ++c) {
+                double s = 0.0;
+                for (int r = 0; r < 15; ++r) s += PJ[r * 15 + fl] * PJ[r * 15 + c];
+                hrow[15 + c] += col_const(mb, c) ? 0.0 : s;
+            }
+        }
+    }
+    cost = warp_sum(cost);
+    __syncwarp();
+    if (lane < 30) {
+#pragma unroll
+        for (int c = 0; c < 30; ++c) sH[lane * 30 + c] = hrow[c];
+    }
+    __syncwarp();
+    // ---- coalesced write of the record
+    for (int e = lane; e < 675; e += 32) {
+        const int blk = e / 225, r = (e % 225) / 15, c = e % 15;
+        out[e] = sH[(blk == 2 ? 15 + r : r) * 30 + (blk == 0 ? c : 15 + c)];
+    }
+    if (lane < 30) out[675 + lane] = gsum;
+    if (lane == 31) out[kItemCost] = cost;
+}
+
+// =====================================================================================================
+// warp-cooperative 15x15 kernels on shared memory (lane r owns row r; lanes >= 15 idle)
+
+// In-place inverse of an SPD block by Gauss-Jordan elimination without pivoting, rows in registers.
+// Returns false (uniformly) when a pivot is not positive (the block is not positive definite) or not finite.
+__device__ __forceinline__ bool spd_inverse15(double* A, double* piv /* 16 doubles scratch */, int lane) {
+    double row[15];
+    const int r = lane < 15 ? lane : 0;
+#pragma unroll
+    for (int k = 0; k < 15; ++k) row[k] = A[r * 15 + k];
+    bool ok = true;
+#pragma unroll
     for (int k = 0; k < 15; ++k) {
-        const double d = A[k * 15 + k];
-        if (!(d > 0.0) || !isfinite(d)) return false;
-        const double l = sqrt(d), inv = 1.0 / l;
+        if (lane == k) {
+            const double p = row[k];
+            const double pinv = 1.0 / p;
+#pragma unroll
+            for (int j = 0; j < 15; ++j) row[j] = (j == k) ? pinv : row[j] * pinv;
+#pragma unroll
+            for (int j = 0; j < 15; ++j) piv[j] = row[j];
+            piv[15] = p;
+        }
         __syncwarp();
-        if (lane == k) A[k * 15 + k] = l;
-        else if (lane > k && lane < 15) A[lane * 15 + k] *= inv;
-        __syncwarp();
-        if (lane > k && lane < 15) {
-            const double lr = A[lane * 15 + k];
-            for (int c = k + 1; c <= lane; ++c) A[lane * 15 + c] -= lr * A[c * 15 + k];
+        const double p = piv[15];
+        if (!(p > 0.0) || !isfinite(p)) ok = false;
+        if (lane != k && lane < 15) {
+            const double f = row[k];
+#pragma unroll
+            for (int j = 0; j < 15; ++j) row[j] = (j == k) ? -f * piv[k] : row[j] - f * piv[j];
         }
         __syncwarp();
     }
-    return true;
-}
-// X <- X L^-T : row r of X solved against lower-triangular L (both in shared memory)
-__device__ __forceinline__ void trsm_rlt15(double* X, const double* L, int lane) {
     if (lane < 15) {
-        double row[15];
 #pragma unroll
-        for (int k = 0; k < 15; ++k) row[k] = X[lane * 15 + k];
+        for (int k = 0; k < 15; ++k) A[lane * 15 + k] = row[k];
+    }
+    __syncwarp();
+    return ok;
+}
+// C = A B   (row r of A in registers of lane r)
+__device__ __forceinline__ void gemm_ab15(double* Cm, const double* A, const double* B, int lane) {
+    if (lane < 15) {
+        double a[15];
 #pragma unroll
-        for (int k = 0; k < 15; ++k) {
-            double s = row[k];
+        for (int k = 0; k < 15; ++k) a[k] = A[lane * 15 + k];
 #pragma unroll
-            for (int m = 0; m < k; ++m) s -= row[m] * L[k * 15 + m];
-            row[k] = s / L[k * 15 + k];
+        for (int c = 0; c < 15; ++c) {
+            double s = 0.0;
+#pragma unroll
+            for (int k = 0; k < 15; ++k) s += a[k] * B[k * 15 + c];
+            Cm[lane * 15 + c] = s;
         }
-#pragma unroll
-        for (int k = 0; k < 15; ++k) X[lane * 15 + k] = row[k];
     }
     __syncwarp();
 }
-// C -= A B^T   (all 15x15, row r of C by lane r)
+// C -= A B^T
 __device__ __forceinline__ void gemm_sub_abt15(double* Cm, const double* A, const double* B, int lane) {
     if (lane < 15) {
         double a[15];
 #pragma unroll
         for (int k = 0; k < 15; ++k) a[k] = A[lane * 15 + k];
+#pragma unroll
         for (int c = 0; c < 15; ++c) {
             double s = 0.0;
 #pragma unroll
@@ -138,36 +344,14 @@ __device__ __forceinline__ void gemm_sub_abt15(double* Cm, const double* A, cons
     }
     __syncwarp();
 }
-// y = L^-1 b (forward), in place on a 15-vector in shared memory; executed redundantly by lane 0
-__device__ __forceinline__ void fwd15(const double* L, double* b, int lane) {
-    if (lane == 0) {
-        for (int k = 0; k < 15; ++k) {
-            double s = b[k];
-            for (int m = 0; m < k; ++m) s -= L[k * 15 + m] * b[m];
-            b[k] = s / L[k * 15 + k];
-        }
-    }
-    __syncwarp();
-}
-// y = L^-T b (backward)
-__device__ __forceinline__ void bwd15(const double* L, double* b, int lane) {
-    if (lane == 0) {
-        for (int k = 14; k >= 0; --k) {
-            double s = b[k];
-            for (int m = k + 1; m < 15; ++m) s -= L[m * 15 + k] * b[m];
-            b[k] = s / L[k * 15 + k];
-        }
-    }
-    __syncwarp();
-}
-// out[r] -= sum_k M[r][k] v[k]      (TRANS: M[k][r])
-template <bool TRANS>
-__device__ __forceinline__ void gemv_sub15(double* out, const double* M, const double* v, int lane) {
+// out[r] (-)= sum_k M[r][k] v[k]   (TRANS: M[k][r])
+template <bool TRANS, bool SUB>
+__device__ __forceinline__ void gemv15(double* out, const double* M, const double* v, int lane) {
     if (lane < 15) {
         double s = 0.0;
 #pragma unroll
         for (int k = 0; k < 15; ++k) s += (TRANS ? M[k * 15 + lane] : M[lane * 15 + k]) * v[k];
-        out[lane] -= s;
+        if (SUB) out[lane] -= s; else out[lane] = s;
     }
     __syncwarp();
 }
@@ -175,53 +359,44 @@ __device__ __forceinline__ void copy_blk(double* dst, const double* src, int lan
     for (int i = lane; i < kBlk; i += 32) dst[i] = src[i];
 }
 
-// per-warp shared memory carve-up (doubles)
-struct WarpSmem {
-    double* cb;      // [n][pad]   laser blocks of the candidate / accepted point
-    double* g;       // [n][15]    gradient J^T r
-    double* b;       // [n][15]    rhs / solution
-    double* hdiag;   // [n][15]    diag(J^T J)
-    double* sc;      // [n][15]    Jacobi scaling
-    double* own;     // [n][21]    6x6 pose block (upper) from ground (+ laser added at assembly)
-    double* blk;     // 6 x 225 work blocks; aliased by the pair linearisation scratch
-    __host__ __device__ static size_t doubles(int n, int pad) { return (size_t)n * (pad + 15 * 4 + 21) + 7 * kBlk + 16; }
-};
-
-__device__ __forceinline__ int pose_index(int k) { return k < 2 ? k : k + 1; }  // 5-vector (px py th0 th1 th2) -> 6-dim pose
+// per-warp shared memory of window_kernel (doubles): 4 blocks (+3 for the arrow topology) + pivot row + rhs [n][15]
+__host__ __device__ inline size_t window_smem_doubles(int n, bool arrow) { return (arrow ? 7 : 4) * kBlk + 16 + (size_t)n * 15 + 16; }
 
 // ---------------------------------------------------------------------------------------------------
 template <bool ARROW>
 __device__ void window_step(const WindowArgs& a, int w, int lane, double* ws) {
     constexpr int NPAD = ARROW ? kPadFree : kPadTrack;
     constexpr int ICOST = ARROW ? 44 : 20;
+    constexpr int IGJ = ARROW ? 36 : 15;
     const int n = a.n_frames;
     LMState st = a.state[w];
     if (st.status != 0) return;
     const LMOptions& opt = a.opt;
+    const int mode = a.mode;
 
-    WarpSmem S;
-    S.cb = ws;
-    S.g = S.cb + (size_t)n * NPAD;
-    S.b = S.g + n * 15;
-    S.hdiag = S.b + n * 15;
-    S.sc = S.hdiag + n * 15;
-    S.own = S.sc + n * 15;
-    S.blk = S.own + n * 21;
-    if ((reinterpret_cast<uintptr_t>(S.blk) & 15) != 0) S.blk += 1;
+    double* Dm = ws;                  // pivot block / its inverse
+    double* Cy = ws + kBlk;           // next diagonal block being assembled
+    double* Um = ws + 2 * kBlk;       // coupling H(i-1, i)
+    double* Tm = ws + 3 * kBlk;       // T = U Dinv
+    double* Wm = ws + 4 * kBlk;       // arrow block H(0, i)          (arrow topology only)
+    double* Tp = ws + 5 * kBlk;       // T' = W Dinv
+    double* D0 = ws + 6 * kBlk;       // accumulated updates of D_0
+    double* piv = ws + (ARROW ? 7 : 4) * kBlk;  // 16
+    double* sb = piv + 16;            // rhs / solution [n][15]
 
     double* x = a.x + (size_t)w * n * 15;
     double* xc = a.xc + (size_t)w * n * 15;
     const uint8_t* cm = a.const_mask + (size_t)w * n;
     const uint8_t* fa = a.frame_active + (size_t)w * n;
-    const int mode = a.mode;
-    auto is_const = [&](int f, int c) -> bool {  // c: column 0..14 of frame f
-        if (mode == 1) return false;
-        const int blk = c < 3 ? 0 : (c < 6 ? 1 : (c < 9 ? 2 : 3));
-        return (cm[f] >> blk) & 1;
-    };
+    const size_t F = (size_t)a.n_windows * n;
+    auto is_const = [&](int f, int c) -> bool { return mode == 1 ? false : col_const(cm[f], c); };
     const double lsq = a.C.laser_sqrt_info * a.C.laser_sqrt_info;
+    const int cand = 1 - st.cur;
+    double* lb_c = a.laser_blocks + ((size_t)cand * F + (size_t)w * n) * NPAD;
+    const double* it_c = a.items + ((size_t)cand * F + (size_t)w * n) * kItem;
 
-    // ---- (1) candidate laser blocks: sum the tiles in a fixed order
+    // ---- (1) candidate laser blocks: sum the tiles in a fixed order; candidate cost
+    double csum = 0.0;
     for (int idx = lane; idx < n * NPAD; idx += 32) {
         const int f = idx / NPAD, k = idx - f * NPAD;
         double s = 0.0;
@@ -229,64 +404,19 @@ __device__ void window_step(const WindowArgs& a, int w, int lane, double* ws) {
             const double* p = a.partial + ((size_t)(w * n + f) * a.tiles) * NPAD + k;
             for (int t = 0; t < a.tiles; ++t) s += p[(size_t)t * NPAD];
         }
-        S.cb[idx] = s;
+        lb_c[idx] = s;
+        if (k == ICOST) csum += lsq * s;
     }
+    for (int f = lane; f < n; f += 32) csum += it_c[(size_t)f * kItem + kItemCost];
+    double cand_cost = 0.5 * warp_sum(csum);
     __syncwarp();
 
-    // ---- small-factor cost at a point (value only): lanes over pairs / frames
-    auto small_cost = [&](const double* X) -> double {
-        double c = 0.0;
-        for (int i = 1 + lane; i < n; i += 32) {
-            const uint8_t ma = mode == 1 ? 0 : cm[i - 1], mb = mode == 1 ? 0 : cm[i];
-            if (a.has_imu && ((ma & 15) != 15 || (mb & 15) != 15)) {
-                const double* blob = a.imu + ((size_t)w * (n - 1) + (i - 1)) * 466;
-                double r[15];
-                imu_raw_residual(a.C, blob, X + 15 * (i - 1), X + 15 * i, r);
-                const double* Sq = blob + 240;
-                for (int row = 0; row < 15; ++row) {
-                    double s = 0.0;
-                    for (int k = row; k < 15; ++k) s += Sq[row * 15 + k] * r[k];  // sqrt_inverse_P = L^T is upper triangular
-                    c += s * s;
-                }
-            }
-            if (a.has_wheel && ((ma & 3) != 3 || (mb & 3) != 3)) {
-                const double* blob = a.wheel + ((size_t)w * (n - 1) + (i - 1)) * 15;
-                double r[3];
-                wheel_residuals<double>(a.C, blob, load3(X + 15 * (i - 1)), load3(X + 15 * (i - 1) + 3), load3(X + 15 * i),
-                                        load3(X + 15 * i + 3), r);
-                c += r[0] * r[0] + r[1] * r[1] + r[2] * r[2];
-            }
-        }
-        if (a.ground_multiplicity > 0)
-            for (int f = lane; f < n; f += 32) {
-                if (mode != 1 && (cm[f] & 3) == 3) continue;
-                double rp, rq;
-                ground_residuals<double>(a.C, load3(X + 15 * f), load3(X + 15 * f + 3), &rp, &rq);
-                c += a.ground_multiplicity * (rp * rp + rq * rq);
-            }
-        if (a.prior_frame >= 0 && lane < 15 && (mode == 1 || (cm[a.prior_frame] & 15) != 15)) {
-            const double* J = a.prior_J + (size_t)w * kBlk;
-            const double* X0 = a.prior_X0 + (size_t)w * 15;
-            const double* xp = X + 15 * a.prior_frame;
-            double s = 0.0;
-            for (int k = 0; k < 15; ++k) s += J[lane * 15 + k] * (xp[k] - X0[k]);
-            c += s * s;
-        }
-        return warp_sum(c);
-    };
-    auto laser_cost = [&]() -> double {
-        double c = 0.0;
-        for (int f = lane; f < n; f += 32) c += S.cb[f * NPAD + ICOST];
-        return lsq * warp_sum(c);
-    };
-
-    // ---- (2) decide on the candidate
+    // ---- decide on the candidate
     bool accepted = false;
     if (!st.started) {
-        // iteration 0: the "candidate" is the initial point
-        st.started = 1;
-        st.cost = 0.5 * (laser_cost() + small_cost(xc));
-        st.initial_cost = st.cost;
+        st.started = 1;   // iteration 0: the "candidate" is the initial point
+        st.cost = cand_cost;
+        st.initial_cost = cand_cost;
         accepted = true;
         double s = 0.0;
         for (int i = lane; i < n * 15; i += 32) {
@@ -297,7 +427,6 @@ __device__ void window_step(const WindowArgs& a, int w, int lane, double* ws) {
         st.x_norm = sqrt(warp_sum(s));
         st.last_success = 1;
     } else {
-        double cand_cost = 0.5 * (laser_cost() + small_cost(xc));
         if (!isfinite(cand_cost)) cand_cost = 1.7976931348623157e308;
         double s = 0.0;
         for (int i = lane; i < n * 15; i += 32)
@@ -341,303 +470,126 @@ __device__ void window_step(const WindowArgs& a, int w, int lane, double* ws) {
             return;
         }
     }
-    __syncwarp();
-    double* lbw = a.laser_blocks + (size_t)w * n * NPAD;
-    if (accepted) {
-        for (int idx = lane; idx < n * NPAD; idx += 32) lbw[idx] = S.cb[idx];
-    } else {
-        for (int idx = lane; idx < n * NPAD; idx += 32) S.cb[idx] = lbw[idx];
-    }
+    if (accepted) st.cur = cand;
     __syncwarp();
     if (mode == 0 && st.iteration >= opt.max_iters) {
         st.status = 1; st.termination = 0;
         if (lane == 0) { a.state[w] = st; a.win_status[w] = 1; }
         return;
     }
+    // the linearisation of the accepted point
+    const double* lb = a.laser_blocks + ((size_t)st.cur * F + (size_t)w * n) * NPAD;
+    const double* itm = a.items + ((size_t)st.cur * F + (size_t)w * n) * kItem;
 
-    // ---- (3) linearise the small factors at x
-    for (int i = lane; i < n * 15; i += 32) { S.g[i] = 0.0; S.hdiag[i] = 0.0; }
-    for (int i = lane; i < n * 21; i += 32) S.own[i] = 0.0;
-    __syncwarp();
-    double* pairw = a.pair + (size_t)w * (n - 1) * 3 * kBlk;
-    {
-        // scratch aliases the work blocks: blob 466 -> 480 | Jw [15][32] | col-major H rows handled in registers
-        double* sblob = S.blk;             // 480
-        double* sJ = S.blk + 480;          // 15 x 32 : whitened Jacobian, column 30 = whitened residual
-        double* sW = sJ + 480;             // wheel: 3 x 16 (cols 0..11 jac, col 12 residual)
-        for (int i = 1; i < n; ++i) {
-            const uint8_t ma = mode == 1 ? 0 : cm[i - 1], mb = mode == 1 ? 0 : cm[i];
-            const double* xa = x + 15 * (i - 1);
-            const double* xb = x + 15 * i;
-            const bool imu_on = a.has_imu && ((ma & 15) != 15 || (mb & 15) != 15);
-            const bool wheel_on = a.has_wheel && ((ma & 3) != 3 || (mb & 3) != 3);
-            double col[15];
-            if (imu_on) {
-                const double* blob = a.imu + ((size_t)w * (n - 1) + (i - 1)) * 466;
-                for (int k = lane; k < 466; k += 32) sblob[k] = blob[k];
-                __syncwarp();
-                if (lane < 30) imu_jacobian_column(a.C, sblob, xa, xb, lane, col);
-                else if (lane == 30) imu_raw_residual(a.C, sblob, xa, xb, col);
-                if (lane < 31) {
-                    // whiten with the upper-triangular sqrt_inverse_P; constant parameter blocks get zero columns
-                    const bool dead = lane < 30 && is_const(lane < 15 ? i - 1 : i, lane % 15);
-                    const double* Sq = sblob + 240;
-#pragma unroll
-                    for (int r = 0; r < 15; ++r) {
-                        double s = 0.0;
-#pragma unroll
-                        for (int k = r; k < 15; ++k) s += Sq[r * 15 + k] * col[k];
-                        sJ[r * 32 + lane] = dead ? 0.0 : s;
-                    }
-                } else {
-#pragma unroll
-                    for (int r = 0; r < 15; ++r) sJ[r * 32 + 31] = 0.0;
-                }
-            } else {
-                for (int k = lane; k < 480; k += 32) sJ[k] = 0.0;
-            }
-            if (wheel_on) {
-                const double* blob = a.wheel + ((size_t)w * (n - 1) + (i - 1)) * 15;
-                if (lane < 13) {
-                    V3<Dual> q[4] = {lift<Dual>(load3(xa)), lift<Dual>(load3(xa + 3)), lift<Dual>(load3(xb)), lift<Dual>(load3(xb + 3))};
-                    if (lane < 12) {
-                        V3<Dual>& t = q[lane / 3];
-                        const int k = lane % 3;
-                        (k == 0 ? t.x : (k == 1 ? t.y : t.z)).d = 1.0;
-                    }
-                    Dual r[3];
-                    wheel_residuals<Dual>(a.C, blob, q[0], q[1], q[2], q[3], r);
-                    const bool dead = lane < 12 && is_const(lane < 6 ? i - 1 : i, lane % 6);
-#pragma unroll
-                    for (int k = 0; k < 3; ++k) sW[k * 16 + lane] = lane == 12 ? r[k].a : (dead ? 0.0 : r[k].d);
-                }
-            } else {
-                for (int k = lane; k < 48; k += 32) sW[k] = 0.0;
-            }
-            __syncwarp();
-            // H_pair row `lane` (30 entries) + gradient entry, straight from shared memory
-            if (lane < 30) {
-                double hrow[30];
-                double mine[15];
-#pragma unroll
-                for (int r = 0; r < 15; ++r) mine[r] = sJ[r * 32 + lane];
-                double gsum = 0.0;
-#pragma unroll
-                for (int r = 0; r < 15; ++r) gsum += mine[r] * sJ[r * 32 + 30];
-#pragma unroll
-                for (int c = 0; c < 30; ++c) {
-                    double s = 0.0;
-#pragma unroll
-                    for (int r = 0; r < 15; ++r) s += mine[r] * sJ[r * 32 + c];
-                    hrow[c] = s;
-                }
-                // wheel: pose columns only.  lane -> wheel column: frame a (0..5) | frame b (15..20)
-                const int fl = lane % 15;
-                if (fl < 6) {
-                    const int wc = (lane < 15 ? 0 : 6) + fl;
-                    const double w0 = sW[wc], w1 = sW[16 + wc], w2 = sW[32 + wc];
-                    gsum += w0 * sW[12] + w1 * sW[16 + 12] + w2 * sW[32 + 12];
-#pragma unroll
-                    for (int c = 0; c < 12; ++c) {
-                        const int hc = (c < 6 ? 0 : 15) + (c % 6);
-                        hrow[hc] += w0 * sW[c] + w1 * sW[16 + c] + w2 * sW[32 + c];
-                    }
-                }
-                const int fr = lane < 15 ? i - 1 : i;
-                S.g[fr * 15 + fl] += gsum;
-                S.hdiag[fr * 15 + fl] += hrow[lane];
-                double* P = pairw + (size_t)(i - 1) * 3 * kBlk;
-                if (lane < 15) {
-#pragma unroll
-                    for (int c = 0; c < 15; ++c) { P[fl * 15 + c] = hrow[c]; P[kBlk + fl * 15 + c] = hrow[15 + c]; }
-                } else {
-#pragma unroll
-                    for (int c = 0; c < 15; ++c) P[2 * kBlk + fl * 15 + c] = hrow[15 + c];
+    // entry (r, c) of the laser 6x6 own-pose block of frame f, unscaled
+    auto laser_own = [&](int f, int r, int c) -> double {
+        if (r == 2 || c == 2 || r > 5 || c > 5 || !fa[f]) return 0.0;
+        if (is_const(f, r) || is_const(f, c)) return 0.0;
+        int ri = r < 2 ? r : r - 1, ci = c < 2 ? c : c - 1;
+        if (ri > ci) { const int t = ri; ri = ci; ci = t; }
+        // upper 5x5 in the order aa(3) | a x bj(6) | bj bj(6)
+        const int src = (ri < 2 && ci < 2) ? (ri + ci) : (ri < 2 ? 3 + ri * 3 + (ci - 2) : 9 + (ri == 2 ? ci - 2 : (ri == 3 ? ci : 5)));
+        return lsq * lb[f * NPAD + src];
+    };
+    auto has_cross = [&](int j) -> bool {
+        return ARROW && mode == 0 && j >= 1 && fa[j] && a.ref_frame && a.ref_frame[(size_t)w * n + j] == 0;
+    };
+    // reference-frame side (arrow): 6x6 block of frame 0 summed over all frames that hang under it
+    auto laser_ref_own = [&](int r, int c) -> double {
+        if (!ARROW || mode != 0) return 0.0;
+        if (r == 2 || c == 2 || r > 5 || c > 5) return 0.0;
+        if (is_const(0, r) || is_const(0, c)) return 0.0;
+        int ri = r < 2 ? r : r - 1, ci = c < 2 ? c : c - 1;
+        if (ri > ci) { const int t = ri; ri = ci; ci = t; }
+        double s = 0.0;
+        for (int j = 1; j < n; ++j) {
+            if (!has_cross(j)) continue;
+            const double* cb = lb + j * NPAD;
+            double v;
+            if (ri < 2 && ci < 2) v = cb[ri + ci];
+            else if (ri < 2) v = -cb[15 + ri * 3 + (ci - 2)];
+            else v = cb[21 + (ri == 2 ? ci - 2 : (ri == 3 ? ci : 5))];
+            s += v;
+        }
+        return lsq * s;
+    };
+    // laser cross block between frame j and its reference frame 0 as H(0, j) (rows 0, cols j), 6x6 pose part
+    auto cross_entry = [&](int j, int r, int c) -> double {
+        if (r == 2 || c == 2) return 0.0;
+        const double* cb = lb + j * NPAD;
+        const int ri = r < 2 ? r : r - 1, ci = c < 2 ? c : c - 1;
+        double v;
+        if (ri < 2 && ci < 2) v = -cb[ri + ci];                      // -(a a^T)
+        else if (ri < 2) v = -cb[3 + ri * 3 + (ci - 2)];             // rows p_0 (-a), cols theta_j (bj)
+        else if (ci < 2) v = cb[15 + ci * 3 + (ri - 2)];             // rows theta_0 (bi), cols p_j (a)
+        else v = cb[27 + (ci - 2) * 3 + (ri - 2)];                   // bj x bi stored [bj][bi]
+        return lsq * v;
+    };
+    // gradient entry c of frame f
+    auto grad = [&](int f, int c) -> double {
+        if (is_const(f, c)) return 0.0;
+        double g = itm[(size_t)f * kItem + kItemGb + c];
+        if (f + 1 < n) g += itm[(size_t)(f + 1) * kItem + kItemGa + c];
+        if (c < 6 && c != 2) {
+            const int k = c < 2 ? c : c - 1;
+            if (fa[f]) g += lsq * lb[f * NPAD + IGJ + k];
+            if (ARROW && mode == 0 && f == 0) {
+                for (int j = 1; j < n; ++j) {
+                    if (!has_cross(j)) continue;
+                    const double* cb = lb + j * NPAD;
+                    g += lsq * (k < 2 ? -cb[36 + k] : cb[41 + k - 2]);
                 }
             }
-            __syncwarp();
         }
-    }
-    // ground: lanes over frames, 6 dual directions each -> 6x6 upper block + gradient
-    if (a.ground_multiplicity > 0)
-        for (int f = lane; f < n; f += 32) {
-            if (mode != 1 && (cm[f] & 3) == 3) continue;
-            double rp, rq, jp[6], jq[6];
-            ground_residuals<double>(a.C, load3(x + 15 * f), load3(x + 15 * f + 3), &rp, &rq);
-#pragma unroll
-            for (int c = 0; c < 6; ++c) {
-                V3<Dual> p = lift<Dual>(load3(x + 15 * f)), th = lift<Dual>(load3(x + 15 * f + 3));
-                V3<Dual>& t = c < 3 ? p : th;
-                (c % 3 == 0 ? t.x : (c % 3 == 1 ? t.y : t.z)).d = 1.0;
-                Dual dp, dq;
-                ground_residuals<Dual>(a.C, p, th, &dp, &dq);
-                const bool dead = is_const(f, c);
-                jp[c] = dead ? 0.0 : dp.d;
-                jq[c] = dead ? 0.0 : dq.d;
-            }
-            const double m = (double)a.ground_multiplicity;
-            int k = 0;
-#pragma unroll
-            for (int r = 0; r < 6; ++r) {
-                S.g[f * 15 + r] += m * (jp[r] * rp + jq[r] * rq);
-#pragma unroll
-                for (int c = r; c < 6; ++c) S.own[f * 21 + k++] += m * (jp[r] * jp[c] + jq[r] * jq[c]);
-            }
-        }
-    __syncwarp();
-    // laser blocks -> gradient and diag; arrow parts are added at assembly time
-    for (int f = lane; f < n; f += 32) {
-        if (!fa[f]) continue;
-        const double* cbf = S.cb + f * NPAD;
-        const int gj = ARROW ? 36 : 15;
-        const bool own_free = !(is_const(f, 0) && is_const(f, 3));
-#pragma unroll
-        for (int k = 0; k < 5; ++k) {
-            const int pc = pose_index(k);
-            if (own_free && !is_const(f, pc)) S.g[f * 15 + pc] += lsq * cbf[gj + k];
-        }
-        int k2 = 0;
-#pragma unroll
-        for (int r = 0; r < 5; ++r)
-#pragma unroll
-            for (int c = r; c < 5; ++c) {
-                // 15 upper entries of the 5x5 block in the order aa(3) | a x bj(6) | bj bj(6)
-                const int src = (r < 2 && c < 2) ? (r + c) : (r < 2 ? 3 + r * 3 + (c - 2) : 9 + (r == 2 ? c - 2 : (r == 3 ? 2 + c - 2 : 5)));
-                const int pr = pose_index(r), pc = pose_index(c);
-                // position of (pr, pc) in the 21-entry upper triangle of the 6x6 block
-                const int dst = pr * 6 - pr * (pr - 1) / 2 + (pc - pr);
-                if (!is_const(f, pr) && !is_const(f, pc)) S.own[f * 21 + dst] += lsq * cbf[src];
-                ++k2;
-            }
-    }
-    __syncwarp();
-    if (ARROW && mode == 0) {
-        // reference-frame side of the laser blocks: gradient of frame rf and its 6x6 block (summed over all j)
-        for (int f = 0; f < n; ++f) {
-            if (!fa[f]) continue;
-            const int rf = a.ref_frame ? a.ref_frame[(size_t)w * n + f] : -1;
-            if (rf < 0) continue;
-            const double* cbf = S.cb + f * NPAD;
-            if (lane < 5) {
-                const int pc = pose_index(lane);
-                if (!is_const(rf, pc)) {
-                    const double gi = lane < 2 ? -cbf[36 + lane] : cbf[41 + lane - 2];
-                    S.g[rf * 15 + pc] += lsq * gi;
-                }
-            }
-            if (lane < 15) {
-                // upper 5x5 of H_ii: aa | -(a x bi) | bi bi
-                int r = 0, c = lane;
-                while (c >= 5 - r) { c -= 5 - r; ++r; }
-                c += r;
-                double v;
-                if (r < 2 && c < 2) v = cbf[r + c];
-                else if (r < 2) v = -cbf[15 + r * 3 + (c - 2)];
-                else v = cbf[21 + (r == 2 ? c - 2 : (r == 3 ? 2 + c - 2 : 5))];
-                const int pr = pose_index(r), pc = pose_index(c);
-                const int dst = pr * 6 - pr * (pr - 1) / 2 + (pc - pr);
-                if (!is_const(rf, pr) && !is_const(rf, pc)) S.own[rf * 21 + dst] += lsq * v;
-            }
-            __syncwarp();
-        }
-    }
-    // own-block diagonals -> hdiag
-    for (int f = lane; f < n; f += 32) {
-#pragma unroll
-        for (int r = 0; r < 6; ++r) S.hdiag[f * 15 + r] += S.own[f * 21 + r * 6 - r * (r - 1) / 2];
-    }
-    __syncwarp();
-    // prior: r = J (x - X0); H += J^T J; g += J^T r
-    const bool prior_on = a.prior_frame >= 0 && (mode == 1 || (cm[a.prior_frame] & 15) != 15);
-    double* sPrior = S.blk + 5 * kBlk;  // J^T J of the prior (kept through the solve)
-    if (prior_on) {
-        const double* J = a.prior_J + (size_t)w * kBlk;
-        const double* X0 = a.prior_X0 + (size_t)w * 15;
-        const double* xp = x + 15 * a.prior_frame;
-        double* tmp = S.blk;  // r
-        if (lane < 15) {
-            double s = 0.0;
-            for (int k = 0; k < 15; ++k) s += J[lane * 15 + k] * (xp[k] - X0[k]);
-            tmp[lane] = s;
-        }
-        __syncwarp();
-        if (lane < 15) {
-            const bool dead = is_const(a.prior_frame, lane);
-            double gs = 0.0;
-            for (int r = 0; r < 15; ++r) gs += J[r * 15 + lane] * tmp[r];
-            for (int c = 0; c < 15; ++c) {
-                double s = 0.0;
-                for (int r = 0; r < 15; ++r) s += J[r * 15 + lane] * J[r * 15 + c];
-                sPrior[lane * 15 + c] = (dead || is_const(a.prior_frame, c)) ? 0.0 : s;
-            }
-            if (!dead) {
-                S.g[a.prior_frame * 15 + lane] += gs;
-                S.hdiag[a.prior_frame * 15 + lane] += sPrior[lane * 15 + lane];
-            }
-        }
-        __syncwarp();
-    }
-
-    // assembled (unscaled) diagonal block of frame i into dst
+        return g;
+    };
+    // unscaled diagonal block of frame i into dst (shared memory)
     auto assemble_D = [&](int i, double* dst) {
         for (int e = lane; e < kBlk; e += 32) {
-            double v = 0.0;
-            if (i >= 1) v += pairw[(size_t)(i - 1) * 3 * kBlk + 2 * kBlk + e];
-            if (i + 1 < n) v += pairw[(size_t)i * 3 * kBlk + e];
             const int r = e / 15, c = e - r * 15;
-            if (r < 6 && c < 6) {
-                const int lo = r < c ? r : c, hi = r < c ? c : r;
-                v += S.own[i * 21 + lo * 6 - lo * (lo - 1) / 2 + (hi - lo)];
-            }
-            if (prior_on && i == a.prior_frame) v += sPrior[e];
+            double v = itm[(size_t)i * kItem + kItemHbb + e];
+            if (i + 1 < n) v += itm[(size_t)(i + 1) * kItem + kItemHaa + e];
+            v += laser_own(i, r, c);
+            if (i == 0) v += laser_ref_own(r, c);
             dst[e] = v;
         }
         __syncwarp();
     };
-    // laser cross block between frame j and its reference frame rf, as H(rf, j) (rows rf, cols j), 6x6 pose part
-    auto cross_entry = [&](int j, int r, int c) -> double {  // r: pose row of rf, c: pose col of j (0..5)
-        if (r == 2 || c == 2) return 0.0;
-        const double* cbf = S.cb + j * NPAD;
-        const int ri = r < 2 ? r : r - 1, ci = c < 2 ? c : c - 1;  // 5-vector indices
-        double v;
-        if (ri < 2 && ci < 2) v = -cbf[ri + ci];                      // -(a a^T)
-        else if (ri < 2) v = -cbf[3 + ri * 3 + (ci - 2)];             // rows p_i (-a), cols theta_j (bj)
-        else if (ci < 2) v = cbf[15 + ci * 3 + (ri - 2)];             // rows theta_i (bi), cols p_j (a)
-        else v = cbf[27 + (ci - 2) * 3 + (ri - 2)];                   // bj x bi stored [bj][bi]
-        return lsq * v;
+    auto diag_H = [&](int f, int c) -> double {
+        double v = itm[(size_t)f * kItem + kItemHbb + c * 16];
+        if (f + 1 < n) v += itm[(size_t)(f + 1) * kItem + kItemHaa + c * 16];
+        v += laser_own(f, c, c);
+        if (f == 0) v += laser_ref_own(c, c);
+        return v;
     };
 
-    // dense outputs for lvio2d_linearize
+    // ---- dense outputs for lvio2d_linearize
     if (a.dense_H) {
         const int dim = 15 * n;
         double* H = a.dense_H + (size_t)w * dim * dim;
         for (size_t e = lane; e < (size_t)dim * dim; e += 32) H[e] = 0.0;
         __syncwarp();
-        double* Dm = S.blk;
         for (int i = 0; i < n; ++i) {
             assemble_D(i, Dm);
             for (int e = lane; e < kBlk; e += 32) H[(size_t)(15 * i + e / 15) * dim + 15 * i + e % 15] = Dm[e];
             if (i >= 1)
                 for (int e = lane; e < kBlk; e += 32) {
-                    const double v = pairw[(size_t)(i - 1) * 3 * kBlk + kBlk + e];  // H(i-1, i)
+                    const double v = itm[(size_t)i * kItem + kItemHab + e];  // H(i-1, i)
                     H[(size_t)(15 * (i - 1) + e / 15) * dim + 15 * i + e % 15] += v;
                     H[(size_t)(15 * i + e % 15) * dim + 15 * (i - 1) + e / 15] += v;
                 }
             __syncwarp();
-            if (ARROW && mode == 0 && fa[i]) {
-                const int rf = a.ref_frame ? a.ref_frame[(size_t)w * n + i] : -1;
-                if (rf >= 0)
-                    for (int e = lane; e < 36; e += 32) {
-                        const int r = e / 6, c = e % 6;
-                        if (is_const(rf, r) || is_const(i, c)) continue;
-                        const double v = cross_entry(i, r, c);
-                        H[(size_t)(15 * rf + r) * dim + 15 * i + c] += v;
-                        H[(size_t)(15 * i + c) * dim + 15 * rf + r] += v;
-                    }
-            }
+            if (has_cross(i))
+                for (int e = lane; e < 36; e += 32) {
+                    const int r = e / 6, c = e % 6;
+                    if (is_const(0, r) || is_const(i, c)) continue;
+                    const double v = cross_entry(i, r, c);
+                    H[(size_t)r * dim + 15 * i + c] += v;
+                    H[(size_t)(15 * i + c) * dim + r] += v;
+                }
             __syncwarp();
         }
-        for (int i = lane; i < dim; i += 32) a.dense_g[(size_t)w * dim + i] = S.g[i];
+        for (int i = lane; i < dim; i += 32) a.dense_g[(size_t)w * dim + i] = grad(i / 15, i % 15);
         if (lane == 0) a.dense_cost[w] = st.cost;
         st.status = 1;
         if (lane == 0) { a.state[w] = st; a.win_status[w] = 1; }
@@ -646,94 +598,78 @@ __device__ void window_step(const WindowArgs& a, int w, int lane, double* ws) {
 
     // ---- marginalisation program: forward elimination of frames 0..n-2 (solver.cpp:4-40)
     if (mode == 1) {
-        double* Dm = S.blk;            // current diagonal block
-        double* Um = S.blk + kBlk;     // coupling H(i, i+1)
-        double* Nx = S.blk + 2 * kBlk; // next diagonal block
-        double* rhs = S.b;             // g = -J^T r
-        for (int i = lane; i < n * 15; i += 32) rhs[i] = -S.g[i];
+        for (int i = lane; i < n * 15; i += 32) sb[i] = -grad(i / 15, i % 15);   // g = -J^T R
         __syncwarp();
         assemble_D(0, Dm);
         for (int i = 0; i + 1 < n; ++i) {
-            assemble_D(i + 1, Nx);
-            copy_blk(Um, pairw + (size_t)i * 3 * kBlk + kBlk, lane);  // H(i, i+1): rows i, cols i+1
+            assemble_D(i + 1, Cy);
+            // Um = H(i+1, i) = H(i, i+1)^T
+            for (int e = lane; e < kBlk; e += 32) Um[e] = itm[(size_t)(i + 1) * kItem + kItemHab + (e % 15) * 15 + e / 15];
             __syncwarp();
-            // E = U^T L^-T (rows i+1) ; Nx -= E E^T ; rhs_{i+1} -= E (L^-1 rhs_i)
-            if (!chol15(Dm, lane)) { st.termination = 5; break; }
-            double* Et = S.blk + 3 * kBlk;
-            for (int e = lane; e < kBlk; e += 32) Et[e] = Um[(e % 15) * 15 + e / 15];
-            __syncwarp();
-            trsm_rlt15(Et, Dm, lane);
-            gemm_sub_abt15(Nx, Et, Et, lane);
-            fwd15(Dm, rhs + 15 * i, lane);
-            gemv_sub15<false>(rhs + 15 * (i + 1), Et, rhs + 15 * i, lane);
-            copy_blk(Dm, Nx, lane);
+            if (!spd_inverse15(Dm, piv, lane)) st.termination = 5;
+            gemm_ab15(Tm, Um, Dm, lane);                 // T = H(i+1,i) Hii^-1
+            gemm_sub_abt15(Cy, Tm, Um, lane);            // H(i+1,i+1) -= T H(i+1,i)^T
+            gemv15<false, true>(sb + 15 * (i + 1), Tm, sb + 15 * i, lane);
+            copy_blk(Dm, Cy, lane);
             __syncwarp();
         }
         for (int e = lane; e < kBlk; e += 32) a.marg_H[(size_t)w * kBlk + e] = Dm[e];
-        if (lane < 15) a.marg_g[(size_t)w * 15 + lane] = rhs[15 * (n - 1) + lane];
+        if (lane < 15) a.marg_g[(size_t)w * 15 + lane] = sb[15 * (n - 1) + lane];
         st.status = 1;
         if (lane == 0) { a.state[w] = st; a.win_status[w] = 1; }
         return;
     }
 
-    // ---- gradient tolerance: |x - Plus(x, -g)|_inf (only after a successful step)
-    if (st.last_success) {
+    // ---- gradient tolerance: |x - Plus(x, -g)|_inf (only after a successful step); gradient kept for the step
+    double* gvec = a.vec + (size_t)w * 2 * n * 15;
+    {
         double mx = 0.0;
-        for (int f = lane; f < n; f += 32) {
+        for (int i = lane; i < n * 15; i += 32) gvec[i] = grad(i / 15, i % 15);
+        __syncwarp();
+        if (st.last_success) {
+            for (int f = lane; f < n; f += 32) {
 #pragma unroll
-            for (int c = 0; c < 15; ++c) {
-                if (is_const(f, c) || (c >= 3 && c < 6)) continue;
-                mx = fmax(mx, fabs(S.g[f * 15 + c]));
-            }
-            if (!is_const(f, 3)) {
-                double neg[3] = {-S.g[f * 15 + 3], -S.g[f * 15 + 4], -S.g[f * 15 + 5]}, out[3];
-                so3_plus(x + 15 * f + 3, neg, out);
+                for (int c = 0; c < 15; ++c) {
+                    if (is_const(f, c) || (c >= 3 && c < 6)) continue;
+                    mx = fmax(mx, fabs(gvec[f * 15 + c]));
+                }
+                if (!is_const(f, 3)) {
+                    double neg[3] = {-gvec[f * 15 + 3], -gvec[f * 15 + 4], -gvec[f * 15 + 5]}, outv[3];
+                    so3_plus(x + 15 * f + 3, neg, outv);
 #pragma unroll
-                for (int c = 0; c < 3; ++c) mx = fmax(mx, fabs(x[15 * f + 3 + c] - out[c]));
+                    for (int c = 0; c < 3; ++c) mx = fmax(mx, fabs(x[15 * f + 3 + c] - outv[c]));
+                }
             }
-        }
-        mx = warp_max(mx);
-        if (mx <= opt.gradient_tolerance) {
-            st.status = 1; st.termination = 3;
-            if (lane == 0) { a.state[w] = st; a.win_status[w] = 1; }
-            return;
+            mx = warp_max(mx);
+            if (mx <= opt.gradient_tolerance) {
+                st.status = 1; st.termination = 3;
+                if (lane == 0) { a.state[w] = st; a.win_status[w] = 1; }
+                return;
+            }
         }
     }
 
     // ---- Jacobi scaling (fixed at iteration 0)
     double* scw = a.scale + (size_t)w * n * 15;
     if (st.iteration == 0) {
-        for (int i = lane; i < n * 15; i += 32) {
-            const double s = is_const(i / 15, i % 15) ? 1.0 : 1.0 / (1.0 + sqrt(S.hdiag[i]));
-            S.sc[i] = s;
-            scw[i] = s;
-        }
-    } else {
-        for (int i = lane; i < n * 15; i += 32) S.sc[i] = scw[i];
+        for (int i = lane; i < n * 15; i += 32)
+            scw[i] = is_const(i / 15, i % 15) ? 1.0 : 1.0 / (1.0 + sqrt(diag_H(i / 15, i % 15)));
+        __syncwarp();
     }
-    __syncwarp();
 
-    // ---- (4) trust-region step; invalid steps shrink the radius and retry without a new evaluation
+    // ---- (3) trust-region step; invalid steps shrink the radius and retry without a new evaluation
     double* facw = a.fac + (size_t)w * n * 3 * kBlk;
-    double* Dm = S.blk;               // diagonal block being factored
-    double* Cy = S.blk + kBlk;        // carry: updated diagonal block of frame i-1
-    double* Em = S.blk + 2 * kBlk;    // E_i
-    double* Fm = S.blk + 3 * kBlk;    // F_i (arrow)
-    double* Wc = S.blk + 4 * kBlk;    // carry: updated arrow block H(0, i-1)
-    // S.blk + 5*kBlk holds the prior block
     bool have_step = false;
-    double step_dot_g = 0.0, lm_quad = 0.0;
     for (;;) {
         if (st.radius < opt.min_radius) { st.status = 1; st.termination = 4; break; }
         ++st.iteration;
         bool ok = true;
-        // rhs = scaled gradient
-        for (int i = lane; i < n * 15; i += 32) S.b[i] = is_const(i / 15, i % 15) ? 0.0 : S.g[i] * S.sc[i];
+        for (int i = lane; i < n * 15; i += 32) sb[i] = is_const(i / 15, i % 15) ? 0.0 : gvec[i] * scw[i];
         __syncwarp();
         auto scale_damp = [&](int i, double* blkp) {  // A = S H S + diag(clamp(diag(S H S)) / radius); const entries -> identity
             for (int e = lane; e < kBlk; e += 32) {
                 const int r = e / 15, c = e - r * 15;
-                double v = blkp[e] * S.sc[i * 15 + r] * S.sc[i * 15 + c];
+                double v = blkp[e] * scw[i * 15 + r] * scw[i * 15 + c];
                 if (r == c) {
                     if (is_const(i, r)) v = 1.0;
                     else v += fmin(fmax(v, opt.min_lm_diagonal), opt.max_lm_diagonal) / st.radius;
@@ -742,108 +678,91 @@ __device__ void window_step(const WindowArgs& a, int w, int lane, double* ws) {
             }
             __syncwarp();
         };
-        double* D0acc = nullptr;
-        // reverse elimination n-1 .. 1
         assemble_D(n - 1, Dm);
         scale_damp(n - 1, Dm);
-        bool have_wc = false;
-        for (int i = n - 1; i >= 1 && ok; --i) {
-            // coupling U_i = H(i-1, i) scaled, plus the laser cross block when frame i's reference is frame i-1 == 0
+        bool have_wc = false, have_d0 = false;
+        for (int i = n - 1; i >= 1; --i) {
+            // coupling U = H(i-1, i), scaled (+ laser cross block / carried fill-in when i == 1: H(0,1) is also the arrow block)
+            const bool cross_i = has_cross(i);
             for (int e = lane; e < kBlk; e += 32) {
                 const int r = e / 15, c = e - r * 15;
-                Em[e] = pairw[(size_t)(i - 1) * 3 * kBlk + kBlk + e] * S.sc[(i - 1) * 15 + r] * S.sc[i * 15 + c];
+                double v = itm[(size_t)i * kItem + kItemHab + e] * scw[(i - 1) * 15 + r] * scw[i * 15 + c];
+                if (ARROW && i == 1) {
+                    if (have_wc) v += Wm[e];
+                    if (cross_i && r < 6 && c < 6 && !is_const(0, r) && !is_const(1, c)) v += cross_entry(1, r, c) * scw[r] * scw[15 + c];
+                }
+                Um[e] = v;
+            }
+            bool arrow_i = false;
+            if (ARROW && i >= 2) {
+                arrow_i = have_wc || cross_i;
+                if (arrow_i)
+                    for (int e = lane; e < kBlk; e += 32) {
+                        const int r = e / 15, c = e - r * 15;
+                        double v = have_wc ? Wm[e] : 0.0;
+                        if (cross_i && r < 6 && c < 6 && !is_const(0, r) && !is_const(i, c)) v += cross_entry(i, r, c) * scw[r] * scw[i * 15 + c];
+                        Wm[e] = v;
+                    }
             }
             __syncwarp();
-            const int rf = (ARROW && fa[i] && a.ref_frame) ? a.ref_frame[(size_t)w * n + i] : -1;
-            bool arrow_i = false;
-            if (ARROW) {
-                // arrow block H(0, i): laser cross term (if rf == 0) + fill-in carried from frame i+1
-                if (i >= 2) {
-                    for (int e = lane; e < kBlk; e += 32) {
-                        const int r = e / 15, c = e - r * 15;
-                        double v = have_wc ? Wc[e] : 0.0;
-                        if (rf == 0 && r < 6 && c < 6 && !is_const(0, r) && !is_const(i, c))
-                            v += cross_entry(i, r, c) * S.sc[r] * S.sc[i * 15 + c];
-                        Fm[e] = v;
-                    }
-                    arrow_i = have_wc || rf == 0;
-                } else {
-                    // i == 1: the arrow block IS the tridiagonal coupling H(0,1)
-                    for (int e = lane; e < kBlk; e += 32) {
-                        const int r = e / 15, c = e - r * 15;
-                        double v = have_wc ? Wc[e] : 0.0;
-                        if (rf == 0 && r < 6 && c < 6 && !is_const(0, r) && !is_const(1, c))
-                            v += cross_entry(1, r, c) * S.sc[r] * S.sc[15 + c];
-                        Em[e] += v;
-                    }
-                }
-                __syncwarp();
-            }
-            ok = chol15(Dm, lane);
-            if (!ok) break;
-            trsm_rlt15(Em, Dm, lane);
-            if (ARROW && arrow_i) trsm_rlt15(Fm, Dm, lane);
-            // store the factor blocks for the back substitution
+            if (!spd_inverse15(Dm, piv, lane)) { ok = false; break; }
+            gemm_ab15(Tm, Um, Dm, lane);                                   // T = U Dinv
+            if (ARROW && arrow_i) gemm_ab15(Tp, Wm, Dm, lane);             // T' = W Dinv
+            gemv15<false, false>(piv, Dm, sb + 15 * i, lane);              // c_i = Dinv b_i
+            if (lane < 15) sb[15 * i + lane] = piv[lane];
+            __syncwarp();
             for (int e = lane; e < kBlk; e += 32) {
-                facw[(size_t)i * 3 * kBlk + e] = Dm[e];
-                facw[(size_t)i * 3 * kBlk + kBlk + e] = Em[e];
-                if (ARROW) facw[(size_t)i * 3 * kBlk + 2 * kBlk + e] = arrow_i ? Fm[e] : 0.0;
+                facw[(size_t)i * 3 * kBlk + e] = Tm[e];
+                if (ARROW) facw[(size_t)i * 3 * kBlk + kBlk + e] = arrow_i ? Tp[e] : 0.0;
             }
-            // rhs: z_i = L_i^-1 b_i ; b_{i-1} -= E_i z_i ; b_0 -= F_i z_i
-            fwd15(Dm, S.b + 15 * i, lane);
-            gemv_sub15<false>(S.b + 15 * (i - 1), Em, S.b + 15 * i, lane);
-            if (ARROW && arrow_i) gemv_sub15<false>(S.b, Fm, S.b + 15 * i, lane);
-            // next diagonal block (frame i-1) minus E E^T
+            gemv15<false, true>(sb + 15 * (i - 1), Um, sb + 15 * i, lane);  // b_{i-1} -= U c_i
+            if (ARROW && arrow_i) gemv15<false, true>(sb, Wm, sb + 15 * i, lane);
             assemble_D(i - 1, Cy);
             scale_damp(i - 1, Cy);
-            gemm_sub_abt15(Cy, Em, Em, lane);
+            gemm_sub_abt15(Cy, Tm, Um, lane);                               // D_{i-1} -= T U^T
             if (ARROW && arrow_i) {
-                // D_0 -= F F^T (kept in the dedicated accumulator until frame 0 is reached) ; H(0, i-1) -= F E^T
-                if (!D0acc) {
-                    D0acc = S.blk + 5 * kBlk + kBlk;  // after the prior block
-                    for (int e = lane; e < kBlk; e += 32) D0acc[e] = 0.0;
-                    __syncwarp();
-                }
-                gemm_sub_abt15(D0acc, Fm, Fm, lane);
-                for (int e = lane; e < kBlk; e += 32) Wc[e] = 0.0;
+                if (!have_d0) { for (int e = lane; e < kBlk; e += 32) D0[e] = 0.0; __syncwarp(); have_d0 = true; }
+                gemm_sub_abt15(D0, Tp, Wm, lane);                           // D_0 -= T' W^T
+                // fill-in for frame i-1: H(0, i-1) = -T' U^T   (Wm is free again after this)
+                for (int e = lane; e < kBlk; e += 32) Dm[e] = 0.0;
                 __syncwarp();
-                gemm_sub_abt15(Wc, Fm, Em, lane);
+                gemm_sub_abt15(Dm, Tp, Um, lane);
+                copy_blk(Wm, Dm, lane);
+                __syncwarp();
                 have_wc = true;
             } else if (ARROW) {
                 have_wc = false;
             }
-            if (ARROW && i - 1 == 0 && D0acc) {
-                for (int e = lane; e < kBlk; e += 32) Cy[e] += D0acc[e];
+            if (ARROW && i - 1 == 0 && have_d0) {
+                for (int e = lane; e < kBlk; e += 32) Cy[e] += D0[e];
                 __syncwarp();
             }
             copy_blk(Dm, Cy, lane);
             __syncwarp();
         }
-        if (ok) ok = chol15(Dm, lane);
+        if (ok) ok = spd_inverse15(Dm, piv, lane);
         if (ok) {
-            for (int e = lane; e < kBlk; e += 32) facw[e] = Dm[e];
-            fwd15(Dm, S.b, lane);
-            bwd15(Dm, S.b, lane);  // y_0
+            gemv15<false, false>(piv, Dm, sb, lane);   // y_0 = D0inv b_0
+            if (lane < 15) sb[lane] = piv[lane];
+            __syncwarp();
             for (int i = 1; i < n; ++i) {
-                copy_blk(Dm, facw + (size_t)i * 3 * kBlk, lane);
-                copy_blk(Em, facw + (size_t)i * 3 * kBlk + kBlk, lane);
-                if (ARROW) copy_blk(Fm, facw + (size_t)i * 3 * kBlk + 2 * kBlk, lane);
+                copy_blk(Tm, facw + (size_t)i * 3 * kBlk, lane);
+                if (ARROW && i >= 2) copy_blk(Tp, facw + (size_t)i * 3 * kBlk + kBlk, lane);
                 __syncwarp();
-                gemv_sub15<true>(S.b + 15 * i, Em, S.b + 15 * (i - 1), lane);
-                if (ARROW && i >= 2) gemv_sub15<true>(S.b + 15 * i, Fm, S.b, lane);
-                bwd15(Dm, S.b + 15 * i, lane);
+                gemv15<true, true>(sb + 15 * i, Tm, sb + 15 * (i - 1), lane);   // y_i = c_i - T^T y_{i-1} - T'^T y_0
+                if (ARROW && i >= 2) gemv15<true, true>(sb + 15 * i, Tp, sb, lane);
             }
             // step = -y ; model_cost_change = -1/2 step.gs + 1/2 sum lm_diag step^2
             double sg = 0.0, lq = 0.0;
             bool finite = true;
             for (int i = lane; i < n * 15; i += 32) {
-                if (is_const(i / 15, i % 15)) { S.b[i] = 0.0; continue; }
-                const double stp = -S.b[i];
-                S.b[i] = stp;
+                if (is_const(i / 15, i % 15)) { sb[i] = 0.0; continue; }
+                const double stp = -sb[i];
+                sb[i] = stp;
                 if (!isfinite(stp)) finite = false;
-                const double gs = S.g[i] * S.sc[i];
-                const double hs = S.hdiag[i] * S.sc[i] * S.sc[i];
-                sg += stp * gs;
+                const double sc = scw[i];
+                const double hs = diag_H(i / 15, i % 15) * sc * sc;
+                sg += stp * gvec[i] * sc;
                 lq += fmin(fmax(hs, opt.min_lm_diagonal), opt.max_lm_diagonal) / st.radius * stp * stp;
             }
             sg = warp_sum(sg);
@@ -851,7 +770,6 @@ __device__ void window_step(const WindowArgs& a, int w, int lane, double* ws) {
             finite = __all_sync(0xffffffffu, finite);
             st.model_cost_change = -0.5 * sg + 0.5 * lq;
             ok = finite && st.model_cost_change > 0.0;
-            step_dot_g = sg; lm_quad = lq;
         }
         __syncwarp();
         if (ok) { have_step = true; st.num_invalid = 0; break; }
@@ -864,17 +782,16 @@ __device__ void window_step(const WindowArgs& a, int w, int lane, double* ws) {
         st.decrease_factor *= 2.0;
         if (st.iteration >= opt.max_iters) { st.status = 1; st.termination = 0; break; }
     }
-    (void)step_dot_g; (void)lm_quad;
     if (!have_step) {
         if (lane == 0) { a.state[w] = st; a.win_status[w] = st.status; }
         return;
     }
 
-    // ---- (5) candidate = Plus(x, step * scale) and its laser frame tables
+    // ---- (4) candidate = Plus(x, step * scale) and its laser frame tables
     for (int f = lane; f < n; f += 32) {
         double d[15];
 #pragma unroll
-        for (int c = 0; c < 15; ++c) d[c] = S.b[f * 15 + c] * S.sc[f * 15 + c];
+        for (int c = 0; c < 15; ++c) d[c] = sb[f * 15 + c] * scw[f * 15 + c];
 #pragma unroll
         for (int c = 0; c < 15; ++c) xc[15 * f + c] = is_const(f, c) ? x[15 * f + c] : x[15 * f + c] + d[c];
         if (!is_const(f, 3)) so3_plus(x + 15 * f + 3, d + 3, xc + 15 * f + 3);
@@ -884,7 +801,7 @@ __device__ void window_step(const WindowArgs& a, int w, int lane, double* ws) {
 }
 
 template <bool ARROW>
-__global__ void __launch_bounds__(128) window_step_kernel(WindowArgs a, int per_warp_doubles) {
+__global__ void __launch_bounds__(128) window_kernel(WindowArgs a, int per_warp_doubles) {
     extern __shared__ __align__(16) double smem[];
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
@@ -893,7 +810,18 @@ __global__ void __launch_bounds__(128) window_step_kernel(WindowArgs a, int per_
     window_step<ARROW>(a, w, lane, smem + (size_t)warp * per_warp_doubles);
 }
 
-// frame tables of arbitrary poses ([F][6] -> [F][24]); used for the initial point and the external reference poses
+__global__ void init_state_kernel(LMState* st, int32_t* status, int n, double radius) {
+    const int w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= n) return;
+    LMState s;
+    s.radius = radius; s.decrease_factor = 2.0; s.cost = 0.0; s.model_cost_change = 0.0; s.x_norm = 0.0; s.initial_cost = 0.0;
+    s.iteration = 0; s.num_invalid = 0; s.status = 0; s.termination = 0; s.n_success = 0; s.n_unsuccess = 0; s.last_success = 0; s.started = 0;
+    s.cur = 0; s.pad0 = 0;
+    st[w] = s;
+    status[w] = 0;
+}
+
+// frame tables of arbitrary poses ([F][stride] -> [F][24]); used for the initial point and the external reference poses
 __global__ void frame_table_kernel(Consts C, const double* poses, int stride, double* tabs, int n) {
     const int f = blockIdx.x * blockDim.x + threadIdx.x;
     if (f >= n) return;

@@ -28,7 +28,7 @@ EXPORTS = [
     "lvio2d_get_states", "lvio2d_set_point_shard", "lvio2d_solve_begin", "lvio2d_eval_laser", "lvio2d_reduce_buffer",
     "lvio2d_set_reduce_buffer", "lvio2d_lm_step", "lvio2d_linearize", "lvio2d_marginalize", "lvio2d_imu_preintegrate",
     "lvio2d_wheel_preintegrate", "lvio2d_eval_laser_factor", "lvio2d_eval_imu_factor", "lvio2d_eval_wheel_factor",
-    "lvio2d_eval_ground_factors",
+    "lvio2d_eval_ground_factors", "lvio2d_set_profiling", "lvio2d_get_profile",
 ]
 
 
@@ -79,6 +79,8 @@ def load_library(path=LIB_PATH):
     lib.lvio2d_eval_imu_factor.argtypes = [vp] + [dp] * 5
     lib.lvio2d_eval_wheel_factor.argtypes = [vp] + [dp] * 5
     lib.lvio2d_eval_ground_factors.argtypes = [vp] + [dp] * 3
+    lib.lvio2d_set_profiling.argtypes = [vp, C.c_int32]
+    lib.lvio2d_get_profile.argtypes = [vp, dp]
     _lib = lib
     return lib
 
@@ -199,6 +201,16 @@ class Context:
             return int(act.value)
         self._check(self.lib.lvio2d_lm_step(self._h, None), "lvio2d_lm_step")
         return None
+
+    # ---- measurement
+    def set_profiling(self, on=True):
+        self._check(self.lib.lvio2d_set_profiling(self._h, int(on)), "lvio2d_set_profiling")
+
+    def get_profile(self):
+        out = np.zeros(8)
+        self._check(self.lib.lvio2d_get_profile(self._h, _d(out)), "lvio2d_get_profile")
+        return dict(scan_ms=out[0], scan_launches=int(out[1]), window_ms=out[2], window_launches=int(out[3]),
+                    kernel_launches=int(out[4]), scan_bytes_per_launch=out[5], factor_ms=out[6], factor_launches=int(out[7]))
 
     # ---- linearisation / marginalisation
     def linearize(self, mode=0):

@@ -1,0 +1,381 @@
+#!/usr/bin/env python
+"""bench.py — front-end solver LM iterations/sec on 1081-beam x 30-keyframe windows (BASELINE.json metric).
+
+One "step" = one full solve (max 10 LM iterations, the reference's fast_mode cap, solver.cpp:800-801) of a batch of B
+synthetic C2 windows per GPU.  `value` = LM iterations executed by all windows of all ranks / device
+time, inputs already resident in HBM (lvio2d_bind_windows).  `e2e` = the same metric through the reference-facing call
+sequence with HOST buffers inside the timed region: lvio2d_set_windows (pinned host -> device) + lvio2d_solve +
+lvio2d_get_states (device -> host).  `roofline` describes the dominant kernel (scan_match_kernel): algorithmic bytes per
+launch / its CUDA-event duration against the measured HBM copy bandwidth.  `cpu_baseline` is the CPU oracle (a port of
+the reference path; the reference itself needs Eigen/Ceres/ROS and cannot be built here) on one core, the reference's
+own threading (solver.cpp:798).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--windows B] [--impl ours|reference]
+Multi-GPU (torchrun, one rank per GPU): windows are independent, so each rank solves its own B windows (weak scaling,
+no data-path collective); only the timing is reduced (max over ranks).  The point-sharded + all-reduce mode the
+north-star also names is measured by `--shard points` (strong scaling of one batch, one NCCL all-reduce per iteration).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+METRIC = "front-end solver iterations/sec (1081-beam x 30-KF window)"
+UNIT = "LM iterations/s"
+MAX_ITERS = 10
+UNIQUE_WINDOWS = 32
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "200", "-i", str(self.index)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+            except (ValueError, IndexError):
+                continue
+            for name, v in zip(names, r[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def build_host_batch(ctx, n_windows, seed0):
+    """B C2 windows: UNIQUE_WINDOWS distinct synthetic windows (ray-cast in numpy), tiled to B (distinct memory)."""
+    import lvio2d_b200 as L
+
+    uniq = min(UNIQUE_WINDOWS, n_windows)
+    sb = L.synth.config_c2(uniq, seed=seed0)
+    hb = ctx.preintegrate_batch(sb)  # device preintegrators
+    times = (n_windows + uniq - 1) // uniq
+    if times > 1:
+        hb = L.synth.tile_batch(hb, times)
+    return hb, uniq
+
+
+def to_device_struct(hb, torch, device):
+    from lvio2d_b200 import abi
+
+    keep = {}
+    s = abi.WindowBatch()
+    s.n_windows, s.n_frames = hb.n_windows, hb.n_frames
+    s.ground_multiplicity, s.prior_frame = hb.ground_multiplicity, hb.prior_frame
+    import ctypes as C
+
+    for name, (_, ctype) in abi._PTR_FIELDS.items():
+        a = hb.arrays[name]
+        if a is None:
+            setattr(s, name, ctype())
+            continue
+        t = torch.from_numpy(a.reshape(-1)).to(device)
+        keep[name] = t
+        setattr(s, name, C.cast(C.c_void_p(t.data_ptr()), ctype))
+    return s, keep
+
+
+def pinned_copy(hb, torch):
+    """The same batch in pinned host memory (what a host caller hands to lvio2d_set_windows)."""
+    from lvio2d_b200 import abi
+
+    fields = {}
+    keep = []
+    for name in abi._PTR_FIELDS:
+        a = hb.arrays[name]
+        if a is None:
+            fields[name] = None
+            continue
+        t = torch.from_numpy(a.reshape(-1).copy()).pin_memory()
+        keep.append(t)
+        fields[name] = t.numpy()
+    out = abi.HostBatch(hb.n_windows, hb.n_frames, hb.ground_multiplicity, hb.prior_frame, **fields)
+    out._pinned = keep
+    return out
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    import lvio2d_b200 as L
+    from lvio2d_b200.solver import Context
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world > 1:
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    device = torch.device("cuda", local_rank)
+    P = L.corridor_params(max_iters=MAX_ITERS, device=local_rank)
+    ctx = Context(P)
+    B = args.windows
+    shard_points = args.shard == "points" and world > 1
+    hb, uniq = build_host_batch(ctx, B, seed0=42 if shard_points else 42 + 1000 * rank)
+    dstruct, keep = to_device_struct(hb, torch, device)
+    ext = torch.cuda.ExternalStream(ctx.stream, device=device)
+
+    def barrier():
+        torch.cuda.synchronize(device)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(device)
+
+    # ------------------------------------------------------------------ device-resident arm
+    ctx.bind_windows(dstruct, keepalive=keep)
+    red = None
+    if shard_points:
+        ctx.set_point_shard(rank, world)
+        _, n_red = ctx.reduce_buffer()
+        red = torch.zeros(n_red, dtype=torch.float64, device=device)
+        ctx.set_reduce_buffer(red.data_ptr(), n_red)
+
+    def one_step():
+        if not shard_points:
+            ctx.solve_async()
+            return
+        ctx.solve_begin()
+        for _ in range(MAX_ITERS + 1):
+            ctx.eval_laser()
+            ctx.sync()                       # the all-reduce runs on torch's NCCL stream
+            dist.all_reduce(red)
+            torch.cuda.current_stream(device).synchronize()
+            ctx.lm_step()
+
+    for _ in range(args.warmup):
+        one_step()
+    ctx.sync()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ctx.set_profiling(True)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record(ext)
+    for _ in range(args.steps):
+        one_step()
+    e1.record(ext)
+    ctx.sync()
+    barrier()
+    dev_ms = e0.elapsed_time(e1)
+    prof = ctx.get_profile()
+    ctx.set_profiling(False)
+    summ = ctx.get_summaries()
+    iters_per_step = int(summ["iterations"].sum())
+    states_dev = ctx.get_states()
+
+    # ------------------------------------------------------------------ end-to-end arm (host buffers, H2D + solve + D2H timed)
+    hp = pinned_copy(hb, torch)
+    out_states = torch.empty(hb.n_windows * hb.n_frames * 15, dtype=torch.float64).pin_memory()
+    out_np = out_states.numpy().reshape(-1, 15)
+    e2e_ms = None
+    if not shard_points:
+        def e2e_step():
+            ctx.set_windows(hp)
+            ctx.solve(want_summary=False)
+            ctx.get_states(out_np)
+
+        for _ in range(max(1, min(args.warmup, 2))):
+            e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            e2e_step()
+        ctx.sync()
+        e2e_ms = (time.perf_counter() - t0) * 1e3
+        assert np.abs(out_np - states_dev).max() < 1e-9, "e2e and device-resident arms disagree"
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ------------------------------------------------------------------ reduce over ranks (max time, sum work)
+    t = torch.tensor([dev_ms, e2e_ms if e2e_ms is not None else 0.0], dtype=torch.float64, device=device)
+    work = torch.tensor([float(iters_per_step)], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        if not shard_points:
+            dist.all_reduce(work, op=dist.ReduceOp.SUM)
+    dev_ms, e2e_ms_all = float(t[0]), float(t[1])
+    total_iters_per_step = float(work[0])
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    value = total_iters_per_step * args.steps / (dev_ms * 1e-3)
+    peak, peak_src = measured_peaks()
+    scan_ms = prof["scan_ms"] / max(1, prof["scan_launches"])
+    achieved = prof["scan_bytes_per_launch"] / (scan_ms * 1e-3) / 1e9 if scan_ms > 0 else 0.0
+    result = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
+        "scaling": "strong" if shard_points else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {
+            "workload": f"C2: 1081 beams x 30 keyframes, fixed associations, IMU+wheel+ground+prior, {MAX_ITERS} LM iterations "
+                        f"(BASELINE.json configs[1]); {B} windows per GPU per step ({uniq} distinct synthetic windows tiled)",
+            "windows_per_gpu": B, "points_per_window": int(hb.n_points // hb.n_windows), "lm_iterations_per_window": MAX_ITERS,
+            "multi_gpu": ("points sharded over ranks, one NCCL all-reduce of the per-frame blocks per iteration" if shard_points
+                          else "independent windows per rank, no data-path collective"),
+            "l2": f"scan data per launch {prof['scan_bytes_per_launch'] / 1e6:.0f} MB > 126 MB L2 (no flush needed)"
+                  if prof["scan_bytes_per_launch"] > 2.0e8 else "working set fits L2: latency-bound configuration",
+        },
+        "e2e": None if shard_points else {
+            "value": total_iters_per_step * args.steps / (e2e_ms_all * 1e-3), "unit": UNIT,
+            "h2d_bytes_per_step": int(hp.nbytes()), "d2h_bytes_per_step": int(out_states.numel() * 8),
+            "ms_per_step": e2e_ms_all / args.steps,
+            "api": "lvio2d_set_windows(pinned host) + lvio2d_solve + lvio2d_get_states",
+        },
+        "gpu_launches": prof["kernel_launches"],
+        "kernel_share": {"scan_match_ms_per_step": prof["scan_ms"] / args.steps, "factor_ms_per_step": prof["factor_ms"] / args.steps, "window_ms_per_step": prof["window_ms"] / args.steps},
+        "roofline": {
+            "kernel": "scan_match_kernel<false,false>", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+            "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+            "algorithmic_bytes_per_launch": prof["scan_bytes_per_launch"], "avg_launch_ms": scan_ms,
+        },
+        "clocks": clocks,
+    }
+    if world == 1 and not args.no_cpu:
+        result["cpu_baseline"] = cpu_baseline(P, hb, seconds=args.cpu_seconds, threads=1)
+    print(json.dumps(result))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def cpu_baseline(P, hb, seconds, threads):
+    """The CPU oracle (port of the reference path) on a bounded sample: the first windows of the same batch."""
+    import oracle_lib as O
+    from lvio2d_b200 import abi
+
+    n = hb.n_frames
+
+    def sub(k):
+        a = hb.arrays
+        po, lo = a["point_offset"], a["line_offset"]
+        np_, nl = int(po[k * n]), int(lo[k * n])
+        return abi.HostBatch(k, n, hb.ground_multiplicity, hb.prior_frame,
+                             states=a["states"].reshape(-1, 15)[:k * n], const_mask=a["const_mask"].reshape(-1)[:k * n],
+                             point_offset=po[:k * n + 1], points=a["points"].reshape(-1, 2)[:np_], point_line=a["point_line"].reshape(-1)[:np_],
+                             point_weight=None if a["point_weight"] is None else a["point_weight"].reshape(-1)[:np_],
+                             line_offset=lo[:k * n + 1], lines=a["lines"].reshape(-1, 4)[:nl], ref_frame=a["ref_frame"].reshape(-1)[:k * n],
+                             ref_pose=a["ref_pose"].reshape(-1, 6)[:k * n], imu=a["imu"].reshape(-1, 466)[:k * (n - 1)],
+                             wheel=a["wheel"].reshape(-1, 15)[:k * (n - 1)],
+                             prior_X0=None if a["prior_X0"] is None else a["prior_X0"].reshape(-1, 15)[:k],
+                             prior_J=None if a["prior_J"] is None else a["prior_J"].reshape(-1, 225)[:k])
+
+    O.build()
+    one = sub(1)
+    t0 = time.perf_counter()
+    _, s = O.solve(P, one, n_threads=1)
+    t1 = time.perf_counter() - t0
+    k = int(max(threads, min(hb.n_windows, seconds / max(t1, 1e-3))))
+    k = max(1, min(k, hb.n_windows))
+    batch = sub(k)
+    t0 = time.perf_counter()
+    _, s = O.solve(P, batch, n_threads=threads)
+    dt = time.perf_counter() - t0
+    return {"value": float(s["iterations"].sum()) / dt, "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": f"{k} of the batch's windows, {int(s['iterations'].sum())} LM iterations in {dt:.1f} s "
+                      f"(oracle/liboracle.so, Jet autodiff, g++ -O3 -march=native)",
+            "host_cpus": os.cpu_count()}
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation of the path.  The reference binary cannot be built here
+    (Eigen, Ceres, ROS absent), so this times the oracle port with all host threads on bounded samples of the same
+    workload."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import lvio2d_b200 as L
+    import oracle_lib as O
+
+    O.build()
+    P = L.corridor_params(max_iters=MAX_ITERS)
+    threads = O.max_threads()
+    sb = L.synth.config_c2(min(UNIQUE_WINDOWS, max(threads, 8)), seed=42)
+    hb = O.preintegrate_batch(P, sb)
+    for _ in range(min(args.warmup, 1)):
+        O.solve(P, hb, n_threads=threads)
+    iters, t0 = 0, time.perf_counter()
+    for _ in range(args.steps):
+        _, s = O.solve(P, hb, n_threads=threads)
+        iters += int(s["iterations"].sum())
+    dt = time.perf_counter() - t0
+    value = iters / dt
+    sample = f"{hb.n_windows} C2 windows per step x {args.steps} steps, {threads} threads over windows"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": int(os.environ.get("WORLD_SIZE", "1")),
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3 / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "C2: 1081 beams x 30 keyframes, fixed associations, IMU+wheel+ground+prior, 10 LM iterations "
+                               "(BASELINE.json configs[1]); CPU oracle port of the reference path (reference itself unbuildable here)"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--windows", type=int, default=4096, help="windows per GPU per step")
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--shard", default="windows", choices=["windows", "points"])
+    ap.add_argument("--cpu-seconds", type=float, default=15.0)
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

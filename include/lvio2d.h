@@ -189,6 +189,15 @@ int lvio2d_reduce_buffer(lvio2d_ctx* ctx, void** device_ptr, int64_t* count);
 int lvio2d_set_reduce_buffer(lvio2d_ctx* ctx, void* device_ptr, int64_t count);
 int lvio2d_lm_step(lvio2d_ctx* ctx, int32_t* n_active /* host out, may be NULL (no sync) */);
 
+/* ---- measurement hooks (bench.py): with profiling on, every scan-match and window-step launch is bracketed by
+ * CUDA events on lvio2d_stream().  lvio2d_get_profile syncs and returns, accumulated since profiling was last
+ * switched on: out[0] scan-match ms, out[1] scan-match launches, out[2] window-step ms, out[3] window-step launches,
+ * out[4] all kernel launches of the context, out[5] scan-match algorithmic bytes (points/lines/tables read + blocks
+ * written by the frames that were actually processed is not tracked on the device; this is the per-launch figure
+ * for all active frames x launches), out[6] factor-kernel ms, out[7] factor-kernel launches. ---- */
+int lvio2d_set_profiling(lvio2d_ctx* ctx, int32_t on);
+int lvio2d_get_profile(lvio2d_ctx* ctx, double* out /* [8] */);
+
 /* ---- one-shot linearisation (test hook + what solver::marginalization builds, solver.cpp:367-380).
  * mode 0: the solver's reduced program (constant blocks have zero rows/cols, inactive residual
  *         blocks dropped); mode 1: the marginalisation program of solver.cpp:257-380 (no constant
