@@ -397,6 +397,101 @@ LV_HD void imu_jacobian_column(const Consts& C, const double* blob, const double
     if (blk == 7) { col[3] = -c0; col[4] = -c1; col[5] = -c2; }                    // v_j
 }
 
+// ------------------------------------------------------------------ all factors of one (frame i-1, frame i) item
+// Generic in T so that one warp lane can carry one derivative direction (Dual seeded on one of the 30 state
+// columns) while another lane carries the plain values: every lane runs the same instruction stream.  The two
+// rotations exp(theta_i), exp(theta_j) are shared by the IMU, wheel and ground residuals
+// (exp_so3(-theta) == exp_so3(theta)^T bit for bit: the quaternion only changes the sign of its vector part).
+template <class T> struct FrameState { V3<T> p, th, v, ba, bw; };
+template <class T> LV_HD M3<T> transpose(const M3<T>& A) {
+    M3<T> B;
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) B.m[i * 3 + j] = A.m[j * 3 + i];
+    return B;
+}
+// r_imu: the 15 residuals BEFORE whitening by sqrt_inverse_P; r_wheel: 3; r_ground: (res_p, res_q) of frame b
+template <class T>
+LV_HD void item_residuals(const Consts& C, const double* imu_blob, const double* wheel_blob, bool ground, const FrameState<T>& a,
+                          const FrameState<T>& b, T* r_imu, T* r_wheel, T* r_ground) {
+    const bool need_a = imu_blob != nullptr || wheel_blob != nullptr;
+    M3<T> Ri, Rj = exp_so3(b.th);
+    if (need_a) Ri = exp_so3(a.th);
+    if (imu_blob) {
+        const double* X = imu_blob;
+        const double* J = imu_blob + 15;
+        const double Dt = imu_blob[465];
+        const V3<T> dba = v3<T>(a.ba.x - X[9], a.ba.y - X[10], a.ba.z - X[11]);
+        const V3<T> dbw = v3<T>(a.bw.x - X[12], a.bw.y - X[13], a.bw.z - X[14]);
+        T ab[9];
+#pragma unroll
+        for (int k = 0; k < 9; ++k) {
+            ab[k] = X[k] + (J[k * 15 + 12] * dbw.x + J[k * 15 + 13] * dbw.y + J[k * 15 + 14] * dbw.z);
+            if (k < 6) ab[k] = ab[k] + (J[k * 15 + 9] * dba.x + J[k * 15 + 10] * dba.y + J[k * 15 + 11] * dba.z);
+        }
+        const double gz = C.g;
+        const V3<T> y1 = v3<T>(b.p.x - a.p.x - a.v.x * Dt, b.p.y - a.p.y - a.v.y * Dt, b.p.z - a.p.z + 0.5 * gz * Dt * Dt - a.v.z * Dt);
+        const V3<T> y2 = v3<T>(b.v.x - a.v.x, b.v.y - a.v.y, b.v.z + gz * Dt - a.v.z);
+        const V3<T> ra = mul_t(Ri, y1), rb = mul_t(Ri, y2);   // R_i^T y
+        r_imu[0] = ab[0] - ra.x; r_imu[1] = ab[1] - ra.y; r_imu[2] = ab[2] - ra.z;
+        r_imu[3] = ab[3] - rb.x; r_imu[4] = ab[4] - rb.y; r_imu[5] = ab[5] - rb.z;
+        const M3<T> E = exp_so3(v3<T>(-ab[6], -ab[7], -ab[8]));
+        const V3<T> rg = log_so3(mul(E, mul_tn(Ri, Rj)));
+        r_imu[6] = rg.x; r_imu[7] = rg.y; r_imu[8] = rg.z;
+        r_imu[9] = b.ba.x - a.ba.x; r_imu[10] = b.ba.y - a.ba.y; r_imu[11] = b.ba.z - a.ba.z;
+        r_imu[12] = b.bw.x - a.bw.x; r_imu[13] = b.bw.y - a.bw.y; r_imu[14] = b.bw.z - a.bw.z;
+    }
+    const Iso Tio = load_iso(C.T_io);
+    if (wheel_blob) {
+        const Iso dT = load_iso(wheel_blob);
+        const M3<T> Rio = lift<T>(Tio.R);
+        const V3<T> tio = lift<T>(Tio.t);
+        const M3<T> Roi = mul(Ri, Rio), Roj = mul(Rj, Rio);
+        const V3<T> toi = mul(Ri, tio) + a.p, toj = mul(Rj, tio) + b.p;
+        const V3<T> p = mul_t(Roi, toj - toi);
+        const V3<T> q = log_so3(mul_tn(Roi, Roj));
+        const V3<double> op = dT.t;
+        const V3<double> oq = log_so3(dT.R);
+        const double o_len = sqrt(op.x * op.x + op.y * op.y);
+        const T len = lv_sqrt(p.x * p.x + p.y * p.y);
+        T angle;
+        if (o_len > 0.0001 && val(len) > 0.0001) {
+            const T cz = (op.x / o_len) * (p.y / len) - (op.y / o_len) * (p.x / len);
+            angle = lv_asin(lv_sqrt(cz * cz));
+        } else {
+            angle = len;
+        }
+        if (val(len) < 0.0001 || o_len < 0.0001) r_wheel[0] = wheel_blob[12] * len;
+        else r_wheel[0] = wheel_blob[12] * (o_len - len);
+        r_wheel[1] = wheel_blob[13] * angle;
+        const T qn = norm(q);
+        const double oqn = norm(oq);
+        if (val(qn) < 0.001 || oqn < 0.001) r_wheel[2] = wheel_blob[14] * qn;
+        else r_wheel[2] = wheel_blob[14] * (oqn - qn);
+    }
+    if (ground) {
+        const T height = Rj.m[6] * Tio.t.x + Rj.m[7] * Tio.t.y + Rj.m[8] * Tio.t.z + b.p.z;
+        const V3<T> zax = v3<T>(Rj.m[0] * Tio.R.m[2] + Rj.m[1] * Tio.R.m[5] + Rj.m[2] * Tio.R.m[8],
+                                Rj.m[3] * Tio.R.m[2] + Rj.m[4] * Tio.R.m[5] + Rj.m[5] * Tio.R.m[8],
+                                Rj.m[6] * Tio.R.m[2] + Rj.m[7] * Tio.R.m[5] + Rj.m[8] * Tio.R.m[8]);
+        const T sinn = norm(cross(zax, v3<T>(T(0.0), T(0.0), T(1.0))));
+        r_ground[0] = C.ground_p_sqrt_info * height;
+        r_ground[1] = C.ground_q_sqrt_info * lv_asin(sinn);
+    }
+}
+LV_HD FrameState<Dual> seed_frame_state(const double* s, int seed /* column 0..14 or -1 */) {
+    FrameState<Dual> f;
+    f.p = lift<Dual>(load3(s)); f.th = lift<Dual>(load3(s + 3)); f.v = lift<Dual>(load3(s + 6));
+    f.ba = lift<Dual>(load3(s + 9)); f.bw = lift<Dual>(load3(s + 12));
+    if (seed >= 0) {
+        V3<Dual>& t = seed < 3 ? f.p : (seed < 6 ? f.th : (seed < 9 ? f.v : (seed < 12 ? f.ba : f.bw)));
+        const int k = seed % 3;
+        (k == 0 ? t.x : (k == 1 ? t.y : t.z)).d = 1.0;
+    }
+    return f;
+}
+
 // ------------------------------------------------------------------ laser frame table
 // C = P (R(theta_j) (R_il c + t_il) + p_j) restricted to xy is the affine map  C = M c + t  on the 2-D
 // scan point; d C / d theta_k = B_k c + b_k (SURVEY.md verification note).  Layout (24 doubles):

@@ -188,7 +188,7 @@ int launch_factors(lvio2d_ctx* ctx, const WindowArgs& a) {
 
 int launch_window(lvio2d_ctx* ctx, const WindowArgs& a) {
     const int per_warp = (int)window_smem_doubles(ctx->n, ctx->arrow);
-    const int wpc = std::max(1, std::min<int>(4, (int)((200 * 1024) / (per_warp * sizeof(double)))));
+    const int wpc = 2;
     const size_t smem = (size_t)wpc * per_warp * sizeof(double);
     const int grid = (ctx->B + wpc - 1) / wpc;
     if (ctx->profiling) cudaEventRecord(next_event(ctx->ev_win, ctx->ev_win_used), ctx->stream);

@@ -98,7 +98,7 @@ struct ReduceScatter<N, 0> {
 __host__ __device__ constexpr int halved5(int n) { for (int i = 0; i < 5; ++i) n = (n + 1) / 2; return n; }
 
 template <bool REF_FREE, bool HAS_WEIGHT>
-__global__ void __launch_bounds__(256) scan_match_kernel(ScanMatchArgs a) {
+__global__ void __launch_bounds__(256, REF_FREE ? 1 : 2) scan_match_kernel(ScanMatchArgs a) {
     constexpr int NACC = REF_FREE ? kAccFree : kAccTrack;
     constexpr int NPAD = REF_FREE ? kPadFree : kPadTrack;
     constexpr int ROW = REF_FREE ? kRowFree : kRowTrack;
@@ -112,6 +112,32 @@ __global__ void __launch_bounds__(256) scan_match_kernel(ScanMatchArgs a) {
     if (a.win_status && a.win_status[f / a.n_frames] != 0) return;
     if (!a.frame_active[f]) return;
     double* tab = smem + (size_t)warp * a.line_cap * ROW;
+
+    // ---- this warp's slice of the frame: rank shard, then tile
+    const int64_t p0 = a.point_offset[f], cnt = a.point_offset[f + 1] - p0;
+    const int64_t s0 = p0 + (cnt * a.shard_rank) / a.shard_world;
+    const int64_t s1 = p0 + (cnt * (a.shard_rank + 1)) / a.shard_world;
+    const int64_t per = (s1 - s0 + a.tiles - 1) / a.tiles;
+    const int64_t pb = s0 + per * tile;
+    const int64_t pe = (pb + per < s1) ? pb + per : s1;
+
+    // software pipeline: the loads of batch k+1 are in flight while batch k is accumulated; batch 0 is issued
+    // before the line table is built
+    constexpr int U = 4;
+    double2 nc[U];
+    int nli[U];
+    double nw[U];
+    auto issue = [&](int64_t base) {
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int64_t p = base + 32 * u;
+            const bool ok = p < pe;
+            nli[u] = ok ? ld_stream_s32(a.point_line + p) : -1;
+            nc[u] = ok ? ld_stream_f64x2(a.points + p) : make_double2(0.0, 0.0);
+            if constexpr (HAS_WEIGHT) nw[u] = ok ? ld_stream_f64(a.point_weight + p) : 0.0;
+        }
+    };
+    issue(pb + lane);
 
     // ---- this frame's table (24 doubles, broadcast loads) and the shared-memory line table
     const double* ft = a.frame_tab + (size_t)f * kFrameTab;
@@ -178,31 +204,17 @@ __global__ void __launch_bounds__(256) scan_match_kernel(ScanMatchArgs a) {
     }
     __syncwarp();
 
-    // ---- this warp's slice of the frame: rank shard, then tile
-    const int64_t p0 = a.point_offset[f], cnt = a.point_offset[f + 1] - p0;
-    const int64_t s0 = p0 + (cnt * a.shard_rank) / a.shard_world;
-    const int64_t s1 = p0 + (cnt * (a.shard_rank + 1)) / a.shard_world;
-    const int64_t per = (s1 - s0 + a.tiles - 1) / a.tiles;
-    const int64_t pb = s0 + per * tile;
-    const int64_t pe = (pb + per < s1) ? pb + per : s1;
-
     double acc[NACC];
 #pragma unroll
     for (int i = 0; i < NACC; ++i) acc[i] = 0.0;
 
-    constexpr int U = 4;
     for (int64_t base = pb + lane; base < pe; base += 32 * U) {
         double2 c[U];
         int li[U];
         double w[U];
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const int64_t p = base + 32 * u;
-            const bool ok = p < pe;
-            li[u] = ok ? ld_stream_s32(a.point_line + p) : -1;
-            c[u] = ok ? ld_stream_f64x2(a.points + p) : make_double2(0.0, 0.0);
-            if constexpr (HAS_WEIGHT) w[u] = ok ? ld_stream_f64(a.point_weight + p) : 0.0;
-        }
+        for (int u = 0; u < U; ++u) { c[u] = nc[u]; li[u] = nli[u]; if constexpr (HAS_WEIGHT) w[u] = nw[u]; }
+        issue(base + 32 * U);
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             if (li[u] < 0) continue;

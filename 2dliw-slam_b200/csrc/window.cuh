@@ -104,7 +104,7 @@ __device__ __forceinline__ bool col_const(uint8_t mask, int c) {  // c: column 0
 // factor_kernel: per-warp shared memory = blob 480 | J 15x32 | wheel 3x16 | ground 2x8 | prior r 16; the 30x30 result
 // aliases blob + J once every lane is done reading them
 constexpr int kFactorSmem = 480 + 480 + 48 + 16 + 16;
-__global__ void __launch_bounds__(128) factor_kernel(WindowArgs a) {
+__global__ void __launch_bounds__(128, 4) factor_kernel(WindowArgs a) {
     extern __shared__ __align__(16) double smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int n = a.n_frames;
@@ -132,72 +132,59 @@ __global__ void __launch_bounds__(128) factor_kernel(WindowArgs a) {
     const bool ground_on = a.ground_multiplicity > 0 && (mb & 3) != 3;
     const bool prior_on = a.prior_frame == i && (mb & 15) != 15;
     double cost = 0.0;
-    // ---- IMU: lanes 0..29 one Jacobian column each, lane 30 the residual
+    // ---- one lane per state column (0..14 frame a, 15..29 frame b), lane 30 carries the values: IMU + wheel +
+    // ground of this item evaluated once in dual arithmetic, every lane on the same instruction stream
     if (imu_on) {
         const double* blob = a.imu + ((size_t)w * (n - 1) + (i - 1)) * 466;
         for (int k = lane; k < 466; k += 32) sblob[k] = blob[k];
         __syncwarp();
-        double col[15];
-        if (lane < 30) imu_jacobian_column(a.C, sblob, xa, xb, lane, col);
-        else if (lane == 30) imu_raw_residual(a.C, sblob, xa, xb, col);
-        if (lane < 31) {
-            const bool dead = lane < 30 && col_const(lane < 15 ? ma : mb, lane % 15);
+    }
+    {
+        const double* wblob = wheel_on ? a.wheel + ((size_t)w * (n - 1) + (i - 1)) * 15 : nullptr;
+        const FrameState<Dual> fa_ = seed_frame_state(xa, lane < 15 ? lane : -1);
+        const FrameState<Dual> fb_ = seed_frame_state(xb, (lane >= 15 && lane < 30) ? lane - 15 : -1);
+        Dual ri[15], rw[3], rg[2];
+        item_residuals<Dual>(a.C, imu_on ? sblob : nullptr, wblob, ground_on, fa_, fb_, ri, rw, rg);
+        const bool value_lane = lane == 30;
+        const bool dead = lane < 30 && col_const(lane < 15 ? ma : mb, lane % 15);
+        if (imu_on) {
             const double* Sq = sblob + 240;  // sqrt_inverse_P = L^T: upper triangular
 #pragma unroll
             for (int r = 0; r < 15; ++r) {
                 double s = 0.0;
 #pragma unroll
-                for (int k = r; k < 15; ++k) s += Sq[r * 15 + k] * col[k];
-                sJ[r * 32 + lane] = dead ? 0.0 : s;
-                if (lane == 30) cost += s * s;
+                for (int k = r; k < 15; ++k) s += Sq[r * 15 + k] * (value_lane ? ri[k].a : ri[k].d);
+                sJ[r * 32 + lane] = (dead || lane == 31) ? 0.0 : s;
+                if (value_lane) cost += s * s;
             }
         } else {
+            for (int k = lane; k < 480; k += 32) sJ[k] = 0.0;
+        }
+        const int fl = lane % 15;
+        if (wheel_on) {
+            if (lane < 30 && fl < 6) {
+                const int wc = (lane < 15 ? 0 : 6) + fl;
 #pragma unroll
-            for (int r = 0; r < 15; ++r) sJ[r * 32 + 31] = 0.0;
-        }
-    } else {
-        for (int k = lane; k < 480; k += 32) sJ[k] = 0.0;
-    }
-    // ---- wheel: lanes 0..11 dual directions, lane 12 value
-    if (wheel_on) {
-        const double* blob = a.wheel + ((size_t)w * (n - 1) + (i - 1)) * 15;
-        if (lane < 13) {
-            V3<Dual> q[4] = {lift<Dual>(load3(xa)), lift<Dual>(load3(xa + 3)), lift<Dual>(load3(xb)), lift<Dual>(load3(xb + 3))};
-            if (lane < 12) {
-                V3<Dual>& t = q[lane / 3];
-                const int k = lane % 3;
-                (k == 0 ? t.x : (k == 1 ? t.y : t.z)).d = 1.0;
-            }
-            Dual r[3];
-            wheel_residuals<Dual>(a.C, blob, q[0], q[1], q[2], q[3], r);
-            const bool dead = lane < 12 && col_const(lane < 6 ? ma : mb, lane % 6);
+                for (int k = 0; k < 3; ++k) sW[k * 16 + wc] = dead ? 0.0 : rw[k].d;
+            } else if (value_lane) {
 #pragma unroll
-            for (int k = 0; k < 3; ++k) {
-                sW[k * 16 + lane] = lane == 12 ? r[k].a : (dead ? 0.0 : r[k].d);
-                if (lane == 12) cost += r[k].a * r[k].a;
+                for (int k = 0; k < 3; ++k) { sW[k * 16 + 12] = rw[k].a; cost += rw[k].a * rw[k].a; }
             }
+        } else {
+            for (int k = lane; k < 48; k += 32) sW[k] = 0.0;
         }
-    } else {
-        for (int k = lane; k < 48; k += 32) sW[k] = 0.0;
-    }
-    // ---- ground of frame i: lanes 16..21 dual directions, lane 22 value
-    if (ground_on) {
-        if (lane >= 16 && lane < 23) {
-            const int c = lane - 16;
-            V3<Dual> p = lift<Dual>(load3(xb)), th = lift<Dual>(load3(xb + 3));
-            if (c < 6) {
-                V3<Dual>& t = c < 3 ? p : th;
-                (c % 3 == 0 ? t.x : (c % 3 == 1 ? t.y : t.z)).d = 1.0;
+        if (ground_on) {
+            if (lane >= 15 && lane < 21) {
+                sG[lane - 15] = dead ? 0.0 : rg[0].d;
+                sG[8 + lane - 15] = dead ? 0.0 : rg[1].d;
+            } else if (value_lane) {
+                sG[6] = rg[0].a;
+                sG[14] = rg[1].a;
+                cost += a.ground_multiplicity * (rg[0].a * rg[0].a + rg[1].a * rg[1].a);
             }
-            Dual dp, dq;
-            ground_residuals<Dual>(a.C, p, th, &dp, &dq);
-            const bool dead = c < 6 && col_const(mb, c);
-            sG[c] = c == 6 ? dp.a : (dead ? 0.0 : dp.d);
-            sG[8 + c] = c == 6 ? dq.a : (dead ? 0.0 : dq.d);
-            if (c == 6) cost += a.ground_multiplicity * (dp.a * dp.a + dq.a * dq.a);
+        } else {
+            if (lane < 16) sG[lane] = 0.0;
         }
-    } else {
-        if (lane < 16) sG[lane] = 0.0;
     }
     // ---- prior of frame i: r = J (x - X0)
     const double* PJ = a.prior_J + (size_t)w * kBlk;
@@ -278,7 +265,7 @@ __global__ void __launch_bounds__(128) factor_kernel(WindowArgs a) {
 
 // In-place inverse of an SPD block by Gauss-Jordan elimination without pivoting, rows in registers.
 // Returns false (uniformly) when a pivot is not positive (the block is not positive definite) or not finite.
-__device__ __forceinline__ bool spd_inverse15(double* A, double* piv /* 16 doubles scratch */, int lane) {
+__device__ __noinline__ bool spd_inverse15(double* A, double* piv /* 16 doubles scratch */, int lane) {
     double row[15];
     const int r = lane < 15 ? lane : 0;
 #pragma unroll
@@ -312,34 +299,44 @@ __device__ __forceinline__ bool spd_inverse15(double* A, double* piv /* 16 doubl
     __syncwarp();
     return ok;
 }
-// C = A B   (row r of A in registers of lane r)
-__device__ __forceinline__ void gemm_ab15(double* Cm, const double* A, const double* B, int lane) {
-    if (lane < 15) {
+// The two GEMM kernels use all 32 lanes: lane = (row r = lane & 15, column half h = lane >> 4): h = 0 computes
+// columns 0..7, h = 1 columns 8..14.
+// C = A B
+__device__ __noinline__ void gemm_ab15(double* Cm, const double* A, const double* B, int lane) {
+    const int r = lane & 15, c0 = (lane >> 4) * 8;
+    if (r < 15) {
         double a[15];
 #pragma unroll
-        for (int k = 0; k < 15; ++k) a[k] = A[lane * 15 + k];
+        for (int k = 0; k < 15; ++k) a[k] = A[r * 15 + k];
 #pragma unroll
-        for (int c = 0; c < 15; ++c) {
-            double s = 0.0;
+        for (int cc = 0; cc < 8; ++cc) {
+            const int c = c0 + cc;
+            if (c < 15) {
+                double s = 0.0;
 #pragma unroll
-            for (int k = 0; k < 15; ++k) s += a[k] * B[k * 15 + c];
-            Cm[lane * 15 + c] = s;
+                for (int k = 0; k < 15; ++k) s += a[k] * B[k * 15 + c];
+                Cm[r * 15 + c] = s;
+            }
         }
     }
     __syncwarp();
 }
 // C -= A B^T
-__device__ __forceinline__ void gemm_sub_abt15(double* Cm, const double* A, const double* B, int lane) {
-    if (lane < 15) {
+__device__ __noinline__ void gemm_sub_abt15(double* Cm, const double* A, const double* B, int lane) {
+    const int r = lane & 15, c0 = (lane >> 4) * 8;
+    if (r < 15) {
         double a[15];
 #pragma unroll
-        for (int k = 0; k < 15; ++k) a[k] = A[lane * 15 + k];
+        for (int k = 0; k < 15; ++k) a[k] = A[r * 15 + k];
 #pragma unroll
-        for (int c = 0; c < 15; ++c) {
-            double s = 0.0;
+        for (int cc = 0; cc < 8; ++cc) {
+            const int c = c0 + cc;
+            if (c < 15) {
+                double s = 0.0;
 #pragma unroll
-            for (int k = 0; k < 15; ++k) s += a[k] * B[c * 15 + k];
-            Cm[lane * 15 + c] -= s;
+                for (int k = 0; k < 15; ++k) s += a[k] * B[c * 15 + k];
+                Cm[r * 15 + c] -= s;
+            }
         }
     }
     __syncwarp();
@@ -801,7 +798,7 @@ __device__ void window_step(const WindowArgs& a, int w, int lane, double* ws) {
 }
 
 template <bool ARROW>
-__global__ void __launch_bounds__(128) window_kernel(WindowArgs a, int per_warp_doubles) {
+__global__ void __launch_bounds__(64, 8) window_kernel(WindowArgs a, int per_warp_doubles) {
     extern __shared__ __align__(16) double smem[];
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;

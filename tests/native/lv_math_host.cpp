@@ -36,6 +36,24 @@ void lvm_ground(const Consts* C, const double* pose, double* res, double* J /*[2
         J[c] = dp.d; J[6 + c] = dq.d;
     }
 }
+// one (frame a, frame b) item through the unified dual evaluation: raw imu residual/Jacobian, wheel, ground
+void lvm_item(const Consts* C, const double* imu_blob, const double* wheel_blob, const double* sa, const double* sb, double* r_imu,
+              double* J_imu /*[15][30]*/, double* r_wheel, double* J_wheel /*[3][30]*/, double* r_ground, double* J_ground /*[2][30]*/) {
+    for (int c = 0; c <= 30; ++c) {
+        FrameState<Dual> a = seed_frame_state(sa, c < 15 ? c : -1), b = seed_frame_state(sb, (c >= 15 && c < 30) ? c - 15 : -1);
+        Dual ri[15], rw[3], rg[2];
+        item_residuals<Dual>(*C, imu_blob, wheel_blob, true, a, b, ri, rw, rg);
+        if (c == 30) {
+            for (int k = 0; k < 15; ++k) r_imu[k] = ri[k].a;
+            for (int k = 0; k < 3; ++k) r_wheel[k] = rw[k].a;
+            for (int k = 0; k < 2; ++k) r_ground[k] = rg[k].a;
+        } else {
+            for (int k = 0; k < 15; ++k) J_imu[k * 30 + c] = ri[k].d;
+            for (int k = 0; k < 3; ++k) J_wheel[k * 30 + c] = rw[k].d;
+            for (int k = 0; k < 2; ++k) J_ground[k * 30 + c] = rg[k].d;
+        }
+    }
+}
 void lvm_frame_table(const Consts* C, const double* pose, double* tab) { laser_frame_table(*C, pose, tab); }
 void lvm_so3_plus(const double* t, const double* d, double* o) { so3_plus(t, d, o); }
 }

@@ -130,3 +130,29 @@ def test_laser_frame_table_reproduces_laser_jacobian(lvm, oracle, params, consts
             jti.append(-tt * (n @ (Bk @ (a2 - a1))) / L_ - n @ (Bk @ a2 + bk))
         want_i = k * s * np.concatenate([-n, [0.0], jti])
         np.testing.assert_allclose(want_i, jac[0, 0:6], rtol=1e-9, atol=1e-8 * np.abs(jac).max())
+
+
+def test_unified_item_matches_oracle(lvm, oracle, params, consts):
+    """item_residuals<Dual>: one lane per state column, IMU + wheel + ground sharing the rotations (factor_kernel)."""
+    for _ in range(8):
+        blob, _, _ = make_imu_blob(oracle, params)
+        steps = np.zeros((2, 7)); steps[:, 0] = 0.05
+        steps[:, 1:4] = [0.7, 0.01, 0.0] + RNG.normal(0, 0.02, (2, 3)); steps[:, 4:7] = [0, 0, 0.3] + RNG.normal(0, 0.02, (2, 3))
+        wblob = oracle.wheel_preintegrate(params, [0, 2], steps)[0]
+        si = np.concatenate([corridor_like_pose(), RNG.normal(0, 0.5, 3), RNG.normal(0, 0.02, 3), RNG.normal(0, 0.002, 3)])
+        sj = si + np.concatenate([RNG.normal(0, 0.05, 3), RNG.normal(0, 0.03, 3), RNG.normal(0, 0.1, 3), RNG.normal(0, 1e-3, 6)])
+        r_imu, J_imu = np.zeros(15), np.zeros((15, 30))
+        r_w, J_w, r_g, J_g = np.zeros(3), np.zeros((3, 30)), np.zeros(2), np.zeros((2, 30))
+        lvm.lvm_item(C.byref(consts), d(blob), d(wblob), d(si), d(sj), d(r_imu), d(J_imu), d(r_w), d(J_w), d(r_g), d(J_g))
+        S = blob[240:465].reshape(15, 15)
+        res, jac = oracle.eval_imu_factor(params, blob, si, sj)
+        np.testing.assert_allclose(S @ r_imu, res, rtol=1e-11, atol=1e-12 * np.abs(res).max())
+        np.testing.assert_allclose(S @ J_imu, jac, rtol=1e-9, atol=1e-11 * np.abs(jac).max())
+        wres, wjac = oracle.eval_wheel_factor(params, wblob, si[:6], sj[:6])
+        np.testing.assert_allclose(r_w, wres, rtol=1e-11, atol=1e-9)
+        pose_cols = [0, 1, 2, 3, 4, 5, 15, 16, 17, 18, 19, 20]
+        np.testing.assert_allclose(J_w[:, pose_cols], wjac, rtol=1e-9, atol=1e-10 * np.abs(wjac).max())
+        assert np.all(np.delete(J_w, pose_cols, axis=1) == 0)
+        gres, gjac = oracle.eval_ground_factors(params, sj[:6])
+        np.testing.assert_allclose(r_g, gres, rtol=1e-11, atol=1e-9)
+        np.testing.assert_allclose(J_g[:, 15:21], gjac, rtol=1e-9, atol=1e-10 * np.abs(gjac).max())
