@@ -173,30 +173,37 @@ template <class T> LV_HD V3<T> normalize_so3(const V3<T>& w) {
 // rotation matrix -> quaternion (Eigen::Quaternion(Matrix3) branches) -> normalised -> angle-axis
 // (ceres::QuaternionToAngleAxis) -> wrapped (common.h:148-163)
 template <class T> LV_HD V3<T> log_so3(const M3<T>& R) {
-    T q[4];  // w x y z
+    T qw, qx, qy, qz;
     T t = R.m[0] + R.m[4] + R.m[8];
     if (val(t) > 0.0) {
         t = lv_sqrt(t + 1.0);
-        q[0] = 0.5 * t;
+        qw = 0.5 * t;
         t = 0.5 / t;
-        q[1] = (R.m[7] - R.m[5]) * t;
-        q[2] = (R.m[2] - R.m[6]) * t;
-        q[3] = (R.m[3] - R.m[1]) * t;
+        qx = (R.m[7] - R.m[5]) * t;
+        qy = (R.m[2] - R.m[6]) * t;
+        qz = (R.m[3] - R.m[1]) * t;
     } else {
+        // largest diagonal element i, then j = i+1, k = i+2 (mod 3); spelled out so that every index is static
         int i = 0;
         if (val(R.m[4]) > val(R.m[0])) i = 1;
-        if (val(R.m[8]) > val(R.m[i * 4])) i = 2;
-        const int j = (i + 1) % 3, k = (j + 1) % 3;
-        t = lv_sqrt(R.m[i * 4] - R.m[j * 4] - R.m[k * 4] + 1.0);
-        q[1 + i] = 0.5 * t;
-        t = 0.5 / t;
-        q[0] = (R.m[k * 3 + j] - R.m[j * 3 + k]) * t;
-        q[1 + j] = (R.m[j * 3 + i] + R.m[i * 3 + j]) * t;
-        q[1 + k] = (R.m[k * 3 + i] + R.m[i * 3 + k]) * t;
+        if (val(R.m[8]) > val(i == 0 ? R.m[0] : R.m[4])) i = 2;
+        if (i == 0) {
+            t = lv_sqrt(R.m[0] - R.m[4] - R.m[8] + 1.0);
+            qx = 0.5 * t; t = 0.5 / t;
+            qw = (R.m[7] - R.m[5]) * t; qy = (R.m[3] + R.m[1]) * t; qz = (R.m[6] + R.m[2]) * t;
+        } else if (i == 1) {
+            t = lv_sqrt(R.m[4] - R.m[8] - R.m[0] + 1.0);
+            qy = 0.5 * t; t = 0.5 / t;
+            qw = (R.m[2] - R.m[6]) * t; qz = (R.m[7] + R.m[5]) * t; qx = (R.m[1] + R.m[3]) * t;
+        } else {
+            t = lv_sqrt(R.m[8] - R.m[0] - R.m[4] + 1.0);
+            qz = 0.5 * t; t = 0.5 / t;
+            qw = (R.m[3] - R.m[1]) * t; qx = (R.m[2] + R.m[6]) * t; qy = (R.m[5] + R.m[7]) * t;
+        }
     }
-    const T qn = lv_sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+    const T qn = lv_sqrt(qw * qw + qx * qx + qy * qy + qz * qz);
     const T qi = T(1.0) / qn;
-    const T w = q[0] * qi, x = q[1] * qi, y = q[2] * qi, z = q[3] * qi;
+    const T w = qw * qi, x = qx * qi, y = qy * qi, z = qz * qi;
     const T s2 = x * x + y * y + z * z;
     T k;
     if (val(s2) > 0.0) {
@@ -411,84 +418,90 @@ template <class T> LV_HD M3<T> transpose(const M3<T>& A) {
         for (int j = 0; j < 3; ++j) B.m[i * 3 + j] = A.m[j * 3 + i];
     return B;
 }
-// r_imu: the 15 residuals BEFORE whitening by sqrt_inverse_P; r_wheel: 3; r_ground: (res_p, res_q) of frame b
+// r_imu: the 15 residuals BEFORE whitening by sqrt_inverse_P
+template <class T>
+LV_HD void item_imu(const Consts& C, const double* imu_blob, const FrameState<T>& a, const FrameState<T>& b, const M3<T>& Ri,
+                    const M3<T>& Rj, T* r_imu) {
+    const double* X = imu_blob;
+    const double* J = imu_blob + 15;
+    const double Dt = imu_blob[465];
+    const V3<T> dba = v3<T>(a.ba.x - X[9], a.ba.y - X[10], a.ba.z - X[11]);
+    const V3<T> dbw = v3<T>(a.bw.x - X[12], a.bw.y - X[13], a.bw.z - X[14]);
+    T ab[9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
+        ab[k] = X[k] + (J[k * 15 + 12] * dbw.x + J[k * 15 + 13] * dbw.y + J[k * 15 + 14] * dbw.z);
+        if (k < 6) ab[k] = ab[k] + (J[k * 15 + 9] * dba.x + J[k * 15 + 10] * dba.y + J[k * 15 + 11] * dba.z);
+    }
+    const double gz = C.g;
+    const V3<T> y1 = v3<T>(b.p.x - a.p.x - a.v.x * Dt, b.p.y - a.p.y - a.v.y * Dt, b.p.z - a.p.z + 0.5 * gz * Dt * Dt - a.v.z * Dt);
+    const V3<T> y2 = v3<T>(b.v.x - a.v.x, b.v.y - a.v.y, b.v.z + gz * Dt - a.v.z);
+    const V3<T> ra = mul_t(Ri, y1), rb = mul_t(Ri, y2);   // R_i^T y
+    r_imu[0] = ab[0] - ra.x; r_imu[1] = ab[1] - ra.y; r_imu[2] = ab[2] - ra.z;
+    r_imu[3] = ab[3] - rb.x; r_imu[4] = ab[4] - rb.y; r_imu[5] = ab[5] - rb.z;
+    const M3<T> E = exp_so3(v3<T>(-ab[6], -ab[7], -ab[8]));
+    const V3<T> rg = log_so3(mul(E, mul_tn(Ri, Rj)));
+    r_imu[6] = rg.x; r_imu[7] = rg.y; r_imu[8] = rg.z;
+    r_imu[9] = b.ba.x - a.ba.x; r_imu[10] = b.ba.y - a.ba.y; r_imu[11] = b.ba.z - a.ba.z;
+    r_imu[12] = b.bw.x - a.bw.x; r_imu[13] = b.bw.y - a.bw.y; r_imu[14] = b.bw.z - a.bw.z;
+}
+template <class T>
+LV_HD void item_wheel(const Consts& C, const double* wheel_blob, const V3<T>& pa, const V3<T>& pb, const M3<T>& Ri, const M3<T>& Rj,
+                      T* r_wheel) {
+    const Iso Tio = load_iso(C.T_io);
+    const Iso dT = load_iso(wheel_blob);
+    const M3<T> Rio = lift<T>(Tio.R);
+    const V3<T> tio = lift<T>(Tio.t);
+    const M3<T> Roi = mul(Ri, Rio), Roj = mul(Rj, Rio);
+    const V3<T> toi = mul(Ri, tio) + pa, toj = mul(Rj, tio) + pb;
+    const V3<T> p = mul_t(Roi, toj - toi);
+    const V3<T> q = log_so3(mul_tn(Roi, Roj));
+    const V3<double> op = dT.t;
+    const V3<double> oq = log_so3(dT.R);
+    const double o_len = sqrt(op.x * op.x + op.y * op.y);
+    const T len = lv_sqrt(p.x * p.x + p.y * p.y);
+    T angle;
+    if (o_len > 0.0001 && val(len) > 0.0001) {
+        const T cz = (op.x / o_len) * (p.y / len) - (op.y / o_len) * (p.x / len);
+        angle = lv_asin(lv_sqrt(cz * cz));
+    } else {
+        angle = len;
+    }
+    if (val(len) < 0.0001 || o_len < 0.0001) r_wheel[0] = wheel_blob[12] * len;
+    else r_wheel[0] = wheel_blob[12] * (o_len - len);
+    r_wheel[1] = wheel_blob[13] * angle;
+    const T qn = norm(q);
+    const double oqn = norm(oq);
+    if (val(qn) < 0.001 || oqn < 0.001) r_wheel[2] = wheel_blob[14] * qn;
+    else r_wheel[2] = wheel_blob[14] * (oqn - qn);
+}
+template <class T> LV_HD void item_ground(const Consts& C, const V3<T>& pb, const M3<T>& Rj, T* r_ground) {
+    const Iso Tio = load_iso(C.T_io);
+    const T height = Rj.m[6] * Tio.t.x + Rj.m[7] * Tio.t.y + Rj.m[8] * Tio.t.z + pb.z;
+    const V3<T> zax = v3<T>(Rj.m[0] * Tio.R.m[2] + Rj.m[1] * Tio.R.m[5] + Rj.m[2] * Tio.R.m[8],
+                            Rj.m[3] * Tio.R.m[2] + Rj.m[4] * Tio.R.m[5] + Rj.m[5] * Tio.R.m[8],
+                            Rj.m[6] * Tio.R.m[2] + Rj.m[7] * Tio.R.m[5] + Rj.m[8] * Tio.R.m[8]);
+    const T sinn = norm(cross(zax, v3<T>(T(0.0), T(0.0), T(1.0))));
+    r_ground[0] = C.ground_p_sqrt_info * height;
+    r_ground[1] = C.ground_q_sqrt_info * lv_asin(sinn);
+}
+// all three together (host tests)
 template <class T>
 LV_HD void item_residuals(const Consts& C, const double* imu_blob, const double* wheel_blob, bool ground, const FrameState<T>& a,
                           const FrameState<T>& b, T* r_imu, T* r_wheel, T* r_ground) {
-    const bool need_a = imu_blob != nullptr || wheel_blob != nullptr;
-    M3<T> Ri, Rj = exp_so3(b.th);
-    if (need_a) Ri = exp_so3(a.th);
-    if (imu_blob) {
-        const double* X = imu_blob;
-        const double* J = imu_blob + 15;
-        const double Dt = imu_blob[465];
-        const V3<T> dba = v3<T>(a.ba.x - X[9], a.ba.y - X[10], a.ba.z - X[11]);
-        const V3<T> dbw = v3<T>(a.bw.x - X[12], a.bw.y - X[13], a.bw.z - X[14]);
-        T ab[9];
-#pragma unroll
-        for (int k = 0; k < 9; ++k) {
-            ab[k] = X[k] + (J[k * 15 + 12] * dbw.x + J[k * 15 + 13] * dbw.y + J[k * 15 + 14] * dbw.z);
-            if (k < 6) ab[k] = ab[k] + (J[k * 15 + 9] * dba.x + J[k * 15 + 10] * dba.y + J[k * 15 + 11] * dba.z);
-        }
-        const double gz = C.g;
-        const V3<T> y1 = v3<T>(b.p.x - a.p.x - a.v.x * Dt, b.p.y - a.p.y - a.v.y * Dt, b.p.z - a.p.z + 0.5 * gz * Dt * Dt - a.v.z * Dt);
-        const V3<T> y2 = v3<T>(b.v.x - a.v.x, b.v.y - a.v.y, b.v.z + gz * Dt - a.v.z);
-        const V3<T> ra = mul_t(Ri, y1), rb = mul_t(Ri, y2);   // R_i^T y
-        r_imu[0] = ab[0] - ra.x; r_imu[1] = ab[1] - ra.y; r_imu[2] = ab[2] - ra.z;
-        r_imu[3] = ab[3] - rb.x; r_imu[4] = ab[4] - rb.y; r_imu[5] = ab[5] - rb.z;
-        const M3<T> E = exp_so3(v3<T>(-ab[6], -ab[7], -ab[8]));
-        const V3<T> rg = log_so3(mul(E, mul_tn(Ri, Rj)));
-        r_imu[6] = rg.x; r_imu[7] = rg.y; r_imu[8] = rg.z;
-        r_imu[9] = b.ba.x - a.ba.x; r_imu[10] = b.ba.y - a.ba.y; r_imu[11] = b.ba.z - a.ba.z;
-        r_imu[12] = b.bw.x - a.bw.x; r_imu[13] = b.bw.y - a.bw.y; r_imu[14] = b.bw.z - a.bw.z;
-    }
-    const Iso Tio = load_iso(C.T_io);
-    if (wheel_blob) {
-        const Iso dT = load_iso(wheel_blob);
-        const M3<T> Rio = lift<T>(Tio.R);
-        const V3<T> tio = lift<T>(Tio.t);
-        const M3<T> Roi = mul(Ri, Rio), Roj = mul(Rj, Rio);
-        const V3<T> toi = mul(Ri, tio) + a.p, toj = mul(Rj, tio) + b.p;
-        const V3<T> p = mul_t(Roi, toj - toi);
-        const V3<T> q = log_so3(mul_tn(Roi, Roj));
-        const V3<double> op = dT.t;
-        const V3<double> oq = log_so3(dT.R);
-        const double o_len = sqrt(op.x * op.x + op.y * op.y);
-        const T len = lv_sqrt(p.x * p.x + p.y * p.y);
-        T angle;
-        if (o_len > 0.0001 && val(len) > 0.0001) {
-            const T cz = (op.x / o_len) * (p.y / len) - (op.y / o_len) * (p.x / len);
-            angle = lv_asin(lv_sqrt(cz * cz));
-        } else {
-            angle = len;
-        }
-        if (val(len) < 0.0001 || o_len < 0.0001) r_wheel[0] = wheel_blob[12] * len;
-        else r_wheel[0] = wheel_blob[12] * (o_len - len);
-        r_wheel[1] = wheel_blob[13] * angle;
-        const T qn = norm(q);
-        const double oqn = norm(oq);
-        if (val(qn) < 0.001 || oqn < 0.001) r_wheel[2] = wheel_blob[14] * qn;
-        else r_wheel[2] = wheel_blob[14] * (oqn - qn);
-    }
-    if (ground) {
-        const T height = Rj.m[6] * Tio.t.x + Rj.m[7] * Tio.t.y + Rj.m[8] * Tio.t.z + b.p.z;
-        const V3<T> zax = v3<T>(Rj.m[0] * Tio.R.m[2] + Rj.m[1] * Tio.R.m[5] + Rj.m[2] * Tio.R.m[8],
-                                Rj.m[3] * Tio.R.m[2] + Rj.m[4] * Tio.R.m[5] + Rj.m[5] * Tio.R.m[8],
-                                Rj.m[6] * Tio.R.m[2] + Rj.m[7] * Tio.R.m[5] + Rj.m[8] * Tio.R.m[8]);
-        const T sinn = norm(cross(zax, v3<T>(T(0.0), T(0.0), T(1.0))));
-        r_ground[0] = C.ground_p_sqrt_info * height;
-        r_ground[1] = C.ground_q_sqrt_info * lv_asin(sinn);
-    }
+    const M3<T> Ri = exp_so3(a.th), Rj = exp_so3(b.th);
+    if (imu_blob) item_imu(C, imu_blob, a, b, Ri, Rj, r_imu);
+    if (wheel_blob) item_wheel(C, wheel_blob, a.p, b.p, Ri, Rj, r_wheel);
+    if (ground) item_ground(C, b.p, Rj, r_ground);
 }
 LV_HD FrameState<Dual> seed_frame_state(const double* s, int seed /* column 0..14 or -1 */) {
+    // branch-free seeding keeps the struct in registers (no address is taken)
     FrameState<Dual> f;
-    f.p = lift<Dual>(load3(s)); f.th = lift<Dual>(load3(s + 3)); f.v = lift<Dual>(load3(s + 6));
-    f.ba = lift<Dual>(load3(s + 9)); f.bw = lift<Dual>(load3(s + 12));
-    if (seed >= 0) {
-        V3<Dual>& t = seed < 3 ? f.p : (seed < 6 ? f.th : (seed < 9 ? f.v : (seed < 12 ? f.ba : f.bw)));
-        const int k = seed % 3;
-        (k == 0 ? t.x : (k == 1 ? t.y : t.z)).d = 1.0;
-    }
+    f.p = v3<Dual>(Dual(s[0], seed == 0 ? 1.0 : 0.0), Dual(s[1], seed == 1 ? 1.0 : 0.0), Dual(s[2], seed == 2 ? 1.0 : 0.0));
+    f.th = v3<Dual>(Dual(s[3], seed == 3 ? 1.0 : 0.0), Dual(s[4], seed == 4 ? 1.0 : 0.0), Dual(s[5], seed == 5 ? 1.0 : 0.0));
+    f.v = v3<Dual>(Dual(s[6], seed == 6 ? 1.0 : 0.0), Dual(s[7], seed == 7 ? 1.0 : 0.0), Dual(s[8], seed == 8 ? 1.0 : 0.0));
+    f.ba = v3<Dual>(Dual(s[9], seed == 9 ? 1.0 : 0.0), Dual(s[10], seed == 10 ? 1.0 : 0.0), Dual(s[11], seed == 11 ? 1.0 : 0.0));
+    f.bw = v3<Dual>(Dual(s[12], seed == 12 ? 1.0 : 0.0), Dual(s[13], seed == 13 ? 1.0 : 0.0), Dual(s[14], seed == 14 ? 1.0 : 0.0));
     return f;
 }
 

@@ -50,8 +50,11 @@ struct LMOptions {
 };
 
 constexpr int kBlk = 225;
-// factor item record: H_aa | H_ab | H_bb | g_a | g_b | cost | pad
-constexpr int kItemHaa = 0, kItemHab = 225, kItemHbb = 450, kItemGa = 675, kItemGb = 690, kItemCost = 705, kItem = 712;
+// factor item record: the symmetric 30x30 J^T J over (frame i-1, frame i) row-major with row stride 30 | g_a | g_b | cost | pad
+constexpr int kItemGa = 900, kItemGb = 915, kItemCost = 930, kItem = 936;
+__device__ __forceinline__ int item_haa(int r, int c) { return r * 30 + c; }
+__device__ __forceinline__ int item_hab(int r, int c) { return r * 30 + 15 + c; }
+__device__ __forceinline__ int item_hbb(int r, int c) { return (15 + r) * 30 + 15 + c; }
 
 struct WindowArgs {
     Consts C;
@@ -101,10 +104,9 @@ __device__ __forceinline__ bool col_const(uint8_t mask, int c) {  // c: column 0
 }
 
 // =====================================================================================================
-// factor_kernel: per-warp shared memory = blob 480 | J 15x32 | wheel 3x16 | ground 2x8 | prior r 16; the 30x30 result
-// aliases blob + J once every lane is done reading them
+// factor_kernel: per-warp shared memory = blob 480 | J 15x32 | wheel 3x16 | ground 2x8 | prior r 16
 constexpr int kFactorSmem = 480 + 480 + 48 + 16 + 16;
-__global__ void __launch_bounds__(128, 4) factor_kernel(WindowArgs a) {
+__global__ void __launch_bounds__(128, 3) factor_kernel(WindowArgs a) {
     extern __shared__ __align__(16) double smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int n = a.n_frames;
@@ -120,7 +122,6 @@ __global__ void __launch_bounds__(128, 4) factor_kernel(WindowArgs a) {
     double* sW = sJ + 480;      // wheel [3][16]: cols 0..11 Jacobian, col 12 residual
     double* sG = sW + 48;       // ground [2][8]: cols 0..5 Jacobian, col 6 residual
     double* sP = sG + 16;       // prior residual [15]
-    double* sH = sblob;         // [30][30], aliases sblob + sJ after the Jacobian products
     const double* X = a.xc + (size_t)w * n * 15;
     const uint8_t* cm = a.const_mask + (size_t)w * n;
     const uint8_t mb = mode == 1 ? 0 : cm[i];
@@ -143,11 +144,14 @@ __global__ void __launch_bounds__(128, 4) factor_kernel(WindowArgs a) {
         const double* wblob = wheel_on ? a.wheel + ((size_t)w * (n - 1) + (i - 1)) * 15 : nullptr;
         const FrameState<Dual> fa_ = seed_frame_state(xa, lane < 15 ? lane : -1);
         const FrameState<Dual> fb_ = seed_frame_state(xb, (lane >= 15 && lane < 30) ? lane - 15 : -1);
-        Dual ri[15], rw[3], rg[2];
-        item_residuals<Dual>(a.C, imu_on ? sblob : nullptr, wblob, ground_on, fa_, fb_, ri, rw, rg);
+        const M3<Dual> Rj = exp_so3(fb_.th);
+        M3<Dual> Ri;
+        if (imu_on || wheel_on) Ri = exp_so3(fa_.th);
         const bool value_lane = lane == 30;
         const bool dead = lane < 30 && col_const(lane < 15 ? ma : mb, lane % 15);
         if (imu_on) {
+            Dual ri[15];
+            item_imu<Dual>(a.C, sblob, fa_, fb_, Ri, Rj, ri);
             const double* Sq = sblob + 240;  // sqrt_inverse_P = L^T: upper triangular
 #pragma unroll
             for (int r = 0; r < 15; ++r) {
@@ -162,6 +166,8 @@ __global__ void __launch_bounds__(128, 4) factor_kernel(WindowArgs a) {
         }
         const int fl = lane % 15;
         if (wheel_on) {
+            Dual rw[3];
+            item_wheel<Dual>(a.C, wblob, fa_.p, fb_.p, Ri, Rj, rw);
             if (lane < 30 && fl < 6) {
                 const int wc = (lane < 15 ? 0 : 6) + fl;
 #pragma unroll
@@ -174,6 +180,8 @@ __global__ void __launch_bounds__(128, 4) factor_kernel(WindowArgs a) {
             for (int k = lane; k < 48; k += 32) sW[k] = 0.0;
         }
         if (ground_on) {
+            Dual rg[2];
+            item_ground<Dual>(a.C, fb_.p, Rj, rg);
             if (lane >= 15 && lane < 21) {
                 sG[lane - 15] = dead ? 0.0 : rg[0].d;
                 sG[8 + lane - 15] = dead ? 0.0 : rg[1].d;
@@ -198,65 +206,65 @@ __global__ void __launch_bounds__(128, 4) factor_kernel(WindowArgs a) {
         }
     }
     __syncwarp();
-    // ---- row `lane` of the 30x30 J^T J of this item + its gradient entry
+    // ---- row `lane` of the symmetric 30x30 J^T J of this item, written column by column: for a fixed column the 30
+    // lanes store 30 consecutive doubles (H is symmetric, so [col][row] is also [row][col])
     double gsum = 0.0;
-    double hrow[30];
     if (lane < 30) {
         double mine[15];
 #pragma unroll
         for (int r = 0; r < 15; ++r) mine[r] = sJ[r * 32 + lane];
 #pragma unroll
         for (int r = 0; r < 15; ++r) gsum += mine[r] * sJ[r * 32 + 30];
-#pragma unroll
-        for (int c = 0; c < 30; ++c) {
-            double s = 0.0;
-#pragma unroll
-            for (int r = 0; r < 15; ++r) s += mine[r] * sJ[r * 32 + c];
-            hrow[c] = s;
-        }
         const int fl = lane % 15;
-        if (fl < 6) {
-            const int wc = (lane < 15 ? 0 : 6) + fl;
-            const double w0 = sW[wc], w1 = sW[16 + wc], w2 = sW[32 + wc];
+        const bool pose_lane = fl < 6;
+        const int wc = (lane < 15 ? 0 : 6) + fl;
+        double w0 = 0.0, w1 = 0.0, w2 = 0.0, jp = 0.0, jq = 0.0;
+        const double m = (double)a.ground_multiplicity;
+        if (pose_lane) {
+            w0 = sW[wc]; w1 = sW[16 + wc]; w2 = sW[32 + wc];
             gsum += w0 * sW[12] + w1 * sW[16 + 12] + w2 * sW[32 + 12];
-#pragma unroll
-            for (int c = 0; c < 12; ++c) {
-                const int hc = (c < 6 ? 0 : 15) + (c % 6);
-                hrow[hc] += w0 * sW[c] + w1 * sW[16 + c] + w2 * sW[32 + c];
-            }
             if (lane >= 15) {
-                const double m = (double)a.ground_multiplicity;
-                const double jp = sG[fl], jq = sG[8 + fl];
+                jp = sG[fl]; jq = sG[8 + fl];
                 gsum += m * (jp * sG[6] + jq * sG[8 + 6]);
-#pragma unroll
-                for (int c = 0; c < 6; ++c) hrow[15 + c] += m * (jp * sG[c] + jq * sG[8 + c]);
             }
         }
-        if (prior_on && lane >= 15 && !col_const(mb, fl)) {
+        const bool prior_lane = prior_on && lane >= 15 && !col_const(mb, fl);
+        if (prior_lane) {
             double gs = 0.0;
             for (int r = 0; r < 15; ++r) gs += PJ[r * 15 + fl] * sP[r];
             gsum += gs;
+        }
 #pragma unroll
-            for (int c = 0; c < 15; ++c) {
-                double s = 0.0;
-                for (int r = 0; r < 15; ++r) s += PJ[r * 15 + fl] * PJ[r * 15 + c];
-                hrow[15 + c] += col_const(mb, c) ? 0.0 : s;
+        for (int c2 = 0; c2 < 30; c2 += 2) {
+            // two columns per 16-byte shared-memory load
+            double s2[2] = {0.0, 0.0};
+#pragma unroll
+            for (int r = 0; r < 15; ++r) {
+                const double2 v = *reinterpret_cast<const double2*>(sJ + r * 32 + c2);
+                s2[0] += mine[r] * v.x;
+                s2[1] += mine[r] * v.y;
+            }
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int c = c2 + h;
+                double s = s2[h];
+                const int cf = c % 15;
+                if (cf < 6) {   // pose column: wheel (both frames) and ground (frame b) terms
+                    const int cw = (c < 15 ? 0 : 6) + cf;
+                    s += w0 * sW[cw] + w1 * sW[16 + cw] + w2 * sW[32 + cw];
+                    if (c >= 15) s += m * (jp * sG[cf] + jq * sG[8 + cf]);
+                }
+                if (c >= 15 && prior_lane && !col_const(mb, cf)) {
+                    double ps = 0.0;
+                    for (int r = 0; r < 15; ++r) ps += PJ[r * 15 + fl] * PJ[r * 15 + cf];
+                    s += ps;
+                }
+                out[c * 30 + lane] = s;
             }
         }
+        out[kItemGa + lane] = gsum;
     }
     cost = warp_sum(cost);
-    __syncwarp();
-    if (lane < 30) {
-#pragma unroll
-        for (int c = 0; c < 30; ++c) sH[lane * 30 + c] = hrow[c];
-    }
-    __syncwarp();
-    // ---- coalesced write of the record
-    for (int e = lane; e < 675; e += 32) {
-        const int blk = e / 225, r = (e % 225) / 15, c = e % 15;
-        out[e] = sH[(blk == 2 ? 15 + r : r) * 30 + (blk == 0 ? c : 15 + c)];
-    }
-    if (lane < 30) out[675 + lane] = gsum;
     if (lane == 31) out[kItemCost] = cost;
 }
 
@@ -544,8 +552,8 @@ __device__ void window_step(const WindowArgs& a, int w, int lane, double* ws) {
     auto assemble_D = [&](int i, double* dst) {
         for (int e = lane; e < kBlk; e += 32) {
             const int r = e / 15, c = e - r * 15;
-            double v = itm[(size_t)i * kItem + kItemHbb + e];
-            if (i + 1 < n) v += itm[(size_t)(i + 1) * kItem + kItemHaa + e];
+            double v = itm[(size_t)i * kItem + item_hbb(r, c)];
+            if (i + 1 < n) v += itm[(size_t)(i + 1) * kItem + item_haa(r, c)];
             v += laser_own(i, r, c);
             if (i == 0) v += laser_ref_own(r, c);
             dst[e] = v;
@@ -553,8 +561,8 @@ __device__ void window_step(const WindowArgs& a, int w, int lane, double* ws) {
         __syncwarp();
     };
     auto diag_H = [&](int f, int c) -> double {
-        double v = itm[(size_t)f * kItem + kItemHbb + c * 16];
-        if (f + 1 < n) v += itm[(size_t)(f + 1) * kItem + kItemHaa + c * 16];
+        double v = itm[(size_t)f * kItem + item_hbb(c, c)];
+        if (f + 1 < n) v += itm[(size_t)(f + 1) * kItem + item_haa(c, c)];
         v += laser_own(f, c, c);
         if (f == 0) v += laser_ref_own(c, c);
         return v;
@@ -571,7 +579,7 @@ __device__ void window_step(const WindowArgs& a, int w, int lane, double* ws) {
             for (int e = lane; e < kBlk; e += 32) H[(size_t)(15 * i + e / 15) * dim + 15 * i + e % 15] = Dm[e];
             if (i >= 1)
                 for (int e = lane; e < kBlk; e += 32) {
-                    const double v = itm[(size_t)i * kItem + kItemHab + e];  // H(i-1, i)
+                    const double v = itm[(size_t)i * kItem + item_hab(e / 15, e % 15)];  // H(i-1, i)
                     H[(size_t)(15 * (i - 1) + e / 15) * dim + 15 * i + e % 15] += v;
                     H[(size_t)(15 * i + e % 15) * dim + 15 * (i - 1) + e / 15] += v;
                 }
@@ -601,7 +609,7 @@ __device__ void window_step(const WindowArgs& a, int w, int lane, double* ws) {
         for (int i = 0; i + 1 < n; ++i) {
             assemble_D(i + 1, Cy);
             // Um = H(i+1, i) = H(i, i+1)^T
-            for (int e = lane; e < kBlk; e += 32) Um[e] = itm[(size_t)(i + 1) * kItem + kItemHab + (e % 15) * 15 + e / 15];
+            for (int e = lane; e < kBlk; e += 32) Um[e] = itm[(size_t)(i + 1) * kItem + item_hab(e % 15, e / 15)];
             __syncwarp();
             if (!spd_inverse15(Dm, piv, lane)) st.termination = 5;
             gemm_ab15(Tm, Um, Dm, lane);                 // T = H(i+1,i) Hii^-1
@@ -683,7 +691,7 @@ __device__ void window_step(const WindowArgs& a, int w, int lane, double* ws) {
             const bool cross_i = has_cross(i);
             for (int e = lane; e < kBlk; e += 32) {
                 const int r = e / 15, c = e - r * 15;
-                double v = itm[(size_t)i * kItem + kItemHab + e] * scw[(i - 1) * 15 + r] * scw[i * 15 + c];
+                double v = itm[(size_t)i * kItem + item_hab(r, c)] * scw[(i - 1) * 15 + r] * scw[i * 15 + c];
                 if (ARROW && i == 1) {
                     if (have_wc) v += Wm[e];
                     if (cross_i && r < 6 && c < 6 && !is_const(0, r) && !is_const(1, c)) v += cross_entry(1, r, c) * scw[r] * scw[15 + c];
