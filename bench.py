@@ -251,6 +251,8 @@ def run_ours(args):
     value = total_iters_per_step * args.steps / (dev_ms * 1e-3)
     peak, peak_src = measured_peaks()
     scan_ms = prof["scan_ms"] / max(1, prof["scan_launches"])
+    if shard_points:
+        prof["scan_bytes_per_launch"] /= world   # each rank streams its own slice of every frame's points
     achieved = prof["scan_bytes_per_launch"] / (scan_ms * 1e-3) / 1e9 if scan_ms > 0 else 0.0
     result = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
