@@ -17,6 +17,7 @@ OK = 0
 ERR_INVALID_ARG, ERR_NO_DEVICE, ERR_CUDA, ERR_NO_WINDOW, ERR_DOMAIN, ERR_ALLOC = -1, -2, -3, -4, -5, -6
 
 CONST_P, CONST_Q, CONST_V, CONST_BS = 1, 2, 4, 8
+ASSOC_FIXED, ASSOC_NEAREST = 0, 1
 
 TERM_NO_CONVERGENCE = 0
 TERM_CONVERGENCE_FUNCTION = 1
@@ -49,12 +50,14 @@ class Params(C.Structure):
         ("imu_bias_gyro_sigma", C.c_double * 3),
         ("wheel_sigma", C.c_double * 3),
         ("max_iters", C.c_int32),
-        ("reserved0", C.c_int32),
+        ("assoc_mode", C.c_int32),
         ("huber_delta", C.c_double),
         ("function_tolerance", C.c_double),
         ("gradient_tolerance", C.c_double),
         ("parameter_tolerance", C.c_double),
         ("initial_trust_region_radius", C.c_double),
+        ("assoc_gate", C.c_double),
+        ("assoc_max_dist", C.c_double),
     ]
 
 

@@ -41,6 +41,7 @@ struct lvio2d_ctx {
     LMOptions opt;
     char err[512] = {0};
     int sm_count = 148;
+    double huber = 0.0;
 
     // problem
     bool have = false, bound = false;
@@ -56,7 +57,7 @@ struct lvio2d_ctx {
     const int32_t* ref_frame = nullptr; const double* ref_pose = nullptr; const double* imu = nullptr; const double* wheel = nullptr;
     const double* prior_X0 = nullptr; const double* prior_J = nullptr; const uint8_t* const_mask = nullptr;
     // work buffers
-    DevBuf b_x0, b_x, b_xc, b_scale, b_ftab, b_reftab, b_wlines, b_part, b_lb, b_items, b_vec, b_fac, b_state, b_status, b_active, b_active1, b_reduce;
+    DevBuf b_x0, b_x, b_xc, b_scale, b_ftab, b_reftab, b_wlines, b_wlen, b_part, b_lb, b_items, b_vec, b_fac, b_state, b_status, b_active, b_active1, b_reduce;
     DevBuf b_tmp[8];
     double* ext_reduce = nullptr; int64_t ext_reduce_count = 0;
     int step_calls = 0;
@@ -127,29 +128,40 @@ cudaEvent_t next_event(std::vector<cudaEvent_t>& pool, size_t& used) {
     return pool[used++];
 }
 
+int scan_row(bool arrow, bool assoc) { return arrow ? kRowFree : (assoc ? kRowTrackAssoc : kRowTrack); }
+
 size_t window_smem_bytes(const lvio2d_ctx* c) { return window_smem_doubles(c->n, c->arrow) * sizeof(double); }
 
 int launch_scan_match(lvio2d_ctx* ctx, int mode = 0) {
     ScanMatchArgs a;
     a.points = ctx->points; a.point_line = ctx->point_line; a.point_weight = ctx->point_weight;
     a.point_offset = ctx->point_offset; a.line_offset = ctx->line_offset;
-    a.wlines = ctx->b_wlines.as<double4>(); a.lines = ctx->lines; a.ref_frame = ctx->ref_frame;
+    a.wlines = ctx->b_wlines.as<double4>(); a.wlen = ctx->b_wlen.as<double>(); a.lines = ctx->lines; a.ref_frame = ctx->ref_frame;
     a.frame_tab = ctx->b_ftab.as<double>(); a.frame_active = (mode == 1 ? ctx->b_active1 : ctx->b_active).as<uint8_t>();
     a.win_status = ctx->b_status.as<int32_t>(); a.partial = ctx->b_part.as<double>();
     a.n_frames = ctx->n; a.tiles = ctx->tiles; a.n_items = ctx->B * ctx->n * ctx->tiles;
     a.line_cap = ctx->line_cap; a.shard_rank = ctx->shard_rank; a.shard_world = ctx->shard_world;
+    a.huber_delta = ctx->huber; a.laser_sqrt_info = ctx->C.laser_sqrt_info;
+    a.assoc_gate = ctx->params.assoc_gate > 0 ? ctx->params.assoc_gate : 0.1;
+    a.assoc_max_dist = ctx->params.assoc_max_dist > 0 ? ctx->params.assoc_max_dist : 0.5;
     if (ctx->N == 0) return LVIO2D_OK;
     const int wpc = 8;
     const int grid = (a.n_items + wpc - 1) / wpc;
-    const size_t smem = (size_t)wpc * ctx->line_cap * (ctx->arrow ? kRowFree : kRowTrack) * sizeof(double);
+    const bool assoc = ctx->params.assoc_mode == LVIO2D_ASSOC_NEAREST;
+    const bool huber = ctx->huber > 0;
+    const size_t smem = (size_t)wpc * ctx->line_cap * scan_row(ctx->arrow, assoc) * sizeof(double);
     if (ctx->profiling) cudaEventRecord(next_event(ctx->ev_scan, ctx->ev_scan_used), ctx->stream);
-#define LAUNCH_SM(RF, HW)                                                                                                \
-    do {                                                                                                                 \
-        CK(cudaFuncSetAttribute(scan_match_kernel<RF, HW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));     \
-        scan_match_kernel<RF, HW><<<grid, wpc * 32, smem, ctx->stream>>>(a);                                             \
+#define LAUNCH_SM(RF, HW, AS, HU)                                                                                            \
+    do {                                                                                                                     \
+        CK(cudaFuncSetAttribute(scan_match_kernel<RF, HW, AS, HU>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        scan_match_kernel<RF, HW, AS, HU><<<grid, wpc * 32, smem, ctx->stream>>>(a);                                         \
     } while (0)
-    if (ctx->arrow) { if (ctx->has_weight) LAUNCH_SM(true, true); else LAUNCH_SM(true, false); }
-    else { if (ctx->has_weight) LAUNCH_SM(false, true); else LAUNCH_SM(false, false); }
+#define DISPATCH_HU(RF, HW, AS) do { if (huber) LAUNCH_SM(RF, HW, AS, true); else LAUNCH_SM(RF, HW, AS, false); } while (0)
+#define DISPATCH_AS(RF, HW) do { if (assoc) DISPATCH_HU(RF, HW, true); else DISPATCH_HU(RF, HW, false); } while (0)
+    if (ctx->arrow) { if (ctx->has_weight) DISPATCH_AS(true, true); else DISPATCH_AS(true, false); }
+    else { if (ctx->has_weight) DISPATCH_AS(false, true); else DISPATCH_AS(false, false); }
+#undef DISPATCH_AS
+#undef DISPATCH_HU
 #undef LAUNCH_SM
     if (ctx->profiling) cudaEventRecord(next_event(ctx->ev_scan, ctx->ev_scan_used), ctx->stream);
     ctx->launches += 1;
@@ -291,7 +303,7 @@ int setup_batch(lvio2d_ctx* ctx, const lvio2d_window_batch* b, bool bind) {
         tiles = (int)std::max<int64_t>(1, std::min<int64_t>(tiles, avg / 64));
         ctx->tiles = tiles;
     }
-    const size_t smem_scan = (size_t)8 * line_cap * (arrow ? kRowFree : kRowTrack) * sizeof(double);
+    const size_t smem_scan = (size_t)8 * line_cap * scan_row(arrow, ctx->params.assoc_mode == LVIO2D_ASSOC_NEAREST) * sizeof(double);
     if (smem_scan > 200 * 1024) return fail(ctx, LVIO2D_ERR_DOMAIN, "local map too large for shared memory");
     if (window_smem_bytes(ctx) > 200 * 1024) return fail(ctx, LVIO2D_ERR_DOMAIN, "n_frames too large for shared memory");
 
@@ -313,7 +325,7 @@ int setup_batch(lvio2d_ctx* ctx, const lvio2d_window_batch* b, bool bind) {
     const size_t ns = (size_t)F * 15 * sizeof(double);
     bool ok = ctx->b_x0.ensure(ns) && ctx->b_x.ensure(ns) && ctx->b_xc.ensure(ns) && ctx->b_scale.ensure(ns) &&
               ctx->b_ftab.ensure((size_t)F * kFrameTab * sizeof(double)) && ctx->b_reftab.ensure((size_t)F * kFrameTab * sizeof(double)) &&
-              ctx->b_wlines.ensure(std::max<size_t>(1, (size_t)ctx->L) * sizeof(double4)) &&
+              ctx->b_wlines.ensure(std::max<size_t>(1, (size_t)ctx->L) * sizeof(double4)) && ctx->b_wlen.ensure(std::max<size_t>(1, (size_t)ctx->L) * sizeof(double)) &&
               ctx->b_part.ensure((size_t)F * ctx->tiles * ctx->npad * sizeof(double)) && ctx->b_lb.ensure((size_t)2 * F * ctx->npad * sizeof(double)) &&
               ctx->b_items.ensure((size_t)2 * F * kItem * sizeof(double)) && ctx->b_vec.ensure((size_t)B * 2 * n * 15 * sizeof(double)) &&
               ctx->b_fac.ensure((size_t)F * 3 * kBlk * sizeof(double)) && ctx->b_state.ensure(sizeof(LMState) * B) &&
@@ -327,7 +339,7 @@ int setup_batch(lvio2d_ctx* ctx, const lvio2d_window_batch* b, bool bind) {
         // world lines of every local map that hangs under an external constant pose
         frame_table_kernel<<<(F + 127) / 128, 128, 0, ctx->stream>>>(ctx->C, ctx->ref_pose, 6, ctx->b_reftab.as<double>(), F);
         world_lines_kernel<<<F, 128, 0, ctx->stream>>>(ctx->lines, ctx->line_offset, ctx->ref_frame,
-                                                       ctx->b_reftab.as<double>(), ctx->b_wlines.as<double4>(), F);
+                                                       ctx->b_reftab.as<double>(), ctx->b_wlines.as<double4>(), ctx->b_wlen.as<double>(), F);
         CK(cudaGetLastError());
     }
     CK(cudaStreamSynchronize(ctx->stream));  // host vectors above go out of scope
@@ -389,6 +401,7 @@ int lvio2d_create(lvio2d_ctx** out, const lvio2d_params* params) {
     ctx->params = *params;
     ctx->C = make_consts(*params);
     ctx->opt = make_opts(*params);
+    ctx->huber = (params->huber_delta > 0 && std::isfinite(params->huber_delta)) ? params->huber_delta : 0.0;
     ctx->sm_count = prop.multiProcessorCount;
     if (cudaSetDevice(ctx->device) != cudaSuccess || cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
         delete ctx;
@@ -404,7 +417,7 @@ void lvio2d_destroy(lvio2d_ctx* ctx) {
     cudaStreamSynchronize(ctx->stream);
     DevBuf* all[] = {&ctx->b_points, &ctx->b_pline, &ctx->b_pweight, &ctx->b_poff, &ctx->b_loff, &ctx->b_lines, &ctx->b_ref, &ctx->b_refpose,
                      &ctx->b_imu, &ctx->b_wheel, &ctx->b_pX0, &ctx->b_pJ, &ctx->b_cmask, &ctx->b_x0, &ctx->b_x, &ctx->b_xc, &ctx->b_scale,
-                     &ctx->b_ftab, &ctx->b_reftab, &ctx->b_wlines, &ctx->b_part, &ctx->b_lb, &ctx->b_items, &ctx->b_vec, &ctx->b_fac, &ctx->b_state,
+                     &ctx->b_ftab, &ctx->b_reftab, &ctx->b_wlines, &ctx->b_wlen, &ctx->b_part, &ctx->b_lb, &ctx->b_items, &ctx->b_vec, &ctx->b_fac, &ctx->b_state,
                      &ctx->b_status, &ctx->b_active, &ctx->b_active1, &ctx->b_reduce};
     for (DevBuf* b : all) b->release();
     for (auto& b : ctx->b_tmp) b.release();

@@ -34,7 +34,8 @@ constexpr int kAccFree = 45;    // [0..14] as above | [15..20] a x bi | [21..26]
 constexpr int kPadTrack = 24;
 constexpr int kPadFree = 48;
 constexpr int kRowTrack = 14;   // f(3) e(9) n(2)
-constexpr int kRowFree = 24;    // + h(3) alpha(3) beta(3) + pad
+constexpr int kRowTrackAssoc = 18;  // + h(3) (foot coordinate along the line, relative to A1) + length
+constexpr int kRowFree = 24;    // + h(3) (relative to A2) alpha(3) beta(3) + length
 
 struct ScanMatchArgs {
     const double2* points;          // [N] scan points in the frame's laser frame
@@ -42,7 +43,8 @@ struct ScanMatchArgs {
     const double* point_weight;     // [N] or nullptr
     const int64_t* point_offset;    // [F+1]
     const int64_t* line_offset;     // [F+1]
-    const double4* wlines;          // [L] (nx, ny, c0, -) world lines, external constant reference pose
+    const double4* wlines;          // [L] (nx, ny, c0, u.A1) world lines, external constant reference pose
+    const double* wlen;             // [L] world length of those lines
     const double4* lines;           // [L] raw (a1x a1y a2x a2y) in the reference laser frame
     const int32_t* ref_frame;       // [F] or nullptr
     const double* frame_tab;        // [F][24] at the evaluation point
@@ -54,6 +56,7 @@ struct ScanMatchArgs {
     int32_t n_items;                // F * tiles
     int32_t line_cap;               // shared-memory rows per warp
     int32_t shard_rank, shard_world;
+    double huber_delta, laser_sqrt_info, assoc_gate, assoc_max_dist;
 };
 
 __device__ __forceinline__ double2 ld_stream_f64x2(const double2* p) {
@@ -97,11 +100,11 @@ struct ReduceScatter<N, 0> {
 // number of values a lane holds after 5 halvings of N
 __host__ __device__ constexpr int halved5(int n) { for (int i = 0; i < 5; ++i) n = (n + 1) / 2; return n; }
 
-template <bool REF_FREE, bool HAS_WEIGHT>
+template <bool REF_FREE, bool HAS_WEIGHT, bool ASSOC, bool HUBER>
 __global__ void __launch_bounds__(256, REF_FREE ? 1 : 2) scan_match_kernel(ScanMatchArgs a) {
     constexpr int NACC = REF_FREE ? kAccFree : kAccTrack;
     constexpr int NPAD = REF_FREE ? kPadFree : kPadTrack;
-    constexpr int ROW = REF_FREE ? kRowFree : kRowTrack;
+    constexpr int ROW = REF_FREE ? kRowFree : (ASSOC ? kRowTrackAssoc : kRowTrack);
     extern __shared__ __align__(16) double smem[];
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
@@ -163,6 +166,13 @@ __global__ void __launch_bounds__(256, REF_FREE ? 1 : 2) scan_match_kernel(ScanM
                 }
                 r[12] = wl.x;
                 r[13] = wl.y;
+                if constexpr (ASSOC) {
+                    const double ux = wl.y, uy = -wl.x;   // n = (-uy, ux)
+                    r[14] = ux * T[0] + uy * T[2];
+                    r[15] = ux * T[1] + uy * T[3];
+                    r[16] = ux * T[4] + uy * T[5] - wl.w;
+                    r[17] = a.wlen[l0 + l];
+                }
             }
         } else {
             const int rf = a.ref_frame[f];
@@ -198,7 +208,7 @@ __global__ void __launch_bounds__(256, REF_FREE ? 1 : 2) scan_match_kernel(ScanM
                 }
                 r[12] = nx;
                 r[13] = ny;
-                r[23] = 0.0;
+                r[23] = len;
             }
         }
     }
@@ -218,6 +228,22 @@ __global__ void __launch_bounds__(256, REF_FREE ? 1 : 2) scan_match_kernel(ScanM
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             if (li[u] < 0) continue;
+            if constexpr (ASSOC) {
+                // nearest line by perpendicular distance among the lines whose extent (+gate) contains the foot
+                int best = -1;
+                double best_d = a.assoc_max_dist;
+                for (int l = 0; l < nl; ++l) {
+                    const double* q = tab + l * ROW;
+                    const double dd = fma(q[0], c[u].x, fma(q[1], c[u].y, q[2]));
+                    double tt = fma(q[14], c[u].x, fma(q[15], c[u].y, q[16]));
+                    const double len = REF_FREE ? q[23] : q[17];
+                    if constexpr (REF_FREE) tt += len;   // h is relative to A2 there
+                    const double ad = fabs(dd);
+                    if (tt >= -a.assoc_gate && tt <= len + a.assoc_gate && ad < best_d) { best_d = ad; best = l; }
+                }
+                if (best < 0) continue;
+                li[u] = best;
+            }
             const double* r = tab + li[u] * ROW;
             const double2 r01 = *reinterpret_cast<const double2*>(r);
             const double2 r23 = *reinterpret_cast<const double2*>(r + 2);
@@ -249,6 +275,23 @@ __global__ void __launch_bounds__(256, REF_FREE ? 1 : 2) scan_match_kernel(ScanM
                 d *= ww; j0 *= ww; j1 *= ww; j2 *= ww; j3 *= ww; j4 *= ww;
                 if constexpr (REF_FREE) { i2 *= ww; i3 *= ww; i4 *= ww; }
             }
+            double cterm;
+            if constexpr (HUBER) {
+                // ceres::HuberLoss on the whitened residual k*|d|: rho' scales J^T J and J^T r, rho replaces r^2
+                const double k = a.laser_sqrt_info;
+                const double q2 = (k * d) * (k * d);
+                if (q2 > a.huber_delta * a.huber_delta) {
+                    const double sq = sqrt(q2);
+                    const double sc = sqrt(a.huber_delta / sq);
+                    cterm = (2.0 * a.huber_delta * sq - a.huber_delta * a.huber_delta) / (k * k);
+                    d *= sc; j0 *= sc; j1 *= sc; j2 *= sc; j3 *= sc; j4 *= sc;
+                    if constexpr (REF_FREE) { i2 *= sc; i3 *= sc; i4 *= sc; }
+                } else {
+                    cterm = d * d;
+                }
+            } else {
+                cterm = d * d;
+            }
             acc[0] = fma(j0, j0, acc[0]); acc[1] = fma(j0, j1, acc[1]); acc[2] = fma(j1, j1, acc[2]);
             acc[3] = fma(j0, j2, acc[3]); acc[4] = fma(j0, j3, acc[4]); acc[5] = fma(j0, j4, acc[5]);
             acc[6] = fma(j1, j2, acc[6]); acc[7] = fma(j1, j3, acc[7]); acc[8] = fma(j1, j4, acc[8]);
@@ -257,7 +300,7 @@ __global__ void __launch_bounds__(256, REF_FREE ? 1 : 2) scan_match_kernel(ScanM
             if constexpr (!REF_FREE) {
                 acc[15] = fma(d, j0, acc[15]); acc[16] = fma(d, j1, acc[16]);
                 acc[17] = fma(d, j2, acc[17]); acc[18] = fma(d, j3, acc[18]); acc[19] = fma(d, j4, acc[19]);
-                acc[20] = fma(d, d, acc[20]);
+                acc[20] += cterm;
             } else {
                 acc[15] = fma(j0, i2, acc[15]); acc[16] = fma(j0, i3, acc[16]); acc[17] = fma(j0, i4, acc[17]);
                 acc[18] = fma(j1, i2, acc[18]); acc[19] = fma(j1, i3, acc[19]); acc[20] = fma(j1, i4, acc[20]);
@@ -269,7 +312,7 @@ __global__ void __launch_bounds__(256, REF_FREE ? 1 : 2) scan_match_kernel(ScanM
                 acc[36] = fma(d, j0, acc[36]); acc[37] = fma(d, j1, acc[37]);
                 acc[38] = fma(d, j2, acc[38]); acc[39] = fma(d, j3, acc[39]); acc[40] = fma(d, j4, acc[40]);
                 acc[41] = fma(d, i2, acc[41]); acc[42] = fma(d, i3, acc[42]); acc[43] = fma(d, i4, acc[43]);
-                acc[44] = fma(d, d, acc[44]);
+                acc[44] += cterm;
             }
         }
     }
@@ -286,7 +329,7 @@ __global__ void __launch_bounds__(256, REF_FREE ? 1 : 2) scan_match_kernel(ScanM
 // world lines for frames whose local map hangs under an external constant reference pose: computed once per
 // set_windows (the reference pose never changes during a solve, solver.cpp:690-691)
 __global__ void world_lines_kernel(const double4* lines, const int64_t* line_offset, const int32_t* ref_frame,
-                                   const double* ref_tab /*[F][24]*/, double4* wlines, int n_frames_total) {
+                                   const double* ref_tab /*[F][24]*/, double4* wlines, double* wlen, int n_frames_total) {
     const int f = blockIdx.x;
     if (f >= n_frames_total) return;
     if (ref_frame && ref_frame[f] >= 0) return;
@@ -297,9 +340,10 @@ __global__ void world_lines_kernel(const double4* lines, const int64_t* line_off
         const double A1x = T[0] * ln.x + T[1] * ln.y + T[4], A1y = T[2] * ln.x + T[3] * ln.y + T[5];
         const double A2x = T[0] * ln.z + T[1] * ln.w + T[4], A2y = T[2] * ln.z + T[3] * ln.w + T[5];
         const double dx = A2x - A1x, dy = A2y - A1y;
-        const double inv = 1.0 / sqrt(dx * dx + dy * dy);
-        const double nx = -dy * inv, ny = dx * inv;
-        wlines[l] = make_double4(nx, ny, nx * A2x + ny * A2y, 0.0);
+        const double len = sqrt(dx * dx + dy * dy), inv = 1.0 / len;
+        const double ux = dx * inv, uy = dy * inv, nx = -uy, ny = ux;
+        wlines[l] = make_double4(nx, ny, nx * A2x + ny * A2y, ux * A1x + uy * A1y);
+        wlen[l] = len;
     }
 }
 

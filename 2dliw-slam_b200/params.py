@@ -90,7 +90,10 @@ def corridor_params(fast_mode=False, max_iters=None, device=0):
     p.wheel_sigma[:] = [0.02, 99999.0, 999.99]
     # ceres default 50; solver.cpp:800-801 lowers it to 10 in fast_mode
     p.max_iters = max_iters if max_iters is not None else (10 if fast_mode else 50)
+    p.assoc_mode = abi.ASSOC_FIXED
     p.huber_delta = 0.0
+    p.assoc_gate = 0.0
+    p.assoc_max_dist = 0.0
     p.function_tolerance = 0.0
     p.gradient_tolerance = 0.0
     p.parameter_tolerance = 0.0

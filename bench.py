@@ -155,6 +155,8 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     device = torch.device("cuda", local_rank)
     P = L.corridor_params(max_iters=MAX_ITERS, device=local_rank)
+    P.assoc_mode = 1 if args.assoc == "nearest" else 0
+    P.huber_delta = args.huber
     ctx = Context(P)
     B = args.windows
     shard_points = args.shard == "points" and world > 1
@@ -259,8 +261,9 @@ def run_ours(args):
         "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
         "scaling": "strong" if shard_points else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {
-            "workload": f"C2: 1081 beams x 30 keyframes, fixed associations, IMU+wheel+ground+prior, {MAX_ITERS} LM iterations "
-                        f"(BASELINE.json configs[1]); {B} windows per GPU per step ({uniq} distinct synthetic windows tiled)",
+            "workload": f"{'C3' if args.assoc == 'nearest' else 'C2'}: 1081 beams x 30 keyframes, {args.assoc} associations, IMU+wheel+ground+prior, {MAX_ITERS} LM iterations "
+                        f"(BASELINE.json configs[{2 if args.assoc == 'nearest' else 1}]); {B} windows per GPU per step ({uniq} distinct synthetic windows tiled)",
+            "association": args.assoc, "huber_delta": args.huber,
             "windows_per_gpu": B, "points_per_window": int(hb.n_points // hb.n_windows), "lm_iterations_per_window": MAX_ITERS,
             "multi_gpu": ("points sharded over ranks, one NCCL all-reduce of the per-frame blocks per iteration" if shard_points
                           else "independent windows per rank, no data-path collective"),
@@ -282,6 +285,8 @@ def run_ours(args):
         },
         "clocks": clocks,
     }
+    if world == 1:
+        result["single_window"] = single_window_latency(P, hb, torch, device)
     if world == 1 and not args.no_cpu:
         result["cpu_baseline"] = cpu_baseline(P, hb, seconds=args.cpu_seconds, threads=1)
     print(json.dumps(result))
@@ -289,26 +294,54 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+def single_window_latency(P, hb, torch, device, reps=20):
+    """The latency-bound figure: ONE C2 window per solve (B = 1), device-resident, 10 LM iterations."""
+    from lvio2d_b200.solver import Context
+
+    one = first_windows(hb, 1)
+    with Context(P) as c:
+        dstruct, keep = to_device_struct(one, torch, device)
+        c.bind_windows(dstruct, keepalive=keep)
+        ext = torch.cuda.ExternalStream(c.stream, device=device)
+        for _ in range(3):
+            c.solve_async()
+        c.sync()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(ext)
+        for _ in range(reps):
+            c.solve_async()
+        e1.record(ext)
+        c.sync()
+        ms = e0.elapsed_time(e1) / reps
+        iters = int(c.get_summaries()["iterations"].sum())
+    return {"value": iters / (ms * 1e-3), "unit": UNIT, "ms_per_solve": ms, "lm_iterations": iters,
+            "note": "one window per launch: launch/latency-bound, the scan data (0.75 MB) lives in L2"}
+
+
+def first_windows(hb, k):
+    from lvio2d_b200 import abi
+
+    n = hb.n_frames
+    a = hb.arrays
+    po, lo = a["point_offset"], a["line_offset"]
+    np_, nl = int(po[k * n]), int(lo[k * n])
+    return abi.HostBatch(k, n, hb.ground_multiplicity, hb.prior_frame,
+                         states=a["states"].reshape(-1, 15)[:k * n], const_mask=a["const_mask"].reshape(-1)[:k * n],
+                         point_offset=po[:k * n + 1], points=a["points"].reshape(-1, 2)[:np_], point_line=a["point_line"].reshape(-1)[:np_],
+                         point_weight=None if a["point_weight"] is None else a["point_weight"].reshape(-1)[:np_],
+                         line_offset=lo[:k * n + 1], lines=a["lines"].reshape(-1, 4)[:nl], ref_frame=a["ref_frame"].reshape(-1)[:k * n],
+                         ref_pose=a["ref_pose"].reshape(-1, 6)[:k * n], imu=a["imu"].reshape(-1, 466)[:k * (n - 1)],
+                         wheel=a["wheel"].reshape(-1, 15)[:k * (n - 1)],
+                         prior_X0=None if a["prior_X0"] is None else a["prior_X0"].reshape(-1, 15)[:k],
+                         prior_J=None if a["prior_J"] is None else a["prior_J"].reshape(-1, 225)[:k])
+
+
 def cpu_baseline(P, hb, seconds, threads):
     """The CPU oracle (port of the reference path) on a bounded sample: the first windows of the same batch."""
     import oracle_lib as O
     from lvio2d_b200 import abi
 
-    n = hb.n_frames
-
-    def sub(k):
-        a = hb.arrays
-        po, lo = a["point_offset"], a["line_offset"]
-        np_, nl = int(po[k * n]), int(lo[k * n])
-        return abi.HostBatch(k, n, hb.ground_multiplicity, hb.prior_frame,
-                             states=a["states"].reshape(-1, 15)[:k * n], const_mask=a["const_mask"].reshape(-1)[:k * n],
-                             point_offset=po[:k * n + 1], points=a["points"].reshape(-1, 2)[:np_], point_line=a["point_line"].reshape(-1)[:np_],
-                             point_weight=None if a["point_weight"] is None else a["point_weight"].reshape(-1)[:np_],
-                             line_offset=lo[:k * n + 1], lines=a["lines"].reshape(-1, 4)[:nl], ref_frame=a["ref_frame"].reshape(-1)[:k * n],
-                             ref_pose=a["ref_pose"].reshape(-1, 6)[:k * n], imu=a["imu"].reshape(-1, 466)[:k * (n - 1)],
-                             wheel=a["wheel"].reshape(-1, 15)[:k * (n - 1)],
-                             prior_X0=None if a["prior_X0"] is None else a["prior_X0"].reshape(-1, 15)[:k],
-                             prior_J=None if a["prior_J"] is None else a["prior_J"].reshape(-1, 225)[:k])
+    sub = lambda k: first_windows(hb, k)
 
     O.build()
     one = sub(1)
@@ -370,6 +403,8 @@ def main():
     ap.add_argument("--windows", type=int, default=4096, help="windows per GPU per step")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--shard", default="windows", choices=["windows", "points"])
+    ap.add_argument("--assoc", default="fixed", choices=["fixed", "nearest"], help="nearest = BASELINE config 3 (in-kernel re-association)")
+    ap.add_argument("--huber", type=float, default=0.0, help="Huber delta on the whitened laser residuals (0 = reference: none)")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()

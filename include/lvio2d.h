@@ -61,6 +61,9 @@ typedef enum lvio2d_status {
 #define LVIO2D_CONST_V 4u
 #define LVIO2D_CONST_BS 8u
 
+#define LVIO2D_ASSOC_FIXED 0
+#define LVIO2D_ASSOC_NEAREST 1
+
 /* termination codes of lvio2d_summary.termination (Ceres TerminationType semantics) */
 #define LVIO2D_TERM_NO_CONVERGENCE 0  /* max_iters reached */
 #define LVIO2D_TERM_CONVERGENCE_FUNCTION 1
@@ -87,13 +90,20 @@ typedef struct lvio2d_params {
     double imu_bias_gyro_sigma[3];
     double wheel_sigma[3];        /* wheel_odom_preintegration.h:19-22 */
     int32_t max_iters;            /* ceres max_num_iterations: 50 default, 10 in fast_mode (solver.cpp:800-801) */
-    int32_t reserved0;
-    double huber_delta;           /* <= 0 or inf: no robust loss = the reference (solver.cpp:635) */
+    int32_t assoc_mode;           /* LVIO2D_ASSOC_FIXED (reference: correspondences frozen before the solve,
+                                     trajectory.cpp:210) or LVIO2D_ASSOC_NEAREST (BASELINE config 3) */
+    double huber_delta;           /* <= 0 or inf: no robust loss = the reference (solver.cpp:635); otherwise Ceres'
+                                     HuberLoss(delta) on every laser point residual */
     /* ceres::Solver::Options defaults the reference never changes; <= 0 selects the default */
     double function_tolerance;    /* 1e-6 */
     double gradient_tolerance;    /* 1e-10 */
     double parameter_tolerance;   /* 1e-8 */
     double initial_trust_region_radius; /* 1e4 */
+    /* LVIO2D_ASSOC_NEAREST: at every evaluation a point with point_line >= 0 is matched to the line of its frame's
+     * local map with the smallest perpendicular distance among the lines whose extent (plus assoc_gate metres at
+     * both ends) contains the point's foot; no such line, or a distance above assoc_max_dist, drops the point. */
+    double assoc_gate;            /* <= 0: 0.1 m */
+    double assoc_max_dist;        /* <= 0: 0.5 m */
 } lvio2d_params;
 
 /* A batch of B independent sliding windows with the same number of frames.  One window is what

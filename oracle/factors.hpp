@@ -11,6 +11,7 @@
 // and auto_diff::compute_res_and_jacobi (src/utilies/common.h:201-217) on Jet<N>.
 #pragma once
 #include <algorithm>
+#include <cmath>
 #include <cstring>
 #include <initializer_list>
 #include <vector>
@@ -30,6 +31,9 @@ struct Params {
     double manifold_q_sqrt_info;  // 1 / manifold_q_sigma
     double Q[12];                 // diagonal of imu_noise::Q: na, nw, nba, nbw (imu_preintegraption.h:30-42)
     double wheel_cov[3];          // diagonal of wheel_noise::wheel_cov
+    double huber_delta;           // <= 0: no loss (the reference)
+    int assoc_mode;               // 0 fixed (the reference), 1 nearest line (BASELINE config 3, an extension)
+    double assoc_gate, assoc_max_dist;
     explicit Params(const lvio2d_params& p) {
         T_imu_to_laser = iso_from_rowmajor_3x4(p.T_imu_to_laser);
         T_imu_to_wheel = iso_from_rowmajor_3x4(p.T_imu_to_wheel);
@@ -37,6 +41,10 @@ struct Params {
         laser_sqrt_info = 1.0 / p.line_to_line_sigma;
         manifold_p_sqrt_info = 1.0 / p.manifold_p_sigma;
         manifold_q_sqrt_info = 1.0 / p.manifold_q_sigma;
+        huber_delta = (p.huber_delta > 0 && std::isfinite(p.huber_delta)) ? p.huber_delta : 0.0;
+        assoc_mode = p.assoc_mode;
+        assoc_gate = p.assoc_gate > 0 ? p.assoc_gate : 0.1;
+        assoc_max_dist = p.assoc_max_dist > 0 ? p.assoc_max_dist : 0.5;
         for (int i = 0; i < 3; ++i) {
             Q[0 + i] = p.imu_noise_acc_sigma[i] * p.imu_noise_acc_sigma[i];
             Q[3 + i] = p.imu_noise_gyro_sigma[i] * p.imu_noise_gyro_sigma[i];

@@ -82,9 +82,35 @@ public:
             if (mode_ == 1) { refs[0].frame = -1; refs[1].frame = -1; }  // only jacobians[2],[3] are kept (solver.cpp:471-472)
             if (!any_free(refs, 4)) continue;
             const double* lines = W_.B->lines + (size_t)W_.l0(j) * 4;
+            const int64_t nl = (W_.B->line_offset ? W_.B->line_offset[W_.f(j) + 1] : 0) - W_.l0(j);
+            // world pose of the laser for the point side and the line side (association only)
+            const Iso3<double> Twj = lie::make_tf<double>(map3(xj), map3(xj + 3)) * P_.T_imu_to_laser;
+            const Iso3<double> Twi = lie::make_tf<double>(map3(xi), map3(xi + 3)) * P_.T_imu_to_laser;
             for (int64_t p = p0; p < p1; ++p) {
-                const int li = W_.B->point_line[p];
+                int li = W_.B->point_line[p];
                 if (li < 0) continue;
+                if (P_.assoc_mode == 1) {
+                    // BASELINE config 3 (extension; the reference freezes correspondences, trajectory.cpp:210): nearest line
+                    // by perpendicular distance among the lines whose extent (+gate) contains the foot of the point
+                    Vec3<double> C = Twj * Vec3<double>(W_.B->points[2 * p], W_.B->points[2 * p + 1], 0.0);
+                    C.z = 0.0;
+                    int best = -1;
+                    double best_d = P_.assoc_max_dist;
+                    for (int64_t l = 0; l < nl; ++l) {
+                        const double* Lr = lines + (size_t)l * 4;
+                        Vec3<double> A1 = Twi * Vec3<double>(Lr[0], Lr[1], 0.0), A2 = Twi * Vec3<double>(Lr[2], Lr[3], 0.0);
+                        A1.z = 0.0; A2.z = 0.0;
+                        const Vec3<double> dlt = A2 - A1;
+                        const double len = norm(dlt);
+                        const Vec3<double> u = dlt / len;
+                        const double t = dot(u, C - A1);
+                        if (t < -P_.assoc_gate || t > len + P_.assoc_gate) continue;
+                        const double d = std::fabs(-u.y * (C.x - A2.x) + u.x * (C.y - A2.y));
+                        if (d < best_d) { best_d = d; best = (int)l; }
+                    }
+                    if (best < 0) continue;
+                    li = best;
+                }
                 const double* L = lines + (size_t)li * 4;
                 const double wgt = W_.B->point_weight ? W_.B->point_weight[p] : 1.0;
                 laser_point_factor fac(&P_, Vec3<double>(L[0], L[1], 0.0), Vec3<double>(L[2], L[3], 0.0),
@@ -95,11 +121,20 @@ public:
                                     [](const laser_point_factor& f, const Jet<12>* const* a, Jet<12>* res) {
                                         f(a[0], a[1], a[2], a[3], res);
                                     });
-                    accumulate(lin, refs, 4, r, J, 1, 12);
                 } else {
                     fac(xi, xi + 3, xj, xj + 3, r);
                 }
-                sumsq += r[0] * r[0];
+                double rho = r[0] * r[0];
+                if (P_.huber_delta > 0 && rho > P_.huber_delta * P_.huber_delta) {
+                    // ceres::HuberLoss + Corrector (rho'' <= 0: residual and Jacobian scaled by sqrt(rho'))
+                    const double sq = std::sqrt(rho);
+                    const double scale = std::sqrt(P_.huber_delta / sq);
+                    rho = 2.0 * P_.huber_delta * sq - P_.huber_delta * P_.huber_delta;
+                    r[0] *= scale;
+                    if (lin) for (int c = 0; c < 12; ++c) J[c] *= scale;
+                }
+                if (lin) accumulate(lin, refs, 4, r, J, 1, 12);
+                sumsq += rho;
             }
         }
         // ---- imu (solver.cpp:701-711) and wheel (solver.cpp:714-723)

@@ -250,3 +250,36 @@ def test_point_sharded_solve_matches_unsharded(oracle, P10):
         got = c.get_states()
         assert np.abs(got - want).max() < 1e-9
         c.close()
+
+
+@pytest.mark.parametrize("case", ["c2_small", "init_beam", "tracking2"])
+@pytest.mark.parametrize("huber,assoc", [(1.5, 0), (0.0, 1), (1.5, 1)])
+def test_huber_and_in_kernel_association_match_oracle(oracle, case, huber, assoc):
+    """The two extensions the north-star names on top of the reference (which has neither: solver.cpp:635,
+    trajectory.cpp:210): Ceres-style Huber loss on the laser residuals and nearest-line re-association at every
+    evaluation (BASELINE config 3).  Parity is against the oracle running the same rules."""
+    from lvio2d_b200.solver import Context
+
+    P = L.corridor_params(max_iters=8)
+    P.huber_delta = huber
+    P.assoc_mode = assoc
+    sb = CASES[case]()
+    hb = oracle.preintegrate_batch(P, sb)
+    with Context(P) as c:
+        c.set_windows(hb)
+        for mode in (0, 1):
+            H, g, cost = c.linearize(mode)
+            oH, og, ocost = oracle.linearize(P, hb, mode=mode)
+            relclose(cost, ocost, 1e-10, "cost")
+            relclose(g, og, 1e-8, "gradient")
+            relclose(H, oH, 1e-8, "hessian")
+        summ = c.solve()
+        got = c.get_states()
+    want, osumm = oracle.solve(P, hb)
+    assert np.array_equal(summ["num_successful_steps"], osumm["num_successful_steps"])
+    relclose(summ["final_cost"], osumm["final_cost"], 1e-8, "final cost")
+    assert np.abs(got - want).max() < 1e-8
+    if huber > 0 and not assoc:
+        # the loss must actually bite on the initial point of these cases
+        P0 = L.corridor_params(max_iters=8)
+        assert oracle.cost(P, hb)[0] < oracle.cost(P0, hb)[0]
