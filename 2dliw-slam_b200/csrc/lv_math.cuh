@@ -51,7 +51,14 @@ LV_HD Dual operator/(Dual x, double s) { const double si = 1.0 / s; return Dual(
 LV_HD double val(double x) { return x; }
 LV_HD double val(Dual x) { return x.a; }
 LV_HD double lv_sqrt(double x) { return sqrt(x); }
-LV_HD Dual lv_sqrt(Dual x) { const double t = sqrt(x.a); return Dual(t, x.d / (2.0 * t)); }
+LV_HD Dual lv_sqrt(Dual x) {
+    const double t = sqrt(x.a);
+#if defined(__CUDA_ARCH__)
+    return Dual(t, x.d * (0.5 * rsqrt(x.a)));   // derivative through the cheaper reciprocal square root
+#else
+    return Dual(t, x.d / (2.0 * t));
+#endif
+}
 LV_HD void lv_sincos(double x, double* s, double* c) {
 #if defined(__CUDA_ARCH__)
     sincos(x, s, c);

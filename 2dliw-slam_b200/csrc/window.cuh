@@ -271,38 +271,40 @@ __global__ void __launch_bounds__(128, 3) factor_kernel(WindowArgs a) {
 // =====================================================================================================
 // warp-cooperative 15x15 kernels on shared memory (lane r owns row r; lanes >= 15 idle)
 
-// In-place inverse of an SPD block by Gauss-Jordan elimination without pivoting, rows in registers.
+// In-place inverse of an SPD block by Gauss-Jordan elimination without pivoting.  30 lanes: lane = (row r = lane & 15,
+// column half h = lane >> 4) keeps 8 (h = 0: columns 0..7) or 7 (h = 1: columns 8..14) entries of its row in registers.
+// Per pivot k the two lanes of row k publish the scaled pivot row, every lane updates its half row.
 // Returns false (uniformly) when a pivot is not positive (the block is not positive definite) or not finite.
 __device__ __noinline__ bool spd_inverse15(double* A, double* piv /* 16 doubles scratch */, int lane) {
-    double row[15];
-    const int r = lane < 15 ? lane : 0;
+    const int r = lane & 15, h = lane >> 4, c0 = h * 8;
+    const bool act = r < 15;
+    double row[8];
 #pragma unroll
-    for (int k = 0; k < 15; ++k) row[k] = A[r * 15 + k];
+    for (int j = 0; j < 8; ++j) row[j] = (act && c0 + j < 15) ? A[r * 15 + c0 + j] : 0.0;
     bool ok = true;
 #pragma unroll
     for (int k = 0; k < 15; ++k) {
-        if (lane == k) {
-            const double p = row[k];
-            const double pinv = 1.0 / p;
+        const int kh = k >> 3, kj = k & 7;                    // which half / register holds column k
+        // the pivot and this row's multiplier live in the half kh: broadcast them
+        const double p = __shfl_sync(0xffffffffu, row[kj], k + 16 * kh);
+        const double f = __shfl_sync(0xffffffffu, row[kj], r + 16 * kh);
+        if (!(p > 0.0) || !isfinite(p)) ok = false;
+        const double pinv = 1.0 / p;
+        if (r == k && act) {
 #pragma unroll
-            for (int j = 0; j < 15; ++j) row[j] = (j == k) ? pinv : row[j] * pinv;
-#pragma unroll
-            for (int j = 0; j < 15; ++j) piv[j] = row[j];
-            piv[15] = p;
+            for (int j = 0; j < 8; ++j) { row[j] = (c0 + j == k) ? pinv : row[j] * pinv; piv[c0 + j] = row[j]; }
         }
         __syncwarp();
-        const double p = piv[15];
-        if (!(p > 0.0) || !isfinite(p)) ok = false;
-        if (lane != k && lane < 15) {
-            const double f = row[k];
+        if (r != k && act) {
+            const double g = f;
 #pragma unroll
-            for (int j = 0; j < 15; ++j) row[j] = (j == k) ? -f * piv[k] : row[j] - f * piv[j];
+            for (int j = 0; j < 8; ++j) row[j] = (c0 + j == k) ? -g * pinv : row[j] - g * piv[c0 + j];
         }
         __syncwarp();
     }
-    if (lane < 15) {
+    if (act) {
 #pragma unroll
-        for (int k = 0; k < 15; ++k) A[lane * 15 + k] = row[k];
+        for (int j = 0; j < 8; ++j) if (c0 + j < 15) A[r * 15 + c0 + j] = row[j];
     }
     __syncwarp();
     return ok;
@@ -671,14 +673,12 @@ __device__ void window_step(const WindowArgs& a, int w, int lane, double* ws) {
         bool ok = true;
         for (int i = lane; i < n * 15; i += 32) sb[i] = is_const(i / 15, i % 15) ? 0.0 : gvec[i] * scw[i];
         __syncwarp();
+        const double inv_radius = 1.0 / st.radius;
         auto scale_damp = [&](int i, double* blkp) {  // A = S H S + diag(clamp(diag(S H S)) / radius); const entries -> identity
             for (int e = lane; e < kBlk; e += 32) {
                 const int r = e / 15, c = e - r * 15;
                 double v = blkp[e] * scw[i * 15 + r] * scw[i * 15 + c];
-                if (r == c) {
-                    if (is_const(i, r)) v = 1.0;
-                    else v += fmin(fmax(v, opt.min_lm_diagonal), opt.max_lm_diagonal) / st.radius;
-                }
+                if (r == c) v = is_const(i, r) ? 1.0 : v + fmin(fmax(v, opt.min_lm_diagonal), opt.max_lm_diagonal) * inv_radius;
                 blkp[e] = v;
             }
             __syncwarp();
@@ -768,7 +768,7 @@ __device__ void window_step(const WindowArgs& a, int w, int lane, double* ws) {
                 const double sc = scw[i];
                 const double hs = diag_H(i / 15, i % 15) * sc * sc;
                 sg += stp * gvec[i] * sc;
-                lq += fmin(fmax(hs, opt.min_lm_diagonal), opt.max_lm_diagonal) / st.radius * stp * stp;
+                lq += fmin(fmax(hs, opt.min_lm_diagonal), opt.max_lm_diagonal) * inv_radius * stp * stp;
             }
             sg = warp_sum(sg);
             lq = warp_sum(lq);
