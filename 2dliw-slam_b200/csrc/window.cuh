@@ -106,7 +106,7 @@ __device__ __forceinline__ bool col_const(uint8_t mask, int c) {  // c: column 0
 // =====================================================================================================
 // factor_kernel: per-warp shared memory = blob 480 | J 15x32 | wheel 3x16 | ground 2x8 | prior r 16
 constexpr int kFactorSmem = 480 + 480 + 48 + 16 + 16;
-__global__ void __launch_bounds__(128, 3) factor_kernel(WindowArgs a) {
+__global__ void __launch_bounds__(128, 4) factor_kernel(WindowArgs a) {
     extern __shared__ __align__(16) double smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int n = a.n_frames;
