@@ -512,6 +512,232 @@ LV_HD FrameState<Dual> seed_frame_state(const double* s, int seed /* column 0..1
     return f;
 }
 
+// ------------------------------------------------------------------ closed-form item Jacobians
+// The same derivatives as the dual-number path above, written with the SO(3) right Jacobian
+//   R(theta + d) = R(theta) Exp(J_r(theta) d),   Log(M Exp(e)) = Log(M) + J_r^-1(Log M) e
+// so that the expensive pieces (3 exponentials, 2 logarithms, 3 J_r, 2 J_r^-1) are computed ONCE per item and every
+// warp lane only does a few 3x3 matrix-vector products for its own state column.  The angle-axis parameterisation is
+// additive (so3_parameterization, factor_common.h:40-53), hence the plain d/d(theta) columns.
+// (Ceres differentiates the quaternion formulas with Jets; they are the same functions, see tests.)
+LV_HD M3<double> so3_right_jacobian(const V3<double>& v) {
+    const double t2 = v.x * v.x + v.y * v.y + v.z * v.z, t = sqrt(t2);
+    double a, b;  // J_r = I - a [v]x + b [v]x^2
+    if (t < 0.05) {
+        a = 0.5 - t2 * (1.0 / 24.0) + t2 * t2 * (1.0 / 720.0) - t2 * t2 * t2 * (1.0 / 40320.0);
+        b = 1.0 / 6.0 - t2 * (1.0 / 120.0) + t2 * t2 * (1.0 / 5040.0) - t2 * t2 * t2 * (1.0 / 362880.0);
+    } else {
+        double sh, ch;
+        lv_sincos(0.5 * t, &sh, &ch);
+        a = 2.0 * sh * sh / t2;                 // (1 - cos t) / t^2
+        b = (t - 2.0 * sh * ch) / (t2 * t);     // (t - sin t) / t^3
+    }
+    const double xx = v.x * v.x, yy = v.y * v.y, zz = v.z * v.z, xy = v.x * v.y, xz = v.x * v.z, yz = v.y * v.z;
+    M3<double> J;
+    J.m[0] = 1.0 - b * (yy + zz); J.m[1] = a * v.z + b * xy;    J.m[2] = -a * v.y + b * xz;
+    J.m[3] = -a * v.z + b * xy;   J.m[4] = 1.0 - b * (xx + zz); J.m[5] = a * v.x + b * yz;
+    J.m[6] = a * v.y + b * xz;    J.m[7] = -a * v.x + b * yz;   J.m[8] = 1.0 - b * (xx + yy);
+    return J;
+}
+LV_HD M3<double> so3_right_jacobian_inverse(const V3<double>& v) {
+    const double t2 = v.x * v.x + v.y * v.y + v.z * v.z, t = sqrt(t2);
+    double c;  // J_r^-1 = I + 1/2 [v]x + c [v]x^2
+    if (t < 0.1) {
+        c = 1.0 / 12.0 + t2 * (1.0 / 720.0) + t2 * t2 * (1.0 / 30240.0) + t2 * t2 * t2 * (1.0 / 1209600.0);
+    } else {
+        double sh, ch;
+        lv_sincos(0.5 * t, &sh, &ch);
+        c = 1.0 / t2 - ch / (2.0 * t * sh);     // 1/t^2 - (1 + cos t) / (2 t sin t)
+    }
+    const double xx = v.x * v.x, yy = v.y * v.y, zz = v.z * v.z, xy = v.x * v.y, xz = v.x * v.z, yz = v.y * v.z;
+    M3<double> J;
+    J.m[0] = 1.0 - c * (yy + zz);   J.m[1] = -0.5 * v.z + c * xy;   J.m[2] = 0.5 * v.y + c * xz;
+    J.m[3] = 0.5 * v.z + c * xy;    J.m[4] = 1.0 - c * (xx + zz);   J.m[5] = -0.5 * v.x + c * yz;
+    J.m[6] = -0.5 * v.y + c * xz;   J.m[7] = 0.5 * v.x + c * yz;    J.m[8] = 1.0 - c * (xx + yy);
+    return J;
+}
+
+// shared, per item (plain doubles; lives in shared memory on the device)
+struct ItemShared {
+    double R[3][9];      // R(theta_i), R(theta_j), R(-gamma_hat)
+    double Jr[3][9];     // their right Jacobians
+    double N[9], rg[3], JinvG[9], a1[3], a2[3];   // N = Ri^T Rj, rg = Log(E N), a1 = Ri^T y1, a2 = Ri^T y2
+    double pa[3], pb[3];  // positions of the two frames
+};
+LV_HD void load_m3(const double* s, M3<double>* M) {
+#pragma unroll
+    for (int i = 0; i < 9; ++i) M->m[i] = s[i];
+}
+LV_HD void store_m3(const M3<double>& M, double* d) {
+#pragma unroll
+    for (int i = 0; i < 9; ++i) d[i] = M.m[i];
+}
+LV_HD V3<double> imu_gamma_hat(const double* blob, const double* sa) {
+    const double* X = blob;
+    const double* J = blob + 15;
+    const double dx = sa[12] - X[12], dy = sa[13] - X[13], dz = sa[14] - X[14];
+    return v3<double>(X[6] + (J[6 * 15 + 12] * dx + J[6 * 15 + 13] * dy + J[6 * 15 + 14] * dz),
+                      X[7] + (J[7 * 15 + 12] * dx + J[7 * 15 + 13] * dy + J[7 * 15 + 14] * dz),
+                      X[8] + (J[8 * 15 + 12] * dx + J[8 * 15 + 13] * dy + J[8 * 15 + 14] * dz));
+}
+// phase 1, slot 0/1/2: rotation + right Jacobian of theta_i / theta_j / -gamma_hat
+LV_HD void item_phase1(const double* imu_blob, const double* sa, const double* sb, int slot, ItemShared* S) {
+    V3<double> v;
+    if (slot == 0) v = load3(sa + 3);
+    else if (slot == 1) v = load3(sb + 3);
+    else v = imu_blob ? neg(imu_gamma_hat(imu_blob, sa)) : v3<double>(0.0, 0.0, 0.0);
+    store_m3(exp_so3(v), S->R[slot]);
+    store_m3(so3_right_jacobian(v), S->Jr[slot]);
+}
+// phase 2 (one lane): IMU rotation residual pieces
+LV_HD void item_phase2(const Consts& C, const double* imu_blob, const double* sa, const double* sb, int slot, ItemShared* S) {
+    M3<double> Ri, Rj;
+    load_m3(S->R[0], &Ri);
+    load_m3(S->R[1], &Rj);
+    if (slot == 0) {
+        M3<double> E;
+        load_m3(S->R[2], &E);
+        const M3<double> N = mul_tn(Ri, Rj);
+        const V3<double> rg = log_so3(mul(E, N));
+        store_m3(N, S->N);
+        S->rg[0] = rg.x; S->rg[1] = rg.y; S->rg[2] = rg.z;
+        store_m3(so3_right_jacobian_inverse(rg), S->JinvG);
+        const double Dt = imu_blob ? imu_blob[465] : 0.0;
+        const double gz = C.g;
+        const V3<double> y1 = v3<double>(sb[0] - sa[0] - sa[6] * Dt, sb[1] - sa[1] - sa[7] * Dt, sb[2] - sa[2] + 0.5 * gz * Dt * Dt - sa[8] * Dt);
+        const V3<double> y2 = v3<double>(sb[6] - sa[6], sb[7] - sa[7], sb[8] + gz * Dt - sa[8]);
+        const V3<double> a1 = mul_t(Ri, y1), a2 = mul_t(Ri, y2);
+        S->a1[0] = a1.x; S->a1[1] = a1.y; S->a1[2] = a1.z;
+        S->a2[0] = a2.x; S->a2[1] = a2.y; S->a2[2] = a2.z;
+        S->pa[0] = sa[0]; S->pa[1] = sa[1]; S->pa[2] = sa[2];
+        S->pb[0] = sb[0]; S->pb[1] = sb[1]; S->pb[2] = sb[2];
+    }
+}
+// R as Dual with derivative R [w]x (w = J_r e_k of that rotation), or zero derivative
+LV_HD M3<Dual> seeded_rotation(const double* R, const double* Jr, int k /* 0..2, or -1: no seed */) {
+    M3<Dual> D;
+    if (k < 0) {
+#pragma unroll
+        for (int i = 0; i < 9; ++i) D.m[i] = Dual(R[i]);
+        return D;
+    }
+    const double wx = Jr[k], wy = Jr[3 + k], wz = Jr[6 + k];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        const double r0 = R[r * 3], r1 = R[r * 3 + 1], r2 = R[r * 3 + 2];
+        D.m[r * 3] = Dual(r0, r1 * wz - r2 * wy);
+        D.m[r * 3 + 1] = Dual(r1, r2 * wx - r0 * wz);
+        D.m[r * 3 + 2] = Dual(r2, r0 * wy - r1 * wx);
+    }
+    return D;
+}
+// wheel + ground residuals of the item as duals along state column c (c = 30: values only)
+LV_HD void item_wheel_ground_dual(const Consts& C, const double* wheel_blob, bool ground, const ItemShared& S, int c, Dual* rw, Dual* rg);
+// column c (0..29) of the un-whitened IMU Jacobian (15), the wheel Jacobian (3) and the ground Jacobian (2, frame b)
+LV_HD void item_column(const Consts& C, const double* imu_blob, const double* wheel_blob, bool ground, const ItemShared& S, int c,
+                       double* col_imu, double* col_wheel, double* col_ground) {
+    const int blk = c / 3, k = c % 3;   // 0 p_i 1 q_i 2 v_i 3 ba_i 4 bw_i 5 p_j 6 q_j 7 v_j 8 ba_j 9 bw_j
+#pragma unroll
+    for (int r = 0; r < 15; ++r) col_imu[r] = 0.0;
+    col_wheel[0] = col_wheel[1] = col_wheel[2] = 0.0;
+    col_ground[0] = col_ground[1] = 0.0;
+    M3<double> Ri, Rj;
+    load_m3(S.R[0], &Ri);
+    load_m3(S.R[1], &Rj);
+    // w = column k of the right Jacobian of this lane's rotation (if any)
+    const double* Jr = blk == 1 ? S.Jr[0] : S.Jr[1];
+    const V3<double> w = v3<double>(Jr[k], Jr[3 + k], Jr[6 + k]);
+    const V3<double> riTk = v3<double>(Ri.m[k * 3], Ri.m[k * 3 + 1], Ri.m[k * 3 + 2]);   // column k of Ri^T = row k of Ri
+    if (imu_blob) {
+        const double* J = imu_blob + 15;
+        const double Dt = imu_blob[465];
+        M3<double> JinvG, N;
+        load_m3(S.JinvG, &JinvG);
+        load_m3(S.N, &N);
+        if (blk == 0) { col_imu[0] = riTk.x; col_imu[1] = riTk.y; col_imu[2] = riTk.z; }
+        else if (blk == 5) { col_imu[0] = -riTk.x; col_imu[1] = -riTk.y; col_imu[2] = -riTk.z; }
+        else if (blk == 2) { col_imu[0] = riTk.x * Dt; col_imu[1] = riTk.y * Dt; col_imu[2] = riTk.z * Dt; col_imu[3] = riTk.x; col_imu[4] = riTk.y; col_imu[5] = riTk.z; }
+        else if (blk == 7) { col_imu[3] = -riTk.x; col_imu[4] = -riTk.y; col_imu[5] = -riTk.z; }
+        else if (blk == 3) {
+#pragma unroll
+            for (int r = 0; r < 6; ++r) col_imu[r] = J[r * 15 + 9 + k];
+#pragma unroll
+            for (int r = 0; r < 3; ++r) col_imu[9 + r] = (r == k) ? -1.0 : 0.0;   // static indices keep the column in registers
+        } else if (blk == 8) {
+#pragma unroll
+            for (int r = 0; r < 3; ++r) col_imu[9 + r] = (r == k) ? 1.0 : 0.0;
+        } else if (blk == 9) {
+#pragma unroll
+            for (int r = 0; r < 3; ++r) col_imu[12 + r] = (r == k) ? 1.0 : 0.0;
+        }
+        else if (blk == 1) {
+            // r_alpha = .. - Ri^T y1: d(Ri^T y)/d theta = [Ri^T y]x J_r  ->  column = w x (Ri^T y)
+            const V3<double> a1 = load3(S.a1), a2 = load3(S.a2);
+            const V3<double> c1 = cross(w, a1), c2 = cross(w, a2);
+            col_imu[0] = c1.x; col_imu[1] = c1.y; col_imu[2] = c1.z;
+            col_imu[3] = c2.x; col_imu[4] = c2.y; col_imu[5] = c2.z;
+            const V3<double> g = mul(JinvG, mul_t(N, w));
+            col_imu[6] = -g.x; col_imu[7] = -g.y; col_imu[8] = -g.z;
+        } else if (blk == 6) {
+            const V3<double> g = mul(JinvG, w);
+            col_imu[6] = g.x; col_imu[7] = g.y; col_imu[8] = g.z;
+        } else {  // blk == 4, bw_i
+#pragma unroll
+            for (int r = 0; r < 6; ++r) col_imu[r] = J[r * 15 + 12 + k];
+            M3<double> JrG;
+            load_m3(S.Jr[2], &JrG);
+            const V3<double> dg = v3<double>(J[6 * 15 + 12 + k], J[7 * 15 + 12 + k], J[8 * 15 + 12 + k]);
+            const V3<double> g = mul(JinvG, mul_t(N, mul(JrG, dg)));
+            col_imu[6] = -g.x; col_imu[7] = -g.y; col_imu[8] = -g.z;
+#pragma unroll
+            for (int r = 0; r < 3; ++r) col_imu[12 + r] = (r == k) ? -1.0 : 0.0;
+        }
+    }
+    // wheel and ground involve the extrinsic T_imu_to_wheel, whose rotation block is only approximately orthonormal
+    // (it goes through a non-normalised quaternion at load time, params.cpp:52): differentiate the actual formulas
+    // with duals, seeded with the exact dR/dtheta_k = R [J_r e_k]x of the two (orthonormal) frame rotations.
+    if (wheel_blob || ground) {
+        Dual rw[3], rgd[2];
+        item_wheel_ground_dual(C, wheel_blob, ground, S, c, rw, rgd);
+#pragma unroll
+        for (int r = 0; r < 3; ++r) col_wheel[r] = wheel_blob ? rw[r].d : 0.0;
+        col_ground[0] = ground ? rgd[0].d : 0.0;
+        col_ground[1] = ground ? rgd[1].d : 0.0;
+    }
+}
+// the raw residual values of the item
+LV_HD void item_values(const Consts& C, const double* imu_blob, const double* wheel_blob, bool ground, const ItemShared& S,
+                       const double* sa, const double* sb, double* r_imu, double* r_wheel, double* r_ground) {
+    if (imu_blob) {
+        const double* X = imu_blob;
+        const double* J = imu_blob + 15;
+        const double dax = sa[9] - X[9], day = sa[10] - X[10], daz = sa[11] - X[11];
+        const double dwx = sa[12] - X[12], dwy = sa[13] - X[13], dwz = sa[14] - X[14];
+#pragma unroll
+        for (int k = 0; k < 6; ++k) {
+            const double ab = X[k] + (J[k * 15 + 12] * dwx + J[k * 15 + 13] * dwy + J[k * 15 + 14] * dwz) +
+                              (J[k * 15 + 9] * dax + J[k * 15 + 10] * day + J[k * 15 + 11] * daz);
+            r_imu[k] = ab - (k < 3 ? S.a1[k] : S.a2[k - 3]);
+        }
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { r_imu[6 + k] = S.rg[k]; r_imu[9 + k] = sb[9 + k] - sa[9 + k]; r_imu[12 + k] = sb[12 + k] - sa[12 + k]; }
+    }
+    if (wheel_blob || ground) {
+        Dual rw[3], rgd[2];
+        item_wheel_ground_dual(C, wheel_blob, ground, S, 30, rw, rgd);
+        if (wheel_blob) { r_wheel[0] = rw[0].a; r_wheel[1] = rw[1].a; r_wheel[2] = rw[2].a; }
+        if (ground) { r_ground[0] = rgd[0].a; r_ground[1] = rgd[1].a; }
+    }
+}
+LV_HD void item_wheel_ground_dual(const Consts& C, const double* wheel_blob, bool ground, const ItemShared& S, int c, Dual* rw, Dual* rg) {
+    const int blk = c / 3, k = c % 3;
+    const M3<Dual> Ri = seeded_rotation(S.R[0], S.Jr[0], blk == 1 ? k : -1);
+    const M3<Dual> Rj = seeded_rotation(S.R[1], S.Jr[1], blk == 6 ? k : -1);
+    const V3<Dual> pa = v3<Dual>(Dual(S.pa[0], c == 0 ? 1.0 : 0.0), Dual(S.pa[1], c == 1 ? 1.0 : 0.0), Dual(S.pa[2], c == 2 ? 1.0 : 0.0));
+    const V3<Dual> pb = v3<Dual>(Dual(S.pb[0], c == 15 ? 1.0 : 0.0), Dual(S.pb[1], c == 16 ? 1.0 : 0.0), Dual(S.pb[2], c == 17 ? 1.0 : 0.0));
+    if (wheel_blob) item_wheel<Dual>(C, wheel_blob, pa, pb, Ri, Rj, rw);
+    if (ground) item_ground<Dual>(C, pb, Rj, rg);
+}
+
 // ------------------------------------------------------------------ laser frame table
 // C = P (R(theta_j) (R_il c + t_il) + p_j) restricted to xy is the affine map  C = M c + t  on the 2-D
 // scan point; d C / d theta_k = B_k c + b_k (SURVEY.md verification note).  Layout (24 doubles):

@@ -54,6 +54,21 @@ void lvm_item(const Consts* C, const double* imu_blob, const double* wheel_blob,
         }
     }
 }
+// the closed-form path of factor_kernel: phases 1/2 then one column per "lane"
+void lvm_item_analytic(const Consts* C, const double* imu_blob, const double* wheel_blob, const double* sa, const double* sb, double* r_imu,
+                       double* J_imu /*[15][30]*/, double* r_wheel, double* J_wheel /*[3][30]*/, double* r_ground, double* J_ground /*[2][30]*/) {
+    ItemShared S;
+    for (int slot = 0; slot < 3; ++slot) item_phase1(imu_blob, sa, sb, slot, &S);
+    item_phase2(*C, imu_blob, sa, sb, 0, &S);
+    item_values(*C, imu_blob, wheel_blob, true, S, sa, sb, r_imu, r_wheel, r_ground);
+    for (int c = 0; c < 30; ++c) {
+        double ci[15], cw[3], cg[2];
+        item_column(*C, imu_blob, wheel_blob, true, S, c, ci, cw, cg);
+        for (int k = 0; k < 15; ++k) J_imu[k * 30 + c] = ci[k];
+        for (int k = 0; k < 3; ++k) J_wheel[k * 30 + c] = cw[k];
+        for (int k = 0; k < 2; ++k) J_ground[k * 30 + c] = cg[k];
+    }
+}
 void lvm_frame_table(const Consts* C, const double* pose, double* tab) { laser_frame_table(*C, pose, tab); }
 void lvm_so3_plus(const double* t, const double* d, double* o) { so3_plus(t, d, o); }
 }

@@ -132,18 +132,24 @@ def test_laser_frame_table_reproduces_laser_jacobian(lvm, oracle, params, consts
         np.testing.assert_allclose(want_i, jac[0, 0:6], rtol=1e-9, atol=1e-8 * np.abs(jac).max())
 
 
-def test_unified_item_matches_oracle(lvm, oracle, params, consts):
-    """item_residuals<Dual>: one lane per state column, IMU + wheel + ground sharing the rotations (factor_kernel)."""
-    for _ in range(8):
+@pytest.mark.parametrize("entry", ["lvm_item", "lvm_item_analytic"])
+def test_unified_item_matches_oracle(lvm, oracle, params, consts, entry):
+    """One (frame i-1, frame i) item: IMU + wheel + ground residuals and Jacobians, through the dual-number path
+    (item_residuals<Dual>) and through the closed-form path factor_kernel uses (item_phase1/2 + item_column)."""
+    for trial in range(12):
         blob, _, _ = make_imu_blob(oracle, params)
         steps = np.zeros((2, 7)); steps[:, 0] = 0.05
-        steps[:, 1:4] = [0.7, 0.01, 0.0] + RNG.normal(0, 0.02, (2, 3)); steps[:, 4:7] = [0, 0, 0.3] + RNG.normal(0, 0.02, (2, 3))
+        if trial < 9:
+            steps[:, 1:4] = [0.7, 0.01, 0.0] + RNG.normal(0, 0.02, (2, 3)); steps[:, 4:7] = [0, 0, 0.3] + RNG.normal(0, 0.02, (2, 3))
+        else:   # standing still: the degenerate branches of wheel_factor.h:45-70
+            steps[:, 1:4] = RNG.normal(0, 1e-5, (2, 3)); steps[:, 4:7] = RNG.normal(0, 1e-4, (2, 3))
         wblob = oracle.wheel_preintegrate(params, [0, 2], steps)[0]
         si = np.concatenate([corridor_like_pose(), RNG.normal(0, 0.5, 3), RNG.normal(0, 0.02, 3), RNG.normal(0, 0.002, 3)])
-        sj = si + np.concatenate([RNG.normal(0, 0.05, 3), RNG.normal(0, 0.03, 3), RNG.normal(0, 0.1, 3), RNG.normal(0, 1e-3, 6)])
+        dpose = np.concatenate([RNG.normal(0, 0.05, 3), RNG.normal(0, 0.03, 3)]) if trial < 9 else np.concatenate([RNG.normal(0, 2e-5, 3), RNG.normal(0, 2e-4, 3)])
+        sj = si + np.concatenate([dpose, RNG.normal(0, 0.1, 3), RNG.normal(0, 1e-3, 6)])
         r_imu, J_imu = np.zeros(15), np.zeros((15, 30))
         r_w, J_w, r_g, J_g = np.zeros(3), np.zeros((3, 30)), np.zeros(2), np.zeros((2, 30))
-        lvm.lvm_item(C.byref(consts), d(blob), d(wblob), d(si), d(sj), d(r_imu), d(J_imu), d(r_w), d(J_w), d(r_g), d(J_g))
+        getattr(lvm, entry)(C.byref(consts), d(blob), d(wblob), d(si), d(sj), d(r_imu), d(J_imu), d(r_w), d(J_w), d(r_g), d(J_g))
         S = blob[240:465].reshape(15, 15)
         res, jac = oracle.eval_imu_factor(params, blob, si, sj)
         np.testing.assert_allclose(S @ r_imu, res, rtol=1e-11, atol=1e-12 * np.abs(res).max())
