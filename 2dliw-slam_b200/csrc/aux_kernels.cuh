@@ -99,6 +99,7 @@ __global__ void __launch_bounds__(128) imu_preintegrate_kernel(Consts C, int n_i
         }
         __syncwarp();
         for (int e = lane; e < 225; e += 32) J[e] = T[e];
+        __syncwarp();   // T is rewritten below (racecheck)
         // T = F P
         if (lane < 15) {
             double f[15];
