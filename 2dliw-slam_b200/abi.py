@@ -1,7 +1,7 @@
 """ctypes mirror of include/lvio2d.h (the C ABI of the B200 front-end solver).
 
 Pure declarations: the structs are shared by the product host code (solver.py) and by the test-side
-oracle wrapper (tests/oracle_lib.py) so both sides receive byte-identical inputs.
+checker in tests/ so that both sides receive byte-identical inputs.
 """
 import ctypes as C
 

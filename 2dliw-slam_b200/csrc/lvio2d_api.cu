@@ -62,6 +62,10 @@ struct lvio2d_ctx {
     double* ext_reduce = nullptr; int64_t ext_reduce_count = 0;
     int step_calls = 0;
     bool have_solution = false;
+    // host staging of the small index arrays (kept alive until the next upload so that copies can stay asynchronous)
+    std::vector<int64_t> h_poff, h_loff;
+    std::vector<int32_t> h_rf;
+    std::vector<uint8_t> h_cm, h_active, h_active1;
     // measurement
     bool profiling = false;
     std::vector<cudaEvent_t> ev_scan, ev_win, ev_fac;   // begin/end pairs
@@ -234,7 +238,7 @@ int begin_solve(lvio2d_ctx* ctx, bool from_solution = false) {
     return LVIO2D_OK;
 }
 
-int setup_batch(lvio2d_ctx* ctx, const lvio2d_window_batch* b, bool bind) {
+int setup_batch(lvio2d_ctx* ctx, const lvio2d_window_batch* b, bool bind, bool async = false) {
     if (!ctx || !b) return LVIO2D_ERR_INVALID_ARG;
     if (b->n_windows < 1 || b->n_frames < 1 || !b->states) return fail(ctx, LVIO2D_ERR_INVALID_ARG, "n_windows/n_frames/states");
     if (b->n_frames > 64) return fail(ctx, LVIO2D_ERR_DOMAIN, "n_frames > 64");
@@ -250,9 +254,12 @@ int setup_batch(lvio2d_ctx* ctx, const lvio2d_window_batch* b, bool bind) {
     ctx->has_weight = b->point_weight != nullptr;
 
     // host-side views of the small index arrays (offsets, masks, ref frames) to derive the launch shape
-    std::vector<int64_t> poff(F + 1, 0), loff(F + 1, 0);
-    std::vector<int32_t> rf(F, -1);
-    std::vector<uint8_t> cm(F, 0);
+    // a previous asynchronous upload may still be reading the staging vectors
+    CK(cudaStreamSynchronize(ctx->stream));
+    std::vector<int64_t>&poff = ctx->h_poff, &loff = ctx->h_loff;
+    std::vector<int32_t>& rf = ctx->h_rf;
+    std::vector<uint8_t>& cm = ctx->h_cm;
+    poff.assign(F + 1, 0); loff.assign(F + 1, 0); rf.assign(F, -1); cm.assign(F, 0);
     const bool has_laser = b->point_offset && b->points && b->point_line && b->line_offset && b->lines;
     if (bind) {
         if (has_laser) {
@@ -273,7 +280,8 @@ int setup_batch(lvio2d_ctx* ctx, const lvio2d_window_batch* b, bool bind) {
     ctx->L = has_laser ? loff[F] : 0;
     bool arrow = false;
     int line_cap = 1;
-    std::vector<uint8_t> active(F, 0), active1(F, 0);
+    std::vector<uint8_t>&active = ctx->h_active, &active1 = ctx->h_active1;
+    active.assign(F, 0); active1.assign(F, 0);
     for (int f = 0; f < F; ++f) {
         if (!has_laser) break;
         const int64_t np = poff[f + 1] - poff[f], nl = loff[f + 1] - loff[f];
@@ -342,7 +350,7 @@ int setup_batch(lvio2d_ctx* ctx, const lvio2d_window_batch* b, bool bind) {
                                                        ctx->b_reftab.as<double>(), ctx->b_wlines.as<double4>(), ctx->b_wlen.as<double>(), F);
         CK(cudaGetLastError());
     }
-    CK(cudaStreamSynchronize(ctx->stream));  // host vectors above go out of scope
+    if (!async) CK(cudaStreamSynchronize(ctx->stream));  // synchronous flavour: the caller's buffers are free again on return
     {
         // algorithmic bytes one scan-match launch moves when every active frame is processed
         double pts = 0, lns = 0, frames = 0;
@@ -432,6 +440,7 @@ void* lvio2d_stream(lvio2d_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr
 
 int lvio2d_set_windows(lvio2d_ctx* ctx, const lvio2d_window_batch* host_batch) { return setup_batch(ctx, host_batch, false); }
 int lvio2d_bind_windows(lvio2d_ctx* ctx, const lvio2d_window_batch* device_batch) { return setup_batch(ctx, device_batch, true); }
+int lvio2d_set_windows_async(lvio2d_ctx* ctx, const lvio2d_window_batch* host_batch) { return setup_batch(ctx, host_batch, false, true); }
 
 int lvio2d_reset_states(lvio2d_ctx* ctx, const double* host_states) {
     if (!ctx || !host_states) return LVIO2D_ERR_INVALID_ARG;
@@ -591,6 +600,14 @@ int lvio2d_get_states(lvio2d_ctx* ctx, double* host_states) {
     CK(cudaSetDevice(ctx->device));
     CK(cudaMemcpyAsync(host_states, ctx->b_x.p, (size_t)ctx->B * ctx->n * 15 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
+    return LVIO2D_OK;
+}
+
+int lvio2d_get_states_async(lvio2d_ctx* ctx, double* host_states) {
+    if (!ctx || !host_states) return LVIO2D_ERR_INVALID_ARG;
+    if (!ctx->have) return fail(ctx, LVIO2D_ERR_NO_WINDOW, "get_states_async");
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaMemcpyAsync(host_states, ctx->b_x.p, (size_t)ctx->B * ctx->n * 15 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     return LVIO2D_OK;
 }
 

@@ -28,7 +28,7 @@ EXPORTS = [
     "lvio2d_get_states", "lvio2d_set_point_shard", "lvio2d_solve_begin", "lvio2d_eval_laser", "lvio2d_reduce_buffer",
     "lvio2d_set_reduce_buffer", "lvio2d_lm_step", "lvio2d_linearize", "lvio2d_marginalize", "lvio2d_imu_preintegrate",
     "lvio2d_wheel_preintegrate", "lvio2d_eval_laser_factor", "lvio2d_eval_imu_factor", "lvio2d_eval_wheel_factor",
-    "lvio2d_eval_ground_factors", "lvio2d_set_profiling", "lvio2d_get_profile",
+    "lvio2d_eval_ground_factors", "lvio2d_set_profiling", "lvio2d_get_profile", "lvio2d_set_windows_async", "lvio2d_get_states_async",
 ]
 
 
@@ -80,6 +80,8 @@ def load_library(path=LIB_PATH):
     lib.lvio2d_eval_wheel_factor.argtypes = [vp] + [dp] * 5
     lib.lvio2d_eval_ground_factors.argtypes = [vp] + [dp] * 3
     lib.lvio2d_set_profiling.argtypes = [vp, C.c_int32]
+    lib.lvio2d_set_windows_async.argtypes = [vp, C.POINTER(abi.WindowBatch)]
+    lib.lvio2d_get_states_async.argtypes = [vp, vp]
     lib.lvio2d_get_profile.argtypes = [vp, dp]
     _lib = lib
     return lib
@@ -138,6 +140,16 @@ class Context:
         s = host_batch.struct()
         self._check(self.lib.lvio2d_set_windows(self._h, C.byref(s)), "lvio2d_set_windows")
         self.n_windows, self.n_frames = host_batch.n_windows, host_batch.n_frames
+
+    def set_windows_async(self, host_batch):
+        """Enqueue the upload only; `host_batch` (pinned) must stay alive and unchanged until sync()."""
+        s = host_batch.struct()
+        self._check(self.lib.lvio2d_set_windows_async(self._h, C.byref(s)), "lvio2d_set_windows_async")
+        self.n_windows, self.n_frames = host_batch.n_windows, host_batch.n_frames
+        self._keep = host_batch
+
+    def get_states_async(self, out):
+        self._check(self.lib.lvio2d_get_states_async(self._h, out.ctypes.data), "lvio2d_get_states_async")
 
     def bind_windows(self, device_struct, keepalive=None):
         """`device_struct`: abi.WindowBatch whose pointers are device pointers; `keepalive` owns the memory."""

@@ -173,6 +173,10 @@ int lvio2d_set_windows(lvio2d_ctx* ctx, const lvio2d_window_batch* host_batch);
 /* zero-copy variant: every pointer of the batch is a device pointer that stays valid until the next
  * set/bind; states are copied into context-owned buffers (they are mutated by solve) */
 int lvio2d_bind_windows(lvio2d_ctx* ctx, const lvio2d_window_batch* device_batch);
+/* asynchronous flavours for pipelining several contexts (host buffers should be pinned): the copies are only
+ * enqueued on lvio2d_stream(); the caller's buffers must stay valid and unchanged until lvio2d_sync() returns */
+int lvio2d_set_windows_async(lvio2d_ctx* ctx, const lvio2d_window_batch* host_batch);
+int lvio2d_get_states_async(lvio2d_ctx* ctx, double* host_states /* [B*n][15] */);
 /* overwrite the states only (same shapes): re-arm a bound batch for another solve */
 int lvio2d_reset_states(lvio2d_ctx* ctx, const double* host_states);
 
