@@ -342,10 +342,12 @@ class Solver:
     The camera path is not supported (`enable_camera: false` in every shipped config).
     """
 
-    def __init__(self, params, fast_mode=False):
+    def __init__(self, params, fast_mode=False, ctx=None):
         self.params = params
         self.fast_mode = bool(fast_mode)
-        self.ctx = Context(params)
+        # `ctx`: any object with Context's set_windows / solve / get_states / marginalize (tests pass a CPU-oracle
+        # stand-in to produce the comparison trajectory; the product default is the CUDA library)
+        self.ctx = ctx if ctx is not None else Context(params)
         self.has_linearized_block = False
         self.linearized_X = None
         self.linearized_jacobians = None

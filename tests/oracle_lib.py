@@ -188,3 +188,30 @@ def marginalize(params, hb, states=None):
 
 def max_threads():
     return int(lib().oracle_max_threads())
+
+
+class OracleContext:
+    """The oracle behind the method names of lvio2d_b200.solver.Context (set_windows / solve / get_states /
+    marginalize), so that tests can run the `Solver` class flow on the CPU restatement and compare trajectories."""
+
+    def __init__(self, params):
+        self.params = params
+        self.hb = None
+        self.states = None
+
+    def set_windows(self, hb):
+        self.hb, self.states = hb, None
+
+    def solve(self, want_summary=True):
+        self.states, summ = solve(self.params, self.hb)
+        return summ
+
+    def get_states(self, out=None):
+        return self.states if self.states is not None else np.array(self.hb["states"], dtype=np.float64)
+
+    def marginalize(self):
+        X0, J, r, _, _ = marginalize(self.params, self.hb, self.states)
+        return X0, J, r
+
+    def close(self):
+        pass
