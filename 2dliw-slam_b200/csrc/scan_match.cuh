@@ -26,6 +26,13 @@
 
 #include "lv_math.cuh"
 
+#ifndef LV_SCAN_U
+#define LV_SCAN_U 4        // batches of 32 points per pipeline stage
+#endif
+#ifndef LV_SCAN_PF
+#define LV_SCAN_PF 0       // L2 prefetch distance in pipeline stages (0 = off)
+#endif
+
 namespace lv {
 
 constexpr int kAccTrack = 21;   // [0..2] aa | [3..8] a x bj | [9..14] bj bj^T (upper) | [15,16] d a | [17..19] d bj | [20] d^2
@@ -126,7 +133,7 @@ __global__ void __launch_bounds__(256, REF_FREE ? 1 : 2) scan_match_kernel(ScanM
 
     // software pipeline: the loads of batch k+1 are in flight while batch k is accumulated; batch 0 is issued
     // before the line table is built
-    constexpr int U = 4;
+    constexpr int U = LV_SCAN_U;
     double2 nc[U];
     int nli[U];
     double nw[U];
@@ -225,6 +232,16 @@ __global__ void __launch_bounds__(256, REF_FREE ? 1 : 2) scan_match_kernel(ScanM
 #pragma unroll
         for (int u = 0; u < U; ++u) { c[u] = nc[u]; li[u] = nli[u]; if constexpr (HAS_WEIGHT) w[u] = nw[u]; }
         issue(base + 32 * U);
+        if constexpr (LV_SCAN_PF > 0) {
+            // pull the stage LV_SCAN_PF stages ahead from HBM into L2: one 128-byte line per lane covers the stage's
+            // points (U*512 B) and line indices (U*128 B) without holding registers
+            const int64_t q = base - lane + (int64_t)32 * U * LV_SCAN_PF;   // first point of that stage
+            if (lane < 4 * U) {            // 8 points per 128-byte line
+                if (q + 8 * lane < pe) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.points + q + 8 * lane));
+            } else if (lane < 5 * U) {     // 32 indices per line
+                if (q + 32 * (lane - 4 * U) < pe) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.point_line + q + 32 * (lane - 4 * U)));
+            }
+        }
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             if (li[u] < 0) continue;

@@ -34,6 +34,13 @@
 #include "lv_math.cuh"
 #include "scan_match.cuh"
 
+#ifndef LV_FACTOR_MINB
+#define LV_FACTOR_MINB 4   // resident CTAs (of 4 warps) per SM the register budget of factor_kernel is sized for
+#endif
+#ifndef LV_FACTOR_ROLL
+#define LV_FACTOR_ROLL 1   // 1: keep the column loop of the J^T J product rolled (smaller instruction footprint)
+#endif
+
 namespace lv {
 
 struct LMState {
@@ -103,10 +110,23 @@ __device__ __forceinline__ bool col_const(uint8_t mask, int c) {  // c: column 0
     return (mask >> blk) & 1;
 }
 
+// asynchronous global -> shared copies (LDGSTS): inputs are fetched while independent arithmetic runs (the IMU blob
+// behind the two exponentials in factor_kernel, the raw blocks of the next frame behind the Gauss-Jordan inverse of
+// the current pivot in window_kernel)
+__device__ __forceinline__ void cp_async8(double* smem_dst, const double* gsrc) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async16(double* smem_dst, const double* gsrc) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
 // =====================================================================================================
 // factor_kernel: per-warp shared memory = blob 480 | J 15x32 | wheel 3x16 | ground 2x8 | prior r 16
-constexpr int kFactorSmem = 480 + 480 + 48 + 16 + 16;
-__global__ void __launch_bounds__(128, 4) factor_kernel(WindowArgs a) {
+constexpr int kFactorSmem = 480 + 480 + 48 + 16 + 16 + 16 + 240;   // ... | wheel blob 16 | prior J 240
+__global__ void __launch_bounds__(128, LV_FACTOR_MINB) factor_kernel(WindowArgs a) {
     extern __shared__ __align__(16) double smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int n = a.n_frames;
@@ -122,6 +142,8 @@ __global__ void __launch_bounds__(128, 4) factor_kernel(WindowArgs a) {
     double* sW = sJ + 480;      // wheel [3][16]: cols 0..11 Jacobian, col 12 residual
     double* sG = sW + 48;       // ground [2][8]: cols 0..5 Jacobian, col 6 residual
     double* sP = sG + 16;       // prior residual [15]
+    double* sWb = sP + 16;      // wheel blob [15]
+    double* sPJ = sWb + 16;     // prior J [225]
     const double* X = a.xc + (size_t)w * n * 15;
     const uint8_t* cm = a.const_mask + (size_t)w * n;
     const uint8_t mb = mode == 1 ? 0 : cm[i];
@@ -135,18 +157,29 @@ __global__ void __launch_bounds__(128, 4) factor_kernel(WindowArgs a) {
     double cost = 0.0;
     // ---- one lane per state column (0..14 frame a, 15..29 frame b), lane 30 carries the values: IMU + wheel +
     // ground of this item evaluated once in dual arithmetic, every lane on the same instruction stream
+    // the constant inputs of this item (IMU blob, wheel blob, prior J) travel to shared memory asynchronously while the
+    // states are seeded and the two exponentials are evaluated
+    const double* PJ = a.prior_J + (size_t)w * kBlk;
     if (imu_on) {
         const double* blob = a.imu + ((size_t)w * (n - 1) + (i - 1)) * 466;
-        for (int k = lane; k < 466; k += 32) sblob[k] = blob[k];
-        __syncwarp();
+        if ((reinterpret_cast<uintptr_t>(blob) & 15) == 0) {
+            for (int k = lane; k < 233; k += 32) cp_async16(sblob + 2 * k, blob + 2 * k);
+        } else {
+            for (int k = lane; k < 466; k += 32) cp_async8(sblob + k, blob + k);
+        }
     }
+    if (wheel_on && lane < 15) cp_async8(sWb + lane, a.wheel + ((size_t)w * (n - 1) + (i - 1)) * 15 + lane);
+    if (prior_on)
+        for (int k = lane; k < kBlk; k += 32) cp_async8(sPJ + k, PJ + k);
     {
-        const double* wblob = wheel_on ? a.wheel + ((size_t)w * (n - 1) + (i - 1)) * 15 : nullptr;
+        const double* wblob = wheel_on ? sWb : nullptr;
         const FrameState<Dual> fa_ = seed_frame_state(xa, lane < 15 ? lane : -1);
         const FrameState<Dual> fb_ = seed_frame_state(xb, (lane >= 15 && lane < 30) ? lane - 15 : -1);
         const M3<Dual> Rj = exp_so3(fb_.th);
         M3<Dual> Ri;
         if (imu_on || wheel_on) Ri = exp_so3(fa_.th);
+        cp_async_wait_all();
+        __syncwarp();
         const bool value_lane = lane == 30;
         const bool dead = lane < 30 && col_const(lane < 15 ? ma : mb, lane % 15);
         if (imu_on) {
@@ -195,7 +228,7 @@ __global__ void __launch_bounds__(128, 4) factor_kernel(WindowArgs a) {
         }
     }
     // ---- prior of frame i: r = J (x - X0)
-    const double* PJ = a.prior_J + (size_t)w * kBlk;
+    PJ = sPJ;
     if (prior_on) {
         if (lane < 15) {
             const double* X0 = a.prior_X0 + (size_t)w * 15;
@@ -234,7 +267,11 @@ __global__ void __launch_bounds__(128, 4) factor_kernel(WindowArgs a) {
             for (int r = 0; r < 15; ++r) gs += PJ[r * 15 + fl] * sP[r];
             gsum += gs;
         }
+#if LV_FACTOR_ROLL
+#pragma unroll 1
+#else
 #pragma unroll
+#endif
         for (int c2 = 0; c2 < 30; c2 += 2) {
             // two columns per 16-byte shared-memory load
             double s2[2] = {0.0, 0.0};
@@ -366,8 +403,9 @@ __device__ __forceinline__ void copy_blk(double* dst, const double* src, int lan
     for (int i = lane; i < kBlk; i += 32) dst[i] = src[i];
 }
 
-// per-warp shared memory of window_kernel (doubles): 4 blocks (+3 for the arrow topology) + pivot row + rhs [n][15]
-__host__ __device__ inline size_t window_smem_doubles(int n, bool arrow) { return (arrow ? 7 : 4) * kBlk + 16 + (size_t)n * 15 + 16; }
+// per-warp shared memory of window_kernel (doubles): 4 blocks (+3 for the arrow topology) + pivot row + one frame's
+// laser block + rhs [n][15]
+__host__ __device__ inline size_t window_smem_doubles(int n, bool arrow) { return (arrow ? 7 : 4) * kBlk + 16 + 48 + (size_t)n * 15 + 16; }
 
 // ---------------------------------------------------------------------------------------------------
 template <bool ARROW>
@@ -389,7 +427,8 @@ __device__ void window_step(const WindowArgs& a, int w, int lane, double* ws) {
     double* Tp = ws + 5 * kBlk;       // T' = W Dinv
     double* D0 = ws + 6 * kBlk;       // accumulated updates of D_0
     double* piv = ws + (ARROW ? 7 : 4) * kBlk;  // 16
-    double* sb = piv + 16;            // rhs / solution [n][15]
+    double* slb = piv + 16;           // laser block of the frame being assembled [NPAD]
+    double* sb = slb + 48;            // rhs / solution [n][15]
 
     double* x = a.x + (size_t)w * n * 15;
     double* xc = a.xc + (size_t)w * n * 15;
@@ -404,15 +443,37 @@ __device__ void window_step(const WindowArgs& a, int w, int lane, double* ws) {
 
     // ---- (1) candidate laser blocks: sum the tiles in a fixed order; candidate cost
     double csum = 0.0;
-    for (int idx = lane; idx < n * NPAD; idx += 32) {
-        const int f = idx / NPAD, k = idx - f * NPAD;
-        double s = 0.0;
-        if (fa[f]) {
-            const double* p = a.partial + ((size_t)(w * n + f) * a.tiles) * NPAD + k;
-            for (int t = 0; t < a.tiles; ++t) s += p[(size_t)t * NPAD];
+    if (a.tiles == 1) {
+        // one tile per frame (the batched shape): 4 independent loads per lane in flight
+        const double* pw = a.partial + (size_t)w * n * NPAD;
+        for (int i0 = lane; i0 < n * NPAD; i0 += 128) {
+            double v[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int idx = i0 + 32 * q;
+                v[q] = (idx < n * NPAD && fa[idx / NPAD]) ? pw[idx] : 0.0;
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int idx = i0 + 32 * q;
+                if (idx < n * NPAD) {
+                    const double s = 0.0 + v[q];
+                    lb_c[idx] = s;
+                    if (idx % NPAD == ICOST) csum += lsq * s;
+                }
+            }
         }
-        lb_c[idx] = s;
-        if (k == ICOST) csum += lsq * s;
+    } else {
+        for (int idx = lane; idx < n * NPAD; idx += 32) {
+            const int f = idx / NPAD, k = idx - f * NPAD;
+            double s = 0.0;
+            if (fa[f]) {
+                const double* p = a.partial + ((size_t)(w * n + f) * a.tiles) * NPAD + k;
+                for (int t = 0; t < a.tiles; ++t) s += p[(size_t)t * NPAD];
+            }
+            lb_c[idx] = s;
+            if (k == ICOST) csum += lsq * s;
+        }
     }
     for (int f = lane; f < n; f += 32) csum += it_c[(size_t)f * kItem + kItemCost];
     double cand_cost = 0.5 * warp_sum(csum);
@@ -426,18 +487,38 @@ __device__ void window_step(const WindowArgs& a, int w, int lane, double* ws) {
         st.initial_cost = cand_cost;
         accepted = true;
         double s = 0.0;
-        for (int i = lane; i < n * 15; i += 32) {
-            const double v = xc[i];
-            x[i] = v;
-            if (!is_const(i / 15, i % 15)) s += v * v;
+        for (int i0 = lane; i0 < n * 15; i0 += 128) {
+            double v[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) v[q] = (i0 + 32 * q < n * 15) ? xc[i0 + 32 * q] : 0.0;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int i = i0 + 32 * q;
+                if (i < n * 15) {
+                    x[i] = v[q];
+                    if (!is_const(i / 15, i % 15)) s += v[q] * v[q];
+                }
+            }
         }
         st.x_norm = sqrt(warp_sum(s));
         st.last_success = 1;
     } else {
         if (!isfinite(cand_cost)) cand_cost = 1.7976931348623157e308;
         double s = 0.0;
-        for (int i = lane; i < n * 15; i += 32)
-            if (!is_const(i / 15, i % 15)) { const double d = x[i] - xc[i]; s += d * d; }
+        for (int i0 = lane; i0 < n * 15; i0 += 128) {
+            double va[4], vb[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const bool in = i0 + 32 * q < n * 15;
+                va[q] = in ? x[i0 + 32 * q] : 0.0;
+                vb[q] = in ? xc[i0 + 32 * q] : 0.0;
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int i = i0 + 32 * q;
+                if (i < n * 15 && !is_const(i / 15, i % 15)) { const double d = va[q] - vb[q]; s += d * d; }
+            }
+        }
         const double step_norm = sqrt(warp_sum(s));
         // ParameterToleranceReached / FunctionToleranceReached come before the step-quality test
         if (step_norm <= opt.parameter_tolerance * (st.x_norm + opt.parameter_tolerance)) {
@@ -451,10 +532,18 @@ __device__ void window_step(const WindowArgs& a, int w, int lane, double* ws) {
                 accepted = rho > opt.min_relative_decrease;
                 if (accepted) {
                     double s2 = 0.0;
-                    for (int i = lane; i < n * 15; i += 32) {
-                        const double v = xc[i];
-                        x[i] = v;
-                        if (!is_const(i / 15, i % 15)) s2 += v * v;
+                    for (int i0 = lane; i0 < n * 15; i0 += 128) {
+                        double v[4];
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) v[q] = (i0 + 32 * q < n * 15) ? xc[i0 + 32 * q] : 0.0;
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const int i = i0 + 32 * q;
+                            if (i < n * 15) {
+                                x[i] = v[q];
+                                if (!is_const(i / 15, i % 15)) s2 += v[q] * v[q];
+                            }
+                        }
                     }
                     st.x_norm = sqrt(warp_sum(s2));
                     st.cost = cand_cost;
@@ -489,15 +578,17 @@ __device__ void window_step(const WindowArgs& a, int w, int lane, double* ws) {
     const double* itm = a.items + ((size_t)st.cur * F + (size_t)w * n) * kItem;
 
     // entry (r, c) of the laser 6x6 own-pose block of frame f, unscaled
-    auto laser_own = [&](int f, int r, int c) -> double {
+    // (blk: the frame's laser block, lb + f * NPAD or its shared-memory copy)
+    auto laser_own_at = [&](const double* blk, int f, int r, int c) -> double {
         if (r == 2 || c == 2 || r > 5 || c > 5 || !fa[f]) return 0.0;
         if (is_const(f, r) || is_const(f, c)) return 0.0;
         int ri = r < 2 ? r : r - 1, ci = c < 2 ? c : c - 1;
         if (ri > ci) { const int t = ri; ri = ci; ci = t; }
         // upper 5x5 in the order aa(3) | a x bj(6) | bj bj(6)
         const int src = (ri < 2 && ci < 2) ? (ri + ci) : (ri < 2 ? 3 + ri * 3 + (ci - 2) : 9 + (ri == 2 ? ci - 2 : (ri == 3 ? ci : 5)));
-        return lsq * lb[f * NPAD + src];
+        return lsq * blk[src];
     };
+    auto laser_own = [&](int f, int r, int c) -> double { return laser_own_at(lb + f * NPAD, f, r, c); };
     auto has_cross = [&](int j) -> bool {
         return ARROW && mode == 0 && j >= 1 && fa[j] && a.ref_frame && a.ref_frame[(size_t)w * n + j] == 0;
     };
@@ -629,9 +720,24 @@ __device__ void window_step(const WindowArgs& a, int w, int lane, double* ws) {
 
     // ---- gradient tolerance: |x - Plus(x, -g)|_inf (only after a successful step); gradient kept for the step
     double* gvec = a.vec + (size_t)w * 2 * n * 15;
+    double* dvec = gvec + n * 15;   // unscaled diagonal of H at the accepted point
     {
         double mx = 0.0;
-        for (int i = lane; i < n * 15; i += 32) gvec[i] = grad(i / 15, i % 15);
+        for (int i0 = lane; i0 < n * 15; i0 += 128) {
+            double g[4], dg[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int i = i0 + 32 * q;
+                const bool in = i < n * 15;
+                g[q] = in ? grad(i / 15, i % 15) : 0.0;
+                dg[q] = in ? diag_H(i / 15, i % 15) : 0.0;
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int i = i0 + 32 * q;
+                if (i < n * 15) { gvec[i] = g[q]; dvec[i] = dg[q]; }
+            }
+        }
         __syncwarp();
         if (st.last_success) {
             for (int f = lane; f < n; f += 32) {
@@ -660,7 +766,7 @@ __device__ void window_step(const WindowArgs& a, int w, int lane, double* ws) {
     double* scw = a.scale + (size_t)w * n * 15;
     if (st.iteration == 0) {
         for (int i = lane; i < n * 15; i += 32)
-            scw[i] = is_const(i / 15, i % 15) ? 1.0 : 1.0 / (1.0 + sqrt(diag_H(i / 15, i % 15)));
+            scw[i] = is_const(i / 15, i % 15) ? 1.0 : 1.0 / (1.0 + sqrt(dvec[i]));
         __syncwarp();
     }
 
@@ -683,21 +789,27 @@ __device__ void window_step(const WindowArgs& a, int w, int lane, double* ws) {
             }
             __syncwarp();
         };
-        assemble_D(n - 1, Dm);
-        scale_damp(n - 1, Dm);
+        // Dm/Cy swap roles every frame (pivot block <-> block being assembled)
+        double* Dp = Dm;
+        double* Cp = Cy;
+        assemble_D(n - 1, Dp);
+        scale_damp(n - 1, Dp);
         bool have_wc = false, have_d0 = false;
         for (int i = n - 1; i >= 1; --i) {
-            // coupling U = H(i-1, i), scaled (+ laser cross block / carried fill-in when i == 1: H(0,1) is also the arrow block)
-            const bool cross_i = has_cross(i);
-            for (int e = lane; e < kBlk; e += 32) {
-                const int r = e / 15, c = e - r * 15;
-                double v = itm[(size_t)i * kItem + item_hab(r, c)] * scw[(i - 1) * 15 + r] * scw[i * 15 + c];
-                if (ARROW && i == 1) {
-                    if (have_wc) v += Wm[e];
-                    if (cross_i && r < 6 && c < 6 && !is_const(0, r) && !is_const(1, c)) v += cross_entry(1, r, c) * scw[r] * scw[15 + c];
+            // raw blocks of this elimination step, fetched asynchronously while the pivot is inverted:
+            // Um <- H(i-1, i) of item i, Cp <- hbb of item i-1, Tm <- haa of item i  (D_{i-1} = hbb + haa + laser)
+            {
+                const double* it_i = itm + (size_t)i * kItem;
+                const double* it_p = itm + (size_t)(i - 1) * kItem;
+                for (int e = lane; e < kBlk; e += 32) {
+                    const int r = e / 15, c = e - r * 15;
+                    cp_async8(Um + e, it_i + item_hab(r, c));
+                    cp_async8(Cp + e, it_p + item_hbb(r, c));
+                    cp_async8(Tm + e, it_i + item_haa(r, c));
                 }
-                Um[e] = v;
+                for (int e = lane; e < NPAD; e += 32) cp_async8(slb + e, lb + (i - 1) * NPAD + e);
             }
+            const bool cross_i = has_cross(i);
             bool arrow_i = false;
             if (ARROW && i >= 2) {
                 arrow_i = have_wc || cross_i;
@@ -710,10 +822,32 @@ __device__ void window_step(const WindowArgs& a, int w, int lane, double* ws) {
                     }
             }
             __syncwarp();
-            if (!spd_inverse15(Dm, piv, lane)) { ok = false; break; }
-            gemm_ab15(Tm, Um, Dm, lane);                                   // T = U Dinv
-            if (ARROW && arrow_i) gemm_ab15(Tp, Wm, Dm, lane);             // T' = W Dinv
-            gemv15<false, false>(piv, Dm, sb + 15 * i, lane);              // c_i = Dinv b_i
+            const bool inv_ok = spd_inverse15(Dp, piv, lane);
+            cp_async_wait_all();
+            __syncwarp();
+            if (!inv_ok) { ok = false; break; }
+            // coupling U = H(i-1, i), scaled (+ laser cross block / carried fill-in when i == 1: H(0,1) is also the arrow
+            // block); D_{i-1} assembled, scaled and damped
+            for (int e = lane; e < kBlk; e += 32) {
+                const int r = e / 15, c = e - r * 15;
+                double v = Um[e] * scw[(i - 1) * 15 + r] * scw[i * 15 + c];
+                if (ARROW && i == 1) {
+                    if (have_wc) v += Wm[e];
+                    if (cross_i && r < 6 && c < 6 && !is_const(0, r) && !is_const(1, c)) v += cross_entry(1, r, c) * scw[r] * scw[15 + c];
+                }
+                Um[e] = v;
+                double dv = Cp[e];
+                dv += Tm[e];
+                dv += laser_own_at(slb, i - 1, r, c);
+                if (i - 1 == 0) dv += laser_ref_own(r, c);
+                dv = dv * scw[(i - 1) * 15 + r] * scw[(i - 1) * 15 + c];
+                if (r == c) dv = is_const(i - 1, r) ? 1.0 : dv + fmin(fmax(dv, opt.min_lm_diagonal), opt.max_lm_diagonal) * inv_radius;
+                Cp[e] = dv;
+            }
+            __syncwarp();
+            gemm_ab15(Tm, Um, Dp, lane);                                   // T = U Dinv
+            if (ARROW && arrow_i) gemm_ab15(Tp, Wm, Dp, lane);             // T' = W Dinv
+            gemv15<false, false>(piv, Dp, sb + 15 * i, lane);              // c_i = Dinv b_i
             if (lane < 15) sb[15 * i + lane] = piv[lane];
             __syncwarp();
             for (int e = lane; e < kBlk; e += 32) {
@@ -722,39 +856,43 @@ __device__ void window_step(const WindowArgs& a, int w, int lane, double* ws) {
             }
             gemv15<false, true>(sb + 15 * (i - 1), Um, sb + 15 * i, lane);  // b_{i-1} -= U c_i
             if (ARROW && arrow_i) gemv15<false, true>(sb, Wm, sb + 15 * i, lane);
-            assemble_D(i - 1, Cy);
-            scale_damp(i - 1, Cy);
-            gemm_sub_abt15(Cy, Tm, Um, lane);                               // D_{i-1} -= T U^T
+            gemm_sub_abt15(Cp, Tm, Um, lane);                               // D_{i-1} -= T U^T
             if (ARROW && arrow_i) {
                 if (!have_d0) { for (int e = lane; e < kBlk; e += 32) D0[e] = 0.0; __syncwarp(); have_d0 = true; }
                 gemm_sub_abt15(D0, Tp, Wm, lane);                           // D_0 -= T' W^T
-                // fill-in for frame i-1: H(0, i-1) = -T' U^T   (Wm is free again after this)
-                for (int e = lane; e < kBlk; e += 32) Dm[e] = 0.0;
+                // fill-in for frame i-1: H(0, i-1) = -T' U^T   (Wm is free again after this; the old pivot block is scratch)
+                for (int e = lane; e < kBlk; e += 32) Dp[e] = 0.0;
                 __syncwarp();
-                gemm_sub_abt15(Dm, Tp, Um, lane);
-                copy_blk(Wm, Dm, lane);
+                gemm_sub_abt15(Dp, Tp, Um, lane);
+                copy_blk(Wm, Dp, lane);
                 __syncwarp();
                 have_wc = true;
             } else if (ARROW) {
                 have_wc = false;
             }
             if (ARROW && i - 1 == 0 && have_d0) {
-                for (int e = lane; e < kBlk; e += 32) Cy[e] += D0[e];
+                for (int e = lane; e < kBlk; e += 32) Cp[e] += D0[e];
                 __syncwarp();
             }
-            copy_blk(Dm, Cy, lane);
-            __syncwarp();
+            { double* t = Dp; Dp = Cp; Cp = t; }
         }
-        if (ok) ok = spd_inverse15(Dm, piv, lane);
+        if (ok) ok = spd_inverse15(Dp, piv, lane);
         if (ok) {
-            gemv15<false, false>(piv, Dm, sb, lane);   // y_0 = D0inv b_0
+            gemv15<false, false>(piv, Dp, sb, lane);   // y_0 = D0inv b_0
             if (lane < 15) sb[lane] = piv[lane];
             __syncwarp();
+            // T_i (and T'_i) come back from global memory one frame ahead of their use (Tm / Um alternate)
+            auto fetch_T = [&](int i, double* dstT) {
+                for (int e = lane; e < kBlk; e += 32) cp_async8(dstT + e, facw + (size_t)i * 3 * kBlk + e);
+            };
+            if (n > 1) fetch_T(1, Tm);
             for (int i = 1; i < n; ++i) {
-                copy_blk(Tm, facw + (size_t)i * 3 * kBlk, lane);
-                if (ARROW && i >= 2) copy_blk(Tp, facw + (size_t)i * 3 * kBlk + kBlk, lane);
+                double* Tc = (i & 1) ? Tm : Um;
+                if (ARROW && i >= 2) for (int e = lane; e < kBlk; e += 32) cp_async8(Tp + e, facw + (size_t)i * 3 * kBlk + kBlk + e);
+                cp_async_wait_all();
                 __syncwarp();
-                gemv15<true, true>(sb + 15 * i, Tm, sb + 15 * (i - 1), lane);   // y_i = c_i - T^T y_{i-1} - T'^T y_0
+                if (i + 1 < n) fetch_T(i + 1, (i & 1) ? Um : Tm);
+                gemv15<true, true>(sb + 15 * i, Tc, sb + 15 * (i - 1), lane);   // y_i = c_i - T^T y_{i-1} - T'^T y_0
                 if (ARROW && i >= 2) gemv15<true, true>(sb + 15 * i, Tp, sb, lane);
             }
             // step = -y ; model_cost_change = -1/2 step.gs + 1/2 sum lm_diag step^2
@@ -766,7 +904,7 @@ __device__ void window_step(const WindowArgs& a, int w, int lane, double* ws) {
                 sb[i] = stp;
                 if (!isfinite(stp)) finite = false;
                 const double sc = scw[i];
-                const double hs = diag_H(i / 15, i % 15) * sc * sc;
+                const double hs = dvec[i] * sc * sc;
                 sg += stp * gvec[i] * sc;
                 lq += fmin(fmax(hs, opt.min_lm_diagonal), opt.max_lm_diagonal) * inv_radius * stp * stp;
             }

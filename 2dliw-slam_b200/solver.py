@@ -19,7 +19,8 @@ import numpy as np
 from . import abi
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "liblvio2d.so")
+# LVIO2D_LIB: another build of the same CUDA library (kernel-variant experiments, scripts/variants.sh)
+LIB_PATH = os.environ.get("LVIO2D_LIB") or os.path.join(_HERE, "csrc", "liblvio2d.so")
 _lib = None
 
 EXPORTS = [
