@@ -56,7 +56,7 @@ struct ScanMatchArgs {
     const int32_t* ref_frame;       // [F] or nullptr
     const double* frame_tab;        // [F][24] at the evaluation point
     const uint8_t* frame_active;    // [F] 1 when the frame's laser residual block is part of the program
-    const int32_t* win_status;      // [B] 0 = window still iterating (nullptr: all)
+    const int32_t* win_status;      // [B] 0 = window still iterating
     double* partial;                // [F][tiles][pad]
     int32_t n_frames;               // frames per window
     int32_t tiles;
@@ -119,12 +119,26 @@ __global__ void __launch_bounds__(256, REF_FREE ? 1 : 2) scan_match_kernel(ScanM
     if (item >= a.n_items) return;
     const int f = item / a.tiles;
     const int tile = item - f * a.tiles;
-    if (a.win_status && a.win_status[f / a.n_frames] != 0) return;
-    if (!a.frame_active[f]) return;
+    // every scalar this warp depends on is requested before the first one is tested, so the prologue costs two
+    // dependent DRAM round trips (these scalars -> points / lines) instead of four
+    // (volatile asm keeps the compiler from sinking the loads below the early-exit tests)
+    int wstat = 0, fact;
+    int64_t p0, p1, l0, l1;
+    asm volatile("ld.global.s32 %0, [%1];" : "=r"(wstat) : "l"(a.win_status + f / a.n_frames));
+    asm volatile("ld.global.u8 %0, [%1];" : "=r"(fact) : "l"(a.frame_active + f));
+    asm volatile("ld.global.s64 %0, [%1];" : "=l"(p0) : "l"(a.point_offset + f));
+    asm volatile("ld.global.s64 %0, [%1];" : "=l"(p1) : "l"(a.point_offset + f + 1));
+    asm volatile("ld.global.s64 %0, [%1];" : "=l"(l0) : "l"(a.line_offset + f));
+    asm volatile("ld.global.s64 %0, [%1];" : "=l"(l1) : "l"(a.line_offset + f + 1));
+    const double* ft = a.frame_tab + (size_t)f * kFrameTab;
+    double T[kFrameTab];
+#pragma unroll
+    for (int i = 0; i < kFrameTab; ++i) T[i] = __ldg(ft + i);
+    if ((wstat != 0) | (fact == 0) | (p1 <= p0) | (l1 < l0)) return;   // (one test on all six: ptxas keeps the loads together)
     double* tab = smem + (size_t)warp * a.line_cap * ROW;
 
     // ---- this warp's slice of the frame: rank shard, then tile
-    const int64_t p0 = a.point_offset[f], cnt = a.point_offset[f + 1] - p0;
+    const int64_t cnt = p1 - p0;
     const int64_t s0 = p0 + (cnt * a.shard_rank) / a.shard_world;
     const int64_t s1 = p0 + (cnt * (a.shard_rank + 1)) / a.shard_world;
     const int64_t per = (s1 - s0 + a.tiles - 1) / a.tiles;
@@ -150,13 +164,8 @@ __global__ void __launch_bounds__(256, REF_FREE ? 1 : 2) scan_match_kernel(ScanM
     issue(pb + lane);
 
     // ---- this frame's table (24 doubles, broadcast loads) and the shared-memory line table
-    const double* ft = a.frame_tab + (size_t)f * kFrameTab;
-    const int64_t l0 = a.line_offset[f];
-    const int nl = (int)(a.line_offset[f + 1] - l0);
+    const int nl = (int)(l1 - l0);
     {
-        double T[kFrameTab];
-#pragma unroll
-        for (int i = 0; i < kFrameTab; ++i) T[i] = __ldg(ft + i);
         if constexpr (!REF_FREE) {
             for (int l = lane; l < nl; l += 32) {
                 const double4 wl = a.wlines[l0 + l];
