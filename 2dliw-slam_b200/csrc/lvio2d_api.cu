@@ -31,6 +31,29 @@ struct DevBuf {
     template <class T> T* as() const { return reinterpret_cast<T*>(p); }
 };
 
+// page-locked host staging array: copies out of it are truly asynchronous (a cudaMemcpyAsync from pageable memory
+// blocks the calling thread until the stream has drained up to it, which serialises chunked uploads with the host)
+template <class T>
+struct PinnedVec {
+    T* p = nullptr;
+    size_t cap = 0, n = 0;
+    bool assign(size_t count, T value) {
+        if (count > cap) {
+            if (p) cudaFreeHost(p);
+            p = nullptr; cap = 0;
+            if (cudaHostAlloc(reinterpret_cast<void**>(&p), std::max<size_t>(count, 64) * sizeof(T), cudaHostAllocDefault) != cudaSuccess) return false;
+            cap = std::max<size_t>(count, 64);
+        }
+        n = count;
+        std::fill(p, p + count, value);
+        return true;
+    }
+    void release() { if (p) cudaFreeHost(p); p = nullptr; cap = n = 0; }
+    T* data() { return p; }
+    T& operator[](size_t i) { return p[i]; }
+    const T& operator[](size_t i) const { return p[i]; }
+};
+
 }  // namespace
 
 struct lvio2d_ctx {
@@ -63,9 +86,9 @@ struct lvio2d_ctx {
     int step_calls = 0;
     bool have_solution = false;
     // host staging of the small index arrays (kept alive until the next upload so that copies can stay asynchronous)
-    std::vector<int64_t> h_poff, h_loff;
-    std::vector<int32_t> h_rf;
-    std::vector<uint8_t> h_cm, h_active, h_active1;
+    PinnedVec<int64_t> h_poff, h_loff;
+    PinnedVec<int32_t> h_rf;
+    PinnedVec<uint8_t> h_cm, h_active, h_active1;
     // measurement
     bool profiling = false;
     std::vector<cudaEvent_t> ev_scan, ev_win, ev_fac;   // begin/end pairs
@@ -256,10 +279,12 @@ int setup_batch(lvio2d_ctx* ctx, const lvio2d_window_batch* b, bool bind, bool a
     // host-side views of the small index arrays (offsets, masks, ref frames) to derive the launch shape
     // a previous asynchronous upload may still be reading the staging vectors
     CK(cudaStreamSynchronize(ctx->stream));
-    std::vector<int64_t>&poff = ctx->h_poff, &loff = ctx->h_loff;
-    std::vector<int32_t>& rf = ctx->h_rf;
-    std::vector<uint8_t>& cm = ctx->h_cm;
-    poff.assign(F + 1, 0); loff.assign(F + 1, 0); rf.assign(F, -1); cm.assign(F, 0);
+    PinnedVec<int64_t>&poff = ctx->h_poff, &loff = ctx->h_loff;
+    PinnedVec<int32_t>& rf = ctx->h_rf;
+    PinnedVec<uint8_t>& cm = ctx->h_cm;
+    PinnedVec<uint8_t>&active = ctx->h_active, &active1 = ctx->h_active1;
+    if (!poff.assign(F + 1, 0) || !loff.assign(F + 1, 0) || !rf.assign(F, -1) || !cm.assign(F, 0) || !active.assign(F, 0) || !active1.assign(F, 0))
+        return fail(ctx, LVIO2D_ERR_ALLOC, "cudaHostAlloc(staging)");
     const bool has_laser = b->point_offset && b->points && b->point_line && b->line_offset && b->lines;
     if (bind) {
         if (has_laser) {
@@ -280,8 +305,6 @@ int setup_batch(lvio2d_ctx* ctx, const lvio2d_window_batch* b, bool bind, bool a
     ctx->L = has_laser ? loff[F] : 0;
     bool arrow = false;
     int line_cap = 1;
-    std::vector<uint8_t>&active = ctx->h_active, &active1 = ctx->h_active1;
-    active.assign(F, 0); active1.assign(F, 0);
     for (int f = 0; f < F; ++f) {
         if (!has_laser) break;
         const int64_t np = poff[f + 1] - poff[f], nl = loff[f + 1] - loff[f];
@@ -429,6 +452,7 @@ void lvio2d_destroy(lvio2d_ctx* ctx) {
                      &ctx->b_status, &ctx->b_active, &ctx->b_active1, &ctx->b_reduce};
     for (DevBuf* b : all) b->release();
     for (auto& b : ctx->b_tmp) b.release();
+    ctx->h_poff.release(); ctx->h_loff.release(); ctx->h_rf.release(); ctx->h_cm.release(); ctx->h_active.release(); ctx->h_active1.release();
     for (auto e : ctx->ev_scan) cudaEventDestroy(e);
     for (auto e : ctx->ev_win) cudaEventDestroy(e);
     for (auto e : ctx->ev_fac) cudaEventDestroy(e);

@@ -29,6 +29,9 @@
 #ifndef LV_SCAN_U
 #define LV_SCAN_U 4        // batches of 32 points per pipeline stage
 #endif
+#ifndef LV_SCAN_EVICT_FIRST
+#define LV_SCAN_EVICT_FIRST 0   // 1: streamed point data is marked evict_first in L2
+#endif
 #ifndef LV_SCAN_PF
 #define LV_SCAN_PF 0       // L2 prefetch distance in pipeline stages (0 = off)
 #endif
@@ -66,19 +69,38 @@ struct ScanMatchArgs {
     double huber_delta, laser_sqrt_info, assoc_gate, assoc_max_dist;
 };
 
-__device__ __forceinline__ double2 ld_stream_f64x2(const double2* p) {
+// streamed (read-once) loads: no L1 allocation, L2 eviction priority evict_first through a cache-hint policy so that the
+// small per-frame metadata, frame tables and tile partials that every launch re-reads stay resident in L2
+__device__ __forceinline__ uint64_t stream_policy() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ double2 ld_stream_f64x2(const double2* p, uint64_t pol) {
     double2 v;
+#if LV_SCAN_EVICT_FIRST
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v2.f64 {%0, %1}, [%2], %3;" : "=d"(v.x), "=d"(v.y) : "l"(p), "l"(pol));
+#else
     asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
+#endif
     return v;
 }
-__device__ __forceinline__ int ld_stream_s32(const int32_t* p) {
+__device__ __forceinline__ int ld_stream_s32(const int32_t* p, uint64_t pol) {
     int v;
+#if LV_SCAN_EVICT_FIRST
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.s32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol));
+#else
     asm volatile("ld.global.nc.L1::no_allocate.s32 %0, [%1];" : "=r"(v) : "l"(p));
+#endif
     return v;
 }
-__device__ __forceinline__ double ld_stream_f64(const double* p) {
+__device__ __forceinline__ double ld_stream_f64(const double* p, uint64_t pol) {
     double v;
+#if LV_SCAN_EVICT_FIRST
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(p), "l"(pol));
+#else
     asm volatile("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(v) : "l"(p));
+#endif
     return v;
 }
 
@@ -151,14 +173,15 @@ __global__ void __launch_bounds__(256, REF_FREE ? 1 : 2) scan_match_kernel(ScanM
     double2 nc[U];
     int nli[U];
     double nw[U];
+    const uint64_t pol = stream_policy();
     auto issue = [&](int64_t base) {
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             const int64_t p = base + 32 * u;
             const bool ok = p < pe;
-            nli[u] = ok ? ld_stream_s32(a.point_line + p) : -1;
-            nc[u] = ok ? ld_stream_f64x2(a.points + p) : make_double2(0.0, 0.0);
-            if constexpr (HAS_WEIGHT) nw[u] = ok ? ld_stream_f64(a.point_weight + p) : 0.0;
+            nli[u] = ok ? ld_stream_s32(a.point_line + p, pol) : -1;
+            nc[u] = ok ? ld_stream_f64x2(a.points + p, pol) : make_double2(0.0, 0.0);
+            if constexpr (HAS_WEIGHT) nw[u] = ok ? ld_stream_f64(a.point_weight + p, pol) : 0.0;
         }
     };
     issue(pb + lane);

@@ -459,7 +459,7 @@ def main():
     ap.add_argument("--assoc", default="fixed", choices=["fixed", "nearest"], help="nearest = BASELINE config 3 (in-kernel re-association)")
     ap.add_argument("--huber", type=float, default=0.0, help="Huber delta on the whitened laser residuals (0 = reference: none)")
     ap.add_argument("--contexts", type=int, default=1, help="split the batch over this many solver contexts / CUDA streams")
-    ap.add_argument("--e2e-chunks", type=int, default=4, help="chunks the end-to-end arm splits the batch into (2 contexts alternate)")
+    ap.add_argument("--e2e-chunks", type=int, default=8, help="chunks the end-to-end arm splits the batch into (2 contexts alternate)")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
