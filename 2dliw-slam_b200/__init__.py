@@ -4,4 +4,4 @@ Import as `lvio2d_b200` (alias package at the repo root).  The compute path is t
 `csrc/liblvio2d.so` reached through the C ABI of include/lvio2d.h; there is no CPU fallback.
 """
 from . import abi, params, synth  # noqa: F401
-from .params import corridor_params  # noqa: F401
+from .params import corridor_line_params, corridor_params  # noqa: F401

@@ -61,6 +61,20 @@ class Params(C.Structure):
     ]
 
 
+class LineParams(C.Structure):
+    """lvio2d_line_params (include/lvio2d.h)."""
+
+    _fields_ = [
+        ("line_continuous_threshold", C.c_double),
+        ("line_max_tolerance_angle_deg", C.c_double),
+        ("line_max_dis", C.c_double),
+        ("line_min_len", C.c_double),
+        ("laser_resolution", C.c_double),
+        ("w_laser_each_scan", C.c_double),
+        ("h_laser_each_scan", C.c_double),
+    ]
+
+
 class WindowBatch(C.Structure):
     """lvio2d_window_batch (include/lvio2d.h)."""
 

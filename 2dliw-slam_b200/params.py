@@ -103,3 +103,12 @@ def corridor_params(fast_mode=False, max_iters=None, device=0):
 
 def params_T(p, name):
     return np.array(list(getattr(p, name)), dtype=np.float64).reshape(3, 4)
+
+
+def corridor_line_params(**overrides):
+    """lvio2d_line_params with the values of config/corridor.yaml:79-89."""
+    lp = abi.LineParams(line_continuous_threshold=0.5, line_max_tolerance_angle_deg=175.0, line_max_dis=0.1,
+                        line_min_len=0.05, laser_resolution=0.1, w_laser_each_scan=100.0, h_laser_each_scan=100.0)
+    for k, v in overrides.items():
+        setattr(lp, k, v)
+    return lp

@@ -441,3 +441,43 @@ def config_tracking2(n_windows=1, seed=42):
     pairs hang between two constant poses, so the solver program drops them by itself, while
     solver::marginalization linearises them too (solver.cpp:448-478)."""
     return make_batch(n_windows, seed, n_frames=2, beams=1081, fov_deg=270.0, topology="tracking", mode="segment")
+
+
+# ----------------------------------------------------------------------------- raw scans for the laser front-end
+def make_scan_batch(n_scans=8, seed=42, beams=1081, fov_deg=270.0, n_interior=8, range_sigma=0.01, max_range=30.0,
+                    width=10.0, height=8.0, dropout=0.01):
+    """Synthetic scans for lvio2d_extract_lines: a width x height room with `n_interior` walls of 1-4 m, the sensor
+    at a random pose at least 0.5 m from the outer walls, one ray per beam (-fov/2 .. fov/2), range noise
+    N(0, range_sigma), beams without a hit (or randomly dropped with probability `dropout`, like the NaN / inf /
+    < 0.1 m readings convert::laser_to_point_times discards, src/utilies/common.cpp:20) removed.
+    Returns (point_offset [S+1] int64, points [N][2])."""
+    rng = np.random.Generator(np.random.MT19937(int(seed)))
+    ang = np.deg2rad(np.linspace(-fov_deg / 2.0, fov_deg / 2.0, beams))
+    pts_all, off = [], [0]
+    for _ in range(n_scans):
+        segs = [[0, 0, width, 0], [width, 0, width, height], [width, height, 0, height], [0, height, 0, 0]]
+        for _k in range(n_interior):
+            c = rng.uniform([1.0, 1.0], [width - 1.0, height - 1.0])
+            a = rng.uniform(0.0, math.pi)
+            ln = rng.uniform(1.0, 4.0)
+            d = 0.5 * ln * np.array([math.cos(a), math.sin(a)])
+            segs.append([*(c - d), *(c + d)])
+        world = np.array(segs)
+        o = rng.uniform([0.5, 0.5], [width - 0.5, height - 0.5])
+        yaw = rng.uniform(-math.pi, math.pi)
+        d = np.stack([np.cos(ang + yaw), np.sin(ang + yaw)], axis=1)
+        s1, e = world[:, 0:2], world[:, 2:4] - world[:, 0:2]
+        so = s1 - o
+        den = d[:, None, 0] * e[None, :, 1] - d[:, None, 1] * e[None, :, 0]
+        with np.errstate(divide="ignore", invalid="ignore"):
+            rho = (so[None, :, 0] * e[None, :, 1] - so[None, :, 1] * e[None, :, 0]) / den
+            u = (so[None, :, 0] * d[:, None, 1] - so[None, :, 1] * d[:, None, 0]) / den
+        ok = (np.abs(den) > 1e-12) & (rho > 0.1) & (u >= 0.0) & (u <= 1.0)
+        rho = np.where(ok, rho, np.inf)
+        r = rho.min(axis=1)
+        valid = np.isfinite(r) & (r < max_range) & (rng.uniform(size=beams) >= dropout)
+        r = r + rng.normal(0.0, range_sigma, size=beams)
+        pts = np.stack([r * np.cos(ang), r * np.sin(ang)], axis=1)[valid]
+        pts_all.append(pts)
+        off.append(off[-1] + len(pts))
+    return np.array(off, dtype=np.int64), np.concatenate(pts_all).reshape(-1, 2)

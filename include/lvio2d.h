@@ -255,6 +255,32 @@ int lvio2d_eval_wheel_factor(lvio2d_ctx* ctx, const double* wheel_blob, const do
 /* ground_factor_p / ground_factor_q (p,q): res[2] = (res_p, res_q), jac[2][6] (ground_factor.h:27-82) */
 int lvio2d_eval_ground_factors(lvio2d_ctx* ctx, const double* pose, double* res, double* jac);
 
+/* ---- laser front-end, step 1: scan points -> line segments.
+ * Replaces, for a batch of scans, laser_manager::spawn_scan (src/trajectory/laser_manager.cpp:350-422) with
+ * scan::add_line's fit and filters (:137-154; fit_line_by_least_square :19-36, create_line :62-94): continuity split,
+ * corner response cos(angle) with step 3, non-maximum suppression, tolerance-angle merge, least-squares fit
+ * (smallest right singular vector of [x y 1]), max-distance / min-length filters, grid-validity test of
+ * scan::xy_to_index (src/trajectory/laser_type.h:34-41).  The output is scan::lines in the reference's order. ---- */
+typedef struct lvio2d_line_params {
+    double line_continuous_threshold;     /* config/corridor.yaml:84 */
+    double line_max_tolerance_angle_deg;  /* :89 (degrees, converted like convert::angle_to_rad) */
+    double line_max_dis;                  /* :86 */
+    double line_min_len;                  /* :85 */
+    double laser_resolution;              /* :81 */
+    double w_laser_each_scan;             /* :79 */
+    double h_laser_each_scan;             /* :80 */
+} lvio2d_line_params;
+/* points: [N][2] (x, y) in the laser frame, scan s owns rows point_offset[s] .. point_offset[s+1]-1 (the de-skewed
+ * points of sensor::laser, z = 0).  Outputs per scan, `max_lines` slots each: n_lines[s] (lines found; when it
+ * exceeds max_lines only the first max_lines are stored), lines [S][max_lines][4] = (p1.x, p1.y, p2.x, p2.y),
+ * abc [S][max_lines][3] (the fitted (a, b, c), sign normalised so that the component of largest magnitude is
+ * positive), index_range [S][max_lines][2] = (index1, index2) into the scan's points.
+ * on_device = 0: every pointer is a host buffer (copied in and out, synchronous).  on_device = 1: every pointer is a
+ * device buffer; the kernel is enqueued on the context's stream and the call returns without synchronising. */
+int lvio2d_extract_lines(lvio2d_ctx* ctx, const lvio2d_line_params* lp, int32_t n_scans, const int64_t* point_offset,
+                         const double* points, int32_t max_lines, int32_t* n_lines, double* lines, double* abc,
+                         int32_t* index_range, int32_t on_device);
+
 #ifdef __cplusplus
 }
 #endif

@@ -10,6 +10,7 @@
 #include <thread>
 
 #include "solver.hpp"
+#include "laser_lines.hpp"
 
 using namespace oracle;
 
@@ -182,6 +183,44 @@ int oracle_marginalize(const lvio2d_params* p, const lvio2d_window_batch* batch,
     }
     return bad ? -1 : 0;
 }
+// ---- scan -> line segments (laser_manager::spawn_scan), same argument layout as lvio2d_extract_lines (host buffers)
+static void normalise_sign(double* v) {
+    int k = 0;
+    for (int i = 1; i < 3; ++i) if (std::fabs(v[i]) > std::fabs(v[k])) k = i;
+    if (v[k] < 0) for (int i = 0; i < 3; ++i) v[i] = -v[i];
+}
+int oracle_extract_lines(const lvio2d_line_params* lp, int32_t n_scans, const int64_t* point_offset, const double* points,
+                         int32_t max_lines, int32_t* n_lines, double* out_lines, double* abc, int32_t* index_range) {
+    lines::LineParams P;
+    P.continuous_threshold = lp->line_continuous_threshold;
+    P.max_tolerance_angle = lp->line_max_tolerance_angle_deg / 180.0 * M_PI;
+    P.max_dis = lp->line_max_dis; P.min_len = lp->line_min_len; P.resolution = lp->laser_resolution;
+    P.w = (int)(lp->w_laser_each_scan / lp->laser_resolution + 1);
+    P.h = (int)(lp->h_laser_each_scan / lp->laser_resolution + 1);
+    for (int s = 0; s < n_scans; ++s) {
+        std::vector<lines::P3> pts;
+        for (int64_t i = point_offset[s]; i < point_offset[s + 1]; ++i) pts.emplace_back(points[2 * i], points[2 * i + 1], 0.0);
+        const std::vector<lines::Line> L = lines::spawn_scan(P, pts);
+        n_lines[s] = (int32_t)L.size();
+        for (int k = 0; k < (int)L.size() && k < max_lines; ++k) {
+            const size_t o = (size_t)s * max_lines + k;
+            out_lines[4 * o] = L[k].p1.x; out_lines[4 * o + 1] = L[k].p1.y; out_lines[4 * o + 2] = L[k].p2.x; out_lines[4 * o + 3] = L[k].p2.y;
+            abc[3 * o] = L[k].abc.x; abc[3 * o + 1] = L[k].abc.y; abc[3 * o + 2] = L[k].abc.z;
+            normalise_sign(abc + 3 * o);
+            index_range[2 * o] = L[k].index1; index_range[2 * o + 1] = L[k].index2;
+        }
+    }
+    return 0;
+}
+// the SVD restatement alone, for the numpy pin: smallest right singular vector of [x y 1]
+void oracle_fit_line(const double* points, int32_t n, double* abc) {
+    std::vector<lines::P3> pts;
+    for (int i = 0; i < n; ++i) pts.emplace_back(points[2 * i], points[2 * i + 1], 0.0);
+    const lines::P3 v = lines::fit_line_by_least_square(pts, 0, n - 1);
+    abc[0] = v.x; abc[1] = v.y; abc[2] = v.z;
+    normalise_sign(abc);
+}
+
 int oracle_max_threads() {
     const unsigned h = std::thread::hardware_concurrency();
     return h ? (int)h : 1;

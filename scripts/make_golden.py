@@ -64,10 +64,24 @@ def factor_case():
     print("factors ok")
 
 
+def lines_case():
+    """Scans + the oracle's scan::lines (laser_manager::spawn_scan): inputs are frozen with the outputs."""
+    lp = L.corridor_line_params()
+    off, pts = L.synth.make_scan_batch(6, 2024)
+    n, lines, abc, rng = O.extract_lines(lp, off, pts, max_lines=128)
+    np.savez_compressed(os.path.join(OUT, "lines_scans.npz"), point_offset=off, points=pts, n_lines=n, lines=lines, abc=abc,
+                        index_range=rng)
+    print("lines ok", n)
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     O.build()
+    if "--lines" in sys.argv:
+        lines_case()
+        sys.exit(0)
     factor_case()
+    lines_case()
     window_case("c1_single_scan", L.synth.config_c1(), 1)
     window_case("c2_small", L.synth.make_batch(2, 42, n_frames=5, beams=120, fov_deg=270.0), 10)
     window_case("tracking2_segments", L.synth.config_tracking2(1), 20)

@@ -27,7 +27,7 @@ def _d(a):
 
 
 def build(force=False):
-    srcs = ["oracle_c.cpp", "solver.hpp", "factors.hpp", "preint.hpp", "lie.hpp", "jet.hpp"]
+    srcs = ["oracle_c.cpp", "laser_lines.hpp", "solver.hpp", "factors.hpp", "preint.hpp", "lie.hpp", "jet.hpp"]
     newest = max(os.path.getmtime(os.path.join(_ROOT, "oracle", s)) for s in srcs)
     if force or not os.path.exists(_LIB_PATH) or os.path.getmtime(_LIB_PATH) < newest:
         subprocess.check_call(["make", "-C", os.path.join(_ROOT, "oracle"), "-s"])
@@ -184,6 +184,26 @@ def marginalize(params, hb, states=None):
     rc = lib().oracle_marginalize(C.byref(params), C.byref(s), _d(st) if st is not None else dp(), _d(X0), _d(J), _d(r), _d(dH), _d(dg))
     assert rc == 0
     return X0, J, r, dH, dg
+
+
+def extract_lines(lp, point_offset, points, max_lines=256):
+    """laser_manager::spawn_scan for a batch of scans (same layout as Context.extract_lines)."""
+    off = np.ascontiguousarray(point_offset, dtype=np.int64)
+    pts = np.ascontiguousarray(points, dtype=np.float64).reshape(-1, 2)
+    S = len(off) - 1
+    n = np.zeros(S, np.int32)
+    lines, abc, rng = np.zeros((S, max_lines, 4)), np.zeros((S, max_lines, 3)), np.zeros((S, max_lines, 2), np.int32)
+    rc = lib().oracle_extract_lines(C.byref(lp), S, off.ctypes.data_as(abi.c_int64_p), _d(pts), int(max_lines),
+                                    n.ctypes.data_as(abi.c_int32_p), _d(lines), _d(abc), rng.ctypes.data_as(abi.c_int32_p))
+    assert rc == 0
+    return n, lines, abc, rng
+
+
+def fit_line(points):
+    pts = np.ascontiguousarray(points, dtype=np.float64).reshape(-1, 2)
+    out = np.zeros(3)
+    lib().oracle_fit_line(_d(pts), len(pts), _d(out))
+    return out
 
 
 def max_threads():
