@@ -11,6 +11,7 @@
 
 #include "../../include/lvio2d.h"
 #include "aux_kernels.cuh"
+#include "scan_lines.cuh"
 
 using namespace lv;
 
@@ -82,6 +83,7 @@ struct lvio2d_ctx {
     // work buffers
     DevBuf b_x0, b_x, b_xc, b_scale, b_ftab, b_reftab, b_wlines, b_wlen, b_part, b_lb, b_items, b_vec, b_fac, b_state, b_status, b_active, b_active1, b_reduce;
     DevBuf b_tmp[8];
+    DevBuf b_ln[12];   // lvio2d_extract_lines: inputs / workspace / outputs
     double* ext_reduce = nullptr; int64_t ext_reduce_count = 0;
     int step_calls = 0;
     bool have_solution = false;
@@ -452,6 +454,7 @@ void lvio2d_destroy(lvio2d_ctx* ctx) {
                      &ctx->b_status, &ctx->b_active, &ctx->b_active1, &ctx->b_reduce};
     for (DevBuf* b : all) b->release();
     for (auto& b : ctx->b_tmp) b.release();
+    for (auto& b : ctx->b_ln) b.release();
     ctx->h_poff.release(); ctx->h_loff.release(); ctx->h_rf.release(); ctx->h_cm.release(); ctx->h_active.release(); ctx->h_active1.release();
     for (auto e : ctx->ev_scan) cudaEventDestroy(e);
     for (auto e : ctx->ev_win) cudaEventDestroy(e);
@@ -762,6 +765,66 @@ int lvio2d_eval_wheel_factor(lvio2d_ctx* ctx, const double* wheel_blob, const do
     const int len[3] = {15, 6, 6};
     return eval_hook(ctx, in, len, 3, res, 3, jac, 36, 2);
 }
+int lvio2d_extract_lines(lvio2d_ctx* ctx, const lvio2d_line_params* lp, int32_t n_scans, const int64_t* point_offset, const double* points,
+                         int32_t max_lines, int32_t* n_lines, double* lines, double* abc, int32_t* index_range, int32_t on_device) {
+    if (!ctx || !lp || n_scans < 0 || !point_offset || max_lines < 1 || !n_lines || !lines || !abc || !index_range) return LVIO2D_ERR_INVALID_ARG;
+    if (!(lp->laser_resolution > 0.0)) return fail(ctx, LVIO2D_ERR_INVALID_ARG, "laser_resolution must be positive");
+    if (n_scans == 0) return LVIO2D_OK;
+    CK(cudaSetDevice(ctx->device));
+    const size_t S = (size_t)n_scans;
+    int64_t N = 0;
+    if (on_device) CK(cudaMemcpyAsync(&N, point_offset + n_scans, sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
+    else {
+        N = point_offset[n_scans];
+        for (int32_t s = 0; s < n_scans; ++s)
+            if (point_offset[s + 1] < point_offset[s]) return fail(ctx, LVIO2D_ERR_INVALID_ARG, "offsets must be non-decreasing");
+    }
+    if (on_device) CK(cudaStreamSynchronize(ctx->stream));
+    if (N < 0) return fail(ctx, LVIO2D_ERR_INVALID_ARG, "negative point count");
+    if (N > 0 && !points) return LVIO2D_ERR_INVALID_ARG;
+    DevBuf* B = ctx->b_ln;
+    const size_t nn = (size_t)std::max<int64_t>(N, 1);
+    bool ok = B[0].ensure(nn * sizeof(double)) && B[1].ensure(nn * sizeof(int32_t)) && B[2].ensure(nn * sizeof(int32_t)) &&
+              B[3].ensure((2 * nn + 2 * S) * sizeof(int32_t)) && B[4].ensure((2 * nn + 2 * S) * sizeof(int32_t)) && B[5].ensure((nn + S) * sizeof(int32_t));
+    if (!on_device)
+        ok = ok && B[6].ensure((S + 1) * sizeof(int64_t)) && B[7].ensure(nn * sizeof(double2)) && B[8].ensure(S * sizeof(int32_t)) &&
+             B[9].ensure(S * max_lines * 4 * sizeof(double)) && B[10].ensure(S * max_lines * 3 * sizeof(double)) && B[11].ensure(S * max_lines * 2 * sizeof(int32_t));
+    if (!ok) return fail(ctx, LVIO2D_ERR_ALLOC, "cudaMalloc(extract_lines)");
+    ScanLinesArgs a;
+    a.n_scans = n_scans; a.max_lines = max_lines;
+    a.continuous_threshold = lp->line_continuous_threshold;
+    a.max_tolerance_angle = lp->line_max_tolerance_angle_deg / 180.0 * M_PI;   // convert::angle_to_rad (common.h:48)
+    a.max_dis = lp->line_max_dis; a.min_len = lp->line_min_len; a.resolution = lp->laser_resolution;
+    a.w = (int)(lp->w_laser_each_scan / lp->laser_resolution + 1);             // laser_manager.cpp:231-236
+    a.h = (int)(lp->h_laser_each_scan / lp->laser_resolution + 1);
+    a.resp = B[0].as<double>(); a.seg_s = B[1].as<int32_t>(); a.seg_e = B[2].as<int32_t>();
+    a.cand = B[3].as<int32_t>(); a.lstart = B[4].as<int32_t>(); a.seg_first = B[5].as<int32_t>();
+    if (on_device) {
+        a.point_offset = point_offset; a.points = reinterpret_cast<const double2*>(points);
+        a.n_lines = n_lines; a.lines = lines; a.abc = abc; a.index_range = index_range;
+    } else {
+        CK(cudaMemcpyAsync(B[6].p, point_offset, (S + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, ctx->stream));
+        if (N > 0) CK(cudaMemcpyAsync(B[7].p, points, (size_t)N * sizeof(double2), cudaMemcpyHostToDevice, ctx->stream));
+        a.point_offset = B[6].as<int64_t>(); a.points = B[7].as<double2>();
+        a.n_lines = B[8].as<int32_t>(); a.lines = B[9].as<double>(); a.abc = B[10].as<double>(); a.index_range = B[11].as<int32_t>();
+        CK(cudaMemsetAsync(B[9].p, 0, S * max_lines * 4 * sizeof(double), ctx->stream));
+        CK(cudaMemsetAsync(B[10].p, 0, S * max_lines * 3 * sizeof(double), ctx->stream));
+        CK(cudaMemsetAsync(B[11].p, 0, S * max_lines * 2 * sizeof(int32_t), ctx->stream));
+    }
+    const int wpc = 4;
+    scan_lines_kernel<<<(n_scans + wpc - 1) / wpc, wpc * 32, 0, ctx->stream>>>(a);
+    ctx->launches += 1;
+    CK(cudaGetLastError());
+    if (!on_device) {
+        CK(cudaMemcpyAsync(n_lines, B[8].p, S * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaMemcpyAsync(lines, B[9].p, S * max_lines * 4 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaMemcpyAsync(abc, B[10].p, S * max_lines * 3 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaMemcpyAsync(index_range, B[11].p, S * max_lines * 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
+    return LVIO2D_OK;
+}
+
 int lvio2d_eval_ground_factors(lvio2d_ctx* ctx, const double* pose, double* res, double* jac) {
     const double* in[1] = {pose};
     const int len[1] = {6};

@@ -1,0 +1,288 @@
+// scan_lines.cuh — scan points -> line segments for a batch of scans, one warp per scan.
+//
+// Replaces laser_manager::spawn_scan (reference src/trajectory/laser_manager.cpp:350-422) together with the fit and
+// the filters of scan::add_line (:137-154; fit_line_by_least_square :19-36, create_line :62-94, project_to_line
+// :8-18, is_continuous / clac_cos / clac_angle :96-120) and the grid-validity test of scan::xy_to_index /
+// is_index_valid (src/trajectory/laser_type.h:34-41).  Output = scan::lines in the reference's order.
+//
+// The reference walks each scan sequentially; here every stage that has no loop-carried dependency is spread over
+// the 32 lanes (points are read through L1, per-point scratch lives in a global workspace that stays L1/L2-resident):
+//   (A) continuity split      break flags -> segment start / end of every point by a max-scan / min-scan over the scan
+//   (B) corner response       cos of the angle at point i between points i-3 and i+3 (clipped to the segment)
+//   (C) non-maximum suppression; the reference's "i += step" after a maximum is a no-op (two strict maxima of a
+//       +-3 window cannot lie within 3 of each other), so the flags are exact without the sequential walk
+//   (D) candidate list        [segment start, maxima..., segment end] per segment, by ordered warp compaction
+//   (E) tolerance-angle merge sequential per segment (loop-carried `last_end_index`): one lane per segment
+//   (F) fit + filters         warp-cooperative per line: moments of [x y 1] -> smallest eigenvector of the 3x3 Gram
+//       matrix by cyclic Jacobi (= V.col(2) of the reference's JacobiSVD), max distance, projections, length, grid test
+// Bound: fp64 ALU / latency (sqrt, div, acos per point); 16 B in and < 1 B out per point, far below the HBM roofline.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace lv {
+
+struct ScanLinesArgs {
+    const int64_t* point_offset;   // [S+1]
+    const double2* points;         // [N]
+    int32_t n_scans, max_lines;
+    double continuous_threshold, max_tolerance_angle, max_dis, min_len, resolution;
+    int32_t w, h;
+    // workspace, indexed like the points (x2 for the candidate arrays)
+    double* resp;                  // [N]
+    int32_t* seg_s;                // [N]
+    int32_t* seg_e;                // [N]
+    int32_t* cand;                 // [2N + 2S]
+    int32_t* lstart;               // [2N + 2S]
+    int32_t* seg_first;            // [N + S]
+    // outputs
+    int32_t* n_lines;              // [S]
+    double* lines;                 // [S][max_lines][4]
+    double* abc;                   // [S][max_lines][3]
+    int32_t* index_range;          // [S][max_lines][2]
+};
+
+constexpr double kLineEpsilo = 0.0008;   // laser_manager.cpp:3
+
+__device__ __forceinline__ double line_clac_cos(double2 pj, double2 pi, double2 pk) {
+    const double ax = pi.x - pj.x, ay = pi.y - pj.y, bx = pk.x - pj.x, by = pk.y - pj.y;
+    const double na = sqrt(ax * ax + ay * ay), nb = sqrt(bx * bx + by * by);
+    if (na < kLineEpsilo) return -1.0;
+    if (nb < kLineEpsilo) return -1.0;
+    return (ax / na) * (bx / nb) + (ay / na) * (by / nb);
+}
+__device__ __forceinline__ double lines_warp_sum(double v) {
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+    return v;
+}
+__device__ __forceinline__ double lines_warp_max(double v) {
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, d));
+    return v;
+}
+
+// eigenvector of the smallest eigenvalue of the symmetric 3x3 matrix (m00 m01 m02; . m11 m12; . . m22), cyclic Jacobi
+__device__ __forceinline__ void smallest_eigvec3(double m00, double m01, double m02, double m11, double m12, double m22, double* v) {
+    double A[3][3] = {{m00, m01, m02}, {m01, m11, m12}, {m02, m12, m22}};
+    double V[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
+#pragma unroll 1
+    for (int sweep = 0; sweep < 24; ++sweep) {
+        const double off = fabs(A[0][1]) + fabs(A[0][2]) + fabs(A[1][2]);
+        if (off == 0.0) break;
+        bool any = false;
+#pragma unroll
+        for (int pq = 0; pq < 3; ++pq) {
+            const int p = pq == 2 ? 1 : 0, q = pq == 0 ? 1 : 2;
+            const double apq = A[p][q];
+            if (fabs(apq) <= 1e-19 * sqrt(fabs(A[p][p] * A[q][q])) || apq == 0.0) continue;
+            any = true;
+            const double theta = (A[q][q] - A[p][p]) / (2.0 * apq);
+            const double t = (theta >= 0.0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+            const double c = 1.0 / sqrt(t * t + 1.0), s = t * c;
+            const int r = 3 - p - q;
+            const double app = A[p][p], aqq = A[q][q], arp = A[r][p], arq = A[r][q];
+            A[p][p] = app - t * apq;
+            A[q][q] = aqq + t * apq;
+            A[p][q] = A[q][p] = 0.0;
+            A[r][p] = A[p][r] = c * arp - s * arq;
+            A[r][q] = A[q][r] = s * arp + c * arq;
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+                const double vp = V[i][p], vq = V[i][q];
+                V[i][p] = c * vp - s * vq;
+                V[i][q] = s * vp + c * vq;
+            }
+        }
+        if (!any) break;
+    }
+    int k = 0;
+    double dk = A[0][0];
+    if (A[1][1] < dk) { k = 1; dk = A[1][1]; }
+    if (A[2][2] < dk) k = 2;
+    v[0] = k == 0 ? V[0][0] : (k == 1 ? V[0][1] : V[0][2]);
+    v[1] = k == 0 ? V[1][0] : (k == 1 ? V[1][1] : V[1][2]);
+    v[2] = k == 0 ? V[2][0] : (k == 1 ? V[2][1] : V[2][2]);
+}
+
+__global__ void __launch_bounds__(128) scan_lines_kernel(ScanLinesArgs a) {
+    const int lane = threadIdx.x & 31;
+    const int s = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (s >= a.n_scans) return;
+    const int64_t p0 = a.point_offset[s];
+    const int n = (int)(a.point_offset[s + 1] - p0);
+    const double2* P = a.points + p0;
+    double* resp = a.resp + p0;
+    int32_t* seg_s = a.seg_s + p0;
+    int32_t* seg_e = a.seg_e + p0;
+    int32_t* cand = a.cand + 2 * p0 + 2 * s;
+    int32_t* lstart = a.lstart + 2 * p0 + 2 * s;
+    int32_t* seg_first = a.seg_first + p0 + s;
+    if (n == 0) { if (lane == 0) a.n_lines[s] = 0; return; }
+
+    // ---- (A) segment start of every point (forward max-scan of the break positions) ...
+    int carry = 0;
+    for (int base = 0; base < n; base += 32) {
+        const int i = base + lane;
+        bool brk = false;
+        if (i < n) {
+            if (i == 0) brk = true;
+            else {
+                const double2 u = P[i - 1], v = P[i];
+                const double dx = u.x - v.x, dy = u.y - v.y;
+                brk = !(sqrt(dx * dx + dy * dy) <= a.continuous_threshold);
+            }
+        }
+        int v = brk ? i : -1;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const int t = __shfl_up_sync(0xffffffffu, v, d); if (lane >= d) v = max(v, t); }
+        v = max(v, carry);
+        if (i < n) seg_s[i] = v;
+        carry = __shfl_sync(0xffffffffu, v, 31);
+    }
+    __syncwarp();
+    // ... and its segment end (backward min-scan of the end positions)
+    carry = n - 1;
+    for (int base = ((n - 1) / 32) * 32; base >= 0; base -= 32) {
+        const int i = base + lane;
+        const bool is_end = i < n && (i == n - 1 || seg_s[i + 1] == i + 1);
+        int v = is_end ? i : 0x7fffffff;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const int t = __shfl_down_sync(0xffffffffu, v, d); if (lane + d < 32) v = min(v, t); }
+        v = min(v, carry);
+        if (i < n) seg_e[i] = v;
+        carry = __shfl_sync(0xffffffffu, v, 0);
+    }
+    __syncwarp();
+
+    // ---- (B) corner responses (laser_manager.cpp:378-382); end points of a segment keep -1
+    for (int i = lane; i < n; i += 32) {
+        const int ss = seg_s[i], ee = seg_e[i];
+        double r = -1.0;
+        if (i > ss && i < ee) r = line_clac_cos(P[i], P[max(i - 3, ss)], P[min(i + 3, ee)]);
+        resp[i] = r;
+    }
+    __syncwarp();
+
+    // ---- (C) + (D) strict local maxima and the ordered candidate list [s, maxima..., e] of every segment
+    int total = 0, n_seg = 0;
+    for (int base = 0; base < n; base += 32) {
+        const int i = base + lane;
+        bool is_s = false, is_e = false, is_max = false;
+        if (i < n) {
+            const int ss = seg_s[i], ee = seg_e[i];
+            is_s = i == ss; is_e = i == ee;
+            if (i > ss && i < ee) {
+                is_max = true;
+                const double ri = resp[i];
+                const int bj = max(i - 3, ss + 1), ej = min(i + 3, ee - 1);
+                for (int j = bj; j <= ej; ++j)
+                    if (j != i && resp[j] >= ri) { is_max = false; break; }
+            }
+        }
+        const int cnt = (is_s ? 1 : 0) + (is_max ? 1 : 0) + (is_e ? 1 : 0);
+        int incl = cnt;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += t; }
+        int pos = total + incl - cnt;
+        const unsigned smask = __ballot_sync(0xffffffffu, is_s);
+        if (is_s) { seg_first[n_seg + __popc(smask & ((1u << lane) - 1u))] = pos; cand[pos++] = i; }
+        if (is_max) cand[pos++] = i;
+        if (is_e) cand[pos++] = i;
+        total += __shfl_sync(0xffffffffu, incl, 31);
+        n_seg += __popc(smask);
+    }
+    __syncwarp();
+
+    // ---- (E) tolerance-angle merge (laser_manager.cpp:404-413): lstart[pos] = index1 of the line that ends at
+    // cand[pos], or -1
+    for (int k = lane; k < n_seg; k += 32) {
+        const int fa = seg_first[k], fb = (k + 1 < n_seg) ? seg_first[k + 1] : total;
+        int last = 0;
+        lstart[fa] = -1;
+        for (int i = 1; i + 1 < fb - fa; ++i) {
+            const double angle = acos(line_clac_cos(P[cand[fa + i]], P[cand[fa + last]], P[cand[fa + i + 1]]));
+            if (fabs(angle) < a.max_tolerance_angle) { lstart[fa + i] = cand[fa + last]; last = i; }
+            else lstart[fa + i] = -1;
+        }
+        lstart[fb - 1] = cand[fa + last];
+    }
+    __syncwarp();
+
+    // ---- (F) fit + filters, line by line in the reference's order
+    int count = 0;
+    double* out_lines = a.lines + (size_t)s * a.max_lines * 4;
+    double* out_abc = a.abc + (size_t)s * a.max_lines * 3;
+    int32_t* out_rng = a.index_range + (size_t)s * a.max_lines * 2;
+    for (int base = 0; base < total; base += 32) {
+        const int pos = base + lane;
+        const int my1 = pos < total ? lstart[pos] : -1;
+        const int my2 = pos < total ? cand[pos] : -1;
+        unsigned todo = __ballot_sync(0xffffffffu, my1 >= 0);
+        while (todo) {
+            const int src = __ffs(todo) - 1;
+            todo &= todo - 1;
+            const int i1 = __shfl_sync(0xffffffffu, my1, src), i2 = __shfl_sync(0xffffffffu, my2, src);
+            if (i2 - i1 < 2) continue;                                   // scan::add_line: fewer than 3 points
+            double sxx = 0, sxy = 0, sx = 0, syy = 0, sy = 0;
+            for (int i = i1 + lane; i <= i2; i += 32) {
+                const double2 p = P[i];
+                sxx += p.x * p.x; sxy += p.x * p.y; sx += p.x; syy += p.y * p.y; sy += p.y;
+            }
+            sxx = lines_warp_sum(sxx); sxy = lines_warp_sum(sxy); sx = lines_warp_sum(sx);
+            syy = lines_warp_sum(syy); sy = lines_warp_sum(sy);
+            double v[3];
+            smallest_eigvec3(sxx, sxy, sx, syy, sy, (double)(i2 - i1 + 1), v);
+            {   // sign convention of the ABI: the component of largest magnitude is positive
+                int k = 0;
+                if (fabs(v[1]) > fabs(v[k])) k = 1;
+                if (fabs(v[2]) > fabs(v[k])) k = 2;
+                if (v[k] < 0.0) { v[0] = -v[0]; v[1] = -v[1]; v[2] = -v[2]; }
+            }
+            // create_line: two points of the fitted line
+            double q1x, q1y, q2x, q2y;
+            if (fabs(v[1]) < 0.5) { q1y = 0.0; q1x = -v[2] / v[0]; q2y = 1.0; q2x = (-v[2] - v[1]) / v[0]; }
+            else { q1x = 0.0; q2x = 1.0; q1y = -v[2] / v[1]; q2y = (-v[2] - v[0]) / v[1]; }
+            // e_laser::dis_from_line (common.h:86-95): rejection of p - q2 from the unit direction
+            double ux = q2x - q1x, uy = q2y - q1y;
+            const double ulen = sqrt(ux * ux + uy * uy);
+            if (ulen * ulen > 0.0) { ux /= ulen; uy /= ulen; }
+            double err = 0.0;
+            bool on_grid = false;
+            for (int i = i1 + lane; i <= i2; i += 32) {
+                const double2 p = P[i];
+                const double rx = p.x - q2x, ry = p.y - q2y;
+                const double t = ux * rx + uy * ry;
+                const double ex = rx - t * ux, ey = ry - t * uy;
+                err = fmax(err, sqrt(ex * ex + ey * ey));
+                const int c = (int)(p.x / a.resolution + a.w / 2), r = (int)(p.y / a.resolution + a.h / 2);
+                on_grid = on_grid || (r >= 0 && r < a.h && c >= 0 && c < a.w);
+            }
+            err = lines_warp_max(err);
+            on_grid = __any_sync(0xffffffffu, on_grid);
+            // project_to_line of the first and last point
+            double e1x, e1y, e2x, e2y;
+            {
+                const double2 pa = P[i1], pb = P[i2];
+                if (ulen < kLineEpsilo) { e1x = pa.x; e1y = pa.y; e2x = pb.x; e2y = pb.y; }
+                else {
+                    const double ta = (pa.x - q1x) * ux + (pa.y - q1y) * uy, tb = (pb.x - q1x) * ux + (pb.y - q1y) * uy;
+                    e1x = q1x + ta * ux; e1y = q1y + ta * uy; e2x = q1x + tb * ux; e2y = q1y + tb * uy;
+                }
+            }
+            const double len = sqrt((e1x - e2x) * (e1x - e2x) + (e1y - e2y) * (e1y - e2y));
+            if (err > a.max_dis) continue;
+            if (len < a.min_len) continue;
+            if (!on_grid) continue;
+            if (count < a.max_lines && lane == 0) {
+                out_lines[4 * count] = e1x; out_lines[4 * count + 1] = e1y; out_lines[4 * count + 2] = e2x; out_lines[4 * count + 3] = e2y;
+                out_abc[3 * count] = v[0]; out_abc[3 * count + 1] = v[1]; out_abc[3 * count + 2] = v[2];
+                out_rng[2 * count] = i1; out_rng[2 * count + 1] = i2;
+            }
+            ++count;
+        }
+    }
+    if (lane == 0) a.n_lines[s] = count;
+}
+
+}  // namespace lv

@@ -1,0 +1,87 @@
+"""GPU parity of lvio2d_extract_lines (scan -> line segments) against the CPU oracle of
+laser_manager::spawn_scan (oracle/laser_lines.hpp), through the C ABI.  Integer outputs (line count, index ranges)
+bit-exact; end points and (a, b, c) within 1e-7 (the device takes the smallest eigenvector of the 3x3 Gram matrix, the
+oracle the smallest right singular vector of [x y 1]: same vector, condition-number-squared rounding)."""
+import numpy as np
+import pytest
+
+import lvio2d_b200 as L
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-7
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    from lvio2d_b200.solver import Context
+
+    c = Context(L.corridor_params())
+    yield c
+    c.close()
+
+
+@pytest.fixture(scope="module")
+def lp():
+    return L.corridor_line_params()
+
+
+def compare(got, want):
+    n, lines, abc, rng = got
+    on, olines, oabc, orng = want
+    assert np.array_equal(n, on)
+    for s in range(len(n)):
+        k = min(int(n[s]), lines.shape[1])
+        assert np.array_equal(rng[s, :k], orng[s, :k]), f"scan {s}"
+        assert np.abs(lines[s, :k] - olines[s, :k]).max(initial=0.0) < TOL
+        assert np.abs(abc[s, :k] - oabc[s, :k]).max(initial=0.0) < TOL
+
+
+@pytest.mark.parametrize("sigma", [0.002, 0.01, 0.03])
+def test_lines_match_oracle(ctx, oracle, lp, sigma):
+    off, pts = L.synth.make_scan_batch(32, 5, range_sigma=sigma)
+    compare(ctx.extract_lines(lp, off, pts), oracle.extract_lines(lp, off, pts))
+
+
+def test_golden_scans(ctx, lp):
+    import os
+
+    G = np.load(os.path.join(os.path.dirname(__file__), "golden", "lines_scans.npz"))
+    got = ctx.extract_lines(lp, G["point_offset"], G["points"], max_lines=G["lines"].shape[1])
+    compare(got, (G["n_lines"], G["lines"], G["abc"], G["index_range"]))
+
+
+def test_edge_cases(ctx, oracle, lp):
+    # empty scans, scans shorter than a line, a single point, ragged sizes, an out-of-grid wall
+    t = np.linspace(0, 1, 30)[:, None]
+    far = (1 - t) * np.array([60.0, 0.0]) + t * np.array([60.5, 3.0])
+    off1, pts1 = L.synth.make_scan_batch(3, 9, beams=200)
+    pts = np.concatenate([pts1, [[1.0, 0.0], [1.0, 0.1]], [[2.0, 2.0]], far])
+    off = np.concatenate([[0, 0], off1[1:], [off1[-1] + 2, off1[-1] + 3, off1[-1] + 3, off1[-1] + 33]]).astype(np.int64)
+    got, want = ctx.extract_lines(lp, off, pts), oracle.extract_lines(lp, off, pts)
+    compare(got, want)
+    assert got[0][0] == 0 and got[0][-1] == 0 and got[0][-2] == 0
+    # more lines than slots: the count is still exact, the first max_lines are stored
+    off, pts = L.synth.make_scan_batch(2, 3)
+    got, want = ctx.extract_lines(lp, off, pts, max_lines=4), oracle.extract_lines(lp, off, pts, max_lines=4)
+    assert got[0].min() > 4
+    compare(got, want)
+    # the wide field of view of BASELINE config 4 (4096 beams, 360 degrees)
+    off, pts = L.synth.make_scan_batch(4, 13, beams=4096, fov_deg=360.0)
+    compare(ctx.extract_lines(lp, off, pts, max_lines=512), oracle.extract_lines(lp, off, pts, max_lines=512))
+
+
+def test_bench_size_batch_properties(ctx, lp):
+    """4096 scans (the batch bench.py times): every stored line satisfies the filters it passed."""
+    off1, pts1 = L.synth.make_scan_batch(64, 21)
+    reps = 64
+    n1 = int(off1[-1])
+    off = np.concatenate([(off1[:-1][None, :] + n1 * np.arange(reps)[:, None]).ravel(), [n1 * reps]]).astype(np.int64)
+    pts = np.tile(pts1, (reps, 1))
+    n, lines, abc, rng = ctx.extract_lines(lp, off, pts, max_lines=160)
+    assert np.array_equal(n.reshape(reps, -1), np.tile(n[:64], (reps, 1)))          # identical scans -> identical results
+    assert np.array_equal(lines.reshape(reps, 64, -1), np.tile(lines[:64].reshape(1, 64, -1), (reps, 1, 1)))
+    for s in range(0, 64):
+        k = int(n[s])
+        d = lines[s, :k, 2:] - lines[s, :k, :2]
+        assert np.all(np.linalg.norm(d, axis=1) >= lp.line_min_len)
+        assert np.all(rng[s, :k, 1] - rng[s, :k, 0] >= 2) and np.all(rng[s, 1:k, 0] >= rng[s, :k - 1, 1])
