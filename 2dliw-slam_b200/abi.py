@@ -75,6 +75,25 @@ class LineParams(C.Structure):
     ]
 
 
+class ScanHeader(C.Structure):
+    """lvio2d_scan_header (include/lvio2d.h)."""
+
+    _fields_ = [
+        ("angle_min", C.c_float),
+        ("angle_increment", C.c_float),
+        ("time_increment", C.c_float),
+        ("reserved", C.c_float),
+        ("stamp", C.c_double),
+        ("linear", C.c_double * 3),
+        ("angular", C.c_double * 3),
+    ]
+
+
+SCAN_HEADER_DTYPE = np.dtype([("angle_min", np.float32), ("angle_increment", np.float32), ("time_increment", np.float32),
+                              ("reserved", np.float32), ("stamp", np.float64), ("linear", np.float64, 3), ("angular", np.float64, 3)])
+assert SCAN_HEADER_DTYPE.itemsize == C.sizeof(ScanHeader)
+
+
 class WindowBatch(C.Structure):
     """lvio2d_window_batch (include/lvio2d.h)."""
 

@@ -83,7 +83,8 @@ struct lvio2d_ctx {
     // work buffers
     DevBuf b_x0, b_x, b_xc, b_scale, b_ftab, b_reftab, b_wlines, b_wlen, b_part, b_lb, b_items, b_vec, b_fac, b_state, b_status, b_active, b_active1, b_reduce;
     DevBuf b_tmp[8];
-    DevBuf b_ln[12];   // lvio2d_extract_lines: inputs / workspace / outputs
+    DevBuf b_ln[14];   // lvio2d_extract_lines: inputs / workspace / outputs
+    DevBuf b_sp[7];    // lvio2d_scan_to_points
     double* ext_reduce = nullptr; int64_t ext_reduce_count = 0;
     int step_calls = 0;
     bool have_solution = false;
@@ -455,6 +456,7 @@ void lvio2d_destroy(lvio2d_ctx* ctx) {
     for (DevBuf* b : all) b->release();
     for (auto& b : ctx->b_tmp) b.release();
     for (auto& b : ctx->b_ln) b.release();
+    for (auto& b : ctx->b_sp) b.release();
     ctx->h_poff.release(); ctx->h_loff.release(); ctx->h_rf.release(); ctx->h_cm.release(); ctx->h_active.release(); ctx->h_active1.release();
     for (auto e : ctx->ev_scan) cudaEventDestroy(e);
     for (auto e : ctx->ev_win) cudaEventDestroy(e);
@@ -765,21 +767,31 @@ int lvio2d_eval_wheel_factor(lvio2d_ctx* ctx, const double* wheel_blob, const do
     const int len[3] = {15, 6, 6};
     return eval_hook(ctx, in, len, 3, res, 3, jac, 36, 2);
 }
-int lvio2d_extract_lines(lvio2d_ctx* ctx, const lvio2d_line_params* lp, int32_t n_scans, const int64_t* point_offset, const double* points,
-                         int32_t max_lines, int32_t* n_lines, double* lines, double* abc, int32_t* index_range, int32_t on_device) {
+int lvio2d_extract_lines(lvio2d_ctx* ctx, const lvio2d_line_params* lp, int32_t n_scans, const int64_t* point_offset, const int32_t* point_count,
+                         const double* points, const double* point_z, int32_t max_lines, int32_t* n_lines, double* lines, double* abc,
+                         int32_t* index_range, int32_t on_device) {
     if (!ctx || !lp || n_scans < 0 || !point_offset || max_lines < 1 || !n_lines || !lines || !abc || !index_range) return LVIO2D_ERR_INVALID_ARG;
     if (!(lp->laser_resolution > 0.0)) return fail(ctx, LVIO2D_ERR_INVALID_ARG, "laser_resolution must be positive");
     if (n_scans == 0) return LVIO2D_OK;
     CK(cudaSetDevice(ctx->device));
     const size_t S = (size_t)n_scans;
+    // N = extent of the point arrays the scans address (with point_count: the end of the last scan's slots)
     int64_t N = 0;
-    if (on_device) CK(cudaMemcpyAsync(&N, point_offset + n_scans, sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
-    else {
-        N = point_offset[n_scans];
-        for (int32_t s = 0; s < n_scans; ++s)
-            if (point_offset[s + 1] < point_offset[s]) return fail(ctx, LVIO2D_ERR_INVALID_ARG, "offsets must be non-decreasing");
+    const int n_off = point_count ? n_scans : n_scans + 1;
+    if (on_device) {
+        int64_t last = 0;
+        int32_t last_cnt = 0;
+        CK(cudaMemcpyAsync(&last, point_offset + n_off - 1, sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
+        if (point_count) CK(cudaMemcpyAsync(&last_cnt, point_count + n_scans - 1, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        N = last + last_cnt;
+    } else {
+        for (int32_t s = 0; s < n_scans; ++s) {
+            const int64_t end = point_count ? point_offset[s] + point_count[s] : point_offset[s + 1];
+            if (end < point_offset[s] || point_offset[s] < 0) return fail(ctx, LVIO2D_ERR_INVALID_ARG, "offsets must be non-decreasing");
+            N = std::max(N, end);
+        }
     }
-    if (on_device) CK(cudaStreamSynchronize(ctx->stream));
     if (N < 0) return fail(ctx, LVIO2D_ERR_INVALID_ARG, "negative point count");
     if (N > 0 && !points) return LVIO2D_ERR_INVALID_ARG;
     DevBuf* B = ctx->b_ln;
@@ -788,7 +800,8 @@ int lvio2d_extract_lines(lvio2d_ctx* ctx, const lvio2d_line_params* lp, int32_t 
               B[3].ensure((2 * nn + 2 * S) * sizeof(int32_t)) && B[4].ensure((2 * nn + 2 * S) * sizeof(int32_t)) && B[5].ensure((nn + S) * sizeof(int32_t));
     if (!on_device)
         ok = ok && B[6].ensure((S + 1) * sizeof(int64_t)) && B[7].ensure(nn * sizeof(double2)) && B[8].ensure(S * sizeof(int32_t)) &&
-             B[9].ensure(S * max_lines * 4 * sizeof(double)) && B[10].ensure(S * max_lines * 3 * sizeof(double)) && B[11].ensure(S * max_lines * 2 * sizeof(int32_t));
+             B[9].ensure(S * max_lines * 4 * sizeof(double)) && B[10].ensure(S * max_lines * 3 * sizeof(double)) && B[11].ensure(S * max_lines * 2 * sizeof(int32_t)) &&
+             B[12].ensure(S * sizeof(int32_t)) && B[13].ensure(nn * sizeof(double));
     if (!ok) return fail(ctx, LVIO2D_ERR_ALLOC, "cudaMalloc(extract_lines)");
     ScanLinesArgs a;
     a.n_scans = n_scans; a.max_lines = max_lines;
@@ -801,11 +814,15 @@ int lvio2d_extract_lines(lvio2d_ctx* ctx, const lvio2d_line_params* lp, int32_t 
     a.cand = B[3].as<int32_t>(); a.lstart = B[4].as<int32_t>(); a.seg_first = B[5].as<int32_t>();
     if (on_device) {
         a.point_offset = point_offset; a.points = reinterpret_cast<const double2*>(points);
+        a.point_count = point_count; a.point_z = point_z;
         a.n_lines = n_lines; a.lines = lines; a.abc = abc; a.index_range = index_range;
     } else {
-        CK(cudaMemcpyAsync(B[6].p, point_offset, (S + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(B[6].p, point_offset, (size_t)n_off * sizeof(int64_t), cudaMemcpyHostToDevice, ctx->stream));
         if (N > 0) CK(cudaMemcpyAsync(B[7].p, points, (size_t)N * sizeof(double2), cudaMemcpyHostToDevice, ctx->stream));
+        if (point_count) CK(cudaMemcpyAsync(B[12].p, point_count, S * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+        if (point_z && N > 0) CK(cudaMemcpyAsync(B[13].p, point_z, (size_t)N * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
         a.point_offset = B[6].as<int64_t>(); a.points = B[7].as<double2>();
+        a.point_count = point_count ? B[12].as<int32_t>() : nullptr; a.point_z = point_z ? B[13].as<double>() : nullptr;
         a.n_lines = B[8].as<int32_t>(); a.lines = B[9].as<double>(); a.abc = B[10].as<double>(); a.index_range = B[11].as<int32_t>();
         CK(cudaMemsetAsync(B[9].p, 0, S * max_lines * 4 * sizeof(double), ctx->stream));
         CK(cudaMemsetAsync(B[10].p, 0, S * max_lines * 3 * sizeof(double), ctx->stream));
@@ -820,6 +837,47 @@ int lvio2d_extract_lines(lvio2d_ctx* ctx, const lvio2d_line_params* lp, int32_t 
         CK(cudaMemcpyAsync(lines, B[9].p, S * max_lines * 4 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaMemcpyAsync(abc, B[10].p, S * max_lines * 3 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaMemcpyAsync(index_range, B[11].p, S * max_lines * 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
+    return LVIO2D_OK;
+}
+
+int lvio2d_scan_to_points(lvio2d_ctx* ctx, int32_t n_scans, int32_t n_beams, const float* ranges, const lvio2d_scan_header* headers, int32_t deskew,
+                          int32_t* point_count, double* points, double* point_z, double* point_time, int32_t on_device) {
+    if (!ctx || n_scans < 0 || n_beams < 1 || !ranges || !headers || !point_count || !points || !point_z) return LVIO2D_ERR_INVALID_ARG;
+    if (n_scans == 0) return LVIO2D_OK;
+    CK(cudaSetDevice(ctx->device));
+    const size_t S = (size_t)n_scans, NB = S * (size_t)n_beams;
+    DevBuf* B = ctx->b_sp;
+    bool ok = B[0].ensure(NB * sizeof(int32_t));
+    if (!on_device)
+        ok = ok && B[1].ensure(NB * sizeof(float)) && B[2].ensure(S * sizeof(lvio2d_scan_header)) && B[3].ensure(S * sizeof(int32_t)) &&
+             B[4].ensure(NB * sizeof(double2)) && B[5].ensure(NB * sizeof(double)) && B[6].ensure(NB * sizeof(double));
+    if (!ok) return fail(ctx, LVIO2D_ERR_ALLOC, "cudaMalloc(scan_to_points)");
+    ScanPointsArgs a;
+    a.n_scans = n_scans; a.n_beams = n_beams; a.deskew = deskew;
+    a.beam_index = B[0].as<int32_t>();
+    if (on_device) {
+        a.ranges = ranges; a.headers = headers; a.point_count = point_count; a.points = reinterpret_cast<double2*>(points);
+        a.point_z = point_z; a.point_time = point_time;
+    } else {
+        CK(cudaMemcpyAsync(B[1].p, ranges, NB * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(B[2].p, headers, S * sizeof(lvio2d_scan_header), cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemsetAsync(B[4].p, 0, NB * sizeof(double2), ctx->stream));
+        CK(cudaMemsetAsync(B[5].p, 0, NB * sizeof(double), ctx->stream));
+        CK(cudaMemsetAsync(B[6].p, 0, NB * sizeof(double), ctx->stream));
+        a.ranges = B[1].as<float>(); a.headers = B[2].as<lvio2d_scan_header>(); a.point_count = B[3].as<int32_t>();
+        a.points = B[4].as<double2>(); a.point_z = B[5].as<double>(); a.point_time = point_time ? B[6].as<double>() : nullptr;
+    }
+    const int wpc = 4;
+    scan_points_kernel<<<(n_scans + wpc - 1) / wpc, wpc * 32, 0, ctx->stream>>>(a);
+    ctx->launches += 1;
+    CK(cudaGetLastError());
+    if (!on_device) {
+        CK(cudaMemcpyAsync(point_count, B[3].p, S * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaMemcpyAsync(points, B[4].p, NB * sizeof(double2), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaMemcpyAsync(point_z, B[5].p, NB * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        if (point_time) CK(cudaMemcpyAsync(point_time, B[6].p, NB * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));
     }
     return LVIO2D_OK;

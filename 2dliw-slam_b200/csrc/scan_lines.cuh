@@ -20,11 +20,16 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "../../include/lvio2d.h"
+#include "lv_math.cuh"
+
 namespace lv {
 
 struct ScanLinesArgs {
-    const int64_t* point_offset;   // [S+1]
+    const int64_t* point_offset;   // [S+1] (or [S] with point_count)
+    const int32_t* point_count;    // [S] or nullptr
     const double2* points;         // [N]
+    const double* point_z;         // [N] or nullptr (z = 0)
     int32_t n_scans, max_lines;
     double continuous_threshold, max_tolerance_angle, max_dis, min_len, resolution;
     int32_t w, h;
@@ -44,12 +49,13 @@ struct ScanLinesArgs {
 
 constexpr double kLineEpsilo = 0.0008;   // laser_manager.cpp:3
 
-__device__ __forceinline__ double line_clac_cos(double2 pj, double2 pi, double2 pk) {
-    const double ax = pi.x - pj.x, ay = pi.y - pj.y, bx = pk.x - pj.x, by = pk.y - pj.y;
-    const double na = sqrt(ax * ax + ay * ay), nb = sqrt(bx * bx + by * by);
+struct P3d { double x, y, z; };
+__device__ __forceinline__ double line_clac_cos(P3d pj, P3d pi, P3d pk) {
+    const double ax = pi.x - pj.x, ay = pi.y - pj.y, az = pi.z - pj.z, bx = pk.x - pj.x, by = pk.y - pj.y, bz = pk.z - pj.z;
+    const double na = sqrt(ax * ax + ay * ay + az * az), nb = sqrt(bx * bx + by * by + bz * bz);
     if (na < kLineEpsilo) return -1.0;
     if (nb < kLineEpsilo) return -1.0;
-    return (ax / na) * (bx / nb) + (ay / na) * (by / nb);
+    return (ax / na) * (bx / nb) + (ay / na) * (by / nb) + (az / na) * (bz / nb);
 }
 __device__ __forceinline__ double lines_warp_sum(double v) {
 #pragma unroll
@@ -110,8 +116,10 @@ __global__ void __launch_bounds__(128) scan_lines_kernel(ScanLinesArgs a) {
     const int s = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (s >= a.n_scans) return;
     const int64_t p0 = a.point_offset[s];
-    const int n = (int)(a.point_offset[s + 1] - p0);
+    const int n = a.point_count ? a.point_count[s] : (int)(a.point_offset[s + 1] - p0);
     const double2* P = a.points + p0;
+    const double* PZ = a.point_z ? a.point_z + p0 : nullptr;
+    auto pt = [&](int i) -> P3d { const double2 q = P[i]; P3d r; r.x = q.x; r.y = q.y; r.z = PZ ? PZ[i] : 0.0; return r; };
     double* resp = a.resp + p0;
     int32_t* seg_s = a.seg_s + p0;
     int32_t* seg_e = a.seg_e + p0;
@@ -128,9 +136,9 @@ __global__ void __launch_bounds__(128) scan_lines_kernel(ScanLinesArgs a) {
         if (i < n) {
             if (i == 0) brk = true;
             else {
-                const double2 u = P[i - 1], v = P[i];
-                const double dx = u.x - v.x, dy = u.y - v.y;
-                brk = !(sqrt(dx * dx + dy * dy) <= a.continuous_threshold);
+                const P3d u = pt(i - 1), v = pt(i);
+                const double dx = u.x - v.x, dy = u.y - v.y, dz = u.z - v.z;
+                brk = !(sqrt(dx * dx + dy * dy + dz * dz) <= a.continuous_threshold);
             }
         }
         int v = brk ? i : -1;
@@ -159,7 +167,7 @@ __global__ void __launch_bounds__(128) scan_lines_kernel(ScanLinesArgs a) {
     for (int i = lane; i < n; i += 32) {
         const int ss = seg_s[i], ee = seg_e[i];
         double r = -1.0;
-        if (i > ss && i < ee) r = line_clac_cos(P[i], P[max(i - 3, ss)], P[min(i + 3, ee)]);
+        if (i > ss && i < ee) r = line_clac_cos(pt(i), pt(max(i - 3, ss)), pt(min(i + 3, ee)));
         resp[i] = r;
     }
     __syncwarp();
@@ -201,7 +209,7 @@ __global__ void __launch_bounds__(128) scan_lines_kernel(ScanLinesArgs a) {
         int last = 0;
         lstart[fa] = -1;
         for (int i = 1; i + 1 < fb - fa; ++i) {
-            const double angle = acos(line_clac_cos(P[cand[fa + i]], P[cand[fa + last]], P[cand[fa + i + 1]]));
+            const double angle = acos(line_clac_cos(pt(cand[fa + i]), pt(cand[fa + last]), pt(cand[fa + i + 1])));
             if (fabs(angle) < a.max_tolerance_angle) { lstart[fa + i] = cand[fa + last]; last = i; }
             else lstart[fa + i] = -1;
         }
@@ -253,8 +261,8 @@ __global__ void __launch_bounds__(128) scan_lines_kernel(ScanLinesArgs a) {
                 const double2 p = P[i];
                 const double rx = p.x - q2x, ry = p.y - q2y;
                 const double t = ux * rx + uy * ry;
-                const double ex = rx - t * ux, ey = ry - t * uy;
-                err = fmax(err, sqrt(ex * ex + ey * ey));
+                const double ex = rx - t * ux, ey = ry - t * uy, ez = PZ ? PZ[i] : 0.0;   // the fitted line lies in z = 0
+                err = fmax(err, sqrt(ex * ex + ey * ey + ez * ez));
                 const int c = (int)(p.x / a.resolution + a.w / 2), r = (int)(p.y / a.resolution + a.h / 2);
                 on_grid = on_grid || (r >= 0 && r < a.h && c >= 0 && c < a.w);
             }
@@ -283,6 +291,98 @@ __global__ void __launch_bounds__(128) scan_lines_kernel(ScanLinesArgs a) {
         }
     }
     if (lane == 0) a.n_lines[s] = count;
+}
+
+// =====================================================================================================
+// LaserScan ranges -> (de-skewed) points: convert::laser_to_point_times (reference src/utilies/common.cpp:4-40) +
+// sensor::laser::correct (src/trajectory/sensor.h:51-94).  One warp per scan, fixed output stride of n_beams slots.
+//   (1) every lane converts beams (float angle arithmetic as declared in the reference, double cos/sin) into candidate
+//       points, written in place at their beam slot;
+//   (2) the "closer than 1 cm to the last KEPT point" filter is the only loop-carried step: a chunk of 32 beams whose
+//       readings are all valid and all >= 1 cm from their immediate predecessor is kept wholesale (then the
+//       predecessor IS the last kept point and the decision is exact); any other chunk is walked by one lane;
+//   (3) de-skew of the kept points, in parallel.
+struct ScanPointsArgs {
+    const float* ranges;                 // [S][n_beams]
+    const lvio2d_scan_header* headers;   // [S]
+    int32_t n_scans, n_beams, deskew;
+    int32_t* point_count;                // [S]
+    double2* points;                     // [S][n_beams]
+    double* point_z;                     // [S][n_beams]
+    double* point_time;                  // [S][n_beams] or nullptr
+    int32_t* beam_index;                 // [S][n_beams] workspace: beam of every kept point
+};
+
+__global__ void __launch_bounds__(128) scan_points_kernel(ScanPointsArgs a) {
+    const int lane = threadIdx.x & 31;
+    const int s = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (s >= a.n_scans) return;
+    const lvio2d_scan_header h = a.headers[s];
+    const int nb = a.n_beams;
+    const float* rg = a.ranges + (size_t)s * nb;
+    double2* out = a.points + (size_t)s * nb;
+    double* outz = a.point_z + (size_t)s * nb;
+    int32_t* bidx = a.beam_index + (size_t)s * nb;
+    int kept = 0;
+    double lastx = 0.0, lasty = 0.0;   // last kept point (uniform across the warp)
+    for (int base = 0; base < nb; base += 32) {
+        const int i = base + lane;
+        bool valid = false;
+        double x = 0.0, y = 0.0;
+        if (i < nb) {
+            const float r = rg[i];
+            valid = !isnan(r) && !isinf(r) && (double)r > 0.1;
+            const float ang = __fadd_rn(h.angle_min, __fmul_rn((float)i, h.angle_increment));   // two roundings, no FMA
+            double sn, cs;
+            sincos((double)ang, &sn, &cs);
+            x = cs * (double)r; y = sn * (double)r;
+        }
+        // distance to the immediate predecessor (previous lane, or the last kept point for lane 0)
+        double px = __shfl_up_sync(0xffffffffu, x, 1), py = __shfl_up_sync(0xffffffffu, y, 1);
+        if (lane == 0) { px = lastx; py = lasty; }
+        const bool has_prev = lane > 0 || kept > 0;
+        const bool far = !has_prev || !(sqrt((x - px) * (x - px) + (y - py) * (y - py)) < 0.01);
+        const unsigned in_mask = __ballot_sync(0xffffffffu, i < nb);
+        const unsigned ok_mask = __ballot_sync(0xffffffffu, valid && far);
+        if (ok_mask == in_mask) {
+            // the whole chunk is kept
+            if (i < nb) { out[kept + lane] = make_double2(x, y); bidx[kept + lane] = i; }
+            const int cnt = __popc(in_mask);
+            lastx = __shfl_sync(0xffffffffu, x, cnt - 1); lasty = __shfl_sync(0xffffffffu, y, cnt - 1);
+            kept += cnt;
+        } else {
+            // sequential walk of this chunk (every lane runs it redundantly on shuffled values: no divergence, no smem)
+            const unsigned vmask = __ballot_sync(0xffffffffu, valid);
+            for (int j = 0; j < 32; ++j) {
+                const double xj = __shfl_sync(0xffffffffu, x, j), yj = __shfl_sync(0xffffffffu, y, j);
+                if (!((vmask >> j) & 1u)) continue;
+                if (kept > 0 && sqrt((xj - lastx) * (xj - lastx) + (yj - lasty) * (yj - lasty)) < 0.01) continue;
+                if (lane == 0) { out[kept] = make_double2(xj, yj); bidx[kept] = base + j; }
+                lastx = xj; lasty = yj;
+                ++kept;
+            }
+        }
+        __syncwarp();
+    }
+    if (lane == 0) a.point_count[s] = kept;
+    __syncwarp();
+    // times and de-skew of the kept points
+    const V3<double> lin = v3<double>(h.linear[0], h.linear[1], h.linear[2]), ang = v3<double>(h.angular[0], h.angular[1], h.angular[2]);
+    for (int k = lane; k < kept; k += 32) {
+        const int i = bidx[k];
+        const double t = h.stamp + (double)((float)(size_t)i * h.time_increment);
+        double2 p = out[k];
+        double z = 0.0;
+        if (a.deskew) {
+            const double dt = t - h.stamp;
+            const M3<double> R = exp_so3(scale(ang, dt));
+            const V3<double> q = mul(R, v3<double>(p.x, p.y, 0.0));
+            p.x = q.x + dt * lin.x; p.y = q.y + dt * lin.y; z = q.z + dt * lin.z;
+            out[k] = p;
+        }
+        outz[k] = z;
+        if (a.point_time) a.point_time[(size_t)s * nb + k] = t;
+    }
 }
 
 }  // namespace lv

@@ -30,7 +30,7 @@ EXPORTS = [
     "lvio2d_set_reduce_buffer", "lvio2d_lm_step", "lvio2d_linearize", "lvio2d_marginalize", "lvio2d_imu_preintegrate",
     "lvio2d_wheel_preintegrate", "lvio2d_eval_laser_factor", "lvio2d_eval_imu_factor", "lvio2d_eval_wheel_factor",
     "lvio2d_eval_ground_factors", "lvio2d_set_profiling", "lvio2d_get_profile", "lvio2d_set_windows_async", "lvio2d_get_states_async",
-    "lvio2d_extract_lines",
+    "lvio2d_extract_lines", "lvio2d_scan_to_points",
 ]
 
 
@@ -84,8 +84,9 @@ def load_library(path=LIB_PATH):
     lib.lvio2d_set_profiling.argtypes = [vp, C.c_int32]
     lib.lvio2d_set_windows_async.argtypes = [vp, C.POINTER(abi.WindowBatch)]
     lib.lvio2d_get_states_async.argtypes = [vp, vp]
-    lib.lvio2d_extract_lines.argtypes = [vp, C.POINTER(abi.LineParams), C.c_int32, abi.c_int64_p, dp, C.c_int32, abi.c_int32_p, dp, dp,
-                                         abi.c_int32_p, C.c_int32]
+    lib.lvio2d_extract_lines.argtypes = [vp, C.POINTER(abi.LineParams), C.c_int32, abi.c_int64_p, abi.c_int32_p, dp, dp, C.c_int32,
+                                         abi.c_int32_p, dp, dp, abi.c_int32_p, C.c_int32]
+    lib.lvio2d_scan_to_points.argtypes = [vp, C.c_int32, C.c_int32, vp, vp, C.c_int32, abi.c_int32_p, dp, dp, dp, C.c_int32]
     lib.lvio2d_get_profile.argtypes = [vp, dp]
     _lib = lib
     return lib
@@ -270,29 +271,57 @@ class Context:
         return sensor_batch.host_batch(imu, wheel)
 
     # ---- per-factor hooks (auto_diff::compute_res_and_jacobi, reference src/utilies/common.h:201-217)
-    def extract_lines(self, line_params, point_offset, points, max_lines=256):
+    def extract_lines(self, line_params, point_offset, points, max_lines=256, point_count=None, point_z=None):
         """laser_manager::spawn_scan for a batch of scans (host buffers): returns n_lines [S], lines [S][max_lines][4],
-        abc [S][max_lines][3], index_range [S][max_lines][2]."""
+        abc [S][max_lines][3], index_range [S][max_lines][2].  With `point_count`, scan s owns point_count[s] points
+        from point_offset[s] (the fixed-stride layout scan_to_points writes)."""
         off = np.ascontiguousarray(point_offset, dtype=np.int64)
         pts = np.ascontiguousarray(points, dtype=np.float64).reshape(-1, 2)
-        S = len(off) - 1
+        cnt = None if point_count is None else np.ascontiguousarray(point_count, dtype=np.int32)
+        pz = None if point_z is None else np.ascontiguousarray(point_z, dtype=np.float64).reshape(-1)
+        S = len(off) - 1 if cnt is None else len(cnt)
         n = np.zeros(S, np.int32)
         lines, abc = np.zeros((S, max_lines, 4)), np.zeros((S, max_lines, 3))
         rng = np.zeros((S, max_lines, 2), np.int32)
-        self._check(self.lib.lvio2d_extract_lines(self._h, C.byref(line_params), S, off.ctypes.data_as(abi.c_int64_p), _d(pts),
-                                                  int(max_lines), n.ctypes.data_as(abi.c_int32_p), _d(lines), _d(abc),
-                                                  rng.ctypes.data_as(abi.c_int32_p), 0), "lvio2d_extract_lines")
+        self._check(self.lib.lvio2d_extract_lines(
+            self._h, C.byref(line_params), S, off.ctypes.data_as(abi.c_int64_p),
+            cnt.ctypes.data_as(abi.c_int32_p) if cnt is not None else abi.c_int32_p(), _d(pts),
+            _d(pz) if pz is not None else abi.c_double_p(), int(max_lines), n.ctypes.data_as(abi.c_int32_p), _d(lines), _d(abc),
+            rng.ctypes.data_as(abi.c_int32_p), 0), "lvio2d_extract_lines")
         return n, lines, abc, rng
 
     def extract_lines_device(self, line_params, n_scans, point_offset_ptr, points_ptr, max_lines, n_lines_ptr, lines_ptr, abc_ptr,
-                             range_ptr):
-        """Same with device pointers (integers); enqueued on the context's stream, no synchronisation."""
+                             range_ptr, point_count_ptr=0, point_z_ptr=0):
+        """Same with device pointers (integers); enqueued on the context's stream."""
         vp = C.c_void_p
-        self._check(self.lib.lvio2d_extract_lines(self._h, C.byref(line_params), int(n_scans), C.cast(vp(point_offset_ptr), abi.c_int64_p),
-                                                  C.cast(vp(points_ptr), abi.c_double_p), int(max_lines),
-                                                  C.cast(vp(n_lines_ptr), abi.c_int32_p), C.cast(vp(lines_ptr), abi.c_double_p),
-                                                  C.cast(vp(abc_ptr), abi.c_double_p), C.cast(vp(range_ptr), abi.c_int32_p), 1),
-                    "lvio2d_extract_lines")
+        self._check(self.lib.lvio2d_extract_lines(
+            self._h, C.byref(line_params), int(n_scans), C.cast(vp(point_offset_ptr), abi.c_int64_p),
+            C.cast(vp(point_count_ptr or None), abi.c_int32_p), C.cast(vp(points_ptr), abi.c_double_p),
+            C.cast(vp(point_z_ptr or None), abi.c_double_p), int(max_lines), C.cast(vp(n_lines_ptr), abi.c_int32_p),
+            C.cast(vp(lines_ptr), abi.c_double_p), C.cast(vp(abc_ptr), abi.c_double_p), C.cast(vp(range_ptr), abi.c_int32_p), 1),
+            "lvio2d_extract_lines")
+
+    def scan_to_points(self, ranges, headers, deskew=True, want_times=False):
+        """convert::laser_to_point_times + sensor::laser::correct for a batch of scans (host buffers).  ranges [S][n_beams]
+        float32, headers: numpy array of abi.SCAN_HEADER_DTYPE.  Returns point_count [S], points [S][n_beams][2],
+        point_z [S][n_beams] (and point_time)."""
+        rg = np.ascontiguousarray(ranges, dtype=np.float32)
+        hd = np.ascontiguousarray(headers, dtype=abi.SCAN_HEADER_DTYPE)
+        S, nb = rg.shape
+        cnt = np.zeros(S, np.int32)
+        pts, pz = np.zeros((S, nb, 2)), np.zeros((S, nb))
+        pt = np.zeros((S, nb)) if want_times else None
+        self._check(self.lib.lvio2d_scan_to_points(self._h, S, nb, rg.ctypes.data, hd.ctypes.data, int(bool(deskew)),
+                                                   cnt.ctypes.data_as(abi.c_int32_p), _d(pts), _d(pz),
+                                                   _d(pt) if pt is not None else abi.c_double_p(), 0), "lvio2d_scan_to_points")
+        return (cnt, pts, pz, pt) if want_times else (cnt, pts, pz)
+
+    def scan_to_points_device(self, n_scans, n_beams, ranges_ptr, headers_ptr, deskew, count_ptr, points_ptr, z_ptr, time_ptr=0):
+        vp = C.c_void_p
+        self._check(self.lib.lvio2d_scan_to_points(self._h, int(n_scans), int(n_beams), ranges_ptr, headers_ptr, int(bool(deskew)),
+                                                   C.cast(vp(count_ptr), abi.c_int32_p), C.cast(vp(points_ptr), abi.c_double_p),
+                                                   C.cast(vp(z_ptr), abi.c_double_p), C.cast(vp(time_ptr or None), abi.c_double_p), 1),
+                    "lvio2d_scan_to_points")
 
     def eval_laser_factor(self, l1_p1, l1_p2, l2_p1, l2_p2, pose_i, pose_j):
         res, jac = np.zeros(2), np.zeros((2, 12))

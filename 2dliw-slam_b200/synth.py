@@ -481,3 +481,48 @@ def make_scan_batch(n_scans=8, seed=42, beams=1081, fov_deg=270.0, n_interior=8,
         pts_all.append(pts)
         off.append(off[-1] + len(pts))
     return np.array(off, dtype=np.int64), np.concatenate(pts_all).reshape(-1, 2)
+
+
+def make_range_batch(n_scans=8, seed=42, beams=1081, fov_deg=270.0, n_interior=8, range_sigma=0.01, max_range=30.0,
+                     width=10.0, height=8.0, scan_period=0.025, moving=True):
+    """Raw sensor_msgs/LaserScan-style input for lvio2d_scan_to_points: float32 ranges [S][beams] (inf where no wall is
+    hit, a few NaN and sub-0.1 m readings sprinkled in, all of which convert::laser_to_point_times drops) and one
+    lvio2d_scan_header per scan (float32 angle_min / angle_increment / time_increment, double stamp, the laser-frame
+    velocity used by sensor::laser::correct).  Same room generator as make_scan_batch."""
+    rng = np.random.Generator(np.random.MT19937(int(seed)))
+    a0 = np.float32(math.radians(-fov_deg / 2.0))
+    da = np.float32(math.radians(fov_deg) / (beams - 1))
+    ang = (a0 + np.arange(beams, dtype=np.float32) * da).astype(np.float64)
+    ranges = np.full((n_scans, beams), np.inf, dtype=np.float32)
+    hdr = np.zeros(n_scans, dtype=abi.SCAN_HEADER_DTYPE)
+    for k in range(n_scans):
+        segs = [[0, 0, width, 0], [width, 0, width, height], [width, height, 0, height], [0, height, 0, 0]]
+        for _k in range(n_interior):
+            c = rng.uniform([1.0, 1.0], [width - 1.0, height - 1.0])
+            a = rng.uniform(0.0, math.pi)
+            ln = rng.uniform(1.0, 4.0)
+            d = 0.5 * ln * np.array([math.cos(a), math.sin(a)])
+            segs.append([*(c - d), *(c + d)])
+        world = np.array(segs)
+        o = rng.uniform([0.3, 0.3], [width - 0.3, height - 0.3])
+        yaw = rng.uniform(-math.pi, math.pi)
+        d = np.stack([np.cos(ang + yaw), np.sin(ang + yaw)], axis=1)
+        s1, e = world[:, 0:2], world[:, 2:4] - world[:, 0:2]
+        so = s1 - o
+        den = d[:, None, 0] * e[None, :, 1] - d[:, None, 1] * e[None, :, 0]
+        with np.errstate(divide="ignore", invalid="ignore"):
+            rho = (so[None, :, 0] * e[None, :, 1] - so[None, :, 1] * e[None, :, 0]) / den
+            u = (so[None, :, 0] * d[:, None, 1] - so[None, :, 1] * d[:, None, 0]) / den
+        ok = (np.abs(den) > 1e-12) & (rho > 0.02) & (u >= 0.0) & (u <= 1.0)
+        r = np.where(ok, rho, np.inf).min(axis=1)
+        r = np.where(np.isfinite(r) & (r < max_range), r + rng.normal(0.0, range_sigma, size=beams), np.inf)
+        r[rng.uniform(size=beams) < 0.005] = np.nan
+        r[rng.uniform(size=beams) < 0.005] = 0.05
+        ranges[k] = r.astype(np.float32)
+        hdr[k]["angle_min"], hdr[k]["angle_increment"] = a0, da
+        hdr[k]["time_increment"] = np.float32(scan_period / beams)
+        hdr[k]["stamp"] = 1.6e9 + 0.1 * k + rng.uniform(0, 0.01)
+        if moving:
+            hdr[k]["linear"] = rng.normal(0.0, [0.5, 0.05, 0.005])
+            hdr[k]["angular"] = rng.normal(0.0, [0.01, 0.01, 0.5])
+    return ranges, hdr

@@ -333,11 +333,73 @@ def run_ours(args):
     }
     if world == 1:
         result["single_window"] = single_window_latency(P, hb, torch, device)
+        result["next_rows"] = {"scan_lines": scan_lines_rate(P, torch, device, cpu=not args.no_cpu)}
     if world == 1 and not args.no_cpu:
         result["cpu_baseline"] = cpu_baseline(P, hb, seconds=args.cpu_seconds, threads=1)
     print(json.dumps(result))
     if world > 1:
         dist.destroy_process_group()
+
+
+def scan_lines_rate(P, torch, device, n_scans=4096, reps=10, cpu=True):
+    """SURVEY section 8f rank 1 (laser_manager::spawn_scan -> lvio2d_extract_lines): scans/s on 4096 synthetic 1081-beam
+    scans (64 distinct, tiled), device-resident and through host buffers, next to the CPU oracle on one core."""
+    import lvio2d_b200 as L
+    from lvio2d_b200.solver import Context
+
+    lp = L.corridor_line_params()
+    off1, pts1 = L.synth.make_scan_batch(64, 21)
+    tile = n_scans // 64
+    n1 = int(off1[-1])
+    off = np.concatenate([(off1[:-1][None, :] + n1 * np.arange(tile)[:, None]).ravel(), [n1 * tile]]).astype(np.int64)
+    pts = np.tile(pts1, (tile, 1))
+    max_lines = 160
+    out = {"scans": n_scans, "points": int(off[-1]), "unit": "scans/s"}
+    with Context(P) as c:
+        d_off, d_pts = torch.from_numpy(off).to(device), torch.from_numpy(pts).to(device)
+        d_n = torch.zeros(n_scans, dtype=torch.int32, device=device)
+        d_lines = torch.zeros(n_scans * max_lines * 4, dtype=torch.float64, device=device)
+        d_abc = torch.zeros(n_scans * max_lines * 3, dtype=torch.float64, device=device)
+        d_rng = torch.zeros(n_scans * max_lines * 2, dtype=torch.int32, device=device)
+        stream = torch.cuda.ExternalStream(c.stream, device=device)
+
+        def run():
+            c.extract_lines_device(lp, n_scans, d_off.data_ptr(), d_pts.data_ptr(), max_lines, d_n.data_ptr(), d_lines.data_ptr(),
+                                   d_abc.data_ptr(), d_rng.data_ptr())
+
+        for _ in range(3):
+            run()
+        c.sync()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(reps):
+            run()
+        e1.record(stream)
+        c.sync()
+        ms = e0.elapsed_time(e1) / reps
+        n_lines = d_n.cpu().numpy()
+        alg_bytes = float(off[-1]) * 16 + float(n_lines.sum()) * (4 + 3) * 8 + n_scans * 12
+        out.update({"value": n_scans / (ms * 1e-3), "ms_per_launch": ms, "lines_found": int(n_lines.sum()),
+                    "roofline": {"bound": "fp64 ALU / latency (sqrt, div, acos per point; sequential merge per segment)",
+                                 "algorithmic_bytes_per_launch": alg_bytes, "achieved_GBps": alg_bytes / (ms * 1e-3) / 1e9,
+                                 "hbm_peak_GBps": measured_peaks()[0]}})
+        t0 = time.perf_counter()
+        for _ in range(3):
+            c.extract_lines(lp, off, pts, max_lines=max_lines)
+        out["e2e"] = {"value": 3 * n_scans / (time.perf_counter() - t0), "unit": "scans/s",
+                      "api": "lvio2d_extract_lines(host buffers): H2D + kernel + D2H, synchronous"}
+    if cpu:
+        import oracle_lib as O
+
+        O.build()
+        t0 = time.perf_counter()
+        done = 0
+        while time.perf_counter() - t0 < 2.0:
+            O.extract_lines(lp, off1, pts1, max_lines=max_lines)
+            done += 64
+        out["cpu_baseline"] = {"value": done / (time.perf_counter() - t0), "unit": "scans/s", "cores": 1, "kind": "port",
+                               "sample": f"{done} scans (oracle/laser_lines.hpp)"}
+    return out
 
 
 def single_window_latency(P, hb, torch, device, reps=20):

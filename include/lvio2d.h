@@ -278,8 +278,29 @@ typedef struct lvio2d_line_params {
  * on_device = 0: every pointer is a host buffer (copied in and out, synchronous).  on_device = 1: every pointer is a
  * device buffer; the kernel is enqueued on the context's stream and the call returns without synchronising. */
 int lvio2d_extract_lines(lvio2d_ctx* ctx, const lvio2d_line_params* lp, int32_t n_scans, const int64_t* point_offset,
-                         const double* points, int32_t max_lines, int32_t* n_lines, double* lines, double* abc,
-                         int32_t* index_range, int32_t on_device);
+                         const int32_t* point_count /* [S] or NULL: scan s has point_count[s] points from point_offset[s] */,
+                         const double* points, const double* point_z /* [N] or NULL (z = 0) */, int32_t max_lines,
+                         int32_t* n_lines, double* lines, double* abc, int32_t* index_range, int32_t on_device);
+
+/* ---- laser front-end, step 0: LaserScan ranges -> (de-skewed) points.
+ * Replaces convert::laser_to_point_times (src/utilies/common.cpp:4-40: polar -> Cartesian in the laser frame, readings
+ * that are NaN / inf / <= 0.1 m dropped, a point closer than 0.01 m to the last KEPT point dropped) followed by
+ * sensor::laser::correct (src/trajectory/sensor.h:51-94: p <- make_tf(dt*linear, dt*angular) * p with
+ * dt = time_of_beam - stamp), which trajectory::add_laser calls before spawn_scan (trajectory.cpp:147, :195). ---- */
+typedef struct lvio2d_scan_header {
+    float angle_min, angle_increment, time_increment, reserved;  /* sensor_msgs/LaserScan fields, float32 on the wire */
+    double stamp;        /* header.stamp.toSec() */
+    double linear[3];    /* correct(linear, angular): velocity of the laser frame expressed in the laser frame */
+    double angular[3];
+} lvio2d_scan_header;
+/* ranges: [S][n_beams] float32.  Outputs use a fixed stride of n_beams slots per scan: point_count[s] points at
+ * points[s*n_beams ...][2] (x, y), point_z[s*n_beams ...] (0 unless de-skewed) and, when not NULL,
+ * point_time[s*n_beams ...] (the beam time stamps, times_ptr of sensor::laser).  deskew = 0 skips correct().
+ * The fixed-stride layout feeds lvio2d_extract_lines directly (point_offset[s] = s*n_beams, point_count).
+ * on_device as in lvio2d_extract_lines. */
+int lvio2d_scan_to_points(lvio2d_ctx* ctx, int32_t n_scans, int32_t n_beams, const float* ranges,
+                          const lvio2d_scan_header* headers, int32_t deskew, int32_t* point_count, double* points,
+                          double* point_z, double* point_time, int32_t on_device);
 
 #ifdef __cplusplus
 }

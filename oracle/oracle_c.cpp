@@ -11,6 +11,7 @@
 
 #include "solver.hpp"
 #include "laser_lines.hpp"
+#include "scan_points.hpp"
 
 using namespace oracle;
 
@@ -189,8 +190,9 @@ static void normalise_sign(double* v) {
     for (int i = 1; i < 3; ++i) if (std::fabs(v[i]) > std::fabs(v[k])) k = i;
     if (v[k] < 0) for (int i = 0; i < 3; ++i) v[i] = -v[i];
 }
-int oracle_extract_lines(const lvio2d_line_params* lp, int32_t n_scans, const int64_t* point_offset, const double* points,
-                         int32_t max_lines, int32_t* n_lines, double* out_lines, double* abc, int32_t* index_range) {
+int oracle_extract_lines(const lvio2d_line_params* lp, int32_t n_scans, const int64_t* point_offset, const int32_t* point_count,
+                         const double* points, const double* point_z, int32_t max_lines, int32_t* n_lines, double* out_lines,
+                         double* abc, int32_t* index_range) {
     lines::LineParams P;
     P.continuous_threshold = lp->line_continuous_threshold;
     P.max_tolerance_angle = lp->line_max_tolerance_angle_deg / 180.0 * M_PI;
@@ -199,7 +201,8 @@ int oracle_extract_lines(const lvio2d_line_params* lp, int32_t n_scans, const in
     P.h = (int)(lp->h_laser_each_scan / lp->laser_resolution + 1);
     for (int s = 0; s < n_scans; ++s) {
         std::vector<lines::P3> pts;
-        for (int64_t i = point_offset[s]; i < point_offset[s + 1]; ++i) pts.emplace_back(points[2 * i], points[2 * i + 1], 0.0);
+        const int64_t end = point_count ? point_offset[s] + point_count[s] : point_offset[s + 1];
+        for (int64_t i = point_offset[s]; i < end; ++i) pts.emplace_back(points[2 * i], points[2 * i + 1], point_z ? point_z[i] : 0.0);
         const std::vector<lines::Line> L = lines::spawn_scan(P, pts);
         n_lines[s] = (int32_t)L.size();
         for (int k = 0; k < (int)L.size() && k < max_lines; ++k) {
@@ -208,6 +211,21 @@ int oracle_extract_lines(const lvio2d_line_params* lp, int32_t n_scans, const in
             abc[3 * o] = L[k].abc.x; abc[3 * o + 1] = L[k].abc.y; abc[3 * o + 2] = L[k].abc.z;
             normalise_sign(abc + 3 * o);
             index_range[2 * o] = L[k].index1; index_range[2 * o + 1] = L[k].index2;
+        }
+    }
+    return 0;
+}
+// ---- LaserScan ranges -> (de-skewed) points, same argument layout as lvio2d_scan_to_points (host buffers)
+int oracle_scan_to_points(int32_t n_scans, int32_t n_beams, const float* ranges, const lvio2d_scan_header* headers, int32_t deskew,
+                          int32_t* point_count, double* points, double* point_z, double* point_time) {
+    for (int s = 0; s < n_scans; ++s) {
+        scanpts::Points P = scanpts::laser_to_point_times(headers[s], ranges + (size_t)s * n_beams, n_beams);
+        if (deskew) scanpts::correct(headers[s], &P);
+        point_count[s] = (int32_t)P.p.size();
+        for (size_t i = 0; i < P.p.size(); ++i) {
+            const size_t o = (size_t)s * n_beams + i;
+            points[2 * o] = P.p[i].x; points[2 * o + 1] = P.p[i].y; point_z[o] = P.p[i].z;
+            if (point_time) point_time[o] = P.t[i];
         }
     }
     return 0;

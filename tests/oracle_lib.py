@@ -27,7 +27,7 @@ def _d(a):
 
 
 def build(force=False):
-    srcs = ["oracle_c.cpp", "laser_lines.hpp", "solver.hpp", "factors.hpp", "preint.hpp", "lie.hpp", "jet.hpp"]
+    srcs = ["oracle_c.cpp", "laser_lines.hpp", "scan_points.hpp", "solver.hpp", "factors.hpp", "preint.hpp", "lie.hpp", "jet.hpp"]
     newest = max(os.path.getmtime(os.path.join(_ROOT, "oracle", s)) for s in srcs)
     if force or not os.path.exists(_LIB_PATH) or os.path.getmtime(_LIB_PATH) < newest:
         subprocess.check_call(["make", "-C", os.path.join(_ROOT, "oracle"), "-s"])
@@ -186,17 +186,34 @@ def marginalize(params, hb, states=None):
     return X0, J, r, dH, dg
 
 
-def extract_lines(lp, point_offset, points, max_lines=256):
+def extract_lines(lp, point_offset, points, max_lines=256, point_count=None, point_z=None):
     """laser_manager::spawn_scan for a batch of scans (same layout as Context.extract_lines)."""
     off = np.ascontiguousarray(point_offset, dtype=np.int64)
     pts = np.ascontiguousarray(points, dtype=np.float64).reshape(-1, 2)
-    S = len(off) - 1
+    cnt = None if point_count is None else np.ascontiguousarray(point_count, dtype=np.int32)
+    pz = None if point_z is None else np.ascontiguousarray(point_z, dtype=np.float64).reshape(-1)
+    S = len(off) - 1 if cnt is None else len(cnt)
     n = np.zeros(S, np.int32)
     lines, abc, rng = np.zeros((S, max_lines, 4)), np.zeros((S, max_lines, 3)), np.zeros((S, max_lines, 2), np.int32)
-    rc = lib().oracle_extract_lines(C.byref(lp), S, off.ctypes.data_as(abi.c_int64_p), _d(pts), int(max_lines),
+    rc = lib().oracle_extract_lines(C.byref(lp), S, off.ctypes.data_as(abi.c_int64_p),
+                                    cnt.ctypes.data_as(abi.c_int32_p) if cnt is not None else abi.c_int32_p(), _d(pts),
+                                    _d(pz) if pz is not None else dp(), int(max_lines),
                                     n.ctypes.data_as(abi.c_int32_p), _d(lines), _d(abc), rng.ctypes.data_as(abi.c_int32_p))
     assert rc == 0
     return n, lines, abc, rng
+
+
+def scan_to_points(ranges, headers, deskew=True):
+    """convert::laser_to_point_times + sensor::laser::correct (same layout as Context.scan_to_points)."""
+    rg = np.ascontiguousarray(ranges, dtype=np.float32)
+    hd = np.ascontiguousarray(headers, dtype=abi.SCAN_HEADER_DTYPE)
+    S, nb = rg.shape
+    cnt = np.zeros(S, np.int32)
+    pts, pz, pt = np.zeros((S, nb, 2)), np.zeros((S, nb)), np.zeros((S, nb))
+    rc = lib().oracle_scan_to_points(S, nb, C.c_void_p(rg.ctypes.data), C.c_void_p(hd.ctypes.data), int(bool(deskew)),
+                                     cnt.ctypes.data_as(abi.c_int32_p), _d(pts), _d(pz), _d(pt))
+    assert rc == 0
+    return cnt, pts, pz, pt
 
 
 def fit_line(points):

@@ -85,3 +85,52 @@ def test_bench_size_batch_properties(ctx, lp):
         d = lines[s, :k, 2:] - lines[s, :k, :2]
         assert np.all(np.linalg.norm(d, axis=1) >= lp.line_min_len)
         assert np.all(rng[s, :k, 1] - rng[s, :k, 0] >= 2) and np.all(rng[s, 1:k, 0] >= rng[s, :k - 1, 1])
+
+
+# ------------------------------------------------------------------ ranges -> points (lvio2d_scan_to_points)
+@pytest.mark.parametrize("deskew", [False, True])
+def test_scan_to_points_matches_oracle(ctx, oracle, deskew):
+    """Counts and time stamps bit-exact (the float32 angle / time arithmetic is replicated rounding by rounding);
+    coordinates to 1e-12 (device sincos vs libm)."""
+    rg, hd = L.synth.make_range_batch(48, 23)
+    rg[5, :] = np.inf          # a scan without a single return
+    rg[6, 100:400] = 0.3       # a long run of close readings: every beam falls under the 1 cm filter chain
+    cnt, pts, pz, pt = ctx.scan_to_points(rg, hd, deskew=deskew, want_times=True)
+    ocnt, opts, opz, opt = oracle.scan_to_points(rg, hd, deskew=deskew)
+    assert np.array_equal(cnt, ocnt) and cnt[5] == 0
+    for s in range(len(cnt)):
+        k = cnt[s]
+        assert np.abs(pts[s, :k] - opts[s, :k]).max(initial=0.0) < 1e-12
+        assert np.abs(pz[s, :k] - opz[s, :k]).max(initial=0.0) < 1e-12
+        assert np.array_equal(pt[s, :k], opt[s, :k])
+
+
+def test_device_chain_ranges_to_lines(ctx, oracle, lp):
+    """ranges -> de-skewed points -> lines, every buffer device-resident between the two calls, against the oracle chain."""
+    import torch
+
+    rg, hd = L.synth.make_range_batch(32, 31)
+    S, nb = rg.shape
+    dev = torch.device("cuda:0")
+    d_rg = torch.from_numpy(rg).to(dev)
+    d_hd = torch.from_numpy(hd.view(np.uint8).reshape(S, -1).copy()).to(dev)
+    d_cnt = torch.zeros(S, dtype=torch.int32, device=dev)
+    d_pts = torch.zeros(S * nb * 2, dtype=torch.float64, device=dev)
+    d_z = torch.zeros(S * nb, dtype=torch.float64, device=dev)
+    d_off = (torch.arange(S, dtype=torch.int64, device=dev) * nb).contiguous()
+    ML = 192
+    d_n = torch.zeros(S, dtype=torch.int32, device=dev)
+    d_lines = torch.zeros(S * ML * 4, dtype=torch.float64, device=dev)
+    d_abc = torch.zeros(S * ML * 3, dtype=torch.float64, device=dev)
+    d_rng = torch.zeros(S * ML * 2, dtype=torch.int32, device=dev)
+    torch.cuda.synchronize()
+    ctx.scan_to_points_device(S, nb, d_rg.data_ptr(), d_hd.data_ptr(), True, d_cnt.data_ptr(), d_pts.data_ptr(), d_z.data_ptr())
+    ctx.extract_lines_device(lp, S, d_off.data_ptr(), d_pts.data_ptr(), ML, d_n.data_ptr(), d_lines.data_ptr(), d_abc.data_ptr(),
+                             d_rng.data_ptr(), point_count_ptr=d_cnt.data_ptr(), point_z_ptr=d_z.data_ptr())
+    ctx.sync()
+    ocnt, opts, opz, _ = oracle.scan_to_points(rg, hd, deskew=True)
+    want = oracle.extract_lines(lp, np.arange(S) * nb, opts.reshape(-1, 2), max_lines=ML, point_count=ocnt, point_z=opz.reshape(-1))
+    got = (d_n.cpu().numpy(), d_lines.cpu().numpy().reshape(S, ML, 4), d_abc.cpu().numpy().reshape(S, ML, 3),
+           d_rng.cpu().numpy().reshape(S, ML, 2))
+    compare(got, want)
+    assert got[0].sum() > 10 * S
