@@ -85,6 +85,7 @@ struct lvio2d_ctx {
     DevBuf b_tmp[8];
     DevBuf b_ln[14];   // lvio2d_extract_lines: inputs / workspace / outputs
     DevBuf b_sp[7];    // lvio2d_scan_to_points
+    DevBuf b_ml[16];   // lvio2d_match_lines
     double* ext_reduce = nullptr; int64_t ext_reduce_count = 0;
     int step_calls = 0;
     bool have_solution = false;
@@ -457,6 +458,7 @@ void lvio2d_destroy(lvio2d_ctx* ctx) {
     for (auto& b : ctx->b_tmp) b.release();
     for (auto& b : ctx->b_ln) b.release();
     for (auto& b : ctx->b_sp) b.release();
+    for (auto& b : ctx->b_ml) b.release();
     ctx->h_poff.release(); ctx->h_loff.release(); ctx->h_rf.release(); ctx->h_cm.release(); ctx->h_active.release(); ctx->h_active1.release();
     for (auto e : ctx->ev_scan) cudaEventDestroy(e);
     for (auto e : ctx->ev_win) cudaEventDestroy(e);
@@ -878,6 +880,91 @@ int lvio2d_scan_to_points(lvio2d_ctx* ctx, int32_t n_scans, int32_t n_beams, con
         CK(cudaMemcpyAsync(points, B[4].p, NB * sizeof(double2), cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaMemcpyAsync(point_z, B[5].p, NB * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
         if (point_time) CK(cudaMemcpyAsync(point_time, B[6].p, NB * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
+    return LVIO2D_OK;
+}
+
+int lvio2d_match_lines(lvio2d_ctx* ctx, const lvio2d_line_params* lp, int32_t n_pairs, int32_t kk, const int64_t* point_offset1,
+                       const int32_t* point_count1, const double* points1, int32_t max_lines1, const int32_t* n_lines1, const double* lines1,
+                       const int32_t* index_range1, int32_t max_lines2, const int32_t* n_lines2, const double* lines2, const double* pose1,
+                       const double* pose2, int32_t* n_match, int32_t* match, int32_t on_device) {
+    if (!ctx || !lp || n_pairs < 0 || kk < 0 || kk > 2 || max_lines1 < 1 || max_lines2 < 1 || !n_lines1 || !lines1 || !n_lines2 || !lines2 ||
+        !pose1 || !pose2 || !n_match || !match)
+        return LVIO2D_ERR_INVALID_ARG;
+    if (points1 && (!point_offset1 || !index_range1)) return fail(ctx, LVIO2D_ERR_INVALID_ARG, "points1 needs point_offset1 and index_range1");
+    if (!(lp->laser_resolution > 0.0)) return fail(ctx, LVIO2D_ERR_INVALID_ARG, "laser_resolution must be positive");
+    if (n_pairs == 0) return LVIO2D_OK;
+    CK(cudaSetDevice(ctx->device));
+    const size_t P = (size_t)n_pairs;
+    int64_t N1 = 0;
+    const int n_off = point_count1 ? n_pairs : n_pairs + 1;
+    if (points1) {
+        if (on_device) {
+            int64_t last = 0;
+            int32_t last_cnt = 0;
+            CK(cudaMemcpyAsync(&last, point_offset1 + n_off - 1, sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
+            if (point_count1) CK(cudaMemcpyAsync(&last_cnt, point_count1 + n_pairs - 1, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+            CK(cudaStreamSynchronize(ctx->stream));
+            N1 = last + last_cnt;
+        } else {
+            for (int32_t p = 0; p < n_pairs; ++p) {
+                const int64_t end = point_count1 ? point_offset1[p] + point_count1[p] : point_offset1[p + 1];
+                if (end < point_offset1[p] || point_offset1[p] < 0) return fail(ctx, LVIO2D_ERR_INVALID_ARG, "offsets must be non-decreasing");
+                N1 = std::max(N1, end);
+            }
+        }
+    }
+    DevBuf* B = ctx->b_ml;
+    const size_t nn = (size_t)std::max<int64_t>(N1, 1);
+    bool ok = B[0].ensure(nn * sizeof(int32_t)) && B[1].ensure(P * max_lines2 * sizeof(double)) && B[2].ensure(P * max_lines2 * 2 * sizeof(int32_t));
+    if (!on_device)
+        ok = ok && B[3].ensure((P + 1) * sizeof(int64_t)) && B[4].ensure(P * sizeof(int32_t)) && B[5].ensure(nn * sizeof(double2)) &&
+             B[6].ensure(P * sizeof(int32_t)) && B[7].ensure(P * max_lines1 * sizeof(double4)) && B[8].ensure(P * max_lines1 * 2 * sizeof(int32_t)) &&
+             B[9].ensure(P * sizeof(int32_t)) && B[10].ensure(P * max_lines2 * sizeof(double4)) && B[11].ensure(P * 6 * sizeof(double)) &&
+             B[12].ensure(P * 6 * sizeof(double)) && B[13].ensure(P * sizeof(int32_t)) && B[14].ensure(P * max_lines2 * 2 * sizeof(int32_t));
+    if (!ok) return fail(ctx, LVIO2D_ERR_ALLOC, "cudaMalloc(match_lines)");
+    MatchLinesArgs a;
+    std::memset(&a, 0, sizeof(a));
+    a.max_lines1 = max_lines1; a.max_lines2 = max_lines2; a.n_pairs = n_pairs; a.kk = kk;
+    std::memcpy(a.T_il, ctx->params.T_imu_to_laser, sizeof(a.T_il));
+    a.resolution = lp->laser_resolution;
+    a.w = (int)(lp->w_laser_each_scan / lp->laser_resolution + 1);
+    a.h = (int)(lp->h_laser_each_scan / lp->laser_resolution + 1);
+    a.cells = B[0].as<int32_t>(); a.diss = B[1].as<double>(); a.prov = B[2].as<int32_t>();
+    if (on_device) {
+        a.point_offset1 = point_offset1; a.point_count1 = point_count1; a.points1 = reinterpret_cast<const double2*>(points1);
+        a.n_lines1 = n_lines1; a.lines1 = reinterpret_cast<const double4*>(lines1); a.index_range1 = index_range1;
+        a.n_lines2 = n_lines2; a.lines2 = reinterpret_cast<const double4*>(lines2); a.pose1 = pose1; a.pose2 = pose2;
+        a.n_match = n_match; a.match = match;
+    } else {
+        auto up = [&](DevBuf& b, const void* src, size_t bytes) -> cudaError_t {
+            return (src && bytes) ? cudaMemcpyAsync(b.p, src, bytes, cudaMemcpyHostToDevice, ctx->stream) : cudaSuccess;
+        };
+        CK(up(B[3], points1 ? point_offset1 : nullptr, (size_t)n_off * sizeof(int64_t)));
+        CK(up(B[4], points1 ? point_count1 : nullptr, P * sizeof(int32_t)));
+        CK(up(B[5], points1, (size_t)N1 * sizeof(double2)));
+        CK(up(B[6], n_lines1, P * sizeof(int32_t)));
+        CK(up(B[7], lines1, P * max_lines1 * sizeof(double4)));
+        CK(up(B[8], index_range1, P * max_lines1 * 2 * sizeof(int32_t)));
+        CK(up(B[9], n_lines2, P * sizeof(int32_t)));
+        CK(up(B[10], lines2, P * max_lines2 * sizeof(double4)));
+        CK(up(B[11], pose1, P * 6 * sizeof(double)));
+        CK(up(B[12], pose2, P * 6 * sizeof(double)));
+        CK(cudaMemsetAsync(B[14].p, 0, P * max_lines2 * 2 * sizeof(int32_t), ctx->stream));
+        a.point_offset1 = points1 ? B[3].as<int64_t>() : nullptr; a.point_count1 = (points1 && point_count1) ? B[4].as<int32_t>() : nullptr;
+        a.points1 = points1 ? B[5].as<double2>() : nullptr;
+        a.n_lines1 = B[6].as<int32_t>(); a.lines1 = B[7].as<double4>(); a.index_range1 = index_range1 ? B[8].as<int32_t>() : nullptr;
+        a.n_lines2 = B[9].as<int32_t>(); a.lines2 = B[10].as<double4>(); a.pose1 = B[11].as<double>(); a.pose2 = B[12].as<double>();
+        a.n_match = B[13].as<int32_t>(); a.match = B[14].as<int32_t>();
+    }
+    const int wpc = 4;
+    match_lines_kernel<<<(n_pairs + wpc - 1) / wpc, wpc * 32, 0, ctx->stream>>>(a);
+    ctx->launches += 1;
+    CK(cudaGetLastError());
+    if (!on_device) {
+        CK(cudaMemcpyAsync(n_match, B[13].p, P * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaMemcpyAsync(match, B[14].p, P * max_lines2 * 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));
     }
     return LVIO2D_OK;

@@ -385,4 +385,140 @@ __global__ void __launch_bounds__(128) scan_points_kernel(ScanPointsArgs a) {
     }
 }
 
+// =====================================================================================================
+// Segment association: laser_manager::do_match (reference src/trajectory/laser_manager.cpp:244-348), one warp per scan
+// pair.  scan 1's line_map (a 1001 x 1001 grid of line lists in the reference) is never built: for a line of scan 2
+// only the (2a+1)^2 cells around its transformed mid point matter, so every lane takes lines of scan 1, walks their
+// rasterisation (packed cell indices of the line's own points, precomputed once per pair; or the 0.05 m samples of the
+// sub-map flavour) and records which of those cells the line covers as a bit mask.  Candidate order of the reference =
+// (cell in raster order, line index), so "first candidate of smallest angle" = lexicographic minimum of
+// (angle, lowest covered cell, line index), reduced across the warp.
+struct MatchLinesArgs {
+    const int64_t* point_offset1; const int32_t* point_count1; const double2* points1;   // points1 == nullptr: sampled flavour
+    int32_t max_lines1; const int32_t* n_lines1; const double4* lines1; const int32_t* index_range1;
+    int32_t max_lines2; const int32_t* n_lines2; const double4* lines2;
+    const double* pose1; const double* pose2;    // [P][6]
+    double T_il[12];
+    int32_t n_pairs, kk, w, h;
+    double resolution;
+    int32_t* cells;     // workspace [N1]: r << 16 | c of every scan-1 point, -1 when off the grid
+    double* diss;       // workspace [P][max_lines2]
+    int32_t* prov;      // workspace [P][max_lines2][2]: pairs before the distance filter
+    int32_t* n_match;   // [P]
+    int32_t* match;     // [P][max_lines2][2]
+};
+
+__device__ __forceinline__ int match_cell(const MatchLinesArgs& a, double x, double y) {
+    const int c = (int)(x / a.resolution + a.w / 2), r = (int)(y / a.resolution + a.h / 2);
+    return (r >= 0 && r < a.h && c >= 0 && c < a.w) ? ((r << 16) | c) : -1;
+}
+// e_laser::dis_from_line (common.h:86-95) for a 3-D point against a line in the plane z = 0
+__device__ __forceinline__ double match_dis_from_line(const V3<double>& p, double4 l) {
+    double ux = l.z - l.x, uy = l.w - l.y;
+    const double n = sqrt(ux * ux + uy * uy);
+    if (n * n > 0.0) { ux /= n; uy /= n; }
+    const double rx = p.x - l.z, ry = p.y - l.w, rz = p.z;
+    const double t = ux * rx + uy * ry;
+    const double ex = rx - t * ux, ey = ry - t * uy;
+    return sqrt(ex * ex + ey * ey + rz * rz);
+}
+
+__global__ void __launch_bounds__(128) match_lines_kernel(MatchLinesArgs a) {
+    const int lane = threadIdx.x & 31;
+    const int p = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (p >= a.n_pairs) return;
+    const int n1 = min(a.n_lines1[p], a.max_lines1), n2 = min(a.n_lines2[p], a.max_lines2);
+    const double4* L1 = a.lines1 + (size_t)p * a.max_lines1;
+    const double4* L2 = a.lines2 + (size_t)p * a.max_lines2;
+    const int32_t* R1 = a.index_range1 ? a.index_range1 + (size_t)p * a.max_lines1 * 2 : nullptr;
+    double* diss = a.diss + (size_t)p * a.max_lines2;
+    int32_t* prov = a.prov + (size_t)p * a.max_lines2 * 2;
+    int32_t* out = a.match + (size_t)p * a.max_lines2 * 2;
+    // T_1_2 = (make_tf(p1, q1) T_il)^-1 (make_tf(p2, q2) T_il)
+    const Iso Til = load_iso(a.T_il);
+    const double* s1 = a.pose1 + 6 * (size_t)p;
+    const double* s2 = a.pose2 + 6 * (size_t)p;
+    const M3<double> Ra = mul(exp_so3(v3<double>(s1[3], s1[4], s1[5])), Til.R), Rb = mul(exp_so3(v3<double>(s2[3], s2[4], s2[5])), Til.R);
+    const V3<double> ta = mul(exp_so3(v3<double>(s1[3], s1[4], s1[5])), Til.t) + v3<double>(s1[0], s1[1], s1[2]);
+    const V3<double> tb = mul(exp_so3(v3<double>(s2[3], s2[4], s2[5])), Til.t) + v3<double>(s2[0], s2[1], s2[2]);
+    const M3<double> R12 = mul_tn(Ra, Rb);
+    const V3<double> t12 = mul_t(Ra, tb - ta);
+    auto tf = [&](double x, double y) -> V3<double> { return mul(R12, v3<double>(x, y, 0.0)) + t12; };
+
+    // packed cells of scan 1's points
+    int64_t q0 = 0;
+    if (a.points1) {
+        q0 = a.point_offset1[p];
+        const int np = a.point_count1 ? a.point_count1[p] : (int)(a.point_offset1[p + 1] - q0);
+        for (int i = lane; i < np; i += 32) { const double2 q = a.points1[q0 + i]; a.cells[q0 + i] = match_cell(a, q.x, q.y); }
+        __syncwarp();
+    }
+    const int aa = 1 + a.kk, side = 2 * aa + 1;
+    int count = 0;
+    for (int i = 0; i < n2; ++i) {
+        const double4 l2 = L2[i];
+        const V3<double> tm = tf((l2.x + l2.z) / 2.0, (l2.y + l2.w) / 2.0);
+        const int c = (int)(tm.x / a.resolution + a.w / 2), r = (int)(tm.y / a.resolution + a.h / 2);
+        const V3<double> e1 = tf(l2.x, l2.y), e2 = tf(l2.z, l2.w);
+        V3<double> v2 = e2 - e1;
+        { const double n = norm(v2); if (n * n > 0.0) v2 = scale(v2, 1.0 / n); }   // (Eigen normalized(): v / norm)
+        double best_angle = 1e300;
+        int best_cell = 64, best_j = 0x7fffffff;
+        for (int j = lane; j < n1; j += 32) {
+            unsigned long long mask = 0ull;
+            auto cover = [&](int cell) {
+                if (cell < 0) return;
+                const int dr = (cell >> 16) - r + aa, dc = (cell & 0xffff) - c + aa;
+                if (dr >= 0 && dr < side && dc >= 0 && dc < side) mask |= 1ull << (dr * side + dc);
+            };
+            const double4 l1 = L1[j];
+            if (a.points1) {
+                for (int q = R1[2 * j]; q <= R1[2 * j + 1]; ++q) cover(a.cells[q0 + q]);
+            } else {
+                const double dx = l1.z - l1.x, dy = l1.w - l1.y, len = sqrt(dx * dx + dy * dy);
+                double ux = dx, uy = dy;
+                if (len * len > 0.0) { ux /= len; uy /= len; }
+                for (double tr = 0; tr <= len; tr += 0.05) cover(match_cell(a, l1.x + ux * tr, l1.y + uy * tr));
+            }
+            if (!mask) continue;
+            double v1x = l1.z - l1.x, v1y = l1.w - l1.y;
+            { const double n = sqrt(v1x * v1x + v1y * v1y); if (n * n > 0.0) { v1x /= n; v1y /= n; } }
+            const double angle = acos(fabs(v1x * v2.x + v1y * v2.y));
+            const int cell = __ffsll((long long)mask) - 1;
+            if (angle < best_angle || (angle == best_angle && (cell < best_cell || (cell == best_cell && j < best_j)))) {
+                best_angle = angle; best_cell = cell; best_j = j;
+            }
+        }
+        // lexicographic minimum of (angle, cell, j) over the warp; lanes without a candidate carry (1e300, 64, INT_MAX)
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) {
+            const double oa = __shfl_xor_sync(0xffffffffu, best_angle, d);
+            const int oc = __shfl_xor_sync(0xffffffffu, best_cell, d), oj = __shfl_xor_sync(0xffffffffu, best_j, d);
+            if (oa < best_angle || (oa == best_angle && (oc < best_cell || (oc == best_cell && oj < best_j)))) { best_angle = oa; best_cell = oc; best_j = oj; }
+        }
+        if (best_j == 0x7fffffff) continue;                     // no candidate (or only NaN angles)
+        if (best_angle / kPi * 180.0 > 10.0) continue;
+        diss[count] = 0.5 * (match_dis_from_line(e1, L1[best_j]) + match_dis_from_line(e2, L1[best_j]));   // same value on every lane
+        if (lane == 0) { prov[2 * count] = best_j; prov[2 * count + 1] = i; }
+        ++count;
+    }
+    __syncwarp();
+    // mean end-point distance (summed in the reference's order), then the 1.2 x filter
+    double aver = 0.0;
+    for (int k = 0; k < count; ++k) aver += diss[k];
+    aver /= (double)count;
+    int kept = 0;
+    for (int base = 0; base < count; base += 32) {
+        const int k = base + lane;
+        const bool keep = k < count && diss[k] < aver * 1.2;
+        const unsigned m = __ballot_sync(0xffffffffu, keep);
+        if (keep) {
+            const int o = kept + __popc(m & ((1u << lane) - 1u));
+            out[2 * o] = prov[2 * k]; out[2 * o + 1] = prov[2 * k + 1];
+        }
+        kept += __popc(m);
+    }
+    if (lane == 0) a.n_match[p] = kept;
+}
+
 }  // namespace lv

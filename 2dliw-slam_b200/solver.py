@@ -30,7 +30,7 @@ EXPORTS = [
     "lvio2d_set_reduce_buffer", "lvio2d_lm_step", "lvio2d_linearize", "lvio2d_marginalize", "lvio2d_imu_preintegrate",
     "lvio2d_wheel_preintegrate", "lvio2d_eval_laser_factor", "lvio2d_eval_imu_factor", "lvio2d_eval_wheel_factor",
     "lvio2d_eval_ground_factors", "lvio2d_set_profiling", "lvio2d_get_profile", "lvio2d_set_windows_async", "lvio2d_get_states_async",
-    "lvio2d_extract_lines", "lvio2d_scan_to_points",
+    "lvio2d_extract_lines", "lvio2d_scan_to_points", "lvio2d_match_lines",
 ]
 
 
@@ -86,6 +86,9 @@ def load_library(path=LIB_PATH):
     lib.lvio2d_get_states_async.argtypes = [vp, vp]
     lib.lvio2d_extract_lines.argtypes = [vp, C.POINTER(abi.LineParams), C.c_int32, abi.c_int64_p, abi.c_int32_p, dp, dp, C.c_int32,
                                          abi.c_int32_p, dp, dp, abi.c_int32_p, C.c_int32]
+    lib.lvio2d_match_lines.argtypes = [vp, C.POINTER(abi.LineParams), C.c_int32, C.c_int32, abi.c_int64_p, abi.c_int32_p, dp, C.c_int32,
+                                       abi.c_int32_p, dp, abi.c_int32_p, C.c_int32, abi.c_int32_p, dp, dp, dp, abi.c_int32_p, abi.c_int32_p,
+                                       C.c_int32]
     lib.lvio2d_scan_to_points.argtypes = [vp, C.c_int32, C.c_int32, vp, vp, C.c_int32, abi.c_int32_p, dp, dp, dp, C.c_int32]
     lib.lvio2d_get_profile.argtypes = [vp, dp]
     _lib = lib
@@ -300,6 +303,31 @@ class Context:
             C.cast(vp(point_z_ptr or None), abi.c_double_p), int(max_lines), C.cast(vp(n_lines_ptr), abi.c_int32_p),
             C.cast(vp(lines_ptr), abi.c_double_p), C.cast(vp(abc_ptr), abi.c_double_p), C.cast(vp(range_ptr), abi.c_int32_p), 1),
             "lvio2d_extract_lines")
+
+    def match_lines(self, line_params, n_lines1, lines1, n_lines2, lines2, pose1, pose2, kk=0, point_offset1=None, points1=None,
+                    index_range1=None, point_count1=None):
+        """laser_manager::do_match for a batch of scan pairs (host buffers).  lines* [P][max_lines*][4] as returned by
+        extract_lines; with points1 / index_range1 scan 1's cells are those of its lines' own points, otherwise the
+        0.05 m samples along each segment.  Returns n_match [P], match [P][max_lines2][2] = (line of scan 1, line of scan 2)."""
+        l1, l2 = np.ascontiguousarray(lines1, dtype=np.float64), np.ascontiguousarray(lines2, dtype=np.float64)
+        n1, n2 = np.ascontiguousarray(n_lines1, dtype=np.int32), np.ascontiguousarray(n_lines2, dtype=np.int32)
+        P, m1, m2 = len(n1), l1.shape[1], l2.shape[1]
+        s1, s2 = np.ascontiguousarray(pose1, dtype=np.float64).reshape(P, 6), np.ascontiguousarray(pose2, dtype=np.float64).reshape(P, 6)
+        i32 = abi.c_int32_p
+        off = pts = rng = cnt = None
+        if points1 is not None:
+            off = np.ascontiguousarray(point_offset1, dtype=np.int64)
+            pts = np.ascontiguousarray(points1, dtype=np.float64).reshape(-1, 2)
+            rng = np.ascontiguousarray(index_range1, dtype=np.int32)
+            cnt = None if point_count1 is None else np.ascontiguousarray(point_count1, dtype=np.int32)
+        nm = np.zeros(P, np.int32)
+        match = np.zeros((P, m2, 2), np.int32)
+        self._check(self.lib.lvio2d_match_lines(
+            self._h, C.byref(line_params), P, int(kk), off.ctypes.data_as(abi.c_int64_p) if off is not None else abi.c_int64_p(),
+            cnt.ctypes.data_as(i32) if cnt is not None else i32(), _d(pts) if pts is not None else abi.c_double_p(), m1,
+            n1.ctypes.data_as(i32), _d(l1), rng.ctypes.data_as(i32) if rng is not None else i32(), m2, n2.ctypes.data_as(i32), _d(l2),
+            _d(s1), _d(s2), nm.ctypes.data_as(i32), match.ctypes.data_as(i32), 0), "lvio2d_match_lines")
+        return nm, match
 
     def scan_to_points(self, ranges, headers, deskew=True, want_times=False):
         """convert::laser_to_point_times + sensor::laser::correct for a batch of scans (host buffers).  ranges [S][n_beams]

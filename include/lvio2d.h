@@ -302,6 +302,25 @@ int lvio2d_scan_to_points(lvio2d_ctx* ctx, int32_t n_scans, int32_t n_beams, con
                           const lvio2d_scan_header* headers, int32_t deskew, int32_t* point_count, double* points,
                           double* point_z, double* point_time, int32_t on_device);
 
+/* ---- laser front-end, step 2: segment association between a reference scan and the
+ * current scan.  Replaces laser_manager::do_match (src/trajectory/laser_manager.cpp:244-348) for a batch of scan
+ * pairs: every line of scan 2 is taken to scan 1's frame (T_1_2 from the two IMU poses and T_imu_to_laser), the lines
+ * rasterised into the (2*(1+kk)+1)^2 cell neighbourhood of its mid point in scan 1's line_map are the candidates, the
+ * candidate of smallest direction angle wins (first one on ties, in the reference's cell / insertion order), pairs
+ * above 10 degrees are dropped, then pairs whose mean end-point distance is >= 1.2 x the average are dropped.
+ * scan 1's line_map is never materialised: a line covers a cell when one of its own points (points1 / index_range1,
+ * the spawn_scan flavour of scan::add_line, :155-191) or, with points1 == NULL, one of the samples taken every 0.05 m
+ * along the segment (the sub-map flavour add_line(p1, p2, false), :192-212) falls into it.
+ * Layouts as produced by lvio2d_extract_lines: lines* [P][max_lines*][4], n_lines* [P], index_range1 [P][max_lines1][2];
+ * scan 1's points as [point_offset1[p] .. +point_count1[p]) (point_count1 == NULL: offsets are [P+1]).
+ * pose1 / pose2: [P][6] (p, q) of the IMU.  Outputs: n_match [P], match [P][max_lines2][2] = (line of scan 1, line of
+ * scan 2) in the reference's order.  on_device as above. */
+int lvio2d_match_lines(lvio2d_ctx* ctx, const lvio2d_line_params* lp, int32_t n_pairs, int32_t kk,
+                       const int64_t* point_offset1, const int32_t* point_count1, const double* points1,
+                       int32_t max_lines1, const int32_t* n_lines1, const double* lines1, const int32_t* index_range1,
+                       int32_t max_lines2, const int32_t* n_lines2, const double* lines2,
+                       const double* pose1, const double* pose2, int32_t* n_match, int32_t* match, int32_t on_device);
+
 #ifdef __cplusplus
 }
 #endif

@@ -12,6 +12,7 @@
 #include "solver.hpp"
 #include "laser_lines.hpp"
 #include "scan_points.hpp"
+#include "laser_match.hpp"
 
 using namespace oracle;
 
@@ -226,6 +227,45 @@ int oracle_scan_to_points(int32_t n_scans, int32_t n_beams, const float* ranges,
             const size_t o = (size_t)s * n_beams + i;
             points[2 * o] = P.p[i].x; points[2 * o + 1] = P.p[i].y; point_z[o] = P.p[i].z;
             if (point_time) point_time[o] = P.t[i];
+        }
+    }
+    return 0;
+}
+// ---- laser_manager::do_match for a batch of scan pairs, same argument layout as lvio2d_match_lines (host buffers)
+int oracle_match_lines(const lvio2d_params* prm, const lvio2d_line_params* lp, int32_t n_pairs, int32_t kk, const int64_t* point_offset1,
+                       const int32_t* point_count1, const double* points1, int32_t max_lines1, const int32_t* n_lines1, const double* lines1,
+                       const int32_t* index_range1, int32_t max_lines2, const int32_t* n_lines2, const double* lines2, const double* pose1,
+                       const double* pose2, int32_t* n_match, int32_t* out) {
+    Params PR(*prm);
+    lines::LineParams P;
+    P.continuous_threshold = lp->line_continuous_threshold;
+    P.max_tolerance_angle = lp->line_max_tolerance_angle_deg / 180.0 * M_PI;
+    P.max_dis = lp->line_max_dis; P.min_len = lp->line_min_len; P.resolution = lp->laser_resolution;
+    P.w = (int)(lp->w_laser_each_scan / lp->laser_resolution + 1);
+    P.h = (int)(lp->h_laser_each_scan / lp->laser_resolution + 1);
+    for (int p = 0; p < n_pairs; ++p) {
+        std::vector<match::Seg> L1, L2;
+        for (int j = 0; j < std::min(n_lines1[p], max_lines1); ++j) {
+            const double* l = lines1 + ((size_t)p * max_lines1 + j) * 4;
+            match::Seg s{lines::P3(l[0], l[1], 0.0), lines::P3(l[2], l[3], 0.0), 0, -1};
+            if (index_range1) { s.index1 = index_range1[((size_t)p * max_lines1 + j) * 2]; s.index2 = index_range1[((size_t)p * max_lines1 + j) * 2 + 1]; }
+            L1.push_back(s);
+        }
+        for (int i = 0; i < std::min(n_lines2[p], max_lines2); ++i) {
+            const double* l = lines2 + ((size_t)p * max_lines2 + i) * 4;
+            L2.push_back(match::Seg{lines::P3(l[0], l[1], 0.0), lines::P3(l[2], l[3], 0.0), 0, -1});
+        }
+        std::vector<lines::P3> pts;
+        if (points1) {
+            const int64_t b = point_offset1[p], e = point_count1 ? b + point_count1[p] : point_offset1[p + 1];
+            for (int64_t i = b; i < e; ++i) pts.emplace_back(points1[2 * i], points1[2 * i + 1], 0.0);
+        }
+        const match::Grid g = match::build_grid(P, L1, points1 ? &pts : nullptr);
+        const auto pairs = match::do_match(P, PR.T_imu_to_laser, L1, g, L2, pose1 + 6 * p, pose2 + 6 * p, kk);
+        n_match[p] = (int32_t)pairs.size();
+        for (size_t k = 0; k < pairs.size() && (int)k < max_lines2; ++k) {
+            out[((size_t)p * max_lines2 + k) * 2] = pairs[k].first;
+            out[((size_t)p * max_lines2 + k) * 2 + 1] = pairs[k].second;
         }
     }
     return 0;

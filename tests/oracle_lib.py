@@ -27,7 +27,7 @@ def _d(a):
 
 
 def build(force=False):
-    srcs = ["oracle_c.cpp", "laser_lines.hpp", "scan_points.hpp", "solver.hpp", "factors.hpp", "preint.hpp", "lie.hpp", "jet.hpp"]
+    srcs = ["oracle_c.cpp", "laser_lines.hpp", "scan_points.hpp", "laser_match.hpp", "solver.hpp", "factors.hpp", "preint.hpp", "lie.hpp", "jet.hpp"]
     newest = max(os.path.getmtime(os.path.join(_ROOT, "oracle", s)) for s in srcs)
     if force or not os.path.exists(_LIB_PATH) or os.path.getmtime(_LIB_PATH) < newest:
         subprocess.check_call(["make", "-C", os.path.join(_ROOT, "oracle"), "-s"])
@@ -214,6 +214,30 @@ def scan_to_points(ranges, headers, deskew=True):
                                      cnt.ctypes.data_as(abi.c_int32_p), _d(pts), _d(pz), _d(pt))
     assert rc == 0
     return cnt, pts, pz, pt
+
+
+def match_lines(params, lp, n_lines1, lines1, n_lines2, lines2, pose1, pose2, kk=0, point_offset1=None, points1=None,
+                index_range1=None, point_count1=None):
+    """laser_manager::do_match for a batch of scan pairs (same layout as Context.match_lines)."""
+    l1, l2 = np.ascontiguousarray(lines1, dtype=np.float64), np.ascontiguousarray(lines2, dtype=np.float64)
+    n1, n2 = np.ascontiguousarray(n_lines1, dtype=np.int32), np.ascontiguousarray(n_lines2, dtype=np.int32)
+    P, m1, m2 = len(n1), l1.shape[1], l2.shape[1]
+    s1, s2 = _arr(pose1).reshape(P, 6), _arr(pose2).reshape(P, 6)
+    i32 = abi.c_int32_p
+    off = pts = rng = cnt = None
+    if points1 is not None:
+        off = np.ascontiguousarray(point_offset1, dtype=np.int64)
+        pts = _arr(points1).reshape(-1, 2)
+        rng = np.ascontiguousarray(index_range1, dtype=np.int32)
+        cnt = None if point_count1 is None else np.ascontiguousarray(point_count1, dtype=np.int32)
+    nm = np.zeros(P, np.int32)
+    match = np.zeros((P, m2, 2), np.int32)
+    rc = lib().oracle_match_lines(C.byref(params), C.byref(lp), P, int(kk), off.ctypes.data_as(abi.c_int64_p) if off is not None else abi.c_int64_p(),
+                                  cnt.ctypes.data_as(i32) if cnt is not None else i32(), _d(pts) if pts is not None else dp(), m1,
+                                  n1.ctypes.data_as(i32), _d(l1), rng.ctypes.data_as(i32) if rng is not None else i32(), m2,
+                                  n2.ctypes.data_as(i32), _d(l2), _d(s1), _d(s2), nm.ctypes.data_as(i32), match.ctypes.data_as(i32))
+    assert rc == 0
+    return nm, match
 
 
 def fit_line(points):

@@ -134,3 +134,46 @@ def test_device_chain_ranges_to_lines(ctx, oracle, lp):
            d_rng.cpu().numpy().reshape(S, ML, 2))
     compare(got, want)
     assert got[0].sum() > 10 * S
+
+
+# ------------------------------------------------------------------ segment association (lvio2d_match_lines)
+def _pairs(oracle, lp, n_pairs, seed, guess_noise=0.0):
+    """Scan pairs of one world seen from two nearby poses (synthetic windows of 2 frames), their lines and IMU poses."""
+    sb = L.synth.make_batch(n_pairs, seed, n_frames=2, beams=1081, n_segments=12, frame_dt=0.3)
+    off = sb.point_offset
+    n, lines, abc, rng = oracle.extract_lines(lp, off, sb.points, max_lines=128)
+    i1, i2 = np.arange(0, 2 * n_pairs, 2), np.arange(1, 2 * n_pairs, 2)
+    g = np.random.default_rng(seed)
+    pose1, pose2 = sb.truth[i1, :6].copy(), sb.truth[i2, :6] + g.normal(0.0, guess_noise, (n_pairs, 6))
+    return dict(n1=n[i1], l1=lines[i1], r1=rng[i1], n2=n[i2], l2=lines[i2], pose1=pose1, pose2=pose2, off1=off[i1],
+                cnt1=np.diff(off)[i1].astype(np.int32), pts=sb.points)
+
+
+@pytest.mark.parametrize("kk,noise", [(0, 0.0), (0, 0.01), (1, 0.02)])
+def test_match_lines_matches_oracle(ctx, oracle, lp, kk, noise):
+    """Integer outputs: bit-exact, both rasterisation flavours (a line's own points / 0.05 m samples)."""
+    P = L.corridor_params()
+    d = _pairs(oracle, lp, 24, 100 + kk, noise)
+    for flavour in ("points", "samples"):
+        kw = dict(point_offset1=d["off1"], points1=d["pts"], index_range1=d["r1"], point_count1=d["cnt1"]) if flavour == "points" else {}
+        nm, m = ctx.match_lines(lp, d["n1"], d["l1"], d["n2"], d["l2"], d["pose1"], d["pose2"], kk=kk, **kw)
+        onm, om = oracle.match_lines(P, lp, d["n1"], d["l1"], d["n2"], d["l2"], d["pose1"], d["pose2"], kk=kk, **kw)
+        assert np.array_equal(nm, onm), flavour
+        for p in range(len(nm)):
+            assert np.array_equal(m[p, :nm[p]], om[p, :nm[p]]), (flavour, p)
+        assert nm.sum() > 5 * len(nm)
+
+
+def test_match_lines_edge_cases(ctx, oracle, lp):
+    P = L.corridor_params()
+    d = _pairs(oracle, lp, 4, 7)
+    # a pair without lines in scan 2, one without lines in scan 1, and a pose so far off that no cell neighbourhood is hit
+    d["n2"][0] = 0
+    d["n1"][1] = 0
+    d["pose2"][2, 0:2] += 40.0
+    nm, m = ctx.match_lines(lp, d["n1"], d["l1"], d["n2"], d["l2"], d["pose1"], d["pose2"], point_offset1=d["off1"], points1=d["pts"],
+                            index_range1=d["r1"], point_count1=d["cnt1"])
+    onm, om = oracle.match_lines(P, lp, d["n1"], d["l1"], d["n2"], d["l2"], d["pose1"], d["pose2"], point_offset1=d["off1"],
+                                 points1=d["pts"], index_range1=d["r1"], point_count1=d["cnt1"])
+    assert np.array_equal(nm, onm) and nm[0] == 0 and nm[1] == 0 and nm[2] == 0 and nm[3] > 0
+    assert np.array_equal(m[3, :nm[3]], om[3, :nm[3]])
