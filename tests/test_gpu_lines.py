@@ -177,3 +177,42 @@ def test_match_lines_edge_cases(ctx, oracle, lp):
                                  points1=d["pts"], index_range1=d["r1"], point_count1=d["cnt1"])
     assert np.array_equal(nm, onm) and nm[0] == 0 and nm[1] == 0 and nm[2] == 0 and nm[3] > 0
     assert np.array_equal(m[3, :nm[3]], om[3, :nm[3]])
+
+
+def test_front_end_chain_feeds_the_solver(oracle, lp):
+    """points -> lines -> association -> laser_match -> solver::solve, every step on the device path, against the same
+    chain on the CPU oracle: the solved pose of the new frame agrees to 1e-6 (bar 1e-4 m / rad)."""
+    from lvio2d_b200.solver import Context, FrameInfo, LaserMatch, Line, Solver
+
+    P = L.corridor_params(max_iters=10)
+    sb = L.synth.make_batch(3, 77, n_frames=2, beams=1081, n_segments=12, frame_dt=0.3)
+    off = sb.point_offset
+    hb = oracle.preintegrate_batch(P, sb)
+    imu, wheel = hb["imu"].reshape(-1, 466), hb["wheel"].reshape(-1, 15)
+
+    def run(extract, match, make_solver):
+        out = []
+        n, lines, _, rng = extract(lp, off, sb.points)
+        for w in range(3):
+            a, b = 2 * w, 2 * w + 1
+            nm, m = match(n[[a]], lines[[a]], n[[b]], lines[[b]], sb.truth[[a], :6], sb.states[[b], :6],
+                          point_offset1=off[[a]], points1=sb.points, index_range1=rng[[a]], point_count1=np.diff(off)[[a]].astype(np.int32))
+            assert nm[0] >= 3
+            l1 = [Line([*lines[a, j, :2], 0.0], [*lines[a, j, 2:], 0.0]) for j, _ in m[0, :nm[0]]]
+            l2 = [Line([*lines[b, i, :2], 0.0], [*lines[b, i, 2:], 0.0]) for _, i in m[0, :nm[0]]]
+            f0 = FrameInfo(0.0, *np.split(sb.truth[a], [3, 6, 9]))
+            sg = sb.states[b]
+            f1 = FrameInfo(0.3, sg[0:3], sg[3:6], sg[6:9], sg[9:15], imu[w], wheel[w])
+            f1.add_laser_match(LaserMatch(l1, l2, sb.truth[a, 0:3], sb.truth[a, 3:6]))
+            sol = make_solver()
+            sol.solve([f0, f1])
+            out.append(np.r_[f1.p, f1.q])
+        return np.array(out)
+
+    with Context(P) as c:
+        got = run(lambda *a: c.extract_lines(*a, max_lines=128), lambda *a, **k: c.match_lines(lp, *a, **k),
+                  lambda: Solver(P, fast_mode=True, ctx=c))
+    want = run(lambda *a: oracle.extract_lines(*a, max_lines=128), lambda *a, **k: oracle.match_lines(P, lp, *a, **k),
+               lambda: Solver(P, fast_mode=True, ctx=oracle.OracleContext(P)))
+    assert np.abs(got - want).max() < 1e-6
+    assert np.abs(got - sb.truth[1::2, :6]).max() < np.abs(sb.states[1::2, :6] - sb.truth[1::2, :6]).max()
