@@ -84,7 +84,7 @@ def run_tracking_lockstep(solver, ref_solver, frames):
     50-iteration mode: most solves stop at the iteration cap inside the zig-zag regime of the norm-type wheel /
     ground residuals, and the reference path itself turns a 1e-12 input change into 1e-3 m after 40 frames —
     tests/test_sequence.py measures that.)  Returns per-frame (max |dp|, max |dq|, rel. error of the prior
-    information J^T J)."""
+    information J^T J, relative difference of the final costs, 1 if the reference path hit the iteration cap)."""
     import copy
 
     window = [frames[0]]
@@ -101,6 +101,8 @@ def run_tracking_lockstep(solver, ref_solver, frames):
         solver.solve(mine)
         dp = max(np.abs(a.p - b.p).max() for a, b in zip(mine, window))
         dq = max(np.abs(a.q - b.q).max() for a, b in zip(mine, window))
+        cost, ref_cost = float(solver.last_summary["final_cost"][0]), float(ref_solver.last_summary["final_cost"][0])
+        capped = int(ref_solver.last_summary["termination"][0]) == 0      # the reference path stopped at the iteration cap
         # marginalise both at the reference's solution so that the priors are comparable
         for a, b in zip(mine, window):
             a.p[:], a.q[:], a.v[:], a.bs[:] = b.p, b.q, b.v, b.bs
@@ -111,7 +113,7 @@ def run_tracking_lockstep(solver, ref_solver, frames):
             A = solver.linearized_jacobians.T @ solver.linearized_jacobians
             Bm = ref_solver.linearized_jacobians.T @ ref_solver.linearized_jacobians
             dj = float(np.abs(A - Bm).max() / np.abs(Bm).max())
-        rows.append((float(dp), float(dq), dj))
+        rows.append((float(dp), float(dq), dj, (cost - ref_cost) / max(ref_cost, 1e-300), float(capped)))
         window = window[-1:]
         if k + 1 < len(frames):
             frames[k + 1].p += f.p - guess_p

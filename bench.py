@@ -16,6 +16,7 @@ no data-path collective); only the timing is reduced (max over ranks).  The poin
 north-star also names is measured by `--shard points` (strong scaling of one batch, one NCCL all-reduce per iteration).
 """
 import argparse
+import ctypes as C
 import json
 import os
 import subprocess
@@ -333,7 +334,7 @@ def run_ours(args):
     }
     if world == 1:
         result["single_window"] = single_window_latency(P, hb, torch, device)
-        result["next_rows"] = {"scan_lines": scan_lines_rate(P, torch, device, cpu=not args.no_cpu)}
+        result["next_rows"] = front_end_rates(P, torch, device, cpu=not args.no_cpu)
     if world == 1 and not args.no_cpu:
         result["cpu_baseline"] = cpu_baseline(P, hb, seconds=args.cpu_seconds, threads=1)
     print(json.dumps(result))
@@ -341,64 +342,108 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
-def scan_lines_rate(P, torch, device, n_scans=4096, reps=10, cpu=True):
-    """SURVEY section 8f rank 1 (laser_manager::spawn_scan -> lvio2d_extract_lines): scans/s on 4096 synthetic 1081-beam
-    scans (64 distinct, tiled), device-resident and through host buffers, next to the CPU oracle on one core."""
+def front_end_rates(P, torch, device, n_scans=4096, reps=10, cpu=True):
+    """SURVEY section 8f rows built so far, each timed device-resident on 4096 synthetic 1081-beam scans (64 distinct,
+    tiled) with CUDA events on the context's stream, next to its CPU oracle on one core:
+      scan_to_points  convert::laser_to_point_times + sensor::laser::correct  -> lvio2d_scan_to_points
+      scan_lines      laser_manager::spawn_scan                                -> lvio2d_extract_lines
+      match_lines     laser_manager::do_match (every scan against itself at the identity relative pose) -> lvio2d_match_lines
+    All three are fp64-ALU / latency-bound (sqrt, div, sincos, acos per point; sequential merge per segment): their
+    algorithmic bytes are reported against the HBM peak only to show how far below that roof they sit."""
     import lvio2d_b200 as L
+    from lvio2d_b200 import abi
     from lvio2d_b200.solver import Context
 
     lp = L.corridor_line_params()
-    off1, pts1 = L.synth.make_scan_batch(64, 21)
+    rg1, hd1 = L.synth.make_range_batch(64, 21)
     tile = n_scans // 64
-    n1 = int(off1[-1])
-    off = np.concatenate([(off1[:-1][None, :] + n1 * np.arange(tile)[:, None]).ravel(), [n1 * tile]]).astype(np.int64)
-    pts = np.tile(pts1, (tile, 1))
-    max_lines = 160
-    out = {"scans": n_scans, "points": int(off[-1]), "unit": "scans/s"}
+    rg, hd = np.tile(rg1, (tile, 1)), np.tile(hd1, tile)
+    S, nb = rg.shape
+    ML = 160
+    peak = measured_peaks()[0]
+    out = {"scans": S, "beams": nb, "unit": "scans/s"}
     with Context(P) as c:
-        d_off, d_pts = torch.from_numpy(off).to(device), torch.from_numpy(pts).to(device)
-        d_n = torch.zeros(n_scans, dtype=torch.int32, device=device)
-        d_lines = torch.zeros(n_scans * max_lines * 4, dtype=torch.float64, device=device)
-        d_abc = torch.zeros(n_scans * max_lines * 3, dtype=torch.float64, device=device)
-        d_rng = torch.zeros(n_scans * max_lines * 2, dtype=torch.int32, device=device)
         stream = torch.cuda.ExternalStream(c.stream, device=device)
+        d_rg = torch.from_numpy(rg).to(device)
+        d_hd = torch.from_numpy(hd.view(np.uint8).reshape(S, -1).copy()).to(device)
+        d_cnt = torch.zeros(S, dtype=torch.int32, device=device)
+        d_pts = torch.zeros(S * nb * 2, dtype=torch.float64, device=device)
+        d_z = torch.zeros(S * nb, dtype=torch.float64, device=device)
+        d_off = (torch.arange(S, dtype=torch.int64, device=device) * nb).contiguous()
+        d_n = torch.zeros(S, dtype=torch.int32, device=device)
+        d_lines = torch.zeros(S * ML * 4, dtype=torch.float64, device=device)
+        d_abc = torch.zeros(S * ML * 3, dtype=torch.float64, device=device)
+        d_rng = torch.zeros(S * ML * 2, dtype=torch.int32, device=device)
+        d_pose = torch.zeros(S * 6, dtype=torch.float64, device=device)
+        d_nm = torch.zeros(S, dtype=torch.int32, device=device)
+        d_m = torch.zeros(S * ML * 2, dtype=torch.int32, device=device)
+        vp = C.c_void_p
 
-        def run():
-            c.extract_lines_device(lp, n_scans, d_off.data_ptr(), d_pts.data_ptr(), max_lines, d_n.data_ptr(), d_lines.data_ptr(),
-                                   d_abc.data_ptr(), d_rng.data_ptr())
+        def k_points():
+            c.scan_to_points_device(S, nb, d_rg.data_ptr(), d_hd.data_ptr(), True, d_cnt.data_ptr(), d_pts.data_ptr(), d_z.data_ptr())
 
-        for _ in range(3):
-            run()
-        c.sync()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(stream)
-        for _ in range(reps):
-            run()
-        e1.record(stream)
-        c.sync()
-        ms = e0.elapsed_time(e1) / reps
-        n_lines = d_n.cpu().numpy()
-        alg_bytes = float(off[-1]) * 16 + float(n_lines.sum()) * (4 + 3) * 8 + n_scans * 12
-        out.update({"value": n_scans / (ms * 1e-3), "ms_per_launch": ms, "lines_found": int(n_lines.sum()),
-                    "roofline": {"bound": "fp64 ALU / latency (sqrt, div, acos per point; sequential merge per segment)",
-                                 "algorithmic_bytes_per_launch": alg_bytes, "achieved_GBps": alg_bytes / (ms * 1e-3) / 1e9,
-                                 "hbm_peak_GBps": measured_peaks()[0]}})
-        t0 = time.perf_counter()
-        for _ in range(3):
-            c.extract_lines(lp, off, pts, max_lines=max_lines)
-        out["e2e"] = {"value": 3 * n_scans / (time.perf_counter() - t0), "unit": "scans/s",
-                      "api": "lvio2d_extract_lines(host buffers): H2D + kernel + D2H, synchronous"}
+        def k_lines():
+            c.extract_lines_device(lp, S, d_off.data_ptr(), d_pts.data_ptr(), ML, d_n.data_ptr(), d_lines.data_ptr(), d_abc.data_ptr(),
+                                   d_rng.data_ptr(), point_count_ptr=d_cnt.data_ptr(), point_z_ptr=d_z.data_ptr())
+
+        def k_match():
+            c._check(c.lib.lvio2d_match_lines(
+                c._h, C.byref(lp), S, 0, C.cast(vp(d_off.data_ptr()), abi.c_int64_p), C.cast(vp(d_cnt.data_ptr()), abi.c_int32_p),
+                C.cast(vp(d_pts.data_ptr()), abi.c_double_p), ML, C.cast(vp(d_n.data_ptr()), abi.c_int32_p),
+                C.cast(vp(d_lines.data_ptr()), abi.c_double_p), C.cast(vp(d_rng.data_ptr()), abi.c_int32_p), ML,
+                C.cast(vp(d_n.data_ptr()), abi.c_int32_p), C.cast(vp(d_lines.data_ptr()), abi.c_double_p),
+                C.cast(vp(d_pose.data_ptr()), abi.c_double_p), C.cast(vp(d_pose.data_ptr()), abi.c_double_p),
+                C.cast(vp(d_nm.data_ptr()), abi.c_int32_p), C.cast(vp(d_m.data_ptr()), abi.c_int32_p), 1), "lvio2d_match_lines")
+
+        def timed(fn):
+            for _ in range(3):
+                fn()
+            c.sync()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            for _ in range(reps):
+                fn()
+            e1.record(stream)
+            c.sync()
+            return e0.elapsed_time(e1) / reps
+
+        ms_p = timed(k_points)
+        ms_l = timed(k_lines)
+        ms_m = timed(k_match)
+        npts, nlines, nmatch = int(d_cnt.sum().item()), int(d_n.sum().item()), int(d_nm.sum().item())
+
+        def row(ms, alg_bytes, extra):
+            r = {"value": S / (ms * 1e-3), "ms_per_launch": ms, "algorithmic_bytes_per_launch": alg_bytes,
+                 "achieved_GBps": alg_bytes / (ms * 1e-3) / 1e9, "hbm_peak_GBps": peak, "bound": "fp64 ALU / latency"}
+            r.update(extra)
+            return r
+
+        out["scan_to_points"] = row(ms_p, S * nb * 4.0 + S * 80.0 + npts * 24.0 + S * 4.0, {"points_kept": npts})
+        out["scan_lines"] = row(ms_l, npts * 24.0 + nlines * 72.0 + S * 16.0, {"lines_found": nlines})
+        out["match_lines"] = row(ms_m, npts * 16.0 + 2 * nlines * 32.0 + nlines * 8.0 + S * 96.0 + nmatch * 8.0, {"pairs_matched": nmatch})
+        out["chain_ms_per_4096_scans"] = ms_p + ms_l + ms_m
     if cpu:
         import oracle_lib as O
 
         O.build()
-        t0 = time.perf_counter()
-        done = 0
-        while time.perf_counter() - t0 < 2.0:
-            O.extract_lines(lp, off1, pts1, max_lines=max_lines)
-            done += 64
-        out["cpu_baseline"] = {"value": done / (time.perf_counter() - t0), "unit": "scans/s", "cores": 1, "kind": "port",
-                               "sample": f"{done} scans (oracle/laser_lines.hpp)"}
+
+        def cpu_rate(fn):
+            t0, done = time.perf_counter(), 0
+            while time.perf_counter() - t0 < 1.5:
+                fn()
+                done += 64
+            return done / (time.perf_counter() - t0)
+
+        cnt, pts, pz, _ = O.scan_to_points(rg1, hd1, True)
+        off1 = np.arange(64, dtype=np.int64) * nb
+        n, lines, _, rng = O.extract_lines(lp, off1, pts.reshape(-1, 2), max_lines=ML, point_count=cnt, point_z=pz.reshape(-1))
+        pose = np.zeros((64, 6))
+        out["cpu_baseline"] = {
+            "unit": "scans/s", "cores": 1, "kind": "port", "sample": "the 64 distinct scans, repeated for 1.5 s per step",
+            "scan_to_points": cpu_rate(lambda: O.scan_to_points(rg1, hd1, True)),
+            "scan_lines": cpu_rate(lambda: O.extract_lines(lp, off1, pts.reshape(-1, 2), max_lines=ML, point_count=cnt, point_z=pz.reshape(-1))),
+            "match_lines": cpu_rate(lambda: O.match_lines(P, lp, n, lines, n, lines, pose, pose, 0, off1, pts.reshape(-1, 2), rng, cnt)),
+        }
     return out
 
 

@@ -9,14 +9,26 @@ import subprocess
 import sys
 
 
-def launches(path):
+def launches(path, full_size_only=False):
+    """Per-kernel (count, total ns).  full_size_only: keep, for every kernel, only the launches with that kernel's largest
+    grid — bench.py also launches the same kernels on small batches (end-to-end chunks, the single-window probe), which
+    would distort the shares of a step of the headline workload."""
     rows = list(csv.reader(open(path)))
     hi = [i for i, r in enumerate(rows) if r and r[0] == "ID"][0]
     hdr = rows[hi]
-    ki, vi, ui = hdr.index("Kernel Name"), hdr.index("Metric Value"), hdr.index("Metric Unit")
+    ki, vi, ui, gi = hdr.index("Kernel Name"), hdr.index("Metric Value"), hdr.index("Metric Unit"), hdr.index("Grid Size")
+    biggest = {}
+    if full_size_only:
+        for r in rows[hi + 1:]:
+            if len(r) > vi:
+                name = r[ki].split("(")[0]
+                g = int(r[gi].strip("()").split(",")[0])
+                biggest[name] = max(biggest.get(name, 0), g)
     agg = collections.OrderedDict()
     for r in rows[hi + 1:]:
         if len(r) <= vi:
+            continue
+        if full_size_only and int(r[gi].strip("()").split(",")[0]) != biggest[r[ki].split("(")[0]]:
             continue
         try:
             v = float(r[vi].replace(",", ""))
@@ -65,6 +77,13 @@ def main():
     agg = launches(lcsv)
     tot = sum(a[1] for a in agg.values())
     for k, (c, t) in agg.items():
+        lines.append(f"| `{k}` | {c} | {t / 1e6:.3f} | {t / c / 1e3:.1f} | {t / tot * 100:.1f}% |")
+    lines += ["", "Launches of the headline batch only (each kernel's largest grid; the list above also holds the small-batch launches of",
+              "the end-to-end chunks and of the single-window probe):", "", "| kernel | launches | total ms | avg us | share |", "|---|---:|---:|---:|---:|"]
+    agg = launches(lcsv, full_size_only=True)
+    main = {k: v for k, v in agg.items() if any(t in k for t in ("scan_match", "factor_kernel", "window_kernel"))}
+    tot = sum(a[1] for a in main.values())
+    for k, (c, t) in main.items():
         lines.append(f"| `{k}` | {c} | {t / 1e6:.3f} | {t / c / 1e3:.1f} | {t / tot * 100:.1f}% |")
     lines += ["", f"full capture: `{rep}` (`ncu --set full --clock-control none --import-source on`)", ""]
     for d in full(rep):
