@@ -405,7 +405,7 @@ __device__ __forceinline__ void copy_blk(double* dst, const double* src, int lan
 
 // per-warp shared memory of window_kernel (doubles): 4 blocks (+3 for the arrow topology) + pivot row + one frame's
 // laser block + rhs [n][15]
-__host__ __device__ inline size_t window_smem_doubles(int n, bool arrow) { return (arrow ? 7 : 4) * kBlk + 16 + 48 + (size_t)n * 15 + 16; }
+__host__ __device__ inline size_t window_smem_doubles(int n, bool arrow) { return (arrow ? 7 : 4) * kBlk + 16 + 48 + 32 + (size_t)n * 15 + 16; }
 
 // ---------------------------------------------------------------------------------------------------
 template <bool ARROW>
@@ -428,7 +428,8 @@ __device__ void window_step(const WindowArgs& a, int w, int lane, double* ws) {
     double* D0 = ws + 6 * kBlk;       // accumulated updates of D_0
     double* piv = ws + (ARROW ? 7 : 4) * kBlk;  // 16
     double* slb = piv + 16;           // laser block of the frame being assembled [NPAD]
-    double* sb = slb + 48;            // rhs / solution [n][15]
+    double* ssc = slb + 48;           // Jacobi scaling of frames i-1 and i [30]
+    double* sb = ssc + 32;            // rhs / solution [n][15]
 
     double* x = a.x + (size_t)w * n * 15;
     double* xc = a.xc + (size_t)w * n * 15;
@@ -589,6 +590,15 @@ __device__ void window_step(const WindowArgs& a, int w, int lane, double* ws) {
         return lsq * blk[src];
     };
     auto laser_own = [&](int f, int r, int c) -> double { return laser_own_at(lb + f * NPAD, f, r, c); };
+    // the same with the frame's const mask and laser flag already in registers
+    auto laser_own_reg = [&](const double* blk, uint8_t mask, bool active, int r, int c) -> double {
+        if (r == 2 || c == 2 || r > 5 || c > 5 || !active) return 0.0;
+        if (col_const(mask, r) || col_const(mask, c)) return 0.0;
+        int ri = r < 2 ? r : r - 1, ci = c < 2 ? c : c - 1;
+        if (ri > ci) { const int t = ri; ri = ci; ci = t; }
+        const int src = (ri < 2 && ci < 2) ? (ri + ci) : (ri < 2 ? 3 + ri * 3 + (ci - 2) : 9 + (ri == 2 ? ci - 2 : (ri == 3 ? ci : 5)));
+        return lsq * blk[src];
+    };
     auto has_cross = [&](int j) -> bool {
         return ARROW && mode == 0 && j >= 1 && fa[j] && a.ref_frame && a.ref_frame[(size_t)w * n + j] == 0;
     };
@@ -808,7 +818,11 @@ __device__ void window_step(const WindowArgs& a, int w, int lane, double* ws) {
                     cp_async8(Tm + e, it_i + item_haa(r, c));
                 }
                 for (int e = lane; e < NPAD; e += 32) cp_async8(slb + e, lb + (i - 1) * NPAD + e);
+                if (lane < 30) cp_async8(ssc + lane, scw + (i - 1) * 15 + lane);
             }
+            // per-frame flags, requested now and consumed after the inverse
+            const uint8_t cm_p = mode == 1 ? 0 : cm[i - 1];
+            const bool fa_p = fa[i - 1] != 0;
             const bool cross_i = has_cross(i);
             bool arrow_i = false;
             if (ARROW && i >= 2) {
@@ -830,7 +844,7 @@ __device__ void window_step(const WindowArgs& a, int w, int lane, double* ws) {
             // block); D_{i-1} assembled, scaled and damped
             for (int e = lane; e < kBlk; e += 32) {
                 const int r = e / 15, c = e - r * 15;
-                double v = Um[e] * scw[(i - 1) * 15 + r] * scw[i * 15 + c];
+                double v = Um[e] * ssc[r] * ssc[15 + c];
                 if (ARROW && i == 1) {
                     if (have_wc) v += Wm[e];
                     if (cross_i && r < 6 && c < 6 && !is_const(0, r) && !is_const(1, c)) v += cross_entry(1, r, c) * scw[r] * scw[15 + c];
@@ -838,10 +852,10 @@ __device__ void window_step(const WindowArgs& a, int w, int lane, double* ws) {
                 Um[e] = v;
                 double dv = Cp[e];
                 dv += Tm[e];
-                dv += laser_own_at(slb, i - 1, r, c);
+                dv += laser_own_reg(slb, cm_p, fa_p, r, c);
                 if (i - 1 == 0) dv += laser_ref_own(r, c);
-                dv = dv * scw[(i - 1) * 15 + r] * scw[(i - 1) * 15 + c];
-                if (r == c) dv = is_const(i - 1, r) ? 1.0 : dv + fmin(fmax(dv, opt.min_lm_diagonal), opt.max_lm_diagonal) * inv_radius;
+                dv = dv * ssc[r] * ssc[c];
+                if (r == c) dv = col_const(cm_p, r) ? 1.0 : dv + fmin(fmax(dv, opt.min_lm_diagonal), opt.max_lm_diagonal) * inv_radius;
                 Cp[e] = dv;
             }
             __syncwarp();
