@@ -89,12 +89,12 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def build_host_batch(ctx, n_windows, seed0):
-    """B C2 windows: UNIQUE_WINDOWS distinct synthetic windows (ray-cast in numpy), tiled to B (distinct memory)."""
+def build_host_batch(ctx, n_windows, seed0, config="c2"):
+    """B C2 (or C4) windows: UNIQUE_WINDOWS distinct synthetic windows (ray-cast in numpy), tiled to B (distinct memory)."""
     import lvio2d_b200 as L
 
-    uniq = min(UNIQUE_WINDOWS, n_windows)
-    sb = L.synth.config_c2(uniq, seed=seed0)
+    uniq = min(UNIQUE_WINDOWS if config == "c2" else 8, n_windows)
+    sb = L.synth.config_c2(uniq, seed=seed0) if config == "c2" else L.synth.config_c4(uniq, seed=seed0)
     hb = ctx.preintegrate_batch(sb)  # device preintegrators
     times = (n_windows + uniq - 1) // uniq
     if times > 1:
@@ -152,8 +152,20 @@ def run_ours(args):
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if world > 1:
+        # NCCL printf()s its version banner to stdout while the communicator is created: stdout is reserved for the ONE
+        # JSON line, so file descriptor 1 points at stderr until the first collective has run
         torch.cuda.set_device(local_rank)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        sys.stdout.flush()
+        saved_fd = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_fd, 1)
+            os.close(saved_fd)
     device = torch.device("cuda", local_rank)
     P = L.corridor_params(max_iters=MAX_ITERS, device=local_rank)
     P.assoc_mode = 1 if args.assoc == "nearest" else 0
@@ -161,7 +173,7 @@ def run_ours(args):
     ctx = Context(P)
     B = args.windows
     shard_points = args.shard == "points" and world > 1
-    hb, uniq = build_host_batch(ctx, B, seed0=42 if shard_points else 42 + 1000 * rank)
+    hb, uniq = build_host_batch(ctx, B, seed0=42 if shard_points else 42 + 1000 * rank, config=args.config)
     dstruct, keep = to_device_struct(hb, torch, device)
     ext = torch.cuda.ExternalStream(ctx.stream, device=device)
 
@@ -200,13 +212,14 @@ def run_ours(args):
             for c2 in extra:
                 c2.solve_async()
             return
-        ctx.solve_begin()
-        for _ in range(MAX_ITERS + 1):
-            ctx.eval_laser()
-            ctx.sync()                       # the all-reduce runs on torch's NCCL stream
-            dist.all_reduce(red)
-            torch.cuda.current_stream(device).synchronize()
-            ctx.lm_step()
+        # everything is ordered on the context's stream: NCCL's stream waits for it and it waits for NCCL, the host
+        # never synchronises inside the solve
+        with torch.cuda.stream(ext):
+            ctx.solve_begin()
+            for _ in range(MAX_ITERS + 1):
+                ctx.eval_laser()
+                dist.all_reduce(red)
+                ctx.lm_step()
 
     def sync_all():
         ctx.sync()
@@ -308,8 +321,11 @@ def run_ours(args):
         "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
         "scaling": "strong" if shard_points else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {
-            "workload": f"{'C3' if args.assoc == 'nearest' else 'C2'}: 1081 beams x 30 keyframes, {args.assoc} associations, IMU+wheel+ground+prior, {MAX_ITERS} LM iterations "
-                        f"(BASELINE.json configs[{2 if args.assoc == 'nearest' else 1}]); {B} windows per GPU per step ({uniq} distinct synthetic windows tiled)",
+            "workload": (f"{'C3' if args.assoc == 'nearest' else 'C2'}: 1081 beams x 30 keyframes, {args.assoc} associations, IMU+wheel+ground+prior, {MAX_ITERS} LM iterations "
+                         f"(BASELINE.json configs[{2 if args.assoc == 'nearest' else 1}]); {B} windows per GPU per step ({uniq} distinct synthetic windows tiled)")
+                        if args.config == "c2" else
+                        (f"C4: 4096 beams x 50 keyframes, fixed associations, IMU+wheel+ground+prior, {MAX_ITERS} LM iterations (BASELINE.json configs[3]); "
+                         f"{B} windows {'in total, points sharded over the ranks' if shard_points else 'per GPU'} ({uniq} distinct synthetic windows tiled)"),
             "association": args.assoc, "huber_delta": args.huber,
             "windows_per_gpu": B, "points_per_window": int(hb.n_points // hb.n_windows), "lm_iterations_per_window": MAX_ITERS,
             "multi_gpu": ("points sharded over ranks, one NCCL all-reduce of the per-frame blocks per iteration" if shard_points
@@ -563,6 +579,7 @@ def main():
     ap.add_argument("--windows", type=int, default=4096, help="windows per GPU per step")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--shard", default="windows", choices=["windows", "points"])
+    ap.add_argument("--config", default="c2", choices=["c2", "c4"], help="c4 = BASELINE configs[3]: 4096 beams x 50 keyframes (use with --shard points)")
     ap.add_argument("--assoc", default="fixed", choices=["fixed", "nearest"], help="nearest = BASELINE config 3 (in-kernel re-association)")
     ap.add_argument("--huber", type=float, default=0.0, help="Huber delta on the whitened laser residuals (0 = reference: none)")
     ap.add_argument("--contexts", type=int, default=1, help="split the batch over this many solver contexts / CUDA streams")
