@@ -5,6 +5,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <vector>
@@ -88,6 +89,7 @@ struct lvio2d_ctx {
     DevBuf b_ml[16];   // lvio2d_match_lines
     double* ext_reduce = nullptr; int64_t ext_reduce_count = 0;
     int step_calls = 0;
+    int window_threads = 0;   // 0 = automatic
     bool have_solution = false;
     // host staging of the small index arrays (kept alive until the next upload so that copies can stay asynchronous)
     PinnedVec<int64_t> h_poff, h_loff;
@@ -230,19 +232,29 @@ int launch_factors(lvio2d_ctx* ctx, const WindowArgs& a) {
 }
 
 int launch_window(lvio2d_ctx* ctx, const WindowArgs& a) {
-    const int per_warp = (int)window_smem_doubles(ctx->n, ctx->arrow);
-    const int wpc = 2;
-    const size_t smem = (size_t)wpc * per_warp * sizeof(double);
-    const int grid = (ctx->B + wpc - 1) / wpc;
+    const int per_window = (int)window_smem_doubles(ctx->n, ctx->arrow);
+    // thread group per window: one warp when the batch fills the machine (4 x 148 CTAs of 128 threads hold 592 windows at
+    // once), four warps below that — the same arithmetic spread four ways, for the latency of small batches
+    // (LVIO2D_WINDOW_THREADS = 32 | 128 forces one of them; used by the tests to cover both)
+    int nt = ctx->B <= 4 * ctx->sm_count ? 128 : 32;
+    if (ctx->window_threads == 32 || ctx->window_threads == 128) nt = ctx->window_threads;
     if (ctx->profiling) cudaEventRecord(next_event(ctx->ev_win, ctx->ev_win_used), ctx->stream);
     ctx->launches += 1;
-    if (ctx->arrow) {
-        CK(cudaFuncSetAttribute(window_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        window_kernel<true><<<grid, wpc * 32, smem, ctx->stream>>>(a, per_warp);
+#define LAUNCH_WIN(AR, NT, GRID, BLOCK, SMEM)                                                                                 \
+    do {                                                                                                                      \
+        CK(cudaFuncSetAttribute(window_kernel<AR, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SMEM)));            \
+        window_kernel<AR, NT><<<GRID, BLOCK, SMEM, ctx->stream>>>(a, per_window);                                             \
+    } while (0)
+    if (nt == 32) {
+        const int wpc = 2;
+        const size_t smem = (size_t)wpc * per_window * sizeof(double);
+        const int grid = (ctx->B + wpc - 1) / wpc;
+        if (ctx->arrow) LAUNCH_WIN(true, 32, grid, wpc * 32, smem); else LAUNCH_WIN(false, 32, grid, wpc * 32, smem);
     } else {
-        CK(cudaFuncSetAttribute(window_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        window_kernel<false><<<grid, wpc * 32, smem, ctx->stream>>>(a, per_warp);
+        const size_t smem = (size_t)per_window * sizeof(double);
+        if (ctx->arrow) LAUNCH_WIN(true, 128, ctx->B, 128, smem); else LAUNCH_WIN(false, 128, ctx->B, 128, smem);
     }
+#undef LAUNCH_WIN
     if (ctx->profiling) cudaEventRecord(next_event(ctx->ev_win, ctx->ev_win_used), ctx->stream);
     CK(cudaGetLastError());
     return LVIO2D_OK;
@@ -442,6 +454,7 @@ int lvio2d_create(lvio2d_ctx** out, const lvio2d_params* params) {
         delete ctx;
         return LVIO2D_ERR_CUDA;
     }
+    if (const char* wt = std::getenv("LVIO2D_WINDOW_THREADS")) ctx->window_threads = std::atoi(wt);
     *out = ctx;
     return LVIO2D_OK;
 }

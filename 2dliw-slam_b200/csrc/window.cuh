@@ -346,17 +346,62 @@ __device__ __noinline__ bool spd_inverse15(double* A, double* piv /* 16 doubles 
     __syncwarp();
     return ok;
 }
-// The two GEMM kernels use all 32 lanes: lane = (row r = lane & 15, column half h = lane >> 4): h = 0 computes
-// columns 0..7, h = 1 columns 8..14.
+// Thread groups: one window is solved by NT threads — one warp (NT = 32, the batched shape: as many windows in flight as
+// possible) or four warps (NT = 128, small batches: the same work spread four ways to cut the latency of one solve).
+template <int NT> __device__ __forceinline__ void grp_sync() {
+    if (NT == 32) __syncwarp(); else __syncthreads();
+}
+// reductions over the group; `red` = 8 doubles of shared scratch (NT > 32 only); every thread gets the result, and the
+// cross-warp part is summed in a fixed order (deterministic)
+template <int NT> __device__ __forceinline__ double grp_sum(double v, double* red, int tid) {
+    v = warp_sum(v);
+    if (NT == 32) return v;
+    __syncthreads();
+    if ((tid & 31) == 0) red[tid >> 5] = v;
+    __syncthreads();
+    double s = 0.0;
+#pragma unroll
+    for (int k = 0; k < NT / 32; ++k) s += red[k];
+    return s;
+}
+template <int NT> __device__ __forceinline__ double grp_max(double v, double* red, int tid) {
+    v = warp_max(v);
+    if (NT == 32) return v;
+    __syncthreads();
+    if ((tid & 31) == 0) red[tid >> 5] = v;
+    __syncthreads();
+    double s = red[0];
+#pragma unroll
+    for (int k = 1; k < NT / 32; ++k) s = fmax(s, red[k]);
+    return s;
+}
+template <int NT> __device__ __forceinline__ bool grp_all(bool v, double* red, int tid) {
+    if (NT == 32) return __all_sync(0xffffffffu, v);
+    return __syncthreads_and(v) != 0;
+}
+// SPD inverse by the first warp of the group, result flag broadcast through `red[4]`
+template <int NT> __device__ __forceinline__ bool grp_inverse15(double* A, double* piv, double* red, int tid) {
+    if (NT == 32) return spd_inverse15(A, piv, tid);
+    if (tid < 32) {
+        const bool ok = spd_inverse15(A, piv, tid);
+        if (tid == 0) red[4] = ok ? 1.0 : 0.0;
+    }
+    __syncthreads();
+    return red[4] != 0.0;
+}
+// The two GEMM kernels: thread = (row r = tid & 15, column group g = tid >> 4); NT / 16 groups of ceil(15 / groups)
+// columns each (NT = 32: 8 + 7 columns, NT = 128: 2 columns per thread).
 // C = A B
-__device__ __noinline__ void gemm_ab15(double* Cm, const double* A, const double* B, int lane) {
-    const int r = lane & 15, c0 = (lane >> 4) * 8;
+template <int NT>
+__device__ __noinline__ void gemm_ab15(double* Cm, const double* A, const double* B, int tid) {
+    constexpr int G = NT / 16, CPG = (15 + G - 1) / G;
+    const int r = tid & 15, c0 = (tid >> 4) * CPG;
     if (r < 15) {
         double a[15];
 #pragma unroll
         for (int k = 0; k < 15; ++k) a[k] = A[r * 15 + k];
 #pragma unroll
-        for (int cc = 0; cc < 8; ++cc) {
+        for (int cc = 0; cc < CPG; ++cc) {
             const int c = c0 + cc;
             if (c < 15) {
                 double s = 0.0;
@@ -366,17 +411,19 @@ __device__ __noinline__ void gemm_ab15(double* Cm, const double* A, const double
             }
         }
     }
-    __syncwarp();
+    grp_sync<NT>();
 }
 // C -= A B^T
-__device__ __noinline__ void gemm_sub_abt15(double* Cm, const double* A, const double* B, int lane) {
-    const int r = lane & 15, c0 = (lane >> 4) * 8;
+template <int NT>
+__device__ __noinline__ void gemm_sub_abt15(double* Cm, const double* A, const double* B, int tid) {
+    constexpr int G = NT / 16, CPG = (15 + G - 1) / G;
+    const int r = tid & 15, c0 = (tid >> 4) * CPG;
     if (r < 15) {
         double a[15];
 #pragma unroll
         for (int k = 0; k < 15; ++k) a[k] = A[r * 15 + k];
 #pragma unroll
-        for (int cc = 0; cc < 8; ++cc) {
+        for (int cc = 0; cc < CPG; ++cc) {
             const int c = c0 + cc;
             if (c < 15) {
                 double s = 0.0;
@@ -386,29 +433,28 @@ __device__ __noinline__ void gemm_sub_abt15(double* Cm, const double* A, const d
             }
         }
     }
-    __syncwarp();
+    grp_sync<NT>();
 }
 // out[r] (-)= sum_k M[r][k] v[k]   (TRANS: M[k][r])
-template <bool TRANS, bool SUB>
-__device__ __forceinline__ void gemv15(double* out, const double* M, const double* v, int lane) {
-    if (lane < 15) {
+template <int NT, bool TRANS, bool SUB>
+__device__ __forceinline__ void gemv15(double* out, const double* M, const double* v, int tid) {
+    if (tid < 15) {
         double s = 0.0;
 #pragma unroll
-        for (int k = 0; k < 15; ++k) s += (TRANS ? M[k * 15 + lane] : M[lane * 15 + k]) * v[k];
-        if (SUB) out[lane] -= s; else out[lane] = s;
+        for (int k = 0; k < 15; ++k) s += (TRANS ? M[k * 15 + tid] : M[tid * 15 + k]) * v[k];
+        if (SUB) out[tid] -= s; else out[tid] = s;
     }
-    __syncwarp();
+    grp_sync<NT>();
 }
-__device__ __forceinline__ void copy_blk(double* dst, const double* src, int lane) {
-    for (int i = lane; i < kBlk; i += 32) dst[i] = src[i];
+template <int NT> __device__ __forceinline__ void copy_blk(double* dst, const double* src, int tid) {
+    for (int i = tid; i < kBlk; i += NT) dst[i] = src[i];
 }
-
 // per-warp shared memory of window_kernel (doubles): 4 blocks (+3 for the arrow topology) + pivot row + one frame's
 // laser block + rhs [n][15]
-__host__ __device__ inline size_t window_smem_doubles(int n, bool arrow) { return (arrow ? 7 : 4) * kBlk + 16 + 48 + 32 + (size_t)n * 15 + 16; }
+__host__ __device__ inline size_t window_smem_doubles(int n, bool arrow) { return (arrow ? 7 : 4) * kBlk + 16 + 48 + 32 + 8 + (size_t)n * 15 + 16; }
 
 // ---------------------------------------------------------------------------------------------------
-template <bool ARROW>
+template <bool ARROW, int NT>
 __device__ void window_step(const WindowArgs& a, int w, int lane, double* ws) {
     constexpr int NPAD = ARROW ? kPadFree : kPadTrack;
     constexpr int ICOST = ARROW ? 44 : 20;
@@ -429,7 +475,8 @@ __device__ void window_step(const WindowArgs& a, int w, int lane, double* ws) {
     double* piv = ws + (ARROW ? 7 : 4) * kBlk;  // 16
     double* slb = piv + 16;           // laser block of the frame being assembled [NPAD]
     double* ssc = slb + 48;           // Jacobi scaling of frames i-1 and i [30]
-    double* sb = ssc + 32;            // rhs / solution [n][15]
+    double* red = ssc + 32;           // cross-warp reduction scratch [8]
+    double* sb = red + 8;             // rhs / solution [n][15]
 
     double* x = a.x + (size_t)w * n * 15;
     double* xc = a.xc + (size_t)w * n * 15;
@@ -447,16 +494,16 @@ __device__ void window_step(const WindowArgs& a, int w, int lane, double* ws) {
     if (a.tiles == 1) {
         // one tile per frame (the batched shape): 4 independent loads per lane in flight
         const double* pw = a.partial + (size_t)w * n * NPAD;
-        for (int i0 = lane; i0 < n * NPAD; i0 += 128) {
+        for (int i0 = lane; i0 < n * NPAD; i0 += 4 * NT) {
             double v[4];
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
-                const int idx = i0 + 32 * q;
+                const int idx = i0 + NT * q;
                 v[q] = (idx < n * NPAD && fa[idx / NPAD]) ? pw[idx] : 0.0;
             }
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
-                const int idx = i0 + 32 * q;
+                const int idx = i0 + NT * q;
                 if (idx < n * NPAD) {
                     const double s = 0.0 + v[q];
                     lb_c[idx] = s;
@@ -465,7 +512,7 @@ __device__ void window_step(const WindowArgs& a, int w, int lane, double* ws) {
             }
         }
     } else {
-        for (int idx = lane; idx < n * NPAD; idx += 32) {
+        for (int idx = lane; idx < n * NPAD; idx += NT) {
             const int f = idx / NPAD, k = idx - f * NPAD;
             double s = 0.0;
             if (fa[f]) {
@@ -476,9 +523,9 @@ __device__ void window_step(const WindowArgs& a, int w, int lane, double* ws) {
             if (k == ICOST) csum += lsq * s;
         }
     }
-    for (int f = lane; f < n; f += 32) csum += it_c[(size_t)f * kItem + kItemCost];
-    double cand_cost = 0.5 * warp_sum(csum);
-    __syncwarp();
+    for (int f = lane; f < n; f += NT) csum += it_c[(size_t)f * kItem + kItemCost];
+    double cand_cost = 0.5 * grp_sum<NT>(csum, red, lane);
+    grp_sync<NT>();
 
     // ---- decide on the candidate
     bool accepted = false;
@@ -488,39 +535,39 @@ __device__ void window_step(const WindowArgs& a, int w, int lane, double* ws) {
         st.initial_cost = cand_cost;
         accepted = true;
         double s = 0.0;
-        for (int i0 = lane; i0 < n * 15; i0 += 128) {
+        for (int i0 = lane; i0 < n * 15; i0 += 4 * NT) {
             double v[4];
 #pragma unroll
-            for (int q = 0; q < 4; ++q) v[q] = (i0 + 32 * q < n * 15) ? xc[i0 + 32 * q] : 0.0;
+            for (int q = 0; q < 4; ++q) v[q] = (i0 + NT * q < n * 15) ? xc[i0 + NT * q] : 0.0;
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
-                const int i = i0 + 32 * q;
+                const int i = i0 + NT * q;
                 if (i < n * 15) {
                     x[i] = v[q];
                     if (!is_const(i / 15, i % 15)) s += v[q] * v[q];
                 }
             }
         }
-        st.x_norm = sqrt(warp_sum(s));
+        st.x_norm = sqrt(grp_sum<NT>(s, red, lane));
         st.last_success = 1;
     } else {
         if (!isfinite(cand_cost)) cand_cost = 1.7976931348623157e308;
         double s = 0.0;
-        for (int i0 = lane; i0 < n * 15; i0 += 128) {
+        for (int i0 = lane; i0 < n * 15; i0 += 4 * NT) {
             double va[4], vb[4];
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
-                const bool in = i0 + 32 * q < n * 15;
-                va[q] = in ? x[i0 + 32 * q] : 0.0;
-                vb[q] = in ? xc[i0 + 32 * q] : 0.0;
+                const bool in = i0 + NT * q < n * 15;
+                va[q] = in ? x[i0 + NT * q] : 0.0;
+                vb[q] = in ? xc[i0 + NT * q] : 0.0;
             }
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
-                const int i = i0 + 32 * q;
+                const int i = i0 + NT * q;
                 if (i < n * 15 && !is_const(i / 15, i % 15)) { const double d = va[q] - vb[q]; s += d * d; }
             }
         }
-        const double step_norm = sqrt(warp_sum(s));
+        const double step_norm = sqrt(grp_sum<NT>(s, red, lane));
         // ParameterToleranceReached / FunctionToleranceReached come before the step-quality test
         if (step_norm <= opt.parameter_tolerance * (st.x_norm + opt.parameter_tolerance)) {
             st.status = 1; st.termination = 2;
@@ -533,20 +580,20 @@ __device__ void window_step(const WindowArgs& a, int w, int lane, double* ws) {
                 accepted = rho > opt.min_relative_decrease;
                 if (accepted) {
                     double s2 = 0.0;
-                    for (int i0 = lane; i0 < n * 15; i0 += 128) {
+                    for (int i0 = lane; i0 < n * 15; i0 += 4 * NT) {
                         double v[4];
 #pragma unroll
-                        for (int q = 0; q < 4; ++q) v[q] = (i0 + 32 * q < n * 15) ? xc[i0 + 32 * q] : 0.0;
+                        for (int q = 0; q < 4; ++q) v[q] = (i0 + NT * q < n * 15) ? xc[i0 + NT * q] : 0.0;
 #pragma unroll
                         for (int q = 0; q < 4; ++q) {
-                            const int i = i0 + 32 * q;
+                            const int i = i0 + NT * q;
                             if (i < n * 15) {
                                 x[i] = v[q];
                                 if (!is_const(i / 15, i % 15)) s2 += v[q] * v[q];
                             }
                         }
                     }
-                    st.x_norm = sqrt(warp_sum(s2));
+                    st.x_norm = sqrt(grp_sum<NT>(s2, red, lane));
                     st.cost = cand_cost;
                     const double t = 2.0 * rho - 1.0;
                     st.radius = st.radius / fmax(1.0 / 3.0, 1.0 - t * t * t);
@@ -568,7 +615,7 @@ __device__ void window_step(const WindowArgs& a, int w, int lane, double* ws) {
         }
     }
     if (accepted) st.cur = cand;
-    __syncwarp();
+    grp_sync<NT>();
     if (mode == 0 && st.iteration >= opt.max_iters) {
         st.status = 1; st.termination = 0;
         if (lane == 0) { a.state[w] = st; a.win_status[w] = 1; }
@@ -653,7 +700,7 @@ __device__ void window_step(const WindowArgs& a, int w, int lane, double* ws) {
     };
     // unscaled diagonal block of frame i into dst (shared memory)
     auto assemble_D = [&](int i, double* dst) {
-        for (int e = lane; e < kBlk; e += 32) {
+        for (int e = lane; e < kBlk; e += NT) {
             const int r = e / 15, c = e - r * 15;
             double v = itm[(size_t)i * kItem + item_hbb(r, c)];
             if (i + 1 < n) v += itm[(size_t)(i + 1) * kItem + item_haa(r, c)];
@@ -661,7 +708,7 @@ __device__ void window_step(const WindowArgs& a, int w, int lane, double* ws) {
             if (i == 0) v += laser_ref_own(r, c);
             dst[e] = v;
         }
-        __syncwarp();
+        grp_sync<NT>();
     };
     auto diag_H = [&](int f, int c) -> double {
         double v = itm[(size_t)f * kItem + item_hbb(c, c)];
@@ -675,29 +722,29 @@ __device__ void window_step(const WindowArgs& a, int w, int lane, double* ws) {
     if (a.dense_H) {
         const int dim = 15 * n;
         double* H = a.dense_H + (size_t)w * dim * dim;
-        for (size_t e = lane; e < (size_t)dim * dim; e += 32) H[e] = 0.0;
-        __syncwarp();
+        for (size_t e = lane; e < (size_t)dim * dim; e += NT) H[e] = 0.0;
+        grp_sync<NT>();
         for (int i = 0; i < n; ++i) {
             assemble_D(i, Dm);
-            for (int e = lane; e < kBlk; e += 32) H[(size_t)(15 * i + e / 15) * dim + 15 * i + e % 15] = Dm[e];
+            for (int e = lane; e < kBlk; e += NT) H[(size_t)(15 * i + e / 15) * dim + 15 * i + e % 15] = Dm[e];
             if (i >= 1)
-                for (int e = lane; e < kBlk; e += 32) {
+                for (int e = lane; e < kBlk; e += NT) {
                     const double v = itm[(size_t)i * kItem + item_hab(e / 15, e % 15)];  // H(i-1, i)
                     H[(size_t)(15 * (i - 1) + e / 15) * dim + 15 * i + e % 15] += v;
                     H[(size_t)(15 * i + e % 15) * dim + 15 * (i - 1) + e / 15] += v;
                 }
-            __syncwarp();
+            grp_sync<NT>();
             if (has_cross(i))
-                for (int e = lane; e < 36; e += 32) {
+                for (int e = lane; e < 36; e += NT) {
                     const int r = e / 6, c = e % 6;
                     if (is_const(0, r) || is_const(i, c)) continue;
                     const double v = cross_entry(i, r, c);
                     H[(size_t)r * dim + 15 * i + c] += v;
                     H[(size_t)(15 * i + c) * dim + r] += v;
                 }
-            __syncwarp();
+            grp_sync<NT>();
         }
-        for (int i = lane; i < dim; i += 32) a.dense_g[(size_t)w * dim + i] = grad(i / 15, i % 15);
+        for (int i = lane; i < dim; i += NT) a.dense_g[(size_t)w * dim + i] = grad(i / 15, i % 15);
         if (lane == 0) a.dense_cost[w] = st.cost;
         st.status = 1;
         if (lane == 0) { a.state[w] = st; a.win_status[w] = 1; }
@@ -706,22 +753,22 @@ __device__ void window_step(const WindowArgs& a, int w, int lane, double* ws) {
 
     // ---- marginalisation program: forward elimination of frames 0..n-2 (solver.cpp:4-40)
     if (mode == 1) {
-        for (int i = lane; i < n * 15; i += 32) sb[i] = -grad(i / 15, i % 15);   // g = -J^T R
-        __syncwarp();
+        for (int i = lane; i < n * 15; i += NT) sb[i] = -grad(i / 15, i % 15);   // g = -J^T R
+        grp_sync<NT>();
         assemble_D(0, Dm);
         for (int i = 0; i + 1 < n; ++i) {
             assemble_D(i + 1, Cy);
             // Um = H(i+1, i) = H(i, i+1)^T
-            for (int e = lane; e < kBlk; e += 32) Um[e] = itm[(size_t)(i + 1) * kItem + item_hab(e % 15, e / 15)];
-            __syncwarp();
-            if (!spd_inverse15(Dm, piv, lane)) st.termination = 5;
-            gemm_ab15(Tm, Um, Dm, lane);                 // T = H(i+1,i) Hii^-1
-            gemm_sub_abt15(Cy, Tm, Um, lane);            // H(i+1,i+1) -= T H(i+1,i)^T
-            gemv15<false, true>(sb + 15 * (i + 1), Tm, sb + 15 * i, lane);
-            copy_blk(Dm, Cy, lane);
-            __syncwarp();
+            for (int e = lane; e < kBlk; e += NT) Um[e] = itm[(size_t)(i + 1) * kItem + item_hab(e % 15, e / 15)];
+            grp_sync<NT>();
+            if (!grp_inverse15<NT>(Dm, piv, red, lane)) st.termination = 5;
+            gemm_ab15<NT>(Tm, Um, Dm, lane);                 // T = H(i+1,i) Hii^-1
+            gemm_sub_abt15<NT>(Cy, Tm, Um, lane);            // H(i+1,i+1) -= T H(i+1,i)^T
+            gemv15<NT, false, true>(sb + 15 * (i + 1), Tm, sb + 15 * i, lane);
+            copy_blk<NT>(Dm, Cy, lane);
+            grp_sync<NT>();
         }
-        for (int e = lane; e < kBlk; e += 32) a.marg_H[(size_t)w * kBlk + e] = Dm[e];
+        for (int e = lane; e < kBlk; e += NT) a.marg_H[(size_t)w * kBlk + e] = Dm[e];
         if (lane < 15) a.marg_g[(size_t)w * 15 + lane] = sb[15 * (n - 1) + lane];
         st.status = 1;
         if (lane == 0) { a.state[w] = st; a.win_status[w] = 1; }
@@ -733,24 +780,24 @@ __device__ void window_step(const WindowArgs& a, int w, int lane, double* ws) {
     double* dvec = gvec + n * 15;   // unscaled diagonal of H at the accepted point
     {
         double mx = 0.0;
-        for (int i0 = lane; i0 < n * 15; i0 += 128) {
+        for (int i0 = lane; i0 < n * 15; i0 += 4 * NT) {
             double g[4], dg[4];
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
-                const int i = i0 + 32 * q;
+                const int i = i0 + NT * q;
                 const bool in = i < n * 15;
                 g[q] = in ? grad(i / 15, i % 15) : 0.0;
                 dg[q] = in ? diag_H(i / 15, i % 15) : 0.0;
             }
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
-                const int i = i0 + 32 * q;
+                const int i = i0 + NT * q;
                 if (i < n * 15) { gvec[i] = g[q]; dvec[i] = dg[q]; }
             }
         }
-        __syncwarp();
+        grp_sync<NT>();
         if (st.last_success) {
-            for (int f = lane; f < n; f += 32) {
+            for (int f = lane; f < n; f += NT) {
 #pragma unroll
                 for (int c = 0; c < 15; ++c) {
                     if (is_const(f, c) || (c >= 3 && c < 6)) continue;
@@ -763,7 +810,7 @@ __device__ void window_step(const WindowArgs& a, int w, int lane, double* ws) {
                     for (int c = 0; c < 3; ++c) mx = fmax(mx, fabs(x[15 * f + 3 + c] - outv[c]));
                 }
             }
-            mx = warp_max(mx);
+            mx = grp_max<NT>(mx, red, lane);
             if (mx <= opt.gradient_tolerance) {
                 st.status = 1; st.termination = 3;
                 if (lane == 0) { a.state[w] = st; a.win_status[w] = 1; }
@@ -775,9 +822,9 @@ __device__ void window_step(const WindowArgs& a, int w, int lane, double* ws) {
     // ---- Jacobi scaling (fixed at iteration 0)
     double* scw = a.scale + (size_t)w * n * 15;
     if (st.iteration == 0) {
-        for (int i = lane; i < n * 15; i += 32)
+        for (int i = lane; i < n * 15; i += NT)
             scw[i] = is_const(i / 15, i % 15) ? 1.0 : 1.0 / (1.0 + sqrt(dvec[i]));
-        __syncwarp();
+        grp_sync<NT>();
     }
 
     // ---- (3) trust-region step; invalid steps shrink the radius and retry without a new evaluation
@@ -787,17 +834,17 @@ __device__ void window_step(const WindowArgs& a, int w, int lane, double* ws) {
         if (st.radius < opt.min_radius) { st.status = 1; st.termination = 4; break; }
         ++st.iteration;
         bool ok = true;
-        for (int i = lane; i < n * 15; i += 32) sb[i] = is_const(i / 15, i % 15) ? 0.0 : gvec[i] * scw[i];
-        __syncwarp();
+        for (int i = lane; i < n * 15; i += NT) sb[i] = is_const(i / 15, i % 15) ? 0.0 : gvec[i] * scw[i];
+        grp_sync<NT>();
         const double inv_radius = 1.0 / st.radius;
         auto scale_damp = [&](int i, double* blkp) {  // A = S H S + diag(clamp(diag(S H S)) / radius); const entries -> identity
-            for (int e = lane; e < kBlk; e += 32) {
+            for (int e = lane; e < kBlk; e += NT) {
                 const int r = e / 15, c = e - r * 15;
                 double v = blkp[e] * scw[i * 15 + r] * scw[i * 15 + c];
                 if (r == c) v = is_const(i, r) ? 1.0 : v + fmin(fmax(v, opt.min_lm_diagonal), opt.max_lm_diagonal) * inv_radius;
                 blkp[e] = v;
             }
-            __syncwarp();
+            grp_sync<NT>();
         };
         // Dm/Cy swap roles every frame (pivot block <-> block being assembled)
         double* Dp = Dm;
@@ -811,13 +858,13 @@ __device__ void window_step(const WindowArgs& a, int w, int lane, double* ws) {
             {
                 const double* it_i = itm + (size_t)i * kItem;
                 const double* it_p = itm + (size_t)(i - 1) * kItem;
-                for (int e = lane; e < kBlk; e += 32) {
+                for (int e = lane; e < kBlk; e += NT) {
                     const int r = e / 15, c = e - r * 15;
                     cp_async8(Um + e, it_i + item_hab(r, c));
                     cp_async8(Cp + e, it_p + item_hbb(r, c));
                     cp_async8(Tm + e, it_i + item_haa(r, c));
                 }
-                for (int e = lane; e < NPAD; e += 32) cp_async8(slb + e, lb + (i - 1) * NPAD + e);
+                for (int e = lane; e < NPAD; e += NT) cp_async8(slb + e, lb + (i - 1) * NPAD + e);
                 if (lane < 30) cp_async8(ssc + lane, scw + (i - 1) * 15 + lane);
             }
             // per-frame flags, requested now and consumed after the inverse
@@ -828,21 +875,21 @@ __device__ void window_step(const WindowArgs& a, int w, int lane, double* ws) {
             if (ARROW && i >= 2) {
                 arrow_i = have_wc || cross_i;
                 if (arrow_i)
-                    for (int e = lane; e < kBlk; e += 32) {
+                    for (int e = lane; e < kBlk; e += NT) {
                         const int r = e / 15, c = e - r * 15;
                         double v = have_wc ? Wm[e] : 0.0;
                         if (cross_i && r < 6 && c < 6 && !is_const(0, r) && !is_const(i, c)) v += cross_entry(i, r, c) * scw[r] * scw[i * 15 + c];
                         Wm[e] = v;
                     }
             }
-            __syncwarp();
-            const bool inv_ok = spd_inverse15(Dp, piv, lane);
+            grp_sync<NT>();
+            const bool inv_ok = grp_inverse15<NT>(Dp, piv, red, lane);
             cp_async_wait_all();
-            __syncwarp();
+            grp_sync<NT>();
             if (!inv_ok) { ok = false; break; }
             // coupling U = H(i-1, i), scaled (+ laser cross block / carried fill-in when i == 1: H(0,1) is also the arrow
             // block); D_{i-1} assembled, scaled and damped
-            for (int e = lane; e < kBlk; e += 32) {
+            for (int e = lane; e < kBlk; e += NT) {
                 const int r = e / 15, c = e - r * 15;
                 double v = Um[e] * ssc[r] * ssc[15 + c];
                 if (ARROW && i == 1) {
@@ -858,61 +905,61 @@ __device__ void window_step(const WindowArgs& a, int w, int lane, double* ws) {
                 if (r == c) dv = col_const(cm_p, r) ? 1.0 : dv + fmin(fmax(dv, opt.min_lm_diagonal), opt.max_lm_diagonal) * inv_radius;
                 Cp[e] = dv;
             }
-            __syncwarp();
-            gemm_ab15(Tm, Um, Dp, lane);                                   // T = U Dinv
-            if (ARROW && arrow_i) gemm_ab15(Tp, Wm, Dp, lane);             // T' = W Dinv
-            gemv15<false, false>(piv, Dp, sb + 15 * i, lane);              // c_i = Dinv b_i
+            grp_sync<NT>();
+            gemm_ab15<NT>(Tm, Um, Dp, lane);                                   // T = U Dinv
+            if (ARROW && arrow_i) gemm_ab15<NT>(Tp, Wm, Dp, lane);             // T' = W Dinv
+            gemv15<NT, false, false>(piv, Dp, sb + 15 * i, lane);              // c_i = Dinv b_i
             if (lane < 15) sb[15 * i + lane] = piv[lane];
-            __syncwarp();
-            for (int e = lane; e < kBlk; e += 32) {
+            grp_sync<NT>();
+            for (int e = lane; e < kBlk; e += NT) {
                 facw[(size_t)i * 3 * kBlk + e] = Tm[e];
                 if (ARROW) facw[(size_t)i * 3 * kBlk + kBlk + e] = arrow_i ? Tp[e] : 0.0;
             }
-            gemv15<false, true>(sb + 15 * (i - 1), Um, sb + 15 * i, lane);  // b_{i-1} -= U c_i
-            if (ARROW && arrow_i) gemv15<false, true>(sb, Wm, sb + 15 * i, lane);
-            gemm_sub_abt15(Cp, Tm, Um, lane);                               // D_{i-1} -= T U^T
+            gemv15<NT, false, true>(sb + 15 * (i - 1), Um, sb + 15 * i, lane);  // b_{i-1} -= U c_i
+            if (ARROW && arrow_i) gemv15<NT, false, true>(sb, Wm, sb + 15 * i, lane);
+            gemm_sub_abt15<NT>(Cp, Tm, Um, lane);                               // D_{i-1} -= T U^T
             if (ARROW && arrow_i) {
-                if (!have_d0) { for (int e = lane; e < kBlk; e += 32) D0[e] = 0.0; __syncwarp(); have_d0 = true; }
-                gemm_sub_abt15(D0, Tp, Wm, lane);                           // D_0 -= T' W^T
+                if (!have_d0) { for (int e = lane; e < kBlk; e += NT) D0[e] = 0.0; grp_sync<NT>(); have_d0 = true; }
+                gemm_sub_abt15<NT>(D0, Tp, Wm, lane);                           // D_0 -= T' W^T
                 // fill-in for frame i-1: H(0, i-1) = -T' U^T   (Wm is free again after this; the old pivot block is scratch)
-                for (int e = lane; e < kBlk; e += 32) Dp[e] = 0.0;
-                __syncwarp();
-                gemm_sub_abt15(Dp, Tp, Um, lane);
-                copy_blk(Wm, Dp, lane);
-                __syncwarp();
+                for (int e = lane; e < kBlk; e += NT) Dp[e] = 0.0;
+                grp_sync<NT>();
+                gemm_sub_abt15<NT>(Dp, Tp, Um, lane);
+                copy_blk<NT>(Wm, Dp, lane);
+                grp_sync<NT>();
                 have_wc = true;
             } else if (ARROW) {
                 have_wc = false;
             }
             if (ARROW && i - 1 == 0 && have_d0) {
-                for (int e = lane; e < kBlk; e += 32) Cp[e] += D0[e];
-                __syncwarp();
+                for (int e = lane; e < kBlk; e += NT) Cp[e] += D0[e];
+                grp_sync<NT>();
             }
             { double* t = Dp; Dp = Cp; Cp = t; }
         }
-        if (ok) ok = spd_inverse15(Dp, piv, lane);
+        if (ok) ok = grp_inverse15<NT>(Dp, piv, red, lane);
         if (ok) {
-            gemv15<false, false>(piv, Dp, sb, lane);   // y_0 = D0inv b_0
+            gemv15<NT, false, false>(piv, Dp, sb, lane);   // y_0 = D0inv b_0
             if (lane < 15) sb[lane] = piv[lane];
-            __syncwarp();
+            grp_sync<NT>();
             // T_i (and T'_i) come back from global memory one frame ahead of their use (Tm / Um alternate)
             auto fetch_T = [&](int i, double* dstT) {
-                for (int e = lane; e < kBlk; e += 32) cp_async8(dstT + e, facw + (size_t)i * 3 * kBlk + e);
+                for (int e = lane; e < kBlk; e += NT) cp_async8(dstT + e, facw + (size_t)i * 3 * kBlk + e);
             };
             if (n > 1) fetch_T(1, Tm);
             for (int i = 1; i < n; ++i) {
                 double* Tc = (i & 1) ? Tm : Um;
-                if (ARROW && i >= 2) for (int e = lane; e < kBlk; e += 32) cp_async8(Tp + e, facw + (size_t)i * 3 * kBlk + kBlk + e);
+                if (ARROW && i >= 2) for (int e = lane; e < kBlk; e += NT) cp_async8(Tp + e, facw + (size_t)i * 3 * kBlk + kBlk + e);
                 cp_async_wait_all();
-                __syncwarp();
+                grp_sync<NT>();
                 if (i + 1 < n) fetch_T(i + 1, (i & 1) ? Um : Tm);
-                gemv15<true, true>(sb + 15 * i, Tc, sb + 15 * (i - 1), lane);   // y_i = c_i - T^T y_{i-1} - T'^T y_0
-                if (ARROW && i >= 2) gemv15<true, true>(sb + 15 * i, Tp, sb, lane);
+                gemv15<NT, true, true>(sb + 15 * i, Tc, sb + 15 * (i - 1), lane);   // y_i = c_i - T^T y_{i-1} - T'^T y_0
+                if (ARROW && i >= 2) gemv15<NT, true, true>(sb + 15 * i, Tp, sb, lane);
             }
             // step = -y ; model_cost_change = -1/2 step.gs + 1/2 sum lm_diag step^2
             double sg = 0.0, lq = 0.0;
             bool finite = true;
-            for (int i = lane; i < n * 15; i += 32) {
+            for (int i = lane; i < n * 15; i += NT) {
                 if (is_const(i / 15, i % 15)) { sb[i] = 0.0; continue; }
                 const double stp = -sb[i];
                 sb[i] = stp;
@@ -922,13 +969,13 @@ __device__ void window_step(const WindowArgs& a, int w, int lane, double* ws) {
                 sg += stp * gvec[i] * sc;
                 lq += fmin(fmax(hs, opt.min_lm_diagonal), opt.max_lm_diagonal) * inv_radius * stp * stp;
             }
-            sg = warp_sum(sg);
-            lq = warp_sum(lq);
-            finite = __all_sync(0xffffffffu, finite);
+            sg = grp_sum<NT>(sg, red, lane);
+            lq = grp_sum<NT>(lq, red, lane);
+            finite = grp_all<NT>(finite, red, lane);
             st.model_cost_change = -0.5 * sg + 0.5 * lq;
             ok = finite && st.model_cost_change > 0.0;
         }
-        __syncwarp();
+        grp_sync<NT>();
         if (ok) { have_step = true; st.num_invalid = 0; break; }
         // HandleInvalidStep
         ++st.num_invalid;
@@ -945,7 +992,7 @@ __device__ void window_step(const WindowArgs& a, int w, int lane, double* ws) {
     }
 
     // ---- (4) candidate = Plus(x, step * scale) and its laser frame tables
-    for (int f = lane; f < n; f += 32) {
+    for (int f = lane; f < n; f += NT) {
         double d[15];
 #pragma unroll
         for (int c = 0; c < 15; ++c) d[c] = sb[f * 15 + c] * scw[f * 15 + c];
@@ -957,14 +1004,20 @@ __device__ void window_step(const WindowArgs& a, int w, int lane, double* ws) {
     if (lane == 0) { a.state[w] = st; a.win_status[w] = 0; }
 }
 
-template <bool ARROW>
-__global__ void __launch_bounds__(64, 8) window_kernel(WindowArgs a, int per_warp_doubles) {
+template <bool ARROW, int NT>
+__global__ void __launch_bounds__(NT == 32 ? 64 : NT, NT == 32 ? 8 : 4) window_kernel(WindowArgs a, int per_window_doubles) {
     extern __shared__ __align__(16) double smem[];
-    const int lane = threadIdx.x & 31;
-    const int warp = threadIdx.x >> 5;
-    const int w = blockIdx.x * (blockDim.x >> 5) + warp;
-    if (w >= a.n_windows) return;
-    window_step<ARROW>(a, w, lane, smem + (size_t)warp * per_warp_doubles);
+    if (NT == 32) {
+        // batched shape: one warp per window, two windows per CTA
+        const int lane = threadIdx.x & 31;
+        const int warp = threadIdx.x >> 5;
+        const int w = blockIdx.x * (blockDim.x >> 5) + warp;
+        if (w >= a.n_windows) return;
+        window_step<ARROW, NT>(a, w, lane, smem + (size_t)warp * per_window_doubles);
+    } else {
+        // small batches: one CTA of NT threads per window
+        window_step<ARROW, NT>(a, blockIdx.x, threadIdx.x, smem);
+    }
 }
 
 __global__ void init_state_kernel(LMState* st, int32_t* status, int n, double radius) {

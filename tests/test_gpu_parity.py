@@ -20,11 +20,20 @@ def P10():
     return L.corridor_params(max_iters=10)
 
 
-@pytest.fixture(scope="module")
-def ctx(P10):
+@pytest.fixture(scope="module", params=[128, 32], ids=["4warps", "1warp"])
+def ctx(P10, request):
+    """One context per thread-group shape of window_kernel (LVIO2D_WINDOW_THREADS is read by lvio2d_create)."""
+    import os
+
     from lvio2d_b200.solver import Context
 
+    old = os.environ.get("LVIO2D_WINDOW_THREADS")
+    os.environ["LVIO2D_WINDOW_THREADS"] = str(request.param)
     c = Context(P10)
+    if old is None:
+        del os.environ["LVIO2D_WINDOW_THREADS"]
+    else:
+        os.environ["LVIO2D_WINDOW_THREADS"] = old
     yield c
     c.close()
 
@@ -118,13 +127,17 @@ def test_linearize_matches_oracle(ctx, oracle, P10, case, mode):
 
 @pytest.mark.parametrize("case,iters", [("c1", 1), ("c2_small", 10), ("tracking2", 20), ("init", 20), ("c2_full", 10),
                                         ("tracking2", 50), ("init", 50)])
-def test_solve_matches_oracle(oracle, case, iters):
+@pytest.mark.parametrize("wt", [32, 128])
+def test_solve_matches_oracle(oracle, case, iters, wt, monkeypatch):
     """Up to ~20 iterations the two minimisers walk in lock-step (differences ~1e-13).  The reference's default of 50
     iterations (solver.cpp:161-168, no fast_mode) ends in a slowly converging zig-zag (the ground/wheel residuals are
     norms) where rounding differences are amplified and an accept/reject decision can flip; there
     the bar is the north-star's 1e-4 m / 1e-4 rad per keyframe, and costs within 1 %."""
     from lvio2d_b200.solver import Context
 
+    # both thread-group shapes of window_kernel: one warp per window (the batched shape) and four warps per window (what
+    # small batches get by default)
+    monkeypatch.setenv("LVIO2D_WINDOW_THREADS", str(wt))
     P = L.corridor_params(max_iters=iters)
     sb = CASES[case]()
     hb = oracle.preintegrate_batch(P, sb)
