@@ -233,11 +233,11 @@ int launch_factors(lvio2d_ctx* ctx, const WindowArgs& a) {
 
 int launch_window(lvio2d_ctx* ctx, const WindowArgs& a) {
     const int per_window = (int)window_smem_doubles(ctx->n, ctx->arrow);
-    // thread group per window: one warp when the batch fills the machine (4 x 148 CTAs of 128 threads hold 592 windows at
-    // once), four warps below that — the same arithmetic spread four ways, for the latency of small batches
-    // (LVIO2D_WINDOW_THREADS = 32 | 128 forces one of them; used by the tests to cover both)
-    int nt = ctx->B <= 4 * ctx->sm_count ? 128 : 32;
-    if (ctx->window_threads == 32 || ctx->window_threads == 128) nt = ctx->window_threads;
+    // thread group per window: one warp when the batch fills the machine, four warps when it fits 4 CTAs per SM,
+    // eight warps when it fits 2 CTAs per SM — the same arithmetic spread four ways, for the latency of small batches
+    // (LVIO2D_WINDOW_THREADS = 32 | 128 | 256 forces one of them; used by the tests to cover both)
+    int nt = ctx->B <= 2 * ctx->sm_count ? 256 : (ctx->B <= 4 * ctx->sm_count ? 128 : 32);
+    if (ctx->window_threads == 32 || ctx->window_threads == 128 || ctx->window_threads == 256) nt = ctx->window_threads;
     if (ctx->profiling) cudaEventRecord(next_event(ctx->ev_win, ctx->ev_win_used), ctx->stream);
     ctx->launches += 1;
 #define LAUNCH_WIN(AR, NT, GRID, BLOCK, SMEM)                                                                                 \
@@ -250,9 +250,12 @@ int launch_window(lvio2d_ctx* ctx, const WindowArgs& a) {
         const size_t smem = (size_t)wpc * per_window * sizeof(double);
         const int grid = (ctx->B + wpc - 1) / wpc;
         if (ctx->arrow) LAUNCH_WIN(true, 32, grid, wpc * 32, smem); else LAUNCH_WIN(false, 32, grid, wpc * 32, smem);
-    } else {
+    } else if (nt == 128) {
         const size_t smem = (size_t)per_window * sizeof(double);
         if (ctx->arrow) LAUNCH_WIN(true, 128, ctx->B, 128, smem); else LAUNCH_WIN(false, 128, ctx->B, 128, smem);
+    } else {
+        const size_t smem = (size_t)per_window * sizeof(double);
+        if (ctx->arrow) LAUNCH_WIN(true, 256, ctx->B, 256, smem); else LAUNCH_WIN(false, 256, ctx->B, 256, smem);
     }
 #undef LAUNCH_WIN
     if (ctx->profiling) cudaEventRecord(next_event(ctx->ev_win, ctx->ev_win_used), ctx->stream);

@@ -351,7 +351,7 @@ __device__ __noinline__ bool spd_inverse15(double* A, double* piv /* 16 doubles 
 template <int NT> __device__ __forceinline__ void grp_sync() {
     if (NT == 32) __syncwarp(); else __syncthreads();
 }
-// reductions over the group; `red` = 8 doubles of shared scratch (NT > 32 only); every thread gets the result, and the
+// reductions over the group; `red` = 16 doubles of shared scratch (NT > 32 only); every thread gets the result, and the
 // cross-warp part is summed in a fixed order (deterministic)
 template <int NT> __device__ __forceinline__ double grp_sum(double v, double* red, int tid) {
     v = warp_sum(v);
@@ -379,15 +379,15 @@ template <int NT> __device__ __forceinline__ bool grp_all(bool v, double* red, i
     if (NT == 32) return __all_sync(0xffffffffu, v);
     return __syncthreads_and(v) != 0;
 }
-// SPD inverse by the first warp of the group, result flag broadcast through `red[4]`
+// SPD inverse by the first warp of the group, result flag broadcast through `red[8]`
 template <int NT> __device__ __forceinline__ bool grp_inverse15(double* A, double* piv, double* red, int tid) {
     if (NT == 32) return spd_inverse15(A, piv, tid);
     if (tid < 32) {
         const bool ok = spd_inverse15(A, piv, tid);
-        if (tid == 0) red[4] = ok ? 1.0 : 0.0;
+        if (tid == 0) red[8] = ok ? 1.0 : 0.0;
     }
     __syncthreads();
-    return red[4] != 0.0;
+    return red[8] != 0.0;
 }
 // The two GEMM kernels: thread = (row r = tid & 15, column group g = tid >> 4); NT / 16 groups of ceil(15 / groups)
 // columns each (NT = 32: 8 + 7 columns, NT = 128: 2 columns per thread).
@@ -451,7 +451,7 @@ template <int NT> __device__ __forceinline__ void copy_blk(double* dst, const do
 }
 // per-warp shared memory of window_kernel (doubles): 4 blocks (+3 for the arrow topology) + pivot row + one frame's
 // laser block + rhs [n][15]
-__host__ __device__ inline size_t window_smem_doubles(int n, bool arrow) { return (arrow ? 7 : 4) * kBlk + 16 + 48 + 32 + 8 + (size_t)n * 15 + 16; }
+__host__ __device__ inline size_t window_smem_doubles(int n, bool arrow) { return (arrow ? 7 : 4) * kBlk + 16 + 48 + 32 + 16 + (size_t)n * 15 + 16; }
 
 // ---------------------------------------------------------------------------------------------------
 template <bool ARROW, int NT>
@@ -475,8 +475,8 @@ __device__ void window_step(const WindowArgs& a, int w, int lane, double* ws) {
     double* piv = ws + (ARROW ? 7 : 4) * kBlk;  // 16
     double* slb = piv + 16;           // laser block of the frame being assembled [NPAD]
     double* ssc = slb + 48;           // Jacobi scaling of frames i-1 and i [30]
-    double* red = ssc + 32;           // cross-warp reduction scratch [8]
-    double* sb = red + 8;             // rhs / solution [n][15]
+    double* red = ssc + 32;           // cross-warp reduction scratch [16]
+    double* sb = red + 16;            // rhs / solution [n][15]
 
     double* x = a.x + (size_t)w * n * 15;
     double* xc = a.xc + (size_t)w * n * 15;
@@ -1005,7 +1005,7 @@ __device__ void window_step(const WindowArgs& a, int w, int lane, double* ws) {
 }
 
 template <bool ARROW, int NT>
-__global__ void __launch_bounds__(NT == 32 ? 64 : NT, NT == 32 ? 8 : 4) window_kernel(WindowArgs a, int per_window_doubles) {
+__global__ void __launch_bounds__(NT == 32 ? 64 : NT, NT == 32 ? 8 : 512 / NT) window_kernel(WindowArgs a, int per_window_doubles) {
     extern __shared__ __align__(16) double smem[];
     if (NT == 32) {
         // batched shape: one warp per window, two windows per CTA

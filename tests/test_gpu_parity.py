@@ -20,7 +20,7 @@ def P10():
     return L.corridor_params(max_iters=10)
 
 
-@pytest.fixture(scope="module", params=[128, 32], ids=["4warps", "1warp"])
+@pytest.fixture(scope="module", params=[256, 128, 32], ids=["8warps", "4warps", "1warp"])
 def ctx(P10, request):
     """One context per thread-group shape of window_kernel (LVIO2D_WINDOW_THREADS is read by lvio2d_create)."""
     import os
@@ -127,7 +127,7 @@ def test_linearize_matches_oracle(ctx, oracle, P10, case, mode):
 
 @pytest.mark.parametrize("case,iters", [("c1", 1), ("c2_small", 10), ("tracking2", 20), ("init", 20), ("c2_full", 10),
                                         ("tracking2", 50), ("init", 50)])
-@pytest.mark.parametrize("wt", [32, 128])
+@pytest.mark.parametrize("wt", [32, 128, 256])
 def test_solve_matches_oracle(oracle, case, iters, wt, monkeypatch):
     """Up to ~20 iterations the two minimisers walk in lock-step (differences ~1e-13).  The reference's default of 50
     iterations (solver.cpp:161-168, no fast_mode) ends in a slowly converging zig-zag (the ground/wheel residuals are
