@@ -90,6 +90,7 @@ struct lvio2d_ctx {
     double* ext_reduce = nullptr; int64_t ext_reduce_count = 0;
     int step_calls = 0;
     int window_threads = 0;   // 0 = automatic
+    bool factor_paired = true; // LVIO2D_FACTOR_PAIRED=0 selects the one-item-per-warp factor kernel
     bool have_solution = false;
     // host staging of the small index arrays (kept alive until the next upload so that copies can stay asynchronous)
     PinnedVec<int64_t> h_poff, h_loff;
@@ -222,10 +223,18 @@ WindowArgs window_args(lvio2d_ctx* ctx, int mode) {
 int launch_factors(lvio2d_ctx* ctx, const WindowArgs& a) {
     const int wpc = 4;
     const int items = ctx->B * ctx->n;
-    const size_t smem = (size_t)wpc * kFactorSmem * sizeof(double);
     if (ctx->profiling) cudaEventRecord(next_event(ctx->ev_fac, ctx->ev_fac_used), ctx->stream);
     ctx->launches += 1;
-    factor_kernel<<<(items + wpc - 1) / wpc, wpc * 32, smem, ctx->stream>>>(a);
+    if (ctx->factor_paired) {
+        // two items per warp (half-warp each for the dual-number part, see factor_pair_kernel)
+        const int pairs = (items + 1) / 2;
+        const size_t smem = (size_t)wpc * kPairSmem * sizeof(double);
+        CK(cudaFuncSetAttribute(factor_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        factor_pair_kernel<<<(pairs + wpc - 1) / wpc, wpc * 32, smem, ctx->stream>>>(a);
+    } else {
+        const size_t smem = (size_t)wpc * kFactorSmem * sizeof(double);
+        factor_kernel<<<(items + wpc - 1) / wpc, wpc * 32, smem, ctx->stream>>>(a);
+    }
     if (ctx->profiling) cudaEventRecord(next_event(ctx->ev_fac, ctx->ev_fac_used), ctx->stream);
     CK(cudaGetLastError());
     return LVIO2D_OK;
@@ -458,6 +467,7 @@ int lvio2d_create(lvio2d_ctx** out, const lvio2d_params* params) {
         return LVIO2D_ERR_CUDA;
     }
     if (const char* wt = std::getenv("LVIO2D_WINDOW_THREADS")) ctx->window_threads = std::atoi(wt);
+    if (const char* fp = std::getenv("LVIO2D_FACTOR_PAIRED")) ctx->factor_paired = std::atoi(fp) != 0;
     *out = ctx;
     return LVIO2D_OK;
 }

@@ -37,6 +37,9 @@
 #ifndef LV_FACTOR_MINB
 #define LV_FACTOR_MINB 4   // resident CTAs (of 4 warps) per SM the register budget of factor_kernel is sized for
 #endif
+#ifndef LV_PAIR_MINB
+#define LV_PAIR_MINB 3     // resident CTAs per SM the register budget of factor_pair_kernel is sized for
+#endif
 #ifndef LV_FACTOR_ROLL
 #define LV_FACTOR_ROLL 1   // 1: keep the column loop of the J^T J product rolled (smaller instruction footprint)
 #endif
@@ -303,6 +306,255 @@ __global__ void __launch_bounds__(128, LV_FACTOR_MINB) factor_kernel(WindowArgs 
     }
     cost = warp_sum(cost);
     if (lane == 31) out[kItemCost] = cost;
+}
+
+// =====================================================================================================
+// factor_pair_kernel: the same items, TWO per warp.
+//
+// Of the 30 state columns of an item only 12 need dual-number arithmetic: theta_a, theta_b, bw_a (the rotation chain
+// of the IMU residual) and p_b (the norm-type wheel residuals; d/dp_a = -d/dp_b exactly, both enter through
+// t_oj - t_oi).  The other 15 columns (v_a, ba_a, v_b, ba_b, bw_b) only touch the IMU factor, linearly:
+//   d r_alpha / d v_a = R_i^T Dt,  d r_beta / d v_a = R_i^T,  d r_beta / d v_b = -R_i^T,
+//   d r_{alpha,beta} / d ba_a = J[:, 9..11],  d r_ba / d ba_{a,b} = -+I,  d r_bw / d bw_b = I
+// — exactly what the dual path produces for them (its products with the zero dual parts add exact zeros).
+// So a half-warp carries one item: sub-lane 0 the values, 1..3 p_b, 4..6 theta_a, 7..9 theta_b, 10..12 bw_a; after the
+// dual evaluation each of the 15 closed-form columns is whitened by one sub-lane.  The J^T J products (30 columns wide)
+// then run for the two items one after the other on the full warp.  Instruction count per item: ~2.8 k instead of
+// ~5.2 k.  Per-warp shared memory: 2 x (blob 480 | whitened J 15x32 | wheel 3x16 | ground 2x8 | wheel blob 16) + prior
+// residual 16 + prior J 240.
+constexpr int kPairHalf = 480 + 480 + 48 + 16 + 16;
+constexpr int kPairSmem = 2 * kPairHalf + 16 + 240;
+__global__ void __launch_bounds__(128, LV_PAIR_MINB) factor_pair_kernel(WindowArgs a) {
+    extern __shared__ __align__(16) double smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int h = lane >> 4, sl = lane & 15;
+    const int n = a.n_frames, total = a.n_windows * n;
+    const int pair = blockIdx.x * (blockDim.x >> 5) + warp;
+    const int item = 2 * pair + h;
+    int w = 0, i = 0;
+    bool live = item < total;
+    if (live) { w = item / n; i = item - w * n; live = a.win_status[w] == 0; }
+    if (!__any_sync(0xffffffffu, live)) return;
+    const int mode = a.mode;
+    double* base = smem + (size_t)warp * kPairSmem;
+    double* sblob = base + h * kPairHalf;
+    double* sJ = sblob + 480;   // whitened IMU Jacobian [15][32]; column 30 = whitened residual
+    double* sW = sJ + 480;      // wheel [3][16]: cols 0..11 Jacobian, col 12 residual
+    double* sG = sW + 48;       // ground [2][8]: cols 0..5 Jacobian, col 6 residual
+    double* sWb = sG + 16;      // wheel blob [15]
+    double* sP = base + 2 * kPairHalf;   // prior residual [15]   (phase B, one item at a time)
+    double* sPJ = sP + 16;               // prior J [225]
+    const double* X = a.xc + (size_t)w * n * 15;
+    const uint8_t* cm = a.const_mask + (size_t)w * n;
+    const uint8_t mb = (mode == 1 || !live) ? 0 : cm[i];
+    const uint8_t ma = (mode == 1 || i == 0 || !live) ? 0 : cm[i - 1];
+    const double* xb = X + 15 * i;
+    const double* xa = X + 15 * (i > 0 ? i - 1 : 0);
+    const bool imu_on = live && i > 0 && a.has_imu && ((ma & 15) != 15 || (mb & 15) != 15);
+    const bool wheel_on = live && i > 0 && a.has_wheel && ((ma & 3) != 3 || (mb & 3) != 3);
+    const bool ground_on = live && a.ground_multiplicity > 0 && (mb & 3) != 3;
+    const bool prior_on = live && a.prior_frame == i && (mb & 15) != 15;
+    // ---- phase A: both items at once.  Constant inputs travel to shared memory while the exponentials are evaluated.
+    if (imu_on) {
+        const double* blob = a.imu + ((size_t)w * (n - 1) + (i - 1)) * 466;
+        if ((reinterpret_cast<uintptr_t>(blob) & 15) == 0) {
+            for (int k = sl; k < 233; k += 16) cp_async16(sblob + 2 * k, blob + 2 * k);
+        } else {
+            for (int k = sl; k < 466; k += 16) cp_async8(sblob + k, blob + k);
+        }
+    }
+    if (wheel_on && sl < 15) cp_async8(sWb + sl, a.wheel + ((size_t)w * (n - 1) + (i - 1)) * 15 + sl);
+    // sub-lane roles
+    const bool value_lane = sl == 0;
+    const bool l_pb = sl >= 1 && sl <= 3, l_ta = sl >= 4 && sl <= 6, l_tb = sl >= 7 && sl <= 9, l_bw = sl >= 10 && sl <= 12;
+    const int kk = l_pb ? sl - 1 : (l_ta ? sl - 4 : (l_tb ? sl - 7 : (l_bw ? sl - 10 : 0)));   // component 0..2
+    const int seed_a = l_ta ? 3 + kk : (l_bw ? 12 + kk : -1);
+    const int seed_b = l_pb ? kk : (l_tb ? 3 + kk : -1);
+    // frame-a / frame-b column this lane's derivative belongs to (p_b lanes also own the negated p_a column)
+    const int col_a = l_ta ? 3 + kk : (l_bw ? 12 + kk : (l_pb ? kk : -1));
+    const int col_b = l_pb ? kk : (l_tb ? 3 + kk : -1);
+    const bool dead_a = col_a >= 0 && col_const(ma, col_a);
+    const bool dead_b = col_b >= 0 && col_const(mb, col_b);
+    double cost = 0.0;
+    {
+        const FrameState<Dual> fa_ = seed_frame_state(xa, seed_a);
+        const FrameState<Dual> fb_ = seed_frame_state(xb, seed_b);
+        const M3<Dual> Rj = exp_so3(fb_.th);
+        M3<Dual> Ri;
+        if (imu_on || wheel_on) Ri = exp_so3(fa_.th);
+        cp_async_wait_all();
+        __syncwarp();
+        if (imu_on) {
+            Dual ri[15];
+            item_imu<Dual>(a.C, sblob, fa_, fb_, Ri, Rj, ri);
+            const double* Sq = sblob + 240;  // sqrt_inverse_P = L^T: upper triangular
+            if (sl <= 12) {
+#pragma unroll
+                for (int r = 0; r < 15; ++r) {
+                    double s = 0.0;
+#pragma unroll
+                    for (int k = r; k < 15; ++k) s += Sq[r * 15 + k] * (value_lane ? ri[k].a : ri[k].d);
+                    if (value_lane) {
+                        sJ[r * 32 + 30] = s; sJ[r * 32 + 31] = 0.0;
+                        cost += s * s;
+                    } else {
+                        if (col_a >= 0) sJ[r * 32 + col_a] = dead_a ? 0.0 : (l_pb ? -s : s);
+                        if (col_b >= 0) sJ[r * 32 + 15 + col_b] = dead_b ? 0.0 : s;
+                    }
+                }
+            }
+            // the 15 closed-form columns, one per sub-lane: t = 0 v_a, 1 ba_a, 2 v_b, 3 ba_b, 4 bw_b; component k
+            if (sl < 15) {
+                const int t = sl / 3, k = sl - 3 * t;
+                const double Dt = sblob[465];
+                const double* Jm = sblob + 15;
+                double rik[3];   // row k of R_i (= column k of R_i^T)
+#pragma unroll
+                for (int j = 0; j < 3; ++j) rik[j] = k == 0 ? Ri.m[j].a : (k == 1 ? Ri.m[3 + j].a : Ri.m[6 + j].a);
+                double raw[15];
+#pragma unroll
+                for (int r = 0; r < 15; ++r) {
+                    double v = 0.0;
+                    if (r < 3) v = t == 0 ? rik[r] * Dt : (t == 1 ? Jm[r * 15 + 9 + k] : 0.0);
+                    else if (r < 6) v = t == 0 ? rik[r - 3] : (t == 1 ? Jm[r * 15 + 9 + k] : (t == 2 ? -rik[r - 3] : 0.0));
+                    else if (r >= 9 && r < 12) v = (r - 9 == k) ? (t == 1 ? -1.0 : (t == 3 ? 1.0 : 0.0)) : 0.0;
+                    else if (r >= 12) v = (r - 12 == k && t == 4) ? 1.0 : 0.0;
+                    raw[r] = v;
+                }
+                // column index: v_a 6.., ba_a 9.., v_b 21.., ba_b 24.., bw_b 27..
+                const int c = (t == 0 ? 6 : (t == 1 ? 9 : (t == 2 ? 21 : (t == 3 ? 24 : 27)))) + k;
+                const bool dead = col_const(c < 15 ? ma : mb, c % 15);
+#pragma unroll
+                for (int r = 0; r < 15; ++r) {
+                    double s = 0.0;
+#pragma unroll
+                    for (int q = r; q < 15; ++q) s += Sq[r * 15 + q] * raw[q];
+                    sJ[r * 32 + c] = dead ? 0.0 : s;
+                }
+            }
+        } else {
+            for (int k = sl; k < 480; k += 16) sJ[k] = 0.0;
+        }
+        if (wheel_on) {
+            Dual rw[3];
+            item_wheel<Dual>(a.C, sWb, fa_.p, fb_.p, Ri, Rj, rw);
+            if (value_lane) {
+#pragma unroll
+                for (int k = 0; k < 3; ++k) { sW[k * 16 + 12] = rw[k].a; cost += rw[k].a * rw[k].a; }
+            } else if (l_pb || l_ta || l_tb) {
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    if (col_a >= 0) sW[k * 16 + col_a] = dead_a ? 0.0 : (l_pb ? -rw[k].d : rw[k].d);
+                    if (col_b >= 0) sW[k * 16 + 6 + col_b] = dead_b ? 0.0 : rw[k].d;
+                }
+            }
+        } else {
+            for (int k = sl; k < 48; k += 16) sW[k] = 0.0;
+        }
+        if (ground_on) {
+            Dual rg[2];
+            item_ground<Dual>(a.C, fb_.p, Rj, rg);
+            if (value_lane) {
+                sG[6] = rg[0].a;
+                sG[14] = rg[1].a;
+                cost += a.ground_multiplicity * (rg[0].a * rg[0].a + rg[1].a * rg[1].a);
+            } else if (col_b >= 0) {
+                sG[col_b] = dead_b ? 0.0 : rg[0].d;
+                sG[8 + col_b] = dead_b ? 0.0 : rg[1].d;
+            }
+        } else {
+            sG[sl] = 0.0;
+        }
+    }
+    __syncwarp();
+    // ---- phase B: J^T J of the two items, one after the other on the full warp (lane = state column)
+#pragma unroll 1
+    for (int hh = 0; hh < 2; ++hh) {
+        const int src = 16 * hh;
+        if (!__shfl_sync(0xffffffffu, (int)live, src)) continue;
+        const int wv = __shfl_sync(0xffffffffu, w, src), iv = __shfl_sync(0xffffffffu, i, src);
+        const uint8_t mbv = (uint8_t)__shfl_sync(0xffffffffu, (int)mb, src);
+        const bool prior_v = __shfl_sync(0xffffffffu, (int)prior_on, src) != 0;
+        const int parity = 1 - a.state[wv].cur;
+        double* out = a.items + ((size_t)parity * total + (size_t)wv * n + iv) * kItem;
+        const double* sJh = base + hh * kPairHalf + 480;
+        const double* sWh = sJh + 480;
+        const double* sGh = sWh + 48;
+        double c_item = lane == src ? cost : 0.0;
+        if (prior_v) {
+            const double* PJg = a.prior_J + (size_t)wv * kBlk;
+            for (int k = lane; k < kBlk; k += 32) cp_async8(sPJ + k, PJg + k);
+            cp_async_wait_all();
+            __syncwarp();
+            if (lane < 15) {
+                const double* X0 = a.prior_X0 + (size_t)wv * 15;
+                const double* xbv = a.xc + ((size_t)wv * n + iv) * 15;
+                double s = 0.0;
+                for (int k = 0; k < 15; ++k) s += sPJ[lane * 15 + k] * (xbv[k] - X0[k]);
+                sP[lane] = s;
+                c_item += s * s;
+            }
+            __syncwarp();
+        }
+        double gsum = 0.0;
+        if (lane < 30) {
+            double mine[15];
+#pragma unroll
+            for (int r = 0; r < 15; ++r) mine[r] = sJh[r * 32 + lane];
+#pragma unroll
+            for (int r = 0; r < 15; ++r) gsum += mine[r] * sJh[r * 32 + 30];
+            const int fl = lane % 15;
+            const bool pose_lane = fl < 6;
+            const int wc = (lane < 15 ? 0 : 6) + fl;
+            double w0 = 0.0, w1 = 0.0, w2 = 0.0, jp = 0.0, jq = 0.0;
+            const double m = (double)a.ground_multiplicity;
+            if (pose_lane) {
+                w0 = sWh[wc]; w1 = sWh[16 + wc]; w2 = sWh[32 + wc];
+                gsum += w0 * sWh[12] + w1 * sWh[16 + 12] + w2 * sWh[32 + 12];
+                if (lane >= 15) {
+                    jp = sGh[fl]; jq = sGh[8 + fl];
+                    gsum += m * (jp * sGh[6] + jq * sGh[8 + 6]);
+                }
+            }
+            const bool prior_lane = prior_v && lane >= 15 && !col_const(mbv, fl);
+            if (prior_lane) {
+                double gs = 0.0;
+                for (int r = 0; r < 15; ++r) gs += sPJ[r * 15 + fl] * sP[r];
+                gsum += gs;
+            }
+#pragma unroll 1
+            for (int c2 = 0; c2 < 30; c2 += 2) {
+                double s2[2] = {0.0, 0.0};
+#pragma unroll
+                for (int r = 0; r < 15; ++r) {
+                    const double2 v = *reinterpret_cast<const double2*>(sJh + r * 32 + c2);
+                    s2[0] += mine[r] * v.x;
+                    s2[1] += mine[r] * v.y;
+                }
+#pragma unroll
+                for (int q = 0; q < 2; ++q) {
+                    const int c = c2 + q;
+                    double s = s2[q];
+                    const int cf = c % 15;
+                    if (cf < 6) {
+                        const int cw = (c < 15 ? 0 : 6) + cf;
+                        s += w0 * sWh[cw] + w1 * sWh[16 + cw] + w2 * sWh[32 + cw];
+                        if (c >= 15) s += m * (jp * sGh[cf] + jq * sGh[8 + cf]);
+                    }
+                    if (c >= 15 && prior_lane && !col_const(mbv, cf)) {
+                        double ps = 0.0;
+                        for (int r = 0; r < 15; ++r) ps += sPJ[r * 15 + fl] * sPJ[r * 15 + cf];
+                        s += ps;
+                    }
+                    out[c * 30 + lane] = s;
+                }
+            }
+            out[kItemGa + lane] = gsum;
+        }
+        c_item = warp_sum(c_item);
+        if (lane == 31) out[kItemCost] = c_item;
+        __syncwarp();   // sP / sPJ are reused by the second item
+    }
 }
 
 // =====================================================================================================

@@ -296,3 +296,23 @@ def test_huber_and_in_kernel_association_match_oracle(oracle, case, huber, assoc
         # the loss must actually bite on the initial point of these cases
         P0 = L.corridor_params(max_iters=8)
         assert oracle.cost(P, hb)[0] < oracle.cost(P0, hb)[0]
+
+
+def test_paired_and_single_factor_kernels_agree(oracle, monkeypatch):
+    """factor_pair_kernel (two items per warp, 12 dual columns + 15 closed-form columns; the default) against factor_kernel
+    (one item per warp, all 30 columns in dual arithmetic): same normal equations, same solve."""
+    from lvio2d_b200.solver import Context
+
+    P = L.corridor_params(max_iters=10)
+    res = {}
+    for case in ("c2_small", "tracking2", "init"):
+        hb = oracle.preintegrate_batch(P, CASES[case]())
+        for paired in ("1", "0"):
+            monkeypatch.setenv("LVIO2D_FACTOR_PAIRED", paired)
+            with Context(P) as c:
+                c.set_windows(hb)
+                H, g, cost = c.linearize(0)
+                c.solve()
+                res[paired] = (H, g, cost, c.get_states())
+        for a, b in zip(res["1"], res["0"]):
+            relclose(a, b, 1e-12, case)
