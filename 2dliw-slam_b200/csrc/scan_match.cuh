@@ -190,8 +190,17 @@ __global__ void __launch_bounds__(256, REF_FREE ? 1 : 2) scan_match_kernel(ScanM
     const int nl = (int)(l1 - l0);
     {
         if constexpr (!REF_FREE) {
-            for (int l = lane; l < nl; l += 32) {
-                const double4 wl = a.wlines[l0 + l];
+            // a lane's lines are requested four at a time before any is consumed: the table build costs one DRAM round
+            // trip per 128 lines instead of one per 32
+            for (int lb = lane; lb < nl; lb += 128) {
+              double4 wl4[4];
+#pragma unroll
+              for (int q = 0; q < 4; ++q) wl4[q] = (lb + 32 * q < nl) ? a.wlines[l0 + lb + 32 * q] : make_double4(0.0, 0.0, 0.0, 0.0);
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                const int l = lb + 32 * q;
+                if (l >= nl) break;
+                const double4 wl = wl4[q];
                 double* r = tab + l * ROW;
                 r[0] = wl.x * T[0] + wl.y * T[2];
                 r[1] = wl.x * T[1] + wl.y * T[3];
@@ -212,6 +221,7 @@ __global__ void __launch_bounds__(256, REF_FREE ? 1 : 2) scan_match_kernel(ScanM
                     r[16] = ux * T[4] + uy * T[5] - wl.w;
                     r[17] = a.wlen[l0 + l];
                 }
+              }
             }
         } else {
             const int rf = a.ref_frame[f];
@@ -219,8 +229,15 @@ __global__ void __launch_bounds__(256, REF_FREE ? 1 : 2) scan_match_kernel(ScanM
             double Ti[kFrameTab];
 #pragma unroll
             for (int i = 0; i < kFrameTab; ++i) Ti[i] = __ldg(fi + i);
-            for (int l = lane; l < nl; l += 32) {
-                const double4 ln = a.lines[l0 + l];
+            for (int lb = lane; lb < nl; lb += 128) {
+              double4 ln4[4];
+#pragma unroll
+              for (int q = 0; q < 4; ++q) ln4[q] = (lb + 32 * q < nl) ? a.lines[l0 + lb + 32 * q] : make_double4(0.0, 0.0, 1.0, 0.0);
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                const int l = lb + 32 * q;
+                if (l >= nl) break;
+                const double4 ln = ln4[q];
                 const double A1x = Ti[0] * ln.x + Ti[1] * ln.y + Ti[4], A1y = Ti[2] * ln.x + Ti[3] * ln.y + Ti[5];
                 const double A2x = Ti[0] * ln.z + Ti[1] * ln.w + Ti[4], A2y = Ti[2] * ln.z + Ti[3] * ln.w + Ti[5];
                 const double dx = A2x - A1x, dy = A2y - A1y;
@@ -248,6 +265,7 @@ __global__ void __launch_bounds__(256, REF_FREE ? 1 : 2) scan_match_kernel(ScanM
                 r[12] = nx;
                 r[13] = ny;
                 r[23] = len;
+              }
             }
         }
     }
