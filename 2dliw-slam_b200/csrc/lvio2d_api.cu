@@ -74,6 +74,7 @@ struct lvio2d_ctx {
     bool arrow = false, has_weight = false, has_imu = false, has_wheel = false;
     int64_t N = 0, L = 0;
     int tiles = 1, line_cap = 1, npad = kPadTrack;
+    int uniform_pts = 0, uniform_lines = 0;   // > 0: all frames have this many points / lines (scan-match fast prologue)
     int shard_rank = 0, shard_world = 1;
     // inputs (owned copies, or borrowed device pointers when bound)
     DevBuf b_points, b_pline, b_pweight, b_poff, b_loff, b_lines, b_ref, b_refpose, b_imu, b_wheel, b_pX0, b_pJ, b_cmask;
@@ -175,6 +176,7 @@ int launch_scan_match(lvio2d_ctx* ctx, int mode = 0) {
     a.win_status = ctx->b_status.as<int32_t>(); a.partial = ctx->b_part.as<double>();
     a.n_frames = ctx->n; a.tiles = ctx->tiles; a.n_items = ctx->B * ctx->n * ctx->tiles;
     a.line_cap = ctx->line_cap; a.shard_rank = ctx->shard_rank; a.shard_world = ctx->shard_world;
+    a.uniform_pts = ctx->uniform_pts; a.uniform_lines = ctx->uniform_lines;
     a.huber_delta = ctx->huber; a.laser_sqrt_info = ctx->C.laser_sqrt_info;
     a.assoc_gate = ctx->params.assoc_gate > 0 ? ctx->params.assoc_gate : 0.1;
     a.assoc_max_dist = ctx->params.assoc_max_dist > 0 ? ctx->params.assoc_max_dist : 0.5;
@@ -351,6 +353,17 @@ int setup_batch(lvio2d_ctx* ctx, const lvio2d_window_batch* b, bool bind, bool a
         active[f] = act ? 1 : 0;
     }
     if (line_cap > 512) return fail(ctx, LVIO2D_ERR_DOMAIN, "more than 512 lines in one local map");
+    {
+        // fixed-size scans: offsets are arithmetic, the scan-match prologue needs no dependent offset loads
+        bool up = has_laser && F > 0 && poff[0] == 0, ul = has_laser && F > 0 && loff[0] == 0;
+        const int64_t P0 = up ? poff[1] - poff[0] : 0, L0 = ul ? loff[1] - loff[0] : 0;
+        for (int f = 0; f < F && (up || ul); ++f) {
+            up = up && poff[f + 1] - poff[f] == P0;
+            ul = ul && loff[f + 1] - loff[f] == L0;
+        }
+        ctx->uniform_pts = (up && P0 > 0 && P0 < (1 << 30)) ? (int)P0 : 0;
+        ctx->uniform_lines = (ul && L0 > 0 && L0 < (1 << 30)) ? (int)L0 : 0;
+    }
     ctx->arrow = arrow;
     ctx->line_cap = line_cap;
     ctx->npad = arrow ? kPadFree : kPadTrack;
