@@ -181,7 +181,7 @@ int launch_scan_match(lvio2d_ctx* ctx, int mode = 0) {
     a.assoc_gate = ctx->params.assoc_gate > 0 ? ctx->params.assoc_gate : 0.1;
     a.assoc_max_dist = ctx->params.assoc_max_dist > 0 ? ctx->params.assoc_max_dist : 0.5;
     if (ctx->N == 0) return LVIO2D_OK;
-    const int wpc = 8;
+    const int wpc = LV_SCAN_WPC;
     const int grid = (a.n_items + wpc - 1) / wpc;
     const bool assoc = ctx->params.assoc_mode == LVIO2D_ASSOC_NEAREST;
     const bool huber = ctx->huber > 0;
@@ -223,7 +223,7 @@ WindowArgs window_args(lvio2d_ctx* ctx, int mode) {
 }
 
 int launch_factors(lvio2d_ctx* ctx, const WindowArgs& a) {
-    const int wpc = 4;
+    const int wpc = ctx->factor_paired ? LV_PAIR_WPC : 4;
     const int items = ctx->B * ctx->n;
     if (ctx->profiling) cudaEventRecord(next_event(ctx->ev_fac, ctx->ev_fac_used), ctx->stream);
     ctx->launches += 1;
@@ -257,7 +257,7 @@ int launch_window(lvio2d_ctx* ctx, const WindowArgs& a) {
         window_kernel<AR, NT><<<GRID, BLOCK, SMEM, ctx->stream>>>(a, per_window);                                             \
     } while (0)
     if (nt == 32) {
-        const int wpc = 2;
+        const int wpc = LV_WINDOW_WPC;
         const size_t smem = (size_t)wpc * per_window * sizeof(double);
         const int grid = (ctx->B + wpc - 1) / wpc;
         if (ctx->arrow) LAUNCH_WIN(true, 32, grid, wpc * 32, smem); else LAUNCH_WIN(false, 32, grid, wpc * 32, smem);
@@ -375,7 +375,7 @@ int setup_batch(lvio2d_ctx* ctx, const lvio2d_window_batch* b, bool bind, bool a
         tiles = (int)std::max<int64_t>(1, std::min<int64_t>(tiles, avg / 64));
         ctx->tiles = tiles;
     }
-    const size_t smem_scan = (size_t)8 * line_cap * scan_row(arrow, ctx->params.assoc_mode == LVIO2D_ASSOC_NEAREST) * sizeof(double);
+    const size_t smem_scan = (size_t)LV_SCAN_WPC * line_cap * scan_row(arrow, ctx->params.assoc_mode == LVIO2D_ASSOC_NEAREST) * sizeof(double);
     if (smem_scan > 200 * 1024) return fail(ctx, LVIO2D_ERR_DOMAIN, "local map too large for shared memory");
     if (window_smem_bytes(ctx) > 200 * 1024) return fail(ctx, LVIO2D_ERR_DOMAIN, "n_frames too large for shared memory");
 

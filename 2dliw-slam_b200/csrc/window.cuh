@@ -40,6 +40,12 @@
 #ifndef LV_PAIR_MINB
 #define LV_PAIR_MINB 3     // resident CTAs per SM the register budget of factor_pair_kernel is sized for
 #endif
+#ifndef LV_WINDOW_WPC
+#define LV_WINDOW_WPC 2    // windows (warps) per CTA of the one-warp-per-window shape
+#endif
+#ifndef LV_PAIR_WPC
+#define LV_PAIR_WPC 4      // warps (item pairs) per CTA of factor_pair_kernel
+#endif
 #ifndef LV_FACTOR_ROLL
 #define LV_FACTOR_ROLL 1   // 1: keep the column loop of the J^T J product rolled (smaller instruction footprint)
 #endif
@@ -324,7 +330,7 @@ __global__ void __launch_bounds__(128, LV_FACTOR_MINB) factor_kernel(WindowArgs 
 // residual 16 + prior J 240.
 constexpr int kPairHalf = 480 + 480 + 48 + 16 + 16;
 constexpr int kPairSmem = 2 * kPairHalf + 16 + 240;
-__global__ void __launch_bounds__(128, LV_PAIR_MINB) factor_pair_kernel(WindowArgs a) {
+__global__ void __launch_bounds__(32 * LV_PAIR_WPC, LV_PAIR_MINB * 4 / LV_PAIR_WPC) factor_pair_kernel(WindowArgs a) {
     extern __shared__ __align__(16) double smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int h = lane >> 4, sl = lane & 15;
@@ -1257,7 +1263,7 @@ __device__ void window_step(const WindowArgs& a, int w, int lane, double* ws) {
 }
 
 template <bool ARROW, int NT>
-__global__ void __launch_bounds__(NT == 32 ? 64 : NT, NT == 32 ? 8 : 512 / NT) window_kernel(WindowArgs a, int per_window_doubles) {
+__global__ void __launch_bounds__(NT == 32 ? 32 * LV_WINDOW_WPC : NT, NT == 32 ? 16 / LV_WINDOW_WPC : 512 / NT) window_kernel(WindowArgs a, int per_window_doubles) {
     extern __shared__ __align__(16) double smem[];
     if (NT == 32) {
         // batched shape: one warp per window, two windows per CTA
