@@ -92,6 +92,7 @@ struct lvio2d_ctx {
     int step_calls = 0;
     int window_threads = 0;   // 0 = automatic
     bool factor_paired = true; // LVIO2D_FACTOR_PAIRED=0 selects the one-item-per-warp factor kernel
+    bool fused_small = true;   // LVIO2D_FUSED_SMALL=0: batches of <= #SM windows also go through the three-kernel loop
     bool have_solution = false;
     // host staging of the small index arrays (kept alive until the next upload so that copies can stay asynchronous)
     PinnedVec<int64_t> h_poff, h_loff;
@@ -167,19 +168,10 @@ int scan_row(bool arrow, bool assoc) { return arrow ? kRowFree : (assoc ? kRowTr
 
 size_t window_smem_bytes(const lvio2d_ctx* c) { return window_smem_doubles(c->n, c->arrow) * sizeof(double); }
 
+ScanMatchArgs scan_args(lvio2d_ctx* ctx, int mode);
+
 int launch_scan_match(lvio2d_ctx* ctx, int mode = 0) {
-    ScanMatchArgs a;
-    a.points = ctx->points; a.point_line = ctx->point_line; a.point_weight = ctx->point_weight;
-    a.point_offset = ctx->point_offset; a.line_offset = ctx->line_offset;
-    a.wlines = ctx->b_wlines.as<double4>(); a.wlen = ctx->b_wlen.as<double>(); a.lines = ctx->lines; a.ref_frame = ctx->ref_frame;
-    a.frame_tab = ctx->b_ftab.as<double>(); a.frame_active = (mode == 1 ? ctx->b_active1 : ctx->b_active).as<uint8_t>();
-    a.win_status = ctx->b_status.as<int32_t>(); a.partial = ctx->b_part.as<double>();
-    a.n_frames = ctx->n; a.tiles = ctx->tiles; a.n_items = ctx->B * ctx->n * ctx->tiles;
-    a.line_cap = ctx->line_cap; a.shard_rank = ctx->shard_rank; a.shard_world = ctx->shard_world;
-    a.uniform_pts = ctx->uniform_pts; a.uniform_lines = ctx->uniform_lines;
-    a.huber_delta = ctx->huber; a.laser_sqrt_info = ctx->C.laser_sqrt_info;
-    a.assoc_gate = ctx->params.assoc_gate > 0 ? ctx->params.assoc_gate : 0.1;
-    a.assoc_max_dist = ctx->params.assoc_max_dist > 0 ? ctx->params.assoc_max_dist : 0.5;
+    ScanMatchArgs a = scan_args(ctx, mode);
     if (ctx->N == 0) return LVIO2D_OK;
     const int wpc = LV_SCAN_WPC;
     const int grid = (a.n_items + wpc - 1) / wpc;
@@ -203,6 +195,22 @@ int launch_scan_match(lvio2d_ctx* ctx, int mode = 0) {
     ctx->launches += 1;
     CK(cudaGetLastError());
     return LVIO2D_OK;
+}
+
+ScanMatchArgs scan_args(lvio2d_ctx* ctx, int mode) {
+    ScanMatchArgs a;
+    a.points = ctx->points; a.point_line = ctx->point_line; a.point_weight = ctx->point_weight;
+    a.point_offset = ctx->point_offset; a.line_offset = ctx->line_offset;
+    a.wlines = ctx->b_wlines.as<double4>(); a.wlen = ctx->b_wlen.as<double>(); a.lines = ctx->lines; a.ref_frame = ctx->ref_frame;
+    a.frame_tab = ctx->b_ftab.as<double>(); a.frame_active = (mode == 1 ? ctx->b_active1 : ctx->b_active).as<uint8_t>();
+    a.win_status = ctx->b_status.as<int32_t>(); a.partial = ctx->b_part.as<double>();
+    a.n_frames = ctx->n; a.tiles = ctx->tiles; a.n_items = ctx->B * ctx->n * ctx->tiles;
+    a.line_cap = ctx->line_cap; a.shard_rank = ctx->shard_rank; a.shard_world = ctx->shard_world;
+    a.uniform_pts = ctx->uniform_pts; a.uniform_lines = ctx->uniform_lines;
+    a.huber_delta = ctx->huber; a.laser_sqrt_info = ctx->C.laser_sqrt_info;
+    a.assoc_gate = ctx->params.assoc_gate > 0 ? ctx->params.assoc_gate : 0.1;
+    a.assoc_max_dist = ctx->params.assoc_max_dist > 0 ? ctx->params.assoc_max_dist : 0.5;
+    return a;
 }
 
 WindowArgs window_args(lvio2d_ctx* ctx, int mode) {
@@ -481,6 +489,7 @@ int lvio2d_create(lvio2d_ctx** out, const lvio2d_params* params) {
     }
     if (const char* wt = std::getenv("LVIO2D_WINDOW_THREADS")) ctx->window_threads = std::atoi(wt);
     if (const char* fp = std::getenv("LVIO2D_FACTOR_PAIRED")) ctx->factor_paired = std::atoi(fp) != 0;
+    if (const char* fs = std::getenv("LVIO2D_FUSED_SMALL")) ctx->fused_small = std::atoi(fs) != 0;
     *out = ctx;
     return LVIO2D_OK;
 }
@@ -620,6 +629,29 @@ int lvio2d_solve_async(lvio2d_ctx* ctx) {
     int rc = begin_solve(ctx);
     if (rc) return rc;
     WindowArgs a = window_args(ctx, 0);
+    // small batches: the whole loop in one launch, one CTA per window (solve_small_kernel)
+    {
+        const bool assoc = ctx->params.assoc_mode == LVIO2D_ASSOC_NEAREST;
+        const size_t smem = std::max({(size_t)8 * ctx->line_cap * scan_row(ctx->arrow, false) * sizeof(double), (size_t)8 * kPairSmem * sizeof(double),
+                                      window_smem_bytes(ctx)});
+        if (ctx->fused_small && ctx->B <= ctx->sm_count && !assoc && !(ctx->huber > 0) && ctx->shard_world == 1 && !ctx->profiling &&
+            smem <= 200 * 1024) {
+            const ScanMatchArgs sa = scan_args(ctx, 0);
+            const int trips = ctx->opt.max_iters + 1;
+#define LAUNCH_SMALL(AR, HW)                                                                                            \
+    do {                                                                                                                \
+        CK(cudaFuncSetAttribute(solve_small_kernel<AR, HW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   \
+        solve_small_kernel<AR, HW><<<ctx->B, 256, smem, ctx->stream>>>(sa, a, trips);                                   \
+    } while (0)
+            if (ctx->arrow) { if (ctx->has_weight) LAUNCH_SMALL(true, true); else LAUNCH_SMALL(true, false); }
+            else { if (ctx->has_weight) LAUNCH_SMALL(false, true); else LAUNCH_SMALL(false, false); }
+#undef LAUNCH_SMALL
+            ctx->launches += 1;
+            CK(cudaGetLastError());
+            ctx->have_solution = true;
+            return LVIO2D_OK;
+        }
+    }
     // trip 0 linearises the initial point; trips 1..max_iters each judge one candidate
     for (int it = 0; it <= ctx->opt.max_iters; ++it) {
         if ((rc = launch_scan_match(ctx))) return rc;

@@ -138,16 +138,12 @@ struct ReduceScatter<N, 0> {
 // number of values a lane holds after 5 halvings of N
 __host__ __device__ constexpr int halved5(int n) { for (int i = 0; i < 5; ++i) n = (n + 1) / 2; return n; }
 
+// one (frame, tile) item on one warp; `tab` = this warp's line table in shared memory (line_cap rows)
 template <bool REF_FREE, bool HAS_WEIGHT, bool ASSOC, bool HUBER>
-__global__ void __launch_bounds__(32 * LV_SCAN_WPC, (REF_FREE ? 8 : LV_SCAN_WARPS_PER_SM) / LV_SCAN_WPC) scan_match_kernel(ScanMatchArgs a) {
+__device__ __forceinline__ void scan_match_item(const ScanMatchArgs& a, const int item, const int lane, double* tab) {
     constexpr int NACC = REF_FREE ? kAccFree : kAccTrack;
     constexpr int NPAD = REF_FREE ? kPadFree : kPadTrack;
     constexpr int ROW = REF_FREE ? kRowFree : (ASSOC ? kRowTrackAssoc : kRowTrack);
-    extern __shared__ __align__(16) double smem[];
-    const int lane = threadIdx.x & 31;
-    const int warp = threadIdx.x >> 5;
-    const int item = blockIdx.x * (blockDim.x >> 5) + warp;
-    if (item >= a.n_items) return;
     const int f = item / a.tiles;
     const int tile = item - f * a.tiles;
     // Prologue.  Ragged batches: every scalar this warp depends on is requested before the first one is tested, so the
@@ -178,7 +174,6 @@ __global__ void __launch_bounds__(32 * LV_SCAN_WPC, (REF_FREE ? 8 : LV_SCAN_WARP
     if (!uni) {
         if ((wstat != 0) | (fact == 0) | (p1 <= p0) | (l1 < l0)) return;   // (one test on all six: ptxas keeps the loads together)
     }
-    double* tab = smem + (size_t)warp * a.line_cap * ROW;
 
     // ---- this warp's slice of the frame: rank shard, then tile
     const int64_t cnt = p1 - p0;
@@ -428,6 +423,17 @@ __global__ void __launch_bounds__(32 * LV_SCAN_WPC, (REF_FREE ? 8 : LV_SCAN_WARP
 #pragma unroll
     for (int i = 0; i < OUTN; ++i)
         if (i < len) out[base + i] = acc[i];
+}
+
+template <bool REF_FREE, bool HAS_WEIGHT, bool ASSOC, bool HUBER>
+__global__ void __launch_bounds__(32 * LV_SCAN_WPC, (REF_FREE ? 8 : LV_SCAN_WARPS_PER_SM) / LV_SCAN_WPC) scan_match_kernel(ScanMatchArgs a) {
+    constexpr int ROW = REF_FREE ? kRowFree : (ASSOC ? kRowTrackAssoc : kRowTrack);
+    extern __shared__ __align__(16) double smem[];
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int item = blockIdx.x * (blockDim.x >> 5) + warp;
+    if (item >= a.n_items) return;
+    scan_match_item<REF_FREE, HAS_WEIGHT, ASSOC, HUBER>(a, item, lane, smem + (size_t)warp * a.line_cap * ROW);
 }
 
 // world lines for frames whose local map hangs under an external constant reference pose: computed once per

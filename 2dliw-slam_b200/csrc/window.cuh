@@ -330,19 +330,16 @@ __global__ void __launch_bounds__(128, LV_FACTOR_MINB) factor_kernel(WindowArgs 
 // residual 16 + prior J 240.
 constexpr int kPairHalf = 480 + 480 + 48 + 16 + 16;
 constexpr int kPairSmem = 2 * kPairHalf + 16 + 240;
-__global__ void __launch_bounds__(32 * LV_PAIR_WPC, LV_PAIR_MINB * 4 / LV_PAIR_WPC) factor_pair_kernel(WindowArgs a) {
-    extern __shared__ __align__(16) double smem[];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+// items `first` and `first + 1` (the second only when count == 2) on one warp; `base` = kPairSmem doubles of shared memory
+__device__ __forceinline__ void factor_pair_item(const WindowArgs& a, const int first, const int count, const int lane, double* base) {
     const int h = lane >> 4, sl = lane & 15;
     const int n = a.n_frames, total = a.n_windows * n;
-    const int pair = blockIdx.x * (blockDim.x >> 5) + warp;
-    const int item = 2 * pair + h;
+    const int item = first + h;
     int w = 0, i = 0;
-    bool live = item < total;
+    bool live = h < count && item < total;
     if (live) { w = item / n; i = item - w * n; live = a.win_status[w] == 0; }
     if (!__any_sync(0xffffffffu, live)) return;
     const int mode = a.mode;
-    double* base = smem + (size_t)warp * kPairSmem;
     double* sblob = base + h * kPairHalf;
     double* sJ = sblob + 480;   // whitened IMU Jacobian [15][32]; column 30 = whitened residual
     double* sW = sJ + 480;      // wheel [3][16]: cols 0..11 Jacobian, col 12 residual
@@ -561,6 +558,13 @@ __global__ void __launch_bounds__(32 * LV_PAIR_WPC, LV_PAIR_MINB * 4 / LV_PAIR_W
         if (lane == 31) out[kItemCost] = c_item;
         __syncwarp();   // sP / sPJ are reused by the second item
     }
+}
+
+__global__ void __launch_bounds__(32 * LV_PAIR_WPC, LV_PAIR_MINB * 4 / LV_PAIR_WPC) factor_pair_kernel(WindowArgs a) {
+    extern __shared__ __align__(16) double smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int pair = blockIdx.x * (blockDim.x >> 5) + warp;
+    factor_pair_item(a, 2 * pair, 2, lane, smem + (size_t)warp * kPairSmem);
 }
 
 // =====================================================================================================
@@ -1275,6 +1279,33 @@ __global__ void __launch_bounds__(NT == 32 ? 32 * LV_WINDOW_WPC : NT, NT == 32 ?
     } else {
         // small batches: one CTA of NT threads per window
         window_step<ARROW, NT>(a, blockIdx.x, threadIdx.x, smem);
+    }
+}
+
+// =====================================================================================================
+// solve_small_kernel: the WHOLE minimiser loop of a small batch in one launch, one CTA of 8 warps per window.
+// The reference's steady-state problem is tiny (2 frames, a few matched segment pairs, up to 50 iterations): launched
+// as three kernels per trip it is bound by ~150 launch + drain latencies.  Here a trip is scan-match items (a warp per
+// frame), factor item pairs (a warp per pair), the window step on all 256 threads, separated by __syncthreads(); the
+// three phases alias the same shared memory.  Same device functions, same arithmetic as the batched kernels.
+template <bool ARROW, bool HAS_WEIGHT>
+__global__ void __launch_bounds__(256, 1) solve_small_kernel(ScanMatchArgs sa, WindowArgs wa, int trips) {
+    extern __shared__ __align__(16) double smem[];
+    constexpr int ROW = ARROW ? kRowFree : kRowTrack;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int w = blockIdx.x;
+    const int n = wa.n_frames;
+    for (int trip = 0; trip < trips; ++trip) {
+        if (wa.win_status[w] != 0) break;                       // uniform: written before the last __syncthreads()
+        if (sa.points)
+            for (int k = warp; k < n * sa.tiles; k += 8)
+                scan_match_item<ARROW, HAS_WEIGHT, false, false>(sa, w * n * sa.tiles + k, lane, smem + (size_t)warp * sa.line_cap * ROW);
+        __syncthreads();                                        // the factor phase reuses the line-table memory
+        for (int k = 2 * warp; k < n; k += 16)
+            factor_pair_item(wa, w * n + k, (k + 1 < n) ? 2 : 1, lane, smem + (size_t)warp * kPairSmem);
+        __syncthreads();                                        // partials and items are complete (block-visible)
+        window_step<ARROW, 256>(wa, w, tid, smem);
+        __syncthreads();
     }
 }
 

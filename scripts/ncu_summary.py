@@ -81,7 +81,7 @@ def main():
     lines += ["", "Launches of the headline batch only (each kernel's largest grid; the list above also holds the small-batch launches of",
               "the end-to-end chunks and of the single-window probe):", "", "| kernel | launches | total ms | avg us | share |", "|---|---:|---:|---:|---:|"]
     agg = launches(lcsv, full_size_only=True)
-    main = {k: v for k, v in agg.items() if any(t in k for t in ("scan_match", "factor_kernel", "window_kernel"))}
+    main = {k: v for k, v in agg.items() if any(t in k for t in ("scan_match", "factor_pair", "factor_kernel")) or ("window_kernel" in k and ", 32>" in k)}
     tot = sum(a[1] for a in main.values())
     for k, (c, t) in main.items():
         lines.append(f"| `{k}` | {c} | {t / 1e6:.3f} | {t / c / 1e3:.1f} | {t / tot * 100:.1f}% |")
