@@ -170,7 +170,7 @@ __device__ __forceinline__ void scan_match_item(const ScanMatchArgs& a, const in
     double T[kFrameTab];
 #pragma unroll
     for (int i = 0; i < kFrameTab; i += 2)
-        asm volatile("ld.global.nc.v2.f64 {%0, %1}, [%2];" : "=d"(T[i]), "=d"(T[i + 1]) : "l"(ft + i));
+        asm volatile("ld.global.v2.f64 {%0, %1}, [%2];" : "=d"(T[i]), "=d"(T[i + 1]) : "l"(ft + i));   // coherent: solve_small_kernel rewrites frame_tab between trips
     if (!uni) {
         if ((wstat != 0) | (fact == 0) | (p1 <= p0) | (l1 < l0)) return;   // (one test on all six: ptxas keeps the loads together)
     }
@@ -260,7 +260,7 @@ __device__ __forceinline__ void scan_match_item(const ScanMatchArgs& a, const in
             const double* fi = a.frame_tab + ((size_t)(f - f % a.n_frames) + rf) * kFrameTab;
             double Ti[kFrameTab];
 #pragma unroll
-            for (int i = 0; i < kFrameTab; ++i) Ti[i] = __ldg(fi + i);
+            for (int i = 0; i < kFrameTab; ++i) Ti[i] = fi[i];   // (plain load: frame_tab is rewritten between the trips of solve_small_kernel)
             for (int lb = lane; lb < nl; lb += 128) {
               double4 ln4[4];
 #pragma unroll

@@ -316,3 +316,23 @@ def test_paired_and_single_factor_kernels_agree(oracle, monkeypatch):
                 res[paired] = (H, g, cost, c.get_states())
         for a, b in zip(res["1"], res["0"]):
             relclose(a, b, 1e-12, case)
+
+
+def test_fused_small_solve_matches_three_kernel_loop(oracle, monkeypatch):
+    """solve_small_kernel (whole minimiser loop in one launch, the default for batches of small windows) against the
+    three-kernel loop on the reference's own problem shapes: identical iteration counts and states to 1e-12."""
+    from lvio2d_b200.solver import Context
+
+    for case, iters in (("tracking2", 20), ("init", 20), ("c2_small", 10)):
+        P = L.corridor_params(max_iters=iters)
+        hb = oracle.preintegrate_batch(P, CASES[case]())
+        res = {}
+        for fused in ("1", "0"):
+            monkeypatch.setenv("LVIO2D_FUSED_SMALL", fused)
+            with Context(P) as c:
+                c.set_windows(hb)
+                summ = c.solve()
+                res[fused] = (summ["iterations"].copy(), summ["final_cost"].copy(), c.get_states())
+        assert np.array_equal(res["1"][0], res["0"][0]), case
+        relclose(res["1"][1], res["0"][1], 1e-12, case + " cost")
+        relclose(res["1"][2], res["0"][2], 1e-12, case + " states")
