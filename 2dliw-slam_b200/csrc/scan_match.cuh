@@ -16,8 +16,9 @@
 // need the sign.  Per line the 12 coefficients (f, e_0, e_1, e_2) + n are staged in shared memory once
 // per (frame, tile); per point the kernel does 8 FMAs for (d, j_theta) and 21 for the accumulation.
 //
-// Work decomposition: one warp per (frame, tile).  Points of a frame are contiguous, so a warp reads
-// 512 B (32 x double2) + 128 B (32 x int32) fully coalesced per step; loads bypass L1 (read once).
+// Work decomposition: one warp per (frame, tile), one warp per CTA (finest scheduling granularity, see LV_SCAN_WPC).
+// Points of a frame are contiguous, so a warp reads 512 B (32 x double2) + 128 B (32 x int32) fully coalesced per
+// step; loads bypass L1 (read once).  Prologue: one DRAM round trip for fixed-size scans, two for ragged batches.
 // Reduction: per-lane register accumulators -> recursive-halving warp shuffle (23 exchanges for 21 values
 // instead of 105) -> one 8-byte store per value.  No atomics; results are bit-reproducible.
 #pragma once

@@ -1,9 +1,12 @@
 // window.cuh — everything of an LM iteration that is NOT the scan-point pass, as two kernels:
 //
-//   factor_kernel  one warp per (window, frame i): the residual blocks hanging on frame i — IMU and wheel factor of
-//                  the pair (i-1, i), `multiplicity` ground factors and the marginalisation prior of frame i —
-//                  evaluated AT THE CANDIDATE point: whitened Jacobians, J^T J blocks, J^T r, r^2.
-//   window_kernel  one warp per window: Ceres' minimiser logic + the linear solve.
+//   factor_pair_kernel  the residual blocks hanging on frame i of a window — IMU and wheel factor of the pair (i-1, i),
+//                  `multiplicity` ground factors and the marginalisation prior of frame i — evaluated AT THE CANDIDATE
+//                  point: whitened Jacobians, J^T J blocks, J^T r, r^2.  Two items per warp (12 dual columns + 15
+//                  closed-form columns each); factor_kernel is the one-item-per-warp, all-dual variant kept for A/B.
+//   window_kernel  Ceres' minimiser logic + the linear solve; one warp per window for large batches, four or eight warps
+//                  per window (template parameter NT) for small ones.
+//   solve_small_kernel  the whole loop (scan-match items, factor pairs, window step) in one launch for tiny windows.
 //
 // Together they replace ceres::Solve as configured by solver::solve / solver::do_init_solve (reference
 // src/factor/solver.cpp:795-802, :161-168) — Ceres 1.14 TrustRegionMinimizer + LevenbergMarquardtStrategy with Jacobi
@@ -12,7 +15,7 @@
 // `multiplicity` times, solver.cpp:727-743), marginalization_factor (marginalization_factor.h:22-53) under the
 // constness rules of solver.cpp:787-794.
 //
-// One trip of the minimiser loop = scan_match_kernel + factor_kernel (both at the candidate, independent of each
+// One trip of the minimiser loop = scan_match_kernel + factor_pair_kernel (both at the candidate, independent of each
 // other) followed by window_kernel:
 //   (1) candidate cost = laser tiles + factor items; Ceres' parameter-/function-tolerance tests, then the
 //       step-quality test rho > 1e-3; accept (flip the per-window buffer parity) or reject; trust-region update;
