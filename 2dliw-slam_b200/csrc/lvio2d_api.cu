@@ -991,7 +991,8 @@ int lvio2d_match_lines(lvio2d_ctx* ctx, const lvio2d_line_params* lp, int32_t n_
     }
     DevBuf* B = ctx->b_ml;
     const size_t nn = (size_t)std::max<int64_t>(N1, 1);
-    bool ok = B[0].ensure(nn * sizeof(int32_t)) && B[1].ensure(P * max_lines2 * sizeof(double)) && B[2].ensure(P * max_lines2 * 2 * sizeof(int32_t));
+    bool ok = B[0].ensure(nn * sizeof(int32_t)) && B[1].ensure(P * max_lines2 * sizeof(double)) && B[2].ensure(P * max_lines2 * 2 * sizeof(int32_t)) &&
+              B[15].ensure(P * max_lines1 * 4 * sizeof(int32_t));
     if (!on_device)
         ok = ok && B[3].ensure((P + 1) * sizeof(int64_t)) && B[4].ensure(P * sizeof(int32_t)) && B[5].ensure(nn * sizeof(double2)) &&
              B[6].ensure(P * sizeof(int32_t)) && B[7].ensure(P * max_lines1 * sizeof(double4)) && B[8].ensure(P * max_lines1 * 2 * sizeof(int32_t)) &&
@@ -1005,7 +1006,7 @@ int lvio2d_match_lines(lvio2d_ctx* ctx, const lvio2d_line_params* lp, int32_t n_
     a.resolution = lp->laser_resolution;
     a.w = (int)(lp->w_laser_each_scan / lp->laser_resolution + 1);
     a.h = (int)(lp->h_laser_each_scan / lp->laser_resolution + 1);
-    a.cells = B[0].as<int32_t>(); a.diss = B[1].as<double>(); a.prov = B[2].as<int32_t>();
+    a.cells = B[0].as<int32_t>(); a.diss = B[1].as<double>(); a.prov = B[2].as<int32_t>(); a.bbox = B[15].as<int32_t>();
     if (on_device) {
         a.point_offset1 = point_offset1; a.point_count1 = point_count1; a.points1 = reinterpret_cast<const double2*>(points1);
         a.n_lines1 = n_lines1; a.lines1 = reinterpret_cast<const double4*>(lines1); a.index_range1 = index_range1;

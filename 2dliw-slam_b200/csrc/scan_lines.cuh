@@ -402,6 +402,7 @@ struct MatchLinesArgs {
     int32_t n_pairs, kk, w, h;
     double resolution;
     int32_t* cells;     // workspace [N1]: r << 16 | c of every scan-1 point, -1 when off the grid
+    int32_t* bbox;      // workspace [P][max_lines1][4]: (rmin, rmax, cmin, cmax) of the cells every scan-1 line covers
     double* diss;       // workspace [P][max_lines2]
     int32_t* prov;      // workspace [P][max_lines2][2]: pairs before the distance filter
     int32_t* n_match;   // [P]
@@ -453,6 +454,28 @@ __global__ void __launch_bounds__(128) match_lines_kernel(MatchLinesArgs a) {
         for (int i = lane; i < np; i += 32) { const double2 q = a.points1[q0 + i]; a.cells[q0 + i] = match_cell(a, q.x, q.y); }
         __syncwarp();
     }
+    // bounding box of every scan-1 line's cells: a line whose box misses the neighbourhood cannot cover any of its cells,
+    // which prunes almost every (line of scan 2, line of scan 1) pair with four comparisons
+    int32_t* bb = a.bbox + (size_t)p * a.max_lines1 * 4;
+    for (int j = lane; j < n1; j += 32) {
+        int rmin = 0x7fffffff, rmax = -1, cmin = 0x7fffffff, cmax = -1;
+        auto grow = [&](int cell) {
+            if (cell < 0) return;
+            const int r = cell >> 16, c = cell & 0xffff;
+            rmin = min(rmin, r); rmax = max(rmax, r); cmin = min(cmin, c); cmax = max(cmax, c);
+        };
+        if (a.points1) {
+            for (int q = R1[2 * j]; q <= R1[2 * j + 1]; ++q) grow(a.cells[q0 + q]);
+        } else {
+            const double4 l1 = L1[j];
+            const double dx = l1.z - l1.x, dy = l1.w - l1.y, len = sqrt(dx * dx + dy * dy);
+            double ux = dx, uy = dy;
+            if (len * len > 0.0) { ux /= len; uy /= len; }
+            for (double tr = 0; tr <= len; tr += 0.05) grow(match_cell(a, l1.x + ux * tr, l1.y + uy * tr));
+        }
+        bb[4 * j] = rmin; bb[4 * j + 1] = rmax; bb[4 * j + 2] = cmin; bb[4 * j + 3] = cmax;
+    }
+    __syncwarp();
     const int aa = 1 + a.kk, side = 2 * aa + 1;
     int count = 0;
     for (int i = 0; i < n2; ++i) {
@@ -465,6 +488,7 @@ __global__ void __launch_bounds__(128) match_lines_kernel(MatchLinesArgs a) {
         double best_angle = 1e300;
         int best_cell = 64, best_j = 0x7fffffff;
         for (int j = lane; j < n1; j += 32) {
+            if (bb[4 * j + 1] < r - aa || bb[4 * j] > r + aa || bb[4 * j + 3] < c - aa || bb[4 * j + 2] > c + aa) continue;
             unsigned long long mask = 0ull;
             auto cover = [&](int cell) {
                 if (cell < 0) return;

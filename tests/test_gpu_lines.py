@@ -216,3 +216,25 @@ def test_front_end_chain_feeds_the_solver(oracle, lp):
                lambda: Solver(P, fast_mode=True, ctx=oracle.OracleContext(P)))
     assert np.abs(got - want).max() < 1e-6
     assert np.abs(got - sb.truth[1::2, :6]).max() < np.abs(sb.states[1::2, :6] - sb.truth[1::2, :6]).max()
+
+
+def test_front_end_error_paths(ctx, lp):
+    """Invalid arguments come back as negative status codes (Lvio2dError), never as a crash or a silent fallback."""
+    from lvio2d_b200 import abi
+    from lvio2d_b200.solver import Lvio2dError
+
+    off, pts = L.synth.make_scan_batch(2, 1, beams=64)
+    with pytest.raises(Lvio2dError):
+        ctx.extract_lines(lp, off[::-1].copy(), pts)                          # decreasing offsets
+    bad = L.corridor_line_params(laser_resolution=0.0)
+    with pytest.raises(Lvio2dError):
+        ctx.extract_lines(bad, off, pts)
+    n, lines, _, rng = ctx.extract_lines(lp, off, pts)
+    pose = np.zeros((2, 6))
+    with pytest.raises(Lvio2dError):
+        ctx.match_lines(lp, n, lines, n, lines, pose, pose, kk=5)             # neighbourhood larger than the 64-bit cell mask
+    with pytest.raises(Lvio2dError):
+        ctx.match_lines(bad, n, lines, n, lines, pose, pose)
+    # zero scans / zero pairs are no-ops
+    n0, _, _, _ = ctx.extract_lines(lp, np.zeros(1, np.int64), np.zeros((0, 2)))
+    assert len(n0) == 0
