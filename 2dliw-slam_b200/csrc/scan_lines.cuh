@@ -13,7 +13,7 @@
 //       +-3 window cannot lie within 3 of each other), so the flags are exact without the sequential walk
 //   (D) candidate list        [segment start, maxima..., segment end] per segment, by ordered warp compaction
 //   (E) tolerance-angle merge sequential per segment (loop-carried `last_end_index`): one lane per segment
-//   (F) fit + filters         warp-cooperative per line: moments of [x y 1] -> smallest eigenvector of the 3x3 Gram
+//   (F) fit + filters         one lane per candidate line: moments of [x y 1] -> smallest eigenvector of the 3x3 Gram
 //       matrix by cyclic Jacobi (= V.col(2) of the reference's JacobiSVD), max distance, projections, length, grid test
 // Bound: fp64 ALU / latency (sqrt, div, acos per point); 16 B in and < 1 B out per point, far below the HBM roofline.
 #pragma once
@@ -217,29 +217,24 @@ __global__ void __launch_bounds__(128) scan_lines_kernel(ScanLinesArgs a) {
     }
     __syncwarp();
 
-    // ---- (F) fit + filters, line by line in the reference's order
+    // ---- (F) fit + filters: one lane per candidate line (32 lines at a time; a line is 3 .. a few hundred points),
+    // accepted lines appended in the reference's order by a ballot compaction
     int count = 0;
     double* out_lines = a.lines + (size_t)s * a.max_lines * 4;
     double* out_abc = a.abc + (size_t)s * a.max_lines * 3;
     int32_t* out_rng = a.index_range + (size_t)s * a.max_lines * 2;
     for (int base = 0; base < total; base += 32) {
         const int pos = base + lane;
-        const int my1 = pos < total ? lstart[pos] : -1;
-        const int my2 = pos < total ? cand[pos] : -1;
-        unsigned todo = __ballot_sync(0xffffffffu, my1 >= 0);
-        while (todo) {
-            const int src = __ffs(todo) - 1;
-            todo &= todo - 1;
-            const int i1 = __shfl_sync(0xffffffffu, my1, src), i2 = __shfl_sync(0xffffffffu, my2, src);
-            if (i2 - i1 < 2) continue;                                   // scan::add_line: fewer than 3 points
+        const int i1 = pos < total ? lstart[pos] : -1;
+        const int i2 = pos < total ? cand[pos] : -1;
+        bool keep = false;
+        double v[3] = {0.0, 0.0, 0.0}, e1x = 0.0, e1y = 0.0, e2x = 0.0, e2y = 0.0;
+        if (i1 >= 0 && i2 - i1 >= 2) {                                   // scan::add_line: at least 3 points
             double sxx = 0, sxy = 0, sx = 0, syy = 0, sy = 0;
-            for (int i = i1 + lane; i <= i2; i += 32) {
+            for (int i = i1; i <= i2; ++i) {
                 const double2 p = P[i];
                 sxx += p.x * p.x; sxy += p.x * p.y; sx += p.x; syy += p.y * p.y; sy += p.y;
             }
-            sxx = lines_warp_sum(sxx); sxy = lines_warp_sum(sxy); sx = lines_warp_sum(sx);
-            syy = lines_warp_sum(syy); sy = lines_warp_sum(sy);
-            double v[3];
             smallest_eigvec3(sxx, sxy, sx, syy, sy, (double)(i2 - i1 + 1), v);
             {   // sign convention of the ABI: the component of largest magnitude is positive
                 int k = 0;
@@ -257,7 +252,7 @@ __global__ void __launch_bounds__(128) scan_lines_kernel(ScanLinesArgs a) {
             if (ulen * ulen > 0.0) { ux /= ulen; uy /= ulen; }
             double err = 0.0;
             bool on_grid = false;
-            for (int i = i1 + lane; i <= i2; i += 32) {
+            for (int i = i1; i <= i2; ++i) {
                 const double2 p = P[i];
                 const double rx = p.x - q2x, ry = p.y - q2y;
                 const double t = ux * rx + uy * ry;
@@ -266,29 +261,26 @@ __global__ void __launch_bounds__(128) scan_lines_kernel(ScanLinesArgs a) {
                 const int c = (int)(p.x / a.resolution + a.w / 2), r = (int)(p.y / a.resolution + a.h / 2);
                 on_grid = on_grid || (r >= 0 && r < a.h && c >= 0 && c < a.w);
             }
-            err = lines_warp_max(err);
-            on_grid = __any_sync(0xffffffffu, on_grid);
             // project_to_line of the first and last point
-            double e1x, e1y, e2x, e2y;
-            {
-                const double2 pa = P[i1], pb = P[i2];
-                if (ulen < kLineEpsilo) { e1x = pa.x; e1y = pa.y; e2x = pb.x; e2y = pb.y; }
-                else {
-                    const double ta = (pa.x - q1x) * ux + (pa.y - q1y) * uy, tb = (pb.x - q1x) * ux + (pb.y - q1y) * uy;
-                    e1x = q1x + ta * ux; e1y = q1y + ta * uy; e2x = q1x + tb * ux; e2y = q1y + tb * uy;
-                }
+            const double2 pa = P[i1], pb = P[i2];
+            if (ulen < kLineEpsilo) { e1x = pa.x; e1y = pa.y; e2x = pb.x; e2y = pb.y; }
+            else {
+                const double ta = (pa.x - q1x) * ux + (pa.y - q1y) * uy, tb = (pb.x - q1x) * ux + (pb.y - q1y) * uy;
+                e1x = q1x + ta * ux; e1y = q1y + ta * uy; e2x = q1x + tb * ux; e2y = q1y + tb * uy;
             }
             const double len = sqrt((e1x - e2x) * (e1x - e2x) + (e1y - e2y) * (e1y - e2y));
-            if (err > a.max_dis) continue;
-            if (len < a.min_len) continue;
-            if (!on_grid) continue;
-            if (count < a.max_lines && lane == 0) {
-                out_lines[4 * count] = e1x; out_lines[4 * count + 1] = e1y; out_lines[4 * count + 2] = e2x; out_lines[4 * count + 3] = e2y;
-                out_abc[3 * count] = v[0]; out_abc[3 * count + 1] = v[1]; out_abc[3 * count + 2] = v[2];
-                out_rng[2 * count] = i1; out_rng[2 * count + 1] = i2;
-            }
-            ++count;
+            keep = !(err > a.max_dis) && !(len < a.min_len) && on_grid;
         }
+        const unsigned m = __ballot_sync(0xffffffffu, keep);
+        if (keep) {
+            const int slot = count + __popc(m & ((1u << lane) - 1u));
+            if (slot < a.max_lines) {
+                out_lines[4 * slot] = e1x; out_lines[4 * slot + 1] = e1y; out_lines[4 * slot + 2] = e2x; out_lines[4 * slot + 3] = e2y;
+                out_abc[3 * slot] = v[0]; out_abc[3 * slot + 1] = v[1]; out_abc[3 * slot + 2] = v[2];
+                out_rng[2 * slot] = i1; out_rng[2 * slot + 1] = i2;
+            }
+        }
+        count += __popc(m);
     }
     if (lane == 0) a.n_lines[s] = count;
 }
