@@ -30,9 +30,6 @@
 #ifndef LV_SCAN_U
 #define LV_SCAN_U 4        // batches of 32 points per pipeline stage
 #endif
-#ifndef LV_SCAN_EVICT_FIRST
-#define LV_SCAN_EVICT_FIRST 0   // 1: streamed point data is marked evict_first in L2
-#endif
 #ifndef LV_SCAN_WPC
 #define LV_SCAN_WPC 1      // warps (= frames in flight) per CTA.  One: the finest scheduling granularity — with 8 the
                            // warps of a CTA retire together and their successors sit in the prologue together
@@ -40,9 +37,6 @@
 #endif
 #ifndef LV_SCAN_WARPS_PER_SM
 #define LV_SCAN_WARPS_PER_SM 16   // register budget: 16 -> 128 registers per thread
-#endif
-#ifndef LV_SCAN_PF
-#define LV_SCAN_PF 0       // L2 prefetch distance in pipeline stages (0 = off)
 #endif
 
 namespace lv {
@@ -79,38 +73,21 @@ struct ScanMatchArgs {
     double huber_delta, laser_sqrt_info, assoc_gate, assoc_max_dist;
 };
 
-// streamed (read-once) loads: no L1 allocation, L2 eviction priority evict_first through a cache-hint policy so that the
-// small per-frame metadata, frame tables and tile partials that every launch re-reads stay resident in L2
-__device__ __forceinline__ uint64_t stream_policy() {
-    uint64_t pol;
-    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
-    return pol;
-}
-__device__ __forceinline__ double2 ld_stream_f64x2(const double2* p, uint64_t pol) {
+// streamed (read-once) loads: no L1 allocation.  (An L2 evict_first cache-hint policy on these loads and
+// prefetch.global.L2 ahead of the pipeline were both measured and made no difference / were slower; see DESIGN.md.)
+__device__ __forceinline__ double2 ld_stream_f64x2(const double2* p) {
     double2 v;
-#if LV_SCAN_EVICT_FIRST
-    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v2.f64 {%0, %1}, [%2], %3;" : "=d"(v.x), "=d"(v.y) : "l"(p), "l"(pol));
-#else
     asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
-#endif
     return v;
 }
-__device__ __forceinline__ int ld_stream_s32(const int32_t* p, uint64_t pol) {
+__device__ __forceinline__ int ld_stream_s32(const int32_t* p) {
     int v;
-#if LV_SCAN_EVICT_FIRST
-    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.s32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol));
-#else
     asm volatile("ld.global.nc.L1::no_allocate.s32 %0, [%1];" : "=r"(v) : "l"(p));
-#endif
     return v;
 }
-__device__ __forceinline__ double ld_stream_f64(const double* p, uint64_t pol) {
+__device__ __forceinline__ double ld_stream_f64(const double* p) {
     double v;
-#if LV_SCAN_EVICT_FIRST
-    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(p), "l"(pol));
-#else
     asm volatile("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(v) : "l"(p));
-#endif
     return v;
 }
 
@@ -190,15 +167,14 @@ __device__ __forceinline__ void scan_match_item(const ScanMatchArgs& a, const in
     double2 nc[U];
     int nli[U];
     double nw[U];
-    const uint64_t pol = stream_policy();
     auto issue = [&](int64_t base) {
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             const int64_t p = base + 32 * u;
             const bool ok = p < pe;
-            nli[u] = ok ? ld_stream_s32(a.point_line + p, pol) : -1;
-            nc[u] = ok ? ld_stream_f64x2(a.points + p, pol) : make_double2(0.0, 0.0);
-            if constexpr (HAS_WEIGHT) nw[u] = ok ? ld_stream_f64(a.point_weight + p, pol) : 0.0;
+            nli[u] = ok ? ld_stream_s32(a.point_line + p) : -1;
+            nc[u] = ok ? ld_stream_f64x2(a.points + p) : make_double2(0.0, 0.0);
+            if constexpr (HAS_WEIGHT) nw[u] = ok ? ld_stream_f64(a.point_weight + p) : 0.0;
         }
     };
     issue(pb + lane);
@@ -315,16 +291,6 @@ __device__ __forceinline__ void scan_match_item(const ScanMatchArgs& a, const in
 #pragma unroll
         for (int u = 0; u < U; ++u) { c[u] = nc[u]; li[u] = nli[u]; if constexpr (HAS_WEIGHT) w[u] = nw[u]; }
         issue(base + 32 * U);
-        if constexpr (LV_SCAN_PF > 0) {
-            // pull the stage LV_SCAN_PF stages ahead from HBM into L2: one 128-byte line per lane covers the stage's
-            // points (U*512 B) and line indices (U*128 B) without holding registers
-            const int64_t q = base - lane + (int64_t)32 * U * LV_SCAN_PF;   // first point of that stage
-            if (lane < 4 * U) {            // 8 points per 128-byte line
-                if (q + 8 * lane < pe) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.points + q + 8 * lane));
-            } else if (lane < 5 * U) {     // 32 indices per line
-                if (q + 32 * (lane - 4 * U) < pe) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.point_line + q + 32 * (lane - 4 * U)));
-            }
-        }
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             if (li[u] < 0) continue;

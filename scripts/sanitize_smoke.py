@@ -1,20 +1,41 @@
-"""Small end-to-end exercise of every kernel for compute-sanitizer (memcheck / racecheck / initcheck)."""
+"""Small end-to-end exercise of every kernel for compute-sanitizer (memcheck / racecheck / initcheck):
+every thread-group shape of window_kernel, both factor kernels, the fused small-batch solve, the three-kernel loop,
+the split-phase (sharded) entry points and the three laser front-end kernels."""
 import os, sys
 R = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, R); sys.path.insert(0, os.path.join(R, "tests"))
 import numpy as np
 import lvio2d_b200 as L
-import oracle_lib as O
 from lvio2d_b200.solver import Context
-for assoc, huber in ((0, 0.0), (1, 1.5)):
-    P = L.corridor_params(max_iters=4); P.assoc_mode = assoc; P.huber_delta = huber
-    for mk in (lambda: L.synth.make_batch(2, 42, n_frames=4, beams=90), lambda: L.synth.config_init(1, n_frames=4), lambda: L.synth.config_tracking2(1), lambda: L.synth.config_c1()):
-        sb = mk()
-        with Context(P) as c:
-            hb = c.preintegrate_batch(sb)
-            c.set_windows(hb)
-            c.linearize(0); c.linearize(1)
-            s = c.solve(); x = c.get_states()
-            c.marginalize()
-            c.set_point_shard(0, 2); c.solve_begin(); c.eval_laser(); c.lm_step(want_active=True); c.set_point_shard(0, 1)
-        print("ok", assoc, huber, hb.n_frames, s["final_cost"])
+
+CASES = (lambda: L.synth.make_batch(2, 42, n_frames=4, beams=90), lambda: L.synth.config_init(1, n_frames=4),
+         lambda: L.synth.config_tracking2(1), lambda: L.synth.config_c1())
+for env in ({}, {"LVIO2D_WINDOW_THREADS": "32", "LVIO2D_FUSED_SMALL": "0"}, {"LVIO2D_WINDOW_THREADS": "128", "LVIO2D_FUSED_SMALL": "0"},
+            {"LVIO2D_FACTOR_PAIRED": "0", "LVIO2D_FUSED_SMALL": "0"}):
+    for k in ("LVIO2D_WINDOW_THREADS", "LVIO2D_FUSED_SMALL", "LVIO2D_FACTOR_PAIRED"):
+        os.environ.pop(k, None)
+    os.environ.update(env)
+    for assoc, huber in ((0, 0.0), (1, 1.5)):
+        P = L.corridor_params(max_iters=3); P.assoc_mode = assoc; P.huber_delta = huber
+        for mk in CASES:
+            sb = mk()
+            with Context(P) as c:
+                hb = c.preintegrate_batch(sb)
+                c.set_windows(hb)
+                c.linearize(0); c.linearize(1)
+                s = c.solve(); x = c.get_states()
+                c.marginalize()
+                c.set_point_shard(0, 2); c.solve_begin(); c.eval_laser(); c.lm_step(want_active=True); c.set_point_shard(0, 1)
+            print("ok", env, assoc, huber, hb.n_frames, s["final_cost"])
+# laser front-end
+lp = L.corridor_line_params()
+rg, hd = L.synth.make_range_batch(3, 5, beams=181)
+rg[1, :] = np.inf
+with Context(L.corridor_params()) as c:
+    cnt, pts, pz = c.scan_to_points(rg, hd, deskew=True)
+    off = np.arange(3, dtype=np.int64) * rg.shape[1]
+    n, lines, abc, rng = c.extract_lines(lp, off, pts.reshape(-1, 2), max_lines=64, point_count=cnt, point_z=pz.reshape(-1))
+    pose = np.zeros((3, 6))
+    nm, m = c.match_lines(lp, n, lines, n, lines, pose, pose, point_offset1=off, points1=pts.reshape(-1, 2), index_range1=rng, point_count1=cnt)
+    nm2, m2 = c.match_lines(lp, n, lines, n, lines, pose, pose, kk=1)
+print("ok front-end", cnt, n, nm, nm2)
