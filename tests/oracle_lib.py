@@ -274,5 +274,18 @@ class OracleContext:
         X0, J, r, _, _ = marginalize(self.params, self.hb, self.states)
         return X0, J, r
 
+    # the laser front-end entry points, same signatures as lvio2d_b200.solver.Context
+    def scan_to_points(self, ranges, headers, deskew=True, want_times=False):
+        cnt, pts, pz, pt = scan_to_points(ranges, headers, deskew)
+        return (cnt, pts, pz, pt) if want_times else (cnt, pts, pz)
+
+    def extract_lines(self, line_params, point_offset, points, max_lines=256, point_count=None, point_z=None):
+        return extract_lines(line_params, point_offset, points, max_lines, point_count, point_z)
+
+    def match_lines(self, line_params, n_lines1, lines1, n_lines2, lines2, pose1, pose2, kk=0, point_offset1=None, points1=None,
+                    index_range1=None, point_count1=None):
+        return match_lines(self.params, line_params, n_lines1, lines1, n_lines2, lines2, pose1, pose2, kk, point_offset1, points1,
+                           index_range1, point_count1)
+
     def close(self):
         pass
