@@ -13,13 +13,27 @@ Same names, argument meaning and call order as the reference so that tests read 
                       returning the `LaserMatch` that `FrameInfo.add_laser_match` / `Solver.solve` take.
 
 The backend is any object with `scan_to_points / extract_lines / match_lines` (`solver.Context`: the CUDA library; the
-tests also pass a CPU-oracle stand-in).  The sub-map bookkeeping of `laser_manager::add_scan` (:424-496) is host logic
-that stays with the caller.
+tests also pass a CPU-oracle stand-in).  The sub-map bookkeeping of `laser_manager::add_scan` (:424-496) and the
+`match_with_front / back / ref` wrappers (:498-547) are host control logic in the reference and are host logic here
+(plain Python on the line lists); matching against a sub-map uses the 0.05 m-sample rasterisation of
+`scan::add_line(p1, p2, false)` inside `lvio2d_match_lines`.
 """
 import numpy as np
 
 from . import abi
+from .params import params_T
 from .solver import LaserMatch, Line
+from .synth import exp_so3
+
+
+def _log_so3(R):
+    """rotation matrix -> rotation vector (only its norm is used, by the motion filter of add_scan)."""
+    c = max(-1.0, min(1.0, (np.trace(R) - 1.0) / 2.0))
+    ang = float(np.arccos(c))
+    if ang < 1e-12:
+        return np.zeros(3)
+    w = np.array([R[2, 1] - R[1, 2], R[0, 2] - R[2, 0], R[1, 0] - R[0, 1]]) / (2.0 * np.sin(ang))
+    return w * ang
 
 
 class Laser:
@@ -63,11 +77,115 @@ class Scan:
         self.time, self.points, self.lines = float(time), points, lines
 
 
-class LaserManager:
-    """lvio_2d::laser_manager restricted to spawn_scan and do_match."""
+class LaserSubmap:
+    """lvio_2d::laser_submap (laser_type.h): a scan and the IMU pose it is expressed under."""
 
-    def __init__(self, backend, line_params, max_lines=256):
+    def __init__(self, scan, current_p, current_q):
+        self.scan_ptr = scan
+        self.current_p, self.current_q = np.array(current_p, dtype=np.float64), np.array(current_q, dtype=np.float64)
+
+
+def _tf(p, q):
+    T = np.eye(4)
+    T[:3, :3], T[:3, 3] = exp_so3(np.asarray(q, dtype=np.float64)), p
+    return T
+
+
+class LaserManager:
+    """lvio_2d::laser_manager: spawn_scan and do_match on the device entry points; add_scan / match_with_* / pop_scan as
+    the reference's host bookkeeping (key-frame deque, reference sub-map and the one being spawned)."""
+
+    def __init__(self, backend, line_params, max_lines=256, params=None, ref_motion_filter_p=0.01, ref_motion_filter_q=0.01,
+                 ref_n_accumulation=100):
         self._be, self.line_params, self.max_lines = backend, line_params, int(max_lines)
+        # config/corridor.yaml:120-122
+        self.ref_motion_filter_p, self.ref_motion_filter_q = ref_motion_filter_p, ref_motion_filter_q
+        self.ref_n_accumulation = int(ref_n_accumulation)
+        self.T_il = np.eye(4)
+        if params is not None:
+            self.T_il[:3, :] = params_T(params, "T_imu_to_laser")
+        self.key_frame = []
+        self.ref_submap_ptr = None
+        self.spawnning_ref_submap_ptr = None
+        self.last_add_tf = np.eye(4)
+        self.current_count = 0
+
+    # ---- scan::add_line(p1, p2, false) (laser_manager.cpp:215-223 -> :137-154): the three fake points p1, mid, p2 are
+    # collinear, so the refit returns the same segment up to rounding; what remains are the filters
+    def _add_line(self, scan, p1, p2):
+        p1, p2 = np.array([p1[0], p1[1], 0.0]), np.array([p2[0], p2[1], 0.0])
+        if np.linalg.norm(p1 - p2) < self.line_params.line_min_len:
+            return
+        d = p2 - p1
+        nrm = np.array([-d[1], d[0]]) / np.linalg.norm(d[:2])
+        scan.lines.append(ScanLine(p1, p2, [nrm[0], nrm[1], -float(nrm @ p1[:2])], 0, -1))
+
+    def _empty_submap(self, current_p, current_q):
+        return LaserSubmap(Scan(0.0, None, []), current_p, current_q)
+
+    def add_scan(self, scan, current_p, current_q):
+        """laser_manager::add_scan (laser_manager.cpp:424-496)."""
+        self.key_frame.append(LaserSubmap(scan, current_p, current_q))
+        current_tf = _tf(current_p, current_q)
+        if self.ref_submap_ptr is not None:
+            d = np.linalg.inv(self.last_add_tf) @ current_tf
+            dq = _log_so3(d[:3, :3])
+            if np.linalg.norm(d[:3, 3]) < self.ref_motion_filter_p and np.linalg.norm(dq) < self.ref_motion_filter_q:
+                return
+        else:
+            self.ref_submap_ptr = self._empty_submap(current_p, current_q)
+            self.last_add_tf = current_tf
+            self.current_count = 1
+            for l in scan.lines:
+                self._add_line(self.ref_submap_ptr.scan_ptr, l.p1, l.p2)
+            return
+        for sub in (self.ref_submap_ptr, self.spawnning_ref_submap_ptr):
+            if sub is None:
+                continue
+            T = np.linalg.inv(self.T_il) @ np.linalg.inv(_tf(sub.current_p, sub.current_q)) @ current_tf @ self.T_il
+            for l in scan.lines:
+                self._add_line(sub.scan_ptr, T[:3, :3] @ l.p1 + T[:3, 3], T[:3, :3] @ l.p2 + T[:3, 3])
+        self.current_count += 1
+        if self.spawnning_ref_submap_ptr is None and self.current_count == self.ref_n_accumulation // 2:
+            self.spawnning_ref_submap_ptr = self._empty_submap(current_p, current_q)
+            self.last_add_tf = current_tf
+            for l in scan.lines:
+                self._add_line(self.spawnning_ref_submap_ptr.scan_ptr, l.p1, l.p2)
+        if self.current_count == self.ref_n_accumulation:
+            self.ref_submap_ptr = self.spawnning_ref_submap_ptr
+            self.spawnning_ref_submap_ptr = self._empty_submap(current_p, current_q)
+            self.last_add_tf = current_tf
+            for l in scan.lines:
+                self._add_line(self.spawnning_ref_submap_ptr.scan_ptr, l.p1, l.p2)
+            self.current_count = self.ref_n_accumulation // 2
+        self.last_add_tf = current_tf
+
+    def _no_match(self, scan, current_p, current_q):
+        m = LaserMatch([], [], current_p, current_q)
+        m.p2, m.q2 = np.array(current_p, dtype=np.float64), np.array(current_q, dtype=np.float64)
+        m.scan2 = scan
+        return m
+
+    def match_with_front(self, scan, current_p, current_q):
+        if not self.key_frame:
+            return self._no_match(scan, current_p, current_q)
+        kf = self.key_frame[0]
+        return self.do_match(kf.scan_ptr, scan, kf.current_p, kf.current_q, current_p, current_q)
+
+    def match_with_back(self, scan, current_p, current_q):
+        if not self.key_frame:
+            return self._no_match(scan, current_p, current_q)
+        kf = self.key_frame[-1]
+        return self.do_match(kf.scan_ptr, scan, kf.current_p, kf.current_q, current_p, current_q)
+
+    def match_with_ref(self, scan, current_p, current_q):
+        if self.ref_submap_ptr is None:
+            return self._no_match(scan, current_p, current_q)
+        r = self.ref_submap_ptr
+        return self.do_match(r.scan_ptr, scan, r.current_p, r.current_q, current_p, current_q)
+
+    def pop_scan(self):
+        return self.key_frame.pop(0) if self.key_frame else None
 
     def spawn_scan(self, laser):
         pts = laser.points
@@ -93,9 +211,12 @@ class LaserManager:
         n1, l1, r1 = self._pack(scan1, m1)
         n2, l2, _ = self._pack(scan2, m2)
         pose1, pose2 = np.concatenate([p1, q1]).reshape(1, 6), np.concatenate([p2, q2]).reshape(1, 6)
-        nm, m = self._be.match_lines(self.line_params, n1, l1, n2, l2, pose1, pose2, kk=kk,
-                                     point_offset1=np.array([0, len(scan1.points)], dtype=np.int64),
-                                     points1=np.ascontiguousarray(scan1.points[:, 0:2]), index_range1=r1)
+        if scan1.points is not None:     # a scan from spawn_scan: its lines cover the cells of their own points
+            kw = dict(point_offset1=np.array([0, len(scan1.points)], dtype=np.int64),
+                      points1=np.ascontiguousarray(scan1.points[:, 0:2]), index_range1=r1)
+        else:                            # a sub-map built by add_line(p1, p2, false): cells sampled along the segments
+            kw = {}
+        nm, m = self._be.match_lines(self.line_params, n1, l1, n2, l2, pose1, pose2, kk=kk, **kw)
         lines1 = [scan1.lines[int(j)] for j, _ in m[0, :int(nm[0])]]
         lines2 = [scan2.lines[int(i)] for _, i in m[0, :int(nm[0])]]
         match = LaserMatch(lines1, lines2, p1, q1)

@@ -76,3 +76,60 @@ def test_front_end_flow_matches_oracle(oracle):
     assert [(scans[0].lines.index(a), scans[1].lines.index(b)) for a, b in zip(match.lines1, match.lines2)] == \
            [(oscans[0].lines.index(a), oscans[1].lines.index(b)) for a, b in zip(omatch.lines1, omatch.lines2)]
     assert np.abs(pose - opose).max() < 1e-6
+
+
+def _scan_sequence(oracle, n=8, seed=11):
+    """n scans of one world along a short trajectory (synthetic window frames), as Scan objects + true IMU poses."""
+    P = L.corridor_params()
+    sb = L.synth.make_batch(1, seed, n_frames=n, beams=BEAMS, fov_deg=FOV, n_segments=12, frame_dt=0.3)
+    be = oracle.OracleContext(P)
+    lm = LaserManager(be, L.corridor_line_params(), max_lines=160, params=P, ref_n_accumulation=6)
+    a0, da = np.float32(math.radians(-FOV / 2.0)), np.float32(math.radians(FOV) / (BEAMS - 1))
+    scans = []
+    for k in range(n):
+        pts = sb.points[sb.point_offset[k]:sb.point_offset[k + 1]]
+        laser = Laser(be, np.linalg.norm(pts, axis=1).astype(np.float32), a0, da, np.float32(0.0), 100.0 + 0.3 * k)
+        scans.append(lm.spawn_scan(laser))
+    return P, sb, lm, scans
+
+
+def test_add_scan_bookkeeping_and_match_with_ref(oracle):
+    """laser_manager::add_scan / match_with_ref (laser_manager.cpp:424-547) as host logic: first scan initialises the
+    reference sub-map, the motion filter skips a scan that did not move, lines arrive in the sub-map's laser frame, the
+    spawning sub-map appears at n/2 and replaces the reference at n; matching a new scan against the sub-map pairs
+    segments that coincide once both are taken to the world."""
+    P, sb, lm, scans = _scan_sequence(oracle)
+    T_il = lm.T_il
+    pose = lambda k: (sb.truth[k, 0:3], sb.truth[k, 3:6])  # noqa: E731
+    m = lm.match_with_ref(scans[0], *pose(0))
+    assert m.lines1 == [] and m.lines2 == [] and np.array_equal(m.p1, m.p2)            # no sub-map yet
+    lm.add_scan(scans[0], *pose(0))
+    assert lm.current_count == 1 and len(lm.ref_submap_ptr.scan_ptr.lines) == len(scans[0].lines)
+    lm.add_scan(scans[0], *pose(0))                                                     # did not move: filtered
+    assert lm.current_count == 1 and len(lm.key_frame) == 2
+    n_ref = len(lm.ref_submap_ptr.scan_ptr.lines)
+    lm.add_scan(scans[1], *pose(1))
+    assert lm.current_count == 2 and len(lm.ref_submap_ptr.scan_ptr.lines) == n_ref + len(scans[1].lines)
+    # a line of scan 1, as stored in the sub-map, is the same world segment as in scan 1's own frame
+    from lvio2d_b200.frontend import _tf
+    Tw0, Tw1 = _tf(*pose(0)) @ T_il, _tf(*pose(1)) @ T_il
+    stored, own = lm.ref_submap_ptr.scan_ptr.lines[n_ref], scans[1].lines[0]
+    # (to the flattening: add_line refits in the x-y plane of the sub-map's laser frame and drops z, like the reference)
+    assert np.allclose((Tw0 @ np.r_[stored.p1, 1.0])[:2], (Tw1 @ np.r_[own.p1, 1.0])[:2], atol=1e-3)
+    lm.add_scan(scans[2], *pose(2))
+    assert lm.current_count == 3 and lm.spawnning_ref_submap_ptr is not None            # n/2 = 3: spawning sub-map created
+    assert len(lm.spawnning_ref_submap_ptr.scan_ptr.lines) == len(scans[2].lines)
+    match = lm.match_with_ref(scans[3], *pose(3))
+    assert len(match.lines1) == len(match.lines2) >= 5
+    Tw3 = _tf(*pose(3)) @ T_il
+    for l1, l2 in zip(match.lines1, match.lines2):
+        a, b = (Tw0 @ np.r_[l1.p1, 1.0])[:2], (Tw0 @ np.r_[l1.p2, 1.0])[:2]
+        u = (b - a) / np.linalg.norm(b - a)
+        for q in (l2.p1, l2.p2):
+            w = (Tw3 @ np.r_[q, 1.0])[:2] - a
+            assert abs(w[0] * u[1] - w[1] * u[0]) < 0.1                                  # point-to-line distance in the world
+    for k in (3, 4, 5):
+        lm.add_scan(scans[k], *pose(k))
+    assert lm.current_count == 3 and np.array_equal(lm.ref_submap_ptr.current_p, sb.truth[2, 0:3])   # rotated at n = 6
+    assert np.array_equal(lm.spawnning_ref_submap_ptr.current_p, sb.truth[5, 0:3])
+    assert lm.pop_scan().scan_ptr is scans[0] and len(lm.key_frame) == 6
