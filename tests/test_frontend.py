@@ -133,3 +133,58 @@ def test_add_scan_bookkeeping_and_match_with_ref(oracle):
     assert lm.current_count == 3 and np.array_equal(lm.ref_submap_ptr.current_p, sb.truth[2, 0:3])   # rotated at n = 6
     assert np.array_equal(lm.spawnning_ref_submap_ptr.current_p, sb.truth[5, 0:3])
     assert lm.pop_scan().scan_ptr is scans[0] and len(lm.key_frame) == 6
+
+
+def _full_pipeline(oracle, backend, solver, n=8, seed=11):
+    """trajectory::add_sensor_data + do_tracking for a short sequence, every step through the mirrored interfaces:
+    message -> Laser -> spawn_scan -> match_with_ref -> frame_info -> solver::solve -> add_scan."""
+    P = solver.params
+    sb = L.synth.make_batch(1, seed, n_frames=n, beams=BEAMS, fov_deg=FOV, n_segments=12, frame_dt=0.3)
+    hb = oracle.preintegrate_batch(P, sb)
+    imu, wheel = hb["imu"].reshape(-1, 466), hb["wheel"].reshape(-1, 15)
+    lm = LaserManager(backend, L.corridor_line_params(), max_lines=160, params=P, ref_n_accumulation=100)
+    a0, da = np.float32(math.radians(-FOV / 2.0)), np.float32(math.radians(FOV) / (BEAMS - 1))
+    frames, out, n_pairs = [], [], []
+    for k in range(n):
+        pts = sb.points[sb.point_offset[k]:sb.point_offset[k + 1]]
+        laser = Laser(backend, np.linalg.norm(pts, axis=1).astype(np.float32), a0, da, np.float32(0.0), 100.0 + 0.3 * k)
+        scan = lm.spawn_scan(laser)
+        s = sb.truth[0] if k == 0 else sb.states[k]
+        f = FrameInfo(0.3 * k, s[0:3], s[3:6], s[6:9], s[9:15], imu[k - 1] if k else None, wheel[k - 1] if k else None)
+        if k > 0:
+            f.p += frames[-1].p - sb.states[k - 1, 0:3] if k > 1 else 0.0       # carry the last correction (cf. replay.run_tracking)
+            match = lm.match_with_ref(scan, f.p, f.q)
+            n_pairs.append(len(match.lines1))
+            f.add_laser_match(match)
+            solver.solve([frames[-1], f])
+        frames.append(f)
+        lm.add_scan(scan, f.p, f.q)
+        out.append(np.r_[f.p, f.q])
+    return sb, np.array(out), n_pairs
+
+
+def test_full_front_end_tracking_pipeline_on_the_oracle(oracle):
+    P = L.corridor_params(max_iters=10)
+    be = oracle.OracleContext(P)
+    sb, traj, n_pairs = _full_pipeline(oracle, be, Solver(P, fast_mode=True, ctx=be))
+    assert min(n_pairs) >= 5
+    err = np.abs(traj[1:, 0:2] - sb.truth[1:, 0:2]).max()
+    guess = np.abs(sb.states[1:, 0:2] - sb.truth[1:, 0:2]).max()
+    assert err < guess
+
+
+@pytest.mark.gpu
+def test_full_front_end_tracking_pipeline_matches_oracle(oracle):
+    """The same pipeline on the CUDA library (fast_mode, 10 iterations: well-posed, see tests/test_sequence.py): every
+    frame's pose within the north-star bar of the CPU path's."""
+    from lvio2d_b200.solver import Context
+
+    P = L.corridor_params(max_iters=10)
+    be = oracle.OracleContext(P)
+    _, want, opairs = _full_pipeline(oracle, be, Solver(P, fast_mode=True, ctx=be))
+    with Context(P) as c:
+        sb, got, pairs = _full_pipeline(oracle, c, Solver(P, fast_mode=True, ctx=c))
+    assert pairs == opairs
+    d = np.abs(got - want)
+    print(f"front-end + tracking, 8 frames: max pose difference CUDA vs oracle {d.max():.3e}")
+    assert d[:, 0:3].max() <= 1e-4 and d[:, 3:6].max() <= 1e-4
