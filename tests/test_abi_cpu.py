@@ -41,6 +41,8 @@ int main(void) {
   printf("%zu %zu %zu\n", sizeof(lvio2d_params), sizeof(lvio2d_window_batch), sizeof(lvio2d_summary));
   printf("%zu %zu %zu %zu\n", offsetof(lvio2d_params, g), offsetof(lvio2d_params, max_iters), offsetof(lvio2d_params, huber_delta), offsetof(lvio2d_params, assoc_max_dist));
   printf("%zu %zu %zu\n", offsetof(lvio2d_window_batch, points), offsetof(lvio2d_window_batch, ground_multiplicity), offsetof(lvio2d_window_batch, prior_J));
+  printf("%zu %zu %zu %zu %zu\n", sizeof(lvio2d_line_params), sizeof(lvio2d_scan_header), offsetof(lvio2d_scan_header, stamp),
+         offsetof(lvio2d_scan_header, linear), offsetof(lvio2d_scan_header, angular));
   return 0; }'''
     import tempfile
 
@@ -52,7 +54,9 @@ int main(void) {
     got = [int(x) for x in out]
     want = [C.sizeof(abi.Params), C.sizeof(abi.WindowBatch), C.sizeof(abi.Summary),
             abi.Params.g.offset, abi.Params.max_iters.offset, abi.Params.huber_delta.offset, abi.Params.assoc_max_dist.offset,
-            abi.WindowBatch.points.offset, abi.WindowBatch.ground_multiplicity.offset, abi.WindowBatch.prior_J.offset]
+            abi.WindowBatch.points.offset, abi.WindowBatch.ground_multiplicity.offset, abi.WindowBatch.prior_J.offset,
+            C.sizeof(abi.LineParams), C.sizeof(abi.ScanHeader), abi.ScanHeader.stamp.offset, abi.ScanHeader.linear.offset,
+            abi.ScanHeader.angular.offset]
     assert got == want
 
 
