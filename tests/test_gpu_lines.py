@@ -220,7 +220,6 @@ def test_front_end_chain_feeds_the_solver(oracle, lp):
 
 def test_front_end_error_paths(ctx, lp):
     """Invalid arguments come back as negative status codes (Lvio2dError), never as a crash or a silent fallback."""
-    from lvio2d_b200 import abi
     from lvio2d_b200.solver import Lvio2dError
 
     off, pts = L.synth.make_scan_batch(2, 1, beams=64)
