@@ -34,6 +34,7 @@ struct Params {
     double huber_delta;           // <= 0: no loss (the reference)
     int assoc_mode;               // 0 fixed (the reference), 1 nearest line (BASELINE config 3, an extension)
     double assoc_gate, assoc_max_dist;
+    bool analytic_laser = false;  // cpu_baseline flavour: closed-form Jacobian of the point-to-line factor instead of Jets
     explicit Params(const lvio2d_params& p) {
         T_imu_to_laser = iso_from_rowmajor_3x4(p.T_imu_to_laser);
         T_imu_to_wheel = iso_from_rowmajor_3x4(p.T_imu_to_wheel);
@@ -117,6 +118,61 @@ struct laser_point_factor {
         return true;
     }
 };
+
+// The same residual with a closed-form 1x12 Jacobian (no Jets) — the "analytic" CPU-baseline flavour SURVEY.md §8d asks
+// to be timed next to the faithful Jet flavour (the reference itself only has the Jet path).  With
+// R(theta + d) = R(theta) Exp(J_r(theta) d):  d(R v)/d theta = -R [v]x J_r(theta).
+inline Mat3<double> so3_right_jacobian(const Vec3<double>& v) {
+    const double t2 = v.x * v.x + v.y * v.y + v.z * v.z, t = std::sqrt(t2);
+    double a, b;  // J_r = I - a [v]x + b [v]x^2
+    if (t < 1e-6) { a = 0.5 - t2 / 24.0; b = 1.0 / 6.0 - t2 / 120.0; }
+    else { a = (1.0 - std::cos(t)) / t2; b = (t - std::sin(t)) / (t2 * t); }
+    Mat3<double> K;
+    K.m[0][1] = -v.z; K.m[0][2] = v.y; K.m[1][0] = v.z; K.m[1][2] = -v.x; K.m[2][0] = -v.y; K.m[2][1] = v.x;
+    const Mat3<double> K2 = K * K;
+    Mat3<double> J = Mat3<double>::identity();
+    for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) J.m[i][j] += -a * K.m[i][j] + b * K2.m[i][j];
+    return J;
+}
+// d(R(theta) v)/d theta as a 3x3 matrix
+inline Mat3<double> d_rotated_d_theta(const Mat3<double>& R, const Vec3<double>& theta, const Vec3<double>& v) {
+    Mat3<double> Vx;
+    Vx.m[0][1] = -v.z; Vx.m[0][2] = v.y; Vx.m[1][0] = v.z; Vx.m[1][2] = -v.x; Vx.m[2][0] = -v.y; Vx.m[2][1] = v.x;
+    Mat3<double> M = R * Vx * so3_right_jacobian(theta);
+    for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) M.m[i][j] = -M.m[i][j];
+    return M;
+}
+// res[0] and jac[12] over (p_i, theta_i, p_j, theta_j) of laser_point_factor
+inline void laser_point_analytic(const Params& P, const Vec3<double>& a1, const Vec3<double>& a2, const Vec3<double>& c, double weight,
+                                 const double* xi, const double* xj, double* res, double* jac) {
+    const Vec3<double> thi(xi[3], xi[4], xi[5]), thj(xj[3], xj[4], xj[5]);
+    const Mat3<double> Ri = lie::exp_so3<double>(thi), Rj = lie::exp_so3<double>(thj);
+    const Mat3<double>& Ril = P.T_imu_to_laser.R;
+    const Vec3<double>& til = P.T_imu_to_laser.t;
+    const Vec3<double> cj = Ril * c + til, b1 = Ril * a1 + til, b2 = Ril * a2 + til;   // in the IMU frames
+    Vec3<double> C = Rj * cj + Vec3<double>(xj[0], xj[1], xj[2]);
+    Vec3<double> A1 = Ri * b1 + Vec3<double>(xi[0], xi[1], xi[2]), A2 = Ri * b2 + Vec3<double>(xi[0], xi[1], xi[2]);
+    // flattened to z = 0: only the x, y rows of every derivative matter
+    const double ex = A2.x - A1.x, ey = A2.y - A1.y, L = std::sqrt(ex * ex + ey * ey);
+    const double ux = ex / L, uy = ey / L, nx = -uy, ny = ux;
+    const double wx = C.x - A2.x, wy = C.y - A2.y;
+    const double d = nx * wx + ny * wy;
+    const double sgn = d < 0 ? -1.0 : 1.0, k = weight * P.laser_sqrt_info;
+    res[0] = k * std::fabs(d);
+    const Mat3<double> dC = d_rotated_d_theta(Rj, thj, cj), dA1 = d_rotated_d_theta(Ri, thi, b1), dA2 = d_rotated_d_theta(Ri, thi, b2);
+    const double t = ux * wx + uy * wy;   // along-line coordinate of C relative to A2
+    for (int q = 0; q < 3; ++q) {
+        // pose j: only C moves
+        jac[6 + q] = k * sgn * (q == 0 ? nx : (q == 1 ? ny : 0.0));
+        jac[9 + q] = k * sgn * (nx * dC.m[0][q] + ny * dC.m[1][q]);
+        // pose i: A1 and A2 move.  d = n.(C - A2), n = perp(u), u = (A2 - A1)/L:
+        //   dd = -n.dA2 + dn.(C - A2),  dn.(C - A2) = -(u.(C - A2)) n.d(A2 - A1)/L
+        const double da1x = (q == 0), da1y = (q == 1);      // d A /d p_i = I
+        jac[q] = k * sgn * (-(nx * da1x + ny * da1y));       // d(A2 - A1)/d p_i = 0
+        const double dex = dA2.m[0][q] - dA1.m[0][q], dey = dA2.m[1][q] - dA1.m[1][q];
+        jac[3 + q] = k * sgn * (-(nx * dA2.m[0][q] + ny * dA2.m[1][q]) - t * (nx * dex + ny * dey) / L);
+    }
+}
 
 // ---------------------------------------------------------------- imu (imu_factor.h:13-89)
 struct imu_factor {

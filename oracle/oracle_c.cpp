@@ -145,8 +145,27 @@ int oracle_cost(const lvio2d_params* p, const lvio2d_window_batch* batch, const 
 }
 // solver::solve / do_init_solve.  n_threads > 1 parallelises over windows (std::thread) for the all-cores
 // baseline; the reference itself is single threaded (solver.cpp:798).
+static int solve_impl(const lvio2d_params* p, const lvio2d_window_batch* batch, double* states_out, lvio2d_summary* summaries, int32_t n_threads,
+                      bool analytic_laser);
 int oracle_solve(const lvio2d_params* p, const lvio2d_window_batch* batch, double* states_out, lvio2d_summary* summaries, int32_t n_threads) {
+    return solve_impl(p, batch, states_out, summaries, n_threads, false);
+}
+// the "analytic" CPU-baseline flavour: closed-form Jacobian for the scan points, Jets for the rest
+int oracle_solve_analytic(const lvio2d_params* p, const lvio2d_window_batch* batch, double* states_out, lvio2d_summary* summaries,
+                          int32_t n_threads) {
+    return solve_impl(p, batch, states_out, summaries, n_threads, true);
+}
+int oracle_eval_laser_point_analytic(const lvio2d_params* p, const double* a1, const double* a2, const double* c, double weight,
+                                     const double* pose_i, const double* pose_j, double* res, double* jac) {
     Params P(*p);
+    laser_point_analytic(P, Vec3<double>(a1[0], a1[1], 0.0), Vec3<double>(a2[0], a2[1], 0.0), Vec3<double>(c[0], c[1], 0.0), weight, pose_i,
+                         pose_j, res, jac);
+    return 0;
+}
+static int solve_impl(const lvio2d_params* p, const lvio2d_window_batch* batch, double* states_out, lvio2d_summary* summaries, int32_t n_threads,
+                      bool analytic_laser) {
+    Params P(*p);
+    P.analytic_laser = analytic_laser;
     LMOptions opt = lm_options_from(*p);
     const int dim = 15 * batch->n_frames;
     std::memcpy(states_out, batch->states, sizeof(double) * (size_t)dim * batch->n_windows);

@@ -116,7 +116,9 @@ public:
                 laser_point_factor fac(&P_, Vec3<double>(L[0], L[1], 0.0), Vec3<double>(L[2], L[3], 0.0),
                                        Vec3<double>(W_.B->points[2 * p], W_.B->points[2 * p + 1], 0.0), wgt);
                 double r[1], J[12];
-                if (lin) {
+                if (lin && P_.analytic_laser) {
+                    laser_point_analytic(P_, fac.a1, fac.a2, fac.c, wgt, xi, xj, r, J);
+                } else if (lin) {
                     autodiff<1, 12>(fac, {xi, xi + 3, xj, xj + 3}, {3, 3, 3, 3}, r, J,
                                     [](const laser_point_factor& f, const Jet<12>* const* a, Jet<12>* res) {
                                         f(a[0], a[1], a[2], a[3], res);

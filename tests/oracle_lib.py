@@ -94,6 +94,15 @@ def eval_laser_point(params, a1, a2, c, weight, pose_i, pose_j):
     return res, jac
 
 
+def eval_laser_point_analytic(params, a1, a2, c, weight, pose_i, pose_j):
+    """The closed-form flavour of the same factor (cpu_baseline "analytic")."""
+    res, jac = np.zeros(1), np.zeros((1, 12))
+    lib().oracle_eval_laser_point_analytic.argtypes = [C.POINTER(abi.Params), dp, dp, dp, C.c_double, dp, dp, dp, dp]
+    lib().oracle_eval_laser_point_analytic(C.byref(params), _d(_arr(a1)), _d(_arr(a2)), _d(_arr(c)), float(weight),
+                                           _d(_arr(pose_i)), _d(_arr(pose_j)), _d(res), _d(jac))
+    return res, jac
+
+
 def eval_imu_factor(params, blob, state_i, state_j):
     res, jac = np.zeros(15), np.zeros((15, 30))
     lib().oracle_eval_imu_factor(C.byref(params), _d(_arr(blob)), _d(_arr(state_i)), _d(_arr(state_j)), _d(res), _d(jac))
@@ -166,12 +175,15 @@ def cost(params, hb, states=None):
     return out
 
 
-def solve(params, hb, n_threads=1):
+def solve(params, hb, n_threads=1, analytic=False):
+    """ceres::Solve restated.  analytic=True: closed-form Jacobian of the scan-point factor instead of Jets (the faster CPU
+    baseline flavour; same minimiser)."""
     B, n = hb.n_windows, hb.n_frames
     states = np.zeros((B * n, 15))
     summ = np.zeros(B, dtype=abi.SUMMARY_DTYPE)
     s = hb.struct()
-    rc = lib().oracle_solve(C.byref(params), C.byref(s), _d(states), summ.ctypes.data_as(C.c_void_p), int(n_threads))
+    fn = lib().oracle_solve_analytic if analytic else lib().oracle_solve
+    rc = fn(C.byref(params), C.byref(s), _d(states), summ.ctypes.data_as(C.c_void_p), int(n_threads))
     assert rc == 0
     return states, summ
 

@@ -27,3 +27,18 @@ def test_reference_arm_under_a_multi_rank_launch_only_rank_zero_works():
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "0"],
                          capture_output=True, text=True, timeout=600, cwd=ROOT, env=env)
     assert out.returncode == 0 and out.stdout.strip() == ""
+
+
+def test_cpu_baseline_leg_reports_both_oracle_flavours(oracle):
+    """bench.py's cpu_baseline (the oracle on a bounded sample of the bench workload, one core) runs without a GPU."""
+    import sys as _sys
+
+    _sys.path.insert(0, ROOT)
+    import bench
+    import lvio2d_b200 as L
+
+    P = L.corridor_params(max_iters=10)
+    hb = oracle.preintegrate_batch(P, L.synth.make_batch(2, 42, n_frames=6, beams=361, fov_deg=270.0))
+    out = bench.cpu_baseline(P, hb, seconds=0.5, threads=1)
+    assert out["kind"] == "port" and out["cores"] == 1 and out["value"] > 0 and out["unit"] == "LM iterations/s"
+    assert out["analytic_jacobian_flavour"]["value"] > 0
