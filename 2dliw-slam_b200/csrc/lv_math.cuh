@@ -348,7 +348,6 @@ LV_HD void imu_raw_residual(const Consts& C, const double* blob, const double* s
 // Column `c` (0..29) of the un-whitened 15x30 Jacobian; columns follow the functor's parameter order
 // (p_i q_i v_i bs_i p_j q_j v_j bs_j).  Linear blocks in closed form, rotation blocks through Dual.
 LV_HD void imu_jacobian_column(const Consts& C, const double* blob, const double* si, const double* sj, int c, double* col /*[15]*/) {
-    const double* X = blob;
     const double* J = blob + 15;
     const double Dt = blob[465];
 #pragma unroll
