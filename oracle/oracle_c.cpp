@@ -13,6 +13,7 @@
 #include "laser_lines.hpp"
 #include "scan_points.hpp"
 #include "laser_match.hpp"
+#include "pose_graph.hpp"
 
 using namespace oracle;
 
@@ -287,6 +288,26 @@ int oracle_match_lines(const lvio2d_params* prm, const lvio2d_line_params* lp, i
             out[((size_t)p * max_lines2 + k) * 2 + 1] = pairs[k].second;
         }
     }
+    return 0;
+}
+// ---- back-end pose graph (keyframe_manager::solve; SURVEY section 8f rank 4 — oracle only, no device path yet)
+int oracle_eval_edge_factor(const double* tf12 /*3x4 row-major*/, double weight, const double* sqrt_info /*6x6*/, const double* pose_i,
+                            const double* pose_j, double* res, double* jac) {
+    posegraph::edge_factor fac{iso_from_rowmajor_3x4(tf12), weight, sqrt_info};
+    autodiff<6, 12>(fac, {pose_i, pose_i + 3, pose_j, pose_j + 3}, {3, 3, 3, 3}, res, jac,
+                    [](const posegraph::edge_factor& f, const Jet<12>* const* a, Jet<12>* r) { f(a[0], a[1], a[2], a[3], r); });
+    return 0;
+}
+int oracle_pose_graph_solve(const lvio2d_params* p, int32_t n_poses, double* poses /*[K][6] in/out*/, int32_t n_edges, const int32_t* edge_index,
+                            const double* edge_tf /*[E][12]*/, const double* edge_weight, const double* sqrt_info, int32_t ground_p,
+                            int32_t ground_q, lvio2d_summary* summary) {
+    Params P(*p);
+    posegraph::Graph G;
+    G.P = &P; G.K = n_poses; G.Jn = sqrt_info; G.ground_p = ground_p != 0; G.ground_q = ground_q != 0;
+    for (int e = 0; e < n_edges; ++e)
+        G.edges.push_back(posegraph::Edge{edge_index[2 * e], edge_index[2 * e + 1], iso_from_rowmajor_3x4(edge_tf + 12 * (size_t)e), edge_weight[e]});
+    const lvio2d_summary S = posegraph::solve(G, lm_options_from(*p), poses);
+    if (summary) *summary = S;
     return 0;
 }
 // the SVD restatement alone, for the numpy pin: smallest right singular vector of [x y 1]

@@ -296,9 +296,11 @@ inline LMOptions lm_options_from(const lvio2d_params& p) {
 
 // Ceres 1.14 TrustRegionMinimizer::Minimize with LevenbergMarquardtStrategy, jacobi_scaling = true,
 // monotonic steps, no inner iterations, no bounds, exact (direct) linear solver.
-inline lvio2d_summary lm_solve(const Params& P, const Window& W, const LMOptions& opt, double* x /* [n][15] in/out */) {
-    const int n = W.n, dim = 15 * n;
-    Evaluator ev(P, W, 0);
+// `Problem` supplies: int dim(); double evaluate(const double* x, Linearization* lin) (cost only when lin == nullptr);
+// void plus(const double* x, const double* delta, const std::vector<uint8_t>& free_col, double* out).
+template <class Problem>
+inline lvio2d_summary lm_minimize(const Problem& ev, const LMOptions& opt, double* x /* [dim] in/out */) {
+    const int dim = ev.dim();
     lvio2d_summary S;
     std::memset(&S, 0, sizeof(S));
     Linearization lin;
@@ -316,7 +318,7 @@ inline lvio2d_summary lm_solve(const Params& P, const Window& W, const LMOptions
         // |x - Plus(x, -g)|_inf  (TrustRegionMinimizer::EvaluateGradientAndJacobian)
         std::vector<double> neg(dim, 0.0), xp(dim);
         for (int c : idx) neg[c] = -L.g[c];
-        plus_states(x, neg.data(), lin.free_col, n, xp.data());
+        ev.plus(x, neg.data(), lin.free_col, xp.data());
         double mx = 0.0;
         for (int c : idx) mx = std::max(mx, std::fabs(x[c] - xp[c]));
         return mx;
@@ -380,7 +382,7 @@ inline lvio2d_summary lm_solve(const Params& P, const Window& W, const LMOptions
         num_consecutive_invalid = 0;
         std::fill(delta.begin(), delta.end(), 0.0);
         for (int a = 0; a < m; ++a) delta[idx[a]] = step[a] * scale[a];
-        plus_states(x, delta.data(), lin.free_col, n, xc.data());
+        ev.plus(x, delta.data(), lin.free_col, xc.data());
         double candidate_cost = ev.evaluate(xc.data(), nullptr);
         if (!std::isfinite(candidate_cost)) candidate_cost = std::numeric_limits<double>::max();
         // ParameterToleranceReached
@@ -411,6 +413,22 @@ inline lvio2d_summary lm_solve(const Params& P, const Window& W, const LMOptions
     S.final_cost = x_cost;
     S.final_radius = radius;
     return S;
+}
+
+// the sliding-window program (solver::solve / do_init_solve)
+struct WindowProblem {
+    Evaluator ev;
+    int n;
+    WindowProblem(const Params& P, const Window& W) : ev(P, W, 0), n(W.n) {}
+    int dim() const { return 15 * n; }
+    double evaluate(const double* x, Linearization* lin) const { return ev.evaluate(x, lin); }
+    void plus(const double* x, const double* delta, const std::vector<uint8_t>& free_col, double* out) const {
+        plus_states(x, delta, free_col, n, out);
+    }
+};
+inline lvio2d_summary lm_solve(const Params& P, const Window& W, const LMOptions& opt, double* x /* [n][15] in/out */) {
+    WindowProblem prob(P, W);
+    return lm_minimize(prob, opt, x);
 }
 
 // cyclic Jacobi eigen-decomposition of a symmetric n x n matrix; eigenvalues ascending (the order

@@ -27,7 +27,7 @@ def _d(a):
 
 
 def build(force=False):
-    srcs = ["oracle_c.cpp", "laser_lines.hpp", "scan_points.hpp", "laser_match.hpp", "solver.hpp", "factors.hpp", "preint.hpp", "lie.hpp", "jet.hpp"]
+    srcs = ["oracle_c.cpp", "laser_lines.hpp", "scan_points.hpp", "laser_match.hpp", "pose_graph.hpp", "solver.hpp", "factors.hpp", "preint.hpp", "lie.hpp", "jet.hpp"]
     newest = max(os.path.getmtime(os.path.join(_ROOT, "oracle", s)) for s in srcs)
     if force or not os.path.exists(_LIB_PATH) or os.path.getmtime(_LIB_PATH) < newest:
         subprocess.check_call(["make", "-C", os.path.join(_ROOT, "oracle"), "-s"])
@@ -250,6 +250,28 @@ def match_lines(params, lp, n_lines1, lines1, n_lines2, lines2, pose1, pose2, kk
                                   n2.ctypes.data_as(i32), _d(l2), _d(s1), _d(s2), nm.ctypes.data_as(i32), match.ctypes.data_as(i32))
     assert rc == 0
     return nm, match
+
+
+def eval_edge_factor(tf12, weight, sqrt_info, pose_i, pose_j):
+    """edge_factor (edge_factor.h:79-126): res[6], jac[6][12] over (p_i, q_i, p_j, q_j)."""
+    res, jac = np.zeros(6), np.zeros((6, 12))
+    lib().oracle_eval_edge_factor.argtypes = [dp, C.c_double, dp, dp, dp, dp, dp]
+    lib().oracle_eval_edge_factor(_d(_arr(tf12).reshape(-1)), float(weight), _d(_arr(sqrt_info).reshape(-1)), _d(_arr(pose_i)), _d(_arr(pose_j)),
+                                  _d(res), _d(jac))
+    return res, jac
+
+
+def pose_graph_solve(params, poses, edge_index, edge_tf, edge_weight, sqrt_info, ground_p=True, ground_q=True):
+    """keyframe_manager::solve (keyframe_manager.cpp:722-838): returns the optimised poses [K][6] and the summary."""
+    x = np.array(poses, dtype=np.float64).reshape(-1, 6).copy()
+    ei = np.ascontiguousarray(edge_index, dtype=np.int32).reshape(-1, 2)
+    et = _arr(edge_tf).reshape(-1, 12)
+    ew = _arr(edge_weight).reshape(-1)
+    summ = np.zeros(1, dtype=abi.SUMMARY_DTYPE)
+    rc = lib().oracle_pose_graph_solve(C.byref(params), len(x), _d(x), len(ei), ei.ctypes.data_as(abi.c_int32_p), _d(et), _d(ew),
+                                       _d(_arr(sqrt_info).reshape(-1)), int(ground_p), int(ground_q), summ.ctypes.data_as(C.c_void_p))
+    assert rc == 0
+    return x, summ
 
 
 def fit_line(points):
