@@ -13,6 +13,7 @@
 #include "../../include/lvio2d.h"
 #include "aux_kernels.cuh"
 #include "scan_lines.cuh"
+#include "pose_graph.cuh"
 
 using namespace lv;
 
@@ -88,6 +89,8 @@ struct lvio2d_ctx {
     DevBuf b_ln[14];   // lvio2d_extract_lines: inputs / workspace / outputs
     DevBuf b_sp[7];    // lvio2d_scan_to_points
     DevBuf b_ml[16];   // lvio2d_match_lines
+    DevBuf b_pg[2];    // lvio2d_pose_graph_solve: int arena, double arena
+    PinnedVec<double> h_pg;   // its per-iteration read-back (scalars + flags)
     double* ext_reduce = nullptr; int64_t ext_reduce_count = 0;
     int step_calls = 0;
     int window_threads = 0;   // 0 = automatic
@@ -507,6 +510,8 @@ void lvio2d_destroy(lvio2d_ctx* ctx) {
     for (auto& b : ctx->b_ln) b.release();
     for (auto& b : ctx->b_sp) b.release();
     for (auto& b : ctx->b_ml) b.release();
+    for (auto& b : ctx->b_pg) b.release();
+    ctx->h_pg.release();
     ctx->h_poff.release(); ctx->h_loff.release(); ctx->h_rf.release(); ctx->h_cm.release(); ctx->h_active.release(); ctx->h_active1.release();
     for (auto e : ctx->ev_scan) cudaEventDestroy(e);
     for (auto e : ctx->ev_win) cudaEventDestroy(e);
@@ -1051,4 +1056,129 @@ int lvio2d_eval_ground_factors(lvio2d_ctx* ctx, const double* pose, double* res,
     return eval_hook(ctx, in, len, 1, res, 2, jac, 12, 3);
 }
 
+}  // extern "C"
+
+// ---- back-end pose graph (pose_graph.cuh)
+namespace {
+struct PgDeviceLauncher {
+    lvio2d_ctx* ctx;
+    cudaError_t err = cudaSuccess;
+    template <int KID> bool go(const pg::Args& a) {
+        const int n = pg::kernel_threads(a, KID);
+        if (n <= 0) return true;
+        pg::pg_kernel<KID><<<(n + 127) / 128, 128, 0, ctx->stream>>>(a, n);
+        ctx->launches += 1;
+        return (err = cudaGetLastError()) == cudaSuccess;
+    }
+    bool run(int kid, const pg::Args& a) {
+        switch (kid) {
+            case pg::K_COLUMNS: return go<pg::K_COLUMNS>(a);
+            case pg::K_ASSEMBLE: return go<pg::K_ASSEMBLE>(a);
+            case pg::K_SCALE: return go<pg::K_SCALE>(a);
+            case pg::K_FACTOR: return go<pg::K_FACTOR>(a);
+            case pg::K_TRISOLVE: return go<pg::K_TRISOLVE>(a);
+            case pg::K_CAPACITANCE: return go<pg::K_CAPACITANCE>(a);
+            case pg::K_COMBINE: return go<pg::K_COMBINE>(a);
+            case pg::K_MODEL: return go<pg::K_MODEL>(a);
+            case pg::K_COST: return go<pg::K_COST>(a);
+        }
+        return false;
+    }
+    bool dense(const pg::Args& a) {
+        pg::pg_dense_kernel<<<1, 256, 0, ctx->stream>>>(a);
+        ctx->launches += 1;
+        return (err = cudaGetLastError()) == cudaSuccess;
+    }
+    bool reduce(const pg::Args& a) {
+        pg::pg_reduce_kernel<<<pg::S_COUNT, 256, 0, ctx->stream>>>(a);
+        ctx->launches += 1;
+        return (err = cudaGetLastError()) == cudaSuccess;
+    }
+    // the synchronisation point of an iteration: S_COUNT scalars + the two flags
+    bool read(const pg::Args& a, double* scal, int32_t* flags) {
+        double* h = ctx->h_pg.data();
+        if ((err = cudaMemcpyAsync(h, a.scal, sizeof(double) * pg::S_COUNT, cudaMemcpyDeviceToHost, ctx->stream)) != cudaSuccess) return false;
+        if ((err = cudaMemcpyAsync(h + pg::S_COUNT, a.flags, sizeof(int32_t) * 2, cudaMemcpyDeviceToHost, ctx->stream)) != cudaSuccess) return false;
+        if ((err = cudaStreamSynchronize(ctx->stream)) != cudaSuccess) return false;
+        std::memcpy(scal, h, sizeof(double) * pg::S_COUNT);
+        std::memcpy(flags, h + pg::S_COUNT, sizeof(int32_t) * 2);
+        return true;
+    }
+};
+
+// uploads the graph into the two arenas and binds every pointer of `a`
+int pg_setup(lvio2d_ctx* ctx, pg::Args& a, int32_t n_poses, const double* poses, int32_t n_edges, const int32_t* edge_index, const double* edge_tf,
+             const double* edge_weight, const double* sqrt_info, int32_t ground_p, int32_t ground_q, int fixed) {
+    std::vector<int32_t> ints;
+    std::memset(&a, 0, sizeof(a));
+    a.K = n_poses; a.E = n_edges;
+    if (!pg::pg_topology(n_poses, n_edges, edge_index, ints, &a.L)) return fail(ctx, LVIO2D_ERR_INVALID_ARG, "pose graph: edge index out of range or self edge");
+    a.fixed = fixed;
+    a.ground_p = ground_p != 0; a.ground_q = ground_q != 0;
+    a.C = ctx->C;
+    std::memcpy(a.Jn, sqrt_info, sizeof(a.Jn));
+    const size_t n_dbl = pg::pg_bind(a, nullptr, nullptr);
+    if (n_dbl > (size_t)16 << 27) return fail(ctx, LVIO2D_ERR_DOMAIN, "pose graph: work space above 16 GiB (too many loop edges x key frames)");
+    if (!ctx->b_pg[0].ensure(sizeof(int32_t) * ints.size()) || !ctx->b_pg[1].ensure(sizeof(double) * n_dbl)) return fail(ctx, LVIO2D_ERR_ALLOC, "cudaMalloc(pose graph)");
+    if (!ctx->h_pg.assign(pg::S_COUNT + 1, 0.0)) return fail(ctx, LVIO2D_ERR_ALLOC, "cudaHostAlloc(pose graph)");
+    pg::pg_bind(a, ctx->b_pg[0].as<int32_t>(), ctx->b_pg[1].as<double>());
+    CK(cudaMemsetAsync(ctx->b_pg[1].p, 0, sizeof(double) * n_dbl, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->b_pg[0].p, ints.data(), sizeof(int32_t) * ints.size(), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(const_cast<double*>(a.edge_tf), edge_tf, sizeof(double) * 12 * (size_t)n_edges, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(const_cast<double*>(a.edge_weight), edge_weight, sizeof(double) * (size_t)n_edges, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(a.x, poses, sizeof(double) * 6 * (size_t)n_poses, cudaMemcpyHostToDevice, ctx->stream));
+    // the host arrays above are pageable: the copies have consumed them when the calls return, `ints` included
+    CK(cudaStreamSynchronize(ctx->stream));
+    return LVIO2D_OK;
+}
+}  // namespace
+
+extern "C" {
+int lvio2d_pose_graph_solve(lvio2d_ctx* ctx, int32_t n_poses, double* poses, int32_t n_edges, const int32_t* edge_index, const double* edge_tf,
+                            const double* edge_weight, const double* sqrt_info, int32_t ground_p, int32_t ground_q, lvio2d_summary* summary) {
+    if (!ctx) return LVIO2D_ERR_INVALID_ARG;
+    if (n_poses <= 0 || n_edges < 0 || !poses || !sqrt_info || (n_edges > 0 && (!edge_index || !edge_tf || !edge_weight)))
+        return fail(ctx, LVIO2D_ERR_INVALID_ARG, "pose graph: null or empty argument");
+    for (int64_t i = 0; i < 6 * (int64_t)n_poses; ++i)
+        if (!std::isfinite(poses[i])) return fail(ctx, LVIO2D_ERR_DOMAIN, "pose graph: non-finite pose");
+    CK(cudaSetDevice(ctx->device));
+    pg::Args a;
+    const int rc = pg_setup(ctx, a, n_poses, poses, n_edges, edge_index, edge_tf, edge_weight, sqrt_info, ground_p, ground_q, n_edges > 0 ? edge_index[0] : -1);
+    if (rc != LVIO2D_OK) return rc;
+    pg::Options opt;
+    opt.max_iters = ctx->opt.max_iters; opt.function_tolerance = ctx->opt.function_tolerance; opt.gradient_tolerance = ctx->opt.gradient_tolerance;
+    opt.parameter_tolerance = ctx->opt.parameter_tolerance; opt.initial_radius = ctx->opt.initial_radius; opt.max_radius = ctx->opt.max_radius;
+    opt.min_radius = ctx->opt.min_radius; opt.min_relative_decrease = ctx->opt.min_relative_decrease; opt.min_lm_diagonal = ctx->opt.min_lm_diagonal;
+    opt.max_lm_diagonal = ctx->opt.max_lm_diagonal; opt.max_consecutive_invalid = ctx->opt.max_consecutive_invalid;
+    PgDeviceLauncher Lr{ctx};
+    lvio2d_summary S;
+    if (!pg::pg_minimize(Lr, a, opt, &S)) return fail(ctx, LVIO2D_ERR_CUDA, "pose graph kernel", Lr.err);
+    CK(cudaMemcpyAsync(poses, a.x, sizeof(double) * 6 * (size_t)n_poses, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (summary) *summary = S;
+    return LVIO2D_OK;
+}
+
+int lvio2d_eval_edge_factor(lvio2d_ctx* ctx, const double* tf12, double weight, const double* sqrt_info, const double* pose_i, const double* pose_j,
+                            double* res, double* jac) {
+    if (!ctx || !tf12 || !sqrt_info || !pose_i || !pose_j || !res || !jac) return LVIO2D_ERR_INVALID_ARG;
+    CK(cudaSetDevice(ctx->device));
+    double x[12];
+    std::memcpy(x, pose_i, sizeof(double) * 6);
+    std::memcpy(x + 6, pose_j, sizeof(double) * 6);
+    const int32_t idx[2] = {0, 1};
+    pg::Args a;
+    const int rc = pg_setup(ctx, a, 2, x, 1, idx, tf12, &weight, sqrt_info, 0, 0, -1);
+    if (rc != LVIO2D_OK) return rc;
+    PgDeviceLauncher Lr{ctx};
+    if (!Lr.run(pg::K_COLUMNS, a)) return fail(ctx, LVIO2D_ERR_CUDA, "pose graph kernel", Lr.err);
+    double EJ[78];
+    CK(cudaMemcpyAsync(EJ, a.EJ, sizeof(EJ), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    for (int r = 0; r < 6; ++r) {
+        res[r] = EJ[72 + r];
+        for (int c = 0; c < 12; ++c) jac[r * 12 + c] = EJ[c * 6 + r];
+    }
+    return LVIO2D_OK;
+}
 }  // extern "C"

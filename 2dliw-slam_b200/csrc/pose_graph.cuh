@@ -638,13 +638,14 @@ inline bool pg_topology(int K, int E, const int32_t* edge_index, VecI& ints, int
 inline size_t pg_bind(Args& a, int32_t* ints, double* dbl) {
     a.ncol = 1 + 6 * a.L;
     const size_t K = (size_t)a.K, E = (size_t)a.E, L = (size_t)a.L, nc = (size_t)a.ncol;
-    int32_t* ip = ints;
-    a.edge_index = ip; ip += 2 * E;
-    a.edge_band = ip; ip += E;
-    a.loop_edge = ip; ip += L;
-    a.inc_off = ip; ip += K + 1;
-    a.inc = ip; ip += 2 * E;
-    a.flags = ip;
+    size_t ioff = 0;
+    auto itake = [&](size_t n) { int32_t* p = ints ? ints + ioff : nullptr; ioff += n; return p; };
+    a.edge_index = itake(2 * E);
+    a.edge_band = itake(E);
+    a.loop_edge = itake(L);
+    a.inc_off = itake(K + 1);
+    a.inc = itake(2 * E);
+    a.flags = itake(2);
     size_t off = 0;
     auto take = [&](size_t n) { double* p = dbl ? dbl + off : nullptr; off += n; return p; };
     a.edge_tf = take(12 * E);

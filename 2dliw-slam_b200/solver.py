@@ -30,7 +30,7 @@ EXPORTS = [
     "lvio2d_set_reduce_buffer", "lvio2d_lm_step", "lvio2d_linearize", "lvio2d_marginalize", "lvio2d_imu_preintegrate",
     "lvio2d_wheel_preintegrate", "lvio2d_eval_laser_factor", "lvio2d_eval_imu_factor", "lvio2d_eval_wheel_factor",
     "lvio2d_eval_ground_factors", "lvio2d_set_profiling", "lvio2d_get_profile", "lvio2d_set_windows_async", "lvio2d_get_states_async",
-    "lvio2d_extract_lines", "lvio2d_scan_to_points", "lvio2d_match_lines",
+    "lvio2d_extract_lines", "lvio2d_scan_to_points", "lvio2d_match_lines", "lvio2d_pose_graph_solve", "lvio2d_eval_edge_factor",
 ]
 
 
@@ -91,6 +91,8 @@ def load_library(path=LIB_PATH):
                                        C.c_int32]
     lib.lvio2d_scan_to_points.argtypes = [vp, C.c_int32, C.c_int32, vp, vp, C.c_int32, abi.c_int32_p, dp, dp, dp, C.c_int32]
     lib.lvio2d_get_profile.argtypes = [vp, dp]
+    lib.lvio2d_pose_graph_solve.argtypes = [vp, C.c_int32, dp, C.c_int32, abi.c_int32_p, dp, dp, dp, C.c_int32, C.c_int32, vp]
+    lib.lvio2d_eval_edge_factor.argtypes = [vp, dp, C.c_double, dp, dp, dp, dp, dp]
     _lib = lib
     return lib
 
@@ -374,6 +376,31 @@ class Context:
         p = _f64(pose)
         self._check(self.lib.lvio2d_eval_ground_factors(self._h, _d(p), _d(res), _d(jac)), "lvio2d_eval_ground_factors")
         return res, jac
+
+    def eval_edge_factor(self, tf12, weight, sqrt_info, pose_i, pose_j):
+        """edge_factor (edge_factor.h:79-126): res[6], jac[6][12] over (p_i, q_i, p_j, q_j)."""
+        res, jac = np.zeros(6), np.zeros((6, 12))
+        a = [_f64(x).reshape(-1) for x in (tf12, sqrt_info, pose_i, pose_j)]
+        self._check(self.lib.lvio2d_eval_edge_factor(self._h, _d(a[0]), float(weight), _d(a[1]), _d(a[2]), _d(a[3]), _d(res), _d(jac)),
+                    "lvio2d_eval_edge_factor")
+        return res, jac
+
+    def pose_graph_solve(self, poses, edge_index, edge_tf, edge_weight, sqrt_info, ground_p=True, ground_q=True):
+        """keyframe_manager::solve (keyframe_manager.cpp:722-838) on the device: returns (poses [K][6], summary)."""
+        x = np.array(poses, dtype=np.float64).reshape(-1, 6).copy()
+        ei = np.ascontiguousarray(edge_index, dtype=np.int32).reshape(-1, 2)
+        et = _f64(edge_tf).reshape(-1, 12)
+        ew = _f64(edge_weight).reshape(-1)
+        if len(et) != len(ei) or len(ew) != len(ei):
+            raise ValueError("edge_index, edge_tf and edge_weight must describe the same number of edges")
+        Jn = _f64(sqrt_info).reshape(-1)
+        if Jn.size != 36:
+            raise ValueError("sqrt_info is edge_noise::J, 6x6")
+        summ = np.zeros(1, dtype=abi.SUMMARY_DTYPE)
+        self._check(self.lib.lvio2d_pose_graph_solve(self._h, len(x), _d(x), len(ei), ei.ctypes.data_as(abi.c_int32_p), _d(et), _d(ew), _d(Jn),
+                                                     int(bool(ground_p)), int(bool(ground_q)), summ.ctypes.data_as(C.c_void_p)),
+                    "lvio2d_pose_graph_solve")
+        return x, summ
 
 
 # ------------------------------------------------------------------------------------------------------

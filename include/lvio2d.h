@@ -321,6 +321,26 @@ int lvio2d_match_lines(lvio2d_ctx* ctx, const lvio2d_line_params* lp, int32_t n_
                        int32_t max_lines2, const int32_t* n_lines2, const double* lines2,
                        const double* pose1, const double* pose2, int32_t* n_match, int32_t* match, int32_t on_device);
 
+/* ---- back-end pose graph.  Replaces keyframe_manager::solve
+ * (src/trajectory/keyframe_manager.cpp:722-838): one ceres::Problem over the key-frame poses (p, q) with an edge_factor
+ * (src/factor/edge_factor.h:79-126) per sequential and per loop edge, ground_factor_p / ground_factor_q on every key
+ * frame (use_ground_p_factor / use_ground_q_factor), the first edge's index1 held constant (:744-748), ceres::Solve
+ * with default options (LM, exact linear solve; the iteration cap and tolerances are the context's lvio2d_params —
+ * give the back-end its own context, it runs on its own thread in the reference, keyframe_manager.cpp:91).
+ * poses: [n_poses][6] (p, q angle-axis), in/out, host memory.  edge_index: [n_edges][2] = (index1, index2), any order;
+ * edges between neighbours (|index1 - index2| = 1) form the block-tridiagonal part, all others (loop_edges) enter as
+ * rank-6 updates.  edge_tf: [n_edges][12] tf12 row-major 3x4.  edge_weight: [n_edges] (1 for seq_edges, loop_edge_k
+ * for loop_edges, :734, :780).  sqrt_info: edge_noise::J row-major 6x6 (edge_factor.h:14-26; the caller builds it,
+ * including the reference's J(1,2) slip if it wants the reference's numbers).  LVIO2D_ERR_INVALID_ARG for an index
+ * out of range or a self edge. ---- */
+int lvio2d_pose_graph_solve(lvio2d_ctx* ctx, int32_t n_poses, double* poses, int32_t n_edges, const int32_t* edge_index,
+                            const double* edge_tf, const double* edge_weight, const double* sqrt_info, int32_t ground_p,
+                            int32_t ground_q, lvio2d_summary* summary);
+/* edge_factor through auto_diff::compute_res_and_jacobi (common.h:201-217): res[6], jac[6][12] row-major over
+ * (p_i, q_i, p_j, q_j). */
+int lvio2d_eval_edge_factor(lvio2d_ctx* ctx, const double* tf12, double weight, const double* sqrt_info,
+                            const double* pose_i, const double* pose_j, double* res, double* jac);
+
 #ifdef __cplusplus
 }
 #endif

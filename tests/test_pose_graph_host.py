@@ -73,7 +73,8 @@ def graph_with_loops(K, loops, seed):
 
 
 @pytest.mark.parametrize("K,loops,ground_q,iters", [(24, [], False, 50), (24, [], True, 12), (40, [(30, 4), (12, 25), (39, 20)], False, 50),
-                                                     (40, [(30, 4), (12, 25), (39, 20)], True, 12), (3, [], False, 50)])
+                                                     (40, [(30, 4), (12, 25), (39, 20)], True, 12), (3, [], False, 50),
+                                                     (200, [(190, 3), (100, 20), (150, 40), (199, 80), (60, 160)], False, 50)])
 def test_host_run_of_the_device_solve_matches_oracle(pgh, consts, oracle, K, loops, ground_q, iters):
     """With ground_q the minimum sits on the kink of asin(|z x e_z|) (reference quirk) and LM crawls along it: rounding
     differences between two correct implementations grow from 1e-13 (12 iterations) to 1e-3 m (50 iterations), so the
@@ -118,3 +119,30 @@ def test_invalid_graph_is_rejected(pgh, consts):
     rc = pgh.pgh_solve(C.byref(consts), d(opt), len(x), d(x), len(bad), bad.ctypes.data_as(C.POINTER(C.c_int32)), d(tfs.reshape(-1).copy()),
                        d(ws.copy()), d(edge_noise_J().reshape(-1).copy()), 1, 1, summ.ctypes.data_as(C.c_void_p), None)
     assert rc == -1
+
+
+def test_keyframe_manager_mirror_on_a_recording_context():
+    """Host bookkeeping of backend.KeyframeManager.solve (edge order: seq edges first so that seq edge 0's index1 is the
+    constant key frame; weights 1 / loop_edge_k; in-place write-back) — the compute call is recorded, not executed."""
+    from lvio2d_b200.backend import Edge, KeyFrame, KeyframeManager, edge_noise_J as product_J
+
+    calls = []
+
+    class Recorder:
+        def pose_graph_solve(self, poses, index, tfs, weights, Jn, gp, gq):
+            calls.append((poses.copy(), index.copy(), tfs.copy(), weights.copy(), Jn.copy(), gp, gq))
+            return poses + 1.0, np.zeros(1, dtype=abi.SUMMARY_DTYPE)
+
+    km = KeyframeManager(Recorder(), loop_edge_k=7.0, use_ground_q_factor=False)
+    km.solve()                      # empty queue: nothing to do
+    assert not calls
+    km.keyframe_queue = [KeyFrame(np.full(3, float(k)), np.full(3, 0.1 * k)) for k in range(4)]
+    km.seq_edges = [Edge(k, k + 1, np.eye(4)) for k in range(3)]
+    km.loop_edges = [Edge(3, 0, np.eye(4)[:3])]
+    km.solve()
+    poses, index, tfs, weights, Jn, gp, gq = calls[0]
+    assert index.tolist() == [[0, 1], [1, 2], [2, 3], [3, 0]] and index.dtype == np.int32
+    assert weights.tolist() == [1.0, 1.0, 1.0, 7.0] and tfs.shape == (4, 3, 4)
+    assert (gp, gq) == (True, False)
+    assert np.array_equal(Jn, edge_noise_J()) and np.array_equal(Jn, product_J((0.1,) * 3, (0.01,) * 3))
+    assert np.array_equal(km.keyframe_queue[2].p, np.full(3, 3.0)) and np.allclose(km.keyframe_queue[2].q, 1.2)

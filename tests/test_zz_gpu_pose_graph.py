@@ -1,0 +1,103 @@
+"""GPU parity of lvio2d_pose_graph_solve / lvio2d_eval_edge_factor (back-end pose graph)
+against the CPU oracle of keyframe_manager::solve (oracle/pose_graph.hpp), through the C ABI.
+
+STATUS: written after the round's GPU minutes were spent — the kernels are cross-compiled for sm_100a and their bodies
+are verified on the CPU against the oracle (tests/test_pose_graph_host.py runs the same `__host__ __device__` bodies
+thread by thread under the same minimiser loop), but this file has not yet run on a B200.  Until it has, the tests are
+xfail(strict=False) (a pass shows up as XPASS) and the file sorts last so that a fault here cannot disturb the verified
+parity tests.  Tolerances: residual 1e-12, Jacobian 1e-9 relative, poses 1e-6 m / rad on smooth problems (north star:
+1e-4), cost 1e-6 relative; see test_pose_graph_host.py for why the kinked problem (ground_q) is compared after 12
+iterations and only bounded after 50."""
+import numpy as np
+import pytest
+
+import lvio2d_b200 as L
+from test_oracle_pose_graph import T_of, edge_noise_J
+from test_pose_graph_host import graph_with_loops
+
+pytestmark = [pytest.mark.gpu, pytest.mark.xfail(strict=False, reason="device path not yet confirmed on a B200 (GPU budget of round 1 spent)")]
+
+
+def make_ctx(**kw):
+    from lvio2d_b200.solver import Context
+
+    return Context(L.corridor_params(**kw))
+
+
+def test_edge_factor_matches_oracle(oracle):
+    g = np.random.default_rng(3)
+    Jn = edge_noise_J()
+    with make_ctx() as ctx:
+        for case in range(20):
+            pi, pj = np.r_[g.uniform(-5, 5, 3), g.normal(0, 0.5, 3)], np.r_[g.uniform(-5, 5, 3), g.normal(0, 0.5, 3)]
+            noise = np.r_[g.normal(0, 0.05, 3), g.normal(0, 0.02, 3)] * (1e-4 if case % 2 else 1.0)
+            tf12 = np.ascontiguousarray((np.linalg.inv(T_of(pi)) @ T_of(pj) @ T_of(noise))[:3, :])
+            w = g.uniform(0.5, 10.0)
+            res, jac = ctx.eval_edge_factor(tf12, w, Jn, pi, pj)
+            want_r, want_J = oracle.eval_edge_factor(tf12, w, Jn, pi, pj)
+            np.testing.assert_allclose(res, want_r, rtol=0, atol=1e-12 * max(1.0, np.abs(want_r).max()))
+            np.testing.assert_allclose(jac, want_J, rtol=0, atol=1e-9 * np.abs(want_J).max())
+
+
+@pytest.mark.parametrize("K,loops,ground_q,iters", [(24, [], False, 50), (24, [], True, 12), (40, [(30, 4), (12, 25), (39, 20)], False, 50),
+                                                     (40, [(30, 4), (12, 25), (39, 20)], True, 12), (3, [], False, 50),
+                                                     (200, [(190, 3), (100, 20), (150, 40), (199, 80), (60, 160)], False, 50)])
+def test_pose_graph_solve_matches_oracle(oracle, K, loops, ground_q, iters):
+    P = L.corridor_params(max_iters=iters)
+    truth, init, edges, tfs, ws = graph_with_loops(K, loops, seed=4 + K)
+    if K == 3:
+        edges, tfs, ws = edges[:2], tfs[:2], ws[:2]
+    Jn = edge_noise_J()
+    want, ws_summ = oracle.pose_graph_solve(P, init, edges, tfs, ws, Jn, ground_p=True, ground_q=ground_q)
+    with make_ctx(max_iters=iters) as ctx:
+        got, summ = ctx.pose_graph_solve(init, edges, tfs, ws, Jn, True, ground_q)
+    assert summ["termination"][0] == ws_summ["termination"][0]
+    assert abs(int(summ["iterations"][0]) - int(ws_summ["iterations"][0])) <= 1
+    assert abs(summ["initial_cost"][0] - ws_summ["initial_cost"][0]) <= 1e-9 * ws_summ["initial_cost"][0]
+    assert abs(summ["final_cost"][0] - ws_summ["final_cost"][0]) <= 1e-6 * max(1.0, ws_summ["final_cost"][0])
+    assert np.array_equal(got[edges[0][0]], init[edges[0][0]])
+    assert np.abs(got - want).max() < 1e-6
+
+
+def test_kinked_problem_after_50_iterations(oracle):
+    P = L.corridor_params(max_iters=50)
+    truth, init, edges, tfs, ws = graph_with_loops(40, [(30, 4), (12, 25), (39, 20)], seed=44)
+    Jn = edge_noise_J()
+    want, ws_summ = oracle.pose_graph_solve(P, init, edges, tfs, ws, Jn)
+    with make_ctx(max_iters=50) as ctx:
+        got, summ = ctx.pose_graph_solve(init, edges, tfs, ws, Jn)
+    assert summ["iterations"][0] == 50 and summ["final_cost"][0] < 1e-2 * summ["initial_cost"][0]
+    assert summ["final_cost"][0] < 2.0 * ws_summ["final_cost"][0]
+    assert np.abs(got - want).max() < 5e-3
+
+
+def test_errors_are_reported():
+    from lvio2d_b200 import abi
+    from lvio2d_b200.solver import Lvio2dError
+
+    truth, init, edges, tfs, ws = graph_with_loops(6, [], seed=1)
+    bad = edges.copy()
+    bad[2] = (3, 3)
+    with make_ctx() as ctx:
+        with pytest.raises(Lvio2dError) as e:
+            ctx.pose_graph_solve(init, bad, tfs, ws, edge_noise_J())
+        assert e.value.status == abi.ERR_INVALID_ARG
+        bad[2] = (3, 99)
+        with pytest.raises(Lvio2dError):
+            ctx.pose_graph_solve(init, bad, tfs, ws, edge_noise_J())
+
+
+def test_keyframe_manager_mirror_writes_back_in_place(oracle):
+    from lvio2d_b200.backend import Edge, KeyFrame, KeyframeManager
+
+    P = L.corridor_params(max_iters=50)
+    truth, init, edges, tfs, ws = graph_with_loops(24, [], seed=28)
+    with make_ctx(max_iters=50) as ctx:
+        km = KeyframeManager(ctx, use_ground_q_factor=False)
+        km.keyframe_queue = [KeyFrame(x[0:3].copy(), x[3:6].copy()) for x in init]
+        km.seq_edges = [Edge(int(i), int(j), tf) for (i, j), tf in zip(edges[:-1], tfs[:-1])]
+        km.loop_edges = [Edge(int(edges[-1][0]), int(edges[-1][1]), tfs[-1])]
+        km.solve()
+    want, _ = oracle.pose_graph_solve(P, init, edges, tfs, ws, edge_noise_J(), ground_p=True, ground_q=False)
+    got = np.array([np.r_[kf.p, kf.q] for kf in km.keyframe_queue])
+    assert np.abs(got - want).max() < 1e-6
