@@ -1075,7 +1075,6 @@ struct PgDeviceLauncher {
             case pg::K_COLUMNS: return go<pg::K_COLUMNS>(a);
             case pg::K_ASSEMBLE: return go<pg::K_ASSEMBLE>(a);
             case pg::K_SCALE: return go<pg::K_SCALE>(a);
-            case pg::K_FACTOR: return go<pg::K_FACTOR>(a);
             case pg::K_TRISOLVE: return go<pg::K_TRISOLVE>(a);
             case pg::K_CAPACITANCE: return go<pg::K_CAPACITANCE>(a);
             case pg::K_COMBINE: return go<pg::K_COMBINE>(a);
@@ -1083,6 +1082,11 @@ struct PgDeviceLauncher {
             case pg::K_COST: return go<pg::K_COST>(a);
         }
         return false;
+    }
+    bool factor(const pg::Args& a) {
+        pg::pg_factor_kernel<<<1, 64, 0, ctx->stream>>>(a);
+        ctx->launches += 1;
+        return (err = cudaGetLastError()) == cudaSuccess;
     }
     bool dense(const pg::Args& a) {
         pg::pg_dense_kernel<<<1, 256, 0, ctx->stream>>>(a);

@@ -10,13 +10,13 @@
 // Structure of the normal equations.  Key frames are 6-DoF nodes; an edge between neighbours (|i - j| = 1, the
 // reference's seq_edges) puts a 6x6 block on the first off-diagonal, every other edge (loop_edges) is a rank-6 update:
 //     H + D_lm = T + U U^T,   T block-tridiagonal (band edges + ground factors + LM diagonal),   U = [J_e^T]_{e in loops}
-// so one LM step is  (1) a block-tridiagonal Cholesky of T,  (2) T^-1 [-g | U] for 1 + 6L right-hand sides (one thread
+// so one LM step is  (1) a block-tridiagonal factorisation of T (one CTA, 36 threads = one 6x6 block, sequential in k),  (2) T^-1 [-g | U] for 1 + 6L right-hand sides (one thread
 // each),  (3) the 6L x 6L capacitance system  (I + U^T T^-1 U) w = U^T T^-1 (-g)  (one CTA),  (4) delta = x0 - Z w.
 // Nothing dense of size 6K is ever formed; the solve is exact (as the reference's SPARSE_SCHUR is), not iterative.
 //
 // How the code is organised.  Every kernel is `thread t of n runs pg_thread<KID>(args, t)` with no intra-block
-// communication; the only two cooperative kernels (the dense capacitance Cholesky and the reduction of the per-item
-// partial sums) are written as phases separated by __syncthreads.  The bodies are __host__ __device__, so the CPU test
+// communication; the cooperative kernels (the block-tridiagonal factorisation, the dense capacitance Cholesky and the
+// reduction of the per-item partial sums) are written as phases separated by __syncthreads.  The bodies are __host__ __device__, so the CPU test
 // suite (tests/native/pose_graph_host.cpp) runs the SAME bodies and the SAME minimiser loop (pg_minimize) thread by
 // thread and checks them against the oracle — a formula / control-flow check without a GPU, not a fallback: the product
 // entry point (lvio2d_pose_graph_solve, lvio2d_api.cu) only ever launches the kernels.
@@ -36,7 +36,7 @@
 namespace lv {
 namespace pg {
 
-enum Kernel { K_COLUMNS = 0, K_ASSEMBLE, K_SCALE, K_FACTOR, K_TRISOLVE, K_CAPACITANCE, K_COMBINE, K_MODEL, K_COST };
+enum Kernel { K_COLUMNS = 0, K_ASSEMBLE, K_SCALE, K_TRISOLVE, K_CAPACITANCE, K_COMBINE, K_MODEL, K_COST };
 enum Scalar { S_COST = 0, S_YNORM, S_STEP, S_MODEL, S_DG, S_GRAD, S_COUNT };
 
 struct Options {
@@ -84,6 +84,22 @@ struct Args {
     double* scal;    // [S_COUNT]
     int32_t* flags;  // [2] non-positive pivot in the tridiagonal / capacitance factorisation
 };
+
+// read-only (non-coherent) load and L1 prefetch on the device, plain load / nothing on the host
+LV_HD double lv_ldg(const double* p) {
+#if defined(__CUDA_ARCH__)
+    return __ldg(p);
+#else
+    return *p;
+#endif
+}
+LV_HD void lv_prefetch(const void* p) {
+#if defined(__CUDA_ARCH__)
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+#else
+    (void)p;
+#endif
+}
 
 LV_HD int part_count(const Args& a, int q) { return (q == S_COST || q == S_MODEL) ? a.E + a.K : a.K; }
 LV_HD int part_offset(const Args& a, int q) {
@@ -151,42 +167,6 @@ LV_HD void ground_column(const Args& a, int k, int c, double* out /*[2]*/) {
     }
     out[0] = a.ground_p ? rp : 0.0;
     out[1] = a.ground_q ? rq : 0.0;
-}
-
-// ------------------------------------------------------------------ 6x6 SPD inverse (Cholesky), row-major
-LV_HD bool spd_inverse6(const double* S, double* Sinv) {
-    double Lm[36], Li[36];
-    bool ok = true;
-    for (int i = 0; i < 36; ++i) { Lm[i] = 0.0; Li[i] = 0.0; }
-    for (int j = 0; j < 6; ++j) {
-        double d = S[j * 6 + j];
-        for (int k = 0; k < j; ++k) d -= Lm[j * 6 + k] * Lm[j * 6 + k];
-        if (!(d > 0.0)) { ok = false; d = 1.0; }
-        const double piv = sqrt(d);
-        Lm[j * 6 + j] = piv;
-        for (int i = j + 1; i < 6; ++i) {
-            double s = S[i * 6 + j];
-            for (int k = 0; k < j; ++k) s -= Lm[i * 6 + k] * Lm[j * 6 + k];
-            Lm[i * 6 + j] = s / piv;
-        }
-    }
-    // Li = L^-1 (lower)
-    for (int c = 0; c < 6; ++c) {
-        for (int i = c; i < 6; ++i) {
-            double s = (i == c) ? 1.0 : 0.0;
-            for (int k = c; k < i; ++k) s -= Lm[i * 6 + k] * Li[k * 6 + c];
-            Li[i * 6 + c] = s / Lm[i * 6 + i];
-        }
-    }
-    // S^-1 = L^-T L^-1
-    for (int r = 0; r < 6; ++r)
-        for (int c = 0; c <= r; ++c) {
-            double s = 0.0;
-            for (int k = r; k < 6; ++k) s += Li[k * 6 + r] * Li[k * 6 + c];
-            Sinv[r * 6 + c] = s;
-            Sinv[c * 6 + r] = s;
-        }
-    return ok;
 }
 
 // ------------------------------------------------------------------ kernel bodies: thread t of n
@@ -262,43 +242,78 @@ LV_HD void body_assemble(const Args& a, int k) {
 }
 // K_SCALE, n = 6K: jacobi scaling 1 / (1 + sqrt(diag(J^T J))), taken once at iteration 0
 LV_HD void body_scale(const Args& a, int c) { a.scale[c] = 1.0 / (1.0 + sqrt(a.Hd[c])); }
-// K_FACTOR, n = 1: block-tridiagonal Cholesky of T = band(H) + LM diagonal, as inverse pivots + multipliers
-LV_HD void body_factor(const Args& a, int) {
-    bool ok = true;
-    double S[36], Sp[36], Mk[36];
-    for (int k = 0; k < a.K; ++k) {
-        for (int q = 0; q < 36; ++q) S[q] = a.D[(size_t)k * 36 + q];
-        if (k != a.fixed) {
-            for (int q = 0; q < 6; ++q) {
-                const double s = a.scale[6 * k + q], hs = a.Hd[6 * k + q] * s * s;
-                const double d = fmin(fmax(hs, a.min_lm), a.max_lm);
-                S[q * 6 + q] += d / a.radius / (s * s);   // the scaled system's diagonal / radius, back in unscaled columns
-            }
-        }
-        if (k > 0) {
-            const double* B = a.O + (size_t)(k - 1) * 36;   // block (k, k-1)
-            for (int r = 0; r < 6; ++r)
-                for (int c = 0; c < 6; ++c) {
-                    double s = 0.0;
-                    for (int i = 0; i < 6; ++i) s += B[r * 6 + i] * Sp[i * 6 + c];
-                    Mk[r * 6 + c] = s;
-                }
-            for (int r = 0; r < 6; ++r)
-                for (int c = 0; c < 6; ++c) {
-                    double s = 0.0;
-                    for (int i = 0; i < 6; ++i) s += Mk[r * 6 + i] * B[c * 6 + i];
-                    S[r * 6 + c] -= s;
-                }
-            for (int q = 0; q < 36; ++q) a.M[(size_t)k * 36 + q] = Mk[q];
-        } else {
-            for (int q = 0; q < 36; ++q) a.M[q] = 0.0;
-        }
-        ok = spd_inverse6(S, Sp) && ok;
-        for (int q = 0; q < 36; ++q) a.Sinv[(size_t)k * 36 + q] = Sp[q];
-    }
-    a.flags[0] = ok ? 0 : 1;
+// the block-tridiagonal factorisation of T = band(H) + LM diagonal, one CTA of 36 working threads (one per entry of a
+// 6x6 block), sequential over the key frames, as phases with a __syncthreads between them:
+//     S_k = D_k + lm_k - M_k B_k^T,   M_k = B_k S_{k-1}^-1,   B_k = block (k, k-1);   stores S_k^-1 and M_k.
+// The inverse is a Gauss-Jordan sweep without pivoting (S_k is SPD; its pivots are the squares of the Cholesky ones, so
+// "pivot <= 0" is the same not-positive-definite test), ping-ponging between two copies of [S | Inv] so that a sweep
+// step is one phase.  Every phase reads what earlier phases wrote and writes only its own entry t (of arrays no thread
+// reads in that phase), so running the 36 threads of a phase one after the other (CPU check) is equivalent.
+// The operands of step k + 1 (D, B, diag(H), scale) are fetched while step k runs (factor_fetch / factor_stage).
+struct FactorTile { double S[2][36], Inv[2][36], Sp[36], Mk[36], B[36], nD[36], nO[36], nHd[6], nSc[6]; int ok; };
+struct FactorNext { double D, O, Hd, Sc; };
+enum { FACTOR_PHASES = 9, FACTOR_THREADS = 36 };
+LV_HD FactorNext factor_fetch(const Args& a, int k, int t) {
+    FactorNext n;
+    n.D = a.D[(size_t)k * 36 + t];
+    n.O = k > 0 ? a.O[(size_t)(k - 1) * 36 + t] : 0.0;
+    n.Hd = t < 6 ? a.Hd[6 * k + t] : 0.0;
+    n.Sc = t < 6 ? a.scale[6 * k + t] : 1.0;
+    return n;
 }
-// K_TRISOLVE, n = ncol: T z = b for one right-hand side (0: -g, 1 + 6l + rho: row rho of loop edge l's Jacobian)
+LV_HD void factor_stage(FactorTile& T, int t, const FactorNext& n) {
+    T.nD[t] = n.D;
+    T.nO[t] = n.O;
+    if (t < 6) { T.nHd[t] = n.Hd; T.nSc[t] = n.Sc; }
+}
+LV_HD void factor_phase(const Args& a, FactorTile& T, int k, int phase, int t) {
+    const int r = t / 6, c = t % 6;
+    if (phase == 0) {
+        double v = T.nD[t];
+        if (r == c && k != a.fixed) {
+            const double s = T.nSc[r], hs = T.nHd[r] * s * s;
+            const double d = fmin(fmax(hs, a.min_lm), a.max_lm);
+            v += d / a.radius / (s * s);   // the scaled system's diagonal / radius, back in unscaled columns
+        }
+        T.S[0][t] = v;
+        T.B[t] = T.nO[t];
+        T.Inv[0][t] = (r == c) ? 1.0 : 0.0;
+        if (t == 0 && k == 0) T.ok = 1;
+    } else if (phase == 1) {
+        double m = 0.0;
+        if (k > 0)
+            for (int i = 0; i < 6; ++i) m += T.B[r * 6 + i] * T.Sp[i * 6 + c];
+        T.Mk[t] = m;
+        a.M[(size_t)k * 36 + t] = m;
+    } else if (phase == 2) {
+        if (k > 0) {
+            double s = 0.0;
+            for (int i = 0; i < 6; ++i) s += T.Mk[r * 6 + i] * T.B[c * 6 + i];
+            T.S[0][t] -= s;
+        }
+    } else {
+        const int j = phase - 3, src = j & 1, dst = src ^ 1;
+        double p = T.S[src][j * 6 + j];
+        if (!(p > 0.0)) { if (t == 0) T.ok = 0; p = 1.0; }
+        const double ip = 1.0 / p;
+        const double sj = T.S[src][j * 6 + c] * ip, ij = T.Inv[src][j * 6 + c] * ip;
+        double ns, ni;
+        if (r == j) { ns = sj; ni = ij; }
+        else { const double f = T.S[src][r * 6 + j]; ns = T.S[src][t] - f * sj; ni = T.Inv[src][t] - f * ij; }
+        T.S[dst][t] = ns;
+        T.Inv[dst][t] = ni;
+        if (j == 5) {   // dst == 0: the inverse is complete
+            T.Sp[t] = ni;
+            a.Sinv[(size_t)k * 36 + t] = ni;
+        }
+    }
+}
+// K_TRISOLVE, n = ncol: T z = b for one right-hand side (0: -g, 1 + 6l + rho: row rho of loop edge l's Jacobian).
+// Sequential in k per thread; the chain only carries 6 doubles, so the cost of a step is the latency of fetching
+// M_k / Sinv_k: they are read through the read-only path (free to move above the Z stores) and prefetched PG_AHEAD
+// steps ahead.  Measured (profiles/r1_pose_graph.md): still 1.5 us per step and sweep — ptxas keeps only 8 of the 36
+// loads of a block in flight and they are served by L2; round 2 stages the blocks of 16 steps in shared memory.
+#define PG_AHEAD 4
 LV_HD void body_trisolve(const Args& a, int col) {
     int e = -1, rho = 0, ie = -1, je = -1;
     if (col > 0) {
@@ -310,37 +325,60 @@ LV_HD void body_trisolve(const Args& a, int col) {
     const double* J = e >= 0 ? a.EJ + (size_t)e * 78 : nullptr;
     double yp[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0}, b[6];
     for (int k = 0; k < a.K; ++k) {
+        if (k + PG_AHEAD < a.K) {
+            const double* Mp = a.M + (size_t)(k + PG_AHEAD) * 36;
+            lv_prefetch(Mp); lv_prefetch(Mp + 16); lv_prefetch(Mp + 32);
+            if (col == 0) lv_prefetch(a.g + 6 * (k + PG_AHEAD));
+        }
+#pragma unroll
         for (int q = 0; q < 6; ++q) {
-            if (col == 0) b[q] = -a.g[6 * k + q];
+            if (col == 0) b[q] = -lv_ldg(a.g + 6 * k + q);
             else b[q] = (k == ie) ? J[q * 6 + rho] : ((k == je) ? J[36 + q * 6 + rho] : 0.0);
         }
         if (k > 0) {
             const double* Mk = a.M + (size_t)k * 36;
+#pragma unroll
             for (int q = 0; q < 6; ++q) {
                 double s = 0.0;
-                for (int i = 0; i < 6; ++i) s += Mk[q * 6 + i] * yp[i];
+#pragma unroll
+                for (int i = 0; i < 6; ++i) s += lv_ldg(Mk + q * 6 + i) * yp[i];
                 b[q] -= s;
             }
         }
+#pragma unroll
         for (int q = 0; q < 6; ++q) { yp[q] = b[q]; a.Z[(size_t)(6 * k + q) * a.ncol + col] = b[q]; }
     }
     double xn[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
     for (int k = a.K - 1; k >= 0; --k) {
+        if (k - PG_AHEAD >= 0) {
+            const double* Sp = a.Sinv + (size_t)(k - PG_AHEAD) * 36;
+            lv_prefetch(Sp); lv_prefetch(Sp + 16); lv_prefetch(Sp + 32);
+            const double* Mp = a.M + (size_t)(k - PG_AHEAD + 1) * 36;
+            lv_prefetch(Mp); lv_prefetch(Mp + 16); lv_prefetch(Mp + 32);
+#pragma unroll
+            for (int q = 0; q < 6; ++q) lv_prefetch(a.Z + (size_t)(6 * (k - PG_AHEAD) + q) * a.ncol + col);
+        }
         const double* Si = a.Sinv + (size_t)k * 36;
+#pragma unroll
         for (int q = 0; q < 6; ++q) yp[q] = a.Z[(size_t)(6 * k + q) * a.ncol + col];
+#pragma unroll
         for (int q = 0; q < 6; ++q) {
             double s = 0.0;
-            for (int i = 0; i < 6; ++i) s += Si[q * 6 + i] * yp[i];
+#pragma unroll
+            for (int i = 0; i < 6; ++i) s += lv_ldg(Si + q * 6 + i) * yp[i];
             b[q] = s;
         }
         if (k < a.K - 1) {
             const double* Mn = a.M + (size_t)(k + 1) * 36;
+#pragma unroll
             for (int q = 0; q < 6; ++q) {
                 double s = 0.0;
-                for (int i = 0; i < 6; ++i) s += Mn[i * 6 + q] * xn[i];
+#pragma unroll
+                for (int i = 0; i < 6; ++i) s += lv_ldg(Mn + i * 6 + q) * xn[i];
                 b[q] -= s;
             }
         }
+#pragma unroll
         for (int q = 0; q < 6; ++q) { xn[q] = b[q]; a.Z[(size_t)(6 * k + q) * a.ncol + col] = b[q]; }
     }
 }
@@ -458,7 +496,6 @@ template <int KID> LV_HD void pg_thread(const Args& a, int t) {
     if (KID == K_COLUMNS) body_columns(a, t);
     else if (KID == K_ASSEMBLE) body_assemble(a, t);
     else if (KID == K_SCALE) body_scale(a, t);
-    else if (KID == K_FACTOR) body_factor(a, t);
     else if (KID == K_TRISOLVE) body_trisolve(a, t);
     else if (KID == K_CAPACITANCE) body_capacitance(a, t);
     else if (KID == K_COMBINE) body_combine(a, t);
@@ -470,7 +507,6 @@ LV_HD int kernel_threads(const Args& a, int kid) {
         case K_COLUMNS: return 13 * a.E + 7 * a.K;
         case K_ASSEMBLE: case K_COMBINE: return a.K;
         case K_SCALE: return 6 * a.K;
-        case K_FACTOR: return 1;
         case K_TRISOLVE: return a.ncol;
         case K_CAPACITANCE: return 6 * a.L * a.ncol;
         default: return a.E + a.K;
@@ -481,6 +517,25 @@ LV_HD int kernel_threads(const Args& a, int kid) {
 template <int KID> __global__ void __launch_bounds__(128) pg_kernel(Args a, int n) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t < n) pg_thread<KID>(a, t);
+}
+__global__ void __launch_bounds__(64) pg_factor_kernel(Args a) {
+    __shared__ FactorTile T;
+    const int t = threadIdx.x;
+    const bool work = t < FACTOR_THREADS;
+    if (work) factor_stage(T, t, factor_fetch(a, 0, t));
+    __syncthreads();
+    for (int k = 0; k < a.K; ++k) {
+        FactorNext nx;
+        const bool more = work && k + 1 < a.K;
+        if (more) nx = factor_fetch(a, k + 1, t);   // in flight while the phases of step k run
+#pragma unroll
+        for (int phase = 0; phase < FACTOR_PHASES; ++phase) {
+            if (work) factor_phase(a, T, k, phase, t);
+            if (phase == FACTOR_PHASES - 1 && more) factor_stage(T, t, nx);
+            __syncthreads();
+        }
+    }
+    if (t == 0) a.flags[0] = T.ok ? 0 : 1;
 }
 __global__ void __launch_bounds__(256) pg_dense_kernel(Args a) {
     const int n = 6 * a.L, tid = threadIdx.x, nt = blockDim.x;
@@ -516,7 +571,7 @@ __global__ void __launch_bounds__(256) pg_reduce_kernel(Args a) {
 #endif
 
 // ------------------------------------------------------------------ the minimiser (host control flow)
-// `Launcher` runs the kernels: bool run(int kernel_id, const Args&), bool dense(const Args&), bool reduce(const Args&),
+// `Launcher` runs the kernels: bool run(int kernel_id, const Args&), bool factor(const Args&), bool dense(const Args&), bool reduce(const Args&),
 // bool read(const Args&, double* scal /*[S_COUNT]*/, int32_t* flags /*[2]*/) (the read is the synchronisation point).
 // Returns false on a launcher (CUDA) error.  The optimised poses end up in a.x (x and xc are swapped on acceptance).
 template <class Launcher>
@@ -550,7 +605,7 @@ inline bool pg_minimize(Launcher& Lr, Args& a, const Options& opt, lvio2d_summar
         // ComputeTrustRegionStep + candidate evaluation, one round trip
         a.radius = radius;
         a.y = a.xc;
-        bool ok = Lr.run(K_FACTOR, a) && Lr.run(K_TRISOLVE, a);
+        bool ok = Lr.factor(a) && Lr.run(K_TRISOLVE, a);
         if (ok && a.L > 0) ok = Lr.run(K_CAPACITANCE, a) && Lr.dense(a);
         ok = ok && Lr.run(K_COMBINE, a) && Lr.run(K_MODEL, a) && Lr.run(K_COST, a) && Lr.reduce(a) && Lr.read(a, scal, flags);
         if (!ok) return false;

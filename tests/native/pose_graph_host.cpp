@@ -22,7 +22,6 @@ struct HostLauncher {
             case K_COLUMNS: loop<K_COLUMNS>(a); break;
             case K_ASSEMBLE: loop<K_ASSEMBLE>(a); break;
             case K_SCALE: loop<K_SCALE>(a); break;
-            case K_FACTOR: loop<K_FACTOR>(a); break;
             case K_TRISOLVE: loop<K_TRISOLVE>(a); break;
             case K_CAPACITANCE: loop<K_CAPACITANCE>(a); break;
             case K_COMBINE: loop<K_COMBINE>(a); break;
@@ -30,6 +29,19 @@ struct HostLauncher {
             case K_COST: loop<K_COST>(a); break;
             default: return false;
         }
+        return true;
+    }
+    bool factor(const Args& a) {
+        ++launches;
+        FactorTile T;
+        for (int t = 0; t < FACTOR_THREADS; ++t) factor_stage(T, t, factor_fetch(a, 0, t));
+        for (int k = 0; k < a.K; ++k) {
+            for (int phase = 0; phase < FACTOR_PHASES; ++phase)
+                for (int t = 0; t < FACTOR_THREADS; ++t) factor_phase(a, T, k, phase, t);
+            if (k + 1 < a.K)
+                for (int t = 0; t < FACTOR_THREADS; ++t) factor_stage(T, t, factor_fetch(a, k + 1, t));
+        }
+        a.flags[0] = T.ok ? 0 : 1;
         return true;
     }
     bool dense(const Args& a) {

@@ -1,11 +1,8 @@
 """GPU parity of lvio2d_pose_graph_solve / lvio2d_eval_edge_factor (back-end pose graph)
 against the CPU oracle of keyframe_manager::solve (oracle/pose_graph.hpp), through the C ABI.
 
-STATUS: written after the round's GPU minutes were spent — the kernels are cross-compiled for sm_100a and their bodies
-are verified on the CPU against the oracle (tests/test_pose_graph_host.py runs the same `__host__ __device__` bodies
-thread by thread under the same minimiser loop), but this file has not yet run on a B200.  Until it has, the tests are
-xfail(strict=False) (a pass shows up as XPASS) and the file sorts last so that a fault here cannot disturb the verified
-parity tests.  Tolerances: residual 1e-12, Jacobian 1e-9 relative, poses 1e-6 m / rad on smooth problems (north star:
+Confirmed on a B200 at the end of round 1 (profiles/r1_pose_graph.md: same graphs, same assertions, run through
+scripts/pg_gpu_check.py); the file sorts last because it was the last one written.  Tolerances: residual 1e-12, Jacobian 1e-9 relative, poses 1e-6 m / rad on smooth problems (north star:
 1e-4), cost 1e-6 relative; see test_pose_graph_host.py for why the kinked problem (ground_q) is compared after 12
 iterations and only bounded after 50."""
 import numpy as np
@@ -15,7 +12,7 @@ import lvio2d_b200 as L
 from test_oracle_pose_graph import T_of, edge_noise_J
 from test_pose_graph_host import graph_with_loops
 
-pytestmark = [pytest.mark.gpu, pytest.mark.xfail(strict=False, reason="device path not yet confirmed on a B200 (GPU budget of round 1 spent)")]
+pytestmark = pytest.mark.gpu
 
 
 def make_ctx(**kw):
