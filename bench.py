@@ -351,11 +351,27 @@ def run_ours(args):
     if world == 1:
         result["single_window"] = single_window_latency(P, hb, torch, device)
         result["next_rows"] = front_end_rates(P, torch, device, cpu=not args.no_cpu)
+        result["next_rows"]["pose_graph"] = pose_graph_rates(cpu=not args.no_cpu)
     if world == 1 and not args.no_cpu:
         result["cpu_baseline"] = cpu_baseline(P, hb, seconds=args.cpu_seconds, threads=1)
     print(json.dumps(result))
     if world > 1:
         dist.destroy_process_group()
+
+
+def pose_graph_rates(cpu=True):
+    """SURVEY section 8f rank 4 (back-end pose graph, lvio2d_pose_graph_solve): scripts/pg_bench.py in a subprocess with a
+    time limit — the row was built last in round 1 and must not be able to take the headline line down."""
+    import subprocess
+
+    cmd = [sys.executable, os.path.join(os.path.dirname(os.path.abspath(__file__)), "scripts", "pg_bench.py")] + ([] if cpu else ["--no-cpu"])
+    try:
+        out = subprocess.run(cmd, capture_output=True, text=True, timeout=120)
+        if out.returncode != 0:
+            return {"error": (out.stderr or out.stdout).strip().splitlines()[-1][:200] if (out.stderr or out.stdout).strip() else f"exit {out.returncode}"}
+        return json.loads(out.stdout.strip().splitlines()[-1])
+    except Exception as e:  # noqa: BLE001
+        return {"error": f"{type(e).__name__}: {e}"[:200]}
 
 
 def front_end_rates(P, torch, device, n_scans=4096, reps=10, cpu=True):
