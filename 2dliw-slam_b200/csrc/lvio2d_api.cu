@@ -13,7 +13,7 @@
 #include "../../include/lvio2d.h"
 #include "aux_kernels.cuh"
 #include "scan_lines.cuh"
-#include "pose_graph.cuh"
+#include "pose_graph_segments.cuh"
 
 using namespace lv;
 
@@ -1088,6 +1088,30 @@ struct PgDeviceLauncher {
         ctx->launches += 1;
         return (err = cudaGetLastError()) == cudaSuccess;
     }
+    // the opt-in partitioned solve (pose_graph_segments.cuh)
+    bool chain_factor(const pg::Args& a, int reduced) {
+        pg::pg_chain_factor_kernel<<<reduced ? 1 : a.P, 64, 0, ctx->stream>>>(a, reduced);
+        ctx->launches += 1;
+        return (err = cudaGetLastError()) == cudaSuccess;
+    }
+    template <int KID> bool seg_go(const pg::Args& a) {
+        const int n = pg::seg_kernel_threads(a, KID);
+        if (n <= 0) return true;
+        pg::pg_seg_kernel<KID><<<(n + 127) / 128, 128, 0, ctx->stream>>>(a, n);
+        ctx->launches += 1;
+        return (err = cudaGetLastError()) == cudaSuccess;
+    }
+    bool seg(int kid, const pg::Args& a) {
+        switch (kid) {
+            case pg::KS_TRISOLVE: return seg_go<pg::KS_TRISOLVE>(a);
+            case pg::KS_REDUCED_BLOCKS: return seg_go<pg::KS_REDUCED_BLOCKS>(a);
+            case pg::KS_REDUCED_RHS: return seg_go<pg::KS_REDUCED_RHS>(a);
+            case pg::KS_REDUCED_TRISOLVE: return seg_go<pg::KS_REDUCED_TRISOLVE>(a);
+            case pg::KS_BACKSUB: return seg_go<pg::KS_BACKSUB>(a);
+        }
+        return false;
+    }
+    bool partitioned(const pg::Args& a) { return pg::pg_partitioned_solve(*this, a); }
     bool dense(const pg::Args& a) {
         pg::pg_dense_kernel<<<1, 256, 0, ctx->stream>>>(a);
         ctx->launches += 1;
@@ -1116,7 +1140,10 @@ int pg_setup(lvio2d_ctx* ctx, pg::Args& a, int32_t n_poses, const double* poses,
     std::vector<int32_t> ints;
     std::memset(&a, 0, sizeof(a));
     a.K = n_poses; a.E = n_edges;
-    if (!pg::pg_topology(n_poses, n_edges, edge_index, ints, &a.L)) return fail(ctx, LVIO2D_ERR_INVALID_ARG, "pose graph: edge index out of range or self edge");
+    // LVIO2D_PG_SEGMENTS=<P>: cut the chain into P segments (pose_graph_segments.cuh; opt-in until confirmed on a B200)
+    const char* seg_env = std::getenv("LVIO2D_PG_SEGMENTS");
+    a.P = pg::pg_segments(n_poses, seg_env ? std::atoi(seg_env) : 0);
+    if (!pg::pg_topology(n_poses, n_edges, edge_index, ints, &a.L, a.P)) return fail(ctx, LVIO2D_ERR_INVALID_ARG, "pose graph: edge index out of range or self edge");
     a.fixed = fixed;
     a.ground_p = ground_p != 0; a.ground_q = ground_q != 0;
     a.C = ctx->C;

@@ -83,6 +83,16 @@ struct Args {
     double* part;    // per-item partials, see part_offset
     double* scal;    // [S_COUNT]
     int32_t* flags;  // [2] non-positive pivot in the tridiagonal / capacitance factorisation
+    // partitioned solve (pose_graph_segments.cuh; P <= 1: off, everything below unused)
+    int P;                     // segments
+    const int32_t* node_seg;   // [K] segment of an interior key frame, or -(i + 1) for separator i
+    int32_t* segflag;          // [P]
+    double* Zx;                // [6K][ncol + 12] segment solutions: right-hand sides + the two spikes
+    double* Rd;                // [P-1][36] reduced (separator) system: diagonal blocks,
+    double* Ro;                // [P-1][36] block (i + 1, i),
+    double* RSinv;             // its factorisation
+    double* RM;
+    double* Zr;                // [6(P-1)][ncol] reduced right-hand sides / solutions
 };
 
 // read-only (non-coherent) load and L1 prefetch on the device, plain load / nothing on the host
@@ -572,6 +582,7 @@ __global__ void __launch_bounds__(256) pg_reduce_kernel(Args a) {
 
 // ------------------------------------------------------------------ the minimiser (host control flow)
 // `Launcher` runs the kernels: bool run(int kernel_id, const Args&), bool factor(const Args&), bool dense(const Args&), bool reduce(const Args&),
+// bool partitioned(const Args&) (only called when a.P > 1, pose_graph_segments.cuh),
 // bool read(const Args&, double* scal /*[S_COUNT]*/, int32_t* flags /*[2]*/) (the read is the synchronisation point).
 // Returns false on a launcher (CUDA) error.  The optimised poses end up in a.x (x and xc are swapped on acceptance).
 template <class Launcher>
@@ -605,7 +616,7 @@ inline bool pg_minimize(Launcher& Lr, Args& a, const Options& opt, lvio2d_summar
         // ComputeTrustRegionStep + candidate evaluation, one round trip
         a.radius = radius;
         a.y = a.xc;
-        bool ok = Lr.factor(a) && Lr.run(K_TRISOLVE, a);
+        bool ok = a.P > 1 ? Lr.partitioned(a) : (Lr.factor(a) && Lr.run(K_TRISOLVE, a));
         if (ok && a.L > 0) ok = Lr.run(K_CAPACITANCE, a) && Lr.dense(a);
         ok = ok && Lr.run(K_COMBINE, a) && Lr.run(K_MODEL, a) && Lr.run(K_COST, a) && Lr.reduce(a) && Lr.read(a, scal, flags);
         if (!ok) return false;
@@ -656,12 +667,12 @@ inline bool pg_minimize(Launcher& Lr, Args& a, const Options& opt, lvio2d_summar
 
 // host-side preparation shared by the product entry point and the CPU check: band / loop classification, the incidence
 // lists, and the carving of the two arenas (one of int32, one of double) every Args pointer lives in.
-// int arena:    [edge_index 2E][edge_band E][loop_edge L][inc_off K+1][inc 2E][flags 2]
+// int arena:    [edge_index 2E][edge_band E][loop_edge L][inc_off K+1][inc 2E][flags 2]  (+ [node_seg K][segflag P] when P > 1)
 // double arena: [edge_tf 12E][edge_weight E][x 6K][xc 6K][EJ 78E][GJ 14K][g 6K][Hd 6K][D 36K][O 36K][scale 6K][Sinv 36K][M 36K]
-//               [Z 6K*ncol][Cm 6L*ncol][w 6L][delta 6K][part][scal S_COUNT]
+//               [Z 6K*ncol][Cm 6L*ncol][w 6L][delta 6K][part][scal S_COUNT]  (+ [Zx 6K(ncol+12)][Rd Ro RSinv RM 36(P-1)][Zr 6(P-1)ncol])
 // Returns false on an invalid graph (index out of range, self edge).  `ints` receives the int arena's host image.
 template <class VecI>
-inline bool pg_topology(int K, int E, const int32_t* edge_index, VecI& ints, int* n_loops) {
+inline bool pg_topology(int K, int E, const int32_t* edge_index, VecI& ints, int* n_loops, int P = 0) {
     VecI band(E, 0), loops, inc_off(K + 1, 0), inc(2 * (size_t)E, 0);
     for (int e = 0; e < E; ++e) {
         const int i = edge_index[2 * e], j = edge_index[2 * e + 1];
@@ -686,10 +697,21 @@ inline bool pg_topology(int K, int E, const int32_t* edge_index, VecI& ints, int
     ints.insert(ints.end(), inc.begin(), inc.end());
     ints.push_back(0);
     ints.push_back(0);
+    if (P > 1) {   // node_seg [K] + segflag [P]; separator i sits at key frame (i + 1) K / P
+        VecI node_seg(K, 0);
+        int c = 0;
+        for (int k = 0; k < K; ++k) {
+            const int next_sep = c < P - 1 ? (int)(((long long)(c + 1) * K) / P) : K;
+            if (k == next_sep) { node_seg[k] = -(c + 1); ++c; }
+            else node_seg[k] = c;
+        }
+        ints.insert(ints.end(), node_seg.begin(), node_seg.end());
+        ints.insert(ints.end(), (size_t)P, 0);
+    }
     *n_loops = (int)loops.size();
     return true;
 }
-// a.K, a.E, a.L must be set; assigns ncol and every pointer.  Returns the number of doubles the double arena needs.
+// a.K, a.E, a.L, a.P must be set; assigns ncol and every pointer.  Returns the number of doubles the double arena needs.
 inline size_t pg_bind(Args& a, int32_t* ints, double* dbl) {
     a.ncol = 1 + 6 * a.L;
     const size_t K = (size_t)a.K, E = (size_t)a.E, L = (size_t)a.L, nc = (size_t)a.ncol;
@@ -701,6 +723,8 @@ inline size_t pg_bind(Args& a, int32_t* ints, double* dbl) {
     a.inc_off = itake(K + 1);
     a.inc = itake(2 * E);
     a.flags = itake(2);
+    a.node_seg = a.P > 1 ? itake(K) : nullptr;
+    a.segflag = a.P > 1 ? itake((size_t)a.P) : nullptr;
     size_t off = 0;
     auto take = [&](size_t n) { double* p = dbl ? dbl + off : nullptr; off += n; return p; };
     a.edge_tf = take(12 * E);
@@ -722,10 +746,23 @@ inline size_t pg_bind(Args& a, int32_t* ints, double* dbl) {
     a.delta = take(6 * K);
     a.part = take((size_t)part_total(a));
     a.scal = take(S_COUNT);
+    if (a.P > 1) {
+        const size_t R = (size_t)a.P - 1;
+        a.Zx = take(6 * K * (nc + 12));
+        a.Rd = take(36 * R); a.Ro = take(36 * R); a.RSinv = take(36 * R); a.RM = take(36 * R);
+        a.Zr = take(6 * R * nc);
+    } else {
+        a.Zx = a.Rd = a.Ro = a.RSinv = a.RM = a.Zr = nullptr;
+    }
     a.y = a.x;
     return off;
 }
-inline size_t pg_int_count(int K, int E, int L) { return 2 * (size_t)E + E + L + K + 1 + 2 * (size_t)E + 2; }
+// the largest useful number of segments for K key frames (0: use the plain path): every segment keeps >= 3 interior key frames
+inline int pg_segments(int K, int requested) {
+    int P = requested;
+    if (P > K / 4) P = K / 4;
+    return P >= 2 ? P : 0;
+}
 
 }  // namespace pg
 }  // namespace lv

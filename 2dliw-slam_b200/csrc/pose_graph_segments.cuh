@@ -1,0 +1,298 @@
+// pose_graph_segments.cuh — the block-tridiagonal solve of pose_graph.cuh with its sequential chains cut into P segments.
+//
+// STATUS: opt-in (LVIO2D_PG_SEGMENTS=<P>, default off).  Written at the end of round 1 from the launch list in
+// profiles/r1_pose_graph.md (the two sequential chains over the key frames are 94 % of an LM iteration); verified on the
+// CPU by the thread-by-thread host run against the oracle (tests/test_pose_graph_host.py), cross-compiled for sm_100a,
+// NOT yet run on a B200 — the default path stays the one that was.
+//
+// Substructuring of T x = b (T block-tridiagonal SPD, 6x6 blocks, K key frames): P - 1 separator key frames
+// s_i = (i + 1) K / P split the chain into P segments of interior key frames.
+//   (1) every segment (one CTA each, concurrently): factorise its interior block-tridiagonal matrix T_c;
+//   (2) every segment: T_c^-1 [ b_c | E_left | E_right ] — the 1 + 6L right-hand sides plus the two 6-column "spikes"
+//       that couple the segment to its separators (E_left = O_{lo-1} at the first row, E_right = O_hi^T at the last);
+//   (3) the Schur complement on the separators is again block-tridiagonal (P - 1 blocks):
+//         R_i      = T_ss - O_{s-1} W_i[s-1] - O_s^T V_{i+1}[s+1]          (V / W: left / right spike solutions)
+//         R_{i,i-1} = - O_{s-1} V_i[s-1]
+//         r_i      = b_s - O_{s-1} z_i[s-1] - O_s^T z_{i+1}[s+1]
+//       factorised and solved by one CTA (P - 1 sequential steps);
+//   (4) interior back-substitution x = z - V x_left - W x_right, all key frames concurrently.
+// Sequential depth: 3 K / P + 2 P block steps instead of 3 K.  Same arithmetic class as the plain path (exact; the
+// elimination order differs, results agree to rounding).
+#pragma once
+#include "pose_graph.cuh"
+
+namespace lv {
+namespace pg {
+
+enum SegKernel { KS_TRISOLVE = 100, KS_REDUCED_BLOCKS, KS_REDUCED_RHS, KS_REDUCED_TRISOLVE, KS_BACKSUB };
+
+LV_HD int sep_node(const Args& a, int i) { return (int)(((long long)(i + 1) * a.K) / a.P); }
+LV_HD int seg_lo(const Args& a, int c) { return c == 0 ? 0 : sep_node(a, c - 1) + 1; }
+LV_HD int seg_hi(const Args& a, int c) { return c == a.P - 1 ? a.K - 1 : sep_node(a, c) - 1; }
+LV_HD int ncol_x(const Args& a) { return a.ncol + 12; }
+
+// one block-tridiagonal system over consecutive entries lo..hi of node-indexed arrays; O[i] = block (i + 1, i)
+struct Chain {
+    const double* D;
+    const double* O;
+    const double* Hd;   // nullptr: D already carries the LM diagonal (reduced system)
+    const double* Sc;
+    double* Sinv;
+    double* M;
+    int lo, hi, fixed;
+};
+LV_HD Chain segment_chain(const Args& a, int c) {
+    Chain ch;
+    ch.D = a.D; ch.O = a.O; ch.Hd = a.Hd; ch.Sc = a.scale; ch.Sinv = a.Sinv; ch.M = a.M;
+    ch.lo = seg_lo(a, c); ch.hi = seg_hi(a, c); ch.fixed = a.fixed;
+    return ch;
+}
+LV_HD Chain reduced_chain(const Args& a) {
+    Chain ch;
+    ch.D = a.Rd; ch.O = a.Ro; ch.Hd = nullptr; ch.Sc = nullptr; ch.Sinv = a.RSinv; ch.M = a.RM;
+    ch.lo = 0; ch.hi = a.P - 2; ch.fixed = -1;
+    return ch;
+}
+// the LM term of key frame k, column r, in unscaled columns (as factor_phase of pose_graph.cuh)
+LV_HD double lm_term(const Args& a, double hd, double sc) {
+    const double hs = hd * sc * sc;
+    const double d = fmin(fmax(hs, a.min_lm), a.max_lm);
+    return d / a.radius / (sc * sc);
+}
+
+// ---- factorisation of a chain: the phases of pose_graph.cuh's factor_phase with a range and optional damping
+LV_HD FactorNext chain_fetch(const Chain& ch, int k, int t) {
+    FactorNext n;
+    n.D = ch.D[(size_t)k * 36 + t];
+    n.O = k > ch.lo ? ch.O[(size_t)(k - 1) * 36 + t] : 0.0;
+    n.Hd = (ch.Hd && t < 6) ? ch.Hd[6 * k + t] : 0.0;
+    n.Sc = (ch.Sc && t < 6) ? ch.Sc[6 * k + t] : 1.0;
+    return n;
+}
+LV_HD void chain_phase(const Args& a, const Chain& ch, FactorTile& T, int k, int phase, int t) {
+    const int r = t / 6, c = t % 6;
+    if (phase == 0) {
+        double v = T.nD[t];
+        if (ch.Hd && r == c && k != ch.fixed) v += lm_term(a, T.nHd[r], T.nSc[r]);
+        T.S[0][t] = v;
+        T.B[t] = T.nO[t];
+        T.Inv[0][t] = (r == c) ? 1.0 : 0.0;
+        if (t == 0 && k == ch.lo) T.ok = 1;
+    } else if (phase == 1) {
+        double m = 0.0;
+        if (k > ch.lo)
+            for (int i = 0; i < 6; ++i) m += T.B[r * 6 + i] * T.Sp[i * 6 + c];
+        T.Mk[t] = m;
+        ch.M[(size_t)k * 36 + t] = m;
+    } else if (phase == 2) {
+        if (k > ch.lo) {
+            double s = 0.0;
+            for (int i = 0; i < 6; ++i) s += T.Mk[r * 6 + i] * T.B[c * 6 + i];
+            T.S[0][t] -= s;
+        }
+    } else {
+        const int j = phase - 3, src = j & 1, dst = src ^ 1;
+        double p = T.S[src][j * 6 + j];
+        if (!(p > 0.0)) { if (t == 0) T.ok = 0; p = 1.0; }
+        const double ip = 1.0 / p;
+        const double sj = T.S[src][j * 6 + c] * ip, ij = T.Inv[src][j * 6 + c] * ip;
+        double ns, ni;
+        if (r == j) { ns = sj; ni = ij; }
+        else { const double f = T.S[src][r * 6 + j]; ns = T.S[src][t] - f * sj; ni = T.Inv[src][t] - f * ij; }
+        T.S[dst][t] = ns;
+        T.Inv[dst][t] = ni;
+        if (j == 5) {
+            T.Sp[t] = ni;
+            ch.Sinv[(size_t)k * 36 + t] = ni;
+        }
+    }
+}
+
+// ---- right-hand sides
+struct ColumnInfo { int e, rho, ie, je; };
+LV_HD ColumnInfo column_info(const Args& a, int col) {
+    ColumnInfo ci;
+    ci.e = -1; ci.rho = 0; ci.ie = -1; ci.je = -1;
+    if (col > 0 && col < a.ncol) {
+        ci.e = a.loop_edge[(col - 1) / 6];
+        ci.rho = (col - 1) % 6;
+        ci.ie = a.edge_index[2 * ci.e];
+        ci.je = a.edge_index[2 * ci.e + 1];
+    }
+    return ci;
+}
+// entry q of key frame k of global right-hand side `col` (0: -g, 1 + 6l + rho: loop edge l, residual row rho)
+LV_HD double global_rhs(const Args& a, const ColumnInfo& ci, int col, int k, int q) {
+    if (col == 0) return -a.g[6 * k + q];
+    const double* J = a.EJ + (size_t)ci.e * 78;
+    return (k == ci.ie) ? J[q * 6 + ci.rho] : ((k == ci.je) ? J[36 + q * 6 + ci.rho] : 0.0);
+}
+// forward / backward block substitution of one right-hand side over a chain; Z[(6k + q) * ncz + col].
+// kind 0: global columns and (col >= ncol) the two spikes of the segment; kind 1: the right-hand side is in Z already.
+LV_HD void chain_trisolve(const Args& a, const Chain& ch, double* Z, int ncz, int col, int kind) {
+    const ColumnInfo ci = column_info(a, kind == 0 ? col : 0);
+    const bool spike = kind == 0 && col >= a.ncol;
+    const bool left = spike && (col - a.ncol) < 6;
+    const int sj = spike ? (col - a.ncol) % 6 : 0;
+    double yp[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0}, b[6];
+    for (int k = ch.lo; k <= ch.hi; ++k) {
+        for (int q = 0; q < 6; ++q) {
+            if (kind == 1) b[q] = Z[(size_t)(6 * k + q) * ncz + col];
+            else if (!spike) b[q] = global_rhs(a, ci, col, k, q);
+            else if (left) b[q] = (k == ch.lo && ch.lo > 0) ? a.O[(size_t)(ch.lo - 1) * 36 + q * 6 + sj] : 0.0;       // O_{lo-1}[:, sj]
+            else b[q] = (k == ch.hi && ch.hi < a.K - 1) ? a.O[(size_t)ch.hi * 36 + sj * 6 + q] : 0.0;                // O_hi^T[:, sj]
+        }
+        if (k > ch.lo) {
+            const double* Mk = ch.M + (size_t)k * 36;
+            for (int q = 0; q < 6; ++q) {
+                double s = 0.0;
+                for (int i = 0; i < 6; ++i) s += lv_ldg(Mk + q * 6 + i) * yp[i];
+                b[q] -= s;
+            }
+        }
+        for (int q = 0; q < 6; ++q) { yp[q] = b[q]; Z[(size_t)(6 * k + q) * ncz + col] = b[q]; }
+    }
+    double xn[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+    for (int k = ch.hi; k >= ch.lo; --k) {
+        const double* Si = ch.Sinv + (size_t)k * 36;
+        for (int q = 0; q < 6; ++q) yp[q] = Z[(size_t)(6 * k + q) * ncz + col];
+        for (int q = 0; q < 6; ++q) {
+            double s = 0.0;
+            for (int i = 0; i < 6; ++i) s += lv_ldg(Si + q * 6 + i) * yp[i];
+            b[q] = s;
+        }
+        if (k < ch.hi) {
+            const double* Mn = ch.M + (size_t)(k + 1) * 36;
+            for (int q = 0; q < 6; ++q) {
+                double s = 0.0;
+                for (int i = 0; i < 6; ++i) s += lv_ldg(Mn + i * 6 + q) * xn[i];
+                b[q] -= s;
+            }
+        }
+        for (int q = 0; q < 6; ++q) { xn[q] = b[q]; Z[(size_t)(6 * k + q) * ncz + col] = b[q]; }
+    }
+}
+
+// ---- kernel bodies
+// KS_TRISOLVE, n = P * (ncol + 12): segment c, column col
+LV_HD void body_seg_trisolve(const Args& a, int t) {
+    const int ncx = ncol_x(a);
+    chain_trisolve(a, segment_chain(a, t / ncx), a.Zx, ncx, t % ncx, 0);
+}
+// KS_REDUCED_BLOCKS, n = (P - 1) * 36: entry (r, c) of R_i and of R_{i, i-1}
+LV_HD void body_reduced_blocks(const Args& a, int t) {
+    const int i = t / 36, r = (t % 36) / 6, c = t % 6;
+    const int s = sep_node(a, i), ncx = ncol_x(a);
+    const double* Ol = a.O + (size_t)(s - 1) * 36;   // block (s, s-1)
+    const double* Or = a.O + (size_t)s * 36;         // block (s+1, s)
+    double v = a.D[(size_t)s * 36 + r * 6 + c];
+    if (r == c && s != a.fixed) v += lm_term(a, a.Hd[6 * s + r], a.scale[6 * s + r]);
+    double off = 0.0;
+    for (int m = 0; m < 6; ++m) {
+        const double W = a.Zx[(size_t)(6 * (s - 1) + m) * ncx + a.ncol + 6 + c];   // right spike of segment i at its last key frame
+        const double V = a.Zx[(size_t)(6 * (s + 1) + m) * ncx + a.ncol + c];       // left spike of segment i+1 at its first key frame
+        v -= Ol[r * 6 + m] * W + Or[m * 6 + r] * V;
+        off -= Ol[r * 6 + m] * a.Zx[(size_t)(6 * (s - 1) + m) * ncx + a.ncol + c]; // left spike of segment i at its last key frame
+    }
+    a.Rd[(size_t)i * 36 + r * 6 + c] = v;
+    if (i > 0) a.Ro[(size_t)(i - 1) * 36 + r * 6 + c] = off;
+}
+// KS_REDUCED_RHS, n = (P - 1) * 6 * ncol
+LV_HD void body_reduced_rhs(const Args& a, int t) {
+    const int col = t % a.ncol, q = (t / a.ncol) % 6, i = t / (6 * a.ncol);
+    const int s = sep_node(a, i), ncx = ncol_x(a);
+    const ColumnInfo ci = column_info(a, col);
+    const double* Ol = a.O + (size_t)(s - 1) * 36;
+    const double* Or = a.O + (size_t)s * 36;
+    double v = global_rhs(a, ci, col, s, q);
+    for (int m = 0; m < 6; ++m)
+        v -= Ol[q * 6 + m] * a.Zx[(size_t)(6 * (s - 1) + m) * ncx + col] + Or[m * 6 + q] * a.Zx[(size_t)(6 * (s + 1) + m) * ncx + col];
+    a.Zr[(size_t)(6 * i + q) * a.ncol + col] = v;
+}
+// KS_REDUCED_TRISOLVE, n = ncol
+LV_HD void body_reduced_trisolve(const Args& a, int col) { chain_trisolve(a, reduced_chain(a), a.Zr, a.ncol, col, 1); }
+// KS_BACKSUB, n = K * ncol: the solution in the layout the plain path leaves it in (a.Z)
+LV_HD void body_backsub(const Args& a, int t) {
+    const int k = t / a.ncol, col = t % a.ncol, ncx = ncol_x(a);
+    const int tag = a.node_seg[k];
+    if (tag < 0) {
+        const int i = -tag - 1;
+        for (int q = 0; q < 6; ++q) a.Z[(size_t)(6 * k + q) * a.ncol + col] = a.Zr[(size_t)(6 * i + q) * a.ncol + col];
+        return;
+    }
+    double xl[6], xr[6];
+    for (int j = 0; j < 6; ++j) {
+        xl[j] = tag > 0 ? a.Zr[(size_t)(6 * (tag - 1) + j) * a.ncol + col] : 0.0;
+        xr[j] = tag < a.P - 1 ? a.Zr[(size_t)(6 * tag + j) * a.ncol + col] : 0.0;
+    }
+    for (int q = 0; q < 6; ++q) {
+        const double* z = a.Zx + (size_t)(6 * k + q) * ncx;
+        double s = z[col];
+        for (int j = 0; j < 6; ++j) s -= z[a.ncol + j] * xl[j] + z[a.ncol + 6 + j] * xr[j];
+        a.Z[(size_t)(6 * k + q) * a.ncol + col] = s;
+    }
+}
+template <int KID> LV_HD void seg_thread(const Args& a, int t) {
+    if (KID == KS_TRISOLVE) body_seg_trisolve(a, t);
+    else if (KID == KS_REDUCED_BLOCKS) body_reduced_blocks(a, t);
+    else if (KID == KS_REDUCED_RHS) body_reduced_rhs(a, t);
+    else if (KID == KS_REDUCED_TRISOLVE) body_reduced_trisolve(a, t);
+    else if (KID == KS_BACKSUB) body_backsub(a, t);
+}
+LV_HD int seg_kernel_threads(const Args& a, int kid) {
+    switch (kid) {
+        case KS_TRISOLVE: return a.P * ncol_x(a);
+        case KS_REDUCED_BLOCKS: return (a.P - 1) * 36;
+        case KS_REDUCED_RHS: return (a.P - 1) * 6 * a.ncol;
+        case KS_REDUCED_TRISOLVE: return a.ncol;
+        default: return a.K * a.ncol;
+    }
+}
+// a whole chain by the 36 working threads of one CTA; `sync` is __syncthreads on the device, nothing on the host (where
+// the caller runs the threads of a phase one after the other)
+#if defined(__CUDACC__)
+template <int KID> __global__ void __launch_bounds__(128) pg_seg_kernel(Args a, int n) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < n) seg_thread<KID>(a, t);
+}
+// reduced == 0: CTA c factorises segment c (flag -> segflag[c]); reduced == 1: one CTA factorises the separator system
+// and folds every flag into flags[0]
+__global__ void __launch_bounds__(64) pg_chain_factor_kernel(Args a, int reduced) {
+    __shared__ FactorTile T;
+    const int t = threadIdx.x;
+    const bool work = t < FACTOR_THREADS;
+    const Chain ch = reduced ? reduced_chain(a) : segment_chain(a, blockIdx.x);
+    if (work) factor_stage(T, t, chain_fetch(ch, ch.lo, t));
+    __syncthreads();
+    for (int k = ch.lo; k <= ch.hi; ++k) {
+        FactorNext nx;
+        const bool more = work && k + 1 <= ch.hi;
+        if (more) nx = chain_fetch(ch, k + 1, t);
+#pragma unroll
+        for (int phase = 0; phase < FACTOR_PHASES; ++phase) {
+            if (work) chain_phase(a, ch, T, k, phase, t);
+            if (phase == FACTOR_PHASES - 1 && more) factor_stage(T, t, nx);
+            __syncthreads();
+        }
+    }
+    if (t == 0) {
+        if (!reduced) {
+            a.segflag[blockIdx.x] = T.ok ? 0 : 1;
+        } else {
+            int bad = T.ok ? 0 : 1;
+            for (int c = 0; c < a.P; ++c) bad |= a.segflag[c];
+            a.flags[0] = bad;
+        }
+    }
+}
+#endif
+
+// the launch sequence of one partitioned solve (what Launcher::partitioned runs): Lr.chain_factor(a, reduced),
+// Lr.seg(kernel id, a)
+template <class Launcher> inline bool pg_partitioned_solve(Launcher& Lr, const Args& a) {
+    return Lr.chain_factor(a, 0) && Lr.seg(KS_TRISOLVE, a) && Lr.seg(KS_REDUCED_BLOCKS, a) && Lr.seg(KS_REDUCED_RHS, a) && Lr.chain_factor(a, 1) &&
+           Lr.seg(KS_REDUCED_TRISOLVE, a) && Lr.seg(KS_BACKSUB, a);
+}
+
+}  // namespace pg
+}  // namespace lv

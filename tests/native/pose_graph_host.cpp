@@ -5,7 +5,7 @@
 #include <cstring>
 #include <vector>
 
-#include "../../2dliw-slam_b200/csrc/pose_graph.cuh"
+#include "../../2dliw-slam_b200/csrc/pose_graph_segments.cuh"
 using namespace lv;
 using namespace lv::pg;
 
@@ -44,6 +44,47 @@ struct HostLauncher {
         a.flags[0] = T.ok ? 0 : 1;
         return true;
     }
+    // the partitioned solve (pose_graph_segments.cuh): segment / reduced factorisations phase by phase, the rest thread by thread
+    bool chain_factor(const Args& a, int reduced) {
+        ++launches;
+        int bad = 0;
+        const int ctas = reduced ? 1 : a.P;
+        for (int cta = 0; cta < ctas; ++cta) {
+            const Chain ch = reduced ? reduced_chain(a) : segment_chain(a, cta);
+            FactorTile T;
+            for (int t = 0; t < FACTOR_THREADS; ++t) factor_stage(T, t, chain_fetch(ch, ch.lo, t));
+            for (int k = ch.lo; k <= ch.hi; ++k) {
+                for (int phase = 0; phase < FACTOR_PHASES; ++phase)
+                    for (int t = 0; t < FACTOR_THREADS; ++t) chain_phase(a, ch, T, k, phase, t);
+                if (k + 1 <= ch.hi)
+                    for (int t = 0; t < FACTOR_THREADS; ++t) factor_stage(T, t, chain_fetch(ch, k + 1, t));
+            }
+            if (!reduced) a.segflag[cta] = T.ok ? 0 : 1;
+            else bad = T.ok ? 0 : 1;
+        }
+        if (reduced) {
+            for (int c = 0; c < a.P; ++c) bad |= a.segflag[c];
+            a.flags[0] = bad;
+        }
+        return true;
+    }
+    template <int KID> static void seg_loop(const Args& a) {
+        const int n = seg_kernel_threads(a, KID);
+        for (int t = 0; t < n; ++t) seg_thread<KID>(a, t);
+    }
+    bool seg(int kid, const Args& a) {
+        ++launches;
+        switch (kid) {
+            case KS_TRISOLVE: seg_loop<KS_TRISOLVE>(a); break;
+            case KS_REDUCED_BLOCKS: seg_loop<KS_REDUCED_BLOCKS>(a); break;
+            case KS_REDUCED_RHS: seg_loop<KS_REDUCED_RHS>(a); break;
+            case KS_REDUCED_TRISOLVE: seg_loop<KS_REDUCED_TRISOLVE>(a); break;
+            case KS_BACKSUB: seg_loop<KS_BACKSUB>(a); break;
+            default: return false;
+        }
+        return true;
+    }
+    bool partitioned(const Args& a) { return pg_partitioned_solve(*this, a); }
     bool dense(const Args& a) {
         ++launches;
         const int n = 6 * a.L, nt = 256;   // the CTA shape of pg_dense_kernel
@@ -75,14 +116,16 @@ struct HostLauncher {
 }  // namespace
 
 extern "C" {
-// same argument meaning as lvio2d_pose_graph_solve; opt5 = {max_iters, function_tol, gradient_tol, parameter_tol, initial_radius}
+// same argument meaning as lvio2d_pose_graph_solve (+ segments: the LVIO2D_PG_SEGMENTS knob, 0 = plain path); opt5 = {max_iters, function_tol, gradient_tol, parameter_tol, initial_radius}
 int pgh_solve(const Consts* C, const double* opt5, int32_t n_poses, double* poses, int32_t n_edges, const int32_t* edge_index, const double* edge_tf,
-              const double* edge_weight, const double* sqrt_info, int32_t ground_p, int32_t ground_q, lvio2d_summary* summary, int32_t* launches) {
+              const double* edge_weight, const double* sqrt_info, int32_t ground_p, int32_t ground_q, lvio2d_summary* summary, int32_t* launches,
+              int32_t segments) {
     std::vector<int32_t> ints;
     Args a;
     std::memset(&a, 0, sizeof(a));
     a.K = n_poses; a.E = n_edges;
-    if (!pg_topology(n_poses, n_edges, edge_index, ints, &a.L)) return -1;
+    a.P = pg_segments(n_poses, segments);
+    if (!pg_topology(n_poses, n_edges, edge_index, ints, &a.L, a.P)) return -1;
     a.fixed = n_edges > 0 ? edge_index[0] : -1;
     a.ground_p = ground_p; a.ground_q = ground_q;
     a.C = *C;

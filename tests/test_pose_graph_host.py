@@ -28,7 +28,7 @@ def pgh(tmp_path_factory):
     return C.CDLL(out)
 
 
-def host_solve(pgh, consts, P, poses, edges, tfs, ws, Jn, ground_p=True, ground_q=True):
+def host_solve(pgh, consts, P, poses, edges, tfs, ws, Jn, ground_p=True, ground_q=True, segments=0):
     x = np.array(poses, dtype=np.float64).reshape(-1, 6).copy()
     ei = np.ascontiguousarray(edges, dtype=np.int32).reshape(-1, 2)
     et = np.ascontiguousarray(tfs, dtype=np.float64).reshape(-1, 12)
@@ -39,7 +39,7 @@ def host_solve(pgh, consts, P, poses, edges, tfs, ws, Jn, ground_p=True, ground_
     summ = np.zeros(1, dtype=abi.SUMMARY_DTYPE)
     launches = C.c_int32(0)
     rc = pgh.pgh_solve(C.byref(consts), d(opt), len(x), d(x), len(ei), ei.ctypes.data_as(C.POINTER(C.c_int32)), d(et), d(ew), d(Jn),
-                       int(ground_p), int(ground_q), summ.ctypes.data_as(C.c_void_p), C.byref(launches))
+                       int(ground_p), int(ground_q), summ.ctypes.data_as(C.c_void_p), C.byref(launches), int(segments))
     assert rc == 0
     return x, summ, launches.value
 
@@ -95,6 +95,27 @@ def test_host_run_of_the_device_solve_matches_oracle(pgh, consts, oracle, K, loo
     assert np.abs(got - want).max() < 1e-7
 
 
+@pytest.mark.parametrize("K,loops,segments", [(40, [(30, 4), (12, 25), (39, 20)], 4), (40, [(30, 4), (12, 25), (39, 20)], 10), (24, [], 3),
+                                              (200, [(190, 3), (100, 20), (150, 40), (199, 80), (60, 160)], 16),
+                                              (200, [(190, 3), (100, 20), (150, 40), (199, 80), (60, 160)], 50), (97, [(90, 7)], 7)])
+def test_partitioned_solve_matches_oracle(pgh, consts, oracle, K, loops, segments):
+    """pose_graph_segments.cuh (opt-in): the chain cut into segments, separators solved by a reduced block-tridiagonal
+    system — same minimiser trajectory as the dense oracle (also with the constant key frame inside a segment, a loop
+    edge ending on a separator, and more segments than K / 4 allows, which clamps)."""
+    P = L.corridor_params(max_iters=50)
+    truth, init, edges, tfs, ws = graph_with_loops(K, loops, seed=4 + K)
+    Jn = edge_noise_J()
+    want, ws_summ = oracle.pose_graph_solve(P, init, edges, tfs, ws, Jn, ground_p=True, ground_q=False)
+    got, summ, launches = host_solve(pgh, consts, P, init, edges, tfs, ws, Jn, True, False, segments=segments)
+    plain, _, plain_launches = host_solve(pgh, consts, P, init, edges, tfs, ws, Jn, True, False)
+    assert launches > plain_launches      # the partitioned sequence really ran
+    for key in ("iterations", "termination", "num_successful_steps", "num_unsuccessful_steps"):
+        assert summ[key][0] == ws_summ[key][0], key
+    assert abs(summ["final_cost"][0] - ws_summ["final_cost"][0]) <= 1e-7 * max(1.0, ws_summ["final_cost"][0])
+    assert np.abs(got - want).max() < 1e-7
+    assert np.abs(got - plain).max() < 1e-9
+
+
 def test_kinked_problem_after_50_iterations(pgh, consts, oracle):
     """The reference's full back-end problem (both ground factors, Ceres' default 50 iterations): still within the
     north-star tolerance class of the oracle's run (5e-3 m / rad here, see above) and four decades below the start cost."""
@@ -117,7 +138,7 @@ def test_invalid_graph_is_rejected(pgh, consts):
     opt = np.array([5, 1e-6, 1e-10, 1e-8, 1e4])
     summ = np.zeros(1, dtype=abi.SUMMARY_DTYPE)
     rc = pgh.pgh_solve(C.byref(consts), d(opt), len(x), d(x), len(bad), bad.ctypes.data_as(C.POINTER(C.c_int32)), d(tfs.reshape(-1).copy()),
-                       d(ws.copy()), d(edge_noise_J().reshape(-1).copy()), 1, 1, summ.ctypes.data_as(C.c_void_p), None)
+                       d(ws.copy()), d(edge_noise_J().reshape(-1).copy()), 1, 1, summ.ctypes.data_as(C.c_void_p), None, 0)
     assert rc == -1
 
 
