@@ -25,7 +25,7 @@ def rel(a, b):
 
 
 def test_golden_files_present():
-    assert sorted(os.path.basename(f) for f in glob.glob(os.path.join(GOLD, "*.npz"))) == sorted([w + ".npz" for w in WINDOWS] + ["factors.npz", "lines_scans.npz"])
+    assert sorted(os.path.basename(f) for f in glob.glob(os.path.join(GOLD, "*.npz"))) == sorted([w + ".npz" for w in WINDOWS] + ["factors.npz", "lines_scans.npz", "pose_graph.npz"])
 
 
 @pytest.mark.parametrize("name", WINDOWS)
@@ -101,3 +101,39 @@ def test_gpu_factors_reproduce_golden():
         l = z["laser_lines"]
         r, J = c.eval_laser_factor(l[0], l[1], l[2], l[3], z["state_i"][:6], z["laser_pose_j"])
         assert rel(r, z["laser_res"]) < 1e-10 and rel(J, z["laser_jac"]) < 1e-9
+
+
+# ---- back-end pose graph (tests/golden/pose_graph.npz, scripts/make_golden_pose_graph.py)
+POSE_GRAPHS = ["ring24", "loops40", "loops40_ground_q_12it"]
+
+
+def load_pose_graph(name):
+    z = np.load(os.path.join(GOLD, "pose_graph.npz"))
+    g = {k.split("__", 1)[1]: z[k] for k in z.files if k.startswith(name + "__")}
+    return g, z["sqrt_info"], L.corridor_params(max_iters=int(g["max_iters"]))
+
+
+@pytest.mark.parametrize("name", POSE_GRAPHS)
+def test_oracle_reproduces_golden_pose_graph(oracle, name):
+    g, Jn, P = load_pose_graph(name)
+    x, s = oracle.pose_graph_solve(P, g["init"], g["edges"], g["tfs"], g["weights"], Jn, ground_p=True, ground_q=bool(g["ground_q"]))
+    assert np.array_equal(s["iterations"], g["iterations"]) and np.array_equal(s["termination"], g["termination"])
+    assert rel(s["final_cost"], g["final_cost"]) < 1e-9 and np.abs(x - g["solved"]).max() < 1e-9
+    e = len(g["edges"]) - 1
+    r, J = oracle.eval_edge_factor(g["tfs"][e], g["weights"][e], Jn, g["init"][g["edges"][e][0]], g["init"][g["edges"][e][1]])
+    assert rel(r, g["last_edge_res"]) < 1e-12 and rel(J, g["last_edge_jac"]) < 1e-12
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", POSE_GRAPHS)
+def test_cuda_reproduces_golden_pose_graph(name):
+    from lvio2d_b200.solver import Context
+
+    g, Jn, P = load_pose_graph(name)
+    with Context(P) as ctx:
+        x, s = ctx.pose_graph_solve(g["init"], g["edges"], g["tfs"], g["weights"], Jn, True, bool(g["ground_q"]))
+        e = len(g["edges"]) - 1
+        r, J = ctx.eval_edge_factor(g["tfs"][e], g["weights"][e], Jn, g["init"][g["edges"][e][0]], g["init"][g["edges"][e][1]])
+    assert np.array_equal(s["termination"], g["termination"]) and abs(int(s["iterations"][0]) - int(g["iterations"][0])) <= 1
+    assert rel(s["final_cost"], g["final_cost"]) < 1e-6 and np.abs(x - g["solved"]).max() < 1e-6
+    assert rel(r, g["last_edge_res"]) < 1e-11 and rel(J, g["last_edge_jac"]) < 1e-9
