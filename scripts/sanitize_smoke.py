@@ -1,6 +1,6 @@
 """Small end-to-end exercise of every kernel for compute-sanitizer (memcheck / racecheck / initcheck):
 every thread-group shape of window_kernel, both factor kernels, the fused small-batch solve, the three-kernel loop,
-the split-phase (sharded) entry points and the three laser front-end kernels."""
+the split-phase (sharded) entry points, the three laser front-end kernels and the pose-graph kernels (both paths)."""
 import os, sys
 R = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, R); sys.path.insert(0, os.path.join(R, "tests"))
@@ -39,3 +39,14 @@ with Context(L.corridor_params()) as c:
     nm, m = c.match_lines(lp, n, lines, n, lines, pose, pose, point_offset1=off, points1=pts.reshape(-1, 2), index_range1=rng, point_count1=cnt)
     nm2, m2 = c.match_lines(lp, n, lines, n, lines, pose, pose, kk=1)
 print("ok front-end", cnt, n, nm, nm2)
+# back-end pose graph: plain path and the opt-in partitioned path (pose_graph_segments.cuh)
+from test_oracle_pose_graph import edge_noise_J
+from test_pose_graph_host import graph_with_loops
+truth, init, edges, tfs, ws = graph_with_loops(40, [(30, 4), (12, 25), (39, 20)], seed=44)
+for segs in ("0", "4"):
+    os.environ["LVIO2D_PG_SEGMENTS"] = segs
+    with Context(L.corridor_params(max_iters=4)) as c:
+        x, s = c.pose_graph_solve(init, edges, tfs, ws, edge_noise_J(), True, True)
+        r, J = c.eval_edge_factor(tfs[0], 1.0, edge_noise_J(), init[0], init[1])
+    print("ok pose graph, segments", segs, s["iterations"][0], s["final_cost"][0])
+os.environ.pop("LVIO2D_PG_SEGMENTS", None)
