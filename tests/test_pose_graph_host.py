@@ -167,3 +167,27 @@ def test_keyframe_manager_mirror_on_a_recording_context():
     assert (gp, gq) == (True, False)
     assert np.array_equal(Jn, edge_noise_J()) and np.array_equal(Jn, product_J((0.1,) * 3, (0.01,) * 3))
     assert np.array_equal(km.keyframe_queue[2].p, np.full(3, 3.0)) and np.allclose(km.keyframe_queue[2].q, 1.2)
+
+
+def test_edge_cases_match_oracle(pgh, consts, oracle):
+    """No edges at all (ground factors only, nothing constant), a single key frame, two key frames with one edge (one free
+    pose), and an edge list with a reversed neighbour edge first (its index1 = key frame 1 is the constant one) plus a
+    duplicated edge."""
+    Jn = edge_noise_J()
+    truth, init, edges, tfs, ws = graph_with_loops(6, [], seed=3)
+    init = init + np.random.default_rng(0).normal(0, 0.01, init.shape)
+    P = L.corridor_params(max_iters=10)
+    e0, t0, w0 = np.zeros((0, 2), np.int32), np.zeros((0, 12)), np.zeros(0)
+    rev = edges.copy()
+    rev[0] = (1, 0)
+    tf_rev = tfs.copy()
+    tf_rev[0] = np.linalg.inv(np.vstack([tfs[0], [0, 0, 0, 1]]))[:3]
+    cases = [(init, e0, t0, w0, False), (init[:1], e0, t0, w0, False), (init[:2], edges[:1], tfs[:1], ws[:1], True),
+             (init, np.vstack([rev, rev[2:3]]), np.concatenate([tf_rev, tf_rev[2:3]]), np.r_[ws, 2.0], False)]
+    for x0, ed, tf, w, gq in cases:
+        want, s1 = oracle.pose_graph_solve(P, x0, ed, tf, w, Jn, ground_p=True, ground_q=gq)
+        got, s2, _ = host_solve(pgh, consts, P, x0, ed, tf, w, Jn, True, gq)
+        for key in ("iterations", "termination", "num_successful_steps"):
+            assert s1[key][0] == s2[key][0], key
+        assert np.abs(got - want).max() < 1e-9
+    assert np.array_equal(got[1], init[1])      # last case: key frame 1 is the constant one
