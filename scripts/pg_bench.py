@@ -54,8 +54,49 @@ def ring_graph(K, loops, seed):
     return init, np.array(edges, np.int32), np.array(tfs), np.array(ws)
 
 
+def cpu_port():
+    """The same algorithm (block-tridiagonal + loop-edge capacitance, same minimiser loop) as scalar C++ on one host core:
+    tests/native/pose_graph_host.cpp — the test suite's thread-by-thread host run of the kernel bodies — built with -O3.
+    A fairer CPU number than the dense oracle; the reference's own SPARSE_SCHUR cannot be built here."""
+    import ctypes as C
+    import subprocess
+    import tempfile
+
+    from test_device_math_host import Consts
+
+    so = os.path.join(tempfile.mkdtemp(prefix="pgh_"), "libpgh.so")
+    subprocess.check_call(["g++", "-O3", "-march=native", "-std=c++17", "-fPIC", "-shared", "-Wno-unknown-pragmas", "-x", "c++",
+                           os.path.join(ROOT, "tests", "native", "pose_graph_host.cpp"), "-o", so])
+    lib = C.CDLL(so)
+    P = L.corridor_params()
+    c = Consts()
+    c.T_il[:] = list(P.T_imu_to_laser)
+    c.T_io[:] = list(P.T_imu_to_wheel)
+    c.g = P.g
+    c.laser_sqrt_info, c.ground_p_sqrt_info, c.ground_q_sqrt_info = 1.0 / P.line_to_line_sigma, 1.0 / P.manifold_p_sigma, 1.0 / P.manifold_q_sigma
+
+    def solve(init, edges, tfs, ws, Jn):
+        from lvio2d_b200 import abi
+
+        dp = C.POINTER(C.c_double)
+        x = np.array(init, dtype=np.float64).copy()
+        ei = np.ascontiguousarray(edges, dtype=np.int32)
+        et, ew, J = np.ascontiguousarray(tfs, dtype=np.float64), np.ascontiguousarray(ws, dtype=np.float64), np.ascontiguousarray(Jn, dtype=np.float64)
+        opt = np.array([50, 1e-6, 1e-10, 1e-8, 1e4])
+        summ = np.zeros(1, dtype=abi.SUMMARY_DTYPE)
+        t0 = time.perf_counter()
+        rc = lib.pgh_solve(C.byref(c), opt.ctypes.data_as(dp), len(x), x.ctypes.data_as(dp), len(ei), ei.ctypes.data_as(C.POINTER(C.c_int32)),
+                           et.ctypes.data_as(dp), ew.ctypes.data_as(dp), J.ctypes.data_as(dp), 1, 0, summ.ctypes.data_as(C.c_void_p), None, 0)
+        dt = time.perf_counter() - t0
+        assert rc == 0
+        return x, summ, dt
+
+    return solve
+
+
 def main():
     cpu = "--no-cpu" not in sys.argv
+    port = cpu_port() if cpu else None
     Jn = edge_noise_J((0.1,) * 3, (0.01,) * 3)
     out = {"unit": "ms per LM iteration (wall clock of lvio2d_pose_graph_solve, host buffers, ground_p on, ground_q off)", "graphs": []}
     for K, nl in ((200, 5), (1000, 8), (4000, 16)):
@@ -77,6 +118,11 @@ def main():
             dc = time.perf_counter() - t0
             row["cpu_oracle_dense_1core"] = {"wall_ms": round(dc * 1e3, 3), "iterations": int(so["iterations"][0]),
                                               "max_abs_pose_diff": float(np.abs(got - want).max())}
+        if port is not None:
+            xp, sp, dp_ = port(init, edges, tfs, ws, Jn)
+            row["cpu_port_same_algorithm_1core"] = {"wall_ms": round(dp_ * 1e3, 3), "iterations": int(sp["iterations"][0]),
+                                                    "ms_per_iteration": round(dp_ * 1e3 / max(1, int(sp["iterations"][0])), 4),
+                                                    "max_abs_pose_diff": float(np.abs(got - xp).max())}
         out["graphs"].append(row)
     print(json.dumps(out))
 
