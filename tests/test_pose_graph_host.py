@@ -191,3 +191,26 @@ def test_edge_cases_match_oracle(pgh, consts, oracle):
             assert s1[key][0] == s2[key][0], key
         assert np.abs(got - want).max() < 1e-9
     assert np.array_equal(got[1], init[1])      # last case: key frame 1 is the constant one
+
+
+def exact_graph(K, n_loops, seed):
+    """Known-answer graph: every edge is the exact relative transform of the truth (a ring in the ground plane, so the
+    ground_p factor is satisfied too) — the unique minimiser is the truth at cost 0; start = truth + N(0, 5 cm / 0.02 rad)."""
+    truth, _, _, _, _ = make_graph(K=K, seed=seed)
+    Ts = [T_of(x) for x in truth]
+    edges = [(k, k + 1) for k in range(K - 1)] + [(K - 1, 0)] + [(K - 10 - 7 * i, 5 + 11 * i) for i in range(n_loops)]
+    tfs = np.array([(np.linalg.inv(Ts[i]) @ Ts[j])[:3] for i, j in edges])
+    ws = np.r_[np.ones(K - 1), np.full(n_loops + 1, 10.0)]
+    g = np.random.default_rng(seed)
+    init = truth + np.c_[g.normal(0, 0.05, (K, 3)), g.normal(0, 0.02, (K, 3))]
+    init[0] = truth[0]
+    return truth, init, np.array(edges, np.int32), tfs, ws
+
+
+@pytest.mark.parametrize("segments", [0, 16])
+def test_known_answer_graph_is_recovered(pgh, consts, segments):
+    """Size-independent property (no oracle needed): the exact graph's truth is recovered; also the full-size GPU check."""
+    truth, init, edges, tfs, ws = exact_graph(300, 6, seed=7)
+    got, summ, _ = host_solve(pgh, consts, L.corridor_params(max_iters=50), init, edges, tfs, ws, edge_noise_J(), True, False, segments=segments)
+    assert summ["termination"][0] in (1, 2, 3) and summ["final_cost"][0] < 1e-9
+    assert np.abs(got - truth).max() < 1e-6

@@ -10,7 +10,7 @@ import pytest
 
 import lvio2d_b200 as L
 from test_oracle_pose_graph import T_of, edge_noise_J
-from test_pose_graph_host import graph_with_loops
+from test_pose_graph_host import exact_graph, graph_with_loops
 
 pytestmark = pytest.mark.gpu
 
@@ -68,6 +68,16 @@ def test_kinked_problem_after_50_iterations(oracle):
     assert summ["iterations"][0] == 50 and summ["final_cost"][0] < 1e-2 * summ["initial_cost"][0]
     assert summ["final_cost"][0] < 4.0 * ws_summ["final_cost"][0]
     assert np.abs(got - want).max() < 2e-2
+
+
+def test_full_size_known_answer_graph_is_recovered():
+    """4000 key frames, 17 loop edges (103 right-hand sides) — far beyond what the dense oracle can do; the exact graph's
+    truth is the unique minimiser (cost 0), so the result is checked against the truth itself."""
+    truth, init, edges, tfs, ws = exact_graph(4000, 16, seed=7)
+    with make_ctx(max_iters=50) as ctx:
+        got, summ = ctx.pose_graph_solve(init, edges, tfs, ws, edge_noise_J(), True, False)
+    assert summ["termination"][0] in (1, 2, 3) and summ["final_cost"][0] < 1e-9
+    assert np.abs(got - truth).max() < 1e-6
 
 
 def test_errors_are_reported():
