@@ -41,6 +41,7 @@ class KeyframeManager:
     """keyframe_queue + seq_edges + loop_edges and `solve()`; poses are written back in place like Ceres does through
     the raw parameter pointers (keyframe_manager.cpp:738-741)."""
     ctx: object                                   # solver.Context created with the back-end's iteration cap (Ceres default 50)
+    # defaults: config/corridor.yaml:106 (loop_edge_k), :110-111 (loop_sigma_p / q), :114-115 (use_ground_*_factor)
     loop_sigma_p: tuple = (0.1, 0.1, 0.1)
     loop_sigma_q: tuple = (0.01, 0.01, 0.01)
     loop_edge_k: float = 10.0
