@@ -10,15 +10,19 @@
 // Structure of the normal equations.  Key frames are 6-DoF nodes; an edge between neighbours (|i - j| = 1, the
 // reference's seq_edges) puts a 6x6 block on the first off-diagonal, every other edge (loop_edges) is a rank-6 update:
 //     H + D_lm = T + U U^T,   T block-tridiagonal (band edges + ground factors + LM diagonal),   U = [J_e^T]_{e in loops}
-// so one LM step is  (1) a block-tridiagonal factorisation of T (one CTA, 36 threads = one 6x6 block, sequential in k),  (2) T^-1 [-g | U] for 1 + 6L right-hand sides (one thread
-// each),  (3) the 6L x 6L capacitance system  (I + U^T T^-1 U) w = U^T T^-1 (-g)  (one CTA),  (4) delta = x0 - Z w.
+// so one LM step is
+//   (1) a block-tridiagonal factorisation of T (one CTA, 36 threads = one 6x6 block, sequential in k),
+//   (2) T^-1 [-g | U] for 1 + 6L right-hand sides (one thread each),
+//   (3) the 6L x 6L capacitance system  (I + U^T T^-1 U) w = U^T T^-1 (-g)  (one CTA),
+//   (4) delta = x0 - Z w.
 // Nothing dense of size 6K is ever formed; the solve is exact (as the reference's SPARSE_SCHUR is), not iterative.
+// pose_graph_segments.cuh (opt-in) cuts the two sequential chains of (1) and (2) into concurrently processed segments.
 //
 // How the code is organised.  Every kernel is `thread t of n runs pg_thread<KID>(args, t)` with no intra-block
 // communication; the cooperative kernels (the block-tridiagonal factorisation, the dense capacitance Cholesky and the
-// reduction of the per-item partial sums) are written as phases separated by __syncthreads.  The bodies are __host__ __device__, so the CPU test
-// suite (tests/native/pose_graph_host.cpp) runs the SAME bodies and the SAME minimiser loop (pg_minimize) thread by
-// thread and checks them against the oracle — a formula / control-flow check without a GPU, not a fallback: the product
+// reduction of the per-item partial sums) are written as phases separated by __syncthreads.  The bodies are
+// __host__ __device__, so the CPU test suite (tests/native/pose_graph_host.cpp) runs the SAME bodies and the SAME
+// minimiser loop (pg_minimize) thread by thread and checks them against the oracle — a formula / control-flow check without a GPU, not a fallback: the product
 // entry point (lvio2d_pose_graph_solve, lvio2d_api.cu) only ever launches the kernels.
 //
 // The minimiser is Ceres 1.14's TrustRegionMinimizer + LevenbergMarquardtStrategy (jacobi scaling, monotonic steps), the
