@@ -1102,6 +1102,12 @@ struct PgDeviceLauncher {
         return (err = cudaGetLastError()) == cudaSuccess;
     }
     bool seg(int kid, const pg::Args& a) {
+        if (kid == pg::KS_TRISOLVE && a.stage) {
+            const dim3 grid(a.P, (pg::ncol_x(a) + 127) / 128);
+            pg::pg_seg_trisolve_staged_kernel<<<grid, 128, 0, ctx->stream>>>(a);
+            ctx->launches += 1;
+            return (err = cudaGetLastError()) == cudaSuccess;
+        }
         switch (kid) {
             case pg::KS_TRISOLVE: return seg_go<pg::KS_TRISOLVE>(a);
             case pg::KS_REDUCED_BLOCKS: return seg_go<pg::KS_REDUCED_BLOCKS>(a);
@@ -1143,6 +1149,8 @@ int pg_setup(lvio2d_ctx* ctx, pg::Args& a, int32_t n_poses, const double* poses,
     // LVIO2D_PG_SEGMENTS=<P>: cut the chain into P segments (pose_graph_segments.cuh; opt-in until confirmed on a B200)
     const char* seg_env = std::getenv("LVIO2D_PG_SEGMENTS");
     a.P = pg::pg_segments(n_poses, seg_env ? std::atoi(seg_env) : 0);
+    const char* stage_env = std::getenv("LVIO2D_PG_STAGE");   // segment solves stage their blocks in shared memory
+    a.stage = (a.P > 1 && stage_env && std::atoi(stage_env) != 0) ? 1 : 0;
     if (!pg::pg_topology(n_poses, n_edges, edge_index, ints, &a.L, a.P)) return fail(ctx, LVIO2D_ERR_INVALID_ARG, "pose graph: edge index out of range or self edge");
     a.fixed = fixed;
     a.ground_p = ground_p != 0; a.ground_q = ground_q != 0;

@@ -89,6 +89,7 @@ struct Args {
     int32_t* flags;  // [2] non-positive pivot in the tridiagonal / capacitance factorisation
     // partitioned solve (pose_graph_segments.cuh; P <= 1: off, everything below unused)
     int P;                     // segments
+    int stage;                 // != 0: segment solves stage their blocks in shared memory (LVIO2D_PG_STAGE)
     const int32_t* node_seg;   // [K] segment of an interior key frame, or -(i + 1) for separator i
     int32_t* segflag;          // [P]
     double* Zx;                // [6K][ncol + 12] segment solutions: right-hand sides + the two spikes

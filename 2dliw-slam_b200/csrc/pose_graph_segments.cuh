@@ -1,6 +1,7 @@
 // pose_graph_segments.cuh — the block-tridiagonal solve of pose_graph.cuh with its sequential chains cut into P segments.
 //
-// STATUS: opt-in (LVIO2D_PG_SEGMENTS=<P>, default off).  Written at the end of round 1 from the launch list in
+// STATUS: opt-in (LVIO2D_PG_SEGMENTS=<P>, default off; LVIO2D_PG_STAGE=1 additionally stages the segment solves' blocks in
+// shared memory).  Written at the end of round 1 from the launch list in
 // profiles/r1_pose_graph.md (the two sequential chains over the key frames are 94 % of an LM iteration); verified on the
 // CPU by the thread-by-thread host run against the oracle (tests/test_pose_graph_host.py), cross-compiled for sm_100a,
 // NOT yet run on a B200 — the default path stays the one that was.
@@ -127,50 +128,87 @@ LV_HD double global_rhs(const Args& a, const ColumnInfo& ci, int col, int k, int
     const double* J = a.EJ + (size_t)ci.e * 78;
     return (k == ci.ie) ? J[q * 6 + ci.rho] : ((k == ci.je) ? J[36 + q * 6 + ci.rho] : 0.0);
 }
-// forward / backward block substitution of one right-hand side over a chain; Z[(6k + q) * ncz + col].
-// kind 0: global columns and (col >= ncol) the two spikes of the segment; kind 1: the right-hand side is in Z already.
-LV_HD void chain_trisolve(const Args& a, const Chain& ch, double* Z, int ncz, int col, int kind) {
-    const ColumnInfo ci = column_info(a, kind == 0 ? col : 0);
-    const bool spike = kind == 0 && col >= a.ncol;
-    const bool left = spike && (col - a.ncol) < 6;
-    const int sj = spike ? (col - a.ncol) % 6 : 0;
-    double yp[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0}, b[6];
-    for (int k = ch.lo; k <= ch.hi; ++k) {
-        for (int q = 0; q < 6; ++q) {
-            if (kind == 1) b[q] = Z[(size_t)(6 * k + q) * ncz + col];
-            else if (!spike) b[q] = global_rhs(a, ci, col, k, q);
-            else if (left) b[q] = (k == ch.lo && ch.lo > 0) ? a.O[(size_t)(ch.lo - 1) * 36 + q * 6 + sj] : 0.0;       // O_{lo-1}[:, sj]
-            else b[q] = (k == ch.hi && ch.hi < a.K - 1) ? a.O[(size_t)ch.hi * 36 + sj * 6 + q] : 0.0;                // O_hi^T[:, sj]
-        }
+// what a thread needs to know about its right-hand side column
+struct ColumnCtx { ColumnInfo ci; bool spike, left; int sj; };
+LV_HD ColumnCtx column_ctx(const Args& a, int col, int kind) {
+    ColumnCtx cc;
+    cc.ci = column_info(a, kind == 0 ? col : 0);
+    cc.spike = kind == 0 && col >= a.ncol;
+    cc.left = cc.spike && (col - a.ncol) < 6;
+    cc.sj = cc.spike ? (col - a.ncol) % 6 : 0;
+    return cc;
+}
+// right-hand side block of key frame k.  kind 0: global columns and (col >= ncol) the two spikes of the segment;
+// kind 1: the right-hand side is in Z already.
+LV_HD void chain_rhs(const Args& a, const Chain& ch, const double* Z, int ncz, int col, int kind, const ColumnCtx& cc, int k, double* b) {
+    for (int q = 0; q < 6; ++q) {
+        if (kind == 1) b[q] = Z[(size_t)(6 * k + q) * ncz + col];
+        else if (!cc.spike) b[q] = global_rhs(a, cc.ci, col, k, q);
+        else if (cc.left) b[q] = (k == ch.lo && ch.lo > 0) ? a.O[(size_t)(ch.lo - 1) * 36 + q * 6 + cc.sj] : 0.0;    // O_{lo-1}[:, sj]
+        else b[q] = (k == ch.hi && ch.hi < a.K - 1) ? a.O[(size_t)ch.hi * 36 + cc.sj * 6 + q] : 0.0;                 // O_hi^T[:, sj]
+    }
+}
+// n forward steps from key frame k0; Mblk = M[k0 .. k0 + n - 1] (global or staged in shared memory); yp carries y_{k0-1}
+LV_HD void forward_steps(const Args& a, const Chain& ch, double* Z, int ncz, int col, int kind, const ColumnCtx& cc, int k0, int n,
+                         const double* Mblk, double* yp) {
+    double b[6];
+    for (int s = 0; s < n; ++s) {
+        const int k = k0 + s;
+        chain_rhs(a, ch, Z, ncz, col, kind, cc, k, b);
         if (k > ch.lo) {
-            const double* Mk = ch.M + (size_t)k * 36;
+            const double* Mk = Mblk + (size_t)s * 36;
             for (int q = 0; q < 6; ++q) {
-                double s = 0.0;
-                for (int i = 0; i < 6; ++i) s += lv_ldg(Mk + q * 6 + i) * yp[i];
-                b[q] -= s;
+                double t = 0.0;
+                for (int i = 0; i < 6; ++i) t += Mk[q * 6 + i] * yp[i];
+                b[q] -= t;
             }
         }
         for (int q = 0; q < 6; ++q) { yp[q] = b[q]; Z[(size_t)(6 * k + q) * ncz + col] = b[q]; }
     }
-    double xn[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
-    for (int k = ch.hi; k >= ch.lo; --k) {
-        const double* Si = ch.Sinv + (size_t)k * 36;
-        for (int q = 0; q < 6; ++q) yp[q] = Z[(size_t)(6 * k + q) * ncz + col];
+}
+// n backward steps from key frame k0 + n - 1 down to k0; Sblk = Sinv[k0 ..], Mnext = M[k0 + 1 ..]; xn carries x_{k0+n}
+LV_HD void backward_steps(const Chain& ch, double* Z, int ncz, int col, int k0, int n, const double* Sblk, const double* Mnext, double* xn) {
+    double y[6], b[6];
+    for (int s = n - 1; s >= 0; --s) {
+        const int k = k0 + s;
+        const double* Si = Sblk + (size_t)s * 36;
+        for (int q = 0; q < 6; ++q) y[q] = Z[(size_t)(6 * k + q) * ncz + col];
         for (int q = 0; q < 6; ++q) {
-            double s = 0.0;
-            for (int i = 0; i < 6; ++i) s += lv_ldg(Si + q * 6 + i) * yp[i];
-            b[q] = s;
+            double t = 0.0;
+            for (int i = 0; i < 6; ++i) t += Si[q * 6 + i] * y[i];
+            b[q] = t;
         }
         if (k < ch.hi) {
-            const double* Mn = ch.M + (size_t)(k + 1) * 36;
+            const double* Mn = Mnext + (size_t)s * 36;
             for (int q = 0; q < 6; ++q) {
-                double s = 0.0;
-                for (int i = 0; i < 6; ++i) s += lv_ldg(Mn + i * 6 + q) * xn[i];
-                b[q] -= s;
+                double t = 0.0;
+                for (int i = 0; i < 6; ++i) t += Mn[i * 6 + q] * xn[i];
+                b[q] -= t;
             }
         }
         for (int q = 0; q < 6; ++q) { xn[q] = b[q]; Z[(size_t)(6 * k + q) * ncz + col] = b[q]; }
     }
+}
+// forward / backward block substitution of one right-hand side over a whole chain, blocks straight from global memory
+LV_HD void chain_trisolve(const Args& a, const Chain& ch, double* Z, int ncz, int col, int kind) {
+    const ColumnCtx cc = column_ctx(a, col, kind);
+    double v[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+    forward_steps(a, ch, Z, ncz, col, kind, cc, ch.lo, ch.hi - ch.lo + 1, ch.M + (size_t)ch.lo * 36, v);
+    for (int q = 0; q < 6; ++q) v[q] = 0.0;
+    backward_steps(ch, Z, ncz, col, ch.lo, ch.hi - ch.lo + 1, ch.Sinv + (size_t)ch.lo * 36, ch.M + (size_t)(ch.lo + 1) * 36, v);
+}
+// the same with the blocks of STAGE_STEPS steps staged in shared memory by the CTA (a.stage != 0): one L2 round trip per
+// STAGE_STEPS steps instead of 4.5 per step (profiles/r1_pose_graph.md).  stage_copy is the cooperative load of a phase.
+enum { STAGE_STEPS = 16 };
+struct StageTile { double M[STAGE_STEPS * 36], S[STAGE_STEPS * 36]; };
+LV_HD void stage_copy(double* dst, const double* src, int count, int tid, int nt) {
+    for (int i = tid; i < count; i += nt) dst[i] = src[i];
+}
+// the blocks of the backward chunk [k0, k0 + n): Sinv[k0 ..] and M[k0 + 1 ..] (the last one only if it exists)
+LV_HD void stage_backward(const Chain& ch, StageTile& T, int k0, int n, int tid, int nt) {
+    stage_copy(T.S, ch.Sinv + (size_t)k0 * 36, n * 36, tid, nt);
+    const int nm = (k0 + n <= ch.hi) ? n : n - 1;
+    stage_copy(T.M, ch.M + (size_t)(k0 + 1) * 36, nm * 36, tid, nt);
 }
 
 // ---- kernel bodies
@@ -254,6 +292,31 @@ LV_HD int seg_kernel_threads(const Args& a, int kid) {
 template <int KID> __global__ void __launch_bounds__(128) pg_seg_kernel(Args a, int n) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t < n) seg_thread<KID>(a, t);
+}
+// KS_TRISOLVE with staging: CTA (c, g) walks segment c for the columns [128 g, 128 g + 128)
+__global__ void __launch_bounds__(128) pg_seg_trisolve_staged_kernel(Args a) {
+    __shared__ StageTile T;
+    const int tid = threadIdx.x, nt = blockDim.x, ncx = ncol_x(a);
+    const Chain ch = segment_chain(a, blockIdx.x);
+    const int col = blockIdx.y * nt + tid;
+    const bool active = col < ncx;
+    const ColumnCtx cc = column_ctx(a, active ? col : 0, 0);
+    double v[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+    for (int k0 = ch.lo; k0 <= ch.hi; k0 += STAGE_STEPS) {
+        const int n = min((int)STAGE_STEPS, ch.hi - k0 + 1);
+        stage_copy(T.M, ch.M + (size_t)k0 * 36, n * 36, tid, nt);
+        __syncthreads();
+        if (active) forward_steps(a, ch, a.Zx, ncx, col, 0, cc, k0, n, T.M, v);
+        __syncthreads();
+    }
+    for (int q = 0; q < 6; ++q) v[q] = 0.0;
+    for (int k1 = ch.hi; k1 >= ch.lo; k1 -= STAGE_STEPS) {
+        const int k0 = max(ch.lo, k1 - (int)STAGE_STEPS + 1), n = k1 - k0 + 1;
+        stage_backward(ch, T, k0, n, tid, nt);
+        __syncthreads();
+        if (active) backward_steps(ch, a.Zx, ncx, col, k0, n, T.S, T.M, v);
+        __syncthreads();
+    }
 }
 // reduced == 0: CTA c factorises segment c (flag -> segflag[c]); reduced == 1: one CTA factorises the separator system
 // and folds every flag into flags[0]

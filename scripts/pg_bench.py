@@ -86,7 +86,7 @@ def cpu_port():
         summ = np.zeros(1, dtype=abi.SUMMARY_DTYPE)
         t0 = time.perf_counter()
         rc = lib.pgh_solve(C.byref(c), opt.ctypes.data_as(dp), len(x), x.ctypes.data_as(dp), len(ei), ei.ctypes.data_as(C.POINTER(C.c_int32)),
-                           et.ctypes.data_as(dp), ew.ctypes.data_as(dp), J.ctypes.data_as(dp), 1, 0, summ.ctypes.data_as(C.c_void_p), None, 0)
+                           et.ctypes.data_as(dp), ew.ctypes.data_as(dp), J.ctypes.data_as(dp), 1, 0, summ.ctypes.data_as(C.c_void_p), None, 0, 0)
         dt = time.perf_counter() - t0
         assert rc == 0
         return x, summ, dt

@@ -67,20 +67,22 @@ for K, nl in ((1000, 8), (4000, 16)):
     say(f"K={K} L={nl + 1}: {s2['iterations'][0]} LM iterations, cost {s2['initial_cost'][0]:.6g} -> {s2['final_cost'][0]:.6g}, wall {dt * 1e3:.1f} ms"
         f" ({dt * 1e3 / max(1, s2['iterations'][0]):.2f} ms / iteration), max |pose - truth| {np.abs(got[:, :3] - truth[:, :3]).max():.3g} m")
 # the opt-in partitioned solve (pose_graph_segments.cuh): parity against the plain path and its wall clock
-for K, nl, P in ((200, 5, 16), (1000, 8, 64), (4000, 16, 64), (4000, 16, 128)):
+for K, nl, P, stage in ((200, 5, 16, 0), (1000, 8, 64, 0), (4000, 16, 64, 0), (4000, 16, 128, 0), (1000, 8, 32, 1), (4000, 16, 64, 1), (4000, 16, 32, 1)):
     loops = [(K - 10 - 7 * i, 5 + 11 * i) for i in range(nl)]
     truth, init, edges, tfs, ws = graph_with_loops(K, loops, seed=K)
     os.environ.pop("LVIO2D_PG_SEGMENTS", None)
     with Context(L.corridor_params(max_iters=50)) as ctx:
         plain, s0 = ctx.pose_graph_solve(init, edges, tfs, ws, Jn, True, False)
     os.environ["LVIO2D_PG_SEGMENTS"] = str(P)
+    os.environ["LVIO2D_PG_STAGE"] = str(stage)
     with Context(L.corridor_params(max_iters=50)) as ctx:
         ctx.pose_graph_solve(init, edges, tfs, ws, Jn, True, False)
         t0 = time.perf_counter()
         got, s2 = ctx.pose_graph_solve(init, edges, tfs, ws, Jn, True, False)
         dt = time.perf_counter() - t0
     os.environ.pop("LVIO2D_PG_SEGMENTS", None)
+    os.environ.pop("LVIO2D_PG_STAGE", None)
     err = np.abs(got - plain).max()
-    say(f"segments={P} K={K} L={nl + 1}: iterations plain/partitioned {s0['iterations'][0]}/{s2['iterations'][0]}, max|dpose| {err:.3g}, wall {dt * 1e3:.1f} ms"
+    say(f"segments={P} stage={stage} K={K} L={nl + 1}: iterations plain/partitioned {s0['iterations'][0]}/{s2['iterations'][0]}, max|dpose| {err:.3g}, wall {dt * 1e3:.1f} ms"
         f" ({dt * 1e3 / max(1, s2['iterations'][0]):.2f} ms / iteration)", "PASS" if err < 1e-7 else "FAIL")
 out.close()

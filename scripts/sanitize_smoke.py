@@ -43,10 +43,12 @@ print("ok front-end", cnt, n, nm, nm2)
 from test_oracle_pose_graph import edge_noise_J
 from test_pose_graph_host import graph_with_loops
 truth, init, edges, tfs, ws = graph_with_loops(40, [(30, 4), (12, 25), (39, 20)], seed=44)
-for segs in ("0", "4"):
+for segs, stage in (("0", "0"), ("4", "0"), ("2", "1")):
     os.environ["LVIO2D_PG_SEGMENTS"] = segs
+    os.environ["LVIO2D_PG_STAGE"] = stage
     with Context(L.corridor_params(max_iters=4)) as c:
         x, s = c.pose_graph_solve(init, edges, tfs, ws, edge_noise_J(), True, True)
         r, J = c.eval_edge_factor(tfs[0], 1.0, edge_noise_J(), init[0], init[1])
-    print("ok pose graph, segments", segs, s["iterations"][0], s["final_cost"][0])
+    print("ok pose graph, segments", segs, "stage", stage, s["iterations"][0], s["final_cost"][0])
 os.environ.pop("LVIO2D_PG_SEGMENTS", None)
+os.environ.pop("LVIO2D_PG_STAGE", None)

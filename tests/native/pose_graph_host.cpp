@@ -2,6 +2,7 @@
 // __host__ __device__ and free of intra-block communication, so the CPU test-suite runs every "kernel" thread by thread
 // (and the two cooperative ones phase by phase) under the product's own minimiser loop and checks the result against the
 // oracle without a GPU.  This is NOT a CPU fallback of the product: it is compiled by tests/test_pose_graph_host.py only.
+#include <algorithm>
 #include <cstring>
 #include <vector>
 
@@ -72,8 +73,37 @@ struct HostLauncher {
         const int n = seg_kernel_threads(a, KID);
         for (int t = 0; t < n; ++t) seg_thread<KID>(a, t);
     }
+    // pg_seg_trisolve_staged_kernel: per CTA (segment c, column group g) the chunk loads and the chunk steps as phases;
+    // the carried 6-vector of every thread lives in `carry` between phases
+    static void staged_trisolve(const Args& a) {
+        const int nt = 128, ncx = ncol_x(a);
+        for (int c = 0; c < a.P; ++c)
+            for (int g = 0; g * nt < ncx; ++g) {
+                const Chain ch = segment_chain(a, c);
+                StageTile T;
+                std::vector<double> carry(6 * nt, 0.0);
+                for (int k0 = ch.lo; k0 <= ch.hi; k0 += STAGE_STEPS) {
+                    const int n = std::min((int)STAGE_STEPS, ch.hi - k0 + 1);
+                    for (int tid = 0; tid < nt; ++tid) stage_copy(T.M, ch.M + (size_t)k0 * 36, n * 36, tid, nt);
+                    for (int tid = 0; tid < nt; ++tid) {
+                        const int col = g * nt + tid;
+                        if (col < ncx) forward_steps(a, ch, a.Zx, ncx, col, 0, column_ctx(a, col, 0), k0, n, T.M, &carry[6 * tid]);
+                    }
+                }
+                std::fill(carry.begin(), carry.end(), 0.0);
+                for (int k1 = ch.hi; k1 >= ch.lo; k1 -= STAGE_STEPS) {
+                    const int k0 = std::max(ch.lo, k1 - (int)STAGE_STEPS + 1), n = k1 - k0 + 1;
+                    for (int tid = 0; tid < nt; ++tid) stage_backward(ch, T, k0, n, tid, nt);
+                    for (int tid = 0; tid < nt; ++tid) {
+                        const int col = g * nt + tid;
+                        if (col < ncx) backward_steps(ch, a.Zx, ncx, col, k0, n, T.S, T.M, &carry[6 * tid]);
+                    }
+                }
+            }
+    }
     bool seg(int kid, const Args& a) {
         ++launches;
+        if (kid == KS_TRISOLVE && a.stage) { staged_trisolve(a); return true; }
         switch (kid) {
             case KS_TRISOLVE: seg_loop<KS_TRISOLVE>(a); break;
             case KS_REDUCED_BLOCKS: seg_loop<KS_REDUCED_BLOCKS>(a); break;
@@ -116,15 +146,16 @@ struct HostLauncher {
 }  // namespace
 
 extern "C" {
-// same argument meaning as lvio2d_pose_graph_solve (+ segments: the LVIO2D_PG_SEGMENTS knob, 0 = plain path); opt5 = {max_iters, function_tol, gradient_tol, parameter_tol, initial_radius}
+// same argument meaning as lvio2d_pose_graph_solve (+ segments / stage: the LVIO2D_PG_SEGMENTS / LVIO2D_PG_STAGE knobs, 0 = plain path); opt5 = {max_iters, function_tol, gradient_tol, parameter_tol, initial_radius}
 int pgh_solve(const Consts* C, const double* opt5, int32_t n_poses, double* poses, int32_t n_edges, const int32_t* edge_index, const double* edge_tf,
               const double* edge_weight, const double* sqrt_info, int32_t ground_p, int32_t ground_q, lvio2d_summary* summary, int32_t* launches,
-              int32_t segments) {
+              int32_t segments, int32_t stage) {
     std::vector<int32_t> ints;
     Args a;
     std::memset(&a, 0, sizeof(a));
     a.K = n_poses; a.E = n_edges;
     a.P = pg_segments(n_poses, segments);
+    a.stage = stage;
     if (!pg_topology(n_poses, n_edges, edge_index, ints, &a.L, a.P)) return -1;
     a.fixed = n_edges > 0 ? edge_index[0] : -1;
     a.ground_p = ground_p; a.ground_q = ground_q;

@@ -28,7 +28,7 @@ def pgh(tmp_path_factory):
     return C.CDLL(out)
 
 
-def host_solve(pgh, consts, P, poses, edges, tfs, ws, Jn, ground_p=True, ground_q=True, segments=0):
+def host_solve(pgh, consts, P, poses, edges, tfs, ws, Jn, ground_p=True, ground_q=True, segments=0, stage=0):
     x = np.array(poses, dtype=np.float64).reshape(-1, 6).copy()
     ei = np.ascontiguousarray(edges, dtype=np.int32).reshape(-1, 2)
     et = np.ascontiguousarray(tfs, dtype=np.float64).reshape(-1, 12)
@@ -39,7 +39,7 @@ def host_solve(pgh, consts, P, poses, edges, tfs, ws, Jn, ground_p=True, ground_
     summ = np.zeros(1, dtype=abi.SUMMARY_DTYPE)
     launches = C.c_int32(0)
     rc = pgh.pgh_solve(C.byref(consts), d(opt), len(x), d(x), len(ei), ei.ctypes.data_as(C.POINTER(C.c_int32)), d(et), d(ew), d(Jn),
-                       int(ground_p), int(ground_q), summ.ctypes.data_as(C.c_void_p), C.byref(launches), int(segments))
+                       int(ground_p), int(ground_q), summ.ctypes.data_as(C.c_void_p), C.byref(launches), int(segments), int(stage))
     assert rc == 0
     return x, summ, launches.value
 
@@ -114,6 +114,9 @@ def test_partitioned_solve_matches_oracle(pgh, consts, oracle, K, loops, segment
     assert abs(summ["final_cost"][0] - ws_summ["final_cost"][0]) <= 1e-7 * max(1.0, ws_summ["final_cost"][0])
     assert np.abs(got - want).max() < 1e-7
     assert np.abs(got - plain).max() < 1e-9
+    # the shared-memory-staged segment solves (chunks of 16 steps; segments of 3 .. 62 key frames cover partial chunks)
+    staged, summ_s, _ = host_solve(pgh, consts, P, init, edges, tfs, ws, Jn, True, False, segments=segments, stage=1)
+    assert summ_s["iterations"][0] == summ["iterations"][0] and np.array_equal(staged, got)
 
 
 def test_kinked_problem_after_50_iterations(pgh, consts, oracle):
@@ -138,7 +141,7 @@ def test_invalid_graph_is_rejected(pgh, consts):
     opt = np.array([5, 1e-6, 1e-10, 1e-8, 1e4])
     summ = np.zeros(1, dtype=abi.SUMMARY_DTYPE)
     rc = pgh.pgh_solve(C.byref(consts), d(opt), len(x), d(x), len(bad), bad.ctypes.data_as(C.POINTER(C.c_int32)), d(tfs.reshape(-1).copy()),
-                       d(ws.copy()), d(edge_noise_J().reshape(-1).copy()), 1, 1, summ.ctypes.data_as(C.c_void_p), None, 0)
+                       d(ws.copy()), d(edge_noise_J().reshape(-1).copy()), 1, 1, summ.ctypes.data_as(C.c_void_p), None, 0, 0)
     assert rc == -1
 
 
