@@ -1146,9 +1146,11 @@ int pg_setup(lvio2d_ctx* ctx, pg::Args& a, int32_t n_poses, const double* poses,
     std::vector<int32_t> ints;
     std::memset(&a, 0, sizeof(a));
     a.K = n_poses; a.E = n_edges;
-    // LVIO2D_PG_SEGMENTS=<P>: cut the chain into P segments (pose_graph_segments.cuh; opt-in until confirmed on a B200)
+    // LVIO2D_PG_SEGMENTS=<P>|auto: cut the chain into P segments (pose_graph_segments.cuh; opt-in until confirmed on a B200)
     const char* seg_env = std::getenv("LVIO2D_PG_SEGMENTS");
-    a.P = pg::pg_segments(n_poses, seg_env ? std::atoi(seg_env) : 0);
+    int want_segments = seg_env ? std::atoi(seg_env) : 0;
+    if (seg_env && std::strcmp(seg_env, "auto") == 0) want_segments = pg::pg_auto_segments(n_poses);
+    a.P = pg::pg_segments(n_poses, want_segments);
     const char* stage_env = std::getenv("LVIO2D_PG_STAGE");   // segment solves stage their blocks in shared memory
     a.stage = (a.P > 1 && stage_env && std::atoi(stage_env) != 0) ? 1 : 0;
     if (!pg::pg_topology(n_poses, n_edges, edge_index, ints, &a.L, a.P)) return fail(ctx, LVIO2D_ERR_INVALID_ARG, "pose graph: edge index out of range or self edge");

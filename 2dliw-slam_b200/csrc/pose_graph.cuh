@@ -762,6 +762,8 @@ inline size_t pg_bind(Args& a, int32_t* ints, double* dbl) {
     a.y = a.x;
     return off;
 }
+// the segment count that minimises the sequential depth 3 K / P + 2 P (LVIO2D_PG_SEGMENTS=auto); below 64 key frames: none
+inline int pg_auto_segments(int K) { return K < 64 ? 0 : (int)std::lround(std::sqrt(1.5 * K)); }
 // the largest useful number of segments for K key frames (0: use the plain path): every segment keeps >= 3 interior key frames
 inline int pg_segments(int K, int requested) {
     int P = requested;

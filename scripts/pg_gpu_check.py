@@ -67,7 +67,8 @@ for K, nl in ((1000, 8), (4000, 16)):
     say(f"K={K} L={nl + 1}: {s2['iterations'][0]} LM iterations, cost {s2['initial_cost'][0]:.6g} -> {s2['final_cost'][0]:.6g}, wall {dt * 1e3:.1f} ms"
         f" ({dt * 1e3 / max(1, s2['iterations'][0]):.2f} ms / iteration), max |pose - truth| {np.abs(got[:, :3] - truth[:, :3]).max():.3g} m")
 # the opt-in partitioned solve (pose_graph_segments.cuh): parity against the plain path and its wall clock
-for K, nl, P, stage in ((200, 5, 16, 0), (1000, 8, 64, 0), (4000, 16, 64, 0), (4000, 16, 128, 0), (1000, 8, 32, 1), (4000, 16, 64, 1), (4000, 16, 32, 1)):
+for K, nl, P, stage in ((200, 5, 16, 0), (1000, 8, 64, 0), (4000, 16, 64, 0), (4000, 16, 128, 0), (1000, 8, 32, 1), (4000, 16, 64, 1), (4000, 16, 32, 1),
+                        (1000, 8, "auto", 1), (4000, 16, "auto", 1)):
     loops = [(K - 10 - 7 * i, 5 + 11 * i) for i in range(nl)]
     truth, init, edges, tfs, ws = graph_with_loops(K, loops, seed=K)
     os.environ.pop("LVIO2D_PG_SEGMENTS", None)
