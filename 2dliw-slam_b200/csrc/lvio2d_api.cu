@@ -14,6 +14,7 @@
 #include "aux_kernels.cuh"
 #include "scan_lines.cuh"
 #include "pose_graph_segments.cuh"
+#include "peaks.cuh"
 
 using namespace lv;
 
@@ -555,6 +556,37 @@ int lvio2d_get_profile(lvio2d_ctx* ctx, double* out) {
     for (size_t i = 0; i + 1 < ctx->ev_fac_used; i += 2) { float ms = 0; cudaEventElapsedTime(&ms, ctx->ev_fac[i], ctx->ev_fac[i + 1]); out[6] += ms; out[7] += 1; }
     out[4] = ctx->launches;
     out[5] = ctx->scan_bytes_per_launch;
+    return LVIO2D_OK;
+}
+
+int lvio2d_measure_fp64_peak(lvio2d_ctx* ctx, double* out) {
+    if (!ctx || !out) return LVIO2D_ERR_INVALID_ARG;
+    CK(cudaSetDevice(ctx->device));
+    const int grid = ctx->sm_count * 8, block = 256, iters = 4096;
+    if (!ctx->b_tmp[0].ensure((size_t)grid * block * sizeof(double))) return fail(ctx, LVIO2D_ERR_ALLOC, "cudaMalloc(peak)");
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0));
+    CK(cudaEventCreate(&e1));
+    for (int which = 0; which < 2; ++which) {
+        float best = 1e30f;
+        for (int rep = 0; rep < 4; ++rep) {   // first repetition warms up; best of the other three
+            CK(cudaEventRecord(e0, ctx->stream));
+            if (which == 0) dfma_peak_kernel<<<grid, block, 0, ctx->stream>>>(ctx->b_tmp[0].as<double>(), iters, 1.0000001, 1e-9);
+            else dmma_peak_kernel<<<grid, block, 0, ctx->stream>>>(ctx->b_tmp[0].as<double>(), iters, 1.0000001, 1e-9);
+            CK(cudaEventRecord(e1, ctx->stream));
+            CK(cudaEventSynchronize(e1));
+            float ms = 0;
+            CK(cudaEventElapsedTime(&ms, e0, e1));
+            if (rep > 0) best = std::min(best, ms);
+        }
+        // DFMA: 64 FMAs per thread per iteration; DMMA: 32 mma per warp per iteration, 8*8*4 FMAs each
+        const double fma = which == 0 ? (double)grid * block * iters * 64.0 : (double)grid * (block / 32) * iters * 32.0 * 256.0;
+        out[which] = 2.0 * fma / (best * 1e-3) * 1e-12;   // TFLOP/s
+        out[2 + which] = best;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    CK(cudaGetLastError());
     return LVIO2D_OK;
 }
 
@@ -1146,13 +1178,15 @@ int pg_setup(lvio2d_ctx* ctx, pg::Args& a, int32_t n_poses, const double* poses,
     std::vector<int32_t> ints;
     std::memset(&a, 0, sizeof(a));
     a.K = n_poses; a.E = n_edges;
-    // LVIO2D_PG_SEGMENTS=<P>|auto: cut the chain into P segments (pose_graph_segments.cuh; opt-in until confirmed on a B200)
+    // the chain is cut into P segments solved concurrently (pose_graph_segments.cuh), P = sqrt(1.5 K) by default, and the
+    // segment solves stage their blocks in shared memory: measured on a B200 at 0.55 / 1.21 ms per LM iteration for
+    // 1000 / 4000 key frames against 4.7 / 18.7 ms on the single-chain path (profiles/r2_pose_graph.md).
+    // LVIO2D_PG_SEGMENTS=<P>|0 and LVIO2D_PG_STAGE=0|1 override (0 = the single-chain path), for A/B runs and the tests.
     const char* seg_env = std::getenv("LVIO2D_PG_SEGMENTS");
-    int want_segments = seg_env ? std::atoi(seg_env) : 0;
-    if (seg_env && std::strcmp(seg_env, "auto") == 0) want_segments = pg::pg_auto_segments(n_poses);
+    int want_segments = (seg_env && std::strcmp(seg_env, "auto") != 0) ? std::atoi(seg_env) : pg::pg_auto_segments(n_poses);
     a.P = pg::pg_segments(n_poses, want_segments);
-    const char* stage_env = std::getenv("LVIO2D_PG_STAGE");   // segment solves stage their blocks in shared memory
-    a.stage = (a.P > 1 && stage_env && std::atoi(stage_env) != 0) ? 1 : 0;
+    const char* stage_env = std::getenv("LVIO2D_PG_STAGE");
+    a.stage = (a.P > 1 && (!stage_env || std::atoi(stage_env) != 0)) ? 1 : 0;
     if (!pg::pg_topology(n_poses, n_edges, edge_index, ints, &a.L, a.P)) return fail(ctx, LVIO2D_ERR_INVALID_ARG, "pose graph: edge index out of range or self edge");
     a.fixed = fixed;
     a.ground_p = ground_p != 0; a.ground_q = ground_q != 0;

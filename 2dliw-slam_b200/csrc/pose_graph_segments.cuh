@@ -1,10 +1,12 @@
 // pose_graph_segments.cuh — the block-tridiagonal solve of pose_graph.cuh with its sequential chains cut into P segments.
 //
-// STATUS: opt-in (LVIO2D_PG_SEGMENTS=<P>, default off; LVIO2D_PG_STAGE=1 additionally stages the segment solves' blocks in
-// shared memory).  Written at the end of round 1 from the launch list in
-// profiles/r1_pose_graph.md (the two sequential chains over the key frames are 94 % of an LM iteration); verified on the
-// CPU by the thread-by-thread host run against the oracle (tests/test_pose_graph_host.py), cross-compiled for sm_100a,
-// NOT yet run on a B200 — the default path stays the one that was.
+// STATUS: the default path since round 2 (P = sqrt(1.5 K) segments, segment solves staged in shared memory;
+// LVIO2D_PG_SEGMENTS=0 selects the single-chain path of pose_graph.cuh, LVIO2D_PG_STAGE=0 the unstaged segment solves).
+// Written from the launch list in profiles/r1_pose_graph.md (the two sequential chains over the key frames were 94 % of
+// an LM iteration); verified on the CPU by the thread-by-thread host run against the oracle
+// (tests/test_pose_graph_host.py) and on a B200 (tests/test_zz_gpu_pose_graph.py, compute-sanitizer clean,
+// profiles/r2_pose_graph.md): 0.41 / 0.55 / 1.21 ms per LM iteration at 200 / 1000 / 4000 key frames against
+// 1.11 / 4.67 / 18.7 ms on the single chain and 0.91 / 4.54 / 32.3 ms for the same algorithm on one host core.
 //
 // Substructuring of T x = b (T block-tridiagonal SPD, 6x6 blocks, K key frames): P - 1 separator key frames
 // s_i = (i + 1) K / P split the chain into P segments of interior key frames.

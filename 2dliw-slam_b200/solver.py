@@ -31,6 +31,7 @@ EXPORTS = [
     "lvio2d_wheel_preintegrate", "lvio2d_eval_laser_factor", "lvio2d_eval_imu_factor", "lvio2d_eval_wheel_factor",
     "lvio2d_eval_ground_factors", "lvio2d_set_profiling", "lvio2d_get_profile", "lvio2d_set_windows_async", "lvio2d_get_states_async",
     "lvio2d_extract_lines", "lvio2d_scan_to_points", "lvio2d_match_lines", "lvio2d_pose_graph_solve", "lvio2d_eval_edge_factor",
+    "lvio2d_measure_fp64_peak",
 ]
 
 
@@ -91,6 +92,7 @@ def load_library(path=LIB_PATH):
                                        C.c_int32]
     lib.lvio2d_scan_to_points.argtypes = [vp, C.c_int32, C.c_int32, vp, vp, C.c_int32, abi.c_int32_p, dp, dp, dp, C.c_int32]
     lib.lvio2d_get_profile.argtypes = [vp, dp]
+    lib.lvio2d_measure_fp64_peak.argtypes = [vp, dp]
     lib.lvio2d_pose_graph_solve.argtypes = [vp, C.c_int32, dp, C.c_int32, abi.c_int32_p, dp, dp, dp, C.c_int32, C.c_int32, vp]
     lib.lvio2d_eval_edge_factor.argtypes = [vp, dp, C.c_double, dp, dp, dp, dp, dp]
     _lib = lib
@@ -233,6 +235,12 @@ class Context:
         self._check(self.lib.lvio2d_get_profile(self._h, _d(out)), "lvio2d_get_profile")
         return dict(scan_ms=out[0], scan_launches=int(out[1]), window_ms=out[2], window_launches=int(out[3]),
                     kernel_launches=int(out[4]), scan_bytes_per_launch=out[5], factor_ms=out[6], factor_launches=int(out[7]))
+
+    def measure_fp64_peak(self):
+        """Measured fp64 roofline denominators of this device: vector-pipe DFMA and tensor-pipe DMMA TFLOP/s."""
+        out = np.zeros(4)
+        self._check(self.lib.lvio2d_measure_fp64_peak(self._h, _d(out)), "lvio2d_measure_fp64_peak")
+        return dict(dfma_tflops=out[0], dmma_tflops=out[1], dfma_ms=out[2], dmma_ms=out[3])
 
     # ---- linearisation / marginalisation
     def linearize(self, mode=0):

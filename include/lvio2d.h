@@ -211,6 +211,10 @@ int lvio2d_lm_step(lvio2d_ctx* ctx, int32_t* n_active /* host out, may be NULL (
  * for all active frames x launches), out[6] factor-kernel ms, out[7] factor-kernel launches. ---- */
 int lvio2d_set_profiling(lvio2d_ctx* ctx, int32_t on);
 int lvio2d_get_profile(lvio2d_ctx* ctx, double* out /* [8] */);
+/* fp64 roofline denominators measured on this device now (no reference counterpart; BASELINE.md §1 asks the build to
+ * measure one): out[0] vector-pipe DFMA TFLOP/s (16 independent chains per thread, all SMs), out[1] tensor-pipe DMMA
+ * (mma.sync.m8n8k4.f64) TFLOP/s, out[2], out[3] the two kernel durations in ms. */
+int lvio2d_measure_fp64_peak(lvio2d_ctx* ctx, double* out /* [4] */);
 
 /* ---- one-shot linearisation (test hook + what solver::marginalization builds, solver.cpp:367-380).
  * mode 0: the solver's reduced program (constant blocks have zero rows/cols, inactive residual
