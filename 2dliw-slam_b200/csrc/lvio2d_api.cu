@@ -527,6 +527,13 @@ int lvio2d_set_windows(lvio2d_ctx* ctx, const lvio2d_window_batch* host_batch) {
 int lvio2d_bind_windows(lvio2d_ctx* ctx, const lvio2d_window_batch* device_batch) { return setup_batch(ctx, device_batch, true); }
 int lvio2d_set_windows_async(lvio2d_ctx* ctx, const lvio2d_window_batch* host_batch) { return setup_batch(ctx, host_batch, false, true); }
 
+int lvio2d_set_max_iterations(lvio2d_ctx* ctx, int32_t max_iters) {
+    if (!ctx) return LVIO2D_ERR_INVALID_ARG;
+    ctx->opt.max_iters = max_iters > 0 ? max_iters : 50;
+    ctx->params.max_iters = ctx->opt.max_iters;
+    return LVIO2D_OK;
+}
+
 int lvio2d_reset_states(lvio2d_ctx* ctx, const double* host_states) {
     if (!ctx || !host_states) return LVIO2D_ERR_INVALID_ARG;
     if (!ctx->have) return fail(ctx, LVIO2D_ERR_NO_WINDOW, "reset_states");

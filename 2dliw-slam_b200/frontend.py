@@ -91,6 +91,16 @@ def _tf(p, q):
     return T
 
 
+def _inv_iso(T):
+    """Eigen::Transform<., Isometry>::inverse(): (R^T, -R^T t) — NOT a general inverse.  The extrinsics come out of
+    lie::normalize_tf without a quaternion normalisation (src/utilies/common.h:183-189), so their rotation block is
+    orthonormal only to the ~1e-7 of the yaml's digits, and the reference's results carry exactly this transpose."""
+    out = np.eye(4)
+    out[:3, :3] = T[:3, :3].T
+    out[:3, 3] = -(T[:3, :3].T @ T[:3, 3])
+    return out
+
+
 class LaserManager:
     """lvio_2d::laser_manager: spawn_scan and do_match on the device entry points; add_scan / match_with_* / pop_scan as
     the reference's host bookkeeping (key-frame deque, reference sub-map and the one being spawned)."""
@@ -110,13 +120,32 @@ class LaserManager:
         self.last_add_tf = np.eye(4)
         self.current_count = 0
 
-    # ---- scan::add_line(p1, p2, false) (laser_manager.cpp:215-223 -> :137-154): the three fake points p1, mid, p2 are
-    # collinear, so the refit returns the same segment up to rounding; what remains are the filters
+    # ---- scan::add_line(p1, p2, false) (laser_manager.cpp:215-223 -> :137-154, :197-213): the three fake points p1, mid,
+    # p2 are collinear in x, y, so the least-squares refit returns the same 2-D line and create_line's projections return
+    # the end points with z = 0 (to rounding; tests/test_ref_frontend.py measures 1e-15 against the reference text).
+    # What remains are the filters: the 3-D distance of the fake points from that z = 0 line (= |z|) against
+    # line_max_dis, the length against line_min_len, and the line only enters `lines` when one of its 0.05 m samples
+    # falls on a valid cell of the sub-map grid.
     def _add_line(self, scan, p1, p2):
-        p1, p2 = np.array([p1[0], p1[1], 0.0]), np.array([p2[0], p2[1], 0.0])
-        if np.linalg.norm(p1 - p2) < self.line_params.line_min_len:
+        p1, p2 = np.asarray(p1, dtype=np.float64), np.asarray(p2, dtype=np.float64)
+        lp = self.line_params
+        if max(abs(p1[2]), abs(p2[2]), abs(0.5 * (p1[2] + p2[2]))) > lp.line_max_dis:
             return
+        p1, p2 = np.array([p1[0], p1[1], 0.0]), np.array([p2[0], p2[1], 0.0])
+        ln = float(np.linalg.norm(p1 - p2))
+        if ln < lp.line_min_len:
+            return
+        w, h = int(lp.w_laser_each_scan / lp.laser_resolution + 1), int(lp.h_laser_each_scan / lp.laser_resolution + 1)
         d = p2 - p1
+        unit = d / ln
+        tr, hit = 0.0, False
+        while tr <= ln and not hit:
+            q = p1 + unit * tr
+            c, r = int(q[0] / lp.laser_resolution + w // 2), int(q[1] / lp.laser_resolution + h // 2)
+            hit = 0 <= r < h and 0 <= c < w
+            tr += 0.05
+        if not hit:
+            return
         nrm = np.array([-d[1], d[0]]) / np.linalg.norm(d[:2])
         scan.lines.append(ScanLine(p1, p2, [nrm[0], nrm[1], -float(nrm @ p1[:2])], 0, -1))
 
@@ -128,7 +157,7 @@ class LaserManager:
         self.key_frame.append(LaserSubmap(scan, current_p, current_q))
         current_tf = _tf(current_p, current_q)
         if self.ref_submap_ptr is not None:
-            d = np.linalg.inv(self.last_add_tf) @ current_tf
+            d = _inv_iso(self.last_add_tf) @ current_tf
             dq = _log_so3(d[:3, :3])
             if np.linalg.norm(d[:3, 3]) < self.ref_motion_filter_p and np.linalg.norm(dq) < self.ref_motion_filter_q:
                 return
@@ -142,7 +171,7 @@ class LaserManager:
         for sub in (self.ref_submap_ptr, self.spawnning_ref_submap_ptr):
             if sub is None:
                 continue
-            T = np.linalg.inv(self.T_il) @ np.linalg.inv(_tf(sub.current_p, sub.current_q)) @ current_tf @ self.T_il
+            T = _inv_iso(self.T_il) @ (_inv_iso(_tf(sub.current_p, sub.current_q)) @ current_tf) @ self.T_il
             for l in scan.lines:
                 self._add_line(sub.scan_ptr, T[:3, :3] @ l.p1 + T[:3, 3], T[:3, :3] @ l.p2 + T[:3, 3])
         self.current_count += 1

@@ -31,7 +31,7 @@ EXPORTS = [
     "lvio2d_wheel_preintegrate", "lvio2d_eval_laser_factor", "lvio2d_eval_imu_factor", "lvio2d_eval_wheel_factor",
     "lvio2d_eval_ground_factors", "lvio2d_set_profiling", "lvio2d_get_profile", "lvio2d_set_windows_async", "lvio2d_get_states_async",
     "lvio2d_extract_lines", "lvio2d_scan_to_points", "lvio2d_match_lines", "lvio2d_pose_graph_solve", "lvio2d_eval_edge_factor",
-    "lvio2d_measure_fp64_peak",
+    "lvio2d_measure_fp64_peak", "lvio2d_set_max_iterations",
 ]
 
 
@@ -93,6 +93,7 @@ def load_library(path=LIB_PATH):
     lib.lvio2d_scan_to_points.argtypes = [vp, C.c_int32, C.c_int32, vp, vp, C.c_int32, abi.c_int32_p, dp, dp, dp, C.c_int32]
     lib.lvio2d_get_profile.argtypes = [vp, dp]
     lib.lvio2d_measure_fp64_peak.argtypes = [vp, dp]
+    lib.lvio2d_set_max_iterations.argtypes = [vp, C.c_int32]
     lib.lvio2d_pose_graph_solve.argtypes = [vp, C.c_int32, dp, C.c_int32, abi.c_int32_p, dp, dp, dp, C.c_int32, C.c_int32, vp]
     lib.lvio2d_eval_edge_factor.argtypes = [vp, dp, C.c_double, dp, dp, dp, dp, dp]
     _lib = lib
@@ -225,6 +226,11 @@ class Context:
             return int(act.value)
         self._check(self.lib.lvio2d_lm_step(self._h, None), "lvio2d_lm_step")
         return None
+
+    def set_max_iterations(self, max_iters):
+        """max_num_iterations of the following solves (solver.cpp:800-801 vs :161-168)."""
+        self._check(self.lib.lvio2d_set_max_iterations(self._h, int(max_iters)), "lvio2d_set_max_iterations")
+        self.params.max_iters = int(max_iters) if max_iters > 0 else 50
 
     # ---- measurement
     def set_profiling(self, on=True):
@@ -525,6 +531,8 @@ class Solver:
         n = len(frame_infos)
         hb = self._batch(frame_infos, "tracking", with_prior=not self.fast_mode, laser_frames={n - 1})
         self.ctx.set_windows(hb)
+        if self.fast_mode:
+            self.ctx.set_max_iterations(10)          # solver.cpp:800-801
         self.last_summary = self.ctx.solve()
         self._write_back(frame_infos, self.ctx.get_states())
         m = frame_infos[-1].laser_match
@@ -537,7 +545,15 @@ class Solver:
         n = len(frame_infos)
         hb = self._batch(frame_infos, "init", with_prior=False, laser_frames=set(range(1, n)))
         self.ctx.set_windows(hb)
-        self.last_summary = self.ctx.solve()
+        # do_init_solve leaves max_num_iterations at Ceres' default 50 even in fast_mode (solver.cpp:161-168)
+        before = int(self.ctx.params.max_iters)
+        if self.fast_mode:
+            self.ctx.set_max_iterations(50)
+        try:
+            self.last_summary = self.ctx.solve()
+        finally:
+            if self.fast_mode:
+                self.ctx.set_max_iterations(before)
         self._write_back(frame_infos, self.ctx.get_states())
         for f in frame_infos:
             if f.laser_match is not None:

@@ -177,6 +177,10 @@ int lvio2d_bind_windows(lvio2d_ctx* ctx, const lvio2d_window_batch* device_batch
  * enqueued on lvio2d_stream(); the caller's buffers must stay valid and unchanged until lvio2d_sync() returns */
 int lvio2d_set_windows_async(lvio2d_ctx* ctx, const lvio2d_window_batch* host_batch);
 int lvio2d_get_states_async(lvio2d_ctx* ctx, double* host_states /* [B*n][15] */);
+/* ceres::Solver::Options::max_num_iterations of the following solves.  The reference sets it per call: solver::solve
+ * lowers it to 10 in fast_mode (src/factor/solver.cpp:800-801), solver::do_init_solve never does (:161-168), so an
+ * initialisation runs Ceres' default 50 iterations whatever fast_mode says.  max_iters <= 0 selects 50. */
+int lvio2d_set_max_iterations(lvio2d_ctx* ctx, int32_t max_iters);
 /* overwrite the states only (same shapes): re-arm a bound batch for another solve */
 int lvio2d_reset_states(lvio2d_ctx* ctx, const double* host_states);
 

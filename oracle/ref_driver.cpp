@@ -127,6 +127,8 @@ int ref_set_params(const double* v, int n) {
 }
 // fast_mode is read on every solver call (solver.cpp:259, :744, :791, :800), so it may change between calls; every
 // other value is cached by the reference's noise singletons on first use
+// test knob of the Ceres stub: cap every ceres::Solve at `cap` iterations (0 = what the reference asks for)
+int ref_set_iteration_cap(int cap) { ceres::stub_detail::max_iterations_cap() = cap; return 0; }
 int ref_set_fast_mode(int on) { param::manager::get_param_manager()->fast_mode = on != 0; return 0; }
 
 // ---- primitives (src/utilies/common.h)

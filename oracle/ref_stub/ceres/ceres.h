@@ -279,6 +279,9 @@ public:
 
 namespace stub_detail {
 inline Solver::Summary& last_summary() { static Solver::Summary s; return s; }
+// test knob (not Ceres): > 0 caps max_num_iterations below what the caller asked for, so that two implementations can be
+// compared in lock-step before the reference's 50-iteration runs enter the rounding-dominated zig-zag regime
+inline int& max_iterations_cap() { static int cap = 0; return cap; }
 
 // the reduced program: variable, used parameter blocks in order of first use; dense evaluation
 struct Program {
@@ -432,10 +435,11 @@ inline void Solve(const Solver::Options& opt, Problem* problem, Solver::Summary*
     scale_jac();
     double radius = opt.initial_trust_region_radius, decrease_factor = 2.0;
     int iteration = 0, invalid = 0;
+    const int max_iterations = stub_detail::max_iterations_cap() > 0 ? std::min(opt.max_num_iterations, stub_detail::max_iterations_cap()) : opt.max_num_iterations;
     bool last_successful = true;
     std::vector<double> A((size_t)n * n), rhs((size_t)n), step((size_t)n), model((size_t)m), diag((size_t)n);
     for (;;) {
-        if (iteration >= opt.max_num_iterations) { finish(NO_CONVERGENCE, 0, "maximum number of iterations reached", iteration, radius); return; }
+        if (iteration >= max_iterations) { finish(NO_CONVERGENCE, 0, "maximum number of iterations reached", iteration, radius); return; }
         if (last_successful && gmax <= opt.gradient_tolerance) { finish(CONVERGENCE, 3, "gradient tolerance reached", iteration, radius); return; }
         if (radius < opt.min_trust_region_radius) { finish(CONVERGENCE, 4, "minimum trust region radius reached", iteration, radius); return; }
         ++iteration;

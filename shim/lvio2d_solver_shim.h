@@ -179,7 +179,7 @@ namespace lvio_2d
                 p.imu_bias_gyro_sigma[i] = PARAM(imu_bias_gyro_sigma)(i);
                 p.wheel_sigma[i] = PARAM(wheel_sigma)(i);
             }
-            p.max_iters = PARAM(fast_mode) ? 10 : 50; // solver.cpp:800-801
+            p.max_iters = 50; // Ceres' default; lowered per call like the reference does (solver.cpp:800-801)
             if (lvio2d_create(&ctx, &p) != LVIO2D_OK)
                 throw std::runtime_error("lvio2d_create failed (no sm_100 device?)");
         }
@@ -192,6 +192,7 @@ namespace lvio_2d
             flat f;
             build(frame_infos, TRACKING, f);
             check(lvio2d_set_windows(ctx, &f.b), "lvio2d_set_windows");
+            check(lvio2d_set_max_iterations(ctx, PARAM(fast_mode) ? 10 : 50), "lvio2d_set_max_iterations"); // solver.cpp:800-801
             check(lvio2d_solve(ctx, nullptr), "lvio2d_solve");
             write_back(frame_infos);
             auto &last = frame_infos.back();
@@ -208,6 +209,8 @@ namespace lvio_2d
             flat f;
             build(frame_infos, INIT, f);
             check(lvio2d_set_windows(ctx, &f.b), "lvio2d_set_windows");
+            // do_init_solve never lowers max_num_iterations: 50 even in fast_mode (solver.cpp:161-168)
+            check(lvio2d_set_max_iterations(ctx, 50), "lvio2d_set_max_iterations");
             check(lvio2d_solve(ctx, nullptr), "lvio2d_solve");
             write_back(frame_infos);
             for (auto &fr : frame_infos)

@@ -297,6 +297,9 @@ class OracleContext:
     def set_windows(self, hb):
         self.hb, self.states = hb, None
 
+    def set_max_iterations(self, max_iters):
+        self.params.max_iters = int(max_iters) if max_iters > 0 else 50
+
     def solve(self, want_summary=True):
         self.states, summ = solve(self.params, self.hb)
         return summ

@@ -113,6 +113,11 @@ def lib():
     return lb
 
 
+def set_iteration_cap(cap):
+    """Stub knob: cap every ceres::Solve of the reference text at `cap` LM iterations (0 = the reference's own setting)."""
+    lib().ref_set_iteration_cap(int(cap))
+
+
 def set_fast_mode(on):
     lib().ref_set_fast_mode(int(bool(on)))
 
@@ -262,9 +267,14 @@ class RefSolver:
             if f.laser_match is not None:
                 m = f.laser_match
                 m.p1, m.q1, m.p2, m.q2 = mpose[i, 0:3].copy(), mpose[i, 3:6].copy(), mpose[i, 6:9].copy(), mpose[i, 9:12].copy()
-        self.last_summary = dict(iterations=int(summ[0]), termination=int(summ[1]), num_successful_steps=int(summ[2]),
-                                 num_unsuccessful_steps=int(summ[3]), initial_cost=summ[4], final_cost=summ[5], final_radius=summ[6],
-                                 fixed_cost=summ[7])
+        # same record layout as lvio2d_b200.solver.Context.solve() returns; Ceres reports costs including the fixed cost
+        # of residual blocks without a variable parameter block, the product reports the reduced program's cost
+        out = np.zeros(1, dtype=abi.SUMMARY_DTYPE)
+        out["iterations"], out["termination"] = int(summ[0]), int(summ[1])
+        out["num_successful_steps"], out["num_unsuccessful_steps"] = int(summ[2]), int(summ[3])
+        out["initial_cost"], out["final_cost"], out["final_radius"] = summ[4] - summ[7], summ[5] - summ[7], summ[6]
+        self.last_summary = out
+        self.fixed_cost = float(summ[7])
         return sqrtH
 
     def solve(self, frame_infos, feature_infos=None):
@@ -277,6 +287,23 @@ class RefSolver:
         sqrtH = self._run(2, frame_infos)
         if not self.fast_mode:
             frame_infos[-1].sqrt_H = sqrtH
+
+    # the attributes lvio2d_b200.solver.Solver keeps (replay.run_tracking_lockstep copies them between solvers)
+    @property
+    def has_linearized_block(self):
+        return self.prior is not None
+
+    @property
+    def linearized_X(self):
+        return None if self.prior is None else self.prior[0]
+
+    @property
+    def linearized_jacobians(self):
+        return None if self.prior is None else self.prior[1]
+
+    @property
+    def linearized_residuals(self):
+        return None if self.prior is None else self.prior[2]
 
     @property
     def prior(self):
