@@ -424,20 +424,20 @@ template <class T> LV_HD M3<T> transpose(const M3<T>& A) {
         for (int j = 0; j < 3; ++j) B.m[i * 3 + j] = A.m[j * 3 + i];
     return B;
 }
-// r_imu: the 15 residuals BEFORE whitening by sqrt_inverse_P
-template <class T>
-LV_HD void item_imu(const Consts& C, const double* imu_blob, const FrameState<T>& a, const FrameState<T>& b, const M3<T>& Ri,
-                    const M3<T>& Rj, T* r_imu) {
-    const double* X = imu_blob;
-    const double* J = imu_blob + 15;
-    const double Dt = imu_blob[465];
+// r_imu: the 15 residuals BEFORE whitening by sqrt_inverse_P.  X = the preintegrated state (15); J(k, 9 + c) =
+// J[k * JS + JO + c], k = 0..8, c = 0..5 are the only entries of the preintegration Jacobian the factor reads (the bias
+// columns of the alpha / beta / gamma rows, imu_factor.h:57-77): JS = 15, JO = 9 on the ABI blob, JS = 6, JO = 0 on the
+// compact copy factor_pair_kernel stages in shared memory.
+template <class T, int JS, int JO>
+LV_HD void item_imu_t(const Consts& C, const double* X, const double* J, const double Dt, const FrameState<T>& a, const FrameState<T>& b,
+                      const M3<T>& Ri, const M3<T>& Rj, T* r_imu) {
     const V3<T> dba = v3<T>(a.ba.x - X[9], a.ba.y - X[10], a.ba.z - X[11]);
     const V3<T> dbw = v3<T>(a.bw.x - X[12], a.bw.y - X[13], a.bw.z - X[14]);
     T ab[9];
 #pragma unroll
     for (int k = 0; k < 9; ++k) {
-        ab[k] = X[k] + (J[k * 15 + 12] * dbw.x + J[k * 15 + 13] * dbw.y + J[k * 15 + 14] * dbw.z);
-        if (k < 6) ab[k] = ab[k] + (J[k * 15 + 9] * dba.x + J[k * 15 + 10] * dba.y + J[k * 15 + 11] * dba.z);
+        ab[k] = X[k] + (J[k * JS + JO + 3] * dbw.x + J[k * JS + JO + 4] * dbw.y + J[k * JS + JO + 5] * dbw.z);
+        if (k < 6) ab[k] = ab[k] + (J[k * JS + JO] * dba.x + J[k * JS + JO + 1] * dba.y + J[k * JS + JO + 2] * dba.z);
     }
     const double gz = C.g;
     const V3<T> y1 = v3<T>(b.p.x - a.p.x - a.v.x * Dt, b.p.y - a.p.y - a.v.y * Dt, b.p.z - a.p.z + 0.5 * gz * Dt * Dt - a.v.z * Dt);
@@ -450,6 +450,11 @@ LV_HD void item_imu(const Consts& C, const double* imu_blob, const FrameState<T>
     r_imu[6] = rg.x; r_imu[7] = rg.y; r_imu[8] = rg.z;
     r_imu[9] = b.ba.x - a.ba.x; r_imu[10] = b.ba.y - a.ba.y; r_imu[11] = b.ba.z - a.ba.z;
     r_imu[12] = b.bw.x - a.bw.x; r_imu[13] = b.bw.y - a.bw.y; r_imu[14] = b.bw.z - a.bw.z;
+}
+template <class T>
+LV_HD void item_imu(const Consts& C, const double* imu_blob, const FrameState<T>& a, const FrameState<T>& b, const M3<T>& Ri,
+                    const M3<T>& Rj, T* r_imu) {
+    item_imu_t<T, 15, 9>(C, imu_blob, imu_blob + 15, imu_blob[465], a, b, Ri, Rj, r_imu);
 }
 template <class T>
 LV_HD void item_wheel(const Consts& C, const double* wheel_blob, const V3<T>& pa, const V3<T>& pb, const M3<T>& Ri, const M3<T>& Rj,

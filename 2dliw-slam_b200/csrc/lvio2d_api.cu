@@ -79,7 +79,7 @@ struct lvio2d_ctx {
     int uniform_pts = 0, uniform_lines = 0;   // > 0: all frames have this many points / lines (scan-match fast prologue)
     int shard_rank = 0, shard_world = 1;
     // inputs (owned copies, or borrowed device pointers when bound)
-    DevBuf b_points, b_pline, b_pweight, b_poff, b_loff, b_lines, b_ref, b_refpose, b_imu, b_wheel, b_pX0, b_pJ, b_cmask;
+    DevBuf b_points, b_pline, b_pweight, b_poff, b_loff, b_lines, b_ref, b_refpose, b_imu, b_wheel, b_pX0, b_pJ, b_pH, b_cmask;
     const double2* points = nullptr; const int32_t* point_line = nullptr; const double* point_weight = nullptr;
     const int64_t* point_offset = nullptr; const int64_t* line_offset = nullptr; const double4* lines = nullptr;
     const int32_t* ref_frame = nullptr; const double* ref_pose = nullptr; const double* imu = nullptr; const double* wheel = nullptr;
@@ -225,7 +225,7 @@ WindowArgs window_args(lvio2d_ctx* ctx, int mode) {
     a.ground_multiplicity = ctx->ground_mult; a.prior_frame = ctx->prior_frame;
     a.has_imu = ctx->has_imu; a.has_wheel = ctx->has_wheel;
     a.const_mask = ctx->const_mask; a.frame_active = (mode == 1 ? ctx->b_active1 : ctx->b_active).as<uint8_t>(); a.ref_frame = ctx->ref_frame;
-    a.imu = ctx->imu; a.wheel = ctx->wheel; a.prior_X0 = ctx->prior_X0; a.prior_J = ctx->prior_J;
+    a.imu = ctx->imu; a.wheel = ctx->wheel; a.prior_X0 = ctx->prior_X0; a.prior_J = ctx->prior_J; a.prior_H = ctx->b_pH.as<double>();
     a.partial = ctx->b_part.as<double>();
     a.x = ctx->b_x.as<double>(); a.xc = ctx->b_xc.as<double>(); a.scale = ctx->b_scale.as<double>();
     a.laser_blocks = ctx->b_lb.as<double>(); a.frame_tab = ctx->b_ftab.as<double>();
@@ -419,6 +419,12 @@ int setup_batch(lvio2d_ctx* ctx, const lvio2d_window_batch* b, bool bind, bool a
     CK(cudaMemcpyAsync(ctx->b_active.p, active.data(), F, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(ctx->b_active1.p, active1.data(), F, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemsetAsync(ctx->b_part.p, 0, (size_t)F * ctx->tiles * ctx->npad * sizeof(double), ctx->stream));
+    if (ctx->prior_frame >= 0) {
+        // J^T J of the marginalisation prior: constant over the solve, so the factor kernel adds it instead of recomputing it
+        if (!ctx->b_pH.ensure((size_t)B * kBlk * sizeof(double))) return fail(ctx, LVIO2D_ERR_ALLOC, "cudaMalloc(prior information)");
+        prior_info_kernel<<<B, 64, 0, ctx->stream>>>(ctx->prior_J, ctx->b_pH.as<double>(), B);
+        CK(cudaGetLastError());
+    }
     if (has_laser && ctx->L > 0) {
         // world lines of every local map that hangs under an external constant pose
         frame_table_kernel<<<(F + 127) / 128, 128, 0, ctx->stream>>>(ctx->C, ctx->ref_pose, 6, ctx->b_reftab.as<double>(), F);
@@ -503,7 +509,7 @@ void lvio2d_destroy(lvio2d_ctx* ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     DevBuf* all[] = {&ctx->b_points, &ctx->b_pline, &ctx->b_pweight, &ctx->b_poff, &ctx->b_loff, &ctx->b_lines, &ctx->b_ref, &ctx->b_refpose,
-                     &ctx->b_imu, &ctx->b_wheel, &ctx->b_pX0, &ctx->b_pJ, &ctx->b_cmask, &ctx->b_x0, &ctx->b_x, &ctx->b_xc, &ctx->b_scale,
+                     &ctx->b_imu, &ctx->b_wheel, &ctx->b_pX0, &ctx->b_pJ, &ctx->b_pH, &ctx->b_cmask, &ctx->b_x0, &ctx->b_x, &ctx->b_xc, &ctx->b_scale,
                      &ctx->b_ftab, &ctx->b_reftab, &ctx->b_wlines, &ctx->b_wlen, &ctx->b_part, &ctx->b_lb, &ctx->b_items, &ctx->b_vec, &ctx->b_fac, &ctx->b_state,
                      &ctx->b_status, &ctx->b_active, &ctx->b_active1, &ctx->b_reduce};
     for (DevBuf* b : all) b->release();

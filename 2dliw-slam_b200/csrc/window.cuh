@@ -69,11 +69,24 @@ struct LMOptions {
 };
 
 constexpr int kBlk = 225;
-// factor item record: the symmetric 30x30 J^T J over (frame i-1, frame i) row-major with row stride 30 | g_a | g_b | cost | pad
-constexpr int kItemGa = 900, kItemGb = 915, kItemCost = 930, kItem = 936;
-__device__ __forceinline__ int item_haa(int r, int c) { return r * 30 + c; }
-__device__ __forceinline__ int item_hab(int r, int c) { return r * 30 + 15 + c; }
-__device__ __forceinline__ int item_hbb(int r, int c) { return (15 + r) * 30 + 15 + c; }
+// Factor item record = the symmetric 32 x 32 product W^T W of the item's whitened Jacobian | residual matrix W
+// (columns 0..14 frame i-1, 15..29 frame i, 30 the whitened residual, 31 zero), i.e. J^T J (30 x 30), J^T r (column 30)
+// and r^T r (entry 30,30) in one matrix, stored as its 10 upper 8 x 8 tiles, tile (ti, tj) row-major at
+// 64 * (ti * 4 - ti (ti - 1) / 2 + tj - ti): exactly what the DMMA accumulators of factor_pair_kernel hold, written with
+// one 16-byte store per lane and tile (512 contiguous bytes per warp).  640 doubles per item (the dense 30 x 30 + g
+// record of round 1 was 936).
+constexpr int kItem = 640;
+__host__ __device__ __forceinline__ int item_idx(int r, int c) {   // entry (r, c) = (c, r), r, c in 0..31
+    if (r > c) { const int t = r; r = c; c = t; }
+    const int ti = r >> 3, tj = c >> 3;
+    return 64 * (ti * 4 - (ti * (ti - 1)) / 2 + tj - ti) + (r & 7) * 8 + (c & 7);
+}
+__device__ __forceinline__ int item_haa(int r, int c) { return item_idx(r, c); }
+__device__ __forceinline__ int item_hab(int r, int c) { return item_idx(r, 15 + c); }
+__device__ __forceinline__ int item_hbb(int r, int c) { return item_idx(15 + r, 15 + c); }
+__device__ __forceinline__ int item_ga(int c) { return item_idx(c, 30); }
+__device__ __forceinline__ int item_gb(int c) { return item_idx(15 + c, 30); }
+constexpr int kItemCost = 64 * 9 + 6 * 8 + 6;   // item_idx(30, 30)
 
 struct WindowArgs {
     Consts C;
@@ -87,6 +100,7 @@ struct WindowArgs {
     const double* wheel;            // [B*(n-1)][15]
     const double* prior_X0;         // [B][15]
     const double* prior_J;          // [B][225]
+    const double* prior_H;          // [B][225]  J^T J of the prior, computed once per upload (prior_info_kernel)
     const double* partial;          // [B*n][tiles][pad]   scan-match output at the candidate
     double* x;                      // [B*n][15] accepted point
     double* xc;                     // [B*n][15] candidate
@@ -135,9 +149,136 @@ __device__ __forceinline__ void cp_async16(double* smem_dst, const double* gsrc)
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
+// fp64 tensor-core product D(8x8) += A(8x4) B(4x8) (DMMA.8x8x4 on sm_100a, measured at 37 TFLOP/s against 33.8 for the
+// vector pipe, at one eighth of the issue slots per FMA).  Lane l = 4 g + t holds A[g][t], B[t][g], D[g][2t], D[g][2t+1].
+__device__ __forceinline__ void dmma884(double& d0, double& d1, const double a, const double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+
 // =====================================================================================================
-// factor_kernel: per-warp shared memory = blob 480 | J 15x32 | wheel 3x16 | ground 2x8 | prior r 16
-constexpr int kFactorSmem = 480 + 480 + 48 + 16 + 16 + 16 + 240;   // ... | wheel blob 16 | prior J 240
+// The factor item: the residual blocks hanging on frame i of a window, evaluated at the candidate point.
+//
+// Shared-memory matrix W of one item, [kWRows][kWS] doubles (row stride 34: 16-byte aligned rows for the DMMA result
+// stores, at most 2-way bank conflicts on the fragment loads):
+//   rows  0..14  IMU factor: Jacobian | residual (column 30), un-whitened after phase A, whitened in place by item_finish
+//   rows 15..17  wheel factor (already weighted by diag(sqrt_inverse_P), wheel_factor.h:58-70)
+//   rows 18..19  the two ground factors times sqrt(multiplicity) (the reference adds them n times, solver.cpp:727-743)
+// Constant parameter blocks have zero columns (Ceres removes them from the reduced program, solver.cpp:787-794);
+// residual blocks whose parameter blocks are all constant have zero rows (their cost is Ceres' fixed_cost).
+constexpr int kWS = 34, kWRows = 20, kWSize = kWRows * kWS;
+constexpr int kCB = 72;   // compact IMU blob: X[15] | pad | J(0..8, 9..14) [9][6] at 16 | Dt at 70
+__device__ __forceinline__ void stage_compact_blob(double* sC, const double* blob, int sl, int nsl) {
+    for (int k = sl; k < 70; k += nsl) {
+        const int src = k < 15 ? k : (k < 69 ? 15 + ((k - 15) / 6) * 15 + 9 + (k - 15) % 6 : 465);
+        cp_async8(sC + (k < 15 ? k : (k < 69 ? k + 1 : 70)), blob + src);
+    }
+}
+
+// Whole warp.  Whitening (when sq != nullptr: rows 0..14 <- sq rows 0..14, upper triangular sqrt_inverse_P read from
+// global memory as DMMA A fragments), W^T W on the tensor pipe, the marginalisation prior of frame i (r = J (x - X0),
+// marginalization_factor.h:50: H += J^T J, g += J^T r, cost += r^T r from the precomputed J^T J), one 16-byte store per
+// lane and tile.
+__device__ __forceinline__ void item_finish(const WindowArgs& a, double* W, const double* sq, const int w, const int i, const uint8_t mb,
+                                            const bool prior_on, double* sPg /* 16 doubles */, double* out, const int lane) {
+    const int g = lane >> 2, t = lane & 3;
+    if (sq) {
+        double af[6], bf[4][4];
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+            const int k = 4 * ks + t;
+            af[ks] = (k < 15 && k >= g) ? __ldg(sq + g * 15 + k) : 0.0;
+        }
+#pragma unroll
+        for (int ks = 2; ks < 4; ++ks) {
+            const int r = 8 + g, k = 4 * ks + t;
+            af[2 + ks] = (r < 15 && k < 15 && k >= r) ? __ldg(sq + r * 15 + k) : 0.0;
+        }
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks)
+#pragma unroll
+            for (int ni = 0; ni < 4; ++ni) bf[ks][ni] = (4 * ks + t < 15) ? W[(4 * ks + t) * kWS + 8 * ni + g] : 0.0;
+        __syncwarp();
+#pragma unroll
+        for (int ni = 0; ni < 4; ++ni) {
+            double c0 = 0.0, c1 = 0.0, d0 = 0.0, d1 = 0.0;
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) dmma884(c0, c1, af[ks], bf[ks][ni]);
+#pragma unroll
+            for (int ks = 2; ks < 4; ++ks) dmma884(d0, d1, af[2 + ks], bf[ks][ni]);
+            *reinterpret_cast<double2*>(W + g * kWS + 8 * ni + 2 * t) = make_double2(c0, c1);
+            if (8 + g < 15) *reinterpret_cast<double2*>(W + (8 + g) * kWS + 8 * ni + 2 * t) = make_double2(d0, d1);
+        }
+        __syncwarp();
+    }
+    double acc[10][2];
+#pragma unroll
+    for (int k = 0; k < 10; ++k) acc[k][0] = acc[k][1] = 0.0;
+#pragma unroll
+    for (int ks = 0; ks < kWRows / 4; ++ks) {
+        double f[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) f[c] = W[(4 * ks + t) * kWS + 8 * c + g];
+        int tile = 0;
+#pragma unroll
+        for (int ti = 0; ti < 4; ++ti)
+#pragma unroll
+            for (int tj = ti; tj < 4; ++tj) { dmma884(acc[tile][0], acc[tile][1], f[ti], f[tj]); ++tile; }
+    }
+    if (prior_on) {
+        const double* PH = a.prior_H + (size_t)w * kBlk;
+        const double* X0 = a.prior_X0 + (size_t)w * 15;
+        const double* xb = a.xc + ((size_t)w * a.n_frames + i) * 15;
+        double gp = 0.0, dl = 0.0;
+        if (lane < 15) {
+#pragma unroll
+            for (int k = 0; k < 15; ++k) gp += PH[lane * 15 + k] * (xb[k] - X0[k]);
+            dl = xb[lane] - X0[lane];
+            sPg[lane] = gp;
+        }
+        const double cost_p = warp_sum(dl * gp);
+        __syncwarp();
+        int tile = 0;
+#pragma unroll
+        for (int ti = 0; ti < 4; ++ti)
+#pragma unroll
+            for (int tj = ti; tj < 4; ++tj) {
+                const int r = 8 * ti + g - 15;
+#pragma unroll
+                for (int q = 0; q < 2; ++q) {
+                    const int c = 8 * tj + 2 * t + q - 15;
+                    if (r >= 0 && r < 15 && !col_const(mb, r)) {
+                        if (c >= 0 && c < 15 && !col_const(mb, c)) acc[tile][q] += PH[r * 15 + c];
+                        else if (c == 15) acc[tile][q] += sPg[r];
+                    } else if (r == 15 && c == 15) acc[tile][q] += cost_p;
+                }
+                ++tile;
+            }
+        __syncwarp();   // sPg may be reused by the next item
+    }
+#pragma unroll
+    for (int tile = 0; tile < 10; ++tile)
+        *reinterpret_cast<double2*>(out + tile * 64 + g * 8 + 2 * t) = make_double2(acc[tile][0], acc[tile][1]);
+}
+
+// J^T J of the marginalisation prior, once per upload: prior_H[w] = prior_J[w]^T prior_J[w]
+__global__ void prior_info_kernel(const double* prior_J, double* prior_H, int n_windows) {
+    const int w = blockIdx.x;
+    if (w >= n_windows) return;
+    const double* J = prior_J + (size_t)w * kBlk;
+    for (int e = threadIdx.x; e < kBlk; e += blockDim.x) {
+        const int r = e / 15, c = e - 15 * r;
+        double s = 0.0;
+#pragma unroll
+        for (int k = 0; k < 15; ++k) s += J[k * 15 + r] * J[k * 15 + c];
+        prior_H[(size_t)w * kBlk + e] = s;
+    }
+}
+
+// =====================================================================================================
+// factor_kernel: one item per warp, every one of the 30 state columns in dual arithmetic (lane c = column c, lane 30 the
+// values), whitened per lane.  The all-dual cross-check of factor_pair_kernel's closed-form columns (LVIO2D_FACTOR_PAIRED=0).
+// Per-warp shared memory: blob 480 | W 680 | wheel blob 16 | prior scratch 16
+constexpr int kFactorSmem = 480 + kWSize + 16 + 16;
 __global__ void __launch_bounds__(128, LV_FACTOR_MINB) factor_kernel(WindowArgs a) {
     extern __shared__ __align__(16) double smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -150,12 +291,9 @@ __global__ void __launch_bounds__(128, LV_FACTOR_MINB) factor_kernel(WindowArgs 
     const int parity = 1 - a.state[w].cur;
     double* out = a.items + ((size_t)parity * a.n_windows * n + item) * kItem;
     double* sblob = smem + (size_t)warp * kFactorSmem;
-    double* sJ = sblob + 480;   // whitened IMU Jacobian [15][32]; column 30 = whitened residual
-    double* sW = sJ + 480;      // wheel [3][16]: cols 0..11 Jacobian, col 12 residual
-    double* sG = sW + 48;       // ground [2][8]: cols 0..5 Jacobian, col 6 residual
-    double* sP = sG + 16;       // prior residual [15]
-    double* sWb = sP + 16;      // wheel blob [15]
-    double* sPJ = sWb + 16;     // prior J [225]
+    double* W = sblob + 480;
+    double* sWb = W + kWSize;   // wheel blob [15]
+    double* sPg = sWb + 16;
     const double* X = a.xc + (size_t)w * n * 15;
     const uint8_t* cm = a.const_mask + (size_t)w * n;
     const uint8_t mb = mode == 1 ? 0 : cm[i];
@@ -166,12 +304,6 @@ __global__ void __launch_bounds__(128, LV_FACTOR_MINB) factor_kernel(WindowArgs 
     const bool wheel_on = i > 0 && a.has_wheel && ((ma & 3) != 3 || (mb & 3) != 3);
     const bool ground_on = a.ground_multiplicity > 0 && (mb & 3) != 3;
     const bool prior_on = a.prior_frame == i && (mb & 15) != 15;
-    double cost = 0.0;
-    // ---- one lane per state column (0..14 frame a, 15..29 frame b), lane 30 carries the values: IMU + wheel +
-    // ground of this item evaluated once in dual arithmetic, every lane on the same instruction stream
-    // the constant inputs of this item (IMU blob, wheel blob, prior J) travel to shared memory asynchronously while the
-    // states are seeded and the two exponentials are evaluated
-    const double* PJ = a.prior_J + (size_t)w * kBlk;
     if (imu_on) {
         const double* blob = a.imu + ((size_t)w * (n - 1) + (i - 1)) * 466;
         if ((reinterpret_cast<uintptr_t>(blob) & 15) == 0) {
@@ -181,10 +313,8 @@ __global__ void __launch_bounds__(128, LV_FACTOR_MINB) factor_kernel(WindowArgs 
         }
     }
     if (wheel_on && lane < 15) cp_async8(sWb + lane, a.wheel + ((size_t)w * (n - 1) + (i - 1)) * 15 + lane);
-    if (prior_on)
-        for (int k = lane; k < kBlk; k += 32) cp_async8(sPJ + k, PJ + k);
+    for (int k = lane; k < kWSize; k += 32) W[k] = 0.0;
     {
-        const double* wblob = wheel_on ? sWb : nullptr;
         const FrameState<Dual> fa_ = seed_frame_state(xa, lane < 15 ? lane : -1);
         const FrameState<Dual> fb_ = seed_frame_state(xb, (lane >= 15 && lane < 30) ? lane - 15 : -1);
         const M3<Dual> Rj = exp_so3(fb_.th);
@@ -194,6 +324,7 @@ __global__ void __launch_bounds__(128, LV_FACTOR_MINB) factor_kernel(WindowArgs 
         __syncwarp();
         const bool value_lane = lane == 30;
         const bool dead = lane < 30 && col_const(lane < 15 ? ma : mb, lane % 15);
+        const double sm = sqrt((double)a.ground_multiplicity);
         if (imu_on) {
             Dual ri[15];
             item_imu<Dual>(a.C, sblob, fa_, fb_, Ri, Rj, ri);
@@ -203,118 +334,35 @@ __global__ void __launch_bounds__(128, LV_FACTOR_MINB) factor_kernel(WindowArgs 
                 double s = 0.0;
 #pragma unroll
                 for (int k = r; k < 15; ++k) s += Sq[r * 15 + k] * (value_lane ? ri[k].a : ri[k].d);
-                sJ[r * 32 + lane] = (dead || lane == 31) ? 0.0 : s;
-                if (value_lane) cost += s * s;
+                W[r * kWS + lane] = (dead || lane == 31) ? 0.0 : s;
             }
-        } else {
-            for (int k = lane; k < 480; k += 32) sJ[k] = 0.0;
         }
         const int fl = lane % 15;
         if (wheel_on) {
             Dual rw[3];
-            item_wheel<Dual>(a.C, wblob, fa_.p, fb_.p, Ri, Rj, rw);
+            item_wheel<Dual>(a.C, sWb, fa_.p, fb_.p, Ri, Rj, rw);
             if (lane < 30 && fl < 6) {
-                const int wc = (lane < 15 ? 0 : 6) + fl;
 #pragma unroll
-                for (int k = 0; k < 3; ++k) sW[k * 16 + wc] = dead ? 0.0 : rw[k].d;
+                for (int k = 0; k < 3; ++k) W[(15 + k) * kWS + lane] = dead ? 0.0 : rw[k].d;
             } else if (value_lane) {
 #pragma unroll
-                for (int k = 0; k < 3; ++k) { sW[k * 16 + 12] = rw[k].a; cost += rw[k].a * rw[k].a; }
+                for (int k = 0; k < 3; ++k) W[(15 + k) * kWS + 30] = rw[k].a;
             }
-        } else {
-            for (int k = lane; k < 48; k += 32) sW[k] = 0.0;
         }
         if (ground_on) {
             Dual rg[2];
             item_ground<Dual>(a.C, fb_.p, Rj, rg);
             if (lane >= 15 && lane < 21) {
-                sG[lane - 15] = dead ? 0.0 : rg[0].d;
-                sG[8 + lane - 15] = dead ? 0.0 : rg[1].d;
+                W[18 * kWS + lane] = dead ? 0.0 : sm * rg[0].d;
+                W[19 * kWS + lane] = dead ? 0.0 : sm * rg[1].d;
             } else if (value_lane) {
-                sG[6] = rg[0].a;
-                sG[14] = rg[1].a;
-                cost += a.ground_multiplicity * (rg[0].a * rg[0].a + rg[1].a * rg[1].a);
+                W[18 * kWS + 30] = sm * rg[0].a;
+                W[19 * kWS + 30] = sm * rg[1].a;
             }
-        } else {
-            if (lane < 16) sG[lane] = 0.0;
-        }
-    }
-    // ---- prior of frame i: r = J (x - X0)
-    PJ = sPJ;
-    if (prior_on) {
-        if (lane < 15) {
-            const double* X0 = a.prior_X0 + (size_t)w * 15;
-            double s = 0.0;
-            for (int k = 0; k < 15; ++k) s += PJ[lane * 15 + k] * (xb[k] - X0[k]);
-            sP[lane] = s;
-            cost += s * s;
         }
     }
     __syncwarp();
-    // ---- row `lane` of the symmetric 30x30 J^T J of this item, written column by column: for a fixed column the 30
-    // lanes store 30 consecutive doubles (H is symmetric, so [col][row] is also [row][col])
-    double gsum = 0.0;
-    if (lane < 30) {
-        double mine[15];
-#pragma unroll
-        for (int r = 0; r < 15; ++r) mine[r] = sJ[r * 32 + lane];
-#pragma unroll
-        for (int r = 0; r < 15; ++r) gsum += mine[r] * sJ[r * 32 + 30];
-        const int fl = lane % 15;
-        const bool pose_lane = fl < 6;
-        const int wc = (lane < 15 ? 0 : 6) + fl;
-        double w0 = 0.0, w1 = 0.0, w2 = 0.0, jp = 0.0, jq = 0.0;
-        const double m = (double)a.ground_multiplicity;
-        if (pose_lane) {
-            w0 = sW[wc]; w1 = sW[16 + wc]; w2 = sW[32 + wc];
-            gsum += w0 * sW[12] + w1 * sW[16 + 12] + w2 * sW[32 + 12];
-            if (lane >= 15) {
-                jp = sG[fl]; jq = sG[8 + fl];
-                gsum += m * (jp * sG[6] + jq * sG[8 + 6]);
-            }
-        }
-        const bool prior_lane = prior_on && lane >= 15 && !col_const(mb, fl);
-        if (prior_lane) {
-            double gs = 0.0;
-            for (int r = 0; r < 15; ++r) gs += PJ[r * 15 + fl] * sP[r];
-            gsum += gs;
-        }
-#if LV_FACTOR_ROLL
-#pragma unroll 1
-#else
-#pragma unroll
-#endif
-        for (int c2 = 0; c2 < 30; c2 += 2) {
-            // two columns per 16-byte shared-memory load
-            double s2[2] = {0.0, 0.0};
-#pragma unroll
-            for (int r = 0; r < 15; ++r) {
-                const double2 v = *reinterpret_cast<const double2*>(sJ + r * 32 + c2);
-                s2[0] += mine[r] * v.x;
-                s2[1] += mine[r] * v.y;
-            }
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const int c = c2 + h;
-                double s = s2[h];
-                const int cf = c % 15;
-                if (cf < 6) {   // pose column: wheel (both frames) and ground (frame b) terms
-                    const int cw = (c < 15 ? 0 : 6) + cf;
-                    s += w0 * sW[cw] + w1 * sW[16 + cw] + w2 * sW[32 + cw];
-                    if (c >= 15) s += m * (jp * sG[cf] + jq * sG[8 + cf]);
-                }
-                if (c >= 15 && prior_lane && !col_const(mb, cf)) {
-                    double ps = 0.0;
-                    for (int r = 0; r < 15; ++r) ps += PJ[r * 15 + fl] * PJ[r * 15 + cf];
-                    s += ps;
-                }
-                out[c * 30 + lane] = s;
-            }
-        }
-        out[kItemGa + lane] = gsum;
-    }
-    cost = warp_sum(cost);
-    if (lane == 31) out[kItemCost] = cost;
+    item_finish(a, W, nullptr, w, i, mb, prior_on, sPg, out, lane);
 }
 
 // =====================================================================================================
@@ -326,13 +374,13 @@ __global__ void __launch_bounds__(128, LV_FACTOR_MINB) factor_kernel(WindowArgs 
 //   d r_alpha / d v_a = R_i^T Dt,  d r_beta / d v_a = R_i^T,  d r_beta / d v_b = -R_i^T,
 //   d r_{alpha,beta} / d ba_a = J[:, 9..11],  d r_ba / d ba_{a,b} = -+I,  d r_bw / d bw_b = I
 // — exactly what the dual path produces for them (its products with the zero dual parts add exact zeros).
-// So a half-warp carries one item: sub-lane 0 the values, 1..3 p_b, 4..6 theta_a, 7..9 theta_b, 10..12 bw_a; after the
-// dual evaluation each of the 15 closed-form columns is whitened by one sub-lane.  The J^T J products (30 columns wide)
-// then run for the two items one after the other on the full warp.  Instruction count per item: ~2.8 k instead of
-// ~5.2 k.  Per-warp shared memory: 2 x (blob 480 | whitened J 15x32 | wheel 3x16 | ground 2x8 | wheel blob 16) + prior
-// residual 16 + prior J 240.
-constexpr int kPairHalf = 480 + 480 + 48 + 16 + 16;
-constexpr int kPairSmem = 2 * kPairHalf + 16 + 240;
+// Phase A, a half-warp per item: sub-lane 0 the values, 1..3 p_b, 4..6 theta_a, 7..9 theta_b, 10..12 bw_a evaluate the
+// residuals in dual arithmetic and drop their UN-whitened column into W; 15 sub-lanes drop the closed-form columns.
+// Phase B, the whole warp, one item after the other (item_finish): whitening by sqrt_inverse_P and the 32 x 32 product
+// W^T W on the fp64 tensor pipe — 24 + 50 DMMA per item where round 1 issued ~700 DFMA + ~450 shared-memory loads.
+// Per-warp shared memory: 2 x (compact blob 72 | W 680 | wheel blob 16) + prior scratch 16 = 12.3 KB (round 1: 18.7 KB).
+constexpr int kPairHalf = kCB + kWSize + 16;
+constexpr int kPairSmem = 2 * kPairHalf + 16;
 // items `first` and `first + 1` (the second only when count == 2) on one warp; `base` = kPairSmem doubles of shared memory
 __device__ __forceinline__ void factor_pair_item(const WindowArgs& a, const int first, const int count, const int lane, double* base) {
     const int h = lane >> 4, sl = lane & 15;
@@ -343,13 +391,10 @@ __device__ __forceinline__ void factor_pair_item(const WindowArgs& a, const int 
     if (live) { w = item / n; i = item - w * n; live = a.win_status[w] == 0; }
     if (!__any_sync(0xffffffffu, live)) return;
     const int mode = a.mode;
-    double* sblob = base + h * kPairHalf;
-    double* sJ = sblob + 480;   // whitened IMU Jacobian [15][32]; column 30 = whitened residual
-    double* sW = sJ + 480;      // wheel [3][16]: cols 0..11 Jacobian, col 12 residual
-    double* sG = sW + 48;       // ground [2][8]: cols 0..5 Jacobian, col 6 residual
-    double* sWb = sG + 16;      // wheel blob [15]
-    double* sP = base + 2 * kPairHalf;   // prior residual [15]   (phase B, one item at a time)
-    double* sPJ = sP + 16;               // prior J [225]
+    double* sC = base + h * kPairHalf;   // compact IMU blob
+    double* W = sC + kCB;
+    double* sWb = W + kWSize;            // wheel blob [15]
+    double* sPg = base + 2 * kPairHalf;
     const double* X = a.xc + (size_t)w * n * 15;
     const uint8_t* cm = a.const_mask + (size_t)w * n;
     const uint8_t mb = (mode == 1 || !live) ? 0 : cm[i];
@@ -360,16 +405,12 @@ __device__ __forceinline__ void factor_pair_item(const WindowArgs& a, const int 
     const bool wheel_on = live && i > 0 && a.has_wheel && ((ma & 3) != 3 || (mb & 3) != 3);
     const bool ground_on = live && a.ground_multiplicity > 0 && (mb & 3) != 3;
     const bool prior_on = live && a.prior_frame == i && (mb & 15) != 15;
+    const double* blob = a.imu + ((size_t)w * (n - 1) + (i > 0 ? i - 1 : 0)) * 466;
     // ---- phase A: both items at once.  Constant inputs travel to shared memory while the exponentials are evaluated.
-    if (imu_on) {
-        const double* blob = a.imu + ((size_t)w * (n - 1) + (i - 1)) * 466;
-        if ((reinterpret_cast<uintptr_t>(blob) & 15) == 0) {
-            for (int k = sl; k < 233; k += 16) cp_async16(sblob + 2 * k, blob + 2 * k);
-        } else {
-            for (int k = sl; k < 466; k += 16) cp_async8(sblob + k, blob + k);
-        }
-    }
+    if (imu_on) stage_compact_blob(sC, blob, sl, 16);
     if (wheel_on && sl < 15) cp_async8(sWb + sl, a.wheel + ((size_t)w * (n - 1) + (i - 1)) * 15 + sl);
+    // rows 15..19 (and the IMU rows of an item without IMU factor) start from zero
+    for (int k = (imu_on ? 15 * kWS : 0) + sl; k < kWSize; k += 16) W[k] = 0.0;
     // sub-lane roles
     const bool value_lane = sl == 0;
     const bool l_pb = sl >= 1 && sl <= 3, l_ta = sl >= 4 && sl <= 6, l_tb = sl >= 7 && sl <= 9, l_bw = sl >= 10 && sl <= 12;
@@ -381,7 +422,6 @@ __device__ __forceinline__ void factor_pair_item(const WindowArgs& a, const int 
     const int col_b = l_pb ? kk : (l_tb ? 3 + kk : -1);
     const bool dead_a = col_a >= 0 && col_const(ma, col_a);
     const bool dead_b = col_b >= 0 && col_const(mb, col_b);
-    double cost = 0.0;
     {
         const FrameState<Dual> fa_ = seed_frame_state(xa, seed_a);
         const FrameState<Dual> fb_ = seed_frame_state(xb, seed_b);
@@ -392,88 +432,69 @@ __device__ __forceinline__ void factor_pair_item(const WindowArgs& a, const int 
         __syncwarp();
         if (imu_on) {
             Dual ri[15];
-            item_imu<Dual>(a.C, sblob, fa_, fb_, Ri, Rj, ri);
-            const double* Sq = sblob + 240;  // sqrt_inverse_P = L^T: upper triangular
-            if (sl <= 12) {
+            item_imu_t<Dual, 6, 0>(a.C, sC, sC + 16, sC[70], fa_, fb_, Ri, Rj, ri);
+            if (value_lane) {
+#pragma unroll
+                for (int r = 0; r < 15; ++r) *reinterpret_cast<double2*>(W + r * kWS + 30) = make_double2(ri[r].a, 0.0);
+            } else if (sl <= 12) {
 #pragma unroll
                 for (int r = 0; r < 15; ++r) {
-                    double s = 0.0;
-#pragma unroll
-                    for (int k = r; k < 15; ++k) s += Sq[r * 15 + k] * (value_lane ? ri[k].a : ri[k].d);
-                    if (value_lane) {
-                        sJ[r * 32 + 30] = s; sJ[r * 32 + 31] = 0.0;
-                        cost += s * s;
-                    } else {
-                        if (col_a >= 0) sJ[r * 32 + col_a] = dead_a ? 0.0 : (l_pb ? -s : s);
-                        if (col_b >= 0) sJ[r * 32 + 15 + col_b] = dead_b ? 0.0 : s;
-                    }
+                    const double s = ri[r].d;
+                    if (col_a >= 0) W[r * kWS + col_a] = dead_a ? 0.0 : (l_pb ? -s : s);
+                    if (col_b >= 0) W[r * kWS + 15 + col_b] = dead_b ? 0.0 : s;
                 }
             }
             // the 15 closed-form columns, one per sub-lane: t = 0 v_a, 1 ba_a, 2 v_b, 3 ba_b, 4 bw_b; component k
             if (sl < 15) {
                 const int t = sl / 3, k = sl - 3 * t;
-                const double Dt = sblob[465];
-                const double* Jm = sblob + 15;
+                const double Dt = sC[70];
+                const double* Jc = sC + 16;
                 double rik[3];   // row k of R_i (= column k of R_i^T)
 #pragma unroll
                 for (int j = 0; j < 3; ++j) rik[j] = k == 0 ? Ri.m[j].a : (k == 1 ? Ri.m[3 + j].a : Ri.m[6 + j].a);
-                double raw[15];
-#pragma unroll
-                for (int r = 0; r < 15; ++r) {
-                    double v = 0.0;
-                    if (r < 3) v = t == 0 ? rik[r] * Dt : (t == 1 ? Jm[r * 15 + 9 + k] : 0.0);
-                    else if (r < 6) v = t == 0 ? rik[r - 3] : (t == 1 ? Jm[r * 15 + 9 + k] : (t == 2 ? -rik[r - 3] : 0.0));
-                    else if (r >= 9 && r < 12) v = (r - 9 == k) ? (t == 1 ? -1.0 : (t == 3 ? 1.0 : 0.0)) : 0.0;
-                    else if (r >= 12) v = (r - 12 == k && t == 4) ? 1.0 : 0.0;
-                    raw[r] = v;
-                }
                 // column index: v_a 6.., ba_a 9.., v_b 21.., ba_b 24.., bw_b 27..
                 const int c = (t == 0 ? 6 : (t == 1 ? 9 : (t == 2 ? 21 : (t == 3 ? 24 : 27)))) + k;
                 const bool dead = col_const(c < 15 ? ma : mb, c % 15);
 #pragma unroll
                 for (int r = 0; r < 15; ++r) {
-                    double s = 0.0;
-#pragma unroll
-                    for (int q = r; q < 15; ++q) s += Sq[r * 15 + q] * raw[q];
-                    sJ[r * 32 + c] = dead ? 0.0 : s;
+                    double v = 0.0;
+                    if (r < 3) v = t == 0 ? rik[r] * Dt : (t == 1 ? Jc[r * 6 + k] : 0.0);
+                    else if (r < 6) v = t == 0 ? rik[r - 3] : (t == 1 ? Jc[r * 6 + k] : (t == 2 ? -rik[r - 3] : 0.0));
+                    else if (r >= 9 && r < 12) v = (r - 9 == k) ? (t == 1 ? -1.0 : (t == 3 ? 1.0 : 0.0)) : 0.0;
+                    else if (r >= 12) v = (r - 12 == k && t == 4) ? 1.0 : 0.0;
+                    W[r * kWS + c] = dead ? 0.0 : v;
                 }
             }
-        } else {
-            for (int k = sl; k < 480; k += 16) sJ[k] = 0.0;
         }
         if (wheel_on) {
             Dual rw[3];
             item_wheel<Dual>(a.C, sWb, fa_.p, fb_.p, Ri, Rj, rw);
             if (value_lane) {
 #pragma unroll
-                for (int k = 0; k < 3; ++k) { sW[k * 16 + 12] = rw[k].a; cost += rw[k].a * rw[k].a; }
+                for (int k = 0; k < 3; ++k) W[(15 + k) * kWS + 30] = rw[k].a;
             } else if (l_pb || l_ta || l_tb) {
 #pragma unroll
                 for (int k = 0; k < 3; ++k) {
-                    if (col_a >= 0) sW[k * 16 + col_a] = dead_a ? 0.0 : (l_pb ? -rw[k].d : rw[k].d);
-                    if (col_b >= 0) sW[k * 16 + 6 + col_b] = dead_b ? 0.0 : rw[k].d;
+                    if (col_a >= 0) W[(15 + k) * kWS + col_a] = dead_a ? 0.0 : (l_pb ? -rw[k].d : rw[k].d);
+                    if (col_b >= 0) W[(15 + k) * kWS + 15 + col_b] = dead_b ? 0.0 : rw[k].d;
                 }
             }
-        } else {
-            for (int k = sl; k < 48; k += 16) sW[k] = 0.0;
         }
         if (ground_on) {
             Dual rg[2];
             item_ground<Dual>(a.C, fb_.p, Rj, rg);
+            const double sm = sqrt((double)a.ground_multiplicity);
             if (value_lane) {
-                sG[6] = rg[0].a;
-                sG[14] = rg[1].a;
-                cost += a.ground_multiplicity * (rg[0].a * rg[0].a + rg[1].a * rg[1].a);
+                W[18 * kWS + 30] = sm * rg[0].a;
+                W[19 * kWS + 30] = sm * rg[1].a;
             } else if (col_b >= 0) {
-                sG[col_b] = dead_b ? 0.0 : rg[0].d;
-                sG[8 + col_b] = dead_b ? 0.0 : rg[1].d;
+                W[18 * kWS + 15 + col_b] = dead_b ? 0.0 : sm * rg[0].d;
+                W[19 * kWS + 15 + col_b] = dead_b ? 0.0 : sm * rg[1].d;
             }
-        } else {
-            sG[sl] = 0.0;
         }
     }
     __syncwarp();
-    // ---- phase B: J^T J of the two items, one after the other on the full warp (lane = state column)
+    // ---- phase B: whitening and W^T W of the two items, one after the other on the full warp
 #pragma unroll 1
     for (int hh = 0; hh < 2; ++hh) {
         const int src = 16 * hh;
@@ -481,85 +502,11 @@ __device__ __forceinline__ void factor_pair_item(const WindowArgs& a, const int 
         const int wv = __shfl_sync(0xffffffffu, w, src), iv = __shfl_sync(0xffffffffu, i, src);
         const uint8_t mbv = (uint8_t)__shfl_sync(0xffffffffu, (int)mb, src);
         const bool prior_v = __shfl_sync(0xffffffffu, (int)prior_on, src) != 0;
+        const bool imu_v = __shfl_sync(0xffffffffu, (int)imu_on, src) != 0;
         const int parity = 1 - a.state[wv].cur;
         double* out = a.items + ((size_t)parity * total + (size_t)wv * n + iv) * kItem;
-        const double* sJh = base + hh * kPairHalf + 480;
-        const double* sWh = sJh + 480;
-        const double* sGh = sWh + 48;
-        double c_item = lane == src ? cost : 0.0;
-        if (prior_v) {
-            const double* PJg = a.prior_J + (size_t)wv * kBlk;
-            for (int k = lane; k < kBlk; k += 32) cp_async8(sPJ + k, PJg + k);
-            cp_async_wait_all();
-            __syncwarp();
-            if (lane < 15) {
-                const double* X0 = a.prior_X0 + (size_t)wv * 15;
-                const double* xbv = a.xc + ((size_t)wv * n + iv) * 15;
-                double s = 0.0;
-                for (int k = 0; k < 15; ++k) s += sPJ[lane * 15 + k] * (xbv[k] - X0[k]);
-                sP[lane] = s;
-                c_item += s * s;
-            }
-            __syncwarp();
-        }
-        double gsum = 0.0;
-        if (lane < 30) {
-            double mine[15];
-#pragma unroll
-            for (int r = 0; r < 15; ++r) mine[r] = sJh[r * 32 + lane];
-#pragma unroll
-            for (int r = 0; r < 15; ++r) gsum += mine[r] * sJh[r * 32 + 30];
-            const int fl = lane % 15;
-            const bool pose_lane = fl < 6;
-            const int wc = (lane < 15 ? 0 : 6) + fl;
-            double w0 = 0.0, w1 = 0.0, w2 = 0.0, jp = 0.0, jq = 0.0;
-            const double m = (double)a.ground_multiplicity;
-            if (pose_lane) {
-                w0 = sWh[wc]; w1 = sWh[16 + wc]; w2 = sWh[32 + wc];
-                gsum += w0 * sWh[12] + w1 * sWh[16 + 12] + w2 * sWh[32 + 12];
-                if (lane >= 15) {
-                    jp = sGh[fl]; jq = sGh[8 + fl];
-                    gsum += m * (jp * sGh[6] + jq * sGh[8 + 6]);
-                }
-            }
-            const bool prior_lane = prior_v && lane >= 15 && !col_const(mbv, fl);
-            if (prior_lane) {
-                double gs = 0.0;
-                for (int r = 0; r < 15; ++r) gs += sPJ[r * 15 + fl] * sP[r];
-                gsum += gs;
-            }
-#pragma unroll 1
-            for (int c2 = 0; c2 < 30; c2 += 2) {
-                double s2[2] = {0.0, 0.0};
-#pragma unroll
-                for (int r = 0; r < 15; ++r) {
-                    const double2 v = *reinterpret_cast<const double2*>(sJh + r * 32 + c2);
-                    s2[0] += mine[r] * v.x;
-                    s2[1] += mine[r] * v.y;
-                }
-#pragma unroll
-                for (int q = 0; q < 2; ++q) {
-                    const int c = c2 + q;
-                    double s = s2[q];
-                    const int cf = c % 15;
-                    if (cf < 6) {
-                        const int cw = (c < 15 ? 0 : 6) + cf;
-                        s += w0 * sWh[cw] + w1 * sWh[16 + cw] + w2 * sWh[32 + cw];
-                        if (c >= 15) s += m * (jp * sGh[cf] + jq * sGh[8 + cf]);
-                    }
-                    if (c >= 15 && prior_lane && !col_const(mbv, cf)) {
-                        double ps = 0.0;
-                        for (int r = 0; r < 15; ++r) ps += sPJ[r * 15 + fl] * sPJ[r * 15 + cf];
-                        s += ps;
-                    }
-                    out[c * 30 + lane] = s;
-                }
-            }
-            out[kItemGa + lane] = gsum;
-        }
-        c_item = warp_sum(c_item);
-        if (lane == 31) out[kItemCost] = c_item;
-        __syncwarp();   // sP / sPJ are reused by the second item
+        const double* sq = imu_v ? a.imu + ((size_t)wv * (n - 1) + (iv - 1)) * 466 + 240 : nullptr;
+        item_finish(a, base + hh * kPairHalf + kCB, sq, wv, iv, mbv, prior_v, sPg, out, lane);
     }
 }
 
@@ -654,26 +601,48 @@ template <int NT> __device__ __forceinline__ bool grp_inverse15(double* A, doubl
     __syncthreads();
     return red[8] != 0.0;
 }
-// The two GEMM kernels: thread = (row r = tid & 15, column group g = tid >> 4); NT / 16 groups of ceil(15 / groups)
-// columns each (NT = 32: 8 + 7 columns, NT = 128: 2 columns per thread).
+// The two 15 x 15 x 15 products run on the fp64 tensor pipe: padded to 16 x 16 x 16 = 2 x 2 tiles x 4 k-steps of
+// DMMA.8x8x4, operands read straight from the packed 15-stride blocks (index 15 reads as zero).  With more than one
+// warp per window the four tiles are dealt to the warps.  16 DMMA + 16 shared-memory loads per product where the
+// vector-pipe version issued 120 DFMA + 135 loads.
 // C = A B
 template <int NT>
 __device__ __noinline__ void gemm_ab15(double* Cm, const double* A, const double* B, int tid) {
-    constexpr int G = NT / 16, CPG = (15 + G - 1) / G;
-    const int r = tid & 15, c0 = (tid >> 4) * CPG;
-    if (r < 15) {
-        double a[15];
+    constexpr int NW = NT / 32;
+    const int lane = tid & 31, wi = tid >> 5, g = lane >> 2, t = lane & 3;
+    if (NW == 1) {
+        double af[2][4], bf[4][2];
 #pragma unroll
-        for (int k = 0; k < 15; ++k) a[k] = A[r * 15 + k];
+        for (int ks = 0; ks < 4; ++ks) {
+            const int k = 4 * ks + t;
+            af[0][ks] = k < 15 ? A[g * 15 + k] : 0.0;
+            af[1][ks] = (k < 15 && g < 7) ? A[(8 + g) * 15 + k] : 0.0;
+            bf[ks][0] = k < 15 ? B[k * 15 + g] : 0.0;
+            bf[ks][1] = (k < 15 && g < 7) ? B[k * 15 + 8 + g] : 0.0;
+        }
 #pragma unroll
-        for (int cc = 0; cc < CPG; ++cc) {
-            const int c = c0 + cc;
-            if (c < 15) {
-                double s = 0.0;
+        for (int mi = 0; mi < 2; ++mi)
 #pragma unroll
-                for (int k = 0; k < 15; ++k) s += a[k] * B[k * 15 + c];
-                Cm[r * 15 + c] = s;
+            for (int ni = 0; ni < 2; ++ni) {
+                double c0 = 0.0, c1 = 0.0;
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks) dmma884(c0, c1, af[mi][ks], bf[ks][ni]);
+                const int r = 8 * mi + g, c = 8 * ni + 2 * t;
+                if (r < 15) { Cm[r * 15 + c] = c0; if (c + 1 < 15) Cm[r * 15 + c + 1] = c1; }
             }
+    } else {
+#pragma unroll
+        for (int tl = 0; tl < 4; ++tl) {
+            if ((tl % NW) != wi) continue;
+            const int mi = tl >> 1, ni = tl & 1, r = 8 * mi + g;
+            double c0 = 0.0, c1 = 0.0;
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) {
+                const int k = 4 * ks + t;
+                dmma884(c0, c1, (r < 15 && k < 15) ? A[r * 15 + k] : 0.0, (k < 15 && 8 * ni + g < 15) ? B[k * 15 + 8 * ni + g] : 0.0);
+            }
+            const int c = 8 * ni + 2 * t;
+            if (r < 15) { Cm[r * 15 + c] = c0; if (c + 1 < 15) Cm[r * 15 + c + 1] = c1; }
         }
     }
     grp_sync<NT>();
@@ -681,21 +650,40 @@ __device__ __noinline__ void gemm_ab15(double* Cm, const double* A, const double
 // C -= A B^T
 template <int NT>
 __device__ __noinline__ void gemm_sub_abt15(double* Cm, const double* A, const double* B, int tid) {
-    constexpr int G = NT / 16, CPG = (15 + G - 1) / G;
-    const int r = tid & 15, c0 = (tid >> 4) * CPG;
-    if (r < 15) {
-        double a[15];
+    constexpr int NW = NT / 32;
+    const int lane = tid & 31, wi = tid >> 5, g = lane >> 2, t = lane & 3;
+    if (NW == 1) {
+        double af[2][4], bf[4][2];
 #pragma unroll
-        for (int k = 0; k < 15; ++k) a[k] = A[r * 15 + k];
+        for (int ks = 0; ks < 4; ++ks) {
+            const int k = 4 * ks + t;
+            af[0][ks] = k < 15 ? -A[g * 15 + k] : 0.0;
+            af[1][ks] = (k < 15 && g < 7) ? -A[(8 + g) * 15 + k] : 0.0;
+            bf[ks][0] = k < 15 ? B[g * 15 + k] : 0.0;
+            bf[ks][1] = (k < 15 && g < 7) ? B[(8 + g) * 15 + k] : 0.0;
+        }
 #pragma unroll
-        for (int cc = 0; cc < CPG; ++cc) {
-            const int c = c0 + cc;
-            if (c < 15) {
-                double s = 0.0;
+        for (int mi = 0; mi < 2; ++mi)
 #pragma unroll
-                for (int k = 0; k < 15; ++k) s += a[k] * B[c * 15 + k];
-                Cm[r * 15 + c] -= s;
+            for (int ni = 0; ni < 2; ++ni) {
+                const int r = 8 * mi + g, c = 8 * ni + 2 * t;
+                double c0 = (r < 15) ? Cm[r * 15 + c] : 0.0, c1 = (r < 15 && c + 1 < 15) ? Cm[r * 15 + c + 1] : 0.0;
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks) dmma884(c0, c1, af[mi][ks], bf[ks][ni]);
+                if (r < 15) { Cm[r * 15 + c] = c0; if (c + 1 < 15) Cm[r * 15 + c + 1] = c1; }
             }
+    } else {
+#pragma unroll
+        for (int tl = 0; tl < 4; ++tl) {
+            if ((tl % NW) != wi) continue;
+            const int mi = tl >> 1, ni = tl & 1, r = 8 * mi + g, c = 8 * ni + 2 * t;
+            double c0 = (r < 15) ? Cm[r * 15 + c] : 0.0, c1 = (r < 15 && c + 1 < 15) ? Cm[r * 15 + c + 1] : 0.0;
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) {
+                const int k = 4 * ks + t;
+                dmma884(c0, c1, (r < 15 && k < 15) ? -A[r * 15 + k] : 0.0, (k < 15 && 8 * ni + g < 15) ? B[(8 * ni + g) * 15 + k] : 0.0);
+            }
+            if (r < 15) { Cm[r * 15 + c] = c0; if (c + 1 < 15) Cm[r * 15 + c + 1] = c1; }
         }
     }
     grp_sync<NT>();
@@ -948,8 +936,8 @@ __device__ void window_step(const WindowArgs& a, int w, int lane, double* ws) {
     // gradient entry c of frame f
     auto grad = [&](int f, int c) -> double {
         if (is_const(f, c)) return 0.0;
-        double g = itm[(size_t)f * kItem + kItemGb + c];
-        if (f + 1 < n) g += itm[(size_t)(f + 1) * kItem + kItemGa + c];
+        double g = itm[(size_t)f * kItem + item_gb(c)];
+        if (f + 1 < n) g += itm[(size_t)(f + 1) * kItem + item_ga(c)];
         if (c < 6 && c != 2) {
             const int k = c < 2 ? c : c - 1;
             if (fa[f]) g += lsq * lb[f * NPAD + IGJ + k];

@@ -248,6 +248,9 @@ def test_gpu_solver_matches_reference_text(fast_mode):
 
 @pytest.mark.gpu
 def test_gpu_init_solve_matches_reference_text():
+    """solver::init_solve on the CUDA library against the reference text: in lock-step under a 15-iteration cap (tight),
+    and at the reference's own 50 iterations in fast_mode (the run ends inside the rounding-dominated zig-zag regime,
+    see check_solve_pair: equally good answers, poses within 1e-3)."""
     import oracle_lib as oracle
 
     P = L.corridor_params(fast_mode=True)
@@ -255,16 +258,30 @@ def test_gpu_init_solve_matches_reference_text():
     hb = oracle.preintegrate_batch(P, sb)
     frames = replay.frames_of(sb, hb["imu"], hb["wheel"])
     frames[0].laser_match = None
-    a, b = copy.deepcopy(frames), copy.deepcopy(frames)
     ref = ref_lib.RefSolver(fast_mode=True)
     mine = Solver(P, fast_mode=True)
+    P15 = L.corridor_params(max_iters=15)
+    mine15 = Solver(P15)
     try:
+        a, b = copy.deepcopy(frames), copy.deepcopy(frames)
         ref.init_solve(a)
         mine.init_solve(b)
-        assert int(mine.last_summary["iterations"][0]) == int(ref.last_summary["iterations"][0])
-        assert np.abs(states_of(a) - states_of(b))[:, 0:6].max() < 1e-4
+        assert int(mine.last_summary["iterations"][0]) == int(ref.last_summary["iterations"][0]) > 10
+        assert np.abs(states_of(a) - states_of(b))[:, 0:6].max() < 1e-3
+        assert float(mine.last_summary["final_cost"][0]) == pytest.approx(float(ref.last_summary["final_cost"][0]), rel=5e-2)
+        ref15 = ref_lib.RefSolver(fast_mode=False)
+        ref_lib.set_iteration_cap(15)
+        try:
+            a, b = copy.deepcopy(frames), copy.deepcopy(frames)
+            ref15.init_solve(a)
+            mine15.init_solve(b)
+            assert int(mine15.last_summary["iterations"][0]) == int(ref15.last_summary["iterations"][0]) == 15
+            assert np.abs(states_of(a) - states_of(b)).max() < 1e-6
+        finally:
+            ref_lib.set_iteration_cap(0)
     finally:
         mine.close()
+        mine15.close()
 
 
 @pytest.mark.gpu
