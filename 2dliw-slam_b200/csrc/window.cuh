@@ -69,24 +69,31 @@ struct LMOptions {
 };
 
 constexpr int kBlk = 225;
-// Factor item record = the symmetric 32 x 32 product W^T W of the item's whitened Jacobian | residual matrix W
-// (columns 0..14 frame i-1, 15..29 frame i, 30 the whitened residual, 31 zero), i.e. J^T J (30 x 30), J^T r (column 30)
-// and r^T r (entry 30,30) in one matrix, stored as its 10 upper 8 x 8 tiles, tile (ti, tj) row-major at
-// 64 * (ti * 4 - ti (ti - 1) / 2 + tj - ti): exactly what the DMMA accumulators of factor_pair_kernel hold, written with
-// one 16-byte store per lane and tile (512 contiguous bytes per warp).  640 doubles per item (the dense 30 x 30 + g
-// record of round 1 was 936).
+// Factor item record = the symmetric 32 x 32 product W^T W of the item's whitened Jacobian | residual matrix W with the
+// columns ordered [frame i-1 (0..14) | zero (15) | frame i (16..30) | whitened residual (31)], i.e. J^T J, J^T r (column
+// 31) and r^T r (entry 31,31) in one matrix, stored as its 10 upper 8 x 8 tiles (64 doubles each, row-major) grouped by
+// the 16 x 16 block the window kernel consumes:
+//   haa = H(i-1, i-1): tiles (0,0) (0,1) (1,1)          at   0,  64, 128
+//   hab = H(i-1, i)  : tiles (0,2) (0,3) (1,2) (1,3)    at 192, 256, 320, 384   (its column 15 is g_a)
+//   hbb = H(i, i)    : tiles (2,2) (2,3) (3,3)          at 448, 512, 576        (its column 15 is g_b, entry (15,15) the cost)
+// — exactly what the DMMA accumulators of the factor kernels hold, written with one 16-byte store per lane and tile, and
+// read by window_kernel as contiguous 16-byte chunks straight into its tile-form blocks.  640 doubles per item (the
+// dense 30 x 30 + g record of round 1 was 936).
 constexpr int kItem = 640;
-__host__ __device__ __forceinline__ int item_idx(int r, int c) {   // entry (r, c) = (c, r), r, c in 0..31
+__host__ __device__ __forceinline__ int item_tile_slot(int ti, int tj) {   // upper tiles only (ti <= tj)
+    return ti == 0 ? (tj == 0 ? 0 : (tj == 1 ? 1 : tj + 1)) : (ti == 1 ? (tj == 1 ? 2 : tj + 3) : (ti == 2 ? tj + 5 : 9));
+}
+__host__ __device__ __forceinline__ int item_idx(int r, int c) {   // entry (r, c) = (c, r) of the 32 x 32 matrix
     if (r > c) { const int t = r; r = c; c = t; }
-    const int ti = r >> 3, tj = c >> 3;
-    return 64 * (ti * 4 - (ti * (ti - 1)) / 2 + tj - ti) + (r & 7) * 8 + (c & 7);
+    return 64 * item_tile_slot(r >> 3, c >> 3) + (r & 7) * 8 + (c & 7);
 }
 __device__ __forceinline__ int item_haa(int r, int c) { return item_idx(r, c); }
-__device__ __forceinline__ int item_hab(int r, int c) { return item_idx(r, 15 + c); }
-__device__ __forceinline__ int item_hbb(int r, int c) { return item_idx(15 + r, 15 + c); }
-__device__ __forceinline__ int item_ga(int c) { return item_idx(c, 30); }
-__device__ __forceinline__ int item_gb(int c) { return item_idx(15 + c, 30); }
-constexpr int kItemCost = 64 * 9 + 6 * 8 + 6;   // item_idx(30, 30)
+__device__ __forceinline__ int item_hab(int r, int c) { return item_idx(r, 16 + c); }
+__device__ __forceinline__ int item_hbb(int r, int c) { return item_idx(16 + r, 16 + c); }
+__device__ __forceinline__ int item_ga(int c) { return item_idx(c, 31); }
+__device__ __forceinline__ int item_gb(int c) { return item_idx(16 + c, 31); }
+constexpr int kItemCost = 64 * 9 + 63;   // item_idx(31, 31)
+constexpr int kItemHab = 192, kItemHbb = 448;
 
 struct WindowArgs {
     Consts C;
@@ -160,7 +167,8 @@ __device__ __forceinline__ void dmma884(double& d0, double& d1, const double a, 
 //
 // Shared-memory matrix W of one item, [kWRows][kWS] doubles (row stride 34: 16-byte aligned rows for the DMMA result
 // stores, at most 2-way bank conflicts on the fragment loads):
-//   rows  0..14  IMU factor: Jacobian | residual (column 30), un-whitened after phase A, whitened in place by item_finish
+//   columns      0..14 frame i-1 | 15 zero | 16..30 frame i | 31 the residual
+//   rows  0..14  IMU factor: Jacobian | residual, un-whitened after phase A, whitened in place by item_finish
 //   rows 15..17  wheel factor (already weighted by diag(sqrt_inverse_P), wheel_factor.h:58-70)
 //   rows 18..19  the two ground factors times sqrt(multiplicity) (the reference adds them n times, solver.cpp:727-743)
 // Constant parameter blocks have zero columns (Ceres removes them from the reduced program, solver.cpp:787-794);
@@ -242,10 +250,10 @@ __device__ __forceinline__ void item_finish(const WindowArgs& a, double* W, cons
         for (int ti = 0; ti < 4; ++ti)
 #pragma unroll
             for (int tj = ti; tj < 4; ++tj) {
-                const int r = 8 * ti + g - 15;
+                const int r = 8 * ti + g - 16;
 #pragma unroll
                 for (int q = 0; q < 2; ++q) {
-                    const int c = 8 * tj + 2 * t + q - 15;
+                    const int c = 8 * tj + 2 * t + q - 16;
                     if (r >= 0 && r < 15 && !col_const(mb, r)) {
                         if (c >= 0 && c < 15 && !col_const(mb, c)) acc[tile][q] += PH[r * 15 + c];
                         else if (c == 15) acc[tile][q] += sPg[r];
@@ -255,9 +263,16 @@ __device__ __forceinline__ void item_finish(const WindowArgs& a, double* W, cons
             }
         __syncwarp();   // sPg may be reused by the next item
     }
+    {
+        int tile = 0;
 #pragma unroll
-    for (int tile = 0; tile < 10; ++tile)
-        *reinterpret_cast<double2*>(out + tile * 64 + g * 8 + 2 * t) = make_double2(acc[tile][0], acc[tile][1]);
+        for (int ti = 0; ti < 4; ++ti)
+#pragma unroll
+            for (int tj = ti; tj < 4; ++tj) {
+                *reinterpret_cast<double2*>(out + item_tile_slot(ti, tj) * 64 + g * 8 + 2 * t) = make_double2(acc[tile][0], acc[tile][1]);
+                ++tile;
+            }
+    }
 }
 
 // J^T J of the marginalisation prior, once per upload: prior_H[w] = prior_J[w]^T prior_J[w]
@@ -325,6 +340,7 @@ __global__ void __launch_bounds__(128, LV_FACTOR_MINB) factor_kernel(WindowArgs 
         const bool value_lane = lane == 30;
         const bool dead = lane < 30 && col_const(lane < 15 ? ma : mb, lane % 15);
         const double sm = sqrt((double)a.ground_multiplicity);
+        const int wcol = lane < 15 ? lane : (lane < 30 ? lane + 1 : (lane == 30 ? 31 : 15));   // column of W this lane owns
         if (imu_on) {
             Dual ri[15];
             item_imu<Dual>(a.C, sblob, fa_, fb_, Ri, Rj, ri);
@@ -334,7 +350,7 @@ __global__ void __launch_bounds__(128, LV_FACTOR_MINB) factor_kernel(WindowArgs 
                 double s = 0.0;
 #pragma unroll
                 for (int k = r; k < 15; ++k) s += Sq[r * 15 + k] * (value_lane ? ri[k].a : ri[k].d);
-                W[r * kWS + lane] = (dead || lane == 31) ? 0.0 : s;
+                W[r * kWS + wcol] = (dead || lane == 31) ? 0.0 : s;
             }
         }
         const int fl = lane % 15;
@@ -343,21 +359,21 @@ __global__ void __launch_bounds__(128, LV_FACTOR_MINB) factor_kernel(WindowArgs 
             item_wheel<Dual>(a.C, sWb, fa_.p, fb_.p, Ri, Rj, rw);
             if (lane < 30 && fl < 6) {
 #pragma unroll
-                for (int k = 0; k < 3; ++k) W[(15 + k) * kWS + lane] = dead ? 0.0 : rw[k].d;
+                for (int k = 0; k < 3; ++k) W[(15 + k) * kWS + wcol] = dead ? 0.0 : rw[k].d;
             } else if (value_lane) {
 #pragma unroll
-                for (int k = 0; k < 3; ++k) W[(15 + k) * kWS + 30] = rw[k].a;
+                for (int k = 0; k < 3; ++k) W[(15 + k) * kWS + 31] = rw[k].a;
             }
         }
         if (ground_on) {
             Dual rg[2];
             item_ground<Dual>(a.C, fb_.p, Rj, rg);
             if (lane >= 15 && lane < 21) {
-                W[18 * kWS + lane] = dead ? 0.0 : sm * rg[0].d;
-                W[19 * kWS + lane] = dead ? 0.0 : sm * rg[1].d;
+                W[18 * kWS + wcol] = dead ? 0.0 : sm * rg[0].d;
+                W[19 * kWS + wcol] = dead ? 0.0 : sm * rg[1].d;
             } else if (value_lane) {
-                W[18 * kWS + 30] = sm * rg[0].a;
-                W[19 * kWS + 30] = sm * rg[1].a;
+                W[18 * kWS + 31] = sm * rg[0].a;
+                W[19 * kWS + 31] = sm * rg[1].a;
             }
         }
     }
@@ -435,13 +451,13 @@ __device__ __forceinline__ void factor_pair_item(const WindowArgs& a, const int 
             item_imu_t<Dual, 6, 0>(a.C, sC, sC + 16, sC[70], fa_, fb_, Ri, Rj, ri);
             if (value_lane) {
 #pragma unroll
-                for (int r = 0; r < 15; ++r) *reinterpret_cast<double2*>(W + r * kWS + 30) = make_double2(ri[r].a, 0.0);
+                for (int r = 0; r < 15; ++r) { W[r * kWS + 31] = ri[r].a; W[r * kWS + 15] = 0.0; }
             } else if (sl <= 12) {
 #pragma unroll
                 for (int r = 0; r < 15; ++r) {
                     const double s = ri[r].d;
                     if (col_a >= 0) W[r * kWS + col_a] = dead_a ? 0.0 : (l_pb ? -s : s);
-                    if (col_b >= 0) W[r * kWS + 15 + col_b] = dead_b ? 0.0 : s;
+                    if (col_b >= 0) W[r * kWS + 16 + col_b] = dead_b ? 0.0 : s;
                 }
             }
             // the 15 closed-form columns, one per sub-lane: t = 0 v_a, 1 ba_a, 2 v_b, 3 ba_b, 4 bw_b; component k
@@ -452,9 +468,9 @@ __device__ __forceinline__ void factor_pair_item(const WindowArgs& a, const int 
                 double rik[3];   // row k of R_i (= column k of R_i^T)
 #pragma unroll
                 for (int j = 0; j < 3; ++j) rik[j] = k == 0 ? Ri.m[j].a : (k == 1 ? Ri.m[3 + j].a : Ri.m[6 + j].a);
-                // column index: v_a 6.., ba_a 9.., v_b 21.., ba_b 24.., bw_b 27..
-                const int c = (t == 0 ? 6 : (t == 1 ? 9 : (t == 2 ? 21 : (t == 3 ? 24 : 27)))) + k;
-                const bool dead = col_const(c < 15 ? ma : mb, c % 15);
+                // column of W: v_a 6.., ba_a 9.., v_b 16 + 6.., ba_b 16 + 9.., bw_b 16 + 12..
+                const int c = (t == 0 ? 6 : (t == 1 ? 9 : (t == 2 ? 22 : (t == 3 ? 25 : 28)))) + k;
+                const bool dead = col_const(c < 15 ? ma : mb, c < 15 ? c : c - 16);
 #pragma unroll
                 for (int r = 0; r < 15; ++r) {
                     double v = 0.0;
@@ -471,12 +487,12 @@ __device__ __forceinline__ void factor_pair_item(const WindowArgs& a, const int 
             item_wheel<Dual>(a.C, sWb, fa_.p, fb_.p, Ri, Rj, rw);
             if (value_lane) {
 #pragma unroll
-                for (int k = 0; k < 3; ++k) W[(15 + k) * kWS + 30] = rw[k].a;
+                for (int k = 0; k < 3; ++k) W[(15 + k) * kWS + 31] = rw[k].a;
             } else if (l_pb || l_ta || l_tb) {
 #pragma unroll
                 for (int k = 0; k < 3; ++k) {
                     if (col_a >= 0) W[(15 + k) * kWS + col_a] = dead_a ? 0.0 : (l_pb ? -rw[k].d : rw[k].d);
-                    if (col_b >= 0) W[(15 + k) * kWS + 15 + col_b] = dead_b ? 0.0 : rw[k].d;
+                    if (col_b >= 0) W[(15 + k) * kWS + 16 + col_b] = dead_b ? 0.0 : rw[k].d;
                 }
             }
         }
@@ -485,11 +501,11 @@ __device__ __forceinline__ void factor_pair_item(const WindowArgs& a, const int 
             item_ground<Dual>(a.C, fb_.p, Rj, rg);
             const double sm = sqrt((double)a.ground_multiplicity);
             if (value_lane) {
-                W[18 * kWS + 30] = sm * rg[0].a;
-                W[19 * kWS + 30] = sm * rg[1].a;
+                W[18 * kWS + 31] = sm * rg[0].a;
+                W[19 * kWS + 31] = sm * rg[1].a;
             } else if (col_b >= 0) {
-                W[18 * kWS + 15 + col_b] = dead_b ? 0.0 : sm * rg[0].d;
-                W[19 * kWS + 15 + col_b] = dead_b ? 0.0 : sm * rg[1].d;
+                W[18 * kWS + 16 + col_b] = dead_b ? 0.0 : sm * rg[0].d;
+                W[19 * kWS + 16 + col_b] = dead_b ? 0.0 : sm * rg[1].d;
             }
         }
     }
@@ -704,11 +720,126 @@ template <int NT> __device__ __forceinline__ void copy_blk(double* dst, const do
 }
 // per-warp shared memory of window_kernel (doubles): 4 blocks (+3 for the arrow topology) + pivot row + one frame's
 // laser block + rhs [n][15]
-__host__ __device__ inline size_t window_smem_doubles(int n, bool arrow) { return (arrow ? 7 : 4) * kBlk + 16 + 48 + 32 + 16 + (size_t)n * 15 + 16; }
+__host__ __device__ inline size_t window_smem_doubles(int n, bool arrow) { return (arrow ? 7 * kBlk : 4 * 256) + 16 + 48 + 32 + 16 + (size_t)n * 15 + 16; }
 
 // ---------------------------------------------------------------------------------------------------
+// =====================================================================================================
+// Tile-form 16 x 16 blocks (the batched fast path of window_step: one warp per window, tracking topology).
+// A 15 x 15 block lives padded to 16 x 16 as four row-major 8 x 8 tiles [t00 | t01 | t10 | t11] — the layout the DMMA
+// fragments want (no guards, 16-byte result stores), the layout the factor kernels write the item record in (so the
+// raw blocks of an elimination step arrive as contiguous 16-byte cp.async chunks, no gather), and a layout whose
+// element index is shifts and masks of the lane id (round 1's packed 15-stride blocks spent half of the kernel's
+// instructions on e / 15, e % 15 and bounds predicates).  Row / column 15 of every block stay zero.
+constexpr int kTB = 256;
+__device__ __forceinline__ int t_idx(int r, int c) { return ((((r >> 3) << 1) + (c >> 3)) << 6) + ((r & 7) << 3) + (c & 7); }
+
+// Gauss-Jordan inverse of an SPD block in tile form (same algorithm and arithmetic as spd_inverse15)
+__device__ __noinline__ bool spd_inverse15_t(double* A, double* piv /* 16 doubles scratch */, int lane) {
+    const int r = lane & 15, h = lane >> 4, c0 = h * 8;
+    const bool act = r < 15;
+    double* rowp = A + ((((r >> 3) << 1) + h) << 6) + ((r & 7) << 3);   // 8 contiguous entries of row r, half h
+    double row[8];
+#pragma unroll
+    for (int j = 0; j < 8; j += 2) {
+        const double2 v = act ? *reinterpret_cast<const double2*>(rowp + j) : make_double2(0.0, 0.0);
+        row[j] = v.x; row[j + 1] = v.y;
+    }
+    bool ok = true;
+#pragma unroll
+    for (int k = 0; k < 15; ++k) {
+        const int kh = k >> 3, kj = k & 7;
+        const double p = __shfl_sync(0xffffffffu, row[kj], k + 16 * kh);
+        const double f = __shfl_sync(0xffffffffu, row[kj], r + 16 * kh);
+        if (!(p > 0.0) || !isfinite(p)) ok = false;
+        const double pinv = 1.0 / p;
+        if (r == k && act) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { row[j] = (c0 + j == k) ? pinv : row[j] * pinv; piv[c0 + j] = row[j]; }
+        }
+        __syncwarp();
+        if (r != k && act) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) row[j] = (c0 + j == k) ? -f * pinv : row[j] - f * piv[c0 + j];
+        }
+        __syncwarp();
+    }
+    if (act) {
+#pragma unroll
+        for (int j = 0; j < 8; j += 2) *reinterpret_cast<double2*>(rowp + j) = make_double2(row[j], row[j + 1]);
+    }
+    __syncwarp();
+    return ok;
+}
+// C = A B (tile form): 16 DMMA, 16 fragment loads, 4 16-byte stores
+__device__ __forceinline__ void gemm_ab_t(double* Cm, const double* A, const double* B, int lane) {
+    const int g = lane >> 2, t = lane & 3;
+    double af[2][4], bf[4][2];
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+#pragma unroll
+        for (int m = 0; m < 2; ++m) {
+            af[m][ks] = A[(((m << 1) + (ks >> 1)) << 6) + (g << 3) + ((ks & 1) << 2) + t];            // A[8m + g][4ks + t]
+            bf[ks][m] = B[((((ks >> 1) << 1) + m) << 6) + ((((ks & 1) << 2) + t) << 3) + g];            // B[4ks + t][8m + g]
+        }
+    }
+#pragma unroll
+    for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+        for (int ni = 0; ni < 2; ++ni) {
+            double c0 = 0.0, c1 = 0.0;
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) dmma884(c0, c1, af[mi][ks], bf[ks][ni]);
+            *reinterpret_cast<double2*>(Cm + (((mi << 1) + ni) << 6) + (g << 3) + (t << 1)) = make_double2(c0, c1);
+        }
+    __syncwarp();
+}
+// C -= A B^T (tile form)
+__device__ __forceinline__ void gemm_sub_abt_t(double* Cm, const double* A, const double* B, int lane) {
+    const int g = lane >> 2, t = lane & 3;
+    double af[2][4], bf[4][2];
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+#pragma unroll
+        for (int m = 0; m < 2; ++m) {
+            af[m][ks] = -A[(((m << 1) + (ks >> 1)) << 6) + (g << 3) + ((ks & 1) << 2) + t];           // -A[8m + g][4ks + t]
+            bf[ks][m] = B[(((m << 1) + (ks >> 1)) << 6) + (g << 3) + ((ks & 1) << 2) + t];            // B[8m + g][4ks + t] = B^T[4ks + t][8m + g]
+        }
+    }
+#pragma unroll
+    for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+        for (int ni = 0; ni < 2; ++ni) {
+            double2* cp = reinterpret_cast<double2*>(Cm + (((mi << 1) + ni) << 6) + (g << 3) + (t << 1));
+            double2 c = *cp;
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) dmma884(c.x, c.y, af[mi][ks], bf[ks][ni]);
+            *cp = c;
+        }
+    __syncwarp();
+}
+// out[r] (-)= sum_k M(r, k) v[k]  (TRANS: M(k, r)), M in tile form, r, k < 15
+template <bool TRANS, bool SUB>
+__device__ __forceinline__ void gemv_t(double* out, const double* M, const double* v, int lane) {
+    if (lane < 15) {
+        double s = 0.0;
+#pragma unroll
+        for (int k = 0; k < 15; ++k) s += M[TRANS ? t_idx(k, lane) : t_idx(lane, k)] * v[k];
+        if (SUB) out[lane] -= s; else out[lane] = s;
+    }
+    __syncwarp();
+}
+
+// item offsets of the three raw blocks of an elimination step, per packed 15 x 15 entry e = 15 r + c:
+// H(i-1, i)(r, c) | hbb(r, c) << 10 | haa(r, c) << 20 — built once per CTA (window_offsets_init), read by every frame
+__device__ __forceinline__ void window_offsets_init(uint32_t* tab, int tid, int nthreads) {
+    for (int e = tid; e < kBlk; e += nthreads) {
+        const int r = e / 15, c = e - r * 15;
+        tab[e] = (uint32_t)item_hab(r, c) | ((uint32_t)item_hbb(r, c) << 10) | ((uint32_t)item_haa(r, c) << 20);
+    }
+}
+
 template <bool ARROW, int NT>
-__device__ void window_step(const WindowArgs& a, int w, int lane, double* ws) {
+__device__ void window_step(const WindowArgs& a, int w, int lane, double* ws, const uint32_t* otab) {
     constexpr int NPAD = ARROW ? kPadFree : kPadTrack;
     constexpr int ICOST = ARROW ? 44 : 20;
     constexpr int IGJ = ARROW ? 36 : 15;
@@ -725,7 +856,7 @@ __device__ void window_step(const WindowArgs& a, int w, int lane, double* ws) {
     double* Wm = ws + 4 * kBlk;       // arrow block H(0, i)          (arrow topology only)
     double* Tp = ws + 5 * kBlk;       // T' = W Dinv
     double* D0 = ws + 6 * kBlk;       // accumulated updates of D_0
-    double* piv = ws + (ARROW ? 7 : 4) * kBlk;  // 16
+    double* piv = ws + (ARROW ? 7 * kBlk : 4 * 256);  // 16
     double* slb = piv + 16;           // laser block of the frame being assembled [NPAD]
     double* ssc = slb + 48;           // Jacobi scaling of frames i-1 and i [30]
     double* red = ssc + 32;           // cross-warp reduction scratch [16]
@@ -1099,116 +1230,8 @@ __device__ void window_step(const WindowArgs& a, int w, int lane, double* ws) {
             }
             grp_sync<NT>();
         };
-        // Dm/Cy swap roles every frame (pivot block <-> block being assembled)
-        double* Dp = Dm;
-        double* Cp = Cy;
-        assemble_D(n - 1, Dp);
-        scale_damp(n - 1, Dp);
-        bool have_wc = false, have_d0 = false;
-        for (int i = n - 1; i >= 1; --i) {
-            // raw blocks of this elimination step, fetched asynchronously while the pivot is inverted:
-            // Um <- H(i-1, i) of item i, Cp <- hbb of item i-1, Tm <- haa of item i  (D_{i-1} = hbb + haa + laser)
-            {
-                const double* it_i = itm + (size_t)i * kItem;
-                const double* it_p = itm + (size_t)(i - 1) * kItem;
-                for (int e = lane; e < kBlk; e += NT) {
-                    const int r = e / 15, c = e - r * 15;
-                    cp_async8(Um + e, it_i + item_hab(r, c));
-                    cp_async8(Cp + e, it_p + item_hbb(r, c));
-                    cp_async8(Tm + e, it_i + item_haa(r, c));
-                }
-                for (int e = lane; e < NPAD; e += NT) cp_async8(slb + e, lb + (i - 1) * NPAD + e);
-                if (lane < 30) cp_async8(ssc + lane, scw + (i - 1) * 15 + lane);
-            }
-            // per-frame flags, requested now and consumed after the inverse
-            const uint8_t cm_p = mode == 1 ? 0 : cm[i - 1];
-            const bool fa_p = fa[i - 1] != 0;
-            const bool cross_i = has_cross(i);
-            bool arrow_i = false;
-            if (ARROW && i >= 2) {
-                arrow_i = have_wc || cross_i;
-                if (arrow_i)
-                    for (int e = lane; e < kBlk; e += NT) {
-                        const int r = e / 15, c = e - r * 15;
-                        double v = have_wc ? Wm[e] : 0.0;
-                        if (cross_i && r < 6 && c < 6 && !is_const(0, r) && !is_const(i, c)) v += cross_entry(i, r, c) * scw[r] * scw[i * 15 + c];
-                        Wm[e] = v;
-                    }
-            }
-            grp_sync<NT>();
-            const bool inv_ok = grp_inverse15<NT>(Dp, piv, red, lane);
-            cp_async_wait_all();
-            grp_sync<NT>();
-            if (!inv_ok) { ok = false; break; }
-            // coupling U = H(i-1, i), scaled (+ laser cross block / carried fill-in when i == 1: H(0,1) is also the arrow
-            // block); D_{i-1} assembled, scaled and damped
-            for (int e = lane; e < kBlk; e += NT) {
-                const int r = e / 15, c = e - r * 15;
-                double v = Um[e] * ssc[r] * ssc[15 + c];
-                if (ARROW && i == 1) {
-                    if (have_wc) v += Wm[e];
-                    if (cross_i && r < 6 && c < 6 && !is_const(0, r) && !is_const(1, c)) v += cross_entry(1, r, c) * scw[r] * scw[15 + c];
-                }
-                Um[e] = v;
-                double dv = Cp[e];
-                dv += Tm[e];
-                dv += laser_own_reg(slb, cm_p, fa_p, r, c);
-                if (i - 1 == 0) dv += laser_ref_own(r, c);
-                dv = dv * ssc[r] * ssc[c];
-                if (r == c) dv = col_const(cm_p, r) ? 1.0 : dv + fmin(fmax(dv, opt.min_lm_diagonal), opt.max_lm_diagonal) * inv_radius;
-                Cp[e] = dv;
-            }
-            grp_sync<NT>();
-            gemm_ab15<NT>(Tm, Um, Dp, lane);                                   // T = U Dinv
-            if (ARROW && arrow_i) gemm_ab15<NT>(Tp, Wm, Dp, lane);             // T' = W Dinv
-            gemv15<NT, false, false>(piv, Dp, sb + 15 * i, lane);              // c_i = Dinv b_i
-            if (lane < 15) sb[15 * i + lane] = piv[lane];
-            grp_sync<NT>();
-            for (int e = lane; e < kBlk; e += NT) {
-                facw[(size_t)i * 3 * kBlk + e] = Tm[e];
-                if (ARROW) facw[(size_t)i * 3 * kBlk + kBlk + e] = arrow_i ? Tp[e] : 0.0;
-            }
-            gemv15<NT, false, true>(sb + 15 * (i - 1), Um, sb + 15 * i, lane);  // b_{i-1} -= U c_i
-            if (ARROW && arrow_i) gemv15<NT, false, true>(sb, Wm, sb + 15 * i, lane);
-            gemm_sub_abt15<NT>(Cp, Tm, Um, lane);                               // D_{i-1} -= T U^T
-            if (ARROW && arrow_i) {
-                if (!have_d0) { for (int e = lane; e < kBlk; e += NT) D0[e] = 0.0; grp_sync<NT>(); have_d0 = true; }
-                gemm_sub_abt15<NT>(D0, Tp, Wm, lane);                           // D_0 -= T' W^T
-                // fill-in for frame i-1: H(0, i-1) = -T' U^T   (Wm is free again after this; the old pivot block is scratch)
-                for (int e = lane; e < kBlk; e += NT) Dp[e] = 0.0;
-                grp_sync<NT>();
-                gemm_sub_abt15<NT>(Dp, Tp, Um, lane);
-                copy_blk<NT>(Wm, Dp, lane);
-                grp_sync<NT>();
-                have_wc = true;
-            } else if (ARROW) {
-                have_wc = false;
-            }
-            if (ARROW && i - 1 == 0 && have_d0) {
-                for (int e = lane; e < kBlk; e += NT) Cp[e] += D0[e];
-                grp_sync<NT>();
-            }
-            { double* t = Dp; Dp = Cp; Cp = t; }
-        }
-        if (ok) ok = grp_inverse15<NT>(Dp, piv, red, lane);
-        if (ok) {
-            gemv15<NT, false, false>(piv, Dp, sb, lane);   // y_0 = D0inv b_0
-            if (lane < 15) sb[lane] = piv[lane];
-            grp_sync<NT>();
-            // T_i (and T'_i) come back from global memory one frame ahead of their use (Tm / Um alternate)
-            auto fetch_T = [&](int i, double* dstT) {
-                for (int e = lane; e < kBlk; e += NT) cp_async8(dstT + e, facw + (size_t)i * 3 * kBlk + e);
-            };
-            if (n > 1) fetch_T(1, Tm);
-            for (int i = 1; i < n; ++i) {
-                double* Tc = (i & 1) ? Tm : Um;
-                if (ARROW && i >= 2) for (int e = lane; e < kBlk; e += NT) cp_async8(Tp + e, facw + (size_t)i * 3 * kBlk + kBlk + e);
-                cp_async_wait_all();
-                grp_sync<NT>();
-                if (i + 1 < n) fetch_T(i + 1, (i & 1) ? Um : Tm);
-                gemv15<NT, true, true>(sb + 15 * i, Tc, sb + 15 * (i - 1), lane);   // y_i = c_i - T^T y_{i-1} - T'^T y_0
-                if (ARROW && i >= 2) gemv15<NT, true, true>(sb + 15 * i, Tp, sb, lane);
-            }
+        // step = -y, model cost change; sets ok
+        auto step_and_model = [&]() {
             // step = -y ; model_cost_change = -1/2 step.gs + 1/2 sum lm_diag step^2
             double sg = 0.0, lq = 0.0;
             bool finite = true;
@@ -1227,6 +1250,221 @@ __device__ void window_step(const WindowArgs& a, int w, int lane, double* ws) {
             finite = grp_all<NT>(finite, red, lane);
             st.model_cost_change = -0.5 * sg + 0.5 * lq;
             ok = finite && st.model_cost_change > 0.0;
+                };
+        constexpr bool FAST = !ARROW && NT == 32;   // the batched shape: tile-form blocks, DMMA products, contiguous item loads
+        if constexpr (FAST) {
+            double* Dp = ws;
+            double* Cp = ws + kTB;
+            double* Ut = ws + 2 * kTB;
+            double* Tt = ws + 3 * kTB;
+            double* facf = a.fac + (size_t)w * n * kTB;
+            // element (r, c) this lane owns in pass q of a block: tile q >> 1, row 4 (q & 1) + (lane >> 3), column lane & 7
+            const int lr = lane >> 3, lc = lane & 7;
+            {   // D_{n-1}, scaled and damped
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    const int r = ((q >> 2) << 3) + ((q & 1) << 2) + lr, c = (((q >> 1) & 1) << 3) + lc;
+                    double v = 0.0;
+                    if (r < 15 && c < 15) {
+                        v = itm[(size_t)(n - 1) * kItem + item_hbb(r, c)] + laser_own(n - 1, r, c);
+                        v = v * scw[(n - 1) * 15 + r] * scw[(n - 1) * 15 + c];
+                        if (r == c) v = is_const(n - 1, r) ? 1.0 : v + fmin(fmax(v, opt.min_lm_diagonal), opt.max_lm_diagonal) * inv_radius;
+                    }
+                    Dp[(q << 5) + lane] = v;
+                }
+                __syncwarp();
+            }
+            for (int i = n - 1; i >= 1; --i) {
+                // raw blocks of this elimination step as contiguous 16-byte chunks, fetched while the pivot is inverted:
+                // Ut <- hab of item i (4 tiles), Tt / Cp slots t00 t01 t11 <- haa of item i / hbb of item i-1
+                {
+                    const double* it_i = itm + (size_t)i * kItem;
+                    const double* it_p = itm + (size_t)(i - 1) * kItem + kItemHbb;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) cp_async16(Ut + 2 * (lane + 32 * k), it_i + kItemHab + 2 * (lane + 32 * k));
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) {
+                        const int slot = (k == 2 ? 3 : k) << 6;
+                        cp_async16(Tt + slot + 2 * lane, it_i + (k << 6) + 2 * lane);
+                        cp_async16(Cp + slot + 2 * lane, it_p + (k << 6) + 2 * lane);
+                    }
+                    if (lane < NPAD) cp_async8(slb + lane, lb + (i - 1) * NPAD + lane);
+                    if (lane < 30) cp_async8(ssc + lane, scw + (i - 1) * 15 + lane);
+                }
+                const uint8_t cm_p = cm[i - 1];
+                const bool fa_p = fa[i - 1] != 0;
+                __syncwarp();
+                const bool inv_ok = spd_inverse15_t(Dp, piv, lane);
+                cp_async_wait_all();
+                __syncwarp();
+                if (!inv_ok) { ok = false; break; }
+                // U = S_{i-1} H(i-1, i) S_i;  D_{i-1} = S (hbb + haa + laser) S + damping.  Read everything, then write in place
+                // (the lower tile t10 of D is the transpose of t01).
+                double uv[8], dv[8];
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    const int r = ((q >> 2) << 3) + ((q & 1) << 2) + lr, c = (((q >> 1) & 1) << 3) + lc;
+                    const int e = (q << 5) + lane;
+                    const int src = (q >> 1) == 2 ? 64 + (lc << 3) + ((q & 1) << 2) + lr : e;
+                    const bool in = r < 15 && c < 15;
+                    const double sr = ssc[r < 15 ? r : 0], sci = ssc[15 + (c < 15 ? c : 0)], scp = ssc[c < 15 ? c : 0];
+                    uv[q] = in ? Ut[e] * sr * sci : 0.0;
+                    double d = Cp[src];
+                    d += Tt[src];
+                    if ((q >> 1) == 0) d += laser_own_reg(slb, cm_p, fa_p, r, c);
+                    d = d * sr * scp;
+                    if (((q >> 1) == 0 || (q >> 1) == 3) && r == c)
+                        d = col_const(cm_p, r) ? 1.0 : d + fmin(fmax(d, opt.min_lm_diagonal), opt.max_lm_diagonal) * inv_radius;
+                    dv[q] = in ? d : 0.0;
+                }
+                __syncwarp();
+#pragma unroll
+                for (int q = 0; q < 8; ++q) { Ut[(q << 5) + lane] = uv[q]; Cp[(q << 5) + lane] = dv[q]; }
+                __syncwarp();
+                gemm_ab_t(Tt, Ut, Dp, lane);                                        // T = U Dinv
+                gemv_t<false, false>(piv, Dp, sb + 15 * i, lane);                   // c_i = Dinv b_i
+                if (lane < 15) sb[15 * i + lane] = piv[lane];
+                __syncwarp();
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    *reinterpret_cast<double2*>(facf + (size_t)i * kTB + 2 * (lane + 32 * k)) = *reinterpret_cast<const double2*>(Tt + 2 * (lane + 32 * k));
+                gemv_t<false, true>(sb + 15 * (i - 1), Ut, sb + 15 * i, lane);      // b_{i-1} -= U c_i
+                gemm_sub_abt_t(Cp, Tt, Ut, lane);                                   // D_{i-1} -= T U^T
+                { double* tsw = Dp; Dp = Cp; Cp = tsw; }
+            }
+            if (ok) ok = spd_inverse15_t(Dp, piv, lane);
+            if (ok) {
+                gemv_t<false, false>(piv, Dp, sb, lane);   // y_0 = D0inv b_0
+                if (lane < 15) sb[lane] = piv[lane];
+                __syncwarp();
+                // T_i comes back from global memory one frame ahead of its use (Tt / Ut alternate)
+                auto fetch_T = [&](int i, double* dstT) {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) cp_async16(dstT + 2 * (lane + 32 * k), facf + (size_t)i * kTB + 2 * (lane + 32 * k));
+                };
+                if (n > 1) fetch_T(1, Tt);
+                for (int i = 1; i < n; ++i) {
+                    double* Tc = (i & 1) ? Tt : Ut;
+                    cp_async_wait_all();
+                    __syncwarp();
+                    if (i + 1 < n) fetch_T(i + 1, (i & 1) ? Ut : Tt);
+                    gemv_t<true, true>(sb + 15 * i, Tc, sb + 15 * (i - 1), lane);   // y_i = c_i - T^T y_{i-1}
+                }
+                step_and_model();
+            }
+        } else {
+        // Dm/Cy swap roles every frame (pivot block <-> block being assembled)
+            double* Dp = Dm;
+            double* Cp = Cy;
+            assemble_D(n - 1, Dp);
+            scale_damp(n - 1, Dp);
+            bool have_wc = false, have_d0 = false;
+            for (int i = n - 1; i >= 1; --i) {
+                // raw blocks of this elimination step, fetched asynchronously while the pivot is inverted:
+                // Um <- H(i-1, i) of item i, Cp <- hbb of item i-1, Tm <- haa of item i  (D_{i-1} = hbb + haa + laser)
+                {
+                    const double* it_i = itm + (size_t)i * kItem;
+                    const double* it_p = itm + (size_t)(i - 1) * kItem;
+                    for (int e = lane; e < kBlk; e += NT) {
+                        const uint32_t pk = otab[e];
+                        cp_async8(Um + e, it_i + (pk & 1023u));
+                        cp_async8(Cp + e, it_p + ((pk >> 10) & 1023u));
+                        cp_async8(Tm + e, it_i + (pk >> 20));
+                    }
+                    for (int e = lane; e < NPAD; e += NT) cp_async8(slb + e, lb + (i - 1) * NPAD + e);
+                    if (lane < 30) cp_async8(ssc + lane, scw + (i - 1) * 15 + lane);
+                }
+                // per-frame flags, requested now and consumed after the inverse
+                const uint8_t cm_p = mode == 1 ? 0 : cm[i - 1];
+                const bool fa_p = fa[i - 1] != 0;
+                const bool cross_i = has_cross(i);
+                bool arrow_i = false;
+                if (ARROW && i >= 2) {
+                    arrow_i = have_wc || cross_i;
+                    if (arrow_i)
+                        for (int e = lane; e < kBlk; e += NT) {
+                            const int r = e / 15, c = e - r * 15;
+                            double v = have_wc ? Wm[e] : 0.0;
+                            if (cross_i && r < 6 && c < 6 && !is_const(0, r) && !is_const(i, c)) v += cross_entry(i, r, c) * scw[r] * scw[i * 15 + c];
+                            Wm[e] = v;
+                        }
+                }
+                grp_sync<NT>();
+                const bool inv_ok = grp_inverse15<NT>(Dp, piv, red, lane);
+                cp_async_wait_all();
+                grp_sync<NT>();
+                if (!inv_ok) { ok = false; break; }
+                // coupling U = H(i-1, i), scaled (+ laser cross block / carried fill-in when i == 1: H(0,1) is also the arrow
+                // block); D_{i-1} assembled, scaled and damped
+                for (int e = lane; e < kBlk; e += NT) {
+                    const int r = e / 15, c = e - r * 15;
+                    double v = Um[e] * ssc[r] * ssc[15 + c];
+                    if (ARROW && i == 1) {
+                        if (have_wc) v += Wm[e];
+                        if (cross_i && r < 6 && c < 6 && !is_const(0, r) && !is_const(1, c)) v += cross_entry(1, r, c) * scw[r] * scw[15 + c];
+                    }
+                    Um[e] = v;
+                    double dv = Cp[e];
+                    dv += Tm[e];
+                    dv += laser_own_reg(slb, cm_p, fa_p, r, c);
+                    if (i - 1 == 0) dv += laser_ref_own(r, c);
+                    dv = dv * ssc[r] * ssc[c];
+                    if (r == c) dv = col_const(cm_p, r) ? 1.0 : dv + fmin(fmax(dv, opt.min_lm_diagonal), opt.max_lm_diagonal) * inv_radius;
+                    Cp[e] = dv;
+                }
+                grp_sync<NT>();
+                gemm_ab15<NT>(Tm, Um, Dp, lane);                                   // T = U Dinv
+                if (ARROW && arrow_i) gemm_ab15<NT>(Tp, Wm, Dp, lane);             // T' = W Dinv
+                gemv15<NT, false, false>(piv, Dp, sb + 15 * i, lane);              // c_i = Dinv b_i
+                if (lane < 15) sb[15 * i + lane] = piv[lane];
+                grp_sync<NT>();
+                for (int e = lane; e < kBlk; e += NT) {
+                    facw[(size_t)i * 3 * kBlk + e] = Tm[e];
+                    if (ARROW) facw[(size_t)i * 3 * kBlk + kBlk + e] = arrow_i ? Tp[e] : 0.0;
+                }
+                gemv15<NT, false, true>(sb + 15 * (i - 1), Um, sb + 15 * i, lane);  // b_{i-1} -= U c_i
+                if (ARROW && arrow_i) gemv15<NT, false, true>(sb, Wm, sb + 15 * i, lane);
+                gemm_sub_abt15<NT>(Cp, Tm, Um, lane);                               // D_{i-1} -= T U^T
+                if (ARROW && arrow_i) {
+                    if (!have_d0) { for (int e = lane; e < kBlk; e += NT) D0[e] = 0.0; grp_sync<NT>(); have_d0 = true; }
+                    gemm_sub_abt15<NT>(D0, Tp, Wm, lane);                           // D_0 -= T' W^T
+                    // fill-in for frame i-1: H(0, i-1) = -T' U^T   (Wm is free again after this; the old pivot block is scratch)
+                    for (int e = lane; e < kBlk; e += NT) Dp[e] = 0.0;
+                    grp_sync<NT>();
+                    gemm_sub_abt15<NT>(Dp, Tp, Um, lane);
+                    copy_blk<NT>(Wm, Dp, lane);
+                    grp_sync<NT>();
+                    have_wc = true;
+                } else if (ARROW) {
+                    have_wc = false;
+                }
+                if (ARROW && i - 1 == 0 && have_d0) {
+                    for (int e = lane; e < kBlk; e += NT) Cp[e] += D0[e];
+                    grp_sync<NT>();
+                }
+                { double* t = Dp; Dp = Cp; Cp = t; }
+            }
+            if (ok) ok = grp_inverse15<NT>(Dp, piv, red, lane);
+            if (ok) {
+                gemv15<NT, false, false>(piv, Dp, sb, lane);   // y_0 = D0inv b_0
+                if (lane < 15) sb[lane] = piv[lane];
+                grp_sync<NT>();
+                // T_i (and T'_i) come back from global memory one frame ahead of their use (Tm / Um alternate)
+                auto fetch_T = [&](int i, double* dstT) {
+                    for (int e = lane; e < kBlk; e += NT) cp_async8(dstT + e, facw + (size_t)i * 3 * kBlk + e);
+                };
+                if (n > 1) fetch_T(1, Tm);
+                for (int i = 1; i < n; ++i) {
+                    double* Tc = (i & 1) ? Tm : Um;
+                    if (ARROW && i >= 2) for (int e = lane; e < kBlk; e += NT) cp_async8(Tp + e, facw + (size_t)i * 3 * kBlk + kBlk + e);
+                    cp_async_wait_all();
+                    grp_sync<NT>();
+                    if (i + 1 < n) fetch_T(i + 1, (i & 1) ? Um : Tm);
+                    gemv15<NT, true, true>(sb + 15 * i, Tc, sb + 15 * (i - 1), lane);   // y_i = c_i - T^T y_{i-1} - T'^T y_0
+                    if (ARROW && i >= 2) gemv15<NT, true, true>(sb + 15 * i, Tp, sb, lane);
+                }
+                step_and_model();
+            }
         }
         grp_sync<NT>();
         if (ok) { have_step = true; st.num_invalid = 0; break; }
@@ -1260,16 +1498,19 @@ __device__ void window_step(const WindowArgs& a, int w, int lane, double* ws) {
 template <bool ARROW, int NT>
 __global__ void __launch_bounds__(NT == 32 ? 32 * LV_WINDOW_WPC : NT, NT == 32 ? 16 / LV_WINDOW_WPC : 512 / NT) window_kernel(WindowArgs a, int per_window_doubles) {
     extern __shared__ __align__(16) double smem[];
+    __shared__ uint32_t otab[kBlk];
+    window_offsets_init(otab, threadIdx.x, blockDim.x);
+    __syncthreads();
     if (NT == 32) {
-        // batched shape: one warp per window, two windows per CTA
+        // batched shape: one warp per window, LV_WINDOW_WPC windows per CTA
         const int lane = threadIdx.x & 31;
         const int warp = threadIdx.x >> 5;
         const int w = blockIdx.x * (blockDim.x >> 5) + warp;
         if (w >= a.n_windows) return;
-        window_step<ARROW, NT>(a, w, lane, smem + (size_t)warp * per_window_doubles);
+        window_step<ARROW, NT>(a, w, lane, smem + (size_t)warp * per_window_doubles, otab);
     } else {
         // small batches: one CTA of NT threads per window
-        window_step<ARROW, NT>(a, blockIdx.x, threadIdx.x, smem);
+        window_step<ARROW, NT>(a, blockIdx.x, threadIdx.x, smem, otab);
     }
 }
 
@@ -1286,6 +1527,9 @@ __global__ void __launch_bounds__(256, 1) solve_small_kernel(ScanMatchArgs sa, W
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int w = blockIdx.x;
     const int n = wa.n_frames;
+    __shared__ uint32_t otab[kBlk];
+    window_offsets_init(otab, tid, 256);
+    __syncthreads();
     for (int trip = 0; trip < trips; ++trip) {
         if (wa.win_status[w] != 0) break;                       // uniform: written before the last __syncthreads()
         if (sa.points)
@@ -1295,7 +1539,7 @@ __global__ void __launch_bounds__(256, 1) solve_small_kernel(ScanMatchArgs sa, W
         for (int k = 2 * warp; k < n; k += 16)
             factor_pair_item(wa, w * n + k, (k + 1 < n) ? 2 : 1, lane, smem + (size_t)warp * kPairSmem);
         __syncthreads();                                        // partials and items are complete (block-visible)
-        window_step<ARROW, 256>(wa, w, tid, smem);
+        window_step<ARROW, 256>(wa, w, tid, smem, otab);
         __syncthreads();
     }
 }
