@@ -255,7 +255,7 @@ int launch_factors(lvio2d_ctx* ctx, const WindowArgs& a) {
 }
 
 int launch_window(lvio2d_ctx* ctx, const WindowArgs& a) {
-    const int per_window = (int)window_smem_doubles(ctx->n, ctx->arrow);
+    int per_window = (int)window_smem_doubles(ctx->n, ctx->arrow);
     // thread group per window: one warp when the batch fills the machine, four warps when it fits 4 CTAs per SM,
     // eight warps when it fits 2 CTAs per SM — the same arithmetic spread four ways, for the latency of small batches
     // (LVIO2D_WINDOW_THREADS = 32 | 128 | 256 forces one of them; used by the tests to cover both)
@@ -270,6 +270,9 @@ int launch_window(lvio2d_ctx* ctx, const WindowArgs& a) {
     } while (0)
     if (nt == 32) {
         const int wpc = LV_WINDOW_WPC;
+        // the fast path (tracking topology, solver program) needs 8.6 KB per window; everything else the generic layout
+        const bool fast = !ctx->arrow && a.mode == 0 && !a.dense_H;
+        if (fast) per_window = kWindowFastSmem;
         const size_t smem = (size_t)wpc * per_window * sizeof(double);
         const int grid = (ctx->B + wpc - 1) / wpc;
         if (ctx->arrow) LAUNCH_WIN(true, 32, grid, wpc * 32, smem); else LAUNCH_WIN(false, 32, grid, wpc * 32, smem);
@@ -411,7 +414,7 @@ int setup_batch(lvio2d_ctx* ctx, const lvio2d_window_batch* b, bool bind, bool a
               ctx->b_ftab.ensure((size_t)F * kFrameTab * sizeof(double)) && ctx->b_reftab.ensure((size_t)F * kFrameTab * sizeof(double)) &&
               ctx->b_wlines.ensure(std::max<size_t>(1, (size_t)ctx->L) * sizeof(double4)) && ctx->b_wlen.ensure(std::max<size_t>(1, (size_t)ctx->L) * sizeof(double)) &&
               ctx->b_part.ensure((size_t)F * ctx->tiles * ctx->npad * sizeof(double)) && ctx->b_lb.ensure((size_t)2 * F * ctx->npad * sizeof(double)) &&
-              ctx->b_items.ensure((size_t)2 * F * kItem * sizeof(double)) && ctx->b_vec.ensure((size_t)B * 2 * n * 15 * sizeof(double)) &&
+              ctx->b_items.ensure((size_t)2 * F * kItem * sizeof(double)) && ctx->b_vec.ensure((size_t)B * 3 * n * 15 * sizeof(double)) &&
               ctx->b_fac.ensure((size_t)F * 3 * kBlk * sizeof(double)) && ctx->b_state.ensure(sizeof(LMState) * B) &&
               ctx->b_status.ensure(sizeof(int32_t) * B) && ctx->b_active.ensure(F) && ctx->b_active1.ensure(F) && ctx->b_reduce.ensure((size_t)F * ctx->npad * sizeof(double));
     if (!ok) return fail(ctx, LVIO2D_ERR_ALLOC, "cudaMalloc(work buffers)");

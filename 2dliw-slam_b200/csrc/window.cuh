@@ -46,6 +46,9 @@
 #ifndef LV_WINDOW_WPC
 #define LV_WINDOW_WPC 2    // windows (warps) per CTA of the one-warp-per-window shape
 #endif
+#ifndef LV_WINDOW_WARPS
+#define LV_WINDOW_WARPS 16 // resident warps per SM the register budget of the one-warp-per-window shape is sized for
+#endif
 #ifndef LV_PAIR_WPC
 #define LV_PAIR_WPC 4      // warps (item pairs) per CTA of factor_pair_kernel
 #endif
@@ -720,7 +723,9 @@ template <int NT> __device__ __forceinline__ void copy_blk(double* dst, const do
 }
 // per-warp shared memory of window_kernel (doubles): 4 blocks (+3 for the arrow topology) + pivot row + one frame's
 // laser block + rhs [n][15]
-__host__ __device__ inline size_t window_smem_doubles(int n, bool arrow) { return (arrow ? 7 * kBlk : 4 * 256) + 16 + 48 + 32 + 16 + (size_t)n * 15 + 16; }
+__host__ __device__ inline size_t window_smem_doubles(int n, bool arrow) { return (arrow ? 7 : 4) * kBlk + 16 + 48 + 32 + 16 + (size_t)n * 15 + 16; }
+// the fast path: Dp | Cp | Ut | Ha | piv | slb | ssc | rolling rhs
+constexpr int kWindowFastSmem = 3 * 256 + 192 + 16 + 32 + 32 + 48;
 
 // ---------------------------------------------------------------------------------------------------
 // =====================================================================================================
@@ -782,6 +787,7 @@ __device__ __forceinline__ void gemm_ab_t(double* Cm, const double* A, const dou
             bf[ks][m] = B[((((ks >> 1) << 1) + m) << 6) + ((((ks & 1) << 2) + t) << 3) + g];            // B[4ks + t][8m + g]
         }
     }
+    __syncwarp();   // C may alias A or B: every fragment is in registers before the first store
 #pragma unroll
     for (int mi = 0; mi < 2; ++mi)
 #pragma unroll
@@ -856,11 +862,15 @@ __device__ void window_step(const WindowArgs& a, int w, int lane, double* ws, co
     double* Wm = ws + 4 * kBlk;       // arrow block H(0, i)          (arrow topology only)
     double* Tp = ws + 5 * kBlk;       // T' = W Dinv
     double* D0 = ws + 6 * kBlk;       // accumulated updates of D_0
-    double* piv = ws + (ARROW ? 7 * kBlk : 4 * 256);  // 16
+    double* piv = ws + (ARROW ? 7 : 4) * kBlk;  // 16
     double* slb = piv + 16;           // laser block of the frame being assembled [NPAD]
     double* ssc = slb + 48;           // Jacobi scaling of frames i-1 and i [30]
     double* red = ssc + 32;           // cross-warp reduction scratch [16]
-    double* sb = red + 16;            // rhs / solution [n][15]
+    // the fast path (one warp per window, tracking topology, solver program) keeps the right-hand side in global memory
+    // and only a rolling two-frame window of it in shared memory: 8.6 KB per warp instead of 12.9
+    constexpr bool FASTC = !ARROW && NT == 32;
+    const bool fast = FASTC && mode == 0 && !a.dense_H;
+    double* sb = fast ? a.vec + ((size_t)w * 3 + 2) * n * 15 : red + 16;   // rhs / solution [n][15]
 
     double* x = a.x + (size_t)w * n * 15;
     double* xc = a.xc + (size_t)w * n * 15;
@@ -1160,7 +1170,7 @@ __device__ void window_step(const WindowArgs& a, int w, int lane, double* ws, co
     }
 
     // ---- gradient tolerance: |x - Plus(x, -g)|_inf (only after a successful step); gradient kept for the step
-    double* gvec = a.vec + (size_t)w * 2 * n * 15;
+    double* gvec = a.vec + (size_t)w * 3 * n * 15;
     double* dvec = gvec + n * 15;   // unscaled diagonal of H at the accepted point
     {
         double mx = 0.0;
@@ -1251,12 +1261,17 @@ __device__ void window_step(const WindowArgs& a, int w, int lane, double* ws, co
             st.model_cost_change = -0.5 * sg + 0.5 * lq;
             ok = finite && st.model_cost_change > 0.0;
                 };
-        constexpr bool FAST = !ARROW && NT == 32;   // the batched shape: tile-form blocks, DMMA products, contiguous item loads
-        if constexpr (FAST) {
+        if constexpr (FASTC) {
+            // shared memory of the fast path (doubles): Dp 256 | Cp 256 | Ut 256 | Ha 192 | piv 16 | slb 32 | ssc 32 | rhs 3 x 16
             double* Dp = ws;
             double* Cp = ws + kTB;
             double* Ut = ws + 2 * kTB;
-            double* Tt = ws + 3 * kTB;
+            double* Ha = ws + 3 * kTB;          // raw haa tiles of item i (slots t00 t01 t11), added into D_{i-1}
+            double* pivf = Ha + 192;
+            double* slbf = pivf + 16;
+            double* sscf = slbf + 32;
+            double* bcur = sscf + 32;           // b_i, later c_i / y_i  (rolling: the full right-hand side lives in global memory)
+            double* bprv = bcur + 16;           // b_{i-1}
             double* facf = a.fac + (size_t)w * n * kTB;
             // element (r, c) this lane owns in pass q of a block: tile q >> 1, row 4 (q & 1) + (lane >> 3), column lane & 7
             const int lr = lane >> 3, lc = lane & 7;
@@ -1272,11 +1287,12 @@ __device__ void window_step(const WindowArgs& a, int w, int lane, double* ws, co
                     }
                     Dp[(q << 5) + lane] = v;
                 }
+                if (lane < 16) bcur[lane] = lane < 15 ? sb[15 * (n - 1) + lane] : 0.0;
                 __syncwarp();
             }
             for (int i = n - 1; i >= 1; --i) {
                 // raw blocks of this elimination step as contiguous 16-byte chunks, fetched while the pivot is inverted:
-                // Ut <- hab of item i (4 tiles), Tt / Cp slots t00 t01 t11 <- haa of item i / hbb of item i-1
+                // Ut <- hab of item i (4 tiles), Ha / Cp slots t00 t01 t11 <- haa of item i / hbb of item i-1
                 {
                     const double* it_i = itm + (size_t)i * kItem;
                     const double* it_p = itm + (size_t)(i - 1) * kItem + kItemHbb;
@@ -1284,17 +1300,17 @@ __device__ void window_step(const WindowArgs& a, int w, int lane, double* ws, co
                     for (int k = 0; k < 4; ++k) cp_async16(Ut + 2 * (lane + 32 * k), it_i + kItemHab + 2 * (lane + 32 * k));
 #pragma unroll
                     for (int k = 0; k < 3; ++k) {
-                        const int slot = (k == 2 ? 3 : k) << 6;
-                        cp_async16(Tt + slot + 2 * lane, it_i + (k << 6) + 2 * lane);
-                        cp_async16(Cp + slot + 2 * lane, it_p + (k << 6) + 2 * lane);
+                        cp_async16(Ha + (k << 6) + 2 * lane, it_i + (k << 6) + 2 * lane);
+                        cp_async16(Cp + ((k == 2 ? 3 : k) << 6) + 2 * lane, it_p + (k << 6) + 2 * lane);
                     }
-                    if (lane < NPAD) cp_async8(slb + lane, lb + (i - 1) * NPAD + lane);
-                    if (lane < 30) cp_async8(ssc + lane, scw + (i - 1) * 15 + lane);
+                    if (lane < NPAD) cp_async8(slbf + lane, lb + (i - 1) * NPAD + lane);
+                    if (lane < 30) cp_async8(sscf + lane, scw + (i - 1) * 15 + lane);
+                    if (lane < 15) cp_async8(bprv + lane, sb + 15 * (i - 1) + lane);
                 }
                 const uint8_t cm_p = cm[i - 1];
                 const bool fa_p = fa[i - 1] != 0;
                 __syncwarp();
-                const bool inv_ok = spd_inverse15_t(Dp, piv, lane);
+                const bool inv_ok = spd_inverse15_t(Dp, pivf, lane);
                 cp_async_wait_all();
                 __syncwarp();
                 if (!inv_ok) { ok = false; break; }
@@ -1303,17 +1319,19 @@ __device__ void window_step(const WindowArgs& a, int w, int lane, double* ws, co
                 double uv[8], dv[8];
 #pragma unroll
                 for (int q = 0; q < 8; ++q) {
-                    const int r = ((q >> 2) << 3) + ((q & 1) << 2) + lr, c = (((q >> 1) & 1) << 3) + lc;
+                    const int tile = q >> 1;
+                    const int r = ((q >> 2) << 3) + ((q & 1) << 2) + lr, c = ((tile & 1) << 3) + lc;
                     const int e = (q << 5) + lane;
-                    const int src = (q >> 1) == 2 ? 64 + (lc << 3) + ((q & 1) << 2) + lr : e;
+                    const int win = ((q & 1) << 5) + lane;                                   // offset inside the tile
+                    const int wtr = (lc << 3) + ((q & 1) << 2) + lr;                         // ... of the transposed entry
                     const bool in = r < 15 && c < 15;
-                    const double sr = ssc[r < 15 ? r : 0], sci = ssc[15 + (c < 15 ? c : 0)], scp = ssc[c < 15 ? c : 0];
+                    const double sr = sscf[r < 15 ? r : 0], sci = sscf[15 + (c < 15 ? c : 0)], scp = sscf[c < 15 ? c : 0];
                     uv[q] = in ? Ut[e] * sr * sci : 0.0;
-                    double d = Cp[src];
-                    d += Tt[src];
-                    if ((q >> 1) == 0) d += laser_own_reg(slb, cm_p, fa_p, r, c);
+                    double d = tile == 2 ? Cp[64 + wtr] : Cp[e];
+                    d += tile == 0 ? Ha[win] : (tile == 3 ? Ha[128 + win] : (tile == 1 ? Ha[64 + win] : Ha[64 + wtr]));
+                    if (tile == 0) d += laser_own_reg(slbf, cm_p, fa_p, r, c);
                     d = d * sr * scp;
-                    if (((q >> 1) == 0 || (q >> 1) == 3) && r == c)
+                    if ((tile == 0 || tile == 3) && r == c)
                         d = col_const(cm_p, r) ? 1.0 : d + fmin(fmax(d, opt.min_lm_diagonal), opt.max_lm_diagonal) * inv_radius;
                     dv[q] = in ? d : 0.0;
                 }
@@ -1321,34 +1339,41 @@ __device__ void window_step(const WindowArgs& a, int w, int lane, double* ws, co
 #pragma unroll
                 for (int q = 0; q < 8; ++q) { Ut[(q << 5) + lane] = uv[q]; Cp[(q << 5) + lane] = dv[q]; }
                 __syncwarp();
-                gemm_ab_t(Tt, Ut, Dp, lane);                                        // T = U Dinv
-                gemv_t<false, false>(piv, Dp, sb + 15 * i, lane);                   // c_i = Dinv b_i
-                if (lane < 15) sb[15 * i + lane] = piv[lane];
-                __syncwarp();
+                gemv_t<false, false>(pivf, Dp, bcur, lane);                         // c_i = Dinv b_i
+                if (lane < 15) { const double ci = pivf[lane]; bcur[lane] = ci; sb[15 * i + lane] = ci; }
+                gemm_ab_t(Dp, Ut, Dp, lane);                                        // T = U Dinv, over Dinv (loads, barrier, stores)
 #pragma unroll
                 for (int k = 0; k < 4; ++k)
-                    *reinterpret_cast<double2*>(facf + (size_t)i * kTB + 2 * (lane + 32 * k)) = *reinterpret_cast<const double2*>(Tt + 2 * (lane + 32 * k));
-                gemv_t<false, true>(sb + 15 * (i - 1), Ut, sb + 15 * i, lane);      // b_{i-1} -= U c_i
-                gemm_sub_abt_t(Cp, Tt, Ut, lane);                                   // D_{i-1} -= T U^T
+                    *reinterpret_cast<double2*>(facf + (size_t)i * kTB + 2 * (lane + 32 * k)) = *reinterpret_cast<const double2*>(Dp + 2 * (lane + 32 * k));
+                gemv_t<false, true>(bprv, Ut, bcur, lane);                          // b_{i-1} -= U c_i
+                gemm_sub_abt_t(Cp, Dp, Ut, lane);                                   // D_{i-1} -= T U^T
                 { double* tsw = Dp; Dp = Cp; Cp = tsw; }
+                { double* tsw = bcur; bcur = bprv; bprv = tsw; }
             }
-            if (ok) ok = spd_inverse15_t(Dp, piv, lane);
+            if (ok) ok = spd_inverse15_t(Dp, pivf, lane);
             if (ok) {
-                gemv_t<false, false>(piv, Dp, sb, lane);   // y_0 = D0inv b_0
-                if (lane < 15) sb[lane] = piv[lane];
+                gemv_t<false, false>(pivf, Dp, bcur, lane);   // y_0 = D0inv b_0
+                if (lane < 15) { const double y = pivf[lane]; bcur[lane] = y; sb[lane] = y; }
                 __syncwarp();
-                // T_i comes back from global memory one frame ahead of its use (Tt / Ut alternate)
-                auto fetch_T = [&](int i, double* dstT) {
+                // T_i and c_i come back from global memory one frame ahead of their use (Ut / Cp alternate)
+                auto fetch_T = [&](int i, double* dstT, double* dstc) {
 #pragma unroll
                     for (int k = 0; k < 4; ++k) cp_async16(dstT + 2 * (lane + 32 * k), facf + (size_t)i * kTB + 2 * (lane + 32 * k));
+                    if (lane < 15) cp_async8(dstc + lane, sb + 15 * i + lane);
                 };
-                if (n > 1) fetch_T(1, Tt);
+                double* ycur = bcur;                          // y_{i-1}
+                double* cA = bprv;                            // c_i buffers alternate with the T buffers
+                double* cB = pivf;
+                if (n > 1) fetch_T(1, Ut, cA);
                 for (int i = 1; i < n; ++i) {
-                    double* Tc = (i & 1) ? Tt : Ut;
+                    double* Tc = (i & 1) ? Ut : Cp;
+                    double* cc = (i & 1) ? cA : cB;
                     cp_async_wait_all();
                     __syncwarp();
-                    if (i + 1 < n) fetch_T(i + 1, (i & 1) ? Ut : Tt);
-                    gemv_t<true, true>(sb + 15 * i, Tc, sb + 15 * (i - 1), lane);   // y_i = c_i - T^T y_{i-1}
+                    if (i + 1 < n) fetch_T(i + 1, (i & 1) ? Cp : Ut, (i & 1) ? cB : cA);
+                    gemv_t<true, true>(cc, Tc, ycur, lane);   // y_i = c_i - T^T y_{i-1}
+                    if (lane < 15) { const double y = cc[lane]; ycur[lane] = y; sb[15 * i + lane] = y; }
+                    __syncwarp();
                 }
                 step_and_model();
             }
@@ -1496,11 +1521,14 @@ __device__ void window_step(const WindowArgs& a, int w, int lane, double* ws, co
 }
 
 template <bool ARROW, int NT>
-__global__ void __launch_bounds__(NT == 32 ? 32 * LV_WINDOW_WPC : NT, NT == 32 ? 16 / LV_WINDOW_WPC : 512 / NT) window_kernel(WindowArgs a, int per_window_doubles) {
+__global__ void __launch_bounds__(NT == 32 ? 32 * LV_WINDOW_WPC : NT, NT == 32 ? LV_WINDOW_WARPS / LV_WINDOW_WPC : 512 / NT) window_kernel(WindowArgs a, int per_window_doubles) {
     extern __shared__ __align__(16) double smem[];
-    __shared__ uint32_t otab[kBlk];
-    window_offsets_init(otab, threadIdx.x, blockDim.x);
-    __syncthreads();
+    constexpr bool FASTC = !ARROW && NT == 32;   // this instantiation never runs the generic elimination loop
+    __shared__ uint32_t otab[FASTC ? 1 : kBlk];
+    if (!FASTC) {
+        window_offsets_init(otab, threadIdx.x, blockDim.x);
+        __syncthreads();
+    }
     if (NT == 32) {
         // batched shape: one warp per window, LV_WINDOW_WPC windows per CTA
         const int lane = threadIdx.x & 31;

@@ -13,7 +13,7 @@ import tempfile
 
 rep, kname = sys.argv[1], sys.argv[2]
 top = int(sys.argv[3]) if len(sys.argv) > 3 else 30
-lib = sys.argv[4] if len(sys.argv) > 4 else os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "2dliw-slam_b200", "csrc", "liblvio2d.so")
+lib = os.path.abspath(sys.argv[4]) if len(sys.argv) > 4 else os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "2dliw-slam_b200", "csrc", "liblvio2d.so")
 tmp = tempfile.mkdtemp()
 subprocess.run(["cuobjdump", "-xelf", "all", lib], cwd=tmp, check=True, stdout=subprocess.DEVNULL)
 cubin = [os.path.join(tmp, f) for f in os.listdir(tmp) if f.endswith(".cubin")][0]
@@ -54,7 +54,7 @@ print("  samples%  inst%   file:line   source")
 for key, c in samp.most_common(top):
     f, l = key
     text = ""
-    p = os.path.join(os.path.dirname(lib), f)
+    p = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "2dliw-slam_b200", "csrc", f)
     if os.path.exists(p):
         if p not in src:
             src[p] = open(p).read().splitlines()
