@@ -119,6 +119,79 @@ class WindowBatch(C.Structure):
     ]
 
 
+IMU_COMPACT = 190
+
+
+class ScanWireStruct(C.Structure):
+    """lvio2d_scan_wire (include/lvio2d.h)."""
+
+    _fields_ = [("n_beams", C.c_int32), ("ranges", C.POINTER(C.c_float)), ("angle", C.POINTER(C.c_float)), ("beam_line", C.POINTER(C.c_uint16)),
+                ("imu_compact", c_double_p)]
+
+
+class ScanWire:
+    """Compact wire encoding of a beam-mode batch's laser input: float32 ranges [F][n_beams], float32 (angle_min,
+    angle_increment) [F][2], uint16 line index per beam [F][n_beams] (0xFFFF = none).  `points()` is the host statement
+    of what the device rebuilds (convert::laser_to_point_times without the 1 cm thinning, src/utilies/common.cpp:6-24)."""
+
+    NONE = 0xFFFF
+
+    def __init__(self, ranges, angle, beam_line, imu_compact=None):
+        self.imu_compact = None if imu_compact is None else np.ascontiguousarray(imu_compact, dtype=np.float64).reshape(-1, IMU_COMPACT)
+        self.ranges = np.ascontiguousarray(ranges, dtype=np.float32)
+        self.angle = np.ascontiguousarray(angle, dtype=np.float32).reshape(-1, 2)
+        self.beam_line = np.ascontiguousarray(beam_line, dtype=np.uint16)
+        assert self.ranges.ndim == 2 and self.beam_line.shape == self.ranges.shape and len(self.angle) == len(self.ranges)
+        self.n_beams = int(self.ranges.shape[1])
+
+    def struct(self):
+        s = ScanWireStruct()
+        s.n_beams = self.n_beams
+        s.ranges = self.ranges.ctypes.data_as(C.POINTER(C.c_float))
+        s.angle = self.angle.ctypes.data_as(C.POINTER(C.c_float))
+        s.beam_line = self.beam_line.ctypes.data_as(C.POINTER(C.c_uint16))
+        s.imu_compact = ptr(self.imu_compact, c_double_p)
+        return s
+
+    def nbytes(self):
+        return self.ranges.nbytes + self.angle.nbytes + self.beam_line.nbytes + (0 if self.imu_compact is None else self.imu_compact.nbytes)
+
+    @staticmethod
+    def compact_imu(blobs):
+        """[k][466] imu_preint_result blobs -> [k][190]: the entries imu_factor::operator() reads (imu_factor.h:52-86)."""
+        b = np.asarray(blobs, dtype=np.float64).reshape(-1, IMU_BLOB)
+        J = b[:, 15:240].reshape(-1, 15, 15)
+        S = b[:, 240:465].reshape(-1, 15, 15)
+        iu = np.triu_indices(15)
+        return np.ascontiguousarray(np.concatenate([b[:, 0:15], J[:, 0:9, 9:15].reshape(len(b), 54), S[:, iu[0], iu[1]], b[:, 465:466]], axis=1))
+
+    def points(self):
+        """-> points [F * n_beams][2] float64, point_line [F * n_beams] int32 (-1 = no part), point_offset [F + 1]"""
+        k = np.arange(self.n_beams, dtype=np.float32)[None, :]
+        ang = (self.angle[:, 0:1] + k * self.angle[:, 1:2]).astype(np.float32)      # float32 products and sums, rounded each
+        a64, r = ang.astype(np.float64), self.ranges.astype(np.float64)
+        valid = np.isfinite(self.ranges) & (r > 0.1)
+        pts = np.stack([np.cos(a64) * r, np.sin(a64) * r], axis=-1)
+        pts[~valid] = 0.0
+        line = np.where(valid & (self.beam_line != self.NONE), self.beam_line.astype(np.int32), -1).astype(np.int32)
+        off = np.arange(len(self.ranges) + 1, dtype=np.int64) * self.n_beams
+        return pts.reshape(-1, 2), line.reshape(-1), off
+
+    @classmethod
+    def from_points(cls, hb, n_beams, angle_min, angle_increment):
+        """Wire form of a HostBatch whose frames hold exactly one point per beam, in beam order: the range is |p|, the
+        direction snaps to the float32 beam grid (synthetic data: nothing is lost but sub-float32 digits)."""
+        pts = hb["points"].reshape(-1, n_beams, 2)
+        F = len(pts)
+        assert F == hb.n_windows * hb.n_frames and np.array_equal(np.diff(hb["point_offset"]), np.full(F, n_beams))
+        rng = np.hypot(pts[..., 0], pts[..., 1]).astype(np.float32)
+        pl = hb["point_line"].reshape(F, n_beams)
+        assert pl.max() < cls.NONE
+        bl = np.where(pl < 0, cls.NONE, pl).astype(np.uint16)
+        ang = np.tile(np.array([[angle_min, angle_increment]], dtype=np.float32), (F, 1))
+        return cls(rng, ang, bl)
+
+
 class Summary(C.Structure):
     """lvio2d_summary (include/lvio2d.h)."""
 

@@ -322,4 +322,40 @@ __global__ void reduce_tiles_kernel(const double* partial, const uint8_t* frame_
     out[idx] = s;
 }
 
+// lvio2d_set_windows_wire: beam k of frame f -> point slot f * n_beams + k, exactly as convert::laser_to_point_times
+// builds it (reference src/utilies/common.cpp:6-24: float32 angle_min + k * angle_increment with two roundings, the
+// cosine / sine in double, times the float32 range) minus its 1 cm thinning, which has no meaning when every beam
+// carries its own line index: a beam the reference would reject (NaN, inf, <= 0.1 m) or that has no line gets -1.
+__global__ void expand_wire_kernel(const float* __restrict__ ranges, const float* __restrict__ angle, const uint16_t* __restrict__ beam_line,
+                                   int n_beams, int64_t total, double2* __restrict__ points, int32_t* __restrict__ point_line) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int64_t f = i / n_beams;
+    const int k = (int)(i - f * n_beams);
+    const float r = ranges[i];
+    const float ang = __fadd_rn(angle[2 * f], __fmul_rn((float)k, angle[2 * f + 1]));
+    double sn, cs;
+    sincos((double)ang, &sn, &cs);
+    const bool valid = !isnan(r) && !isinf(r) && (double)r > 0.1;
+    points[i] = valid ? make_double2(cs * (double)r, sn * (double)r) : make_double2(0.0, 0.0);
+    const uint16_t l = beam_line[i];
+    point_line[i] = (valid && l != 0xFFFFu) ? (int32_t)l : -1;
+}
+
+// lvio2d_scan_wire::imu_compact -> the ABI blob layout the factor kernels read (entries imu_factor never reads stay zero)
+__global__ void expand_imu_compact_kernel(const double* __restrict__ compact, double* __restrict__ blobs, int n_blobs) {
+    const int b = blockIdx.x;
+    if (b >= n_blobs) return;
+    const double* c = compact + (size_t)b * 190;
+    double* o = blobs + (size_t)b * 466;
+    for (int k = threadIdx.x; k < 466; k += blockDim.x) {
+        double v = 0.0;
+        if (k < 15) v = c[k];
+        else if (k < 240) { const int r = (k - 15) / 15, q = (k - 15) % 15; if (r < 9 && q >= 9) v = c[15 + r * 6 + (q - 9)]; }
+        else if (k < 465) { const int r = (k - 240) / 15, q = (k - 240) % 15; if (q >= r) v = c[69 + r * 15 - (r * (r - 1)) / 2 + (q - r)]; }
+        else v = c[189];
+        o[k] = v;
+    }
+}
+
 }  // namespace lv

@@ -79,7 +79,7 @@ struct lvio2d_ctx {
     int uniform_pts = 0, uniform_lines = 0;   // > 0: all frames have this many points / lines (scan-match fast prologue)
     int shard_rank = 0, shard_world = 1;
     // inputs (owned copies, or borrowed device pointers when bound)
-    DevBuf b_points, b_pline, b_pweight, b_poff, b_loff, b_lines, b_ref, b_refpose, b_imu, b_wheel, b_pX0, b_pJ, b_pH, b_cmask;
+    DevBuf b_points, b_pline, b_pweight, b_poff, b_loff, b_lines, b_ref, b_refpose, b_imu, b_wheel, b_pX0, b_pJ, b_pH, b_cmask, b_wr, b_wa, b_wl, b_wi;
     const double2* points = nullptr; const int32_t* point_line = nullptr; const double* point_weight = nullptr;
     const int64_t* point_offset = nullptr; const int64_t* line_offset = nullptr; const double4* lines = nullptr;
     const int32_t* ref_frame = nullptr; const double* ref_pose = nullptr; const double* imu = nullptr; const double* wheel = nullptr;
@@ -306,7 +306,7 @@ int begin_solve(lvio2d_ctx* ctx, bool from_solution = false) {
     return LVIO2D_OK;
 }
 
-int setup_batch(lvio2d_ctx* ctx, const lvio2d_window_batch* b, bool bind, bool async = false) {
+int setup_batch(lvio2d_ctx* ctx, const lvio2d_window_batch* b, bool bind, bool async = false, const lvio2d_scan_wire* wire = nullptr) {
     if (!ctx || !b) return LVIO2D_ERR_INVALID_ARG;
     if (b->n_windows < 1 || b->n_frames < 1 || !b->states) return fail(ctx, LVIO2D_ERR_INVALID_ARG, "n_windows/n_frames/states");
     if (b->n_frames > 64) return fail(ctx, LVIO2D_ERR_DOMAIN, "n_frames > 64");
@@ -317,7 +317,7 @@ int setup_batch(lvio2d_ctx* ctx, const lvio2d_window_batch* b, bool bind, bool a
     ctx->ground_mult = b->ground_multiplicity;
     ctx->prior_frame = (b->prior_frame >= 0 && b->prior_X0 && b->prior_J) ? b->prior_frame : -1;
     if (ctx->prior_frame >= n) return fail(ctx, LVIO2D_ERR_INVALID_ARG, "prior_frame >= n_frames");
-    ctx->has_imu = b->imu != nullptr && n > 1;
+    ctx->has_imu = (b->imu != nullptr || (wire && wire->imu_compact)) && n > 1;
     ctx->has_wheel = b->wheel != nullptr && n > 1;
     ctx->has_weight = b->point_weight != nullptr;
 
@@ -330,7 +330,8 @@ int setup_batch(lvio2d_ctx* ctx, const lvio2d_window_batch* b, bool bind, bool a
     PinnedVec<uint8_t>&active = ctx->h_active, &active1 = ctx->h_active1;
     if (!poff.assign(F + 1, 0) || !loff.assign(F + 1, 0) || !rf.assign(F, -1) || !cm.assign(F, 0) || !active.assign(F, 0) || !active1.assign(F, 0))
         return fail(ctx, LVIO2D_ERR_ALLOC, "cudaHostAlloc(staging)");
-    const bool has_laser = b->point_offset && b->points && b->point_line && b->line_offset && b->lines;
+    if (wire && (bind || wire->n_beams < 1 || !wire->ranges || !wire->angle || !wire->beam_line)) return fail(ctx, LVIO2D_ERR_INVALID_ARG, "scan wire: host arrays ranges / angle / beam_line");
+    const bool has_laser = wire ? (b->line_offset && b->lines) : (b->point_offset && b->points && b->point_line && b->line_offset && b->lines);
     if (bind) {
         if (has_laser) {
             CK(cudaMemcpy(poff.data(), b->point_offset, sizeof(int64_t) * (F + 1), cudaMemcpyDeviceToHost));
@@ -340,7 +341,8 @@ int setup_batch(lvio2d_ctx* ctx, const lvio2d_window_batch* b, bool bind, bool a
         if (b->const_mask) CK(cudaMemcpy(cm.data(), b->const_mask, F, cudaMemcpyDeviceToHost));
     } else {
         if (has_laser) {
-            std::memcpy(poff.data(), b->point_offset, sizeof(int64_t) * (F + 1));
+            if (wire) for (int f = 0; f <= F; ++f) poff[f] = (int64_t)f * wire->n_beams;   // every beam is a point slot
+            else std::memcpy(poff.data(), b->point_offset, sizeof(int64_t) * (F + 1));
             std::memcpy(loff.data(), b->line_offset, sizeof(int64_t) * (F + 1));
             if (b->ref_frame) std::memcpy(rf.data(), b->ref_frame, sizeof(int32_t) * F);
         }
@@ -395,16 +397,41 @@ int setup_batch(lvio2d_ctx* ctx, const lvio2d_window_batch* b, bool bind, bool a
     if (window_smem_bytes(ctx) > 200 * 1024) return fail(ctx, LVIO2D_ERR_DOMAIN, "n_frames too large for shared memory");
 
     int rc;
-    if ((rc = take<double2>(ctx, bind, ctx->b_points, ctx->points, has_laser ? b->points : nullptr, (size_t)ctx->N))) return rc;
-    if ((rc = take<int32_t>(ctx, bind, ctx->b_pline, ctx->point_line, has_laser ? b->point_line : nullptr, (size_t)ctx->N))) return rc;
-    if ((rc = take<double>(ctx, bind, ctx->b_pweight, ctx->point_weight, has_laser ? b->point_weight : nullptr, (size_t)ctx->N))) return rc;
+    if (wire && has_laser) {
+        // compact wire encoding (lvio2d_set_windows_wire): float32 ranges + uint16 line indices travel, the double points
+        // and int32 indices the scan-match kernel streams are rebuilt on the device
+        const size_t N = (size_t)ctx->N;
+        const float* d_r; const float* d_a; const uint16_t* d_l;
+        if ((rc = take<float>(ctx, false, ctx->b_wr, d_r, wire->ranges, N))) return rc;
+        if ((rc = take<float>(ctx, false, ctx->b_wa, d_a, wire->angle, (size_t)F * 2))) return rc;
+        if ((rc = take<uint16_t>(ctx, false, ctx->b_wl, d_l, wire->beam_line, N))) return rc;
+        if (!ctx->b_points.ensure(N * sizeof(double2)) || !ctx->b_pline.ensure(N * sizeof(int32_t))) return fail(ctx, LVIO2D_ERR_ALLOC, "cudaMalloc(points)");
+        expand_wire_kernel<<<(unsigned)((N + 255) / 256), 256, 0, ctx->stream>>>(d_r, d_a, d_l, wire->n_beams, (int64_t)N, ctx->b_points.as<double2>(), ctx->b_pline.as<int32_t>());
+        CK(cudaGetLastError());
+        ctx->launches += 1;
+        ctx->points = ctx->b_points.as<double2>(); ctx->point_line = ctx->b_pline.as<int32_t>(); ctx->point_weight = nullptr;
+        ctx->has_weight = false;
+    } else {
+        if ((rc = take<double2>(ctx, bind, ctx->b_points, ctx->points, has_laser ? b->points : nullptr, (size_t)ctx->N))) return rc;
+        if ((rc = take<int32_t>(ctx, bind, ctx->b_pline, ctx->point_line, has_laser ? b->point_line : nullptr, (size_t)ctx->N))) return rc;
+        if ((rc = take<double>(ctx, bind, ctx->b_pweight, ctx->point_weight, has_laser ? b->point_weight : nullptr, (size_t)ctx->N))) return rc;
+    }
     if ((rc = take<int64_t>(ctx, false, ctx->b_poff, ctx->point_offset, poff.data(), (size_t)F + 1))) return rc;
     if ((rc = take<int64_t>(ctx, false, ctx->b_loff, ctx->line_offset, loff.data(), (size_t)F + 1))) return rc;
     if ((rc = take<double4>(ctx, bind, ctx->b_lines, ctx->lines, has_laser ? b->lines : nullptr, (size_t)ctx->L))) return rc;
     if ((rc = take<int32_t>(ctx, false, ctx->b_ref, ctx->ref_frame, rf.data(), (size_t)F))) return rc;
     if ((rc = take<uint8_t>(ctx, false, ctx->b_cmask, ctx->const_mask, cm.data(), (size_t)F))) return rc;
     if ((rc = take<double>(ctx, bind, ctx->b_refpose, ctx->ref_pose, has_laser ? b->ref_pose : nullptr, (size_t)F * 6))) return rc;
-    if ((rc = take<double>(ctx, bind, ctx->b_imu, ctx->imu, ctx->has_imu ? b->imu : nullptr, (size_t)B * (n - 1) * LVIO2D_IMU_BLOB))) return rc;
+    if (wire && wire->imu_compact && ctx->has_imu) {
+        const size_t nb = (size_t)B * (n - 1);
+        const double* d_c;
+        if ((rc = take<double>(ctx, false, ctx->b_wi, d_c, wire->imu_compact, nb * LVIO2D_IMU_COMPACT))) return rc;
+        if (!ctx->b_imu.ensure(nb * LVIO2D_IMU_BLOB * sizeof(double))) return fail(ctx, LVIO2D_ERR_ALLOC, "cudaMalloc(imu)");
+        expand_imu_compact_kernel<<<(unsigned)nb, 128, 0, ctx->stream>>>(d_c, ctx->b_imu.as<double>(), (int)nb);
+        CK(cudaGetLastError());
+        ctx->launches += 1;
+        ctx->imu = ctx->b_imu.as<double>();
+    } else if ((rc = take<double>(ctx, bind, ctx->b_imu, ctx->imu, ctx->has_imu ? b->imu : nullptr, (size_t)B * (n - 1) * LVIO2D_IMU_BLOB))) return rc;
     if ((rc = take<double>(ctx, bind, ctx->b_wheel, ctx->wheel, ctx->has_wheel ? b->wheel : nullptr, (size_t)B * (n - 1) * LVIO2D_WHEEL_BLOB))) return rc;
     if ((rc = take<double>(ctx, bind, ctx->b_pX0, ctx->prior_X0, ctx->prior_frame >= 0 ? b->prior_X0 : nullptr, (size_t)B * 15))) return rc;
     if ((rc = take<double>(ctx, bind, ctx->b_pJ, ctx->prior_J, ctx->prior_frame >= 0 ? b->prior_J : nullptr, (size_t)B * 225))) return rc;
@@ -512,7 +539,7 @@ void lvio2d_destroy(lvio2d_ctx* ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     DevBuf* all[] = {&ctx->b_points, &ctx->b_pline, &ctx->b_pweight, &ctx->b_poff, &ctx->b_loff, &ctx->b_lines, &ctx->b_ref, &ctx->b_refpose,
-                     &ctx->b_imu, &ctx->b_wheel, &ctx->b_pX0, &ctx->b_pJ, &ctx->b_pH, &ctx->b_cmask, &ctx->b_x0, &ctx->b_x, &ctx->b_xc, &ctx->b_scale,
+                     &ctx->b_imu, &ctx->b_wheel, &ctx->b_pX0, &ctx->b_pJ, &ctx->b_pH, &ctx->b_cmask, &ctx->b_wr, &ctx->b_wa, &ctx->b_wl, &ctx->b_wi, &ctx->b_x0, &ctx->b_x, &ctx->b_xc, &ctx->b_scale,
                      &ctx->b_ftab, &ctx->b_reftab, &ctx->b_wlines, &ctx->b_wlen, &ctx->b_part, &ctx->b_lb, &ctx->b_items, &ctx->b_vec, &ctx->b_fac, &ctx->b_state,
                      &ctx->b_status, &ctx->b_active, &ctx->b_active1, &ctx->b_reduce};
     for (DevBuf* b : all) b->release();
@@ -535,6 +562,10 @@ void* lvio2d_stream(lvio2d_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr
 int lvio2d_set_windows(lvio2d_ctx* ctx, const lvio2d_window_batch* host_batch) { return setup_batch(ctx, host_batch, false); }
 int lvio2d_bind_windows(lvio2d_ctx* ctx, const lvio2d_window_batch* device_batch) { return setup_batch(ctx, device_batch, true); }
 int lvio2d_set_windows_async(lvio2d_ctx* ctx, const lvio2d_window_batch* host_batch) { return setup_batch(ctx, host_batch, false, true); }
+int lvio2d_set_windows_wire(lvio2d_ctx* ctx, const lvio2d_window_batch* host_batch, const lvio2d_scan_wire* wire, int32_t async) {
+    if (!wire) return LVIO2D_ERR_INVALID_ARG;
+    return setup_batch(ctx, host_batch, false, async != 0, wire);
+}
 
 int lvio2d_set_max_iterations(lvio2d_ctx* ctx, int32_t max_iters) {
     if (!ctx) return LVIO2D_ERR_INVALID_ARG;

@@ -31,7 +31,7 @@ EXPORTS = [
     "lvio2d_wheel_preintegrate", "lvio2d_eval_laser_factor", "lvio2d_eval_imu_factor", "lvio2d_eval_wheel_factor",
     "lvio2d_eval_ground_factors", "lvio2d_set_profiling", "lvio2d_get_profile", "lvio2d_set_windows_async", "lvio2d_get_states_async",
     "lvio2d_extract_lines", "lvio2d_scan_to_points", "lvio2d_match_lines", "lvio2d_pose_graph_solve", "lvio2d_eval_edge_factor",
-    "lvio2d_measure_fp64_peak", "lvio2d_set_max_iterations",
+    "lvio2d_measure_fp64_peak", "lvio2d_set_max_iterations", "lvio2d_set_windows_wire",
 ]
 
 
@@ -94,6 +94,7 @@ def load_library(path=LIB_PATH):
     lib.lvio2d_get_profile.argtypes = [vp, dp]
     lib.lvio2d_measure_fp64_peak.argtypes = [vp, dp]
     lib.lvio2d_set_max_iterations.argtypes = [vp, C.c_int32]
+    lib.lvio2d_set_windows_wire.argtypes = [vp, C.POINTER(abi.WindowBatch), C.POINTER(abi.ScanWireStruct), C.c_int32]
     lib.lvio2d_pose_graph_solve.argtypes = [vp, C.c_int32, dp, C.c_int32, abi.c_int32_p, dp, dp, dp, C.c_int32, C.c_int32, vp]
     lib.lvio2d_eval_edge_factor.argtypes = [vp, dp, C.c_double, dp, dp, dp, dp, dp]
     _lib = lib
@@ -160,6 +161,13 @@ class Context:
         self._check(self.lib.lvio2d_set_windows_async(self._h, C.byref(s)), "lvio2d_set_windows_async")
         self.n_windows, self.n_frames = host_batch.n_windows, host_batch.n_frames
         self._keep = host_batch
+
+    def set_windows_wire(self, host_batch, wire, async_=False):
+        """lvio2d_set_windows_wire: `host_batch` without points / point_line / point_offset, the laser input as abi.ScanWire."""
+        s, ws = host_batch.struct(), wire.struct()
+        self._check(self.lib.lvio2d_set_windows_wire(self._h, C.byref(s), C.byref(ws), int(bool(async_))), "lvio2d_set_windows_wire")
+        self.n_windows, self.n_frames = host_batch.n_windows, host_batch.n_frames
+        self._keep = (host_batch, wire)
 
     def get_states_async(self, out):
         self._check(self.lib.lvio2d_get_states_async(self._h, out.ctypes.data), "lvio2d_get_states_async")

@@ -5,15 +5,22 @@ One "step" = one full solve (max 10 LM iterations, the reference's fast_mode cap
 synthetic C2 windows per GPU.  `value` = LM iterations executed by all windows of all ranks / device
 time, inputs already resident in HBM (lvio2d_bind_windows).  `e2e` = the same metric through the reference-facing call
 sequence with HOST buffers inside the timed region: lvio2d_set_windows (pinned host -> device) + lvio2d_solve +
-lvio2d_get_states (device -> host).  `roofline` describes the dominant kernel (scan_match_kernel): algorithmic bytes per
-launch / its CUDA-event duration against the measured HBM copy bandwidth.  `cpu_baseline` is the CPU oracle (a port of
-the reference path; the reference itself needs Eigen/Ceres/ROS and cannot be built here) on one core, the reference's
-own threading (solver.cpp:798).
+lvio2d_get_states (device -> host); since round 2 the laser input travels in the compact wire encoding
+(lvio2d_set_windows_wire: float32 ranges + uint16 line index per beam, 6 instead of 20 bytes per beam; the device rebuilds
+the points the way convert::laser_to_point_times does), `e2e_expanded_points` keeps the round-1 upload next to it.
+`roofline` describes scan_match_kernel, the HBM-bound kernel BASELINE.json's target is quoted on (algorithmic bytes per
+launch / its CUDA-event duration against the measured HBM copy bandwidth); `rooflines` adds the other two kernels of an LM
+iteration (factor_pair_kernel, window_kernel: fp64-bound, against the DFMA / DMMA rates measured in this run) — since
+round 2 the three take about a third of a step each.  `cpu_baseline` is the CPU oracle (a port of the reference path,
+pinned to the reference's own source text by oracle/_ref; the reference binary needs Eigen/Ceres/ROS and cannot be built
+here) on one core, the reference's own threading (solver.cpp:798).
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--windows B] [--impl ours|reference]
 Multi-GPU (torchrun, one rank per GPU): windows are independent, so each rank solves its own B windows (weak scaling,
 no data-path collective); only the timing is reduced (max over ranks).  The point-sharded + all-reduce mode the
-north-star also names is measured by `--shard points` (strong scaling of one batch, one NCCL all-reduce per iteration).
+north-star also names (BASELINE.json configs[3]) is measured in the same launch whenever WORLD_SIZE > 1 and reported as
+`points_sharded` (C4 windows, every frame's points split over the ranks, one all-reduce of the per-frame blocks per LM
+iteration; `--shard points` makes it the headline instead).
 """
 import argparse
 import ctypes as C
@@ -30,6 +37,10 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
+# algorithmic fp64 work: a factor item = whitening 15 x 15 (upper) x 31 + the symmetric 32 x 32 x 20 product
+# + ~3 k for residuals and the 12 dual columns; a window frame = 15^3 x 2 x 3 (inverse, T = U Dinv, D -= T U^T) + 3 gemv
+FACTOR_FLOP_PER_ITEM = 15 * 16 * 31 + 32 * 33 * 20 + 3000
+WINDOW_FLOP_PER_FRAME = 3 * 2 * 15 ** 3 + 3 * 2 * 225
 METRIC = "front-end solver iterations/sec (1081-beam x 30-KF window)"
 UNIT = "LM iterations/s"
 MAX_ITERS = 10
@@ -141,6 +152,101 @@ def pinned_copy(hb, torch):
     return out
 
 
+def points_sharded_block(torch, dist, device, rank, world, local_rank, steps=3, warmup=1):
+    """BASELINE.json configs[3] inside the default multi-GPU launch: C4 windows (4096 beams x 50 key frames), every frame's
+    points split over the ranks, one all-reduce (sum) of the per-frame laser blocks per LM iteration, the small factors
+    and the block solve replicated.  Two shapes: a batch of 256 windows and ONE window (the only case where splitting
+    points rather than windows is the natural thing to do).  Every rank also times the same batch un-sharded, so the
+    speed-up is against this run's own single-GPU number.  Times are device times (CUDA events on the context's
+    stream), max over ranks."""
+    import lvio2d_b200 as L
+    from lvio2d_b200.solver import Context
+
+    P = L.corridor_params(max_iters=MAX_ITERS, device=local_rank)
+    out = {"unit": "ms per step (one 10-iteration solve of the batch)", "exchange": "torch.distributed all_reduce (NCCL) of the reduce buffer on the context's stream, "
+           "11 per solve; no host synchronisation inside the solve"}
+    for name, Bw in (("c4_256_windows", 256), ("c4_single_window", 1)):
+        ctx = Context(P)
+        hb, _ = build_host_batch(ctx, Bw, seed0=42, config="c4")     # the same batch on every rank
+        dstruct, keep = to_device_struct(hb, torch, device)
+        ctx.bind_windows(dstruct, keepalive=keep)
+        ext = torch.cuda.ExternalStream(ctx.stream, device=device)
+
+        def timed(step):
+            for _ in range(warmup):
+                step()
+            ctx.sync()
+            dist.barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(ext)
+            for _ in range(steps):
+                step()
+            e1.record(ext)
+            ctx.sync()
+            t = torch.tensor([e0.elapsed_time(e1) / steps], dtype=torch.float64, device=device)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t[0])
+
+        ctx.set_point_shard(0, 1)
+        t1 = timed(ctx.solve_async)
+        x1 = ctx.get_states()
+        ctx.set_point_shard(rank, world)
+        _, n_red = ctx.reduce_buffer()
+        red = torch.zeros(n_red, dtype=torch.float64, device=device)
+        ctx.set_reduce_buffer(red.data_ptr(), n_red)
+
+        def sharded():
+            with torch.cuda.stream(ext):
+                ctx.solve_begin()
+                for _ in range(MAX_ITERS + 1):
+                    ctx.eval_laser()
+                    dist.all_reduce(red)
+                    ctx.lm_step()
+
+        ctx.set_profiling(True)
+        tn = timed(sharded)
+        prof = ctx.get_profile()
+        ctx.set_profiling(False)
+        xn = ctx.get_states()
+
+        def only_allreduce():
+            with torch.cuda.stream(ext):
+                for _ in range(MAX_ITERS + 1):
+                    dist.all_reduce(red)
+
+        tar = timed(only_allreduce)
+        per = (warmup + steps)
+        out[name] = {
+            "windows": Bw, "points_per_window": int(hb.n_points // hb.n_windows), "n1_ms_per_step": t1, "sharded_ms_per_step": tn,
+            "speedup_vs_n1": t1 / tn, "efficiency": t1 / tn / world,
+            "allreduce_us_per_iteration": tar * 1e3 / (MAX_ITERS + 1), "allreduce_bytes": int(n_red * 8),
+            "per_rank_ms_per_step": {"scan_match": prof["scan_ms"] / per, "factor_replicated": prof["factor_ms"] / per, "window_replicated": prof["window_ms"] / per},
+            "max_state_diff_vs_unsharded": float(np.abs(xn - x1).max()),
+            "limiter": "replicated factor + window kernels (Amdahl): only the scan-match share shrinks with the rank count",
+        }
+        ctx.close()
+        del keep, dstruct, red
+        torch.cuda.empty_cache()
+    return out
+
+
+def pinned_wire(wire, w0, w1, n_frames, torch):
+    """Windows [w0, w1) of a ScanWire in pinned host memory."""
+    from lvio2d_b200 import abi
+
+    f0, f1 = w0 * n_frames, w1 * n_frames
+    keep = [torch.from_numpy(np.ascontiguousarray(x[f0:f1])).pin_memory() for x in (wire.ranges, wire.angle, wire.beam_line.view(np.int16))]
+    imu = None
+    if wire.imu_compact is not None:
+        keep.append(torch.from_numpy(np.ascontiguousarray(wire.imu_compact[w0 * (n_frames - 1):w1 * (n_frames - 1)])).pin_memory())
+        imu = keep[3].numpy()
+    out = abi.ScanWire(keep[0].numpy(), keep[1].numpy(), keep[2].numpy().view(np.uint16), imu)
+    assert out.ranges.ctypes.data == keep[0].data_ptr() and out.beam_line.ctypes.data == keep[2].data_ptr()
+    assert imu is None or out.imu_compact.ctypes.data == keep[3].data_ptr()
+    out._pinned = keep
+    return out
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -171,9 +277,19 @@ def run_ours(args):
     P.assoc_mode = 1 if args.assoc == "nearest" else 0
     P.huber_delta = args.huber
     ctx = Context(P)
+    fp64 = ctx.measure_fp64_peak()
     B = args.windows
     shard_points = args.shard == "points" and world > 1
     hb, uniq = build_host_batch(ctx, B, seed0=42 if shard_points else 42 + 1000 * rank, config=args.config)
+    wire = None
+    if args.config == "c2" and not shard_points:
+        # the benchmark's points are what the sensor's float32 ranges give on the float32 beam grid
+        from lvio2d_b200 import abi
+        import math
+        wire = abi.ScanWire.from_points(hb, 1081, np.float32(math.radians(-135.0)), np.float32(math.radians(270.0) / 1080))
+        wp, wl, _ = wire.points()
+        hb = hb.replace(points=wp, point_line=wl)
+        wire.imu_compact = abi.ScanWire.compact_imu(hb["imu"])
     dstruct, keep = to_device_struct(hb, torch, device)
     ext = torch.cuda.ExternalStream(ctx.stream, device=device)
 
@@ -259,18 +375,32 @@ def run_ours(args):
     hp = pinned_copy(hb, torch)
     out_states = torch.empty(hb.n_windows * hb.n_frames * 15, dtype=torch.float64).pin_memory()
     out_np = out_states.numpy().reshape(-1, 15)
-    e2e_ms = None
+    e2e_ms = e2e_expanded_ms = None
+    e2e_bytes = 0
     if not shard_points:
         # the batch goes through the public API in `--e2e-chunks` chunks alternating over two contexts, so that the
         # host->device copy of chunk k+1 (copy engine) overlaps the solve of chunk k (SMs)
         n_chunks = max(1, args.e2e_chunks)
         per = (B + n_chunks - 1) // n_chunks
         bounds = [(k * per, min(B, (k + 1) * per)) for k in range(n_chunks) if k * per < B]
-        chunks = [pinned_copy(window_slice(hb, a, b), torch) if n_chunks > 1 else hp for a, b in bounds]
-        ectx = [ctx] + ([Context(P)] if n_chunks > 1 else [])
+        ectx = [ctx] + [Context(P) for _ in range(max(0, min(args.e2e_contexts, n_chunks) - 1))]
         nf = hb.n_frames
 
-        def e2e_step():
+        def timed(step):
+            for _ in range(max(1, min(args.warmup, 2))):
+                step()
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(args.steps):
+                step()
+            ms = (time.perf_counter() - t0) * 1e3
+            assert np.abs(out_np - states_dev).max() < 1e-9, "e2e and device-resident arms disagree"
+            return ms
+
+        # (a) round-1 encoding: double points + int32 indices
+        chunks = [pinned_copy(window_slice(hb, a, b), torch) for a, b in bounds]
+
+        def e2e_expanded_step():
             for k, ((a, b), ch) in enumerate(zip(bounds, chunks)):
                 c = ectx[k % len(ectx)]
                 c.set_windows_async(ch)
@@ -279,24 +409,45 @@ def run_ours(args):
             for c in ectx:
                 c.sync()
 
-        for _ in range(max(1, min(args.warmup, 2))):
-            e2e_step()
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(args.steps):
-            e2e_step()
-        e2e_ms = (time.perf_counter() - t0) * 1e3
-        assert np.abs(out_np - states_dev).max() < 1e-9, "e2e and device-resident arms disagree"
+        if wire is None:
+            e2e_ms = timed(e2e_expanded_step)
+            e2e_bytes = int(hp.nbytes())
+        else:
+            e2e_expanded_ms = timed(e2e_expanded_step)
+            out_np[:] = 0.0
+            del chunks
+            # (b) wire encoding: float32 ranges + uint16 line index per beam
+            wchunks = []
+            for a, b in bounds:
+                bare = pinned_copy(window_slice(hb, a, b).replace(points=None, point_line=None, point_offset=None, imu=None), torch)
+                wk = pinned_wire(wire, a, b, nf, torch)
+                wchunks.append((bare, wk))
+            e2e_bytes = int(sum(bare.nbytes() + wk.nbytes() for bare, wk in wchunks))
+
+            def e2e_wire_step():
+                for k, ((a, b), (bare, wk)) in enumerate(zip(bounds, wchunks)):
+                    c = ectx[k % len(ectx)]
+                    c.set_windows_wire(bare, wk, async_=True)
+                    c.solve_async()
+                    c.get_states_async(out_np[a * nf:b * nf])
+                for c in ectx:
+                    c.sync()
+
+            e2e_ms = timed(e2e_wire_step)
     clocks = sampler.stop() if rank == 0 else None
+    sharded_block = None
+    if world > 1 and not shard_points and not args.no_points_sharded:
+        sharded_block = points_sharded_block(torch, dist, device, rank, world, local_rank)
 
     # ------------------------------------------------------------------ reduce over ranks (max time, sum work)
-    t = torch.tensor([dev_ms, e2e_ms if e2e_ms is not None else 0.0], dtype=torch.float64, device=device)
+    t = torch.tensor([dev_ms, e2e_ms if e2e_ms is not None else 0.0, e2e_expanded_ms if e2e_expanded_ms is not None else 0.0],
+                     dtype=torch.float64, device=device)
     work = torch.tensor([float(iters_per_step)], dtype=torch.float64, device=device)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         if not shard_points:
             dist.all_reduce(work, op=dist.ReduceOp.SUM)
-    dev_ms, e2e_ms_all = float(t[0]), float(t[1])
+    dev_ms, e2e_ms_all, e2e_exp_ms_all = float(t[0]), float(t[1]), float(t[2])
     total_iters_per_step = float(work[0])
     if rank != 0:
         if world > 1:
@@ -310,12 +461,13 @@ def run_ours(args):
         prof["scan_bytes_per_launch"] /= world   # each rank streams its own slice of every frame's points
     achieved = prof["scan_bytes_per_launch"] / (scan_ms * 1e-3) / 1e9 if scan_ms > 0 else 0.0
     traffic = None
-    tpath = os.path.join(ROOT, "profiles", "r1_ncu_traffic.json")
-    if os.path.exists(tpath) and args.assoc == "fixed" and not shard_points:
-        with open(tpath) as f:
-            t_ = json.load(f)
-        if int(t_["windows"]) == B:   # ncu capture of the same launch shape (never measured under this run)
-            traffic = t_["dram_bytes_read"] + t_["dram_bytes_write"]
+    for tname in ("r2_ncu_traffic.json", "r1_ncu_traffic.json"):
+        tpath = os.path.join(ROOT, "profiles", tname)
+        if traffic is None and os.path.exists(tpath) and args.assoc == "fixed" and not shard_points:
+            with open(tpath) as f:
+                t_ = json.load(f)
+            if int(t_["windows"]) == B:   # ncu capture of the same launch shape (never measured under this run)
+                traffic = t_["dram_bytes_read"] + t_["dram_bytes_write"]
     result = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
@@ -335,25 +487,54 @@ def run_ours(args):
         },
         "e2e": None if shard_points else {
             "value": total_iters_per_step * args.steps / (e2e_ms_all * 1e-3), "unit": UNIT,
-            "h2d_bytes_per_step": int(hp.nbytes()), "d2h_bytes_per_step": int(out_states.numel() * 8),
+            "h2d_bytes_per_step": e2e_bytes, "d2h_bytes_per_step": int(out_states.numel() * 8),
             "ms_per_step": e2e_ms_all / args.steps,
-            "api": f"lvio2d_set_windows_async(pinned host) + lvio2d_solve_async + lvio2d_get_states_async + lvio2d_sync, {args.e2e_chunks} chunks over 2 contexts",
+            "api": (f"lvio2d_set_windows_wire(pinned host: float32 ranges + uint16 line index per beam, lines, the 190 doubles of each IMU preintegration the factor reads, wheel blobs, states; async) + "
+                    f"lvio2d_solve_async + lvio2d_get_states_async + lvio2d_sync, {args.e2e_chunks} chunks over {args.e2e_contexts} contexts") if wire is not None else
+                   f"lvio2d_set_windows_async(pinned host) + lvio2d_solve_async + lvio2d_get_states_async + lvio2d_sync, {args.e2e_chunks} chunks over {args.e2e_contexts} contexts",
         },
         "gpu_launches": prof["kernel_launches"],
         "kernel_share": {"scan_match_ms_per_step": prof["scan_ms"] / args.steps, "factor_ms_per_step": prof["factor_ms"] / args.steps, "window_ms_per_step": prof["window_ms"] / args.steps},
         "roofline": {
             "kernel": "scan_match_kernel<false,false>", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-            "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+            "frac": achieved / peak, "traffic": traffic, "traffic_source": "static: ncu --set full capture of the same launch shape (profiles/r*_ncu_traffic.json), not measured in this run",
+            "peak_source": peak_src,
             "algorithmic_bytes_per_launch": prof["scan_bytes_per_launch"], "avg_launch_ms": scan_ms,
         },
         "clocks": clocks,
     }
+    if wire is not None and e2e_exp_ms_all > 0:
+        result["e2e_expanded_points"] = {
+            "value": total_iters_per_step * args.steps / (e2e_exp_ms_all * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(hp.nbytes()),
+            "ms_per_step": e2e_exp_ms_all / args.steps, "api": "round-1 upload: lvio2d_set_windows_async with double points + int32 indices"}
+    # the other two kernels of an LM iteration against the fp64 rates measured on this device in this run
+    fac_ms = prof["factor_ms"] / max(1, prof["factor_launches"])
+    win_ms = prof["window_ms"] / max(1, prof["window_launches"])
+    items = B * hb.n_frames
+    fac_flop = items * FACTOR_FLOP_PER_ITEM
+    win_flop = items * WINDOW_FLOP_PER_FRAME
+    result["fp64_peak"] = {"dfma_tflops": fp64["dfma_tflops"], "dmma_tflops": fp64["dmma_tflops"],
+                           "how": "lvio2d_measure_fp64_peak: 16 independent DFMA chains per thread / 8 independent DMMA.8x8x4 tiles per warp, all SMs, best of 3"}
+    result["rooflines"] = [
+        result["roofline"],
+        {"kernel": "factor_pair_kernel", "bound": "fp64 (vector + tensor pipe), latency", "achieved": fac_flop / (fac_ms * 1e-3) / 1e12, "peak": fp64["dfma_tflops"],
+         "unit": "TFLOP/s", "frac": fac_flop / (fac_ms * 1e-3) / 1e12 / fp64["dfma_tflops"], "traffic": None, "avg_launch_ms": fac_ms,
+         "algorithmic_flop_per_launch": fac_flop, "algorithmic_flop_per_item": FACTOR_FLOP_PER_ITEM,
+         "algorithmic_bytes_per_launch": items * (466 + 15 + 640) * 8},
+        {"kernel": "window_kernel<false,32>", "bound": "fp64 (vector + tensor pipe), latency", "achieved": win_flop / (win_ms * 1e-3) / 1e12, "peak": fp64["dfma_tflops"],
+         "unit": "TFLOP/s", "frac": win_flop / (win_ms * 1e-3) / 1e12 / fp64["dfma_tflops"], "traffic": None, "avg_launch_ms": win_ms,
+         "algorithmic_flop_per_launch": win_flop, "algorithmic_flop_per_frame": WINDOW_FLOP_PER_FRAME,
+         "algorithmic_bytes_per_launch": items * (640 + 256 + 256) * 8},
+    ]
+    if sharded_block is not None:
+        result["points_sharded"] = sharded_block
     if world == 1:
         result["single_window"] = single_window_latency(P, hb, torch, device)
         result["next_rows"] = front_end_rates(P, torch, device, cpu=not args.no_cpu)
         result["next_rows"]["pose_graph"] = pose_graph_rates(cpu=not args.no_cpu)
     if world == 1 and not args.no_cpu:
-        result["cpu_baseline"] = cpu_baseline(P, hb, seconds=args.cpu_seconds, threads=1)
+        result["cpu_baseline"] = cpu_baseline(P, hb, seconds=args.cpu_seconds, threads=1, states_dev=states_dev)
+        result["pose_err_vs_oracle"] = result["cpu_baseline"].pop("pose_err_vs_oracle")
     print(json.dumps(result))
     if world > 1:
         dist.destroy_process_group()
@@ -528,7 +709,7 @@ def first_windows(hb, k):
     return window_slice(hb, 0, k)
 
 
-def cpu_baseline(P, hb, seconds, threads):
+def cpu_baseline(P, hb, seconds, threads, states_dev=None):
     """The CPU oracle (port of the reference path) on a bounded sample: the first windows of the same batch."""
     import oracle_lib as O
     from lvio2d_b200 import abi
@@ -544,12 +725,17 @@ def cpu_baseline(P, hb, seconds, threads):
     k = max(1, min(k, hb.n_windows))
     batch = sub(k)
     t0 = time.perf_counter()
-    _, s = O.solve(P, batch, n_threads=threads)
+    ost, s = O.solve(P, batch, n_threads=threads)
     dt = time.perf_counter() - t0
     out = {"value": float(s["iterations"].sum()) / dt, "unit": UNIT, "cores": threads, "kind": "port",
            "sample": f"{k} of the batch's windows, {int(s['iterations'].sum())} LM iterations in {dt:.1f} s "
                      f"(oracle/liboracle.so, Jet autodiff, g++ -O3 -march=native)",
            "host_cpus": os.cpu_count()}
+    if states_dev is not None:
+        # the windows the oracle just solved against the states the device-resident arm produced for them
+        d = np.abs(np.asarray(states_dev).reshape(-1, 15)[:k * hb.n_frames] - ost.reshape(-1, 15))
+        out["pose_err_vs_oracle"] = {"windows": k, "max_abs_position_m": float(d[:, 0:3].max()), "max_abs_rotation_rad": float(d[:, 3:6].max()),
+                                     "max_abs_state": float(d.max()), "bar": "1e-4 m / 1e-4 rad per key frame (BASELINE.json north_star)"}
     # disclosed next to the headline baseline: the same minimiser with a closed-form Jacobian for the
     # scan-point factor — faster than what the reference does (it differentiates with Jets), a fairer CPU number
     ka = max(1, min(k, 8))
@@ -601,16 +787,18 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--windows", type=int, default=4096, help="windows per GPU per step")
+    ap.add_argument("--windows", type=int, default=4736, help="windows per GPU per step (default 32 x 148 SMs: the one-warp-per-window kernel keeps 16 warps per SM resident, so 4736 windows are exactly two full waves; round 1 used 4096)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--shard", default="windows", choices=["windows", "points"])
     ap.add_argument("--config", default="c2", choices=["c2", "c4"], help="c4 = BASELINE configs[3]: 4096 beams x 50 keyframes (use with --shard points)")
     ap.add_argument("--assoc", default="fixed", choices=["fixed", "nearest"], help="nearest = BASELINE config 3 (in-kernel re-association)")
     ap.add_argument("--huber", type=float, default=0.0, help="Huber delta on the whitened laser residuals (0 = reference: none)")
     ap.add_argument("--contexts", type=int, default=1, help="split the batch over this many solver contexts / CUDA streams")
-    ap.add_argument("--e2e-chunks", type=int, default=8, help="chunks the end-to-end arm splits the batch into (2 contexts alternate)")
+    ap.add_argument("--e2e-chunks", type=int, default=8, help="chunks the end-to-end arm splits the batch into")
+    ap.add_argument("--e2e-contexts", type=int, default=4, help="solver contexts (CUDA streams) the chunks rotate over: the upload of one chunk overlaps the solves of the others")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-points-sharded", action="store_true", help="skip the points_sharded block of multi-GPU runs")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

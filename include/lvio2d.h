@@ -181,6 +181,25 @@ int lvio2d_get_states_async(lvio2d_ctx* ctx, double* host_states /* [B*n][15] */
  * lowers it to 10 in fast_mode (src/factor/solver.cpp:800-801), solver::do_init_solve never does (:161-168), so an
  * initialisation runs Ceres' default 50 iterations whatever fast_mode says.  max_iters <= 0 selects 50. */
 int lvio2d_set_max_iterations(lvio2d_ctx* ctx, int32_t max_iters);
+/* Compact wire encoding of the laser input of a beam-mode batch: what the sensor delivers (one sensor_msgs/LaserScan per
+ * frame, float32) plus a 16-bit line index per beam, instead of 16-byte points and 32-bit indices — 6 instead of 20 bytes
+ * per beam across PCIe.  The device rebuilds the points like convert::laser_to_point_times does (src/utilies/common.cpp:6-24:
+ * float32 angle_min + k * angle_increment, cos / sin in double, times the float32 range) without its 1 cm thinning;
+ * beams the reference rejects (NaN, inf, <= 0.1 m) and beams with index 0xFFFF take no part.  Every frame has n_beams
+ * point slots.  In `host_batch` points / point_line / point_weight / point_offset are ignored; lines, line_offset,
+ * ref_frame, ref_pose and everything else are as for lvio2d_set_windows. */
+typedef struct lvio2d_scan_wire {
+    int32_t n_beams;
+    const float* ranges;          /* [B*n][n_beams] */
+    const float* angle;           /* [B*n][2]  angle_min, angle_increment */
+    const uint16_t* beam_line;    /* [B*n][n_beams]  index into the frame's line list, 0xFFFF = no correspondence */
+    /* optional (NULL: host_batch->imu is used): the 190 doubles of every imu_preint_result that imu_factor::operator()
+     * reads (src/factor/imu_factor.h:52-86) instead of the 466 of the full blob:
+     *   X[15] | J(k, 9..14), k = 0..8, row-major [9][6] | the upper triangle of sqrt_inverse_P row by row (120) | Dt */
+    const double* imu_compact;    /* [B*(n-1)][LVIO2D_IMU_COMPACT] */
+} lvio2d_scan_wire;
+#define LVIO2D_IMU_COMPACT 190
+int lvio2d_set_windows_wire(lvio2d_ctx* ctx, const lvio2d_window_batch* host_batch, const lvio2d_scan_wire* wire, int32_t async);
 /* overwrite the states only (same shapes): re-arm a bound batch for another solve */
 int lvio2d_reset_states(lvio2d_ctx* ctx, const double* host_states);
 
