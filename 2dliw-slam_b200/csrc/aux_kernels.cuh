@@ -342,20 +342,4 @@ __global__ void expand_wire_kernel(const float* __restrict__ ranges, const float
     point_line[i] = (valid && l != 0xFFFFu) ? (int32_t)l : -1;
 }
 
-// lvio2d_scan_wire::imu_compact -> the ABI blob layout the factor kernels read (entries imu_factor never reads stay zero)
-__global__ void expand_imu_compact_kernel(const double* __restrict__ compact, double* __restrict__ blobs, int n_blobs) {
-    const int b = blockIdx.x;
-    if (b >= n_blobs) return;
-    const double* c = compact + (size_t)b * 190;
-    double* o = blobs + (size_t)b * 466;
-    for (int k = threadIdx.x; k < 466; k += blockDim.x) {
-        double v = 0.0;
-        if (k < 15) v = c[k];
-        else if (k < 240) { const int r = (k - 15) / 15, q = (k - 15) % 15; if (r < 9 && q >= 9) v = c[15 + r * 6 + (q - 9)]; }
-        else if (k < 465) { const int r = (k - 240) / 15, q = (k - 240) % 15; if (q >= r) v = c[69 + r * 15 - (r * (r - 1)) / 2 + (q - r)]; }
-        else v = c[189];
-        o[k] = v;
-    }
-}
-
 }  // namespace lv

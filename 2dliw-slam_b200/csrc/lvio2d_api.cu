@@ -74,6 +74,7 @@ struct lvio2d_ctx {
     bool have = false, bound = false;
     int B = 0, n = 0, ground_mult = 0, prior_frame = -1;
     bool arrow = false, has_weight = false, has_imu = false, has_wheel = false;
+    int imu_stride = LVIO2D_IMU_BLOB;   // LVIO2D_IMU_COMPACT when the batch came with lvio2d_scan_wire::imu_compact
     int64_t N = 0, L = 0;
     int tiles = 1, line_cap = 1, npad = kPadTrack;
     int uniform_pts = 0, uniform_lines = 0;   // > 0: all frames have this many points / lines (scan-match fast prologue)
@@ -223,7 +224,7 @@ WindowArgs window_args(lvio2d_ctx* ctx, int mode) {
     a.C = ctx->C; a.opt = ctx->opt;
     a.n_windows = ctx->B; a.n_frames = ctx->n; a.tiles = ctx->tiles; a.arrow = ctx->arrow; a.mode = mode;
     a.ground_multiplicity = ctx->ground_mult; a.prior_frame = ctx->prior_frame;
-    a.has_imu = ctx->has_imu; a.has_wheel = ctx->has_wheel;
+    a.has_imu = ctx->has_imu; a.has_wheel = ctx->has_wheel; a.imu_stride = ctx->imu_stride;
     a.const_mask = ctx->const_mask; a.frame_active = (mode == 1 ? ctx->b_active1 : ctx->b_active).as<uint8_t>(); a.ref_frame = ctx->ref_frame;
     a.imu = ctx->imu; a.wheel = ctx->wheel; a.prior_X0 = ctx->prior_X0; a.prior_J = ctx->prior_J; a.prior_H = ctx->b_pH.as<double>();
     a.partial = ctx->b_part.as<double>();
@@ -422,15 +423,11 @@ int setup_batch(lvio2d_ctx* ctx, const lvio2d_window_batch* b, bool bind, bool a
     if ((rc = take<int32_t>(ctx, false, ctx->b_ref, ctx->ref_frame, rf.data(), (size_t)F))) return rc;
     if ((rc = take<uint8_t>(ctx, false, ctx->b_cmask, ctx->const_mask, cm.data(), (size_t)F))) return rc;
     if ((rc = take<double>(ctx, bind, ctx->b_refpose, ctx->ref_pose, has_laser ? b->ref_pose : nullptr, (size_t)F * 6))) return rc;
+    ctx->imu_stride = LVIO2D_IMU_BLOB;
     if (wire && wire->imu_compact && ctx->has_imu) {
-        const size_t nb = (size_t)B * (n - 1);
-        const double* d_c;
-        if ((rc = take<double>(ctx, false, ctx->b_wi, d_c, wire->imu_compact, nb * LVIO2D_IMU_COMPACT))) return rc;
-        if (!ctx->b_imu.ensure(nb * LVIO2D_IMU_BLOB * sizeof(double))) return fail(ctx, LVIO2D_ERR_ALLOC, "cudaMalloc(imu)");
-        expand_imu_compact_kernel<<<(unsigned)nb, 128, 0, ctx->stream>>>(d_c, ctx->b_imu.as<double>(), (int)nb);
-        CK(cudaGetLastError());
-        ctx->launches += 1;
-        ctx->imu = ctx->b_imu.as<double>();
+        // the factor kernels read the compact records in place (no expansion pass, 1.5 instead of 3.7 KB per item from HBM)
+        if ((rc = take<double>(ctx, false, ctx->b_wi, ctx->imu, wire->imu_compact, (size_t)B * (n - 1) * LVIO2D_IMU_COMPACT))) return rc;
+        ctx->imu_stride = LVIO2D_IMU_COMPACT;
     } else if ((rc = take<double>(ctx, bind, ctx->b_imu, ctx->imu, ctx->has_imu ? b->imu : nullptr, (size_t)B * (n - 1) * LVIO2D_IMU_BLOB))) return rc;
     if ((rc = take<double>(ctx, bind, ctx->b_wheel, ctx->wheel, ctx->has_wheel ? b->wheel : nullptr, (size_t)B * (n - 1) * LVIO2D_WHEEL_BLOB))) return rc;
     if ((rc = take<double>(ctx, bind, ctx->b_pX0, ctx->prior_X0, ctx->prior_frame >= 0 ? b->prior_X0 : nullptr, (size_t)B * 15))) return rc;

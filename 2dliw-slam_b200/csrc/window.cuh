@@ -103,6 +103,7 @@ struct WindowArgs {
     LMOptions opt;
     int32_t n_windows, n_frames, tiles, arrow, mode;  // mode 0: solver program, 1: marginalisation program
     int32_t ground_multiplicity, prior_frame, has_imu, has_wheel;
+    int32_t imu_stride;             // 466: ABI blobs; 190: the compact records of lvio2d_scan_wire::imu_compact
     const uint8_t* const_mask;      // [B*n]
     const uint8_t* frame_active;    // [B*n] laser block active
     const int32_t* ref_frame;       // [B*n] or nullptr
@@ -178,18 +179,22 @@ __device__ __forceinline__ void dmma884(double& d0, double& d1, const double a, 
 // residual blocks whose parameter blocks are all constant have zero rows (their cost is Ceres' fixed_cost).
 constexpr int kWS = 34, kWRows = 20, kWSize = kWRows * kWS;
 constexpr int kCB = 72;   // compact IMU blob: X[15] | pad | J(0..8, 9..14) [9][6] at 16 | Dt at 70
-__device__ __forceinline__ void stage_compact_blob(double* sC, const double* blob, int sl, int nsl) {
+__device__ __forceinline__ void stage_compact_blob(double* sC, const double* blob, int sl, int nsl, bool compact) {
     for (int k = sl; k < 70; k += nsl) {
-        const int src = k < 15 ? k : (k < 69 ? 15 + ((k - 15) / 6) * 15 + 9 + (k - 15) % 6 : 465);
+        const int src = compact ? (k < 69 ? k : 189) : (k < 15 ? k : (k < 69 ? 15 + ((k - 15) / 6) * 15 + 9 + (k - 15) % 6 : 465));
         cp_async8(sC + (k < 15 ? k : (k < 69 ? k + 1 : 70)), blob + src);
     }
+}
+// entry (r, k), k >= r, of the upper-triangular sqrt_inverse_P: row-major 15 x 15 in the ABI blob, packed rows in the compact record
+__device__ __forceinline__ double sqrt_info_at(const double* sq, bool compact, int r, int k) {
+    return __ldg(sq + (compact ? r * 15 - (r * (r - 1)) / 2 + (k - r) : r * 15 + k));
 }
 
 // Whole warp.  Whitening (when sq != nullptr: rows 0..14 <- sq rows 0..14, upper triangular sqrt_inverse_P read from
 // global memory as DMMA A fragments), W^T W on the tensor pipe, the marginalisation prior of frame i (r = J (x - X0),
 // marginalization_factor.h:50: H += J^T J, g += J^T r, cost += r^T r from the precomputed J^T J), one 16-byte store per
 // lane and tile.
-__device__ __forceinline__ void item_finish(const WindowArgs& a, double* W, const double* sq, const int w, const int i, const uint8_t mb,
+__device__ __forceinline__ void item_finish(const WindowArgs& a, double* W, const double* sq, const bool sq_packed, const int w, const int i, const uint8_t mb,
                                             const bool prior_on, double* sPg /* 16 doubles */, double* out, const int lane) {
     const int g = lane >> 2, t = lane & 3;
     if (sq) {
@@ -197,12 +202,12 @@ __device__ __forceinline__ void item_finish(const WindowArgs& a, double* W, cons
 #pragma unroll
         for (int ks = 0; ks < 4; ++ks) {
             const int k = 4 * ks + t;
-            af[ks] = (k < 15 && k >= g) ? __ldg(sq + g * 15 + k) : 0.0;
+            af[ks] = (k < 15 && k >= g) ? sqrt_info_at(sq, sq_packed, g, k) : 0.0;
         }
 #pragma unroll
         for (int ks = 2; ks < 4; ++ks) {
             const int r = 8 + g, k = 4 * ks + t;
-            af[2 + ks] = (r < 15 && k < 15 && k >= r) ? __ldg(sq + r * 15 + k) : 0.0;
+            af[2 + ks] = (r < 15 && k < 15 && k >= r) ? sqrt_info_at(sq, sq_packed, r, k) : 0.0;
         }
 #pragma unroll
         for (int ks = 0; ks < 4; ++ks)
@@ -323,8 +328,18 @@ __global__ void __launch_bounds__(128, LV_FACTOR_MINB) factor_kernel(WindowArgs 
     const bool ground_on = a.ground_multiplicity > 0 && (mb & 3) != 3;
     const bool prior_on = a.prior_frame == i && (mb & 15) != 15;
     if (imu_on) {
-        const double* blob = a.imu + ((size_t)w * (n - 1) + (i - 1)) * 466;
-        if ((reinterpret_cast<uintptr_t>(blob) & 15) == 0) {
+        const double* blob = a.imu + ((size_t)w * (n - 1) + (i - 1)) * a.imu_stride;
+        if (a.imu_stride != 466) {
+            // compact record -> the blob layout item_imu reads (entries imu_factor never reads stay zero)
+            for (int k = lane; k < 466; k += 32) {
+                double v = 0.0;
+                if (k < 15) v = blob[k];
+                else if (k < 240) { const int r = (k - 15) / 15, q = (k - 15) % 15; if (r < 9 && q >= 9) v = blob[15 + r * 6 + (q - 9)]; }
+                else if (k < 465) { const int r = (k - 240) / 15, q = (k - 240) % 15; if (q >= r) v = blob[69 + r * 15 - (r * (r - 1)) / 2 + (q - r)]; }
+                else v = blob[189];
+                sblob[k] = v;
+            }
+        } else if ((reinterpret_cast<uintptr_t>(blob) & 15) == 0) {
             for (int k = lane; k < 233; k += 32) cp_async16(sblob + 2 * k, blob + 2 * k);
         } else {
             for (int k = lane; k < 466; k += 32) cp_async8(sblob + k, blob + k);
@@ -381,7 +396,7 @@ __global__ void __launch_bounds__(128, LV_FACTOR_MINB) factor_kernel(WindowArgs 
         }
     }
     __syncwarp();
-    item_finish(a, W, nullptr, w, i, mb, prior_on, sPg, out, lane);
+    item_finish(a, W, nullptr, false, w, i, mb, prior_on, sPg, out, lane);
 }
 
 // =====================================================================================================
@@ -424,9 +439,10 @@ __device__ __forceinline__ void factor_pair_item(const WindowArgs& a, const int 
     const bool wheel_on = live && i > 0 && a.has_wheel && ((ma & 3) != 3 || (mb & 3) != 3);
     const bool ground_on = live && a.ground_multiplicity > 0 && (mb & 3) != 3;
     const bool prior_on = live && a.prior_frame == i && (mb & 15) != 15;
-    const double* blob = a.imu + ((size_t)w * (n - 1) + (i > 0 ? i - 1 : 0)) * 466;
+    const bool compact = a.imu_stride != 466;
+    const double* blob = a.imu + ((size_t)w * (n - 1) + (i > 0 ? i - 1 : 0)) * a.imu_stride;
     // ---- phase A: both items at once.  Constant inputs travel to shared memory while the exponentials are evaluated.
-    if (imu_on) stage_compact_blob(sC, blob, sl, 16);
+    if (imu_on) stage_compact_blob(sC, blob, sl, 16, compact);
     if (wheel_on && sl < 15) cp_async8(sWb + sl, a.wheel + ((size_t)w * (n - 1) + (i - 1)) * 15 + sl);
     // rows 15..19 (and the IMU rows of an item without IMU factor) start from zero
     for (int k = (imu_on ? 15 * kWS : 0) + sl; k < kWSize; k += 16) W[k] = 0.0;
@@ -524,8 +540,8 @@ __device__ __forceinline__ void factor_pair_item(const WindowArgs& a, const int 
         const bool imu_v = __shfl_sync(0xffffffffu, (int)imu_on, src) != 0;
         const int parity = 1 - a.state[wv].cur;
         double* out = a.items + ((size_t)parity * total + (size_t)wv * n + iv) * kItem;
-        const double* sq = imu_v ? a.imu + ((size_t)wv * (n - 1) + (iv - 1)) * 466 + 240 : nullptr;
-        item_finish(a, base + hh * kPairHalf + kCB, sq, wv, iv, mbv, prior_v, sPg, out, lane);
+        const double* sq = imu_v ? a.imu + ((size_t)wv * (n - 1) + (iv - 1)) * a.imu_stride + (compact ? 69 : 240) : nullptr;
+        item_finish(a, base + hh * kPairHalf + kCB, sq, compact, wv, iv, mbv, prior_v, sPg, out, lane);
     }
 }
 

@@ -289,7 +289,8 @@ def run_ours(args):
         wire = abi.ScanWire.from_points(hb, 1081, np.float32(math.radians(-135.0)), np.float32(math.radians(270.0) / 1080))
         wp, wl, _ = wire.points()
         hb = hb.replace(points=wp, point_line=wl)
-        wire.imu_compact = abi.ScanWire.compact_imu(hb["imu"])
+        if not args.no_imu_compact:
+            wire.imu_compact = abi.ScanWire.compact_imu(hb["imu"])
     dstruct, keep = to_device_struct(hb, torch, device)
     ext = torch.cuda.ExternalStream(ctx.stream, device=device)
 
@@ -386,13 +387,20 @@ def run_ours(args):
         ectx = [ctx] + [Context(P) for _ in range(max(0, min(args.e2e_contexts, n_chunks) - 1))]
         nf = hb.n_frames
 
-        def timed(step):
-            for _ in range(max(1, min(args.warmup, 2))):
-                step()
+        def timed(enqueue):
+            """K steps through the public API, every step uploading its own inputs and reading its own result back.  The
+            steps are enqueued back to back (the upload of a chunk overlaps the solves of earlier chunks, of this step or
+            the previous one: lvio2d_set_windows_* waits for its own context's stream only); the clock stops when the
+            last result has arrived."""
+            def run(k):
+                for _ in range(k):
+                    enqueue()
+                for c in ectx:
+                    c.sync()
+            run(max(1, min(args.warmup, 2)))
             barrier()
             t0 = time.perf_counter()
-            for _ in range(args.steps):
-                step()
+            run(args.steps)
             ms = (time.perf_counter() - t0) * 1e3
             assert np.abs(out_np - states_dev).max() < 1e-9, "e2e and device-resident arms disagree"
             return ms
@@ -406,8 +414,6 @@ def run_ours(args):
                 c.set_windows_async(ch)
                 c.solve_async()
                 c.get_states_async(out_np[a * nf:b * nf])
-            for c in ectx:
-                c.sync()
 
         if wire is None:
             e2e_ms = timed(e2e_expanded_step)
@@ -419,7 +425,7 @@ def run_ours(args):
             # (b) wire encoding: float32 ranges + uint16 line index per beam
             wchunks = []
             for a, b in bounds:
-                bare = pinned_copy(window_slice(hb, a, b).replace(points=None, point_line=None, point_offset=None, imu=None), torch)
+                bare = pinned_copy(window_slice(hb, a, b).replace(points=None, point_line=None, point_offset=None, **({} if wire.imu_compact is None else {"imu": None})), torch)
                 wk = pinned_wire(wire, a, b, nf, torch)
                 wchunks.append((bare, wk))
             e2e_bytes = int(sum(bare.nbytes() + wk.nbytes() for bare, wk in wchunks))
@@ -430,8 +436,6 @@ def run_ours(args):
                     c.set_windows_wire(bare, wk, async_=True)
                     c.solve_async()
                     c.get_states_async(out_np[a * nf:b * nf])
-                for c in ectx:
-                    c.sync()
 
             e2e_ms = timed(e2e_wire_step)
     clocks = sampler.stop() if rank == 0 else None
@@ -794,10 +798,11 @@ def main():
     ap.add_argument("--assoc", default="fixed", choices=["fixed", "nearest"], help="nearest = BASELINE config 3 (in-kernel re-association)")
     ap.add_argument("--huber", type=float, default=0.0, help="Huber delta on the whitened laser residuals (0 = reference: none)")
     ap.add_argument("--contexts", type=int, default=1, help="split the batch over this many solver contexts / CUDA streams")
-    ap.add_argument("--e2e-chunks", type=int, default=8, help="chunks the end-to-end arm splits the batch into")
+    ap.add_argument("--e2e-chunks", type=int, default=4, help="chunks the end-to-end arm splits the batch into")
     ap.add_argument("--e2e-contexts", type=int, default=4, help="solver contexts (CUDA streams) the chunks rotate over: the upload of one chunk overlaps the solves of the others")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-imu-compact", action="store_true", help="end-to-end arm: upload the full 466-double IMU blobs instead of the 190 doubles the factor reads")
     ap.add_argument("--no-points-sharded", action="store_true", help="skip the points_sharded block of multi-GPU runs")
     args = ap.parse_args()
     if args.impl == "reference":
