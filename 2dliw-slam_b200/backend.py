@@ -61,7 +61,8 @@ class KeyframeManager:
         tfs = np.array([np.asarray(e.tf12, dtype=np.float64)[:3, :4] for e in edges])
         weights = np.r_[np.ones(len(self.seq_edges)), np.full(len(self.loop_edges), float(self.loop_edge_k))]
         out, summ = self.ctx.pose_graph_solve(poses, index, tfs, weights, edge_noise_J(self.loop_sigma_p, self.loop_sigma_q),
-                                              self.use_ground_p_factor, self.use_ground_q_factor)
+                                              self.use_ground_p_factor, self.use_ground_q_factor,
+                                              fixed_pose=self.seq_edges[0].index1 if self.seq_edges else -1)   # keyframe_manager.cpp:744-748
         for kf, x in zip(self.keyframe_queue, out):
             kf.p[:] = x[0:3]
             kf.q[:] = x[3:6]

@@ -73,14 +73,14 @@ struct lvio2d_ctx {
     // problem
     bool have = false, bound = false;
     int B = 0, n = 0, ground_mult = 0, prior_frame = -1;
-    bool arrow = false, has_weight = false, has_imu = false, has_wheel = false;
+    bool arrow = false, has_weight = false, has_imu = false, has_wheel = false, assoc_grid = false;
     int imu_stride = LVIO2D_IMU_BLOB;   // LVIO2D_IMU_COMPACT when the batch came with lvio2d_scan_wire::imu_compact
     int64_t N = 0, L = 0;
     int tiles = 1, line_cap = 1, npad = kPadTrack;
     int uniform_pts = 0, uniform_lines = 0;   // > 0: all frames have this many points / lines (scan-match fast prologue)
     int shard_rank = 0, shard_world = 1;
     // inputs (owned copies, or borrowed device pointers when bound)
-    DevBuf b_points, b_pline, b_pweight, b_poff, b_loff, b_lines, b_ref, b_refpose, b_imu, b_wheel, b_pX0, b_pJ, b_pH, b_cmask, b_wr, b_wa, b_wl, b_wi;
+    DevBuf b_points, b_pline, b_pweight, b_poff, b_loff, b_lines, b_ref, b_refpose, b_imu, b_wheel, b_pX0, b_pJ, b_pH, b_cmask, b_wr, b_wa, b_wl, b_wi, b_agp, b_agm;
     const double2* points = nullptr; const int32_t* point_line = nullptr; const double* point_weight = nullptr;
     const int64_t* point_offset = nullptr; const int64_t* line_offset = nullptr; const double4* lines = nullptr;
     const int32_t* ref_frame = nullptr; const double* ref_pose = nullptr; const double* imu = nullptr; const double* wheel = nullptr;
@@ -182,7 +182,7 @@ int launch_scan_match(lvio2d_ctx* ctx, int mode = 0) {
     const int grid = (a.n_items + wpc - 1) / wpc;
     const bool assoc = ctx->params.assoc_mode == LVIO2D_ASSOC_NEAREST;
     const bool huber = ctx->huber > 0;
-    const size_t smem = (size_t)wpc * ctx->line_cap * scan_row(ctx->arrow, assoc) * sizeof(double);
+    const size_t smem = (size_t)wpc * (ctx->line_cap * scan_row(ctx->arrow, assoc) + ((assoc && !ctx->arrow) ? kAssocGridDoubles : 0)) * sizeof(double);
     if (ctx->profiling) cudaEventRecord(next_event(ctx->ev_scan, ctx->ev_scan_used), ctx->stream);
 #define LAUNCH_SM(RF, HW, AS, HU)                                                                                            \
     do {                                                                                                                     \
@@ -215,6 +215,8 @@ ScanMatchArgs scan_args(lvio2d_ctx* ctx, int mode) {
     a.huber_delta = ctx->huber; a.laser_sqrt_info = ctx->C.laser_sqrt_info;
     a.assoc_gate = ctx->params.assoc_gate > 0 ? ctx->params.assoc_gate : 0.1;
     a.assoc_max_dist = ctx->params.assoc_max_dist > 0 ? ctx->params.assoc_max_dist : 0.5;
+    a.assoc_grid_par = ctx->assoc_grid ? ctx->b_agp.as<double>() : nullptr;
+    a.assoc_grid_mask = ctx->assoc_grid ? ctx->b_agm.as<unsigned long long>() : nullptr;
     return a;
 }
 
@@ -371,6 +373,16 @@ int setup_batch(lvio2d_ctx* ctx, const lvio2d_window_batch* b, bool bind, bool a
         active[f] = act ? 1 : 0;
     }
     if (line_cap > 512) return fail(ctx, LVIO2D_ERR_DOMAIN, "more than 512 lines in one local map");
+    // host buffers of moderate size: every correspondence must point into its own frame's line list.  (Bound device
+    // buffers and large uploads are not scanned on the host; the kernel skips out-of-range indices instead of reading
+    // outside its line table.)
+    if (!bind && !wire && has_laser && ctx->N <= ((int64_t)1 << 22)) {
+        for (int f = 0; f < F; ++f) {
+            const int64_t nl = loff[f + 1] - loff[f];
+            for (int64_t p = poff[f]; p < poff[f + 1]; ++p)
+                if (b->point_line[p] >= nl) return fail(ctx, LVIO2D_ERR_INVALID_ARG, "point_line index beyond the frame's line list");
+        }
+    }
     {
         // fixed-size scans: offsets are arithmetic, the scan-match prologue needs no dependent offset loads
         bool up = has_laser && F > 0 && poff[0] == 0, ul = has_laser && F > 0 && loff[0] == 0;
@@ -393,7 +405,7 @@ int setup_batch(lvio2d_ctx* ctx, const lvio2d_window_batch* b, bool bind, bool a
         tiles = (int)std::max<int64_t>(1, std::min<int64_t>(tiles, avg / 64));
         ctx->tiles = tiles;
     }
-    const size_t smem_scan = (size_t)LV_SCAN_WPC * line_cap * scan_row(arrow, ctx->params.assoc_mode == LVIO2D_ASSOC_NEAREST) * sizeof(double);
+    const size_t smem_scan = (size_t)LV_SCAN_WPC * (line_cap * scan_row(arrow, ctx->params.assoc_mode == LVIO2D_ASSOC_NEAREST) + kAssocGridDoubles) * sizeof(double);
     if (smem_scan > 200 * 1024) return fail(ctx, LVIO2D_ERR_DOMAIN, "local map too large for shared memory");
     if (window_smem_bytes(ctx) > 200 * 1024) return fail(ctx, LVIO2D_ERR_DOMAIN, "n_frames too large for shared memory");
 
@@ -458,6 +470,18 @@ int setup_batch(lvio2d_ctx* ctx, const lvio2d_window_batch* b, bool bind, bool a
         world_lines_kernel<<<F, 128, 0, ctx->stream>>>(ctx->lines, ctx->line_offset, ctx->ref_frame,
                                                        ctx->b_reftab.as<double>(), ctx->b_wlines.as<double4>(), ctx->b_wlen.as<double>(), F);
         CK(cudaGetLastError());
+        // in-kernel re-association: the candidate grid of every frame's local map (LVIO2D_ASSOC_GRID=0: all-lines loop)
+        ctx->assoc_grid = false;
+        const char* ag = std::getenv("LVIO2D_ASSOC_GRID");
+        if (ctx->params.assoc_mode == LVIO2D_ASSOC_NEAREST && !arrow && !(ag && std::atoi(ag) == 0)) {
+            if (!ctx->b_agp.ensure((size_t)F * 4 * sizeof(double)) || !ctx->b_agm.ensure((size_t)F * kAssocGridDoubles * sizeof(unsigned long long)))
+                return fail(ctx, LVIO2D_ERR_ALLOC, "cudaMalloc(association grid)");
+            const double gate = ctx->params.assoc_gate > 0 ? ctx->params.assoc_gate : 0.1, md = ctx->params.assoc_max_dist > 0 ? ctx->params.assoc_max_dist : 0.5;
+            assoc_grid_kernel<<<F, 128, 0, ctx->stream>>>(ctx->b_wlines.as<double4>(), ctx->b_wlen.as<double>(), ctx->line_offset, ctx->ref_frame, gate, md,
+                                                          ctx->b_agp.as<double>(), ctx->b_agm.as<unsigned long long>(), F);
+            CK(cudaGetLastError());
+            ctx->assoc_grid = true;
+        }
     }
     if (!async) CK(cudaStreamSynchronize(ctx->stream));  // synchronous flavour: the caller's buffers are free again on return
     {
@@ -536,7 +560,7 @@ void lvio2d_destroy(lvio2d_ctx* ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     DevBuf* all[] = {&ctx->b_points, &ctx->b_pline, &ctx->b_pweight, &ctx->b_poff, &ctx->b_loff, &ctx->b_lines, &ctx->b_ref, &ctx->b_refpose,
-                     &ctx->b_imu, &ctx->b_wheel, &ctx->b_pX0, &ctx->b_pJ, &ctx->b_pH, &ctx->b_cmask, &ctx->b_wr, &ctx->b_wa, &ctx->b_wl, &ctx->b_wi, &ctx->b_x0, &ctx->b_x, &ctx->b_xc, &ctx->b_scale,
+                     &ctx->b_imu, &ctx->b_wheel, &ctx->b_pX0, &ctx->b_pJ, &ctx->b_pH, &ctx->b_cmask, &ctx->b_wr, &ctx->b_wa, &ctx->b_wl, &ctx->b_wi, &ctx->b_agp, &ctx->b_agm, &ctx->b_x0, &ctx->b_x, &ctx->b_xc, &ctx->b_scale,
                      &ctx->b_ftab, &ctx->b_reftab, &ctx->b_wlines, &ctx->b_wlen, &ctx->b_part, &ctx->b_lb, &ctx->b_items, &ctx->b_vec, &ctx->b_fac, &ctx->b_state,
                      &ctx->b_status, &ctx->b_active, &ctx->b_active1, &ctx->b_reduce};
     for (DevBuf* b : all) b->release();
@@ -1067,6 +1091,13 @@ int lvio2d_match_lines(lvio2d_ctx* ctx, const lvio2d_line_params* lp, int32_t n_
                 const int64_t end = point_count1 ? point_offset1[p] + point_count1[p] : point_offset1[p + 1];
                 if (end < point_offset1[p] || point_offset1[p] < 0) return fail(ctx, LVIO2D_ERR_INVALID_ARG, "offsets must be non-decreasing");
                 N1 = std::max(N1, end);
+                // every line's point range must lie inside its scan (host buffers only; device buffers are clamped by the kernel)
+                const int64_t cnt = end - point_offset1[p];
+                const int32_t nl = std::min(n_lines1[p], max_lines1);
+                for (int32_t l = 0; l < nl; ++l) {
+                    const int32_t* r = index_range1 + ((size_t)p * max_lines1 + l) * 2;
+                    if (r[0] < 0 || r[1] < r[0] || r[1] >= cnt) return fail(ctx, LVIO2D_ERR_INVALID_ARG, "index_range1 outside the scan's points");
+                }
             }
         }
     }
@@ -1254,15 +1285,23 @@ int pg_setup(lvio2d_ctx* ctx, pg::Args& a, int32_t n_poses, const double* poses,
 
 extern "C" {
 int lvio2d_pose_graph_solve(lvio2d_ctx* ctx, int32_t n_poses, double* poses, int32_t n_edges, const int32_t* edge_index, const double* edge_tf,
-                            const double* edge_weight, const double* sqrt_info, int32_t ground_p, int32_t ground_q, lvio2d_summary* summary) {
+                            const double* edge_weight, const double* sqrt_info, int32_t ground_p, int32_t ground_q, int32_t fixed_pose,
+                            lvio2d_summary* summary) {
     if (!ctx) return LVIO2D_ERR_INVALID_ARG;
     if (n_poses <= 0 || n_edges < 0 || !poses || !sqrt_info || (n_edges > 0 && (!edge_index || !edge_tf || !edge_weight)))
         return fail(ctx, LVIO2D_ERR_INVALID_ARG, "pose graph: null or empty argument");
+    if (fixed_pose < -1 || fixed_pose >= n_poses) return fail(ctx, LVIO2D_ERR_INVALID_ARG, "pose graph: fixed_pose out of range");
     for (int64_t i = 0; i < 6 * (int64_t)n_poses; ++i)
         if (!std::isfinite(poses[i])) return fail(ctx, LVIO2D_ERR_DOMAIN, "pose graph: non-finite pose");
+    for (int64_t i = 0; i < 12 * (int64_t)n_edges; ++i)
+        if (!std::isfinite(edge_tf[i])) return fail(ctx, LVIO2D_ERR_DOMAIN, "pose graph: non-finite edge transform");
+    for (int64_t i = 0; i < n_edges; ++i)
+        if (!std::isfinite(edge_weight[i])) return fail(ctx, LVIO2D_ERR_DOMAIN, "pose graph: non-finite edge weight");
+    for (int i = 0; i < 36; ++i)
+        if (!std::isfinite(sqrt_info[i])) return fail(ctx, LVIO2D_ERR_DOMAIN, "pose graph: non-finite sqrt_info");
     CK(cudaSetDevice(ctx->device));
     pg::Args a;
-    const int rc = pg_setup(ctx, a, n_poses, poses, n_edges, edge_index, edge_tf, edge_weight, sqrt_info, ground_p, ground_q, n_edges > 0 ? edge_index[0] : -1);
+    const int rc = pg_setup(ctx, a, n_poses, poses, n_edges, edge_index, edge_tf, edge_weight, sqrt_info, ground_p, ground_q, fixed_pose);
     if (rc != LVIO2D_OK) return rc;
     pg::Options opt;
     opt.max_iters = ctx->opt.max_iters; opt.function_tolerance = ctx->opt.function_tolerance; opt.gradient_tolerance = ctx->opt.gradient_tolerance;

@@ -498,7 +498,8 @@ LV_HD void body_cost(const Args& a, int t) {
         const double* yk = a.y + 6 * k;
         double rp, rq;
         ground_residuals<double>(a.C, load3(yk), load3(yk + 3), &rp, &rq);
-        a.part[part_offset(a, S_COST) + t] = (a.ground_p ? rp * rp : 0.0) + (a.ground_q ? rq * rq : 0.0);
+        // (the ground factors of the constant key frame have no variable block: Ceres counts them as fixed cost)
+        a.part[part_offset(a, S_COST) + t] = k == a.fixed ? 0.0 : (a.ground_p ? rp * rp : 0.0) + (a.ground_q ? rq * rq : 0.0);
         double n2 = 0.0, s2 = 0.0;
         if (k != a.fixed)
             for (int q = 0; q < 6; ++q) { n2 += yk[q] * yk[q]; const double d = a.x[6 * k + q] - yk[q]; s2 += d * d; }

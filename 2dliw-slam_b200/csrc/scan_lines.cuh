@@ -440,9 +440,11 @@ __global__ void __launch_bounds__(128) match_lines_kernel(MatchLinesArgs a) {
 
     // packed cells of scan 1's points
     int64_t q0 = 0;
+    int np1 = 0;    // points of scan 1: index ranges are clamped to it (device buffers are not validated on the host)
     if (a.points1) {
         q0 = a.point_offset1[p];
         const int np = a.point_count1 ? a.point_count1[p] : (int)(a.point_offset1[p + 1] - q0);
+        np1 = np;
         for (int i = lane; i < np; i += 32) { const double2 q = a.points1[q0 + i]; a.cells[q0 + i] = match_cell(a, q.x, q.y); }
         __syncwarp();
     }
@@ -457,7 +459,7 @@ __global__ void __launch_bounds__(128) match_lines_kernel(MatchLinesArgs a) {
             rmin = min(rmin, r); rmax = max(rmax, r); cmin = min(cmin, c); cmax = max(cmax, c);
         };
         if (a.points1) {
-            for (int q = R1[2 * j]; q <= R1[2 * j + 1]; ++q) grow(a.cells[q0 + q]);
+            for (int q = max(R1[2 * j], 0); q <= min(R1[2 * j + 1], np1 - 1); ++q) grow(a.cells[q0 + q]);
         } else {
             const double4 l1 = L1[j];
             const double dx = l1.z - l1.x, dy = l1.w - l1.y, len = sqrt(dx * dx + dy * dy);
@@ -489,7 +491,7 @@ __global__ void __launch_bounds__(128) match_lines_kernel(MatchLinesArgs a) {
             };
             const double4 l1 = L1[j];
             if (a.points1) {
-                for (int q = R1[2 * j]; q <= R1[2 * j + 1]; ++q) cover(a.cells[q0 + q]);
+                for (int q = max(R1[2 * j], 0); q <= min(R1[2 * j + 1], np1 - 1); ++q) cover(a.cells[q0 + q]);
             } else {
                 const double dx = l1.z - l1.x, dy = l1.w - l1.y, len = sqrt(dx * dx + dy * dy);
                 double ux = dx, uy = dy;

@@ -47,7 +47,7 @@ constexpr int kAccFree = 45;    // [0..14] as above | [15..20] a x bi | [21..26]
 constexpr int kPadTrack = 24;
 constexpr int kPadFree = 48;
 constexpr int kRowTrack = 14;   // f(3) e(9) n(2)
-constexpr int kRowTrackAssoc = 18;  // + h(3) (foot coordinate along the line, relative to A1) + length
+constexpr int kRowTrackAssoc = 20;  // + h(3) (foot coordinate along the line, relative to A1) + length + (d, s1): the line in the map frame
 constexpr int kRowFree = 24;    // + h(3) (relative to A2) alpha(3) beta(3) + length
 
 struct ScanMatchArgs {
@@ -71,7 +71,17 @@ struct ScanMatchArgs {
     int32_t shard_rank, shard_world;
     int32_t uniform_pts, uniform_lines;   // > 0: every frame has exactly this many points / lines (offsets are f * count)
     double huber_delta, laser_sqrt_info, assoc_gate, assoc_max_dist;
+    // in-kernel re-association (BASELINE config 3): per frame a kAssocG x kAssocG grid over the world bounding box of the
+    // frame's local map, every cell holding the bit mask of the lines a point inside it can possibly match (built once
+    // per upload by assoc_grid_kernel); null: every point tests every line
+    const double* assoc_grid_par;        // [F][4]  x0, y0, 1 / cell_x, 1 / cell_y   (1 / cell_x == 0: no grid for this frame)
+    const unsigned long long* assoc_grid_mask;   // [F][kAssocG * kAssocG][2]
 };
+#ifndef LV_ASSOC_G
+#define LV_ASSOC_G 16
+#endif
+constexpr int kAssocG = LV_ASSOC_G;
+constexpr int kAssocGridDoubles = kAssocG * kAssocG * 2;   // shared-memory copy per warp (as 64-bit words)
 
 // streamed (read-once) loads: no L1 allocation.  (An L2 evict_first cache-hint policy on these loads and
 // prefetch.global.L2 ahead of the pipeline were both measured and made no difference / were slower; see DESIGN.md.)
@@ -229,6 +239,8 @@ __device__ __forceinline__ void scan_match_item(const ScanMatchArgs& a, const in
                     r[15] = ux * T[1] + uy * T[3];
                     r[16] = ux * T[4] + uy * T[5] - wl.w;
                     r[17] = a.wlen[l0 + l];
+                    r[18] = wl.z;      // the same line in the frame the points are mapped to by (T[0..5]): n.P = d, u.P - s1 in [0, len]
+                    r[19] = wl.w;
                 }
               }
             }
@@ -278,6 +290,22 @@ __device__ __forceinline__ void scan_match_item(const ScanMatchArgs& a, const in
             }
         }
     }
+    // in-kernel association: this frame's candidate grid next to the line table
+    bool use_grid = false;
+    double gx0 = 0.0, gy0 = 0.0, gix = 0.0, giy = 0.0;
+    unsigned long long* gmask = reinterpret_cast<unsigned long long*>(tab + (size_t)a.line_cap * ROW);
+    if constexpr (ASSOC && !REF_FREE) {
+        if (a.assoc_grid_par) {
+            const double* gp = a.assoc_grid_par + (size_t)f * 4;
+            gx0 = gp[0]; gy0 = gp[1]; gix = gp[2]; giy = gp[3];
+            use_grid = gix > 0.0;
+            if (use_grid) {
+                const unsigned long long* src = a.assoc_grid_mask + (size_t)f * kAssocGridDoubles;
+#pragma unroll
+                for (int q = 0; q < kAssocGridDoubles / 32; ++q) gmask[lane + 32 * q] = __ldg(src + lane + 32 * q);
+            }
+        }
+    }
     __syncwarp();
 
     double acc[NACC];
@@ -294,11 +322,12 @@ __device__ __forceinline__ void scan_match_item(const ScanMatchArgs& a, const in
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             if (li[u] < 0) continue;
+            if constexpr (!ASSOC) { if (li[u] >= nl) continue; }   // an index beyond the frame's line list takes no part (never an out-of-table read)
             if constexpr (ASSOC) {
                 // nearest line by perpendicular distance among the lines whose extent (+gate) contains the foot
                 int best = -1;
                 double best_d = a.assoc_max_dist;
-                for (int l = 0; l < nl; ++l) {
+                auto test_line = [&](const int l) {
                     const double* q = tab + l * ROW;
                     const double dd = fma(q[0], c[u].x, fma(q[1], c[u].y, q[2]));
                     double tt = fma(q[14], c[u].x, fma(q[15], c[u].y, q[16]));
@@ -306,6 +335,34 @@ __device__ __forceinline__ void scan_match_item(const ScanMatchArgs& a, const in
                     if constexpr (REF_FREE) tt += len;   // h is relative to A2 there
                     const double ad = fabs(dd);
                     if (tt >= -a.assoc_gate && tt <= len + a.assoc_gate && ad < best_d) { best_d = ad; best = l; }
+                };
+                if constexpr (!REF_FREE) {
+                    // the point in the frame the lines live in; a candidate costs 3 wide loads and 4 FMAs there
+                    const double X = fma(T[0], c[u].x, fma(T[1], c[u].y, T[4])), Y = fma(T[2], c[u].x, fma(T[3], c[u].y, T[5]));
+                    auto test_world = [&](const int l) {
+                        const double* q = tab + l * ROW;
+                        const double2 nn = *reinterpret_cast<const double2*>(q + 12);
+                        const double2 ds = *reinterpret_cast<const double2*>(q + 18);
+                        const double len = q[17];
+                        const double dd = fma(nn.x, X, fma(nn.y, Y, -ds.x));
+                        const double tt = fma(nn.y, X, fma(-nn.x, Y, -ds.y));
+                        const double ad = fabs(dd);
+                        if (tt >= -a.assoc_gate && tt <= len + a.assoc_gate && ad < best_d) { best_d = ad; best = l; }
+                    };
+                    if (use_grid) {
+                        // only the lines registered in the point's cell — in increasing line order, so that ties resolve
+                        // exactly like the all-lines loop
+                        const double gx = (X - gx0) * gix, gy = (Y - gy0) * giy;
+                        if (!(gx >= 0.0 && gx < (double)kAssocG && gy >= 0.0 && gy < (double)kAssocG)) continue;   // outside every line's reach
+                        const int cell = (int)gy * kAssocG + (int)gx;
+                        unsigned long long m0 = gmask[2 * cell], m1 = gmask[2 * cell + 1];
+                        while (m0) { const int l = __ffsll((long long)m0) - 1; m0 &= m0 - 1; test_world(l); }
+                        while (m1) { const int l = 63 + __ffsll((long long)m1); m1 &= m1 - 1; test_world(l); }
+                    } else {
+                        for (int l = 0; l < nl; ++l) test_world(l);
+                    }
+                } else {
+                    for (int l = 0; l < nl; ++l) test_line(l);
                 }
                 if (best < 0) continue;
                 li[u] = best;
@@ -400,7 +457,7 @@ __global__ void __launch_bounds__(32 * LV_SCAN_WPC, (REF_FREE ? 8 : LV_SCAN_WARP
     const int warp = threadIdx.x >> 5;
     const int item = blockIdx.x * (blockDim.x >> 5) + warp;
     if (item >= a.n_items) return;
-    scan_match_item<REF_FREE, HAS_WEIGHT, ASSOC, HUBER>(a, item, lane, smem + (size_t)warp * a.line_cap * ROW);
+    scan_match_item<REF_FREE, HAS_WEIGHT, ASSOC, HUBER>(a, item, lane, smem + (size_t)warp * (a.line_cap * ROW + ((ASSOC && !REF_FREE) ? kAssocGridDoubles : 0)));
 }
 
 // world lines for frames whose local map hangs under an external constant reference pose: computed once per
@@ -422,6 +479,70 @@ __global__ void world_lines_kernel(const double4* lines, const int64_t* line_off
         wlines[l] = make_double4(nx, ny, nx * A2x + ny * A2y, ux * A1x + uy * A1y);
         wlen[l] = len;
     }
+}
+
+// Candidate grid of the in-kernel association, once per upload: one CTA per frame.  A point P can match line l only when
+// |n.P - d| < max_dist and -gate <= u.P - s1 <= len + gate — a rectangle around the segment.  Every cell that rectangle
+// can touch (separating-axis test of the cell against the two line axes, plus a 1e-6 m safety margin for the rounding of
+// the cell index) gets bit l.  Frames with more than 128 lines keep the all-lines loop (par[2] = 0).
+__global__ void assoc_grid_kernel(const double4* wlines, const double* wlen, const int64_t* line_offset, const int32_t* ref_frame,
+                                  double gate, double max_dist, double* par, unsigned long long* mask, int n_frames_total) {
+    const int f = blockIdx.x;
+    if (f >= n_frames_total) return;
+    __shared__ unsigned long long sm[kAssocGridDoubles];
+    __shared__ double red[4][32];
+    double* gp = par + (size_t)f * 4;
+    const int64_t l0 = line_offset[f];
+    const int nl = (int)(line_offset[f + 1] - l0);
+    const int tid = threadIdx.x;
+    for (int k = tid; k < kAssocGridDoubles; k += blockDim.x) sm[k] = 0ull;
+    if (nl <= 0 || nl > 128 || (ref_frame && ref_frame[f] >= 0)) {
+        if (tid < 4) gp[tid] = 0.0;
+        for (int k = tid; k < kAssocGridDoubles; k += blockDim.x) mask[(size_t)f * kAssocGridDoubles + k] = 0ull;
+        return;
+    }
+    const double eps = 1e-6, md = max_dist + eps, gt = gate + eps;
+    // bounding box of every line's rectangle
+    double x0 = 1e300, y0 = 1e300, x1 = -1e300, y1 = -1e300;
+    double4 wl = make_double4(0, 0, 0, 0);
+    double len = 0.0;
+    if (tid < nl) {
+        wl = wlines[l0 + tid];
+        len = wlen[l0 + tid];
+        const double nx = wl.x, ny = wl.y, ux = wl.y, uy = -wl.x;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const double s = (k & 1) ? wl.w + len + gt : wl.w - gt, d = (k & 2) ? wl.z + md : wl.z - md;
+            const double px = s * ux + d * nx, py = s * uy + d * ny;
+            x0 = fmin(x0, px); x1 = fmax(x1, px); y0 = fmin(y0, py); y1 = fmax(y1, py);
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        x0 = fmin(x0, __shfl_xor_sync(0xffffffffu, x0, o)); y0 = fmin(y0, __shfl_xor_sync(0xffffffffu, y0, o));
+        x1 = fmax(x1, __shfl_xor_sync(0xffffffffu, x1, o)); y1 = fmax(y1, __shfl_xor_sync(0xffffffffu, y1, o));
+    }
+    if ((tid & 31) == 0) { red[0][tid >> 5] = x0; red[1][tid >> 5] = y0; red[2][tid >> 5] = x1; red[3][tid >> 5] = y1; }
+    __syncthreads();
+    const int nw = blockDim.x >> 5;
+    x0 = red[0][0]; y0 = red[1][0]; x1 = red[2][0]; y1 = red[3][0];
+    for (int k = 1; k < nw; ++k) { x0 = fmin(x0, red[0][k]); y0 = fmin(y0, red[1][k]); x1 = fmax(x1, red[2][k]); y1 = fmax(y1, red[3][k]); }
+    x0 -= eps; y0 -= eps; x1 += eps; y1 += eps;
+    const double cx = (x1 - x0) / kAssocG, cy = (y1 - y0) / kAssocG;
+    if (tid < nl) {
+        const double nx = wl.x, ny = wl.y, ux = wl.y, uy = -wl.x;
+        const double rn = 0.5 * (fabs(nx) * cx + fabs(ny) * cy) + eps, ru = 0.5 * (fabs(ux) * cx + fabs(uy) * cy) + eps;   // half extents of a cell on the two axes
+        for (int gy = 0; gy < kAssocG; ++gy)
+            for (int gx = 0; gx < kAssocG; ++gx) {
+                const double px = x0 + (gx + 0.5) * cx, py = y0 + (gy + 0.5) * cy;
+                const double dn = fabs(nx * px + ny * py - wl.z), su = ux * px + uy * py - wl.w;
+                if (dn <= md + rn && su >= -gt - ru && su <= len + gt + ru)
+                    atomicOr(&sm[2 * (gy * kAssocG + gx) + (tid >> 6)], 1ull << (tid & 63));
+            }
+    }
+    __syncthreads();
+    for (int k = tid; k < kAssocGridDoubles; k += blockDim.x) mask[(size_t)f * kAssocGridDoubles + k] = sm[k];
+    if (tid == 0) { gp[0] = x0; gp[1] = y0; gp[2] = 1.0 / cx; gp[3] = 1.0 / cy; }
 }
 
 }  // namespace lv

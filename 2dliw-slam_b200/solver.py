@@ -95,7 +95,7 @@ def load_library(path=LIB_PATH):
     lib.lvio2d_measure_fp64_peak.argtypes = [vp, dp]
     lib.lvio2d_set_max_iterations.argtypes = [vp, C.c_int32]
     lib.lvio2d_set_windows_wire.argtypes = [vp, C.POINTER(abi.WindowBatch), C.POINTER(abi.ScanWireStruct), C.c_int32]
-    lib.lvio2d_pose_graph_solve.argtypes = [vp, C.c_int32, dp, C.c_int32, abi.c_int32_p, dp, dp, dp, C.c_int32, C.c_int32, vp]
+    lib.lvio2d_pose_graph_solve.argtypes = [vp, C.c_int32, dp, C.c_int32, abi.c_int32_p, dp, dp, dp, C.c_int32, C.c_int32, C.c_int32, vp]
     lib.lvio2d_eval_edge_factor.argtypes = [vp, dp, C.c_double, dp, dp, dp, dp, dp]
     _lib = lib
     return lib
@@ -407,8 +407,9 @@ class Context:
                     "lvio2d_eval_edge_factor")
         return res, jac
 
-    def pose_graph_solve(self, poses, edge_index, edge_tf, edge_weight, sqrt_info, ground_p=True, ground_q=True):
-        """keyframe_manager::solve (keyframe_manager.cpp:722-838) on the device: returns (poses [K][6], summary)."""
+    def pose_graph_solve(self, poses, edge_index, edge_tf, edge_weight, sqrt_info, ground_p=True, ground_q=True, fixed_pose=None):
+        """keyframe_manager::solve (keyframe_manager.cpp:722-838) on the device: returns (poses [K][6], summary).
+        fixed_pose: the constant key frame (-1: none); None = index1 of the first edge, the reference's seq_edges[0]."""
         x = np.array(poses, dtype=np.float64).reshape(-1, 6).copy()
         ei = np.ascontiguousarray(edge_index, dtype=np.int32).reshape(-1, 2)
         et = _f64(edge_tf).reshape(-1, 12)
@@ -420,7 +421,8 @@ class Context:
             raise ValueError("sqrt_info is edge_noise::J, 6x6")
         summ = np.zeros(1, dtype=abi.SUMMARY_DTYPE)
         self._check(self.lib.lvio2d_pose_graph_solve(self._h, len(x), _d(x), len(ei), ei.ctypes.data_as(abi.c_int32_p), _d(et), _d(ew), _d(Jn),
-                                                     int(bool(ground_p)), int(bool(ground_q)), summ.ctypes.data_as(C.c_void_p)),
+                                                     int(bool(ground_p)), int(bool(ground_q)),
+                                                     (int(ei[0, 0]) if len(ei) else -1) if fixed_pose is None else int(fixed_pose), summ.ctypes.data_as(C.c_void_p)),
                     "lvio2d_pose_graph_solve")
         return x, summ
 

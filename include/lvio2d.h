@@ -358,11 +358,15 @@ int lvio2d_match_lines(lvio2d_ctx* ctx, const lvio2d_line_params* lp, int32_t n_
  * edges between neighbours (|index1 - index2| = 1) form the block-tridiagonal part, all others (loop_edges) enter as
  * rank-6 updates.  edge_tf: [n_edges][12] tf12 row-major 3x4.  edge_weight: [n_edges] (1 for seq_edges, loop_edge_k
  * for loop_edges, :734, :780).  sqrt_info: edge_noise::J row-major 6x6 (edge_factor.h:14-26; the caller builds it,
- * including the reference's J(1,2) slip if it wants the reference's numbers).  LVIO2D_ERR_INVALID_ARG for an index
- * out of range or a self edge. ---- */
+ * including the reference's J(1,2) slip if it wants the reference's numbers).  fixed_pose: the key frame held constant, -1
+ * for none — the reference calls SetParameterBlockConstant on seq_edges[0]->index1 inside its seq_edges loop only
+ * (:744-748), so a graph without sequential edges has none.  Ceres drops the residual blocks whose parameter blocks are
+ * all constant from the reduced program: the ground factors of the fixed key frame count as fixed cost, not in the
+ * function-tolerance test.  LVIO2D_ERR_INVALID_ARG for an index out of range or a self edge, LVIO2D_ERR_DOMAIN for a
+ * non-finite pose, transform, weight or sqrt_info entry. ---- */
 int lvio2d_pose_graph_solve(lvio2d_ctx* ctx, int32_t n_poses, double* poses, int32_t n_edges, const int32_t* edge_index,
                             const double* edge_tf, const double* edge_weight, const double* sqrt_info, int32_t ground_p,
-                            int32_t ground_q, lvio2d_summary* summary);
+                            int32_t ground_q, int32_t fixed_pose, lvio2d_summary* summary);
 /* edge_factor through auto_diff::compute_res_and_jacobi (common.h:201-217): res[6], jac[6][12] row-major over
  * (p_i, q_i, p_j, q_j). */
 int lvio2d_eval_edge_factor(lvio2d_ctx* ctx, const double* tf12, double weight, const double* sqrt_info,

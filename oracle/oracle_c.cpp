@@ -300,10 +300,10 @@ int oracle_eval_edge_factor(const double* tf12 /*3x4 row-major*/, double weight,
 }
 int oracle_pose_graph_solve(const lvio2d_params* p, int32_t n_poses, double* poses /*[K][6] in/out*/, int32_t n_edges, const int32_t* edge_index,
                             const double* edge_tf /*[E][12]*/, const double* edge_weight, const double* sqrt_info, int32_t ground_p,
-                            int32_t ground_q, lvio2d_summary* summary) {
+                            int32_t ground_q, int32_t fixed_pose, lvio2d_summary* summary) {
     Params P(*p);
     posegraph::Graph G;
-    G.P = &P; G.K = n_poses; G.Jn = sqrt_info; G.ground_p = ground_p != 0; G.ground_q = ground_q != 0;
+    G.P = &P; G.K = n_poses; G.Jn = sqrt_info; G.ground_p = ground_p != 0; G.ground_q = ground_q != 0; G.fixed = fixed_pose;
     for (int e = 0; e < n_edges; ++e)
         G.edges.push_back(posegraph::Edge{edge_index[2 * e], edge_index[2 * e + 1], iso_from_rowmajor_3x4(edge_tf + 12 * (size_t)e), edge_weight[e]});
     const lvio2d_summary S = posegraph::solve(G, lm_options_from(*p), poses);

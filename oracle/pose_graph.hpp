@@ -45,6 +45,8 @@ struct Graph {
     std::vector<Edge> edges;
     const double* Jn;
     bool ground_p, ground_q;
+    int fixed = -2;   // constant key frame; -1: none; -2: index1 of the first edge (the reference's seq_edges[0], keyframe_manager.cpp:744-748)
+    int fixed_pose() const { return fixed == -2 ? (edges.empty() ? -1 : edges[0].i1) : fixed; }
 };
 
 struct Problem {
@@ -83,7 +85,7 @@ struct Problem {
             lin->g.assign(dimv, 0.0);
             lin->free_col.assign(dimv, 1);
             // the first sequential edge's index1 is held constant; the reference always builds edges from key frame 0
-            if (!G.edges.empty()) for (int k = 0; k < 6; ++k) lin->free_col[6 * G.edges[0].i1 + k] = 0;
+            if (G.fixed_pose() >= 0) for (int k = 0; k < 6; ++k) lin->free_col[6 * G.fixed_pose() + k] = 0;
         }
         double sumsq = 0.0;
         for (const Edge& e : G.edges) {
@@ -103,6 +105,7 @@ struct Problem {
         }
         for (int i = 0; i < G.K; ++i) {
             const double* xi = x + 6 * i;
+            if (i == G.fixed_pose()) continue;   // no variable block: Ceres moves these residual blocks to the fixed cost
             for (int which = 0; which < 2; ++which) {
                 if (which == 0 ? !G.ground_p : !G.ground_q) continue;
                 double r[1], J[6];

@@ -59,7 +59,8 @@ namespace lvio2d_shim
                 Jn[6 * r + c] = J(r, c);
         lvio2d_summary summary;
         const int rc = lvio2d_pose_graph_solve(ctx, K, poses.data(), E, index.data(), tf.data(), weight.data(), Jn,
-                                               PARAM(use_ground_p_factor) ? 1 : 0, PARAM(use_ground_q_factor) ? 1 : 0, &summary);
+                                               PARAM(use_ground_p_factor) ? 1 : 0, PARAM(use_ground_q_factor) ? 1 : 0,
+                                               seq_edges.empty() ? -1 : seq_edges[0]->index1, &summary); // SetParameterBlockConstant only inside the seq_edges loop, :744-748
         if (rc != LVIO2D_OK)
             throw std::runtime_error(std::string("lvio2d_pose_graph_solve: ") + lvio2d_strerror(rc) + " (" + lvio2d_last_error(ctx) + ")");
         for (int i = 0; i < K; i++) // Ceres writes through the raw parameter pointers

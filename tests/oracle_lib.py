@@ -261,15 +261,17 @@ def eval_edge_factor(tf12, weight, sqrt_info, pose_i, pose_j):
     return res, jac
 
 
-def pose_graph_solve(params, poses, edge_index, edge_tf, edge_weight, sqrt_info, ground_p=True, ground_q=True):
-    """keyframe_manager::solve (keyframe_manager.cpp:722-838): returns the optimised poses [K][6] and the summary."""
+def pose_graph_solve(params, poses, edge_index, edge_tf, edge_weight, sqrt_info, ground_p=True, ground_q=True, fixed_pose=None):
+    """keyframe_manager::solve (keyframe_manager.cpp:722-838): returns the optimised poses [K][6] and the summary.
+    fixed_pose: the constant key frame (-1: none); None = index1 of the first edge (the reference's seq_edges[0])."""
     x = np.array(poses, dtype=np.float64).reshape(-1, 6).copy()
     ei = np.ascontiguousarray(edge_index, dtype=np.int32).reshape(-1, 2)
     et = _arr(edge_tf).reshape(-1, 12)
     ew = _arr(edge_weight).reshape(-1)
     summ = np.zeros(1, dtype=abi.SUMMARY_DTYPE)
     rc = lib().oracle_pose_graph_solve(C.byref(params), len(x), _d(x), len(ei), ei.ctypes.data_as(abi.c_int32_p), _d(et), _d(ew),
-                                       _d(_arr(sqrt_info).reshape(-1)), int(ground_p), int(ground_q), summ.ctypes.data_as(C.c_void_p))
+                                       _d(_arr(sqrt_info).reshape(-1)), int(ground_p), int(ground_q),
+                                       (int(ei[0, 0]) if len(ei) else -1) if fixed_pose is None else int(fixed_pose), summ.ctypes.data_as(C.c_void_p))
     assert rc == 0
     return x, summ
 

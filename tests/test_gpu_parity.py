@@ -305,6 +305,70 @@ def test_huber_and_in_kernel_association_match_oracle(oracle, case, huber, assoc
         assert oracle.cost(P, hb)[0] < oracle.cost(P0, hb)[0]
 
 
+def test_out_of_range_correspondences(oracle):
+    """A point_line index beyond its frame's line list: rejected on the host-buffer path (LVIO2D_ERR_INVALID_ARG); on a path
+    the host cannot scan (here: the wire encoding) the kernel skips the point instead of reading outside its line table."""
+    from lvio2d_b200 import abi
+    from lvio2d_b200.solver import Context, Lvio2dError
+
+    P = L.corridor_params(max_iters=4)
+    hb = oracle.preintegrate_batch(P, L.synth.make_batch(1, 5, n_frames=4, beams=361, fov_deg=270.0))
+    pl = hb["point_line"].copy()
+    nl = int(np.diff(hb["line_offset"])[1])
+    k = int(hb["point_offset"][1]) + 3
+    pl[k] = nl + 7
+    with Context(P) as c:
+        with pytest.raises(Lvio2dError) as e:
+            c.set_windows(hb.replace(point_line=pl))
+        assert e.value.status == abi.ERR_INVALID_ARG
+        # the same batch with that point dropped is what the guarded kernel must compute
+        drop = pl.copy()
+        drop[k] = -1
+        c.set_windows(hb.replace(point_line=drop))
+        H0, g0, c0 = c.linearize(0)
+    if np.all(np.diff(hb["point_offset"]) == 361):
+        import math
+        wire = abi.ScanWire.from_points(hb, 361, np.float32(math.radians(-135.0)), np.float32(math.radians(270.0) / 360))
+        wire.beam_line.reshape(-1)[k] = nl + 7
+        pts, line, off = wire.points()
+        line[k] = -1
+        with Context(P) as c:
+            c.set_windows_wire(hb.replace(points=None, point_line=None, point_offset=None), wire)
+            H1, g1, c1 = c.linearize(0)
+            c.set_windows(hb.replace(points=pts, point_line=line, point_offset=off))
+            H2, g2, c2 = c.linearize(0)
+        assert np.array_equal(H1, H2) and np.array_equal(g1, g2) and np.array_equal(c1, c2)
+
+
+def test_association_grid_equals_the_all_lines_loop(oracle, monkeypatch):
+    """BASELINE config 3: the precomputed candidate grid (16 x 16 cells over the local map, one bit per line) must pick
+    exactly the line the all-lines loop picks — bit-identical normal equations and states, with ragged line counts, points
+    outside the map and a gate / cut-off other than the defaults."""
+    from lvio2d_b200.solver import Context
+
+    for gate, md in ((0.0, 0.0), (0.03, 0.2)):
+        P = L.corridor_params(max_iters=6)
+        P.assoc_mode = 1
+        P.assoc_gate, P.assoc_max_dist = gate, md
+        sb = L.synth.make_batch(3, 11, n_frames=6, beams=400, fov_deg=270.0)
+        hb = oracle.preintegrate_batch(P, sb)
+        pts = hb["points"].reshape(-1, 2).copy()
+        pts[::37] *= 40.0                                 # a few points far outside the map
+        hb = hb.replace(points=pts)
+        res = {}
+        for grid in ("1", "0"):
+            monkeypatch.setenv("LVIO2D_ASSOC_GRID", grid)
+            with Context(P) as c:
+                c.set_windows(hb)
+                H, g, cost = c.linearize(0)
+                c.solve()
+                res[grid] = (H, g, cost, c.get_states())
+        for a, b in zip(res["1"], res["0"]):
+            assert np.array_equal(a, b)
+        want, _ = oracle.solve(P, hb)
+        assert np.abs(res["1"][3] - want).max() < 1e-8
+
+
 def test_paired_and_single_factor_kernels_agree(oracle, monkeypatch):
     """factor_pair_kernel (two items per warp, 12 dual columns + 15 closed-form columns; the default) against factor_kernel
     (one item per warp, all 30 columns in dual arithmetic): same normal equations, same solve."""

@@ -150,11 +150,12 @@ def test_keyframe_manager_mirror_on_a_recording_context():
     constant key frame; weights 1 / loop_edge_k; in-place write-back) — the compute call is recorded, not executed."""
     from lvio2d_b200.backend import Edge, KeyFrame, KeyframeManager, edge_noise_J as product_J
 
-    calls = []
+    calls, fixed = [], []
 
     class Recorder:
-        def pose_graph_solve(self, poses, index, tfs, weights, Jn, gp, gq):
+        def pose_graph_solve(self, poses, index, tfs, weights, Jn, gp, gq, fixed_pose=None):
             calls.append((poses.copy(), index.copy(), tfs.copy(), weights.copy(), Jn.copy(), gp, gq))
+            fixed.append(fixed_pose)
             return poses + 1.0, np.zeros(1, dtype=abi.SUMMARY_DTYPE)
 
     km = KeyframeManager(Recorder(), loop_edge_k=7.0, use_ground_q_factor=False)
@@ -170,6 +171,10 @@ def test_keyframe_manager_mirror_on_a_recording_context():
     assert (gp, gq) == (True, False)
     assert np.array_equal(Jn, edge_noise_J()) and np.array_equal(Jn, product_J((0.1,) * 3, (0.01,) * 3))
     assert np.array_equal(km.keyframe_queue[2].p, np.full(3, 3.0)) and np.allclose(km.keyframe_queue[2].q, 1.2)
+    assert fixed == [0]                      # seq_edges[0].index1 (keyframe_manager.cpp:744-748)
+    km.seq_edges = []
+    km.solve()
+    assert fixed == [0, -1]                  # loop edges only: the reference holds nothing constant
 
 
 def test_edge_cases_match_oracle(pgh, consts, oracle):
