@@ -337,7 +337,8 @@ def test_out_of_range_correspondences(oracle):
             H1, g1, c1 = c.linearize(0)
             c.set_windows(hb.replace(points=pts, point_line=line, point_offset=off))
             H2, g2, c2 = c.linearize(0)
-        assert np.array_equal(H1, H2) and np.array_equal(g1, g2) and np.array_equal(c1, c2)
+        # (the device's sincos and numpy's cos / sin differ in the last bit of a few points)
+        assert np.abs(H1 - H2).max() <= 1e-12 * np.abs(H2).max() and np.abs(g1 - g2).max() <= 1e-11 * np.abs(g2).max() and np.abs(c1 - c2).max() <= 1e-12 * np.abs(c2).max()
 
 
 def test_association_grid_equals_the_all_lines_loop(oracle, monkeypatch):
