@@ -13,6 +13,7 @@
 #include "../../include/lvio2d.h"
 #include "aux_kernels.cuh"
 #include "scan_lines.cuh"
+#include "submap.cuh"
 #include "pose_graph_segments.cuh"
 #include "peaks.cuh"
 
@@ -1154,6 +1155,174 @@ int lvio2d_match_lines(lvio2d_ctx* ctx, const lvio2d_line_params* lp, int32_t n_
         CK(cudaMemcpyAsync(match, B[14].p, P * max_lines2 * 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));
     }
+    return LVIO2D_OK;
+}
+
+// ---- device-resident reference sub-map (submap.cuh)
+struct lvio2d_submap {
+    lvio2d_ctx* ctx = nullptr;
+    int32_t n_managers = 0, line_cap = 0, n_accumulation = 0;
+    lvio2d_line_params lp{};
+    double filter_p = 0, filter_q = 0;
+    DevBuf meta, sub_pose, last_pose, sub_n, sub_lines;   // state
+    DevBuf in_n, in_lines, in_pose;                       // staging of host scans
+};
+
+static int submap_zero(lvio2d_submap* sm) {
+    lvio2d_ctx* ctx = sm->ctx;
+    CK(cudaMemsetAsync(sm->meta.p, 0, sm->meta.cap, ctx->stream));
+    CK(cudaMemsetAsync(sm->sub_pose.p, 0, sm->sub_pose.cap, ctx->stream));
+    CK(cudaMemsetAsync(sm->last_pose.p, 0, sm->last_pose.cap, ctx->stream));
+    CK(cudaMemsetAsync(sm->sub_n.p, 0, sm->sub_n.cap, ctx->stream));
+    return LVIO2D_OK;
+}
+
+int lvio2d_submap_create(lvio2d_ctx* ctx, int32_t n_managers, int32_t line_cap, const lvio2d_line_params* lp, double ref_motion_filter_p,
+                         double ref_motion_filter_q, int32_t ref_n_accumulation, lvio2d_submap** out) {
+    if (!ctx || !lp || !out || n_managers < 1 || line_cap < 1 || ref_n_accumulation < 1) return LVIO2D_ERR_INVALID_ARG;
+    if (!(lp->laser_resolution > 0.0)) return fail(ctx, LVIO2D_ERR_INVALID_ARG, "laser_resolution must be positive");
+    if (!std::isfinite(ref_motion_filter_p) || !std::isfinite(ref_motion_filter_q)) return fail(ctx, LVIO2D_ERR_INVALID_ARG, "motion filter thresholds must be finite");
+    CK(cudaSetDevice(ctx->device));
+    lvio2d_submap* sm = new (std::nothrow) lvio2d_submap;
+    if (!sm) return fail(ctx, LVIO2D_ERR_ALLOC, "new lvio2d_submap");
+    sm->ctx = ctx; sm->n_managers = n_managers; sm->line_cap = line_cap; sm->n_accumulation = ref_n_accumulation;
+    sm->lp = *lp; sm->filter_p = ref_motion_filter_p; sm->filter_q = ref_motion_filter_q;
+    const size_t M = (size_t)n_managers;
+    const bool ok = sm->meta.ensure(M * 4 * sizeof(int32_t)) && sm->sub_pose.ensure(2 * M * 6 * sizeof(double)) && sm->last_pose.ensure(M * 6 * sizeof(double)) &&
+                    sm->sub_n.ensure(2 * M * sizeof(int32_t)) && sm->sub_lines.ensure(2 * M * (size_t)line_cap * sizeof(double4));
+    if (!ok) { lvio2d_submap_destroy(sm); return fail(ctx, LVIO2D_ERR_ALLOC, "cudaMalloc(submap)"); }
+    const int rc = submap_zero(sm);
+    if (rc != LVIO2D_OK) { lvio2d_submap_destroy(sm); return rc; }
+    *out = sm;
+    return LVIO2D_OK;
+}
+
+void lvio2d_submap_destroy(lvio2d_submap* sm) {
+    if (!sm) return;
+    cudaSetDevice(sm->ctx->device);
+    cudaStreamSynchronize(sm->ctx->stream);
+    DevBuf* all[] = {&sm->meta, &sm->sub_pose, &sm->last_pose, &sm->sub_n, &sm->sub_lines, &sm->in_n, &sm->in_lines, &sm->in_pose};
+    for (DevBuf* b : all) b->release();
+    delete sm;
+}
+
+int lvio2d_submap_reset(lvio2d_submap* sm) {
+    if (!sm) return LVIO2D_ERR_INVALID_ARG;
+    lvio2d_ctx* ctx = sm->ctx;
+    CK(cudaSetDevice(ctx->device));
+    return submap_zero(sm);
+}
+
+int lvio2d_submap_add_scan(lvio2d_submap* sm, int32_t max_lines, const int32_t* n_lines, const double* lines, const double* pose, int32_t on_device) {
+    if (!sm) return LVIO2D_ERR_INVALID_ARG;
+    lvio2d_ctx* ctx = sm->ctx;
+    if (max_lines < 1 || !n_lines || !lines || !pose) return fail(ctx, LVIO2D_ERR_INVALID_ARG, "submap_add_scan: null argument or max_lines < 1");
+    CK(cudaSetDevice(ctx->device));
+    const size_t M = (size_t)sm->n_managers;
+    SubmapArgs a;
+    std::memset(&a, 0, sizeof(a));
+    a.n_managers = sm->n_managers; a.line_cap = sm->line_cap; a.max_lines = max_lines; a.n_accumulation = sm->n_accumulation;
+    a.filter_p = sm->filter_p; a.filter_q = sm->filter_q;
+    std::memcpy(a.T_il, ctx->params.T_imu_to_laser, sizeof(a.T_il));
+    a.line_max_dis = sm->lp.line_max_dis; a.line_min_len = sm->lp.line_min_len; a.resolution = sm->lp.laser_resolution;
+    a.w = (int)(sm->lp.w_laser_each_scan / sm->lp.laser_resolution + 1);
+    a.h = (int)(sm->lp.h_laser_each_scan / sm->lp.laser_resolution + 1);
+    a.meta = sm->meta.as<int32_t>(); a.sub_pose = sm->sub_pose.as<double>(); a.last_pose = sm->last_pose.as<double>();
+    a.sub_n = sm->sub_n.as<int32_t>(); a.sub_lines = sm->sub_lines.as<double4>();
+    if (on_device) {
+        a.n_lines = n_lines; a.lines = reinterpret_cast<const double4*>(lines); a.pose = pose;
+    } else {
+        for (size_t m = 0; m < M; ++m)
+            for (int k = 0; k < 6; ++k)
+                if (n_lines[m] >= 0 && !std::isfinite(pose[6 * m + k])) return fail(ctx, LVIO2D_ERR_INVALID_ARG, "submap_add_scan: pose is not finite");
+        if (!sm->in_n.ensure(M * sizeof(int32_t)) || !sm->in_lines.ensure(M * (size_t)max_lines * sizeof(double4)) || !sm->in_pose.ensure(M * 6 * sizeof(double)))
+            return fail(ctx, LVIO2D_ERR_ALLOC, "cudaMalloc(submap scan)");
+        CK(cudaMemcpyAsync(sm->in_n.p, n_lines, M * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(sm->in_lines.p, lines, M * (size_t)max_lines * sizeof(double4), cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(sm->in_pose.p, pose, M * 6 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        a.n_lines = sm->in_n.as<int32_t>(); a.lines = sm->in_lines.as<double4>(); a.pose = sm->in_pose.as<double>();
+    }
+    const int wpc = 4;
+    submap_add_scan_kernel<<<(sm->n_managers + wpc - 1) / wpc, wpc * 32, 0, ctx->stream>>>(a);
+    ctx->launches += 1;
+    CK(cudaGetLastError());
+    if (!on_device) CK(cudaStreamSynchronize(ctx->stream));   // the staging buffers are the caller's again
+    return LVIO2D_OK;
+}
+
+int lvio2d_submap_get(lvio2d_submap* sm, int32_t which, int32_t* meta, double* pose, int32_t* n_lines, double* lines) {
+    if (!sm) return LVIO2D_ERR_INVALID_ARG;
+    lvio2d_ctx* ctx = sm->ctx;
+    if (which < 0 || which > 1) return fail(ctx, LVIO2D_ERR_INVALID_ARG, "submap_get: which must be 0 (reference) or 1 (spawning)");
+    CK(cudaSetDevice(ctx->device));
+    const size_t M = (size_t)sm->n_managers;
+    if (meta) CK(cudaMemcpyAsync(meta, sm->meta.p, M * 4 * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    if (pose) CK(cudaMemcpyAsync(pose, sm->sub_pose.as<double>() + which * M * 6, M * 6 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    if (n_lines) CK(cudaMemcpyAsync(n_lines, sm->sub_n.as<int32_t>() + which * M, M * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    if (lines)
+        CK(cudaMemcpyAsync(lines, sm->sub_lines.as<double4>() + which * M * sm->line_cap, M * (size_t)sm->line_cap * sizeof(double4), cudaMemcpyDeviceToHost,
+                           ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return LVIO2D_OK;
+}
+
+int lvio2d_submap_device(lvio2d_submap* sm, const int32_t** meta, const double** ref_pose, const int32_t** ref_n_lines, const double** ref_lines) {
+    if (!sm) return LVIO2D_ERR_INVALID_ARG;
+    if (meta) *meta = sm->meta.as<int32_t>();
+    if (ref_pose) *ref_pose = sm->sub_pose.as<double>();
+    if (ref_n_lines) *ref_n_lines = sm->sub_n.as<int32_t>();
+    if (ref_lines) *ref_lines = sm->sub_lines.as<double>();
+    return LVIO2D_OK;
+}
+
+int lvio2d_submap_match(lvio2d_submap* sm, int32_t kk, int32_t max_lines2, const int32_t* n_lines2, const double* lines2, const double* pose2,
+                        int32_t* n_match, int32_t* match, double* matched_lines1, double* ref_pose, int32_t on_device) {
+    if (!sm) return LVIO2D_ERR_INVALID_ARG;
+    lvio2d_ctx* ctx = sm->ctx;
+    if (kk < 0 || kk > 2 || max_lines2 < 1 || !n_lines2 || !lines2 || !pose2 || !n_match || !match)
+        return fail(ctx, LVIO2D_ERR_INVALID_ARG, "submap_match: null argument, max_lines2 < 1 or kk outside 0..2");
+    CK(cudaSetDevice(ctx->device));
+    const size_t P = (size_t)sm->n_managers;
+    const double4* sub_lines = sm->sub_lines.as<double4>();
+    if (on_device) {   // everything is in device memory already: the sampled flavour of lvio2d_match_lines on the resident arrays
+        const int rc = lvio2d_match_lines(ctx, &sm->lp, sm->n_managers, kk, nullptr, nullptr, nullptr, sm->line_cap, sm->sub_n.as<int32_t>(),
+                                          sm->sub_lines.as<double>(), nullptr, max_lines2, n_lines2, lines2, sm->sub_pose.as<double>(), pose2, n_match,
+                                          match, 1);
+        if (rc != LVIO2D_OK) return rc;
+        if (matched_lines1 || ref_pose) {
+            submap_gather_kernel<<<sm->n_managers, 128, 0, ctx->stream>>>(sm->n_managers, sm->line_cap, max_lines2, n_match, match, sub_lines,
+                                                                          sm->sub_pose.as<double>(), reinterpret_cast<double4*>(matched_lines1), ref_pose);
+            ctx->launches += 1;
+            CK(cudaGetLastError());
+        }
+        return LVIO2D_OK;
+    }
+    // scan 2 and its pose go up, the pairs (and the matched sub-map lines) come back; scan 1 is the resident reference sub-map
+    DevBuf* B = ctx->b_ml;
+    if (!B[9].ensure(P * sizeof(int32_t)) || !B[10].ensure(P * max_lines2 * sizeof(double4)) || !B[12].ensure(P * 6 * sizeof(double)) ||
+        !B[13].ensure(P * sizeof(int32_t)) || !B[14].ensure(P * max_lines2 * 2 * sizeof(int32_t)) || !B[7].ensure(P * max_lines2 * sizeof(double4)) ||
+        !B[11].ensure(P * 6 * sizeof(double)))
+        return fail(ctx, LVIO2D_ERR_ALLOC, "cudaMalloc(submap_match)");
+    CK(cudaMemcpyAsync(B[9].p, n_lines2, P * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(B[10].p, lines2, P * max_lines2 * sizeof(double4), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(B[12].p, pose2, P * 6 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemsetAsync(B[14].p, 0, P * max_lines2 * 2 * sizeof(int32_t), ctx->stream));
+    const int rc = lvio2d_match_lines(ctx, &sm->lp, sm->n_managers, kk, nullptr, nullptr, nullptr, sm->line_cap, sm->sub_n.as<int32_t>(),
+                                      sm->sub_lines.as<double>(), nullptr, max_lines2, B[9].as<int32_t>(), B[10].as<double>(), sm->sub_pose.as<double>(),
+                                      B[12].as<double>(), B[13].as<int32_t>(), B[14].as<int32_t>(), 1);
+    if (rc != LVIO2D_OK) return rc;
+    if (matched_lines1 || ref_pose) {
+        submap_gather_kernel<<<sm->n_managers, 128, 0, ctx->stream>>>(sm->n_managers, sm->line_cap, max_lines2, B[13].as<int32_t>(), B[14].as<int32_t>(), sub_lines,
+                                                                      sm->sub_pose.as<double>(), matched_lines1 ? B[7].as<double4>() : nullptr,
+                                                                      ref_pose ? B[11].as<double>() : nullptr);
+        ctx->launches += 1;
+        CK(cudaGetLastError());
+        if (matched_lines1) CK(cudaMemcpyAsync(matched_lines1, B[7].p, P * max_lines2 * sizeof(double4), cudaMemcpyDeviceToHost, ctx->stream));
+        if (ref_pose) CK(cudaMemcpyAsync(ref_pose, B[11].p, P * 6 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    CK(cudaMemcpyAsync(n_match, B[13].p, P * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(match, B[14].p, P * max_lines2 * 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
     return LVIO2D_OK;
 }
 

@@ -106,8 +106,11 @@ class LaserManager:
     the reference's host bookkeeping (key-frame deque, reference sub-map and the one being spawned)."""
 
     def __init__(self, backend, line_params, max_lines=256, params=None, ref_motion_filter_p=0.01, ref_motion_filter_q=0.01,
-                 ref_n_accumulation=100):
+                 ref_n_accumulation=100, device_submap=False, line_cap=16384):
         self._be, self.line_params, self.max_lines = backend, line_params, int(max_lines)
+        # device_submap: the reference sub-map and the spawning one live in device memory (lvio2d_submap_*), add_scan and
+        # match_with_ref become one kernel each and ref_submap_ptr / spawnning_ref_submap_ptr stay None on the host
+        self._dev = backend.submap(line_params, 1, line_cap, ref_motion_filter_p, ref_motion_filter_q, ref_n_accumulation) if device_submap else None
         # config/corridor.yaml:120-122
         self.ref_motion_filter_p, self.ref_motion_filter_q = ref_motion_filter_p, ref_motion_filter_q
         self.ref_n_accumulation = int(ref_n_accumulation)
@@ -155,6 +158,10 @@ class LaserManager:
     def add_scan(self, scan, current_p, current_q):
         """laser_manager::add_scan (laser_manager.cpp:424-496)."""
         self.key_frame.append(LaserSubmap(scan, current_p, current_q))
+        if self._dev is not None:
+            n, lines, _ = self._pack(scan, max(1, len(scan.lines)))
+            self._dev.add_scan(n, lines, np.concatenate([current_p, current_q]))
+            return
         current_tf = _tf(current_p, current_q)
         if self.ref_submap_ptr is not None:
             d = _inv_iso(self.last_add_tf) @ current_tf
@@ -208,6 +215,19 @@ class LaserManager:
         return self.do_match(kf.scan_ptr, scan, kf.current_p, kf.current_q, current_p, current_q)
 
     def match_with_ref(self, scan, current_p, current_q):
+        if self._dev is not None:
+            meta = self._dev.get(0, want_lines=False)[0]
+            if not meta[0, 0]:
+                return self._no_match(scan, current_p, current_q)
+            n2, l2, _ = self._pack(scan, max(1, len(scan.lines)))
+            nm, m, l1, pose = self._dev.match(n2, l2, np.concatenate([current_p, current_q]), want_lines1=True)
+            pairs = m[0, :int(nm[0])]
+            match = LaserMatch([Line([*l1[0, k, 0:2], 0.0], [*l1[0, k, 2:4], 0.0]) for k in range(len(pairs))], [scan.lines[int(i)] for _, i in pairs],
+                               pose[0, 0:3], pose[0, 3:6])
+            match.p2, match.q2 = np.array(current_p, dtype=np.float64), np.array(current_q, dtype=np.float64)
+            match.scan2 = scan
+            match.index_pairs = pairs.copy()
+            return match
         if self.ref_submap_ptr is None:
             return self._no_match(scan, current_p, current_q)
         r = self.ref_submap_ptr

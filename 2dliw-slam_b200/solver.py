@@ -31,7 +31,8 @@ EXPORTS = [
     "lvio2d_wheel_preintegrate", "lvio2d_eval_laser_factor", "lvio2d_eval_imu_factor", "lvio2d_eval_wheel_factor",
     "lvio2d_eval_ground_factors", "lvio2d_set_profiling", "lvio2d_get_profile", "lvio2d_set_windows_async", "lvio2d_get_states_async",
     "lvio2d_extract_lines", "lvio2d_scan_to_points", "lvio2d_match_lines", "lvio2d_pose_graph_solve", "lvio2d_eval_edge_factor",
-    "lvio2d_measure_fp64_peak", "lvio2d_set_max_iterations", "lvio2d_set_windows_wire",
+    "lvio2d_measure_fp64_peak", "lvio2d_set_max_iterations", "lvio2d_set_windows_wire", "lvio2d_submap_create", "lvio2d_submap_destroy",
+    "lvio2d_submap_reset", "lvio2d_submap_add_scan", "lvio2d_submap_get", "lvio2d_submap_device", "lvio2d_submap_match",
 ]
 
 
@@ -91,6 +92,14 @@ def load_library(path=LIB_PATH):
                                        abi.c_int32_p, dp, abi.c_int32_p, C.c_int32, abi.c_int32_p, dp, dp, dp, abi.c_int32_p, abi.c_int32_p,
                                        C.c_int32]
     lib.lvio2d_scan_to_points.argtypes = [vp, C.c_int32, C.c_int32, vp, vp, C.c_int32, abi.c_int32_p, dp, dp, dp, C.c_int32]
+    lib.lvio2d_submap_create.argtypes = [vp, C.c_int32, C.c_int32, C.POINTER(abi.LineParams), C.c_double, C.c_double, C.c_int32, C.POINTER(vp)]
+    lib.lvio2d_submap_destroy.argtypes = [vp]
+    lib.lvio2d_submap_destroy.restype = None
+    lib.lvio2d_submap_reset.argtypes = [vp]
+    lib.lvio2d_submap_add_scan.argtypes = [vp, C.c_int32, vp, vp, vp, C.c_int32]
+    lib.lvio2d_submap_get.argtypes = [vp, C.c_int32, abi.c_int32_p, dp, abi.c_int32_p, dp]
+    lib.lvio2d_submap_device.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]
+    lib.lvio2d_submap_match.argtypes = [vp, C.c_int32, C.c_int32, vp, vp, vp, vp, vp, vp, vp, C.c_int32]
     lib.lvio2d_get_profile.argtypes = [vp, dp]
     lib.lvio2d_measure_fp64_peak.argtypes = [vp, dp]
     lib.lvio2d_set_max_iterations.argtypes = [vp, C.c_int32]
@@ -353,6 +362,10 @@ class Context:
             _d(s1), _d(s2), nm.ctypes.data_as(i32), match.ctypes.data_as(i32), 0), "lvio2d_match_lines")
         return nm, match
 
+    def submap(self, line_params, n_managers=1, line_cap=16384, ref_motion_filter_p=0.01, ref_motion_filter_q=0.01, ref_n_accumulation=100):
+        """A batch of device-resident reference sub-maps (laser_manager::add_scan / match_with_ref), see Submap."""
+        return Submap(self, line_params, n_managers, line_cap, ref_motion_filter_p, ref_motion_filter_q, ref_n_accumulation)
+
     def scan_to_points(self, ranges, headers, deskew=True, want_times=False):
         """convert::laser_to_point_times + sensor::laser::correct for a batch of scans (host buffers).  ranges [S][n_beams]
         float32, headers: numpy array of abi.SCAN_HEADER_DTYPE.  Returns point_count [S], points [S][n_beams][2],
@@ -429,6 +442,76 @@ class Context:
 
 # ------------------------------------------------------------------------------------------------------
 # The reference's solver surface
+class Submap:
+    """lvio2d_submap: the reference sub-map and the one being spawned of `n_managers` independent laser managers, kept in
+    device memory (reference state: laser_manager.h ref_submap_ptr / spawnning_ref_submap_ptr / last_add_tf /
+    current_count; transitions: laser_manager.cpp:424-496).  Host-buffer flavour of the C entry points; the device-pointer
+    flavour (on_device = 1) is reached through add_scan_device / match_device."""
+
+    def __init__(self, ctx, line_params, n_managers, line_cap, filter_p, filter_q, n_accumulation):
+        self._ctx, self.n_managers, self.line_cap = ctx, int(n_managers), int(line_cap)
+        self._h = C.c_void_p()
+        ctx._check(ctx.lib.lvio2d_submap_create(ctx._h, self.n_managers, self.line_cap, C.byref(line_params), float(filter_p), float(filter_q),
+                                                int(n_accumulation), C.byref(self._h)), "lvio2d_submap_create")
+
+    def close(self):
+        if self._h:
+            self._ctx.lib.lvio2d_submap_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def reset(self):
+        self._ctx._check(self._ctx.lib.lvio2d_submap_reset(self._h), "lvio2d_submap_reset")
+
+    def add_scan(self, n_lines, lines, pose):
+        """n_lines [M] (negative: no scan for that manager), lines [M][max_lines][4], pose [M][6]."""
+        n = np.ascontiguousarray(n_lines, dtype=np.int32).reshape(self.n_managers)
+        l = np.ascontiguousarray(lines, dtype=np.float64).reshape(self.n_managers, -1, 4)
+        s = np.ascontiguousarray(pose, dtype=np.float64).reshape(self.n_managers, 6)
+        self._ctx._check(self._ctx.lib.lvio2d_submap_add_scan(self._h, l.shape[1], n.ctypes.data, l.ctypes.data, s.ctypes.data, 0), "lvio2d_submap_add_scan")
+
+    def add_scan_device(self, max_lines, n_lines_ptr, lines_ptr, pose_ptr):
+        self._ctx._check(self._ctx.lib.lvio2d_submap_add_scan(self._h, int(max_lines), n_lines_ptr, lines_ptr, pose_ptr, 1), "lvio2d_submap_add_scan")
+
+    def get(self, which=0, want_lines=True):
+        """Host copy: meta [M][4] (has reference, has spawning, current_count, last scan added), pose [M][6], n_lines [M], lines."""
+        M = self.n_managers
+        meta, pose, n = np.zeros((M, 4), np.int32), np.zeros((M, 6)), np.zeros(M, np.int32)
+        lines = np.zeros((M, self.line_cap, 4)) if want_lines else None
+        self._ctx._check(self._ctx.lib.lvio2d_submap_get(self._h, int(which), meta.ctypes.data_as(abi.c_int32_p), _d(pose), n.ctypes.data_as(abi.c_int32_p),
+                                                         _d(lines) if lines is not None else abi.c_double_p()), "lvio2d_submap_get")
+        return meta, pose, n, lines
+
+    def device_pointers(self):
+        """(meta, ref_pose, ref_n_lines, ref_lines) device addresses, slot 0 of the last three = the reference sub-map."""
+        out = [C.c_void_p() for _ in range(4)]
+        self._ctx._check(self._ctx.lib.lvio2d_submap_device(self._h, *[C.byref(o) for o in out]), "lvio2d_submap_device")
+        return tuple(int(o.value or 0) for o in out)
+
+    def match(self, n_lines2, lines2, pose2, kk=0, want_lines1=False):
+        """laser_manager::match_with_ref for every manager: n_match [M], match [M][max_lines2][2] = (sub-map line, scan line);
+        with want_lines1 also the matched sub-map lines' end points [M][max_lines2][4] and the sub-maps' poses [M][6]."""
+        M = self.n_managers
+        n = np.ascontiguousarray(n_lines2, dtype=np.int32).reshape(M)
+        l = np.ascontiguousarray(lines2, dtype=np.float64).reshape(M, -1, 4)
+        s = np.ascontiguousarray(pose2, dtype=np.float64).reshape(M, 6)
+        nm, match = np.zeros(M, np.int32), np.zeros((M, l.shape[1], 2), np.int32)
+        l1, rp = (np.zeros((M, l.shape[1], 4)), np.zeros((M, 6))) if want_lines1 else (None, None)
+        self._ctx._check(self._ctx.lib.lvio2d_submap_match(self._h, int(kk), l.shape[1], n.ctypes.data, l.ctypes.data, s.ctypes.data, nm.ctypes.data,
+                                                           match.ctypes.data, l1.ctypes.data if want_lines1 else None,
+                                                           rp.ctypes.data if want_lines1 else None, 0), "lvio2d_submap_match")
+        return (nm, match, l1, rp) if want_lines1 else (nm, match)
+
+    def match_device(self, max_lines2, n_lines2_ptr, lines2_ptr, pose2_ptr, n_match_ptr, match_ptr, kk=0, lines1_ptr=None, ref_pose_ptr=None):
+        self._ctx._check(self._ctx.lib.lvio2d_submap_match(self._h, int(kk), int(max_lines2), n_lines2_ptr, lines2_ptr, pose2_ptr, n_match_ptr,
+                                                           match_ptr, lines1_ptr, ref_pose_ptr, 1), "lvio2d_submap_match")
+
+
 class Line:
     """lvio_2d::line (reference src/trajectory/laser_type.h:13-21): end points in a laser frame, z = 0."""
 

@@ -348,6 +348,48 @@ int lvio2d_match_lines(lvio2d_ctx* ctx, const lvio2d_line_params* lp, int32_t n_
                        int32_t max_lines2, const int32_t* n_lines2, const double* lines2,
                        const double* pose1, const double* pose2, int32_t* n_match, int32_t* match, int32_t on_device);
 
+/* ---- laser front-end, step 3: the reference sub-map, resident in device memory.
+ * Replaces the state of laser_manager::add_scan (src/trajectory/laser_manager.cpp:424-496: ref_submap_ptr,
+ * spawnning_ref_submap_ptr, last_add_tf, current_count) and laser_manager::match_with_ref (:531-546) for a batch of
+ * `n_managers` independent laser managers (one per robot / stream).  add_scan applies the motion filter
+ * (ref_motion_filter_p / ref_motion_filter_q, config/corridor.yaml:120-121), founds the reference sub-map with the
+ * first scan, takes every later scan's lines to the frame of the reference sub-map and of the one being spawned
+ * (T_il^-1 (make_tf(sub)^-1 make_tf(current)) T_il, Isometry inverses) and appends them through the filters of
+ * scan::add_line(p1, p2, false) (:215-223: |z| of the transformed end points against line_max_dis, length against
+ * line_min_len, one 0.05 m sample on the grid), founds the spawning sub-map after ref_n_accumulation / 2 accepted
+ * scans and hands it over at ref_n_accumulation (:472-489).  Lines are kept in the reference's append order, so
+ * lvio2d_submap_match returns the pairs laser_manager::do_match would.
+ * line_cap: slots per sub-map (a corridor.yaml run appends up to ~100 lines per scan over ref_n_accumulation = 100
+ * scans); lines beyond it are counted in n_lines but not stored. ---- */
+typedef struct lvio2d_submap lvio2d_submap;
+int lvio2d_submap_create(lvio2d_ctx* ctx, int32_t n_managers, int32_t line_cap, const lvio2d_line_params* lp,
+                         double ref_motion_filter_p, double ref_motion_filter_q, int32_t ref_n_accumulation,
+                         lvio2d_submap** out);
+void lvio2d_submap_destroy(lvio2d_submap* sm);
+/* back to "no scan seen" for every manager */
+int lvio2d_submap_reset(lvio2d_submap* sm);
+/* One scan per manager: n_lines [M] (a negative count = no scan for this manager in this call), lines
+ * [M][max_lines][4] as produced by lvio2d_extract_lines, pose [M][6] = (current_p, current_q) of the IMU.
+ * on_device = 0: host buffers, synchronous.  on_device = 1: device buffers, enqueued on the context's stream. */
+int lvio2d_submap_add_scan(lvio2d_submap* sm, int32_t max_lines, const int32_t* n_lines, const double* lines,
+                           const double* pose, int32_t on_device);
+/* Host copy of the state (tests, visualisation): which = 0 reference sub-map, 1 the one being spawned.
+ * meta [M][4] = (has reference, has spawning, current_count, last add_scan passed the motion filter), pose [M][6],
+ * n_lines [M], lines [M][line_cap][4]; any output may be NULL. */
+int lvio2d_submap_get(lvio2d_submap* sm, int32_t which, int32_t* meta, double* pose, int32_t* n_lines, double* lines);
+/* Device pointers of the state, for chaining with lvio2d_match_lines(on_device = 1) / lvio2d_set_windows(bind):
+ * meta [M][4], ref_pose [2][M][6], ref_n_lines [2][M], ref_lines [2][M][line_cap][4] (slot 0 = reference sub-map). */
+int lvio2d_submap_device(lvio2d_submap* sm, const int32_t** meta, const double** ref_pose, const int32_t** ref_n_lines,
+                         const double** ref_lines);
+/* laser_manager::match_with_ref for every manager: the current scans (n_lines2 [M], lines2 [M][max_lines2][4], pose2
+ * [M][6]) against the resident reference sub-maps.  n_match [M], match [M][max_lines2][2] = (line of the sub-map, line
+ * of the scan); a manager without a reference sub-map returns no pairs.  Optional outputs (NULL to skip), which make a
+ * copy of the sub-map unnecessary: matched_lines1 [M][max_lines2][4] = end points of the sub-map line of every pair
+ * (laser_match::lines1), ref_pose [M][6] = the sub-map's pose (laser_match::p1, q1).  on_device as above. */
+int lvio2d_submap_match(lvio2d_submap* sm, int32_t kk, int32_t max_lines2, const int32_t* n_lines2, const double* lines2,
+                        const double* pose2, int32_t* n_match, int32_t* match, double* matched_lines1, double* ref_pose,
+                        int32_t on_device);
+
 /* ---- back-end pose graph.  Replaces keyframe_manager::solve
  * (src/trajectory/keyframe_manager.cpp:722-838): one ceres::Problem over the key-frame poses (p, q) with an edge_factor
  * (src/factor/edge_factor.h:79-126) per sequential and per loop edge, ground_factor_p / ground_factor_q on every key

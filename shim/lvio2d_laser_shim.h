@@ -5,7 +5,10 @@
 //                                     (reference src/trajectory/sensor.h:43-46, :51-94; src/utilies/common.cpp:4-40)
 //   lvio2d_shim::spawn_scan        -> body of laser_manager::spawn_scan (src/trajectory/laser_manager.cpp:350-422)
 //   lvio2d_shim::do_match          -> body of laser_manager::do_match   (src/trajectory/laser_manager.cpp:244-348)
-// The sub-map bookkeeping (laser_manager::add_scan, match_with_*) is unchanged host code and keeps calling do_match.
+//   lvio2d_shim::device_submap     -> the state and bodies of laser_manager::add_scan (:424-496) and match_with_ref
+//                                     (:531-546): ref_submap_ptr / spawnning_ref_submap_ptr / last_add_tf / current_count
+//                                     live in device memory (lvio2d_submap_*), one kernel per call
+// match_with_front / match_with_back / pop_scan (the key_frame deque) are unchanged host code and keep calling do_match.
 //
 // NOT compiled in this repository: it needs the reference's own headers (Eigen, ROS messages, laser_type.h), which are
 // absent from the build image.  `lvio2d_b200.frontend.{Laser, LaserManager}` is the same logic in Python and is what
@@ -139,4 +142,74 @@ namespace lvio2d_shim
         }
         return ret;
     }
+
+    // laser_manager's reference sub-map on the device.  In laser_manager: a member `lvio2d_shim::device_submap ref_;`,
+    // add_scan(scan_ptr, p, q) { key_frame.push_back(...); ref_.add_scan(scan_ptr, p, q); } and
+    // match_with_ref(scan_ptr, p, q) { return ref_.match_with_ref(scan_ptr, p, q); }.
+    class device_submap
+    {
+    public:
+        device_submap(lvio2d_ctx *ctx, int line_cap = 16384) : ctx_(ctx)
+        {
+            const lvio2d_line_params lp = line_params();
+            check(lvio2d_submap_create(ctx, 1, line_cap, &lp, PARAM(ref_motion_filter_p), PARAM(ref_motion_filter_q),
+                                       PARAM(ref_n_accumulation), &sm_),
+                  "lvio2d_submap_create");
+        }
+        ~device_submap() { lvio2d_submap_destroy(sm_); }
+        device_submap(const device_submap &) = delete;
+        device_submap &operator=(const device_submap &) = delete;
+
+        void add_scan(const lvio_2d::scan::ptr &scan_ptr, const Eigen::Vector3d &p, const Eigen::Vector3d &q)
+        {
+            std::vector<double> l;
+            const int32_t n = pack(scan_ptr, l);
+            const double pose[6] = {p(0), p(1), p(2), q(0), q(1), q(2)};
+            check(lvio2d_submap_add_scan(sm_, std::max<int32_t>(1, n), &n, l.data(), pose, 0), "lvio2d_submap_add_scan");
+        }
+
+        lvio_2d::laser_match::ptr match_with_ref(const lvio_2d::scan::ptr &scan_ptr, const Eigen::Vector3d &p, const Eigen::Vector3d &q)
+        {
+            lvio_2d::laser_match::ptr ret(new lvio_2d::laser_match);
+            ret->p1 = p; ret->p2 = p; ret->q1 = q; ret->q2 = q;
+            ret->scan2 = scan_ptr;
+            int32_t meta[4] = {0, 0, 0, 0};
+            check(lvio2d_submap_get(sm_, 0, meta, nullptr, nullptr, nullptr), "lvio2d_submap_get");
+            if (!meta[0])
+                return ret; // ref_submap_ptr == nullptr
+            std::vector<double> l2;
+            const int32_t n2 = pack(scan_ptr, l2), m2 = std::max<int32_t>(1, n2);
+            const double pose2[6] = {p(0), p(1), p(2), q(0), q(1), q(2)};
+            int32_t n_match = 0;
+            std::vector<int32_t> pairs(2 * (size_t)m2);
+            std::vector<double> l1(4 * (size_t)m2);
+            double pose1[6];
+            check(lvio2d_submap_match(sm_, 0, m2, &n2, l2.data(), pose2, &n_match, pairs.data(), l1.data(), pose1, 0), "lvio2d_submap_match");
+            ret->p1 = Eigen::Vector3d(pose1[0], pose1[1], pose1[2]);
+            ret->q1 = Eigen::Vector3d(pose1[3], pose1[4], pose1[5]);
+            for (int k = 0; k < n_match; k++)
+            {
+                // laser_match only reads p1 / p2 of lines1 (laser_factor's constructor)
+                const Eigen::Vector3d a(l1[4 * k], l1[4 * k + 1], 0), b(l1[4 * k + 2], l1[4 * k + 3], 0);
+                const Eigen::Vector2d nrm = Eigen::Vector2d(a(1) - b(1), b(0) - a(0)).normalized();
+                ret->lines1.push_back(std::make_shared<lvio_2d::line>(a, b, Eigen::Vector3d(nrm(0), nrm(1), -nrm.dot(a.head<2>()))));
+                ret->lines2.push_back(scan_ptr->lines[pairs[2 * k + 1]]);
+            }
+            return ret;
+        }
+
+    private:
+        static int32_t pack(const lvio_2d::scan::ptr &s, std::vector<double> &l)
+        {
+            l.assign(4 * std::max<size_t>(1, s->lines.size()), 0.0);
+            for (size_t j = 0; j < s->lines.size(); j++)
+            {
+                l[4 * j] = s->lines[j]->p1(0); l[4 * j + 1] = s->lines[j]->p1(1);
+                l[4 * j + 2] = s->lines[j]->p2(0); l[4 * j + 3] = s->lines[j]->p2(1);
+            }
+            return (int32_t)s->lines.size();
+        }
+        lvio2d_ctx *ctx_;
+        lvio2d_submap *sm_ = nullptr;
+    };
 } // namespace lvio2d_shim

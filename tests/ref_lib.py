@@ -362,6 +362,9 @@ class RefScan:
         except Exception:
             pass
 
+    def num_lines(self):
+        return int(lib().ref_scan_num_lines(self._h))
+
     def lines(self):
         """-> [n][9] = p1 p2 abc, corners [m][3]"""
         n, m = lib().ref_scan_num_lines(self._h), lib().ref_scan_num_corners(self._h)
