@@ -532,6 +532,8 @@ def run_ours(args):
     ]
     if sharded_block is not None:
         result["points_sharded"] = sharded_block
+    if world == 1 and args.assoc == "fixed" and args.config == "c2":
+        result["c3"] = c3_block(L, Context, local_rank, args.huber, dstruct, keep, torch, device, steps=min(args.steps, 5))
     if world == 1:
         result["single_window"] = single_window_latency(P, hb, torch, device)
         result["next_rows"] = front_end_rates(P, torch, device, cpu=not args.no_cpu)
@@ -542,6 +544,35 @@ def run_ours(args):
     print(json.dumps(result))
     if world > 1:
         dist.destroy_process_group()
+
+
+def c3_block(L, Context, local_rank, huber, dstruct, keep, torch, device, steps):
+    """BASELINE.json configs[2] (C3) beside the headline: the same resident batch, but every LM iteration re-associates
+    every point to its nearest reference line in the kernel (assoc_mode 1: per-frame 16x16 candidate grid + distance test)."""
+    P3 = L.corridor_params(max_iters=MAX_ITERS, device=local_rank)
+    P3.assoc_mode = 1
+    P3.huber_delta = huber
+    c3 = Context(P3)
+    c3.bind_windows(dstruct, keepalive=keep)
+    ext = torch.cuda.ExternalStream(c3.stream, device=device)
+    for _ in range(3):
+        c3.solve_async()
+    c3.sync()
+    c3.set_profiling(True)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(ext)
+    for _ in range(steps):
+        c3.solve_async()
+    e1.record(ext)
+    c3.sync()
+    ms = e0.elapsed_time(e1)
+    prof = c3.get_profile()
+    iters = int(c3.get_summaries()["iterations"].sum())
+    c3.close()
+    return {"value": iters * steps / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms / steps, "steps": steps, "warmup": 3,
+            "workload": "C3: 1081 beams x 30 keyframes, nearest-line re-association every iteration (BASELINE.json configs[2]), same windows as the headline",
+            "scan_match_ms_per_step": prof["scan_ms"] / steps, "factor_ms_per_step": prof["factor_ms"] / steps,
+            "window_ms_per_step": prof["window_ms"] / steps}
 
 
 def pose_graph_rates(cpu=True):
