@@ -133,7 +133,7 @@ def test_submap_batch_matches_host_mirror(ctx, oracle):
             l_in[m] = lines[ks[m]]
             pose_in[m] = traj[m][f]
         if f % 5 == 2:
-            nm, mt = sm.match(np.abs(n_in), l_in, pose_in)
+            nm, mt = sm.match(nl[ks], l_in, pose_in)
             for m in range(M):
                 hm = hosts[m].match_with_ref(scans[ks[m]], pose_in[m, 0:3], pose_in[m, 3:6])
                 sub = hosts[m].ref_submap_ptr
