@@ -851,6 +851,60 @@ __device__ __forceinline__ void gemv_t(double* out, const double* M, const doubl
     __syncwarp();
 }
 
+// C -= A^T B (tile form)
+__device__ __forceinline__ void gemm_sub_atb_t(double* Cm, const double* A, const double* B, int lane) {
+    const int g = lane >> 2, t = lane & 3;
+    double af[2][4], bf[4][2];
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+#pragma unroll
+        for (int m = 0; m < 2; ++m) {
+            af[m][ks] = -A[((((ks >> 1) << 1) + m) << 6) + ((((ks & 1) << 2) + t) << 3) + g];           // -A[4ks + t][8m + g] = -A^T[8m + g][4ks + t]
+            bf[ks][m] = B[((((ks >> 1) << 1) + m) << 6) + ((((ks & 1) << 2) + t) << 3) + g];            // B[4ks + t][8m + g]
+        }
+    }
+#pragma unroll
+    for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+        for (int ni = 0; ni < 2; ++ni) {
+            double2* cp = reinterpret_cast<double2*>(Cm + (((mi << 1) + ni) << 6) + (g << 3) + (t << 1));
+            double2 c = *cp;
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) dmma884(c.x, c.y, af[mi][ks], bf[ks][ni]);
+            *cp = c;
+        }
+    __syncwarp();
+}
+// C = -A B (tile form); C may alias A or B
+__device__ __forceinline__ void gemm_neg_ab_t(double* Cm, const double* A, const double* B, int lane) {
+    const int g = lane >> 2, t = lane & 3;
+    double af[2][4], bf[4][2];
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+#pragma unroll
+        for (int m = 0; m < 2; ++m) {
+            af[m][ks] = -A[(((m << 1) + (ks >> 1)) << 6) + (g << 3) + ((ks & 1) << 2) + t];
+            bf[ks][m] = B[((((ks >> 1) << 1) + m) << 6) + ((((ks & 1) << 2) + t) << 3) + g];
+        }
+    }
+    __syncwarp();
+#pragma unroll
+    for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+        for (int ni = 0; ni < 2; ++ni) {
+            double c0 = 0.0, c1 = 0.0;
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) dmma884(c0, c1, af[mi][ks], bf[ks][ni]);
+            *reinterpret_cast<double2*>(Cm + (((mi << 1) + ni) << 6) + (g << 3) + (t << 1)) = make_double2(c0, c1);
+        }
+    __syncwarp();
+}
+// shared memory of the cyclic-reduction shape (doubles) behind the generic per-window area: D [n] | U [1..n-1] | rhs [n][16]
+// | pivot rows [16][16] | flag [2] | extra scratch blocks
+__host__ __device__ inline size_t window_cr_doubles(int n, int extra_scratch) {
+    return (size_t)n * kTB + (size_t)(n > 1 ? n - 1 : 0) * kTB + (size_t)n * 16 + 256 + 2 + (size_t)extra_scratch * kTB;
+}
+
 // item offsets of the three raw blocks of an elimination step, per packed 15 x 15 entry e = 15 r + c:
 // H(i-1, i)(r, c) | hbb(r, c) << 10 | haa(r, c) << 20 — built once per CTA (window_offsets_init), read by every frame
 __device__ __forceinline__ void window_offsets_init(uint32_t* tab, int tid, int nthreads) {
