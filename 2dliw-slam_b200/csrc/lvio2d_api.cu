@@ -265,6 +265,12 @@ int launch_window(lvio2d_ctx* ctx, const WindowArgs& a) {
     // (LVIO2D_WINDOW_THREADS = 32 | 128 | 256 forces one of them; used by the tests to cover both)
     int nt = ctx->B <= 2 * ctx->sm_count ? 256 : (ctx->B <= 4 * ctx->sm_count ? 128 : 32);
     if (ctx->window_threads == 32 || ctx->window_threads == 128 || ctx->window_threads == 256) nt = ctx->window_threads;
+    // small batches of the tracking topology: sixteen warps per window and cyclic reduction over the frames (sequential
+    // depth log2 n instead of n), when the window's blocks fit the CTA's shared memory (n <= 50 or so)
+    const size_t cr_base = ((window_smem_doubles(ctx->n, false) + 1) & ~(size_t)1) * sizeof(double);
+    const size_t cr_budget = 231000;   // 227 KB minus the kernel's static shared memory
+    const bool cr_fits = !ctx->arrow && a.mode == 0 && !a.dense_H && cr_base + window_cr_doubles(ctx->n, 0) * sizeof(double) <= cr_budget;
+    if (cr_fits && ((nt == 256 && ctx->window_threads == 0) || ctx->window_threads == 512)) nt = 512;
     if (ctx->profiling) cudaEventRecord(next_event(ctx->ev_win, ctx->ev_win_used), ctx->stream);
     ctx->launches += 1;
 #define LAUNCH_WIN(AR, NT, GRID, BLOCK, SMEM)                                                                                 \
@@ -272,7 +278,13 @@ int launch_window(lvio2d_ctx* ctx, const WindowArgs& a) {
         CK(cudaFuncSetAttribute(window_kernel<AR, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SMEM)));            \
         window_kernel<AR, NT><<<GRID, BLOCK, SMEM, ctx->stream>>>(a, per_window);                                             \
     } while (0)
-    if (nt == 32) {
+    if (nt == 512) {
+        WindowArgs b = a;
+        b.cr_scratch = (int)std::min<size_t>(13, (cr_budget - cr_base - window_cr_doubles(ctx->n, 0) * sizeof(double)) / (kTB * sizeof(double)));
+        const size_t smem = cr_base + window_cr_doubles(ctx->n, b.cr_scratch) * sizeof(double);
+        CK(cudaFuncSetAttribute(window_kernel<false, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        window_kernel<false, 512><<<ctx->B, 512, smem, ctx->stream>>>(b, per_window);
+    } else if (nt == 32) {
         const int wpc = LV_WINDOW_WPC;
         // the fast path (tracking topology, solver program) needs 8.6 KB per window; everything else the generic layout
         const bool fast = !ctx->arrow && a.mode == 0 && !a.dense_H;

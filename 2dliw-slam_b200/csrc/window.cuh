@@ -130,6 +130,7 @@ struct WindowArgs {
     // optional marginalisation outputs
     double* marg_H;                 // [B][225] Schur complement on the last frame
     double* marg_g;                 // [B][15]
+    int cr_scratch;                 // cyclic-reduction shape (NT = 512): scratch blocks behind the fixed arrays (0..13)
 };
 
 __device__ __forceinline__ double warp_sum(double v) {
@@ -1331,7 +1332,121 @@ __device__ void window_step(const WindowArgs& a, int w, int lane, double* ws, co
             st.model_cost_change = -0.5 * sg + 0.5 * lq;
             ok = finite && st.model_cost_change > 0.0;
                 };
-        if constexpr (FASTC) {
+        if constexpr (!ARROW && NT == 512) {
+            // ---- cyclic reduction (small batches: one CTA of 16 warps per window).  The block-tridiagonal system is
+            // eliminated level by level — level l removes the frames i = s (mod 2s), s = 2^l, all of them concurrently,
+            // one warp each — so the sequential depth is ceil(log2 n) + 1 pivot inversions instead of n.  For an
+            // eliminated frame i with live neighbours l = i - s, r = i + s:
+            //     Dinv = D_i^-1, c_i = Dinv b_i, TL = U_i Dinv, Y = Dinv U_r          (U_k = coupling H(left of k, k))
+            //     D_l -= TL U_i^T, b_l -= U_i c_i          |  D_r -= U_r^T Y, b_r -= U_r^T c_i,  U_r <- -TL U_r
+            // and on the way back x_i = c_i - TL^T x_l - Y x_r.  TL and Y stay in the dead slots of U_i and D_i.
+            // Same LM system as the other shapes; the elimination ORDER differs (nested dissection instead of n-1 .. 0),
+            // so results agree with them to rounding, not bit for bit.
+            const int wi = lane >> 5, wl = lane & 31;
+            constexpr int NW = NT / 32;
+            double* crb = ws + ((window_smem_doubles(n, false) + 1) & ~(size_t)1);
+            double* Db = crb;                                   // [n][256]
+            double* Ub = Db + (size_t)(n - 1) * kTB;            // U_f at Ub + f * 256, f >= 1 (no slot for frame 0)
+            double* rb = Db + (size_t)(2 * n - 1) * kTB;        // [n][16]
+            double* pv = rb + (size_t)n * 16;                   // [16][16]
+            double* flg = pv + 256;                             // [2]
+            double* Sx = flg + 2;                               // extra scratch blocks
+            const int nscr = min(NW, 3 + a.cr_scratch);         // warps that can hold a TL block at the same time
+            double* Sw = wi < 3 ? ws + wi * kTB : Sx + (size_t)(wi - 3) * kTB;   // the first three live in the generic area
+            const int lr = wl >> 3, lc = wl & 7;
+            if (lane == 0) flg[0] = 0.0;
+            // level-0 blocks: D_f = S (hbb_f + haa_{f+1} + laser_f) S + damping, U_f = S_{f-1} H(f-1, f) S_f, b_f
+            for (int f = wi; f < n; f += NW) {
+                const double* it_f = itm + (size_t)f * kItem;
+                const bool nxt = f + 1 < n;
+                const double* it_n = itm + (size_t)(nxt ? f + 1 : f) * kItem;
+                const uint8_t cm_f = cm[f];
+                const bool fa_f = fa[f] != 0;
+                const double* blk = lb + f * NPAD;
+                double hb[8], ha[8], hu[8];
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    const int tile = q >> 1;
+                    const int win = ((q & 1) << 5) + wl, wtr = (lc << 3) + ((q & 1) << 2) + lr;
+                    const int off = tile == 0 ? win : (tile == 1 ? 64 + win : (tile == 2 ? 64 + wtr : 128 + win));
+                    hb[q] = it_f[kItemHbb + off];
+                    ha[q] = nxt ? it_n[off] : 0.0;
+                    hu[q] = f >= 1 ? it_f[kItemHab + (q << 5) + wl] : 0.0;
+                }
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    const int tile = q >> 1;
+                    const int r = ((q >> 2) << 3) + ((q & 1) << 2) + lr, c = ((tile & 1) << 3) + lc;
+                    const bool in = r < 15 && c < 15;
+                    const double sr = scw[f * 15 + (r < 15 ? r : 0)], sc = scw[f * 15 + (c < 15 ? c : 0)];
+                    double d = hb[q] + ha[q];
+                    if (tile == 0) d += laser_own_reg(blk, cm_f, fa_f, r, c);
+                    d = d * sr * sc;
+                    if ((tile == 0 || tile == 3) && r == c)
+                        d = col_const(cm_f, r) ? 1.0 : d + fmin(fmax(d, opt.min_lm_diagonal), opt.max_lm_diagonal) * inv_radius;
+                    Db[(size_t)f * kTB + (q << 5) + wl] = in ? d : 0.0;
+                    if (f >= 1) Ub[(size_t)f * kTB + (q << 5) + wl] = in ? hu[q] * scw[(f - 1) * 15 + r] * sc : 0.0;
+                }
+                if (wl < 16) rb[f * 16 + wl] = wl < 15 ? sb[f * 15 + wl] : 0.0;
+            }
+            __syncthreads();
+            int s = 1;
+            for (; s < n; s <<= 1) {
+                const int cnt = (n - s + 2 * s - 1) / (2 * s);           // frames s, 3s, 5s, ... < n
+                for (int base = 0; base < cnt; base += nscr) {
+                    const int k = base + wi;
+                    const bool act = wi < nscr && k < cnt;
+                    const int i = s + 2 * s * k, l = i - s, r = i + s;
+                    const bool has_r = act && r < n;
+                    if (act) {
+                        double* Di = Db + (size_t)i * kTB;
+                        const double* Ui = Ub + (size_t)i * kTB;
+                        if (!spd_inverse15_t(Di, pv + wi * 16, wl) && wl == 0) flg[0] = 1.0;
+                        gemv_t<false, false>(pv + wi * 16, Di, rb + i * 16, wl);                 // c_i = Dinv b_i
+                        if (wl < 15) rb[i * 16 + wl] = pv[wi * 16 + wl];
+                        gemm_ab_t(Sw, Ui, Di, wl);                                               // TL = U_i Dinv
+                        if (has_r) gemm_ab_t(Di, Di, Ub + (size_t)r * kTB, wl);                  // Y = Dinv U_r, over Dinv
+                        gemm_sub_abt_t(Db + (size_t)l * kTB, Sw, Ui, wl);                        // D_l -= TL U_i^T
+                        gemv_t<false, true>(rb + l * 16, Ui, rb + i * 16, wl);                   // b_l -= U_i c_i
+                    }
+                    __syncthreads();
+                    if (has_r) {
+                        double* Ur = Ub + (size_t)r * kTB;
+                        gemm_sub_atb_t(Db + (size_t)r * kTB, Ur, Db + (size_t)i * kTB, wl);      // D_r -= U_r^T Y
+                        gemv_t<true, true>(rb + r * 16, Ur, rb + i * 16, wl);                    // b_r -= U_r^T c_i
+                        gemm_neg_ab_t(Ur, Sw, Ur, wl);                                           // U_r <- H(l, r) = -TL U_r
+                    }
+                    if (act) {
+                        double* Ui = Ub + (size_t)i * kTB;
+#pragma unroll
+                        for (int q = 0; q < 4; ++q)
+                            *reinterpret_cast<double2*>(Ui + 2 * (wl + 32 * q)) = *reinterpret_cast<const double2*>(Sw + 2 * (wl + 32 * q));
+                    }
+                    __syncthreads();
+                }
+            }
+            if (wi == 0) {
+                if (!spd_inverse15_t(Db, pv, wl) && wl == 0) flg[0] = 1.0;
+                gemv_t<false, false>(pv, Db, rb, wl);                                            // x_0 = D_0^-1 b_0
+                if (wl < 15) rb[wl] = pv[wl];
+            }
+            __syncthreads();
+            ok = flg[0] == 0.0;
+            if (ok) {
+                for (s >>= 1; s >= 1; s >>= 1) {
+                    const int cnt = (n - s + 2 * s - 1) / (2 * s);
+                    for (int k = wi; k < cnt; k += NW) {
+                        const int i = s + 2 * s * k, l = i - s, r = i + s;
+                        gemv_t<true, true>(rb + i * 16, Ub + (size_t)i * kTB, rb + l * 16, wl);          // x_i = c_i - TL^T x_l
+                        if (r < n) gemv_t<false, true>(rb + i * 16, Db + (size_t)i * kTB, rb + r * 16, wl);   //     - Y x_r
+                    }
+                    __syncthreads();
+                }
+                for (int e = lane; e < n * 15; e += NT) sb[e] = rb[(e / 15) * 16 + e % 15];
+                __syncthreads();
+                step_and_model();
+            }
+        } else if constexpr (FASTC) {
             // shared memory of the fast path (doubles): Dp 256 | Cp 256 | Ut 256 | Ha 192 | piv 16 | slb 32 | ssc 32 | rhs 3 x 16
             double* Dp = ws;
             double* Cp = ws + kTB;

@@ -127,7 +127,7 @@ def test_linearize_matches_oracle(ctx, oracle, P10, case, mode):
 
 @pytest.mark.parametrize("case,iters", [("c1", 1), ("c2_small", 10), ("tracking2", 20), ("init", 20), ("c2_full", 10),
                                         ("tracking2", 50), ("init", 50)])
-@pytest.mark.parametrize("wt", [32, 128, 256])
+@pytest.mark.parametrize("wt", [32, 128, 256, 512])
 def test_solve_matches_oracle(oracle, case, iters, wt, monkeypatch):
     """Up to ~20 iterations the two minimisers walk in lock-step (differences ~1e-13).  The reference's default of 50
     iterations (solver.cpp:161-168, no fast_mode) ends in a slowly converging zig-zag (the ground/wheel residuals are
@@ -138,6 +138,10 @@ def test_solve_matches_oracle(oracle, case, iters, wt, monkeypatch):
     # both thread-group shapes of window_kernel: one warp per window (the batched shape) and four warps per window (what
     # small batches get by default)
     monkeypatch.setenv("LVIO2D_WINDOW_THREADS", str(wt))
+    if wt == 512:
+        # sixteen warps per window + cyclic reduction over the frames (tracking topology only; the initialisation
+        # topology keeps eight warps): the three-kernel loop, not the fused small-batch kernel (which runs eight warps)
+        monkeypatch.setenv("LVIO2D_FUSED_SMALL", "0")
     P = L.corridor_params(max_iters=iters)
     sb = CASES[case]()
     hb = oracle.preintegrate_batch(P, sb)
