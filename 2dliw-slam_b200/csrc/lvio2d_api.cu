@@ -270,7 +270,8 @@ int launch_window(lvio2d_ctx* ctx, const WindowArgs& a) {
     const size_t cr_base = ((window_smem_doubles(ctx->n, false) + 1) & ~(size_t)1) * sizeof(double);
     const size_t cr_budget = 231000;   // 227 KB minus the kernel's static shared memory
     const bool cr_fits = !ctx->arrow && a.mode == 0 && !a.dense_H && cr_base + window_cr_doubles(ctx->n, 0) * sizeof(double) <= cr_budget;
-    if (cr_fits && ((nt == 256 && ctx->window_threads == 0) || ctx->window_threads == 512)) nt = 512;
+    // (measured, C2: 512 beats the next best shape up to 3 x 148 windows — 3.89 vs 4.18 ms per solve at 444 — and loses from 4 x 148)
+    if (cr_fits && ((ctx->B <= 3 * ctx->sm_count && ctx->window_threads == 0) || ctx->window_threads == 512)) nt = 512;
     if (ctx->profiling) cudaEventRecord(next_event(ctx->ev_win, ctx->ev_win_used), ctx->stream);
     ctx->launches += 1;
 #define LAUNCH_WIN(AR, NT, GRID, BLOCK, SMEM)                                                                                 \
