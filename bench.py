@@ -775,10 +775,15 @@ def cpu_baseline(P, hb, seconds, threads, states_dev=None):
     k = int(max(threads, min(hb.n_windows, seconds / max(t1, 1e-3))))
     k = max(1, min(k, hb.n_windows))
     batch = sub(k)
+    O.linear_solve_seconds(reset=True)
     t0 = time.perf_counter()
     ost, s = O.solve(P, batch, n_threads=threads)
     dt = time.perf_counter() - t0
+    lin_s = O.linear_solve_seconds() if threads == 1 else None
     out = {"value": float(s["iterations"].sum()) / dt, "unit": UNIT, "cores": threads, "kind": "port",
+           "linear_solve_share": None if lin_s is None else lin_s / dt,
+           "linear_solve_note": "share of the time in the oracle's DENSE Cholesky of the reduced system (the reference's SPARSE_SCHUR would use the band); "
+                                "the rest is residual / Jacobian evaluation with Jets",
            "sample": f"{k} of the batch's windows, {int(s['iterations'].sum())} LM iterations in {dt:.1f} s "
                      f"(oracle/liboracle.so, Jet autodiff, g++ -O3 -march=native)",
            "host_cpus": os.cpu_count()}

@@ -151,6 +151,12 @@ static int solve_impl(const lvio2d_params* p, const lvio2d_window_batch* batch, 
 int oracle_solve(const lvio2d_params* p, const lvio2d_window_batch* batch, double* states_out, lvio2d_summary* summaries, int32_t n_threads) {
     return solve_impl(p, batch, states_out, summaries, n_threads, false);
 }
+// seconds the calling thread's single-threaded solves spent in the linear solve since the last reset (reset != 0 clears it)
+double oracle_linear_solve_seconds(int32_t reset) {
+    const double t = lm_linear_solve_seconds();
+    if (reset) lm_linear_solve_seconds() = 0.0;
+    return t;
+}
 // the "analytic" CPU-baseline flavour: closed-form Jacobian for the scan points, Jets for the rest
 int oracle_solve_analytic(const lvio2d_params* p, const lvio2d_window_batch* batch, double* states_out, lvio2d_summary* summaries,
                           int32_t n_threads) {

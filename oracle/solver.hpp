@@ -8,6 +8,7 @@
 // Dense normal equations stand in for Ceres' SPARSE_SCHUR / DENSE_SCHUR (the linear-solver type changes
 // speed, not the step).
 #pragma once
+#include <chrono>
 #include <cmath>
 #include <cstdint>
 #include <cstring>
@@ -298,6 +299,10 @@ inline LMOptions lm_options_from(const lvio2d_params& p) {
 // monotonic steps, no inner iterations, no bounds, exact (direct) linear solver.
 // `Problem` supplies: int dim(); double evaluate(const double* x, Linearization* lin) (cost only when lin == nullptr);
 // void plus(const double* x, const double* delta, const std::vector<uint8_t>& free_col, double* out).
+// seconds spent in the linear solve (scaled system build, Cholesky, substitutions) by lm_minimize on this thread since the
+// last reset: bench.py reports its share of the CPU baseline (the oracle solves the dense reduced system, the reference's
+// SPARSE_SCHUR would exploit the band)
+inline double& lm_linear_solve_seconds() { static thread_local double t = 0.0; return t; }
 template <class Problem>
 inline lvio2d_summary lm_minimize(const Problem& ev, const LMOptions& opt, double* x /* [dim] in/out */) {
     const int dim = ev.dim();
@@ -341,6 +346,7 @@ inline lvio2d_summary lm_minimize(const Problem& ev, const LMOptions& opt, doubl
         if (radius < opt.min_trust_region_radius) { S.termination = LVIO2D_TERM_CONVERGENCE_RADIUS; break; }
         ++iteration;
         // ComputeTrustRegionStep: scaled normal equations + LM diagonal
+        const auto t_lin0 = std::chrono::steady_clock::now();
         for (int a = 0; a < m; ++a) {
             gs[a] = lin.g[idx[a]] * scale[a];
             for (int b = 0; b < m; ++b) Hs[(size_t)a * m + b] = lin.H[(size_t)idx[a] * dim + idx[b]] * scale[a] * scale[b];
@@ -358,6 +364,7 @@ inline lvio2d_summary lm_minimize(const Problem& ev, const LMOptions& opt, doubl
             for (int i = m - 1; i >= 0; --i) { double s = y[i]; for (int j = i + 1; j < m; ++j) s -= Lc[(size_t)j * m + i] * step[j]; step[i] = s / Lc[(size_t)i * m + i]; }
             for (int i = 0; i < m; ++i) { step[i] = -step[i]; if (!std::isfinite(step[i])) valid = false; }
         }
+        lm_linear_solve_seconds() += std::chrono::duration<double>(std::chrono::steady_clock::now() - t_lin0).count();
         if (valid) {
             // model_cost_change = -(J step)^T (r + J step / 2) = -step^T gs - 1/2 step^T Hs step
             double sg = 0.0, shs = 0.0;

@@ -188,6 +188,14 @@ def solve(params, hb, n_threads=1, analytic=False):
     return states, summ
 
 
+def linear_solve_seconds(reset=False):
+    """Seconds this thread's single-threaded solves spent in the linear solve (dense reduced system) since the last reset."""
+    fn = lib().oracle_linear_solve_seconds
+    fn.restype = C.c_double
+    fn.argtypes = [C.c_int32]
+    return float(fn(1 if reset else 0))
+
+
 def marginalize(params, hb, states=None):
     B = hb.n_windows
     X0, J, r, dH, dg = np.zeros((B, 15)), np.zeros((B, 15, 15)), np.zeros((B, 15)), np.zeros((B, 15, 15)), np.zeros((B, 15))
