@@ -126,7 +126,7 @@ class ScanWireStruct(C.Structure):
     """lvio2d_scan_wire (include/lvio2d.h)."""
 
     _fields_ = [("n_beams", C.c_int32), ("ranges", C.POINTER(C.c_float)), ("angle", C.POINTER(C.c_float)), ("beam_line", C.POINTER(C.c_uint16)),
-                ("imu_compact", c_double_p)]
+                ("imu_compact", c_double_p), ("shared_lines", C.c_int32), ("reserved", C.c_int32)]
 
 
 class ScanWire:
@@ -136,7 +136,8 @@ class ScanWire:
 
     NONE = 0xFFFF
 
-    def __init__(self, ranges, angle, beam_line, imu_compact=None):
+    def __init__(self, ranges, angle, beam_line, imu_compact=None, shared_lines=False):
+        self.shared_lines = bool(shared_lines)   # the batch's lines / line_offset are per WINDOW (one sub-map per window)
         self.imu_compact = None if imu_compact is None else np.ascontiguousarray(imu_compact, dtype=np.float64).reshape(-1, IMU_COMPACT)
         self.ranges = np.ascontiguousarray(ranges, dtype=np.float32)
         self.angle = np.ascontiguousarray(angle, dtype=np.float32).reshape(-1, 2)
@@ -151,6 +152,7 @@ class ScanWire:
         s.angle = self.angle.ctypes.data_as(C.POINTER(C.c_float))
         s.beam_line = self.beam_line.ctypes.data_as(C.POINTER(C.c_uint16))
         s.imu_compact = ptr(self.imu_compact, c_double_p)
+        s.shared_lines, s.reserved = int(self.shared_lines), 0
         return s
 
     def nbytes(self):

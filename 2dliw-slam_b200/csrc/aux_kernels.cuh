@@ -342,4 +342,15 @@ __global__ void expand_wire_kernel(const float* __restrict__ ranges, const float
     point_line[i] = (valid && l != 0xFFFFu) ? (int32_t)l : -1;
 }
 
+// lvio2d_scan_wire::shared_lines: one line list per window -> the per-frame layout the kernels read
+__global__ void expand_shared_lines_kernel(const double4* __restrict__ shared, const int64_t* __restrict__ window_offset,
+                                           const int64_t* __restrict__ line_offset, int n_frames, int n_total_frames, double4* __restrict__ out) {
+    const int f = blockIdx.x;
+    if (f >= n_total_frames) return;
+    const double4* src = shared + window_offset[f / n_frames];
+    double4* dst = out + line_offset[f];
+    const int nl = (int)(line_offset[f + 1] - line_offset[f]);
+    for (int l = threadIdx.x; l < nl; l += blockDim.x) dst[l] = src[l];
+}
+
 }  // namespace lv

@@ -101,7 +101,9 @@ struct lvio2d_ctx {
     bool fused_small = true;   // LVIO2D_FUSED_SMALL=0: batches of <= #SM windows also go through the three-kernel loop
     bool have_solution = false;
     // host staging of the small index arrays (kept alive until the next upload so that copies can stay asynchronous)
-    PinnedVec<int64_t> h_poff, h_loff;
+    PinnedVec<int64_t> h_poff, h_loff, h_woff;
+    cudaEvent_t ev_staged = nullptr;   // recorded behind the last copy out of the staging vectors of an upload
+    DevBuf b_wsl, b_wso;      // lvio2d_scan_wire::shared_lines: the per-window line lists and their offsets
     PinnedVec<int32_t> h_rf;
     PinnedVec<uint8_t> h_cm, h_active, h_active1;
     // measurement
@@ -339,8 +341,12 @@ int setup_batch(lvio2d_ctx* ctx, const lvio2d_window_batch* b, bool bind, bool a
     ctx->has_weight = b->point_weight != nullptr;
 
     // host-side views of the small index arrays (offsets, masks, ref frames) to derive the launch shape
-    // a previous asynchronous upload may still be reading the staging vectors
-    CK(cudaStreamSynchronize(ctx->stream));
+    // a previous asynchronous upload may still be reading the staging vectors: wait for ITS copies, not for the whole
+    // stream — the solve enqueued behind them may keep running while the host prepares the next upload (a host that waits
+    // for the solve leaves this context idle until it comes round again, which cost the chunked end-to-end arm a third
+    // of its throughput once PCIe was no longer the bottleneck)
+    if (ctx->ev_staged) CK(cudaEventSynchronize(ctx->ev_staged));
+    else CK(cudaEventCreateWithFlags(&ctx->ev_staged, cudaEventDisableTiming));
     PinnedVec<int64_t>&poff = ctx->h_poff, &loff = ctx->h_loff;
     PinnedVec<int32_t>& rf = ctx->h_rf;
     PinnedVec<uint8_t>& cm = ctx->h_cm;
@@ -349,6 +355,7 @@ int setup_batch(lvio2d_ctx* ctx, const lvio2d_window_batch* b, bool bind, bool a
         return fail(ctx, LVIO2D_ERR_ALLOC, "cudaHostAlloc(staging)");
     if (wire && (bind || wire->n_beams < 1 || !wire->ranges || !wire->angle || !wire->beam_line)) return fail(ctx, LVIO2D_ERR_INVALID_ARG, "scan wire: host arrays ranges / angle / beam_line");
     const bool has_laser = wire ? (b->line_offset && b->lines) : (b->point_offset && b->points && b->point_line && b->line_offset && b->lines);
+    const bool shared_lines = wire && wire->shared_lines != 0 && has_laser;
     if (bind) {
         if (has_laser) {
             CK(cudaMemcpy(poff.data(), b->point_offset, sizeof(int64_t) * (F + 1), cudaMemcpyDeviceToHost));
@@ -360,7 +367,18 @@ int setup_batch(lvio2d_ctx* ctx, const lvio2d_window_batch* b, bool bind, bool a
         if (has_laser) {
             if (wire) for (int f = 0; f <= F; ++f) poff[f] = (int64_t)f * wire->n_beams;   // every beam is a point slot
             else std::memcpy(poff.data(), b->point_offset, sizeof(int64_t) * (F + 1));
-            std::memcpy(loff.data(), b->line_offset, sizeof(int64_t) * (F + 1));
+            if (shared_lines) {
+                // one line list per window: the per-frame offsets of the replicated layout
+                if (!ctx->h_woff.assign(B + 1, 0)) return fail(ctx, LVIO2D_ERR_ALLOC, "cudaHostAlloc(staging)");
+                std::memcpy(ctx->h_woff.data(), b->line_offset, sizeof(int64_t) * (B + 1));
+                for (int w = 0; w < B; ++w) {
+                    const int64_t nl = ctx->h_woff[w + 1] - ctx->h_woff[w];
+                    if (nl < 0) return fail(ctx, LVIO2D_ERR_INVALID_ARG, "offsets must be non-decreasing");
+                    for (int k = 0; k < n; ++k) loff[(size_t)w * n + k + 1] = loff[(size_t)w * n + k] + nl;
+                }
+            } else {
+                std::memcpy(loff.data(), b->line_offset, sizeof(int64_t) * (F + 1));
+            }
             if (b->ref_frame) std::memcpy(rf.data(), b->ref_frame, sizeof(int32_t) * F);
         }
         if (b->const_mask) std::memcpy(cm.data(), b->const_mask, F);
@@ -445,7 +463,18 @@ int setup_batch(lvio2d_ctx* ctx, const lvio2d_window_batch* b, bool bind, bool a
     }
     if ((rc = take<int64_t>(ctx, false, ctx->b_poff, ctx->point_offset, poff.data(), (size_t)F + 1))) return rc;
     if ((rc = take<int64_t>(ctx, false, ctx->b_loff, ctx->line_offset, loff.data(), (size_t)F + 1))) return rc;
-    if ((rc = take<double4>(ctx, bind, ctx->b_lines, ctx->lines, has_laser ? b->lines : nullptr, (size_t)ctx->L))) return rc;
+    if (shared_lines) {
+        const double4* d_sl; const int64_t* d_wo;
+        if ((rc = take<double4>(ctx, false, ctx->b_wsl, d_sl, b->lines, (size_t)ctx->h_woff[B]))) return rc;
+        if ((rc = take<int64_t>(ctx, false, ctx->b_wso, d_wo, ctx->h_woff.data(), (size_t)B + 1))) return rc;
+        if (!ctx->b_lines.ensure(std::max<size_t>(1, (size_t)ctx->L) * sizeof(double4))) return fail(ctx, LVIO2D_ERR_ALLOC, "cudaMalloc(lines)");
+        ctx->lines = ctx->b_lines.as<double4>();
+        if (ctx->L > 0 && d_sl) {
+            expand_shared_lines_kernel<<<F, 128, 0, ctx->stream>>>(d_sl, d_wo, ctx->line_offset, n, F, ctx->b_lines.as<double4>());
+            CK(cudaGetLastError());
+            ctx->launches += 1;
+        }
+    } else if ((rc = take<double4>(ctx, bind, ctx->b_lines, ctx->lines, has_laser ? b->lines : nullptr, (size_t)ctx->L))) return rc;
     if ((rc = take<int32_t>(ctx, false, ctx->b_ref, ctx->ref_frame, rf.data(), (size_t)F))) return rc;
     if ((rc = take<uint8_t>(ctx, false, ctx->b_cmask, ctx->const_mask, cm.data(), (size_t)F))) return rc;
     if ((rc = take<double>(ctx, bind, ctx->b_refpose, ctx->ref_pose, has_laser ? b->ref_pose : nullptr, (size_t)F * 6))) return rc;
@@ -471,6 +500,7 @@ int setup_batch(lvio2d_ctx* ctx, const lvio2d_window_batch* b, bool bind, bool a
     CK(cudaMemcpyAsync(ctx->b_x0.p, b->states, ns, bind ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(ctx->b_active.p, active.data(), F, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(ctx->b_active1.p, active1.data(), F, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaEventRecord(ctx->ev_staged, ctx->stream));   // every copy out of the staging vectors is enqueued
     CK(cudaMemsetAsync(ctx->b_part.p, 0, (size_t)F * ctx->tiles * ctx->npad * sizeof(double), ctx->stream));
     if (ctx->prior_frame >= 0) {
         // J^T J of the marginalisation prior: constant over the solve, so the factor kernel adds it instead of recomputing it
@@ -574,7 +604,7 @@ void lvio2d_destroy(lvio2d_ctx* ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     DevBuf* all[] = {&ctx->b_points, &ctx->b_pline, &ctx->b_pweight, &ctx->b_poff, &ctx->b_loff, &ctx->b_lines, &ctx->b_ref, &ctx->b_refpose,
-                     &ctx->b_imu, &ctx->b_wheel, &ctx->b_pX0, &ctx->b_pJ, &ctx->b_pH, &ctx->b_cmask, &ctx->b_wr, &ctx->b_wa, &ctx->b_wl, &ctx->b_wi, &ctx->b_agp, &ctx->b_agm, &ctx->b_x0, &ctx->b_x, &ctx->b_xc, &ctx->b_scale,
+                     &ctx->b_imu, &ctx->b_wheel, &ctx->b_pX0, &ctx->b_pJ, &ctx->b_pH, &ctx->b_cmask, &ctx->b_wr, &ctx->b_wa, &ctx->b_wl, &ctx->b_wi, &ctx->b_wsl, &ctx->b_wso, &ctx->b_agp, &ctx->b_agm, &ctx->b_x0, &ctx->b_x, &ctx->b_xc, &ctx->b_scale,
                      &ctx->b_ftab, &ctx->b_reftab, &ctx->b_wlines, &ctx->b_wlen, &ctx->b_part, &ctx->b_lb, &ctx->b_items, &ctx->b_vec, &ctx->b_fac, &ctx->b_state,
                      &ctx->b_status, &ctx->b_active, &ctx->b_active1, &ctx->b_reduce};
     for (DevBuf* b : all) b->release();
@@ -584,10 +614,11 @@ void lvio2d_destroy(lvio2d_ctx* ctx) {
     for (auto& b : ctx->b_ml) b.release();
     for (auto& b : ctx->b_pg) b.release();
     ctx->h_pg.release();
-    ctx->h_poff.release(); ctx->h_loff.release(); ctx->h_rf.release(); ctx->h_cm.release(); ctx->h_active.release(); ctx->h_active1.release();
+    ctx->h_poff.release(); ctx->h_loff.release(); ctx->h_woff.release(); ctx->h_rf.release(); ctx->h_cm.release(); ctx->h_active.release(); ctx->h_active1.release();
     for (auto e : ctx->ev_scan) cudaEventDestroy(e);
     for (auto e : ctx->ev_win) cudaEventDestroy(e);
     for (auto e : ctx->ev_fac) cudaEventDestroy(e);
+    if (ctx->ev_staged) cudaEventDestroy(ctx->ev_staged);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
 }

@@ -312,7 +312,9 @@ __device__ __forceinline__ void scan_match_item(const ScanMatchArgs& a, const in
 #pragma unroll
     for (int i = 0; i < NACC; ++i) acc[i] = 0.0;
 
-    for (int64_t base = pb + lane; base < pe; base += 32 * U) {
+    // (ASSOC: the trip count is the same on every lane — the candidate union below is a warp collective; lanes past the end
+    // carry li = -1)
+    for (int64_t base = pb + lane; ASSOC ? (base - lane < pe) : (base < pe); base += 32 * U) {
         double2 c[U];
         int li[U];
         double w[U];
@@ -321,7 +323,7 @@ __device__ __forceinline__ void scan_match_item(const ScanMatchArgs& a, const in
         issue(base + 32 * U);
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-            if (li[u] < 0) continue;
+            if constexpr (!(ASSOC && !REF_FREE)) { if (li[u] < 0) continue; }
             if constexpr (!ASSOC) { if (li[u] >= nl) continue; }   // an index beyond the frame's line list takes no part (never an out-of-table read)
             if constexpr (ASSOC) {
                 // nearest line by perpendicular distance among the lines whose extent (+gate) contains the foot
@@ -350,15 +352,28 @@ __device__ __forceinline__ void scan_match_item(const ScanMatchArgs& a, const in
                         if (tt >= -a.assoc_gate && tt <= len + a.assoc_gate && ad < best_d) { best_d = ad; best = l; }
                     };
                     if (use_grid) {
-                        // only the lines registered in the point's cell — in increasing line order, so that ties resolve
-                        // exactly like the all-lines loop
+                        // Only lines registered in a cell can pass the test for a point of that cell, so testing MORE lines
+                        // than the point's own cell lists changes nothing: the warp tests the UNION of its 32 points' cell
+                        // masks (32 consecutive beams: one to three cells) in one uniform loop — no divergence, broadcast
+                        // loads — in increasing line order, so that ties resolve exactly like the all-lines loop.
                         const double gx = (X - gx0) * gix, gy = (Y - gy0) * giy;
-                        if (!(gx >= 0.0 && gx < (double)kAssocG && gy >= 0.0 && gy < (double)kAssocG)) continue;   // outside every line's reach
-                        const int cell = (int)gy * kAssocG + (int)gx;
-                        unsigned long long m0 = gmask[2 * cell], m1 = gmask[2 * cell + 1];
-                        while (m0) { const int l = __ffsll((long long)m0) - 1; m0 &= m0 - 1; test_world(l); }
-                        while (m1) { const int l = 63 + __ffsll((long long)m1); m1 &= m1 - 1; test_world(l); }
+                        const bool inside = li[u] >= 0 && gx >= 0.0 && gx < (double)kAssocG && gy >= 0.0 && gy < (double)kAssocG;
+                        const int cell = inside ? (int)gy * kAssocG + (int)gx : 0;
+                        const ulonglong2 mm = *reinterpret_cast<const ulonglong2*>(gmask + 2 * cell);
+                        const unsigned long long m0 = inside ? mm.x : 0ull, m1 = inside ? mm.y : 0ull;
+                        unsigned un[4];
+                        un[0] = __reduce_or_sync(0xffffffffu, (unsigned)m0);
+                        un[1] = __reduce_or_sync(0xffffffffu, (unsigned)(m0 >> 32));
+                        un[2] = __reduce_or_sync(0xffffffffu, (unsigned)m1);
+                        un[3] = __reduce_or_sync(0xffffffffu, (unsigned)(m1 >> 32));
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            unsigned m = un[q];
+                            while (m) { const int l = 32 * q + __ffs((int)m) - 1; m &= m - 1; test_world(l); }
+                        }
+                        if (!inside) continue;   // no correspondence, or outside every line's reach
                     } else {
+                        if (li[u] < 0) continue;
                         for (int l = 0; l < nl; ++l) test_world(l);
                     }
                 } else {

@@ -392,6 +392,7 @@ def run_ours(args):
     out_np = out_states.numpy().reshape(-1, 15)
     e2e_ms = e2e_expanded_ms = None
     e2e_bytes = 0
+    e2e_shared = False
     if not shard_points:
         # the batch goes through the public API in `--e2e-chunks` chunks alternating over two contexts, so that the
         # host->device copy of chunk k+1 (copy engine) overlaps the solve of chunk k (SMs)
@@ -438,10 +439,25 @@ def run_ours(args):
             del chunks
             # (b) wire encoding: float32 ranges + uint16 line index per beam
             wchunks = []
+            # every frame of a window was matched against the same sub-map (same lines, same reference pose): the lines
+            # travel once per window (lvio2d_scan_wire::shared_lines) unless --no-shared-lines
+            lo = hb["line_offset"]
+            ln4 = hb["lines"].reshape(-1, 4)
+            per_frame = np.diff(lo)
+            shared = (not args.no_shared_lines) and bool(np.all(per_frame == per_frame[0])) and per_frame[0] > 0
+            if shared:
+                l3 = ln4.reshape(B, nf, int(per_frame[0]), 4)
+                shared = bool(np.all(l3 == l3[:, :1]))
             for a, b in bounds:
-                bare = pinned_copy(window_slice(hb, a, b).replace(points=None, point_line=None, point_offset=None, **({} if wire.imu_compact is None else {"imu": None})), torch)
+                sub = window_slice(hb, a, b).replace(points=None, point_line=None, point_offset=None, **({} if wire.imu_compact is None else {"imu": None}))
+                if shared:
+                    k = b - a
+                    sub = sub.replace(lines=l3[a:b, 0].reshape(-1, 4), line_offset=np.arange(k + 1, dtype=np.int64) * int(per_frame[0]))
+                bare = pinned_copy(sub, torch)
                 wk = pinned_wire(wire, a, b, nf, torch)
+                wk.shared_lines = shared
                 wchunks.append((bare, wk))
+            e2e_shared = shared
             e2e_bytes = int(sum(bare.nbytes() + wk.nbytes() for bare, wk in wchunks))
 
             def e2e_wire_step():
@@ -509,7 +525,7 @@ def run_ours(args):
             "value": total_iters_per_step * args.steps / (e2e_ms_all * 1e-3), "unit": UNIT,
             "h2d_bytes_per_step": e2e_bytes, "d2h_bytes_per_step": int(out_states.numel() * 8),
             "ms_per_step": e2e_ms_all / args.steps,
-            "api": (f"lvio2d_set_windows_wire(pinned host: float32 ranges + uint16 line index per beam, lines, the 190 doubles of each IMU preintegration the factor reads, wheel blobs, states; async) + "
+            "api": (f"lvio2d_set_windows_wire(pinned host: float32 ranges + uint16 line index per beam, {"the sub-map's lines once per window" if e2e_shared else "every frame's lines"}, the 190 doubles of each IMU preintegration the factor reads, wheel blobs, states; async) + "
                     f"lvio2d_solve_async + lvio2d_get_states_async + lvio2d_sync, {args.e2e_chunks} chunks over {args.e2e_contexts} contexts") if wire is not None else
                    f"lvio2d_set_windows_async(pinned host) + lvio2d_solve_async + lvio2d_get_states_async + lvio2d_sync, {args.e2e_chunks} chunks over {args.e2e_contexts} contexts",
         },
@@ -855,6 +871,7 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-imu-compact", action="store_true", help="end-to-end arm: upload the full 466-double IMU blobs instead of the 190 doubles the factor reads")
+    ap.add_argument("--no-shared-lines", action="store_true", help="e2e arm: upload every frame's own copy of the sub-map lines")
     ap.add_argument("--no-points-sharded", action="store_true", help="skip the points_sharded block of multi-GPU runs")
     args = ap.parse_args()
     if args.impl == "reference":

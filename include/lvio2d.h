@@ -197,6 +197,13 @@ typedef struct lvio2d_scan_wire {
      * reads (src/factor/imu_factor.h:52-86) instead of the 466 of the full blob:
      *   X[15] | J(k, 9..14), k = 0..8, row-major [9][6] | the upper triangle of sqrt_inverse_P row by row (120) | Dt */
     const double* imu_compact;    /* [B*(n-1)][LVIO2D_IMU_COMPACT] */
+    /* 1: the frames of a window were matched against the SAME sub-map (laser_match::lines1 of consecutive frames are
+     * shared_ptrs into one laser_submap, laser_manager.cpp:544-545) and its lines travel once per window:
+     * host_batch->line_offset has n_windows + 1 entries and every frame of window w uses the lines
+     * [line_offset[w], line_offset[w + 1]); beam_line indexes that list.  The device replicates them into the per-frame
+     * layout.  0: line_offset has n_windows * n_frames + 1 entries as for lvio2d_set_windows. */
+    int32_t shared_lines;
+    int32_t reserved;
 } lvio2d_scan_wire;
 #define LVIO2D_IMU_COMPACT 190
 int lvio2d_set_windows_wire(lvio2d_ctx* ctx, const lvio2d_window_batch* host_batch, const lvio2d_scan_wire* wire, int32_t async);

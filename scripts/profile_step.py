@@ -19,9 +19,11 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--windows", type=int, default=4096)
 ap.add_argument("--solves", type=int, default=2)
 ap.add_argument("--config", default="c2")
+ap.add_argument("--assoc", default="fixed", choices=["fixed", "nearest"])
 args = ap.parse_args()
 device = torch.device("cuda", 0)
 P = L.corridor_params(max_iters=bench.MAX_ITERS)
+P.assoc_mode = 1 if args.assoc == "nearest" else 0
 ctx = Context(P)
 hb, _ = bench.build_host_batch(ctx, args.windows, seed0=42, config=args.config)
 dstruct, keep = bench.to_device_struct(hb, torch, device)

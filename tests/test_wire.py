@@ -104,6 +104,22 @@ def test_gpu_wire_upload_solves_like_the_expanded_batch(oracle):
         x3 = c.get_states()
     assert np.array_equal(x3, x1) and np.array_equal(s3["iterations"], s1["iterations"])
     wire.imu_compact = None
+    # one line list per window (every frame of a window matched against the same sub-map): identical results
+    n, lo = hb.n_frames, hb["line_offset"]
+    per = np.diff(lo)
+    if np.all(per == per[0]):
+        l3 = hb["lines"].reshape(hb.n_windows, n, int(per[0]), 4)
+        if np.all(l3 == l3[:, :1]):
+            wire.shared_lines = True
+            sh = bare.replace(lines=l3[:, 0].reshape(-1, 4), line_offset=np.arange(hb.n_windows + 1, dtype=np.int64) * int(per[0]))
+            with Context(P) as c:
+                c.set_windows_wire(sh, wire)
+                s4 = c.solve()
+                x4 = c.get_states()
+            assert np.array_equal(x4, x1) and np.array_equal(s4["iterations"], s1["iterations"])
+            wire.shared_lines = False
+        else:
+            pytest.fail("the synthetic windows are expected to share their sub-map lines")
     # beams without a line take no part: knock out every third beam on the wire and in the expanded batch alike
     wire.beam_line[:, ::3] = abi.ScanWire.NONE
     pts, line, off = wire.points()
