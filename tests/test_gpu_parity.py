@@ -403,6 +403,10 @@ def test_fused_small_solve_matches_three_kernel_loop(oracle, monkeypatch):
         P = L.corridor_params(max_iters=iters)
         hb = oracle.preintegrate_batch(P, CASES[case]())
         res = {}
+        # the fused kernel runs eight warps per window; the loop is pinned to the same thread-group shape (its default for a
+        # batch this small is the cyclic-reduction shape, which eliminates in another order: equal to ~1e-12, covered by
+        # test_solve_matches_oracle[512-*])
+        monkeypatch.setenv("LVIO2D_WINDOW_THREADS", "256")
         for fused in ("1", "0"):
             monkeypatch.setenv("LVIO2D_FUSED_SMALL", fused)
             with Context(P) as c:
