@@ -442,6 +442,8 @@ int setup_batch(lvio2d_ctx* ctx, const lvio2d_window_batch* b, bool bind, bool a
     if (window_smem_bytes(ctx) > 200 * 1024) return fail(ctx, LVIO2D_ERR_DOMAIN, "n_frames too large for shared memory");
 
     int rc;
+    const float* wire_r = nullptr; const float* wire_a = nullptr; const uint16_t* wire_l = nullptr;
+    const double4* shared_src = nullptr; const int64_t* shared_off = nullptr;
     if (wire && has_laser) {
         // compact wire encoding (lvio2d_set_windows_wire): float32 ranges + uint16 line indices travel, the double points
         // and int32 indices the scan-match kernel streams are rebuilt on the device
@@ -451,9 +453,9 @@ int setup_batch(lvio2d_ctx* ctx, const lvio2d_window_batch* b, bool bind, bool a
         if ((rc = take<float>(ctx, false, ctx->b_wa, d_a, wire->angle, (size_t)F * 2))) return rc;
         if ((rc = take<uint16_t>(ctx, false, ctx->b_wl, d_l, wire->beam_line, N))) return rc;
         if (!ctx->b_points.ensure(N * sizeof(double2)) || !ctx->b_pline.ensure(N * sizeof(int32_t))) return fail(ctx, LVIO2D_ERR_ALLOC, "cudaMalloc(points)");
-        expand_wire_kernel<<<(unsigned)((N + 255) / 256), 256, 0, ctx->stream>>>(d_r, d_a, d_l, wire->n_beams, (int64_t)N, ctx->b_points.as<double2>(), ctx->b_pline.as<int32_t>());
-        CK(cudaGetLastError());
-        ctx->launches += 1;
+        // (launched below, behind every host -> device copy of this upload: a kernel in the middle of the copy sequence waits
+        // for SMs that other contexts' solves keep busy, and the copies queued behind it leave PCIe idle meanwhile)
+        wire_r = d_r; wire_a = d_a; wire_l = d_l;
         ctx->points = ctx->b_points.as<double2>(); ctx->point_line = ctx->b_pline.as<int32_t>(); ctx->point_weight = nullptr;
         ctx->has_weight = false;
     } else {
@@ -469,11 +471,7 @@ int setup_batch(lvio2d_ctx* ctx, const lvio2d_window_batch* b, bool bind, bool a
         if ((rc = take<int64_t>(ctx, false, ctx->b_wso, d_wo, ctx->h_woff.data(), (size_t)B + 1))) return rc;
         if (!ctx->b_lines.ensure(std::max<size_t>(1, (size_t)ctx->L) * sizeof(double4))) return fail(ctx, LVIO2D_ERR_ALLOC, "cudaMalloc(lines)");
         ctx->lines = ctx->b_lines.as<double4>();
-        if (ctx->L > 0 && d_sl) {
-            expand_shared_lines_kernel<<<F, 128, 0, ctx->stream>>>(d_sl, d_wo, ctx->line_offset, n, F, ctx->b_lines.as<double4>());
-            CK(cudaGetLastError());
-            ctx->launches += 1;
-        }
+        if (ctx->L > 0 && d_sl) { shared_src = d_sl; shared_off = d_wo; }
     } else if ((rc = take<double4>(ctx, bind, ctx->b_lines, ctx->lines, has_laser ? b->lines : nullptr, (size_t)ctx->L))) return rc;
     if ((rc = take<int32_t>(ctx, false, ctx->b_ref, ctx->ref_frame, rf.data(), (size_t)F))) return rc;
     if ((rc = take<uint8_t>(ctx, false, ctx->b_cmask, ctx->const_mask, cm.data(), (size_t)F))) return rc;
@@ -501,6 +499,17 @@ int setup_batch(lvio2d_ctx* ctx, const lvio2d_window_batch* b, bool bind, bool a
     CK(cudaMemcpyAsync(ctx->b_active.p, active.data(), F, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(ctx->b_active1.p, active1.data(), F, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaEventRecord(ctx->ev_staged, ctx->stream));   // every copy out of the staging vectors is enqueued
+    if (wire_r) {
+        const size_t N = (size_t)ctx->N;
+        expand_wire_kernel<<<(unsigned)((N + 255) / 256), 256, 0, ctx->stream>>>(wire_r, wire_a, wire_l, wire->n_beams, (int64_t)N, ctx->b_points.as<double2>(), ctx->b_pline.as<int32_t>());
+        CK(cudaGetLastError());
+        ctx->launches += 1;
+    }
+    if (shared_src) {
+        expand_shared_lines_kernel<<<F, 128, 0, ctx->stream>>>(shared_src, shared_off, ctx->line_offset, n, F, ctx->b_lines.as<double4>());
+        CK(cudaGetLastError());
+        ctx->launches += 1;
+    }
     CK(cudaMemsetAsync(ctx->b_part.p, 0, (size_t)F * ctx->tiles * ctx->npad * sizeof(double), ctx->stream));
     if (ctx->prior_frame >= 0) {
         // J^T J of the marginalisation prior: constant over the solve, so the factor kernel adds it instead of recomputing it
