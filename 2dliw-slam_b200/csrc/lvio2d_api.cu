@@ -100,7 +100,6 @@ struct lvio2d_ctx {
     bool factor_paired = true; // LVIO2D_FACTOR_PAIRED=0 selects the one-item-per-warp factor kernel
     bool fused_small = true;   // LVIO2D_FUSED_SMALL=0: batches of <= #SM windows also go through the three-kernel loop
     bool have_solution = false;
-    bool direct = false;       // the flow in progress lets scan-match write the laser blocks in place (tiles == 1, one rank)
     // host staging of the small index arrays (kept alive until the next upload so that copies can stay asynchronous)
     PinnedVec<int64_t> h_poff, h_loff, h_woff;
     cudaEvent_t ev_staged = nullptr;   // recorded behind the last copy out of the staging vectors of an upload
@@ -221,10 +220,6 @@ ScanMatchArgs scan_args(lvio2d_ctx* ctx, int mode) {
     a.assoc_max_dist = ctx->params.assoc_max_dist > 0 ? ctx->params.assoc_max_dist : 0.5;
     a.assoc_grid_par = ctx->assoc_grid ? ctx->b_agp.as<double>() : nullptr;
     a.assoc_grid_mask = ctx->assoc_grid ? ctx->b_agm.as<unsigned long long>() : nullptr;
-    a.direct_blocks = ctx->direct ? ctx->b_lb.as<double>() : nullptr;
-    a.cur = &ctx->b_state.as<LMState>()->cur;
-    a.cur_stride = (int32_t)(sizeof(LMState) / sizeof(int32_t));
-    a.n_total_frames = ctx->B * ctx->n;
     return a;
 }
 
@@ -242,7 +237,6 @@ WindowArgs window_args(lvio2d_ctx* ctx, int mode) {
     a.laser_blocks = ctx->b_lb.as<double>(); a.frame_tab = ctx->b_ftab.as<double>();
     a.items = ctx->b_items.as<double>(); a.vec = ctx->b_vec.as<double>(); a.fac = ctx->b_fac.as<double>();
     a.state = ctx->b_state.as<LMState>(); a.win_status = ctx->b_status.as<int32_t>();
-    a.direct_blocks = ctx->direct ? 1 : 0;
     return a;
 }
 
@@ -735,7 +729,6 @@ int lvio2d_eval_laser(lvio2d_ctx* ctx) {
     if (!ctx) return LVIO2D_ERR_INVALID_ARG;
     if (!ctx->have) return fail(ctx, LVIO2D_ERR_NO_WINDOW, "eval_laser");
     CK(cudaSetDevice(ctx->device));
-    ctx->direct = false;   // the blocks travel through the reduce buffer
     int rc = launch_scan_match(ctx);
     if (rc) return rc;
     const int F = ctx->B * ctx->n;
@@ -767,7 +760,6 @@ int lvio2d_lm_step(lvio2d_ctx* ctx, int32_t* n_active) {
     if (!ctx) return LVIO2D_ERR_INVALID_ARG;
     if (!ctx->have) return fail(ctx, LVIO2D_ERR_NO_WINDOW, "lm_step");
     CK(cudaSetDevice(ctx->device));
-    ctx->direct = false;
     WindowArgs a = window_args(ctx, 0);
     // the (all-reduced) per-frame blocks stand in for the tile partials
     a.partial = ctx->ext_reduce ? ctx->ext_reduce : ctx->b_reduce.as<double>();
@@ -795,7 +787,6 @@ int lvio2d_solve_async(lvio2d_ctx* ctx) {
     CK(cudaSetDevice(ctx->device));
     int rc = begin_solve(ctx);
     if (rc) return rc;
-    ctx->direct = ctx->tiles == 1 && ctx->shard_world == 1;
     WindowArgs a = window_args(ctx, 0);
     // small batches: the whole loop in one launch, one CTA per window (solve_small_kernel)
     {
@@ -892,7 +883,6 @@ int lvio2d_linearize(lvio2d_ctx* ctx, int32_t mode, double* H, double* g, double
     if (!ctx->b_tmp[0].ensure(ctx->B * dim * dim * sizeof(double)) || !ctx->b_tmp[1].ensure(ctx->B * dim * sizeof(double)) ||
         !ctx->b_tmp[2].ensure(ctx->B * sizeof(double)))
         return fail(ctx, LVIO2D_ERR_ALLOC, "cudaMalloc(linearize)");
-    ctx->direct = false;
     WindowArgs a = window_args(ctx, mode);
     a.dense_H = ctx->b_tmp[0].as<double>(); a.dense_g = ctx->b_tmp[1].as<double>(); a.dense_cost = ctx->b_tmp[2].as<double>();
     int rc = run_linearize(ctx, mode, a);
@@ -913,7 +903,6 @@ int lvio2d_marginalize(lvio2d_ctx* ctx, double* X0, double* J_lin, double* r_lin
         !ctx->b_tmp[5].ensure((size_t)B * 15 * sizeof(double)) || !ctx->b_tmp[6].ensure((size_t)B * 225 * sizeof(double)) ||
         !ctx->b_tmp[7].ensure((size_t)B * 15 * sizeof(double)))
         return fail(ctx, LVIO2D_ERR_ALLOC, "cudaMalloc(marginalize)");
-    ctx->direct = false;
     WindowArgs a = window_args(ctx, 1);
     a.marg_H = ctx->b_tmp[3].as<double>(); a.marg_g = ctx->b_tmp[4].as<double>();
     int rc = run_linearize(ctx, 1, a);

@@ -64,13 +64,6 @@ struct ScanMatchArgs {
     const uint8_t* frame_active;    // [F] 1 when the frame's laser residual block is part of the program
     const int32_t* win_status;      // [B] 0 = window still iterating
     double* partial;                // [F][tiles][pad]
-    // tiles == 1, no exchange between ranks: a frame's block IS its one tile, so the warp writes it straight into the
-    // parity buffer the window kernel reads the candidate's linearisation from (direct_blocks [2][F][pad], parity
-    // 1 - cur of the window), and the window kernel's copy pass over `partial` disappears
-    double* direct_blocks;          // or nullptr
-    const int32_t* cur;             // &state[0].cur
-    int32_t cur_stride;             // in int32 units
-    int32_t n_total_frames;
     int32_t n_frames;               // frames per window
     int32_t tiles;
     int32_t n_items;                // F * tiles
@@ -151,8 +144,6 @@ __device__ __forceinline__ void scan_match_item(const ScanMatchArgs& a, const in
     int wstat = 0, fact;
     int64_t p0, p1, l0, l1;
     asm volatile("ld.global.s32 %0, [%1];" : "=r"(wstat) : "l"(a.win_status + f / a.n_frames));
-    int wcur = 0;
-    if (a.direct_blocks) asm volatile("ld.global.s32 %0, [%1];" : "=r"(wcur) : "l"(a.cur + (size_t)(f / a.n_frames) * a.cur_stride));
     asm volatile("ld.global.u8 %0, [%1];" : "=r"(fact) : "l"(a.frame_active + f));
     if (uni) {
         p0 = (int64_t)f * a.uniform_pts; p1 = p0 + a.uniform_pts;
@@ -466,7 +457,7 @@ __device__ __forceinline__ void scan_match_item(const ScanMatchArgs& a, const in
 
     int base = 0, len = NACC;
     ReduceScatter<NACC, 16>::run(acc, lane, base, len);
-    double* out = a.direct_blocks ? a.direct_blocks + ((size_t)(1 - wcur) * a.n_total_frames + f) * NPAD : a.partial + (size_t)item * NPAD;
+    double* out = a.partial + (size_t)item * NPAD;
     constexpr int OUTN = halved5(NACC);
 #pragma unroll
     for (int i = 0; i < OUTN; ++i)

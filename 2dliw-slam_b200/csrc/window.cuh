@@ -130,7 +130,6 @@ struct WindowArgs {
     // optional marginalisation outputs
     double* marg_H;                 // [B][225] Schur complement on the last frame
     double* marg_g;                 // [B][15]
-    int direct_blocks;              // 1: scan-match wrote the candidate's laser blocks in place (ScanMatchArgs::direct_blocks)
     int cr_scratch;                 // cyclic-reduction shape (NT = 512): scratch blocks behind the fixed arrays (0..13)
 };
 
@@ -957,12 +956,7 @@ __device__ void window_step(const WindowArgs& a, int w, int lane, double* ws, co
 
     // ---- (1) candidate laser blocks: sum the tiles in a fixed order; candidate cost
     double csum = 0.0;
-    if (a.direct_blocks) {
-        // the blocks are already where they belong; only the candidate cost is summed (inactive frames hold stale data:
-        // every later read of a frame's block is guarded by its active flag)
-        for (int f = lane; f < n; f += NT)
-            if (fa[f]) csum += lsq * lb_c[f * NPAD + ICOST];
-    } else if (a.tiles == 1) {
+    if (a.tiles == 1) {
         // one tile per frame (the batched shape): 4 independent loads per lane in flight
         const double* pw = a.partial + (size_t)w * n * NPAD;
         for (int i0 = lane; i0 < n * NPAD; i0 += 4 * NT) {
