@@ -399,7 +399,7 @@ def run_ours(args):
         n_chunks = max(1, args.e2e_chunks)
         per = (B + n_chunks - 1) // n_chunks
         bounds = [(k * per, min(B, (k + 1) * per)) for k in range(n_chunks) if k * per < B]
-        ectx = [ctx] + [Context(P) for _ in range(max(0, min(args.e2e_contexts, n_chunks) - 1))]
+        ectx = [ctx] + [Context(P) for _ in range(max(0, min(args.e2e_contexts, 2 * n_chunks) - 1))]
         nf = hb.n_frames
 
         def timed(enqueue):
@@ -460,9 +460,15 @@ def run_ours(args):
             e2e_shared = shared
             e2e_bytes = int(sum(bare.nbytes() + wk.nbytes() for bare, wk in wchunks))
 
+            parity = [0]
+
             def e2e_wire_step():
+                # with at least twice as many contexts as chunks, consecutive steps alternate between two sets of contexts:
+                # the upload of step s + 1 never queues behind the solve of step s on the same stream (double buffering)
+                shift = len(bounds) * parity[0] if len(ectx) >= 2 * len(bounds) else 0
+                parity[0] ^= 1
                 for k, ((a, b), (bare, wk)) in enumerate(zip(bounds, wchunks)):
-                    c = ectx[k % len(ectx)]
+                    c = ectx[(k + shift) % len(ectx)]
                     c.set_windows_wire(bare, wk, async_=True)
                     c.solve_async()
                     c.get_states_async(out_np[a * nf:b * nf])

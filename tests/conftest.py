@@ -13,6 +13,17 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run with -m gpu on a B200 box)")
 
 
+@pytest.fixture(autouse=True)
+def _production_factor_kernel(monkeypatch):
+    """Small batches would get the one-item-per-warp factor kernel by the library's batch-size rule; the tests pin the
+    two-items-per-warp kernel the large batches of the bench run, unless a test (or the environment) chooses itself."""
+    import os
+
+    if "LVIO2D_FACTOR_PAIRED" not in os.environ:
+        monkeypatch.setenv("LVIO2D_FACTOR_PAIRED", "1")
+    yield
+
+
 @pytest.fixture(scope="session")
 def oracle():
     import oracle_lib

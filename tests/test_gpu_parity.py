@@ -383,13 +383,17 @@ def test_paired_and_single_factor_kernels_agree(oracle, monkeypatch):
     res = {}
     for case in ("c2_small", "tracking2", "init"):
         hb = oracle.preintegrate_batch(P, CASES[case]())
-        for paired in ("1", "0"):
-            monkeypatch.setenv("LVIO2D_FACTOR_PAIRED", paired)
+        for paired in ("1", "0", "auto"):
+            if paired == "auto":
+                monkeypatch.delenv("LVIO2D_FACTOR_PAIRED")     # the library's own rule: one item per warp for a batch this small
+            else:
+                monkeypatch.setenv("LVIO2D_FACTOR_PAIRED", paired)
             with Context(P) as c:
                 c.set_windows(hb)
                 H, g, cost = c.linearize(0)
                 c.solve()
                 res[paired] = (H, g, cost, c.get_states())
+        assert all(np.array_equal(x, y) for x, y in zip(res["auto"], res["0"]))
         for a, b in zip(res["1"], res["0"]):
             relclose(a, b, 1e-12, case)
 
