@@ -321,12 +321,67 @@ __device__ __forceinline__ void scan_match_item(const ScanMatchArgs& a, const in
 #pragma unroll
         for (int u = 0; u < U; ++u) { c[u] = nc[u]; li[u] = nli[u]; if constexpr (HAS_WEIGHT) w[u] = nw[u]; }
         issue(base + 32 * U);
+        bool assoc_done = false;
+        if constexpr (ASSOC && !REF_FREE) {
+            if (use_grid) {
+                // Nearest line by perpendicular distance among the lines whose extent (+gate) contains the foot, for the
+                // warp's U x 32 points at once.  Only lines registered in a point's grid cell can pass the test for it, so
+                // testing MORE lines than a point's own cell lists changes nothing: the warp walks the UNION of the cell
+                // masks of all its points (128 consecutive beams: a few cells) in one uniform loop — no divergence, one
+                // broadcast load of a candidate for U points — in increasing line order, so that ties resolve exactly like
+                // the all-lines loop.
+                double X[U], Y[U], bd[U];
+                int bl[U];
+                unsigned long long m0 = 0ull, m1 = 0ull;
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    X[u] = fma(T[0], c[u].x, fma(T[1], c[u].y, T[4]));
+                    Y[u] = fma(T[2], c[u].x, fma(T[3], c[u].y, T[5]));
+                    const double gx = (X[u] - gx0) * gix, gy = (Y[u] - gy0) * giy;
+                    const bool inside = li[u] >= 0 && gx >= 0.0 && gx < (double)kAssocG && gy >= 0.0 && gy < (double)kAssocG;
+                    const int cell = inside ? (int)gy * kAssocG + (int)gx : 0;
+                    const ulonglong2 mm = *reinterpret_cast<const ulonglong2*>(gmask + 2 * cell);
+                    if (inside) { m0 |= mm.x; m1 |= mm.y; }
+                    bd[u] = a.assoc_max_dist;
+                    bl[u] = inside ? -1 : -2;      // -2: no correspondence, or outside every line's reach
+                }
+                unsigned un[4];
+                un[0] = __reduce_or_sync(0xffffffffu, (unsigned)m0);
+                un[1] = __reduce_or_sync(0xffffffffu, (unsigned)(m0 >> 32));
+                un[2] = __reduce_or_sync(0xffffffffu, (unsigned)m1);
+                un[3] = __reduce_or_sync(0xffffffffu, (unsigned)(m1 >> 32));
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    unsigned m = un[q];
+                    while (m) {
+                        const int l = 32 * q + __ffs((int)m) - 1;
+                        m &= m - 1;
+                        const double* qr = tab + l * ROW;
+                        const double2 nn = *reinterpret_cast<const double2*>(qr + 12);
+                        const double2 ds = *reinterpret_cast<const double2*>(qr + 18);
+                        const double hi = qr[17] + a.assoc_gate;
+#pragma unroll
+                        for (int u = 0; u < U; ++u) {
+                            const double dd = fma(nn.x, X[u], fma(nn.y, Y[u], -ds.x));
+                            const double tt = fma(nn.y, X[u], fma(-nn.x, Y[u], -ds.y));
+                            const double ad = fabs(dd);
+                            if (tt >= -a.assoc_gate && tt <= hi && ad < bd[u]) { bd[u] = ad; bl[u] = (bl[u] == -2) ? -2 : l; }
+                        }
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < U; ++u) li[u] = bl[u];
+                assoc_done = true;
+            }
+        }
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             if constexpr (!(ASSOC && !REF_FREE)) { if (li[u] < 0) continue; }
             if constexpr (!ASSOC) { if (li[u] >= nl) continue; }   // an index beyond the frame's line list takes no part (never an out-of-table read)
-            if constexpr (ASSOC) {
-                // nearest line by perpendicular distance among the lines whose extent (+gate) contains the foot
+            if constexpr (ASSOC && !REF_FREE) { if (assoc_done && li[u] < 0) continue; }
+            if constexpr (ASSOC) { if (!assoc_done) {
+                // nearest line by perpendicular distance among the lines whose extent (+gate) contains the foot (the
+                // all-lines loop: initialisation topology, or no candidate grid)
                 int best = -1;
                 double best_d = a.assoc_max_dist;
                 auto test_line = [&](const int l) {
@@ -351,37 +406,14 @@ __device__ __forceinline__ void scan_match_item(const ScanMatchArgs& a, const in
                         const double ad = fabs(dd);
                         if (tt >= -a.assoc_gate && tt <= len + a.assoc_gate && ad < best_d) { best_d = ad; best = l; }
                     };
-                    if (use_grid) {
-                        // Only lines registered in a cell can pass the test for a point of that cell, so testing MORE lines
-                        // than the point's own cell lists changes nothing: the warp tests the UNION of its 32 points' cell
-                        // masks (32 consecutive beams: one to three cells) in one uniform loop — no divergence, broadcast
-                        // loads — in increasing line order, so that ties resolve exactly like the all-lines loop.
-                        const double gx = (X - gx0) * gix, gy = (Y - gy0) * giy;
-                        const bool inside = li[u] >= 0 && gx >= 0.0 && gx < (double)kAssocG && gy >= 0.0 && gy < (double)kAssocG;
-                        const int cell = inside ? (int)gy * kAssocG + (int)gx : 0;
-                        const ulonglong2 mm = *reinterpret_cast<const ulonglong2*>(gmask + 2 * cell);
-                        const unsigned long long m0 = inside ? mm.x : 0ull, m1 = inside ? mm.y : 0ull;
-                        unsigned un[4];
-                        un[0] = __reduce_or_sync(0xffffffffu, (unsigned)m0);
-                        un[1] = __reduce_or_sync(0xffffffffu, (unsigned)(m0 >> 32));
-                        un[2] = __reduce_or_sync(0xffffffffu, (unsigned)m1);
-                        un[3] = __reduce_or_sync(0xffffffffu, (unsigned)(m1 >> 32));
-#pragma unroll
-                        for (int q = 0; q < 4; ++q) {
-                            unsigned m = un[q];
-                            while (m) { const int l = 32 * q + __ffs((int)m) - 1; m &= m - 1; test_world(l); }
-                        }
-                        if (!inside) continue;   // no correspondence, or outside every line's reach
-                    } else {
-                        if (li[u] < 0) continue;
-                        for (int l = 0; l < nl; ++l) test_world(l);
-                    }
+                    if (li[u] < 0) continue;
+                    for (int l = 0; l < nl; ++l) test_world(l);
                 } else {
                     for (int l = 0; l < nl; ++l) test_line(l);
                 }
                 if (best < 0) continue;
                 li[u] = best;
-            }
+            } }
             const double* r = tab + li[u] * ROW;
             const double2 r01 = *reinterpret_cast<const double2*>(r);
             const double2 r23 = *reinterpret_cast<const double2*>(r + 2);
