@@ -420,3 +420,111 @@ def test_fused_small_solve_matches_three_kernel_loop(oracle, monkeypatch):
         assert np.array_equal(res["1"][0], res["0"][0]), case
         relclose(res["1"][1], res["0"][1], 1e-12, case + " cost")
         relclose(res["1"][2], res["0"][2], 1e-12, case + " states")
+
+
+def _ragged(hb, keep_points, keep_lines=None, unmatched_frame=None):
+    """The same windows with frame f keeping only its first keep_points[f] points (and keep_lines[f] lines; points whose
+    line was cut become unmatched), optionally every point of one frame unmatched."""
+    po, lo = hb["point_offset"], hb["line_offset"]
+    pts, pl, ln = hb["points"].reshape(-1, 2), hb["point_line"].reshape(-1), hb["lines"].reshape(-1, 4)
+    F = len(po) - 1
+    P2, L2, I2, O2, LO2 = [], [], [], [0], [0]
+    for f in range(F):
+        kp = min(int(keep_points[f]), int(po[f + 1] - po[f]))
+        kl = int(lo[f + 1] - lo[f]) if keep_lines is None else min(int(keep_lines[f]), int(lo[f + 1] - lo[f]))
+        idx = pl[po[f]:po[f] + kp].copy()
+        idx[idx >= kl] = -1
+        if unmatched_frame is not None and f == unmatched_frame:
+            idx[:] = -1
+        P2.append(pts[po[f]:po[f] + kp]); I2.append(idx); L2.append(ln[lo[f]:lo[f] + kl])
+        O2.append(O2[-1] + kp); LO2.append(LO2[-1] + kl)
+    return hb.replace(points=np.concatenate(P2).reshape(-1, 2), point_line=np.concatenate(I2), point_offset=np.array(O2, np.int64),
+                      lines=np.concatenate(L2).reshape(-1, 4), line_offset=np.array(LO2, np.int64), point_weight=None)
+
+
+@pytest.mark.parametrize("wt", [32, 256, 512])
+def test_ragged_and_degenerate_windows_match_oracle(oracle, wt, monkeypatch):
+    """Ragged batches take the offset-table path of the scan-match kernel (the bench's uniform batches take the arithmetic
+    one): frames with different point and line counts, a frame without points, a frame whose points are all unmatched, a
+    frame whose local map lost most of its lines — normal equations and the 10-iteration solve against the oracle."""
+    from lvio2d_b200.solver import Context
+
+    monkeypatch.setenv("LVIO2D_WINDOW_THREADS", str(wt))
+    monkeypatch.setenv("LVIO2D_FUSED_SMALL", "0")
+    P = L.corridor_params(max_iters=10)
+    sb = L.synth.make_batch(3, 77, n_frames=6, beams=240, fov_deg=270.0)
+    hb0 = oracle.preintegrate_batch(P, sb)
+    F = 18
+    g = np.random.default_rng(5)
+    keep = g.integers(40, 241, F)
+    keep[4] = 0                                  # a frame without points
+    keep[9] = 1
+    lines = g.integers(3, 60, F)
+    lines[13] = 2                                # most correspondences of this frame point at lines that are gone
+    hb = _ragged(hb0, keep, lines, unmatched_frame=7)
+    assert len(set(np.diff(hb["point_offset"]))) > 5
+    with Context(P) as c:
+        c.set_windows(hb)
+        H, gr, cost = c.linearize(0)
+        summ = c.solve()
+        got = c.get_states()
+    oH, og, ocost = oracle.linearize(P, hb, mode=0)
+    relclose(cost, ocost, 1e-11, "cost")
+    relclose(gr, og, 1e-9, "gradient")
+    relclose(H, oH, 1e-9, "hessian")
+    want, osumm = oracle.solve(P, hb)
+    assert np.array_equal(summ["iterations"], osumm["iterations"]) and np.array_equal(summ["num_successful_steps"], osumm["num_successful_steps"])
+    assert np.abs(got - want).max() < 1e-9
+    assert np.all(summ["final_cost"] <= summ["initial_cost"])
+
+
+def test_longest_window_and_single_frame(oracle):
+    """n_frames = 64 is the longest window the ABI accepts (65 is a domain error); a window of one frame has no IMU /
+    wheel factor at all."""
+    from lvio2d_b200.solver import Context, Lvio2dError
+
+    P = L.corridor_params(max_iters=5)
+    for n in (64, 1):
+        sb = L.synth.make_batch(2, 11, n_frames=n, beams=60, fov_deg=270.0)
+        hb = oracle.preintegrate_batch(P, sb)
+        with Context(P) as c:
+            c.set_windows(hb)
+            summ = c.solve()
+            got = c.get_states()
+        want, osumm = oracle.solve(P, hb)
+        assert np.array_equal(summ["iterations"], osumm["iterations"]), n
+        assert np.abs(got - want).max() < 1e-8, (n, np.abs(got - want).max())
+    sb = L.synth.make_batch(1, 11, n_frames=65, beams=20, fov_deg=270.0)
+    hb = oracle.preintegrate_batch(P, sb)
+    with Context(P) as c:
+        with pytest.raises(Lvio2dError):
+            c.set_windows(hb)
+
+
+def test_bench_size_batch_properties():
+    """At the bench's size (148 x 8 windows of 30 x 1081, no oracle run possible): identical windows give identical
+    results wherever they sit in the batch, costs never increase, every window reports the iteration cap, and a second
+    solve started from the first one's result only descends further."""
+    import torch
+
+    import bench
+    from lvio2d_b200.solver import Context
+
+    P = L.corridor_params(max_iters=bench.MAX_ITERS)
+    dev = torch.device("cuda:0")
+    with Context(P) as c:
+        hb, uniq = bench.build_host_batch(c, 1184, seed0=42, config="c2")
+        d, keep = bench.to_device_struct(hb, torch, dev)
+        c.bind_windows(d, keepalive=keep)
+        summ = c.solve()
+        x = c.get_states().reshape(1184, -1)
+        assert np.all(summ["final_cost"] <= summ["initial_cost"]) and np.all(np.isfinite(x))
+        assert np.all(summ["iterations"] == bench.MAX_ITERS)
+        for w in range(uniq, 1184):          # window w is a copy of window w % uniq
+            assert np.array_equal(x[w], x[w % uniq]), w
+        c.reset_states(x.reshape(-1, 15))
+        summ2 = c.solve()
+        x2 = c.get_states().reshape(1184, -1)
+        assert np.all(summ2["final_cost"] <= summ["final_cost"] * (1 + 1e-12))
+        moved = np.abs(x2 - x).reshape(1184, 30, 15)
+        assert moved[:, :, 0:6].max() < 0.1           # ten more iterations from the 10-iteration point (the zig-zag directions still move by centimetres)
