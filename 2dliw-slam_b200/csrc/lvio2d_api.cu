@@ -1217,6 +1217,7 @@ int lvio2d_match_lines(lvio2d_ctx* ctx, const lvio2d_line_params* lp, int32_t n_
 // ---- device-resident reference sub-map (submap.cuh)
 struct lvio2d_submap {
     lvio2d_ctx* ctx = nullptr;
+    int device = 0;            // copies: lvio2d_submap_destroy must not touch a context that is already gone
     int32_t n_managers = 0, line_cap = 0, n_accumulation = 0;
     lvio2d_line_params lp{};
     double filter_p = 0, filter_q = 0;
@@ -1241,7 +1242,7 @@ int lvio2d_submap_create(lvio2d_ctx* ctx, int32_t n_managers, int32_t line_cap, 
     CK(cudaSetDevice(ctx->device));
     lvio2d_submap* sm = new (std::nothrow) lvio2d_submap;
     if (!sm) return fail(ctx, LVIO2D_ERR_ALLOC, "new lvio2d_submap");
-    sm->ctx = ctx; sm->n_managers = n_managers; sm->line_cap = line_cap; sm->n_accumulation = ref_n_accumulation;
+    sm->ctx = ctx; sm->device = ctx->device; sm->n_managers = n_managers; sm->line_cap = line_cap; sm->n_accumulation = ref_n_accumulation;
     sm->lp = *lp; sm->filter_p = ref_motion_filter_p; sm->filter_q = ref_motion_filter_q;
     const size_t M = (size_t)n_managers;
     const bool ok = sm->meta.ensure(M * 4 * sizeof(int32_t)) && sm->sub_pose.ensure(2 * M * 6 * sizeof(double)) && sm->last_pose.ensure(M * 6 * sizeof(double)) &&
@@ -1255,8 +1256,8 @@ int lvio2d_submap_create(lvio2d_ctx* ctx, int32_t n_managers, int32_t line_cap, 
 
 void lvio2d_submap_destroy(lvio2d_submap* sm) {
     if (!sm) return;
-    cudaSetDevice(sm->ctx->device);
-    cudaStreamSynchronize(sm->ctx->stream);
+    cudaSetDevice(sm->device);
+    cudaDeviceSynchronize();   // (not the context's stream: the context may have been destroyed first)
     DevBuf* all[] = {&sm->meta, &sm->sub_pose, &sm->last_pose, &sm->sub_n, &sm->sub_lines, &sm->in_n, &sm->in_lines, &sm->in_pose};
     for (DevBuf* b : all) b->release();
     delete sm;

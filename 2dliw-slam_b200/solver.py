@@ -13,6 +13,7 @@ csrc/liblvio2d.so is missing or no sm_100 device is present, `Context()` raises.
 """
 import ctypes as C
 import os
+import weakref
 
 import numpy as np
 
@@ -131,9 +132,15 @@ class Context:
             raise Lvio2dError(rc, "lvio2d_create", self.lib.lvio2d_strerror(rc).decode())
         self.n_windows = self.n_frames = 0
         self._keep = None
+        self._submaps = []
 
     def close(self):
         if self._h:
+            for ref in self._submaps:      # sub-maps enqueue on this context's stream: they go first
+                sm = ref()
+                if sm is not None:
+                    sm.close()
+            self._submaps = []
             self.lib.lvio2d_destroy(self._h)
             self._h = C.c_void_p()
 
@@ -364,7 +371,9 @@ class Context:
 
     def submap(self, line_params, n_managers=1, line_cap=16384, ref_motion_filter_p=0.01, ref_motion_filter_q=0.01, ref_n_accumulation=100):
         """A batch of device-resident reference sub-maps (laser_manager::add_scan / match_with_ref), see Submap."""
-        return Submap(self, line_params, n_managers, line_cap, ref_motion_filter_p, ref_motion_filter_q, ref_n_accumulation)
+        sm = Submap(self, line_params, n_managers, line_cap, ref_motion_filter_p, ref_motion_filter_q, ref_n_accumulation)
+        self._submaps.append(weakref.ref(sm))
+        return sm
 
     def scan_to_points(self, ranges, headers, deskew=True, want_times=False):
         """convert::laser_to_point_times + sensor::laser::correct for a batch of scans (host buffers).  ranges [S][n_beams]

@@ -372,6 +372,7 @@ typedef struct lvio2d_submap lvio2d_submap;
 int lvio2d_submap_create(lvio2d_ctx* ctx, int32_t n_managers, int32_t line_cap, const lvio2d_line_params* lp,
                          double ref_motion_filter_p, double ref_motion_filter_q, int32_t ref_n_accumulation,
                          lvio2d_submap** out);
+/* (safe after lvio2d_destroy of its context; every other lvio2d_submap_* call needs the context alive) */
 void lvio2d_submap_destroy(lvio2d_submap* sm);
 /* back to "no scan seen" for every manager */
 int lvio2d_submap_reset(lvio2d_submap* sm);
