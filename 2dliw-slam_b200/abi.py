@@ -126,7 +126,7 @@ class ScanWireStruct(C.Structure):
     """lvio2d_scan_wire (include/lvio2d.h)."""
 
     _fields_ = [("n_beams", C.c_int32), ("ranges", C.POINTER(C.c_float)), ("angle", C.POINTER(C.c_float)), ("beam_line", C.POINTER(C.c_uint16)),
-                ("imu_compact", c_double_p), ("shared_lines", C.c_int32), ("reserved", C.c_int32)]
+                ("imu_compact", c_double_p), ("shared_lines", C.c_int32), ("reserved", C.c_int32), ("beam_line8", C.POINTER(C.c_uint8))]
 
 
 class ScanWire:
@@ -138,6 +138,7 @@ class ScanWire:
 
     def __init__(self, ranges, angle, beam_line, imu_compact=None, shared_lines=False):
         self.shared_lines = bool(shared_lines)   # the batch's lines / line_offset are per WINDOW (one sub-map per window)
+        self.beam_line8 = None                    # optional 8-bit flavour of beam_line (narrow())
         self.imu_compact = None if imu_compact is None else np.ascontiguousarray(imu_compact, dtype=np.float64).reshape(-1, IMU_COMPACT)
         self.ranges = np.ascontiguousarray(ranges, dtype=np.float32)
         self.angle = np.ascontiguousarray(angle, dtype=np.float32).reshape(-1, 2)
@@ -153,10 +154,20 @@ class ScanWire:
         s.beam_line = self.beam_line.ctypes.data_as(C.POINTER(C.c_uint16))
         s.imu_compact = ptr(self.imu_compact, c_double_p)
         s.shared_lines, s.reserved = int(self.shared_lines), 0
+        s.beam_line8 = self.beam_line8.ctypes.data_as(C.POINTER(C.c_uint8)) if self.beam_line8 is not None else C.POINTER(C.c_uint8)()
         return s
 
+    def narrow(self):
+        """8-bit line indices (0xFF = none) when every index fits: 5 instead of 6 bytes per beam.  Returns True when used."""
+        valid = self.beam_line != self.NONE
+        if valid.any() and int(self.beam_line[valid].max()) >= 255:
+            return False
+        self.beam_line8 = np.where(valid, self.beam_line, 255).astype(np.uint8)
+        return True
+
     def nbytes(self):
-        return self.ranges.nbytes + self.angle.nbytes + self.beam_line.nbytes + (0 if self.imu_compact is None else self.imu_compact.nbytes)
+        idx = self.beam_line.nbytes if self.beam_line8 is None else self.beam_line8.nbytes
+        return self.ranges.nbytes + self.angle.nbytes + idx + (0 if self.imu_compact is None else self.imu_compact.nbytes)
 
     @staticmethod
     def compact_imu(blobs):

@@ -326,7 +326,8 @@ __global__ void reduce_tiles_kernel(const double* partial, const uint8_t* frame_
 // builds it (reference src/utilies/common.cpp:6-24: float32 angle_min + k * angle_increment with two roundings, the
 // cosine / sine in double, times the float32 range) minus its 1 cm thinning, which has no meaning when every beam
 // carries its own line index: a beam the reference would reject (NaN, inf, <= 0.1 m) or that has no line gets -1.
-__global__ void expand_wire_kernel(const float* __restrict__ ranges, const float* __restrict__ angle, const uint16_t* __restrict__ beam_line,
+template <class IDX>   // uint16_t (0xFFFF = none) or uint8_t (0xFF = none)
+__global__ void expand_wire_kernel(const float* __restrict__ ranges, const float* __restrict__ angle, const IDX* __restrict__ beam_line,
                                    int n_beams, int64_t total, double2* __restrict__ points, int32_t* __restrict__ point_line) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= total) return;
@@ -338,8 +339,8 @@ __global__ void expand_wire_kernel(const float* __restrict__ ranges, const float
     sincos((double)ang, &sn, &cs);
     const bool valid = !isnan(r) && !isinf(r) && (double)r > 0.1;
     points[i] = valid ? make_double2(cs * (double)r, sn * (double)r) : make_double2(0.0, 0.0);
-    const uint16_t l = beam_line[i];
-    point_line[i] = (valid && l != 0xFFFFu) ? (int32_t)l : -1;
+    const IDX l = beam_line[i];
+    point_line[i] = (valid && l != (IDX)~(IDX)0) ? (int32_t)l : -1;
 }
 
 // lvio2d_scan_wire::shared_lines: one line list per window -> the per-frame layout the kernels read

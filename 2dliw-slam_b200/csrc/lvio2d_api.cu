@@ -356,7 +356,8 @@ int setup_batch(lvio2d_ctx* ctx, const lvio2d_window_batch* b, bool bind, bool a
     PinnedVec<uint8_t>&active = ctx->h_active, &active1 = ctx->h_active1;
     if (!poff.assign(F + 1, 0) || !loff.assign(F + 1, 0) || !rf.assign(F, -1) || !cm.assign(F, 0) || !active.assign(F, 0) || !active1.assign(F, 0))
         return fail(ctx, LVIO2D_ERR_ALLOC, "cudaHostAlloc(staging)");
-    if (wire && (bind || wire->n_beams < 1 || !wire->ranges || !wire->angle || !wire->beam_line)) return fail(ctx, LVIO2D_ERR_INVALID_ARG, "scan wire: host arrays ranges / angle / beam_line");
+    if (wire && (bind || wire->n_beams < 1 || !wire->ranges || !wire->angle || (!wire->beam_line && !wire->beam_line8)))
+        return fail(ctx, LVIO2D_ERR_INVALID_ARG, "scan wire: host arrays ranges / angle / beam_line");
     const bool has_laser = wire ? (b->line_offset && b->lines) : (b->point_offset && b->points && b->point_line && b->line_offset && b->lines);
     const bool shared_lines = wire && wire->shared_lines != 0 && has_laser;
     if (bind) {
@@ -445,20 +446,23 @@ int setup_batch(lvio2d_ctx* ctx, const lvio2d_window_batch* b, bool bind, bool a
     if (window_smem_bytes(ctx) > 200 * 1024) return fail(ctx, LVIO2D_ERR_DOMAIN, "n_frames too large for shared memory");
 
     int rc;
-    const float* wire_r = nullptr; const float* wire_a = nullptr; const uint16_t* wire_l = nullptr;
+    const float* wire_r = nullptr; const float* wire_a = nullptr; const uint16_t* wire_l = nullptr; const uint8_t* wire_l8 = nullptr;
     const double4* shared_src = nullptr; const int64_t* shared_off = nullptr;
     if (wire && has_laser) {
         // compact wire encoding (lvio2d_set_windows_wire): float32 ranges + uint16 line indices travel, the double points
         // and int32 indices the scan-match kernel streams are rebuilt on the device
         const size_t N = (size_t)ctx->N;
-        const float* d_r; const float* d_a; const uint16_t* d_l;
+        const float* d_r; const float* d_a; const uint16_t* d_l = nullptr; const uint8_t* d_l8 = nullptr;
         if ((rc = take<float>(ctx, false, ctx->b_wr, d_r, wire->ranges, N))) return rc;
         if ((rc = take<float>(ctx, false, ctx->b_wa, d_a, wire->angle, (size_t)F * 2))) return rc;
-        if ((rc = take<uint16_t>(ctx, false, ctx->b_wl, d_l, wire->beam_line, N))) return rc;
+        if (wire->beam_line8) {
+            if (line_cap > 255) return fail(ctx, LVIO2D_ERR_INVALID_ARG, "beam_line8 needs local maps of at most 255 lines");
+            if ((rc = take<uint8_t>(ctx, false, ctx->b_wl, d_l8, wire->beam_line8, N))) return rc;
+        } else if ((rc = take<uint16_t>(ctx, false, ctx->b_wl, d_l, wire->beam_line, N))) return rc;
         if (!ctx->b_points.ensure(N * sizeof(double2)) || !ctx->b_pline.ensure(N * sizeof(int32_t))) return fail(ctx, LVIO2D_ERR_ALLOC, "cudaMalloc(points)");
         // (launched below, behind every host -> device copy of this upload: a kernel in the middle of the copy sequence waits
         // for SMs that other contexts' solves keep busy, and the copies queued behind it leave PCIe idle meanwhile)
-        wire_r = d_r; wire_a = d_a; wire_l = d_l;
+        wire_r = d_r; wire_a = d_a; wire_l = d_l; wire_l8 = d_l8;
         ctx->points = ctx->b_points.as<double2>(); ctx->point_line = ctx->b_pline.as<int32_t>(); ctx->point_weight = nullptr;
         ctx->has_weight = false;
     } else {
@@ -504,7 +508,10 @@ int setup_batch(lvio2d_ctx* ctx, const lvio2d_window_batch* b, bool bind, bool a
     CK(cudaEventRecord(ctx->ev_staged, ctx->stream));   // every copy out of the staging vectors is enqueued
     if (wire_r) {
         const size_t N = (size_t)ctx->N;
-        expand_wire_kernel<<<(unsigned)((N + 255) / 256), 256, 0, ctx->stream>>>(wire_r, wire_a, wire_l, wire->n_beams, (int64_t)N, ctx->b_points.as<double2>(), ctx->b_pline.as<int32_t>());
+        if (wire_l8)
+            expand_wire_kernel<uint8_t><<<(unsigned)((N + 255) / 256), 256, 0, ctx->stream>>>(wire_r, wire_a, wire_l8, wire->n_beams, (int64_t)N, ctx->b_points.as<double2>(), ctx->b_pline.as<int32_t>());
+        else
+            expand_wire_kernel<uint16_t><<<(unsigned)((N + 255) / 256), 256, 0, ctx->stream>>>(wire_r, wire_a, wire_l, wire->n_beams, (int64_t)N, ctx->b_points.as<double2>(), ctx->b_pline.as<int32_t>());
         CK(cudaGetLastError());
         ctx->launches += 1;
     }

@@ -257,6 +257,11 @@ def pinned_wire(wire, w0, w1, n_frames, torch):
     out = abi.ScanWire(keep[0].numpy(), keep[1].numpy(), keep[2].numpy().view(np.uint16), imu)
     assert out.ranges.ctypes.data == keep[0].data_ptr() and out.beam_line.ctypes.data == keep[2].data_ptr()
     assert imu is None or out.imu_compact.ctypes.data == keep[3].data_ptr()
+    if wire.beam_line8 is not None:     # local maps of <= 255 lines: the indices travel in 8 bits
+        k8 = torch.from_numpy(np.ascontiguousarray(wire.beam_line8[f0:f1])).pin_memory()
+        keep.append(k8)
+        out.beam_line8 = k8.numpy()
+        assert out.beam_line8.ctypes.data == k8.data_ptr()
     out._pinned = keep
     return out
 
@@ -305,6 +310,7 @@ def run_ours(args):
         hb = hb.replace(points=wp, point_line=wl)
         if not args.no_imu_compact:
             wire.imu_compact = abi.ScanWire.compact_imu(hb["imu"])
+        wire.narrow()
     dstruct, keep = to_device_struct(hb, torch, device)
     ext = torch.cuda.ExternalStream(ctx.stream, device=device)
 
@@ -531,7 +537,7 @@ def run_ours(args):
             "value": total_iters_per_step * args.steps / (e2e_ms_all * 1e-3), "unit": UNIT,
             "h2d_bytes_per_step": e2e_bytes, "d2h_bytes_per_step": int(out_states.numel() * 8),
             "ms_per_step": e2e_ms_all / args.steps,
-            "api": (f"lvio2d_set_windows_wire(pinned host: float32 ranges + uint16 line index per beam, {"the sub-map's lines once per window" if e2e_shared else "every frame's lines"}, the 190 doubles of each IMU preintegration the factor reads, wheel blobs, states; async) + "
+            "api": (f"lvio2d_set_windows_wire(pinned host: float32 ranges + {'uint8' if wire.beam_line8 is not None else 'uint16'} line index per beam, {"the sub-map's lines once per window" if e2e_shared else "every frame's lines"}, the 190 doubles of each IMU preintegration the factor reads, wheel blobs, states; async) + "
                     f"lvio2d_solve_async + lvio2d_get_states_async + lvio2d_sync, {args.e2e_chunks} chunks over {args.e2e_contexts} contexts") if wire is not None else
                    f"lvio2d_set_windows_async(pinned host) + lvio2d_solve_async + lvio2d_get_states_async + lvio2d_sync, {args.e2e_chunks} chunks over {args.e2e_contexts} contexts",
         },

@@ -204,6 +204,9 @@ typedef struct lvio2d_scan_wire {
      * layout.  0: line_offset has n_windows * n_frames + 1 entries as for lvio2d_set_windows. */
     int32_t shared_lines;
     int32_t reserved;
+    /* optional, replaces beam_line when not NULL: the same indices in 8 bits (0xFF = no correspondence), for local maps of
+     * at most 255 lines — 5 instead of 6 bytes per beam */
+    const uint8_t* beam_line8;    /* [B*n][n_beams] */
 } lvio2d_scan_wire;
 #define LVIO2D_IMU_COMPACT 190
 int lvio2d_set_windows_wire(lvio2d_ctx* ctx, const lvio2d_window_batch* host_batch, const lvio2d_scan_wire* wire, int32_t async);

@@ -120,6 +120,14 @@ def test_gpu_wire_upload_solves_like_the_expanded_batch(oracle):
             wire.shared_lines = False
         else:
             pytest.fail("the synthetic windows are expected to share their sub-map lines")
+    # 8-bit line indices (local maps of at most 255 lines): identical results
+    assert wire.narrow() and wire.nbytes() < 6 * wire.ranges.size
+    with Context(P) as c:
+        c.set_windows_wire(bare, wire)
+        s5 = c.solve()
+        x5 = c.get_states()
+    assert np.array_equal(x5, x1) and np.array_equal(s5["iterations"], s1["iterations"])
+    wire.beam_line8 = None
     # beams without a line take no part: knock out every third beam on the wire and in the expanded batch alike
     wire.beam_line[:, ::3] = abi.ScanWire.NONE
     pts, line, off = wire.points()
