@@ -102,7 +102,11 @@ struct lvio2d_ctx {
     bool have_solution = false;
     // host staging of the small index arrays (kept alive until the next upload so that copies can stay asynchronous)
     PinnedVec<int64_t> h_poff, h_loff, h_woff;
-    cudaEvent_t ev_staged = nullptr;   // recorded behind the last copy out of the staging vectors of an upload
+    cudaEvent_t ev_staged = nullptr;
+    // the factor kernel of a trip can run on a second stream beside the scan-match kernel (both only read the candidate; fork /
+    // join with events).  Measured: nothing for a batch that fills the machine (26.16 vs 26.20 ms per step: either kernel
+    // occupies every SM), 0.84 vs 0.88 ms for a single window — so it is on for small batches; LVIO2D_OVERLAP=0|1 forces it
+    cudaStream_t stream2 = nullptr; cudaEvent_t ev_fork = nullptr, ev_join = nullptr; int overlap = -1;   // -1: small batches only   // recorded behind the last copy out of the staging vectors of an upload
     DevBuf b_wsl, b_wso;      // lvio2d_scan_wire::shared_lines: the per-window line lists and their offsets
     PinnedVec<int32_t> h_rf;
     PinnedVec<uint8_t> h_cm, h_active, h_active1;
@@ -240,25 +244,26 @@ WindowArgs window_args(lvio2d_ctx* ctx, int mode) {
     return a;
 }
 
-int launch_factors(lvio2d_ctx* ctx, const WindowArgs& a) {
+int launch_factors(lvio2d_ctx* ctx, const WindowArgs& a, cudaStream_t on = nullptr) {
+    const cudaStream_t st = on ? on : ctx->stream;
     const int items = ctx->B * ctx->n;
     // two items per warp is the throughput shape; when the items do not even fill the machine one item per warp is the
     // shorter chain (measured: 19 vs 22 us per launch up to ~1100 items, 53 vs 45 us at 4440)
     const bool paired = ctx->factor_paired < 0 ? items > 8 * ctx->sm_count : ctx->factor_paired != 0;
     const int wpc = paired ? LV_PAIR_WPC : 4;
-    if (ctx->profiling) cudaEventRecord(next_event(ctx->ev_fac, ctx->ev_fac_used), ctx->stream);
+    if (ctx->profiling) cudaEventRecord(next_event(ctx->ev_fac, ctx->ev_fac_used), st);
     ctx->launches += 1;
     if (paired) {
         // two items per warp (half-warp each for the dual-number part, see factor_pair_kernel)
         const int pairs = (items + 1) / 2;
         const size_t smem = (size_t)wpc * kPairSmem * sizeof(double);
         CK(cudaFuncSetAttribute(factor_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        factor_pair_kernel<<<(pairs + wpc - 1) / wpc, wpc * 32, smem, ctx->stream>>>(a);
+        factor_pair_kernel<<<(pairs + wpc - 1) / wpc, wpc * 32, smem, st>>>(a);
     } else {
         const size_t smem = (size_t)wpc * kFactorSmem * sizeof(double);
-        factor_kernel<<<(items + wpc - 1) / wpc, wpc * 32, smem, ctx->stream>>>(a);
+        factor_kernel<<<(items + wpc - 1) / wpc, wpc * 32, smem, st>>>(a);
     }
-    if (ctx->profiling) cudaEventRecord(next_event(ctx->ev_fac, ctx->ev_fac_used), ctx->stream);
+    if (ctx->profiling) cudaEventRecord(next_event(ctx->ev_fac, ctx->ev_fac_used), st);
     CK(cudaGetLastError());
     return LVIO2D_OK;
 }
@@ -614,6 +619,13 @@ int lvio2d_create(lvio2d_ctx** out, const lvio2d_params* params) {
     if (const char* wt = std::getenv("LVIO2D_WINDOW_THREADS")) ctx->window_threads = std::atoi(wt);
     if (const char* fp = std::getenv("LVIO2D_FACTOR_PAIRED")) ctx->factor_paired = std::atoi(fp) != 0 ? 1 : 0;
     if (const char* fs = std::getenv("LVIO2D_FUSED_SMALL")) ctx->fused_small = std::atoi(fs) != 0;
+    if (cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming) != cudaSuccess) {
+        lvio2d_destroy(ctx);
+        return LVIO2D_ERR_CUDA;
+    }
+    if (const char* ov = std::getenv("LVIO2D_OVERLAP")) ctx->overlap = std::atoi(ov) != 0 ? 1 : 0;
     *out = ctx;
     return LVIO2D_OK;
 }
@@ -638,6 +650,9 @@ void lvio2d_destroy(lvio2d_ctx* ctx) {
     for (auto e : ctx->ev_win) cudaEventDestroy(e);
     for (auto e : ctx->ev_fac) cudaEventDestroy(e);
     if (ctx->ev_staged) cudaEventDestroy(ctx->ev_staged);
+    if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+    if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
+    if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -825,9 +840,19 @@ int lvio2d_solve_async(lvio2d_ctx* ctx) {
         }
     }
     // trip 0 linearises the initial point; trips 1..max_iters each judge one candidate
+    const bool overlap = ctx->N > 0 && !ctx->profiling && (ctx->overlap < 0 ? ctx->B <= 3 * ctx->sm_count : ctx->overlap != 0);
     for (int it = 0; it <= ctx->opt.max_iters; ++it) {
-        if ((rc = launch_scan_match(ctx))) return rc;
-        if ((rc = launch_factors(ctx, a))) return rc;
+        if (overlap) {
+            CK(cudaEventRecord(ctx->ev_fork, ctx->stream));
+            CK(cudaStreamWaitEvent(ctx->stream2, ctx->ev_fork, 0));
+            if ((rc = launch_factors(ctx, a, ctx->stream2))) return rc;
+            CK(cudaEventRecord(ctx->ev_join, ctx->stream2));
+            if ((rc = launch_scan_match(ctx))) return rc;
+            CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
+        } else {
+            if ((rc = launch_scan_match(ctx))) return rc;
+            if ((rc = launch_factors(ctx, a))) return rc;
+        }
         if ((rc = launch_window(ctx, a))) return rc;
     }
     ctx->have_solution = true;
