@@ -714,6 +714,40 @@ def front_end_rates(P, torch, device, n_scans=4096, reps=10, cpu=True):
         out["scan_lines"] = row(ms_l, npts * 24.0 + nlines * 72.0 + S * 16.0, {"lines_found": nlines})
         out["match_lines"] = row(ms_m, npts * 16.0 + 2 * nlines * 32.0 + nlines * 8.0 + S * 96.0 + nmatch * 8.0, {"pairs_matched": nmatch})
         out["chain_ms_per_4096_scans"] = ms_p + ms_l + ms_m
+        # row f2, second half: the reference sub-map resident on the device, one laser manager per scan stream.  Every
+        # manager first accumulates 20 scans (poses 2 cm apart), then match_with_ref + add_scan are timed per frame.
+        sm = c.submap(lp, S, 4096, 0.01, 0.01, 100)
+        poses = np.zeros((S, 6))
+        d_pose2 = torch.zeros(S * 6, dtype=torch.float64, device=device)
+
+        def step_pose(k):
+            poses[:, 0] = 0.02 * k
+            d_pose2.copy_(torch.from_numpy(poses.reshape(-1)))
+
+        def k_submap():
+            sm.match_device(ML, d_n.data_ptr(), d_lines.data_ptr(), d_pose2.data_ptr(), d_nm.data_ptr(), d_m.data_ptr())
+            sm.add_scan_device(ML, d_n.data_ptr(), d_lines.data_ptr(), d_pose2.data_ptr())
+
+        for k in range(20):
+            step_pose(k)
+            k_submap()
+        c.sync()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ms_s = 0.0
+        for k in range(20, 20 + reps):
+            step_pose(k)
+            torch.cuda.synchronize(device)
+            e0.record(stream)
+            k_submap()
+            e1.record(stream)
+            c.sync()
+            ms_s += e0.elapsed_time(e1) / reps
+        meta, _, n_ref, _ = sm.get(0, want_lines=False)
+        out["submap_match_and_add_scan"] = {"value": S / (ms_s * 1e-3), "ms_per_launch_pair": ms_s, "managers": S,
+                                            "reference_submap_lines_mean": float(n_ref.mean()), "pairs_matched": int(d_nm.sum().item()),
+                                            "note": "laser_manager::match_with_ref + add_scan per frame, sub-maps resident on the device (lvio2d_submap_*); "
+                                                    "no CPU port timed (the host mirror is Python)"}
+        sm.close()
     if cpu:
         import oracle_lib as O
 
