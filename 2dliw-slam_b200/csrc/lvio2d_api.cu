@@ -92,6 +92,7 @@ struct lvio2d_ctx {
     DevBuf b_ln[14];   // lvio2d_extract_lines: inputs / workspace / outputs
     DevBuf b_sp[7];    // lvio2d_scan_to_points
     DevBuf b_ml[16];   // lvio2d_match_lines
+    int32_t* match_bbox = nullptr;   // set by lvio2d_submap_match around its call: the sub-map's own boxes of scan 1's lines
     DevBuf b_pg[2];    // lvio2d_pose_graph_solve: int arena, double arena
     PinnedVec<double> h_pg;   // its per-iteration read-back (scalars + flags)
     double* ext_reduce = nullptr; int64_t ext_reduce_count = 0;
@@ -1208,6 +1209,7 @@ int lvio2d_match_lines(lvio2d_ctx* ctx, const lvio2d_line_params* lp, int32_t n_
     a.w = (int)(lp->w_laser_each_scan / lp->laser_resolution + 1);
     a.h = (int)(lp->h_laser_each_scan / lp->laser_resolution + 1);
     a.cells = B[0].as<int32_t>(); a.diss = B[1].as<double>(); a.prov = B[2].as<int32_t>(); a.bbox = B[15].as<int32_t>();
+    if (ctx->match_bbox) { a.bbox = ctx->match_bbox; a.bbox_ready = 1; }
     if (on_device) {
         a.point_offset1 = point_offset1; a.point_count1 = point_count1; a.points1 = reinterpret_cast<const double2*>(points1);
         a.n_lines1 = n_lines1; a.lines1 = reinterpret_cast<const double4*>(lines1); a.index_range1 = index_range1;
@@ -1253,7 +1255,7 @@ struct lvio2d_submap {
     int32_t n_managers = 0, line_cap = 0, n_accumulation = 0;
     lvio2d_line_params lp{};
     double filter_p = 0, filter_q = 0;
-    DevBuf meta, sub_pose, last_pose, sub_n, sub_lines;   // state
+    DevBuf meta, sub_pose, last_pose, sub_n, sub_lines, sub_bbox;   // state
     DevBuf in_n, in_lines, in_pose;                       // staging of host scans
 };
 
@@ -1263,6 +1265,8 @@ static int submap_zero(lvio2d_submap* sm) {
     CK(cudaMemsetAsync(sm->sub_pose.p, 0, sm->sub_pose.cap, ctx->stream));
     CK(cudaMemsetAsync(sm->last_pose.p, 0, sm->last_pose.cap, ctx->stream));
     CK(cudaMemsetAsync(sm->sub_n.p, 0, sm->sub_n.cap, ctx->stream));
+    CK(cudaMemsetAsync(sm->sub_lines.p, 0, sm->sub_lines.cap, ctx->stream));   // (slots beyond n_lines read as zero in lvio2d_submap_get)
+    CK(cudaMemsetAsync(sm->sub_bbox.p, 0, sm->sub_bbox.cap, ctx->stream));
     return LVIO2D_OK;
 }
 
@@ -1278,7 +1282,8 @@ int lvio2d_submap_create(lvio2d_ctx* ctx, int32_t n_managers, int32_t line_cap, 
     sm->lp = *lp; sm->filter_p = ref_motion_filter_p; sm->filter_q = ref_motion_filter_q;
     const size_t M = (size_t)n_managers;
     const bool ok = sm->meta.ensure(M * 4 * sizeof(int32_t)) && sm->sub_pose.ensure(2 * M * 6 * sizeof(double)) && sm->last_pose.ensure(M * 6 * sizeof(double)) &&
-                    sm->sub_n.ensure(2 * M * sizeof(int32_t)) && sm->sub_lines.ensure(2 * M * (size_t)line_cap * sizeof(double4));
+                    sm->sub_n.ensure(2 * M * sizeof(int32_t)) && sm->sub_lines.ensure(2 * M * (size_t)line_cap * sizeof(double4)) &&
+                    sm->sub_bbox.ensure(2 * M * (size_t)line_cap * sizeof(int4));
     if (!ok) { lvio2d_submap_destroy(sm); return fail(ctx, LVIO2D_ERR_ALLOC, "cudaMalloc(submap)"); }
     const int rc = submap_zero(sm);
     if (rc != LVIO2D_OK) { lvio2d_submap_destroy(sm); return rc; }
@@ -1290,7 +1295,7 @@ void lvio2d_submap_destroy(lvio2d_submap* sm) {
     if (!sm) return;
     cudaSetDevice(sm->device);
     cudaDeviceSynchronize();   // (not the context's stream: the context may have been destroyed first)
-    DevBuf* all[] = {&sm->meta, &sm->sub_pose, &sm->last_pose, &sm->sub_n, &sm->sub_lines, &sm->in_n, &sm->in_lines, &sm->in_pose};
+    DevBuf* all[] = {&sm->meta, &sm->sub_pose, &sm->last_pose, &sm->sub_n, &sm->sub_lines, &sm->sub_bbox, &sm->in_n, &sm->in_lines, &sm->in_pose};
     for (DevBuf* b : all) b->release();
     delete sm;
 }
@@ -1317,7 +1322,7 @@ int lvio2d_submap_add_scan(lvio2d_submap* sm, int32_t max_lines, const int32_t* 
     a.w = (int)(sm->lp.w_laser_each_scan / sm->lp.laser_resolution + 1);
     a.h = (int)(sm->lp.h_laser_each_scan / sm->lp.laser_resolution + 1);
     a.meta = sm->meta.as<int32_t>(); a.sub_pose = sm->sub_pose.as<double>(); a.last_pose = sm->last_pose.as<double>();
-    a.sub_n = sm->sub_n.as<int32_t>(); a.sub_lines = sm->sub_lines.as<double4>();
+    a.sub_n = sm->sub_n.as<int32_t>(); a.sub_lines = sm->sub_lines.as<double4>(); a.sub_bbox = sm->sub_bbox.as<int4>();
     if (on_device) {
         a.n_lines = n_lines; a.lines = reinterpret_cast<const double4*>(lines); a.pose = pose;
     } else {
@@ -1374,9 +1379,11 @@ int lvio2d_submap_match(lvio2d_submap* sm, int32_t kk, int32_t max_lines2, const
     const size_t P = (size_t)sm->n_managers;
     const double4* sub_lines = sm->sub_lines.as<double4>();
     if (on_device) {   // everything is in device memory already: the sampled flavour of lvio2d_match_lines on the resident arrays
+        ctx->match_bbox = sm->sub_bbox.as<int32_t>();
         const int rc = lvio2d_match_lines(ctx, &sm->lp, sm->n_managers, kk, nullptr, nullptr, nullptr, sm->line_cap, sm->sub_n.as<int32_t>(),
                                           sm->sub_lines.as<double>(), nullptr, max_lines2, n_lines2, lines2, sm->sub_pose.as<double>(), pose2, n_match,
                                           match, 1);
+        ctx->match_bbox = nullptr;
         if (rc != LVIO2D_OK) return rc;
         if (matched_lines1 || ref_pose) {
             submap_gather_kernel<<<sm->n_managers, 128, 0, ctx->stream>>>(sm->n_managers, sm->line_cap, max_lines2, n_match, match, sub_lines,
@@ -1396,9 +1403,11 @@ int lvio2d_submap_match(lvio2d_submap* sm, int32_t kk, int32_t max_lines2, const
     CK(cudaMemcpyAsync(B[10].p, lines2, P * max_lines2 * sizeof(double4), cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(B[12].p, pose2, P * 6 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemsetAsync(B[14].p, 0, P * max_lines2 * 2 * sizeof(int32_t), ctx->stream));
+    ctx->match_bbox = sm->sub_bbox.as<int32_t>();
     const int rc = lvio2d_match_lines(ctx, &sm->lp, sm->n_managers, kk, nullptr, nullptr, nullptr, sm->line_cap, sm->sub_n.as<int32_t>(),
                                       sm->sub_lines.as<double>(), nullptr, max_lines2, B[9].as<int32_t>(), B[10].as<double>(), sm->sub_pose.as<double>(),
                                       B[12].as<double>(), B[13].as<int32_t>(), B[14].as<int32_t>(), 1);
+    ctx->match_bbox = nullptr;
     if (rc != LVIO2D_OK) return rc;
     if (matched_lines1 || ref_pose) {
         submap_gather_kernel<<<sm->n_managers, 128, 0, ctx->stream>>>(sm->n_managers, sm->line_cap, max_lines2, B[13].as<int32_t>(), B[14].as<int32_t>(), sub_lines,

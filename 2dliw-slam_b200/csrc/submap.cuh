@@ -31,6 +31,7 @@ struct SubmapArgs {
     double* last_pose;    // [M][6]: the pose behind last_add_tf
     int32_t* sub_n;       // [2][M]
     double4* sub_lines;   // [2][M][line_cap]
+    int4* sub_bbox;       // [2][M][line_cap]: (rmin, rmax, cmin, cmax) of the grid cells the line's 0.05 m samples cover
     // one scan per manager
     const int32_t* n_lines;   // [M]; a negative count skips the manager (no scan for it in this call)
     const double4* lines;     // [M][max_lines]
@@ -59,11 +60,12 @@ __device__ __forceinline__ IsoD iso_mul(const IsoD& A, const IsoD& B) {
 
 // scan::add_line(p1, p2, false) for the `n` lines of the scan, taken through T (or as they are), appended to dst in
 // scan order.  Returns the new line count; lines beyond line_cap are counted, not stored.
-__device__ __forceinline__ int submap_append(const SubmapArgs& a, double4* dst, int count, const double4* L, int n, const IsoD* T, int lane) {
+__device__ __forceinline__ int submap_append(const SubmapArgs& a, double4* dst, int4* dbox, int count, const double4* L, int n, const IsoD* T, int lane) {
     for (int base = 0; base < n; base += 32) {
         const int i = base + lane;
         bool keep = false;
         double4 o = make_double4(0, 0, 0, 0);
+        int rmin = 0x7fffffff, rmax = -1, cmin = 0x7fffffff, cmax = -1;
         if (i < n) {
             const double4 l = L[i];
             V3<double> p1 = v3<double>(l.x, l.y, 0.0), p2 = v3<double>(l.z, l.w, 0.0);
@@ -73,10 +75,15 @@ __device__ __forceinline__ int submap_append(const SubmapArgs& a, double4* dst, 
             const double len = sqrt(dx * dx + dy * dy);
             if (!(zmax > a.line_max_dis) && !(len < a.line_min_len)) {
                 const double ux = dx / len, uy = dy / len;
-                for (double tr = 0.0; tr <= len && !keep; tr += 0.05) {
+                // the same walk lvio2d_match_lines takes over the line (sampled flavour): its box is kept with the line, so a
+                // match against the sub-map does not walk ~800 lines again for every scan
+                for (double tr = 0.0; tr <= len; tr += 0.05) {
                     const double qx = p1.x + ux * tr, qy = p1.y + uy * tr;
                     const int c = (int)(qx / a.resolution + a.w / 2), r = (int)(qy / a.resolution + a.h / 2);
-                    keep = r >= 0 && r < a.h && c >= 0 && c < a.w;
+                    if (r >= 0 && r < a.h && c >= 0 && c < a.w) {
+                        keep = true;
+                        rmin = min(rmin, r); rmax = max(rmax, r); cmin = min(cmin, c); cmax = max(cmax, c);
+                    }
                 }
                 o = make_double4(p1.x, p1.y, p2.x, p2.y);
             }
@@ -84,7 +91,7 @@ __device__ __forceinline__ int submap_append(const SubmapArgs& a, double4* dst, 
         const unsigned m = __ballot_sync(0xffffffffu, keep);
         if (keep) {
             const int slot = count + __popc(m & ((1u << lane) - 1u));
-            if (slot < a.line_cap) dst[slot] = o;
+            if (slot < a.line_cap) { dst[slot] = o; dbox[slot] = make_int4(rmin, rmax, cmin, cmax); }
         }
         count += __popc(m);
     }
@@ -106,6 +113,8 @@ __global__ void __launch_bounds__(128) submap_add_scan_kernel(SubmapArgs a) {
     double* last = a.last_pose + 6 * (size_t)m;
     double4* ref_lines = a.sub_lines + (size_t)m * a.line_cap;
     double4* spawn_lines = a.sub_lines + ((size_t)M + m) * a.line_cap;
+    int4* ref_box = a.sub_bbox + (size_t)m * a.line_cap;
+    int4* spawn_box = a.sub_bbox + ((size_t)M + m) * a.line_cap;
     int has_ref = meta[0], has_spawn = meta[1], count = meta[2];
     int n_ref = a.sub_n[m], n_spawn = a.sub_n[M + m];
     __syncwarp();   // every lane has read the state before lane 0 rewrites it
@@ -122,7 +131,7 @@ __global__ void __launch_bounds__(128) submap_add_scan_kernel(SubmapArgs a) {
     if (!has_ref) {
         set_pose(ref_pose);
         set_pose(last);
-        n_ref = submap_append(a, ref_lines, 0, L, n, nullptr, lane);
+        n_ref = submap_append(a, ref_lines, ref_box, 0, L, n, nullptr, lane);
         has_ref = 1; count = 1;
         commit(1);
         return;
@@ -136,17 +145,17 @@ __global__ void __launch_bounds__(128) submap_add_scan_kernel(SubmapArgs a) {
     const IsoD Tli = iso_inv(Til);
     {
         const IsoD T = iso_mul(iso_mul(Tli, iso_mul(iso_inv(iso_from_pose(ref_pose)), Tc)), Til);
-        n_ref = submap_append(a, ref_lines, n_ref, L, n, &T, lane);
+        n_ref = submap_append(a, ref_lines, ref_box, n_ref, L, n, &T, lane);
     }
     if (has_spawn) {
         const IsoD T = iso_mul(iso_mul(Tli, iso_mul(iso_inv(iso_from_pose(spawn_pose)), Tc)), Til);
-        n_spawn = submap_append(a, spawn_lines, n_spawn, L, n, &T, lane);
+        n_spawn = submap_append(a, spawn_lines, spawn_box, n_spawn, L, n, &T, lane);
     }
     ++count;
     if (!has_spawn && count == a.n_accumulation / 2) {
         __syncwarp();
         set_pose(spawn_pose);
-        n_spawn = submap_append(a, spawn_lines, 0, L, n, nullptr, lane);
+        n_spawn = submap_append(a, spawn_lines, spawn_box, 0, L, n, nullptr, lane);
         has_spawn = 1;
     }
     if (count == a.n_accumulation) {
@@ -154,13 +163,13 @@ __global__ void __launch_bounds__(128) submap_add_scan_kernel(SubmapArgs a) {
         // manager without a reference: the next scan founds it again, as the reference's null pointer does)
         __syncwarp();
         const int stored = min(n_spawn, a.line_cap);
-        for (int i = lane; i < stored; i += 32) ref_lines[i] = spawn_lines[i];
+        for (int i = lane; i < stored; i += 32) { ref_lines[i] = spawn_lines[i]; ref_box[i] = spawn_box[i]; }
         if (lane < 6) ref_pose[lane] = spawn_pose[lane];
         has_ref = has_spawn;
         n_ref = has_spawn ? n_spawn : 0;
         __syncwarp();
         set_pose(spawn_pose);
-        n_spawn = submap_append(a, spawn_lines, 0, L, n, nullptr, lane);
+        n_spawn = submap_append(a, spawn_lines, spawn_box, 0, L, n, nullptr, lane);
         has_spawn = 1;
         count = a.n_accumulation / 2;
     }

@@ -639,7 +639,7 @@ def front_end_rates(P, torch, device, n_scans=4096, reps=10, cpu=True):
     tiled) with CUDA events on the context's stream, next to its CPU oracle on one core:
       scan_to_points  convert::laser_to_point_times + sensor::laser::correct  -> lvio2d_scan_to_points
       scan_lines      laser_manager::spawn_scan                                -> lvio2d_extract_lines
-      match_lines     laser_manager::do_match (every scan against itself at the identity relative pose) -> lvio2d_match_lines
+      match_lines     laser_manager::do_match (every scan against itself seen from a pose 3.6 cm / 0.01 rad away) -> lvio2d_match_lines
     All three are fp64-ALU / latency-bound (sqrt, div, sincos, acos per point; sequential merge per segment): their
     algorithmic bytes are reported against the HBM peak only to show how far below that roof they sit."""
     import lvio2d_b200 as L
@@ -667,6 +667,10 @@ def front_end_rates(P, torch, device, n_scans=4096, reps=10, cpu=True):
         d_abc = torch.zeros(S * ML * 3, dtype=torch.float64, device=device)
         d_rng = torch.zeros(S * ML * 2, dtype=torch.int32, device=device)
         d_pose = torch.zeros(S * 6, dtype=torch.float64, device=device)
+        # scan 2 = the same scan seen from a pose 3.6 cm and 0.01 rad away (an exact self-match is degenerate: every
+        # direction cosine is 1 up to rounding, and acos of 1 + 1 ulp is NaN — the pair count would depend on FMA contraction)
+        pose2_row = np.array([0.03, 0.02, 0.0, 0.0, 0.0, 0.01])
+        d_poseb = torch.from_numpy(np.tile(pose2_row, S)).to(device)
         d_nm = torch.zeros(S, dtype=torch.int32, device=device)
         d_m = torch.zeros(S * ML * 2, dtype=torch.int32, device=device)
         vp = C.c_void_p
@@ -684,7 +688,7 @@ def front_end_rates(P, torch, device, n_scans=4096, reps=10, cpu=True):
                 C.cast(vp(d_pts.data_ptr()), abi.c_double_p), ML, C.cast(vp(d_n.data_ptr()), abi.c_int32_p),
                 C.cast(vp(d_lines.data_ptr()), abi.c_double_p), C.cast(vp(d_rng.data_ptr()), abi.c_int32_p), ML,
                 C.cast(vp(d_n.data_ptr()), abi.c_int32_p), C.cast(vp(d_lines.data_ptr()), abi.c_double_p),
-                C.cast(vp(d_pose.data_ptr()), abi.c_double_p), C.cast(vp(d_pose.data_ptr()), abi.c_double_p),
+                C.cast(vp(d_pose.data_ptr()), abi.c_double_p), C.cast(vp(d_poseb.data_ptr()), abi.c_double_p),
                 C.cast(vp(d_nm.data_ptr()), abi.c_int32_p), C.cast(vp(d_m.data_ptr()), abi.c_int32_p), 1), "lvio2d_match_lines")
 
         def timed(fn):
@@ -729,21 +733,27 @@ def front_end_rates(P, torch, device, n_scans=4096, reps=10, cpu=True):
             sm.add_scan_device(ML, d_n.data_ptr(), d_lines.data_ptr(), d_pose2.data_ptr())
 
         for k in range(20):
+            c.sync()
             step_pose(k)
+            torch.cuda.synchronize(device)     # the pose copy runs on torch's stream, the kernels on the context's
             k_submap()
         c.sync()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        ms_s = 0.0
+        e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+        ms_s = ms_match = 0.0
         for k in range(20, 20 + reps):
+            c.sync()
             step_pose(k)
             torch.cuda.synchronize(device)
             e0.record(stream)
-            k_submap()
+            sm.match_device(ML, d_n.data_ptr(), d_lines.data_ptr(), d_pose2.data_ptr(), d_nm.data_ptr(), d_m.data_ptr())
             e1.record(stream)
+            sm.add_scan_device(ML, d_n.data_ptr(), d_lines.data_ptr(), d_pose2.data_ptr())
+            e2.record(stream)
             c.sync()
-            ms_s += e0.elapsed_time(e1) / reps
+            ms_s += e0.elapsed_time(e2) / reps
+            ms_match += e0.elapsed_time(e1) / reps
         meta, _, n_ref, _ = sm.get(0, want_lines=False)
-        out["submap_match_and_add_scan"] = {"value": S / (ms_s * 1e-3), "ms_per_launch_pair": ms_s, "managers": S,
+        out["submap_match_and_add_scan"] = {"value": S / (ms_s * 1e-3), "ms_per_launch_pair": ms_s, "ms_match": ms_match, "ms_add_scan": ms_s - ms_match, "managers": S,
                                             "reference_submap_lines_mean": float(n_ref.mean()), "pairs_matched": int(d_nm.sum().item()),
                                             "note": "laser_manager::match_with_ref + add_scan per frame, sub-maps resident on the device (lvio2d_submap_*); "
                                                     "no CPU port timed (the host mirror is Python)"}
@@ -768,7 +778,7 @@ def front_end_rates(P, torch, device, n_scans=4096, reps=10, cpu=True):
             "unit": "scans/s", "cores": 1, "kind": "port", "sample": "the 64 distinct scans, repeated for 1.5 s per step",
             "scan_to_points": cpu_rate(lambda: O.scan_to_points(rg1, hd1, True)),
             "scan_lines": cpu_rate(lambda: O.extract_lines(lp, off1, pts.reshape(-1, 2), max_lines=ML, point_count=cnt, point_z=pz.reshape(-1))),
-            "match_lines": cpu_rate(lambda: O.match_lines(P, lp, n, lines, n, lines, pose, pose, 0, off1, pts.reshape(-1, 2), rng, cnt)),
+            "match_lines": cpu_rate(lambda: O.match_lines(P, lp, n, lines, n, lines, pose, pose + np.array([0.03, 0.02, 0.0, 0.0, 0.0, 0.01]), 0, off1, pts.reshape(-1, 2), rng, cnt)),
         }
     return out
 
