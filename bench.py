@@ -726,6 +726,7 @@ def front_end_rates(P, torch, device, n_scans=4096, reps=10, cpu=True):
 
         def step_pose(k):
             poses[:, 0] = 0.02 * k
+            poses[:, 5] = 0.003 * k      # (a pure translation would make every direction cosine 1 +- 1 ulp: degenerate, see above)
             d_pose2.copy_(torch.from_numpy(poses.reshape(-1)))
 
         def k_submap():

@@ -28,6 +28,7 @@ with Context(L.corridor_params()) as c:
     stream = torch.cuda.ExternalStream(c.stream, device=dev)
     for k in range(warm + 3):
         poses[:, 0] = 0.02 * k
+        poses[:, 5] = 0.003 * k
         d_pose = torch.from_numpy(poses.reshape(-1).copy()).to(dev)
         torch.cuda.synchronize(dev)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
