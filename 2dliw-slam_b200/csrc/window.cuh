@@ -742,7 +742,15 @@ template <int NT> __device__ __forceinline__ void copy_blk(double* dst, const do
 // laser block + rhs [n][15]
 __host__ __device__ inline size_t window_smem_doubles(int n, bool arrow) { return (arrow ? 7 : 4) * kBlk + 16 + 48 + 32 + 16 + (size_t)n * 15 + 16; }
 // the fast path: Dp | Cp | Ut | Ha | piv | slb | ssc | rolling rhs
-constexpr int kWindowFastSmem = 3 * 256 + 192 + 16 + 32 + 32 + 48;
+#ifndef LV_WINDOW_BULK
+#define LV_WINDOW_BULK 0   // 1: the raw blocks of an elimination step arrive by cp.async.bulk + mbarrier (4 bulk copies issued by one
+                           // lane) instead of ten 16-byte cp.async per lane.  Measured on the B200: see DESIGN.md section 3.3.
+#endif
+constexpr int kWindowFastSmem = 3 * 256 + 192 + 16 + 32 + 32 + 48 + (LV_WINDOW_BULK ? 2 : 0);
+__device__ __forceinline__ void bulk_g2s(double* smem_dst, const double* gsrc, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc), "r"(bytes), "r"(bar) : "memory");
+}
 
 // ---------------------------------------------------------------------------------------------------
 // =====================================================================================================
@@ -1460,6 +1468,13 @@ __device__ void window_step(const WindowArgs& a, int w, int lane, double* ws, co
             double* facf = a.fac + (size_t)w * n * kTB;
             // element (r, c) this lane owns in pass q of a block: tile q >> 1, row 4 (q & 1) + (lane >> 3), column lane & 7
             const int lr = lane >> 3, lc = lane & 7;
+#if LV_WINDOW_BULK
+            const uint32_t bar = (uint32_t)__cvta_generic_to_shared(ws + kWindowFastSmem - 2);
+            uint32_t bar_phase = 0;
+            if (lane == 0) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(bar) : "memory");
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+#endif
             {   // D_{n-1}, scaled and damped
 #pragma unroll
                 for (int q = 0; q < 8; ++q) {
@@ -1481,6 +1496,17 @@ __device__ void window_step(const WindowArgs& a, int w, int lane, double* ws, co
                 {
                     const double* it_i = itm + (size_t)i * kItem;
                     const double* it_p = itm + (size_t)(i - 1) * kItem + kItemHbb;
+#if LV_WINDOW_BULK
+                    __syncwarp();
+                    if (lane == 0) {
+                        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(2048u + 1536u + 1024u + 512u) : "memory");
+                        bulk_g2s(Ut, it_i + kItemHab, 2048u, bar);
+                        bulk_g2s(Ha, it_i, 1536u, bar);
+                        bulk_g2s(Cp, it_p, 1024u, bar);
+                        bulk_g2s(Cp + 192, it_p + 128, 512u, bar);
+                    }
+#else
 #pragma unroll
                     for (int k = 0; k < 4; ++k) cp_async16(Ut + 2 * (lane + 32 * k), it_i + kItemHab + 2 * (lane + 32 * k));
 #pragma unroll
@@ -1488,6 +1514,7 @@ __device__ void window_step(const WindowArgs& a, int w, int lane, double* ws, co
                         cp_async16(Ha + (k << 6) + 2 * lane, it_i + (k << 6) + 2 * lane);
                         cp_async16(Cp + ((k == 2 ? 3 : k) << 6) + 2 * lane, it_p + (k << 6) + 2 * lane);
                     }
+#endif
                     if (lane < NPAD) cp_async8(slbf + lane, lb + (i - 1) * NPAD + lane);
                     if (lane < 30) cp_async8(sscf + lane, scw + (i - 1) * 15 + lane);
                     if (lane < 15) cp_async8(bprv + lane, sb + 15 * (i - 1) + lane);
@@ -1497,6 +1524,15 @@ __device__ void window_step(const WindowArgs& a, int w, int lane, double* ws, co
                 __syncwarp();
                 const bool inv_ok = spd_inverse15_t(Dp, pivf, lane);
                 cp_async_wait_all();
+#if LV_WINDOW_BULK
+                {
+                    uint32_t done = 0;
+                    while (!done)
+                        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                                     : "=r"(done) : "r"(bar), "r"(bar_phase) : "memory");
+                    bar_phase ^= 1u;
+                }
+#endif
                 __syncwarp();
                 if (!inv_ok) { ok = false; break; }
                 // U = S_{i-1} H(i-1, i) S_i;  D_{i-1} = S (hbb + haa + laser) S + damping.  Read everything, then write in place
