@@ -1237,7 +1237,9 @@ int lvio2d_match_lines(lvio2d_ctx* ctx, const lvio2d_line_params* lp, int32_t n_
         a.n_match = B[13].as<int32_t>(); a.match = B[14].as<int32_t>();
     }
     const int wpc = 4;
-    match_lines_kernel<<<(n_pairs + wpc - 1) / wpc, wpc * 32, 0, ctx->stream>>>(a);
+    // few pairs: the four warps of a CTA share one pair (a quarter of the latency); many pairs: one warp each
+    if (n_pairs <= 2 * ctx->sm_count) match_lines_kernel<4><<<n_pairs, wpc * 32, 0, ctx->stream>>>(a);
+    else match_lines_kernel<1><<<(n_pairs + wpc - 1) / wpc, wpc * 32, 0, ctx->stream>>>(a);
     ctx->launches += 1;
     CK(cudaGetLastError());
     if (!on_device) {

@@ -417,12 +417,20 @@ __device__ __forceinline__ double match_dis_from_line(const V3<double>& p, doubl
     return sqrt(ex * ex + ey * ey + rz * rz);
 }
 
+// WPP = warps per pair: 1 (one warp per pair, four pairs per CTA: the batched shape) or 4 (the CTA shares one pair: its warps
+// take the lines of scan 2 round robin and warp 0 gathers the results in order — the same pairs, a quarter of the latency,
+// for the few-robots case where one warp walking a 1600-line sub-map 47 times is the whole critical path)
+template <int WPP>
 __global__ void __launch_bounds__(128) match_lines_kernel(MatchLinesArgs a) {
     __shared__ int queue_all[4][64];
     int* queue = queue_all[threadIdx.x >> 5];
     const int lane = threadIdx.x & 31;
-    const int p = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int wid = threadIdx.x >> 5;
+    const int p = WPP == 1 ? blockIdx.x * (blockDim.x >> 5) + wid : blockIdx.x;
     if (p >= a.n_pairs) return;
+    const int tl = WPP == 1 ? lane : threadIdx.x;          // thread index within the group that owns the pair
+    constexpr int TG = 32 * WPP;
+    auto group_sync = [&]() { if (WPP == 1) __syncwarp(); else __syncthreads(); };
     const int n1 = min(a.n_lines1[p], a.max_lines1), n2 = min(a.n_lines2[p], a.max_lines2);
     const double4* L1 = a.lines1 + (size_t)p * a.max_lines1;
     const double4* L2 = a.lines2 + (size_t)p * a.max_lines2;
@@ -448,13 +456,13 @@ __global__ void __launch_bounds__(128) match_lines_kernel(MatchLinesArgs a) {
         q0 = a.point_offset1[p];
         const int np = a.point_count1 ? a.point_count1[p] : (int)(a.point_offset1[p + 1] - q0);
         np1 = np;
-        for (int i = lane; i < np; i += 32) { const double2 q = a.points1[q0 + i]; a.cells[q0 + i] = match_cell(a, q.x, q.y); }
-        __syncwarp();
+        for (int i = tl; i < np; i += TG) { const double2 q = a.points1[q0 + i]; a.cells[q0 + i] = match_cell(a, q.x, q.y); }
+        group_sync();
     }
     // bounding box of every scan-1 line's cells: a line whose box misses the neighbourhood cannot cover any of its cells,
     // which prunes almost every (line of scan 2, line of scan 1) pair with four comparisons
     int32_t* bb = a.bbox + (size_t)p * a.max_lines1 * 4;
-    for (int j = lane; j < (a.bbox_ready ? 0 : n1); j += 32) {
+    for (int j = tl; j < (a.bbox_ready ? 0 : n1); j += TG) {
         int rmin = 0x7fffffff, rmax = -1, cmin = 0x7fffffff, cmax = -1;
         auto grow = [&](int cell) {
             if (cell < 0) return;
@@ -472,10 +480,10 @@ __global__ void __launch_bounds__(128) match_lines_kernel(MatchLinesArgs a) {
         }
         bb[4 * j] = rmin; bb[4 * j + 1] = rmax; bb[4 * j + 2] = cmin; bb[4 * j + 3] = cmax;
     }
-    __syncwarp();
+    group_sync();
     const int aa = 1 + a.kk, side = 2 * aa + 1;
     int count = 0;
-    for (int i = 0; i < n2; ++i) {
+    for (int i = (WPP == 1 ? 0 : wid); i < n2; i += WPP) {
         const double4 l2 = L2[i];
         const V3<double> tm = tf((l2.x + l2.z) / 2.0, (l2.y + l2.w) / 2.0);
         const int c = (int)(tm.x / a.resolution + a.w / 2), r = (int)(tm.y / a.resolution + a.h / 2);
@@ -568,11 +576,36 @@ __global__ void __launch_bounds__(128) match_lines_kernel(MatchLinesArgs a) {
             const int oc = __shfl_xor_sync(0xffffffffu, best_cell, d), oj = __shfl_xor_sync(0xffffffffu, best_j, d);
             if (oa < best_angle || (oa == best_angle && (oc < best_cell || (oc == best_cell && oj < best_j)))) { best_angle = oa; best_cell = oc; best_j = oj; }
         }
-        if (best_j == 0x7fffffff) continue;                     // no candidate (or only NaN angles)
-        if (best_angle / kPi * 180.0 > 10.0) continue;
-        diss[count] = 0.5 * (match_dis_from_line(e1, L1[best_j]) + match_dis_from_line(e2, L1[best_j]));   // same value on every lane
-        if (lane == 0) { prov[2 * count] = best_j; prov[2 * count + 1] = i; }
-        ++count;
+        const bool matched = best_j != 0x7fffffff /* a candidate, and not only NaN angles */ && !(best_angle / kPi * 180.0 > 10.0);
+        if (WPP == 1) {
+            if (!matched) continue;
+            diss[count] = 0.5 * (match_dis_from_line(e1, L1[best_j]) + match_dis_from_line(e2, L1[best_j]));   // same value on every lane
+            if (lane == 0) { prov[2 * count] = best_j; prov[2 * count + 1] = i; }
+            ++count;
+        } else if (lane == 0) {
+            // slot i of the workspace; warp 0 compacts the slots in order below
+            prov[2 * i] = matched ? best_j : -1;
+            prov[2 * i + 1] = i;
+            if (matched) diss[i] = 0.5 * (match_dis_from_line(e1, L1[best_j]) + match_dis_from_line(e2, L1[best_j]));
+        }
+    }
+    if (WPP > 1) {
+        __syncthreads();
+        if (wid != 0) return;
+        for (int base = 0; base < n2; base += 32) {       // (slot o <= slot k: a chunk is read completely before it is written)
+            const int k = base + lane;
+            const bool has = k < n2 && prov[2 * k] >= 0;
+            const int bj = k < n2 ? prov[2 * k] : 0;
+            const double dk = has ? diss[k] : 0.0;
+            const unsigned m = __ballot_sync(0xffffffffu, has);
+            __syncwarp();
+            if (has) {
+                const int o = count + __popc(m & ((1u << lane) - 1u));
+                prov[2 * o] = bj; prov[2 * o + 1] = k; diss[o] = dk;
+            }
+            count += __popc(m);
+            __syncwarp();
+        }
     }
     __syncwarp();
     // mean end-point distance (summed in the reference's order), then the 1.2 x filter
