@@ -25,7 +25,7 @@ def rel(a, b):
 
 
 def test_golden_files_present():
-    assert sorted(os.path.basename(f) for f in glob.glob(os.path.join(GOLD, "*.npz"))) == sorted([w + ".npz" for w in WINDOWS] + ["factors.npz", "lines_scans.npz", "pose_graph.npz"])
+    assert sorted(os.path.basename(f) for f in glob.glob(os.path.join(GOLD, "*.npz"))) == sorted([w + ".npz" for w in WINDOWS] + ["factors.npz", "lines_scans.npz", "pose_graph.npz", "ref_text.npz"])
 
 
 @pytest.mark.parametrize("name", WINDOWS)
